@@ -1,0 +1,84 @@
+"""ctypes binding of libdfnet_b200.so (the C ABI declared in include/dfnet_b200.h).
+
+There is no fallback: if the shared library is missing the import fails loudly, and every
+compute entry point refuses to run without a CUDA device.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdfnet_b200.so")
+
+# every symbol include/dfnet_b200.h declares (tests check that the library exports them all)
+SYMBOLS = [
+    "dfb_last_error", "dfb_version", "dfb_device_ok", "dfb_linspace_f32", "dfb_nerf_create", "dfb_nerf_destroy",
+    "dfb_nerf_load", "dfb_nerf_set_embeddings", "dfb_nerfw_forward", "dfb_render_workspace_bytes",
+    "dfb_render_fwd", "dfb_render_image_host", "dfb_sample_pdf", "dfb_raw2outputs", "dfb_get_rays",
+    "dfb_launch_count", "dfb_profile_enable", "dfb_profile_read",
+]
+
+MMA_FP32_SIMT, MMA_F16, MMA_BF16 = 0, 1, 2
+MMA_KINDS = {"fp32": MMA_FP32_SIMT, "f16": MMA_F16, "bf16": MMA_BF16}
+
+
+class NerfDesc(C.Structure):
+    _fields_ = [("D", C.c_int32), ("W", C.c_int32), ("skip", C.c_int32), ("L_xyz", C.c_int32), ("L_dir", C.c_int32),
+                ("a_dim", C.c_int32), ("t_dim", C.c_int32), ("hist_bin", C.c_int32), ("n_vocab", C.c_int32),
+                ("beta_min", C.c_float), ("has_fine", C.c_int32)]
+
+
+class RenderCfg(C.Structure):
+    _fields_ = [("N_samples", C.c_int32), ("N_importance", C.c_int32), ("test_time", C.c_int32),
+                ("perturb", C.c_int32), ("mma_kind", C.c_int32), ("lindisp", C.c_int32),
+                ("raw_noise_std", C.c_float), ("reserved", C.c_int32)]
+
+
+class RenderExtras(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in
+                ("rgb0", "disp0", "acc0", "z_std", "beta", "transient_sigmas", "raw", "weights_coarse", "z_vals",
+                 "z_samples", "inds", "depth")]
+
+
+class DfbError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C dfnet_b200/csrc` (there is no non-CUDA fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
+    lib.dfb_last_error.restype = C.c_char_p
+    lib.dfb_last_error.argtypes = []
+    lib.dfb_version.argtypes = []
+    lib.dfb_device_ok.argtypes = []
+    lib.dfb_launch_count.restype = i64
+    lib.dfb_launch_count.argtypes = []
+    lib.dfb_linspace_f32.argtypes = [f32, f32, i32, C.POINTER(C.c_float)]
+    lib.dfb_nerf_create.argtypes = [C.POINTER(NerfDesc), C.POINTER(vp)]
+    lib.dfb_nerf_destroy.argtypes = [vp]
+    lib.dfb_nerf_destroy.restype = None
+    lib.dfb_nerf_load.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i64), i32]
+    lib.dfb_nerf_set_embeddings.argtypes = [vp, vp, vp]
+    lib.dfb_nerfw_forward.argtypes = [vp, i32, i32, vp, i64, vp, vp]
+    lib.dfb_render_workspace_bytes.argtypes = [vp, C.POINTER(RenderCfg), i64, C.POINTER(C.c_size_t)]
+    lib.dfb_render_fwd.argtypes = [vp, C.POINTER(RenderCfg), vp, vp, i32, i32, f32, f32, f32, vp, i64, vp, vp, vp, vp,
+                                   vp, C.POINTER(RenderExtras), vp, C.c_size_t, vp]
+    lib.dfb_render_image_host.argtypes = [vp, C.POINTER(RenderCfg), vp, i32, i32, f32, f32, f32, vp, vp, vp, vp, vp,
+                                          C.c_size_t, vp]
+    lib.dfb_sample_pdf.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp, vp]
+    lib.dfb_raw2outputs.argtypes = [vp, vp, i64, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.dfb_get_rays.argtypes = [vp, i32, i32, i32, f32, vp, vp, vp]
+    lib.dfb_profile_enable.argtypes = [i32]
+    lib.dfb_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(i64)]
+    return lib
+
+
+lib = _load()
+
+
+def check(rc):
+    if rc != 0:
+        raise DfbError(f"libdfnet_b200 error {rc}: {lib.dfb_last_error().decode()}")

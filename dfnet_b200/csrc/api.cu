@@ -1,0 +1,346 @@
+// C ABI entry points for rendering (see include/dfnet_b200.h).  Orchestrates the kernels of
+// render_kernels.cu / mlp_simt.cu / mlp_tc.cu the way models/rendering.py:245-400 chains
+// render -> batchify_rays -> render_rays -> {network_query_fn, raw2outputs_NeRFW, sample_pdf}.
+#include <algorithm>
+
+#include "common.cuh"
+
+using namespace dfb;
+
+namespace {
+
+constexpr int64_t kChunkRays = 1 << 16;  // internal batchify (bounds the workspace, not a tuning knob of the ABI)
+
+struct WsLayout {
+  size_t rayrec, extra, z_c, raw_c, rb_c, w_c, z_s, z_all, raw_f, rb_f, lin, total;
+};
+
+size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+WsLayout ws_layout(const DfbNerf* n, const DfbRenderCfg* c, int64_t rays) {
+  const DfbNerfDesc& d = n->desc;
+  const int Nc = c->N_samples, Nf = c->N_importance, S = Nc + Nf, W = d.W;
+  const int n_extra = 27 + d.a_dim + d.t_dim;
+  const int Cc = c->test_time ? 1 : 4;
+  WsLayout L;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
+  L.lin = take((size_t)(Nc + std::max(Nf, 1)) * 4);
+  L.rayrec = take((size_t)rays * kRayRec * 4);
+  L.extra = take((size_t)rays * n_extra * 4);
+  L.z_c = take((size_t)rays * Nc * 4);
+  L.raw_c = take((size_t)rays * Nc * Cc * 4);
+  L.rb_c = take((size_t)rays * (W / 2) * 4);
+  L.w_c = take((size_t)rays * Nc * 4);
+  L.z_s = take((size_t)rays * std::max(Nf, 1) * 4);
+  L.z_all = take((size_t)rays * S * 4);
+  L.raw_f = take(Nf > 0 ? (size_t)rays * S * 9 * 4 : 0);
+  L.rb_f = take(Nf > 0 ? (size_t)rays * W * 4 : 0);
+  L.total = off;
+  return L;
+}
+
+int check_cfg(const DfbNerf* n, const DfbRenderCfg* c) {
+  DFB_REQUIRE(n && c, DFB_ERR_INVALID, "null handle or config");
+  DFB_REQUIRE(c->N_samples >= 4 && c->N_samples <= 1024, DFB_ERR_INVALID, "N_samples %d out of range", c->N_samples);
+  DFB_REQUIRE(c->N_importance >= 0 && c->N_importance <= 1024, DFB_ERR_INVALID, "N_importance out of range");
+  DFB_REQUIRE(c->raw_noise_std == 0.f, DFB_ERR_UNSUPPORTED,
+              "raw_noise_std != 0 needs torch.randn draws; pass 0 (render_kwargs_test) or add noise on the host");
+  DFB_REQUIRE(!(c->N_importance == 0 && c->test_time), DFB_ERR_INVALID,
+              "N_importance == 0 with test_time yields rgb_map = None in the reference (rendering.py:188-193)");
+  DFB_REQUIRE(c->N_importance == 0 || n->desc.has_fine, DFB_ERR_INVALID, "N_importance > 0 needs network_fine");
+  DFB_REQUIRE(n->net[0].loaded && (c->N_importance == 0 || n->net[1].loaded), DFB_ERR_INVALID, "parameters not loaded");
+  DFB_REQUIRE(c->N_importance == 0 || n->has_emb, DFB_ERR_INVALID, "embedding_a / embedding_t not set");
+  DFB_REQUIRE(c->mma_kind >= 0 && c->mma_kind <= 2, DFB_ERR_INVALID, "unknown mma_kind %d", c->mma_kind);
+  return DFB_OK;
+}
+
+// ---- optional per-kernel timing of the two MLP launches (bench.py roofline) ----------------
+struct ProfRec { cudaEvent_t a, b; int which; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+
+int run_mlp_inner(const DfbNerf* n, const DfbRenderCfg* c, int which, int mode, const float* rayrec, const float* z,
+                  const float* rb, int64_t rays, int S, float* raw, cudaStream_t st) {
+  if (c->mma_kind != DFB_MMA_FP32_SIMT) {
+    DFB_REQUIRE(tc_supported(n, which, mode), DFB_ERR_UNSUPPORTED,
+                "tcgen05 path supports netwidth 256 / netdepth 8 test-time networks; use DFB_MMA_FP32_SIMT");
+    return launch_mlp_tc_rays(n, which, mode, c->mma_kind, rayrec, z, rb, rays, S, raw, st);
+  }
+  return launch_mlp_simt_rays(n, which, mode, rayrec, z, rb, rays, S, raw, st);
+}
+
+int run_mlp(const DfbNerf* n, const DfbRenderCfg* c, int which, int mode, const float* rayrec, const float* z,
+            const float* rb, int64_t rays, int S, float* raw, cudaStream_t st) {
+  if (!g_prof_on) return run_mlp_inner(n, c, which, mode, rayrec, z, rb, rays, S, raw, st);
+  ProfRec r;
+  r.which = which;
+  DFB_CHECK_CUDA(cudaEventCreate(&r.a));
+  DFB_CHECK_CUDA(cudaEventCreate(&r.b));
+  DFB_CHECK_CUDA(cudaEventRecord(r.a, st));
+  int rc = run_mlp_inner(n, c, which, mode, rayrec, z, rb, rays, S, raw, st);
+  DFB_CHECK_CUDA(cudaEventRecord(r.b, st));
+  g_prof.push_back(r);
+  return rc;
+}
+
+}  // namespace
+
+extern "C" int dfb_render_workspace_bytes(const DfbNerf* n, const DfbRenderCfg* c, int64_t n_rays, size_t* out) {
+  int rc = check_cfg(n, c);
+  if (rc) return rc;
+  DFB_REQUIRE(out && n_rays >= 0, DFB_ERR_INVALID, "bad arguments");
+  *out = ws_layout(n, c, std::min<int64_t>(std::max<int64_t>(n_rays, 1), kChunkRays)).total;
+  return DFB_OK;
+}
+
+extern "C" int dfb_render_fwd(DfbNerf* n, const DfbRenderCfg* c, const float* rays, const float* c2w, int H, int W,
+                              float focal, float near, float far, const float* hist, int64_t N, const float* t_rand,
+                              const float* u, float* rgb, float* disp, float* acc, const DfbRenderExtras* ex, void* ws,
+                              size_t ws_bytes, void* stream) {
+  int rc = check_cfg(n, c);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  DFB_REQUIRE((rays != nullptr) != (c2w != nullptr), DFB_ERR_INVALID, "pass exactly one of rays / c2w");
+  DFB_REQUIRE(!c2w || ((int64_t)H * W == N && hist), DFB_ERR_INVALID, "c2w mode needs N == H*W and a histogram");
+  DFB_REQUIRE(rgb && disp && acc, DFB_ERR_INVALID, "rgb/disp/acc outputs are required");
+  const DfbNerfDesc& d = n->desc;
+  const int Nc = c->N_samples, Nf = c->N_importance, S = Nc + Nf;
+  DFB_REQUIRE(!c->perturb || (t_rand && (Nf == 0 || u)), DFB_ERR_INVALID,
+              "perturb > 0 needs the uniform draws t_rand [N,Nc] and u [N,Nf] (rendering.py:282,36)");
+  if (N == 0) return DFB_OK;
+  DFB_CHECK_CUDA(cudaSetDevice(n->device));
+  const int64_t chunk = std::min<int64_t>(N, kChunkRays);
+  const WsLayout L = ws_layout(n, c, chunk);
+  DFB_REQUIRE(ws && ws_bytes >= L.total, DFB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", L.total, ws_bytes);
+  char* base = (char*)ws;
+  auto P = [&](size_t off) { return (float*)(base + off); };
+
+  // t_vals / u grids exactly as torch.linspace builds them (host, ATen order); cached on the handle.
+  if (n->lin_nc != Nc || n->lin_nf != Nf) {
+    std::vector<float> lin(Nc + std::max(Nf, 1));
+    dfb_linspace_f32(0.f, 1.f, Nc, lin.data());
+    if (Nf > 0) dfb_linspace_f32(0.f, 1.f, Nf, lin.data() + Nc);
+    if (n->lin_dev) cudaFree(n->lin_dev);
+    n->lin_dev = nullptr;
+    DFB_CHECK_CUDA(cudaMalloc(&n->lin_dev, lin.size() * 4));
+    DFB_CHECK_CUDA(cudaMemcpy(n->lin_dev, lin.data(), lin.size() * 4, cudaMemcpyHostToDevice));
+    n->lin_nc = Nc, n->lin_nf = Nf;
+  }
+  const float* d_lin = n->lin_dev;
+
+  const int n_extra = 27 + d.a_dim + d.t_dim;
+  const bool train = !c->test_time;
+  const int Cc = train ? 4 : 1;
+  const int hb = d.hist_bin;
+
+  for (int64_t r0 = 0; r0 < N; r0 += chunk) {
+    const int64_t nr = std::min<int64_t>(chunk, N - r0);
+    PrepArgs pa = {};
+    pa.rays = rays ? rays + r0 * (11 + hb) : nullptr;
+    pa.c2w = c2w, pa.c2w_ld = 4, pa.H = H, pa.W = W, pa.focal = focal, pa.near = near, pa.far = far, pa.hist = hist;
+    pa.hb = hb, pa.n_vocab = d.n_vocab, pa.emb_a = n->emb_a, pa.emb_t = n->emb_t;
+    pa.N = nr, pa.Nc = Nc, pa.t_vals = d_lin, pa.t_rand = c->perturb ? t_rand + r0 * Nc : nullptr;
+    pa.lindisp = c->lindisp, pa.rayrec = P(L.rayrec), pa.z = P(L.z_c);
+    const bool need_extra = train || Nf > 0;
+    pa.extra = need_extra ? P(L.extra) : nullptr;
+    pa.n_extra = n_extra, pa.a_dim = d.a_dim, pa.t_dim = d.t_dim;
+    if (need_extra && !n->has_emb) {
+      // coarse-only train mode never reads the embeddings; give the kernel zeros via hist idx 0
+      DFB_REQUIRE(Nf == 0, DFB_ERR_INVALID, "embeddings not set");
+      pa.a_dim = 0, pa.t_dim = 0, pa.n_extra = 27;
+    }
+    pa.pix0 = r0;  // c2w mode: global pixel index of this chunk's first ray
+    rc = launch_prep(pa, st);
+    if (rc) return rc;
+
+    const float* rayrec = P(L.rayrec);
+    // ---- coarse network (rendering.py:289-295) ---------------------------------------------
+    float* raw_c = P(L.raw_c);
+    float* rb_c = nullptr;
+    if (train) {
+      rb_c = P(L.rb_c);
+      rc = launch_raybias(pa.extra, pa.n_extra, nr, n->net[0], false, rb_c, n->net[0].n_dt, st);
+      if (rc) return rc;
+    }
+    rc = run_mlp(n, c, 0, train ? MLP_STATIC : MLP_SIGMA, rayrec, P(L.z_c), rb_c, nr, Nc, raw_c, st);
+    if (rc) return rc;
+    CompositeArgs ca = {};
+    ca.raw = raw_c, ca.z = P(L.z_c), ca.N = nr, ca.S = Nc, ca.C = Cc, ca.typ_fine = 0, ca.test_time = c->test_time;
+    ca.beta_min = d.beta_min;
+    ca.weights = P(L.w_c);
+    if (Nf == 0) {
+      ca.rgb = rgb + r0 * 3, ca.disp = disp + r0, ca.acc = acc + r0;
+      ca.depth = ex && ex->depth ? ex->depth + r0 : nullptr;
+    } else if (train && ex) {
+      ca.rgb = ex->rgb0 ? ex->rgb0 + r0 * 3 : nullptr;
+      ca.disp = ex->disp0 ? ex->disp0 + r0 : nullptr;
+      ca.acc = ex->acc0 ? ex->acc0 + r0 : nullptr;
+    }
+    rc = launch_composite(ca, st);
+    if (rc) return rc;
+    if (ex && ex->weights_coarse)
+      DFB_CHECK_CUDA(cudaMemcpyAsync(ex->weights_coarse + r0 * Nc, P(L.w_c), (size_t)nr * Nc * 4, cudaMemcpyDeviceToDevice, st));
+    if (Nf == 0) {
+      if (ex && ex->raw)
+        DFB_CHECK_CUDA(cudaMemcpyAsync(ex->raw + r0 * Nc * Cc, raw_c, (size_t)nr * Nc * Cc * 4, cudaMemcpyDeviceToDevice, st));
+      if (ex && ex->z_vals)
+        DFB_CHECK_CUDA(cudaMemcpyAsync(ex->z_vals + r0 * Nc, P(L.z_c), (size_t)nr * Nc * 4, cudaMemcpyDeviceToDevice, st));
+      continue;
+    }
+    // ---- hierarchical sampling (rendering.py:300-305) ----------------------------------------
+    SampleArgs sa = {};
+    sa.z_c = P(L.z_c), sa.w_c = P(L.w_c), sa.Nc = Nc, sa.N = nr, sa.Nf = Nf;
+    sa.u = c->perturb ? u + r0 * Nf : nullptr, sa.u_lin = d_lin + Nc;
+    sa.samples = ex && ex->z_samples ? ex->z_samples + r0 * Nf : nullptr;
+    sa.inds = ex && ex->inds ? ex->inds + r0 * Nf : nullptr;
+    sa.z_vals = ex && ex->z_vals ? ex->z_vals + r0 * S : P(L.z_all);
+    sa.z_std = train && ex && ex->z_std ? ex->z_std + r0 : nullptr;
+    rc = launch_sample(sa, st);
+    if (rc) return rc;
+    const float* z_all = sa.z_vals;
+    // ---- fine network (rendering.py:307-316) -------------------------------------------------
+    float* rb_f = P(L.rb_f);
+    rc = launch_raybias(pa.extra, pa.n_extra, nr, n->net[1], true, rb_f, n->net[1].n_dt, st);
+    if (rc) return rc;
+    float* raw_f = ex && ex->raw ? ex->raw + r0 * S * 9 : P(L.raw_f);
+    rc = run_mlp(n, c, 1, MLP_FULL, rayrec, z_all, rb_f, nr, S, raw_f, st);
+    if (rc) return rc;
+    CompositeArgs cf = {};
+    cf.raw = raw_f, cf.z = z_all, cf.N = nr, cf.S = S, cf.C = 9, cf.typ_fine = 1, cf.test_time = c->test_time;
+    cf.beta_min = d.beta_min;
+    cf.rgb = rgb + r0 * 3, cf.disp = disp + r0, cf.acc = acc + r0;
+    if (ex) {
+      cf.depth = ex->depth ? ex->depth + r0 : nullptr;
+      cf.beta = ex->beta ? ex->beta + r0 : nullptr;
+      cf.tsig = ex->transient_sigmas ? ex->transient_sigmas + r0 * S : nullptr;
+    }
+    rc = launch_composite(cf, st);
+    if (rc) return rc;
+  }
+  return DFB_OK;
+}
+
+extern "C" int dfb_render_image_host(DfbNerf* n, const DfbRenderCfg* c, const float* c2w_host, int H, int W, float focal,
+                                     float near, float far, const float* hist_host, float* rgb_host, float* disp_host,
+                                     float* acc_host, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_cfg(n, c);
+  if (rc) return rc;
+  DFB_REQUIRE(c2w_host && hist_host && rgb_host && disp_host && acc_host, DFB_ERR_INVALID, "null host buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  DFB_CHECK_CUDA(cudaSetDevice(n->device));
+  const int64_t N = (int64_t)H * W;
+  // the image-sized staging lives at the tail of the caller's workspace
+  size_t need = 0;
+  rc = dfb_render_workspace_bytes(n, c, N, &need);
+  if (rc) return rc;
+  const size_t stage = align256(16 * 4) + align256(n->desc.hist_bin * 4) + align256((size_t)N * 5 * 4);
+  DFB_REQUIRE(ws && ws_bytes >= need + stage, DFB_ERR_WORKSPACE,
+              "workspace too small: dfb_render_image_host needs %zu bytes (render %zu + staging %zu)", need + stage, need, stage);
+  char* tail = (char*)ws + need;
+  float* d_c2w = (float*)tail;
+  float* d_hist = (float*)(tail + align256(16 * 4));
+  float* d_out = (float*)(tail + align256(16 * 4) + align256(n->desc.hist_bin * 4));
+  DFB_CHECK_CUDA(cudaMemcpyAsync(d_c2w, c2w_host, 12 * 4, cudaMemcpyHostToDevice, st));
+  DFB_CHECK_CUDA(cudaMemcpyAsync(d_hist, hist_host, n->desc.hist_bin * 4, cudaMemcpyHostToDevice, st));
+  rc = dfb_render_fwd(n, c, nullptr, d_c2w, H, W, focal, near, far, d_hist, N, nullptr, nullptr, d_out, d_out + 3 * N,
+                      d_out + 4 * N, nullptr, ws, need, stream);
+  if (rc) return rc;
+  DFB_CHECK_CUDA(cudaMemcpyAsync(rgb_host, d_out, (size_t)N * 3 * 4, cudaMemcpyDeviceToHost, st));
+  DFB_CHECK_CUDA(cudaMemcpyAsync(disp_host, d_out + 3 * N, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+  DFB_CHECK_CUDA(cudaMemcpyAsync(acc_host, d_out + 4 * N, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+  return DFB_OK;
+}
+
+extern "C" int dfb_sample_pdf(const float* bins, const float* weights, const float* u, int64_t N, int n_bins, int Nf,
+                              float* samples, int32_t* inds, void* stream) {
+  DFB_REQUIRE(bins && weights && (samples || inds), DFB_ERR_INVALID, "null argument");
+  if (N == 0) return DFB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* d_lin = nullptr;
+  if (!u) {
+    std::vector<float> lin(Nf);
+    dfb_linspace_f32(0.f, 1.f, Nf, lin.data());
+    DFB_CHECK_CUDA(cudaMallocAsync(&d_lin, Nf * 4, st));
+    DFB_CHECK_CUDA(cudaMemcpyAsync(d_lin, lin.data(), Nf * 4, cudaMemcpyHostToDevice, st));
+    DFB_CHECK_CUDA(cudaStreamSynchronize(st));
+  }
+  SampleArgs sa = {};
+  sa.bins = bins, sa.weights = weights, sa.nb = n_bins, sa.u = u, sa.u_lin = d_lin, sa.N = N, sa.Nf = Nf;
+  sa.samples = samples, sa.inds = inds;
+  int rc = launch_sample(sa, st);
+  if (d_lin) cudaFreeAsync(d_lin, st);
+  return rc;
+}
+
+extern "C" int dfb_raw2outputs(const float* raw, const float* z_vals, int64_t N, int S, int C, int typ, int test_time,
+                               float beta_min, float* rgb, float* disp, float* acc, float* weights, float* depth,
+                               float* transient_sigmas, float* beta, void* stream) {
+  DFB_REQUIRE(raw && z_vals, DFB_ERR_INVALID, "null argument");
+  DFB_REQUIRE(C == 1 || C == 4 || C == 9, DFB_ERR_INVALID, "raw must have 1, 4 or 9 channels");
+  DFB_REQUIRE((typ == 1) == (C == 9), DFB_ERR_INVALID, "fine compositing takes 9 channels, coarse 1 or 4");
+  if (N == 0) return DFB_OK;
+  CompositeArgs ca = {};
+  ca.raw = raw, ca.z = z_vals, ca.N = N, ca.S = S, ca.C = C, ca.typ_fine = typ, ca.test_time = test_time;
+  ca.beta_min = beta_min, ca.rgb = rgb, ca.disp = disp, ca.acc = acc, ca.weights = weights, ca.depth = depth;
+  ca.tsig = transient_sigmas, ca.beta = beta;
+  return launch_composite(ca, (cudaStream_t)stream);
+}
+
+extern "C" int dfb_get_rays(const float* c2w, int row_stride, int H, int W, float focal, float* rays_o, float* rays_d,
+                            void* stream) {
+  DFB_REQUIRE(c2w && rays_o && rays_d && H > 0 && W > 0, DFB_ERR_INVALID, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t N = (int64_t)H * W;
+  float *rec = nullptr, *z = nullptr, *lin = nullptr;
+  DFB_CHECK_CUDA(cudaMallocAsync(&rec, N * kRayRec * 4, st));
+  DFB_CHECK_CUDA(cudaMallocAsync(&z, N * 4, st));
+  DFB_CHECK_CUDA(cudaMallocAsync(&lin, 4, st));
+  DFB_CHECK_CUDA(cudaMemsetAsync(lin, 0, 4, st));
+  float hist0 = 0.f;
+  float* d_hist = nullptr;
+  DFB_CHECK_CUDA(cudaMallocAsync(&d_hist, 4, st));
+  DFB_CHECK_CUDA(cudaMemcpyAsync(d_hist, &hist0, 4, cudaMemcpyHostToDevice, st));
+  PrepArgs pa = {};
+  pa.c2w = c2w, pa.c2w_ld = row_stride, pa.H = H, pa.W = W, pa.focal = focal, pa.near = 0.f, pa.far = 1.f;
+  pa.hist = d_hist, pa.hb = 1, pa.n_vocab = 1, pa.N = N, pa.Nc = 1, pa.t_vals = lin, pa.rayrec = rec, pa.z = z;
+  int rc = launch_prep(pa, st);
+  if (rc == DFB_OK) {
+    DFB_CHECK_CUDA(cudaMemcpy2DAsync(rays_o, 12, rec, kRayRec * 4, 12, N, cudaMemcpyDeviceToDevice, st));
+    DFB_CHECK_CUDA(cudaMemcpy2DAsync(rays_d, 12, rec + 3, kRayRec * 4, 12, N, cudaMemcpyDeviceToDevice, st));
+  }
+  DFB_CHECK_CUDA(cudaStreamSynchronize(st));  // hist0 is a stack variable
+  cudaFreeAsync(rec, st), cudaFreeAsync(z, st), cudaFreeAsync(lin, st), cudaFreeAsync(d_hist, st);
+  return rc;
+}
+
+extern "C" int dfb_nerfw_forward(DfbNerf* n, int which, int mode, const float* x, int64_t P, float* out, void* stream) {
+  DFB_REQUIRE(n && x && out, DFB_ERR_INVALID, "null argument");
+  DFB_REQUIRE(which == 0 || which == 1, DFB_ERR_INVALID, "which must be 0 or 1");
+  DFB_REQUIRE(mode >= 0 && mode <= 2, DFB_ERR_INVALID, "mode must be 0 (sigma), 1 (static) or 2 (full)");
+  DFB_CHECK_CUDA(cudaSetDevice(n->device));
+  return launch_mlp_simt_embedded(n, which, mode, x, P, out, (cudaStream_t)stream);
+}
+
+extern "C" int dfb_profile_enable(int on) {
+  g_prof_on = on != 0;
+  return DFB_OK;
+}
+
+extern "C" int dfb_profile_read(double* coarse_ms, double* fine_ms, int64_t* coarse_launches, int64_t* fine_launches) {
+  double ms[2] = {0, 0};
+  int64_t cnt[2] = {0, 0};
+  for (auto& r : g_prof) {
+    DFB_CHECK_CUDA(cudaEventSynchronize(r.b));
+    float t = 0.f;
+    DFB_CHECK_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    ms[r.which] += t, cnt[r.which] += 1;
+    cudaEventDestroy(r.a), cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  if (coarse_ms) *coarse_ms = ms[0];
+  if (fine_ms) *fine_ms = ms[1];
+  if (coarse_launches) *coarse_launches = cnt[0];
+  if (fine_launches) *fine_launches = cnt[1];
+  return DFB_OK;
+}

@@ -1,0 +1,167 @@
+// Internal shared declarations for libdfnet_b200 (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/dfnet_b200.h"
+
+namespace dfb {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define DFB_CHECK_CUDA(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      dfb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return DFB_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+#define DFB_REQUIRE(cond, code, ...)  \
+  do {                                \
+    if (!(cond)) {                    \
+      dfb::set_error(__VA_ARGS__);    \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+#define DFB_LAUNCH_CHECK()                                                      \
+  do {                                                                          \
+    dfb::count_launch();                                                        \
+    cudaError_t _e = cudaGetLastError();                                        \
+    if (_e != cudaSuccess) {                                                    \
+      dfb::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return DFB_ERR_CUDA;                                                      \
+    }                                                                           \
+  } while (0)
+
+constexpr int kRayRec = 12;  // o3 d3 near far vd3 pad
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// One network's parameters in kernel layouts (device memory unless noted).
+struct NetPack {
+  bool loaded = false;
+  bool fine = false;  // has appearance input + transient branch
+  int D = 0, W = 0, skip = -1, pek = 0, in_xyz = 0, in_dir = 0, a_dim = 0, t_dim = 0;
+
+  // ---- fp32 SIMT layout: every matrix transposed to [K][N] (N contiguous) ----------
+  float* blob32 = nullptr;          // single allocation, offsets below are in floats
+  size_t blob32_floats = 0;
+  std::vector<size_t> trunk_w;      // D entries; K = pek (layer 0), pek+W (skip layer: [pe|h]) or W
+  std::vector<size_t> trunk_b;
+  size_t sigma_w = 0, sigma_b = 0;  // [W], [1]
+  size_t final_w = 0, final_b = 0;  // [W][W], [W]
+  size_t dt_w = 0;                  // [W][Ndt]: dir_encoding[:, :W] (cols 0..W/2) | transient_encoding.0[:, :W]
+  int n_dt = 0;                     // W/2 (static only) or W (fine)
+  size_t dirx_w = 0, dirx_b = 0;    // ray-constant part of dir_encoding: [in_dir+a_dim][W/2], bias [W/2]
+  size_t tx_w = 0, tx_b = 0;        // ray-constant part of transient_encoding.0: [t_dim][W/2], bias [W/2]
+  size_t t_w[3] = {0, 0, 0}, t_b[3] = {0, 0, 0};  // transient_encoding.{2,4,6}: [W/2][W/2]
+  size_t rgb_w = 0, rgb_b = 0;      // static_rgb [3][W/2] (row-major, as in torch), [3]
+  size_t tsig_w = 0, tsig_b = 0;    // [W/2], [1]
+  size_t trgb_w = 0, trgb_b = 0;    // [3][W/2], [3]
+  size_t tbeta_w = 0, tbeta_b = 0;  // [W/2], [1]
+
+  // ---- tcgen05 layout (W == 256 only): 16-bit core-matrix panels, see mlp_tc.cu ------
+  void* blob16[2] = {nullptr, nullptr};  // [0] fp16, [1] bf16
+  size_t blob16_bytes = 0;
+};
+
+}  // namespace dfb
+
+struct DfbNerf {
+  DfbNerfDesc desc;
+  int device = 0;
+  dfb::NetPack net[2];
+  float* emb_a = nullptr;  // [n_vocab,5]
+  float* emb_t = nullptr;  // [n_vocab,2]
+  bool has_emb = false;
+  int num_sms = 0;
+  float* lin_dev = nullptr;  // [Nc | Nf] linspace grids of the last render config
+  int lin_nc = -1, lin_nf = -1;
+};
+
+namespace dfb {
+
+// ---- kernels / launchers defined across translation units ------------------------------
+enum MlpMode { MLP_SIGMA = 0, MLP_STATIC = 1, MLP_FULL = 2 };
+
+// rays+z driven MLP (SIMT fp32).  raw: [P, C] with C = 1/4/9 for the three modes.
+int launch_mlp_simt_rays(const DfbNerf* nerf, int which, int mode, const float* rayrec, const float* z,
+                         const float* raybias, int64_t n_rays, int S, float* raw, cudaStream_t st);
+// embedded-input MLP (SIMT fp32), the NeRFW.forward seam.
+int launch_mlp_simt_embedded(const DfbNerf* nerf, int which, int mode, const float* x, int64_t P, float* out,
+                             cudaStream_t st);
+// tcgen05 MLP (W == 256).  kind: DFB_MMA_F16 / DFB_MMA_BF16.
+int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const float* rayrec, const float* z,
+                       const float* raybias, int64_t n_rays, int S, float* raw, cudaStream_t st);
+bool tc_supported(const DfbNerf* nerf, int which, int mode);
+int pack_tc_weights(DfbNerf* nerf, int which, const std::vector<std::vector<float>>& P);
+
+
+// ---- argument blocks of the non-MLP render kernels (render_kernels.cu) ----------------
+struct PrepArgs {
+  const float* rays;    // [N, 11+hb] or null
+  const float* c2w;     // [3,4] (row stride c2w_ld) or null
+  int c2w_ld;
+  int H, W;
+  float focal, near, far;
+  const float* hist;    // [hb] (c2w mode)
+  int hb, n_vocab;
+  const float* emb_a;   // [n_vocab,5] or null
+  const float* emb_t;   // [n_vocab,2] or null
+  int64_t N;
+  int64_t pix0;         // c2w mode: pixel index of ray 0 of this launch
+  int Nc;
+  const float* t_vals;  // [Nc] device
+  const float* t_rand;  // [N,Nc] or null
+  int lindisp;
+  float* rayrec;        // [N,12]
+  float* extra;         // [N, n_extra] or null : dirPE(27) | a(5*hb) | t(2*hb)
+  int n_extra, a_dim, t_dim;
+  float* z;             // [N,Nc]
+};
+
+struct CompositeArgs {
+  const float* raw;  // [N,S,C]
+  const float* z;    // [N,S]
+  int64_t N;
+  int S, C;          // C: 1 (coarse+test: sigma), 4 (rgb,sigma), 9 (full)
+  int typ_fine, test_time;
+  float beta_min;
+  float *rgb, *disp, *acc, *weights, *depth, *tsig, *beta;  // any may be null
+};
+
+struct SampleArgs {
+  // mode A (render path): z_c [N,Nc] and coarse weights [N,Nc]; bins = mids, weights[1:-1]
+  const float* z_c;
+  const float* w_c;
+  int Nc;
+  // mode B (seam): bins [N,nb], weights [N,nb-1]
+  const float* bins;
+  const float* weights;
+  int nb;
+  const float* u;      // [N,Nf] or null
+  const float* u_lin;  // [Nf] linspace(0,1,Nf) when u == null
+  int64_t N;
+  int Nf;
+  float* samples;      // [N,Nf] or null
+  int32_t* inds;       // [N,Nf] or null
+  float* z_vals;       // [N,Nc+Nf] sorted union, or null (mode A only)
+  float* z_std;        // [N] or null
+};
+
+int launch_prep(const PrepArgs& a, cudaStream_t st);
+int launch_raybias(const float* extra, int ld, int64_t N, const NetPack& np, bool with_transient, float* rb,
+                   int rb_ld, cudaStream_t st);
+int launch_composite(const CompositeArgs& a, cudaStream_t st);
+int launch_sample(const SampleArgs& a, cudaStream_t st);
+
+}  // namespace dfb

@@ -1,0 +1,399 @@
+// Ray generation, ray-constant MLP inputs, volumetric compositing and hierarchical
+// sampling kernels (everything on the render path except the 256-wide contractions).
+//
+// Reference arithmetic (paths relative to /root/reference/script):
+//   k_prep_rays      models/ray_utils.py:5-15 (get_rays), models/rendering.py:366-389 (ray record),
+//                    :269-287 (z_vals, stratified jitter), models/nerfw.py:69-78 (hist -> embedding rows)
+//   k_raybias        the ray-constant columns of dir_encoding / transient_encoding.0
+//                    (models/nerfw.py:337-345: cat([xyz_encoding_final, input_dir_a]) etc.)
+//   k_composite      models/rendering.py:132-243 (raw2outputs_NeRFW)
+//   k_sample_pdf     models/rendering.py:24-65 (sample_pdf) and :300-304 (z_mid, sort(cat))
+// Index parity: the float32 sum uses ATen's vector order, the cdf / transmittance scans run
+// sequentially in float64 like ATen-CPU, products and sums are rounded separately (no FMA).
+#include "common.cuh"
+
+namespace dfb {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// --------------------------------------------------------------------------------------
+// k_prep_rays
+// --------------------------------------------------------------------------------------
+
+constexpr int kPrepThreads = 128;
+
+__global__ void __launch_bounds__(kPrepThreads) k_prep_rays(PrepArgs a) {
+  extern __shared__ float sm[];
+  float* rec = sm;                                  // [128][12]
+  int* hidx = (int*)(sm + kPrepThreads * kRayRec);  // [128][hb]
+  const int tid = threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.x * kPrepThreads;
+  const int64_t r = r0 + tid;
+  const int nloc = (int)min((int64_t)kPrepThreads, a.N - r0);
+  if (r < a.N) {
+    float o[3], d[3], vd[3], nr, fr;
+    if (a.c2w) {
+      const int64_t rg = a.pix0 + r;
+      const int pj = (int)(rg / a.W), pi = (int)(rg % a.W);
+      const float dx = __fdiv_rn(__fsub_rn((float)pi, (float)(a.W * 0.5)), a.focal);
+      const float dy = -__fdiv_rn(__fsub_rn((float)pj, (float)(a.H * 0.5)), a.focal);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float* R = a.c2w + k * a.c2w_ld;
+        d[k] = __fadd_rn(__fadd_rn(__fmul_rn(dx, R[0]), __fmul_rn(dy, R[1])), __fmul_rn(-1.0f, R[2]));
+        o[k] = R[3];
+      }
+      const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+#pragma unroll
+      for (int k = 0; k < 3; ++k) vd[k] = __fdiv_rn(d[k], nrm);
+      nr = a.near, fr = a.far;
+      for (int b = 0; b < a.hb; ++b) hidx[tid * a.hb + b] = min(max((int)a.hist[b], 0), a.n_vocab - 1);
+    } else {
+      const float* p = a.rays + r * (11 + a.hb);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) o[k] = p[k], d[k] = p[3 + k], vd[k] = p[8 + k];
+      nr = p[6], fr = p[7];
+      for (int b = 0; b < a.hb; ++b) hidx[tid * a.hb + b] = min(max((int)p[11 + b], 0), a.n_vocab - 1);
+    }
+    float* q = rec + tid * kRayRec;
+    q[0] = o[0], q[1] = o[1], q[2] = o[2], q[3] = d[0], q[4] = d[1], q[5] = d[2];
+    q[6] = nr, q[7] = fr, q[8] = vd[0], q[9] = vd[1], q[10] = vd[2], q[11] = 0.f;
+  }
+  __syncthreads();
+  for (int i = tid; i < nloc * kRayRec; i += kPrepThreads) a.rayrec[r0 * kRayRec + i] = rec[i];
+  // z_vals (rendering.py:269-285)
+  for (int i = tid; i < nloc * a.Nc; i += kPrepThreads) {
+    const int rl = i / a.Nc, s = i % a.Nc;
+    const float nr = rec[rl * kRayRec + 6], fr = rec[rl * kRayRec + 7];
+    auto zat = [&](int k) {
+      const float t = a.t_vals[k];
+      if (!a.lindisp) return __fadd_rn(__fmul_rn(nr, __fsub_rn(1.f, t)), __fmul_rn(fr, t));
+      return __fdiv_rn(1.f, __fadd_rn(__fmul_rn(__fdiv_rn(1.f, nr), __fsub_rn(1.f, t)), __fmul_rn(__fdiv_rn(1.f, fr), t)));
+    };
+    float zv = zat(s);
+    if (a.t_rand) {
+      const float lower = s == 0 ? zv : __fmul_rn(0.5f, __fadd_rn(zv, zat(s - 1)));
+      const float upper = s == a.Nc - 1 ? zv : __fmul_rn(0.5f, __fadd_rn(zat(s + 1), zv));
+      zv = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), a.t_rand[(r0 + rl) * a.Nc + s]));
+    }
+    a.z[r0 * a.Nc + i] = zv;
+  }
+  if (a.extra) {
+    const int ne = a.n_extra;
+    for (int i = tid; i < nloc * ne; i += kPrepThreads) {
+      const int rl = i / ne, c = i % ne;
+      float v;
+      if (c < 27) {
+        if (c < 3) v = rec[rl * kRayRec + 8 + c];
+        else {
+          const int l = (c - 3) / 6, rr = (c - 3) % 6;
+          const float x = __fmul_rn(rec[rl * kRayRec + 8 + rr % 3], (float)(1 << l));
+          v = rr < 3 ? sinf(x) : cosf(x);
+        }
+      } else if (c < 27 + a.a_dim) {
+        const int e = c - 27;
+        v = a.emb_a[hidx[rl * a.hb + e / 5] * 5 + e % 5];
+      } else {
+        const int e = c - 27 - a.a_dim;
+        v = a.emb_t[hidx[rl * a.hb + e / 2] * 2 + e % 2];
+      }
+      a.extra[r0 * ne + i] = v;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------
+// k_raybias: rb[r][0:H] = b_dir + extra[r][0:nd] . Wdx ; rb[r][H:2H] = b_t0 + extra[r][nd:nd+nt] . Wtx
+// --------------------------------------------------------------------------------------
+__global__ void k_raybias(const float* __restrict__ extra, int ld, int64_t N, int nd, int nt, int Hh,
+                          const float* __restrict__ dirx_w, const float* __restrict__ dirx_b,
+                          const float* __restrict__ tx_w, const float* __restrict__ tx_b, float* __restrict__ rb,
+                          int n_rb, int rb_ld) {
+  // block = n_rb threads (one output column each), 8 rays per block
+  extern __shared__ float sm[];
+  const int64_t r0 = (int64_t)blockIdx.x * 8;
+  const int nloc = (int)min((int64_t)8, N - r0);
+  const int ne = nd + nt;
+  for (int i = threadIdx.x; i < nloc * ne; i += blockDim.x) sm[i] = extra[(r0 + i / ne) * ld + i % ne];
+  __syncthreads();
+  const int n = threadIdx.x;
+  if (n >= n_rb) return;
+  const bool tr = n >= Hh;
+  const int col = tr ? n - Hh : n;
+  const float* w = tr ? tx_w : dirx_w;
+  const int k0 = tr ? nd : 0, kn = tr ? nt : nd;
+  const float b = tr ? tx_b[col] : dirx_b[col];
+  for (int rl = 0; rl < nloc; ++rl) {
+    float acc = 0.f;
+    for (int k = 0; k < kn; ++k) acc = fmaf(sm[rl * ne + k0 + k], w[k * Hh + col], acc);
+    rb[(r0 + rl) * rb_ld + n] = acc + b;
+  }
+}
+
+// --------------------------------------------------------------------------------------
+// k_composite: raw2outputs_NeRFW, one warp per ray
+// --------------------------------------------------------------------------------------
+
+constexpr int kWarpsPerBlock = 4;
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_composite(CompositeArgs a) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  if (ray >= a.N) return;
+  const int S = a.S, C = a.C;
+  float* oma = sm + (size_t)warp * 4 * S;  // 1 - alpha
+  float* omas = oma + S;                   // 1 - static alpha
+  float* T = omas + S;                     // transmittance
+  float* Ts = T + S;                       // static-only transmittance
+  const float* raw = a.raw + ray * S * C;
+  const float* z = a.z + ray * S;
+  const bool full = (C == 9);
+  const bool static_depth = full && a.test_time;  // rendering.py:214-230
+  for (int i = lane; i < S; i += 32) {
+    const float delta = (i + 1 < S) ? __fsub_rn(z[i + 1], z[i]) : 1e2f;
+    const float nd = -delta;
+    if (full) {
+      const float ss = raw[i * 9 + 3], st = raw[i * 9 + 7];
+      oma[i] = __fsub_rn(1.f, __fsub_rn(1.f, expf(__fmul_rn(nd, __fadd_rn(ss, st)))));
+      omas[i] = __fsub_rn(1.f, __fsub_rn(1.f, expf(__fmul_rn(nd, ss))));
+    } else {
+      const float ss = fmaxf(raw[i * C + (C - 1)], 0.f);  // relu(sigma + 0*noise)
+      oma[i] = __fsub_rn(1.f, __fsub_rn(1.f, expf(__fmul_rn(nd, ss))));
+    }
+  }
+  __syncwarp();
+  // exclusive cumprod, float64 running product rounded per element (ATen-CPU cumprod)
+  if (lane == 0) {
+    double t = 1.0;
+    for (int i = 0; i < S; ++i) { T[i] = (float)t; t *= (double)oma[i]; }
+  } else if (lane == 1 && static_depth) {
+    double t = 1.0;
+    for (int i = 0; i < S; ++i) { Ts[i] = (float)t; t *= (double)omas[i]; }
+  }
+  __syncwarp();
+  float s_acc = 0.f, s_depth = 0.f, s_beta = 0.f, s_r[3] = {0, 0, 0}, t_r[3] = {0, 0, 0};
+  for (int i = lane; i < S; i += 32) {
+    const float delta = (i + 1 < S) ? __fsub_rn(z[i + 1], z[i]) : 1e2f;
+    const float nd = -delta;
+    const float zi = z[i], Ti = T[i];
+    if (full) {
+      const float ss = raw[i * 9 + 3], st = raw[i * 9 + 7];
+      const float al = __fsub_rn(1.f, expf(__fmul_rn(nd, __fadd_rn(ss, st))));
+      const float als = __fsub_rn(1.f, expf(__fmul_rn(nd, ss)));
+      const float alt = __fsub_rn(1.f, expf(__fmul_rn(nd, st)));
+      const float w = __fmul_rn(al, Ti), sw = __fmul_rn(als, Ti), tw = __fmul_rn(alt, Ti);
+      if (a.weights) a.weights[ray * S + i] = w;
+      if (a.tsig) a.tsig[ray * S + i] = st;
+      s_acc += w;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        s_r[c] += __fmul_rn(sw, raw[i * 9 + c]);
+        t_r[c] += __fmul_rn(tw, raw[i * 9 + 4 + c]);
+      }
+      s_beta += __fmul_rn(tw, raw[i * 9 + 8]);
+      s_depth += static_depth ? __fmul_rn(__fmul_rn(als, Ts[i]), zi) : __fmul_rn(w, zi);
+    } else {
+      const float ss = fmaxf(raw[i * C + (C - 1)], 0.f);
+      const float al = __fsub_rn(1.f, expf(__fmul_rn(nd, ss)));
+      const float w = __fmul_rn(al, Ti);
+      if (a.weights) a.weights[ray * S + i] = w;
+      s_acc += w;
+      if (C == 4) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) s_r[c] += __fmul_rn(w, raw[i * 4 + c]);
+        s_depth += __fmul_rn(w, zi);
+      }
+    }
+  }
+  s_acc = warp_sum(s_acc);
+  s_depth = warp_sum(s_depth);
+  s_beta = warp_sum(s_beta);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) s_r[c] = warp_sum(s_r[c]), t_r[c] = warp_sum(t_r[c]);
+  if (lane == 0) {
+    if (a.acc) a.acc[ray] = s_acc;
+    if (C != 1) {
+      if (a.rgb)
+        for (int c = 0; c < 3; ++c) a.rgb[ray * 3 + c] = full ? __fadd_rn(s_r[c], t_r[c]) : s_r[c];
+      if (a.depth) a.depth[ray] = s_depth;
+      if (a.disp) a.disp[ray] = __fdiv_rn(1.f, fmaxf(1e-10f, __fdiv_rn(s_depth, s_acc)));
+      if (a.beta) a.beta[ray] = full ? __fadd_rn(s_beta, a.beta_min) : 0.f;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------
+// k_sample_pdf: inverse-CDF sampling (+ optional merge-sort with the coarse depths)
+// --------------------------------------------------------------------------------------
+__device__ __forceinline__ int ceil_log2_i(int x) { return x <= 1 ? 0 : 32 - __clz(x - 1); }
+
+// torch.sum over a contiguous float32 row in ATen-CPU's order (see oracle aten_sum_lastdim).
+__device__ float aten_sum_warp(const float* x, int n, int lane) {
+  const int vec_size = n >> 3, size_ilp = vec_size >> 2;
+  float p = 0.f;
+  if (lane < 8) {
+    float acc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[j][k] = 0.f;
+    const int lp = max(4, ceil_log2_i(size_ilp) / 4), lstep = 1 << lp, lmask = lstep - 1;
+    int i = 0;
+    while (i + lstep <= size_ilp) {
+      for (int j = 0; j < lstep; ++j, ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[0][k] += x[(i * 4 + k) * 8 + lane];
+      for (int j = 1; j < 4; ++j) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { acc[j][k] += acc[j - 1][k]; acc[j - 1][k] = 0.f; }
+        if ((i & (lmask << (j * lp))) != 0) break;
+      }
+    }
+    for (; i < size_ilp; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[0][k] += x[(i * 4 + k) * 8 + lane];
+    for (int j = 1; j < 4; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[0][k] += acc[j][k];
+    p = acc[0][0];
+    for (int v = size_ilp * 4; v < vec_size; ++v) p += x[v * 8 + lane];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) p += acc[0][k];
+  }
+  float fin = 0.f;
+  for (int k = vec_size * 8; k < n; ++k) fin += x[k];
+#pragma unroll
+  for (int l = 0; l < 8; ++l) fin += __shfl_sync(0xffffffffu, p, l);
+  return fin;
+}
+
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_sample_pdf(SampleArgs a) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  if (ray >= a.N) return;
+  const bool modeA = a.z_c != nullptr;
+  const int nb = modeA ? a.Nc - 1 : a.nb, nw = nb - 1, Nf = a.Nf;
+  const int S = modeA ? a.Nc + Nf : 0;
+  const int per_warp = 3 * nb + 8 + (modeA ? a.Nc + Nf : Nf);
+  float* bins = sm + (size_t)warp * per_warp;
+  float* pdf = bins + nb;
+  float* cdf = pdf + nb;
+  float* zall = cdf + nb + 8;  // [Nc coarse | Nf samples] (mode A) or [Nf]
+  float* smp = modeA ? zall + a.Nc : zall;
+  if (modeA) {
+    const float* z = a.z_c + ray * a.Nc;
+    const float* w = a.w_c + ray * a.Nc;
+    for (int i = lane; i < a.Nc; i += 32) zall[i] = z[i];
+    for (int i = lane; i < nb; i += 32) bins[i] = __fmul_rn(0.5f, __fadd_rn(z[i + 1], z[i]));
+    for (int i = lane; i < nw; i += 32) pdf[i] = __fadd_rn(w[i + 1], 1e-5f);
+  } else {
+    for (int i = lane; i < nb; i += 32) bins[i] = a.bins[ray * nb + i];
+    for (int i = lane; i < nw; i += 32) pdf[i] = __fadd_rn(a.weights[ray * nw + i], 1e-5f);
+  }
+  __syncwarp();
+  const float tot = aten_sum_warp(pdf, nw, lane);
+  __syncwarp();
+  for (int i = lane; i < nw; i += 32) pdf[i] = __fdiv_rn(pdf[i], tot);
+  __syncwarp();
+  if (lane == 0) {  // float64 running sum rounded per element (ATen-CPU cumsum)
+    double c = 0.0;
+    cdf[0] = 0.f;
+    for (int i = 0; i < nw; ++i) { c += (double)pdf[i]; cdf[i + 1] = (float)c; }
+  }
+  __syncwarp();
+  float s1 = 0.f;
+  for (int k = lane; k < Nf; k += 32) {
+    const float u = a.u ? a.u[ray * Nf + k] : a.u_lin[k];
+    int lo = 0, hi = nb;  // searchsorted(right=True): first index with cdf > u
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (cdf[mid] <= u) lo = mid + 1; else hi = mid;
+    }
+    const int below = max(0, lo - 1), above = min(nb - 1, lo);
+    const float c0 = cdf[below], c1 = cdf[above];
+    float denom = __fsub_rn(c1, c0);
+    if (denom < 1e-5f) denom = 1.f;
+    const float t = __fdiv_rn(__fsub_rn(u, c0), denom);
+    const float v = __fadd_rn(bins[below], __fmul_rn(t, __fsub_rn(bins[above], bins[below])));
+    smp[k] = v;
+    s1 += v;
+    if (a.samples) a.samples[ray * Nf + k] = v;
+    if (a.inds) a.inds[ray * Nf + k] = lo;
+  }
+  __syncwarp();
+  if (a.z_std) {  // torch.std(z_samples, -1, unbiased=False) (rendering.py:327)
+    const float mean = warp_sum(s1) / (float)Nf;
+    float s2 = 0.f;
+    for (int k = lane; k < Nf; k += 32) { const float dlt = smp[k] - mean; s2 = fmaf(dlt, dlt, s2); }
+    s2 = warp_sum(s2);
+    if (lane == 0) a.z_std[ray] = sqrtf(s2 / (float)Nf);
+  }
+  if (modeA && a.z_vals) {  // torch.sort(torch.cat([z_vals, z_samples], -1), -1) values
+    for (int i = lane; i < S; i += 32) {
+      const float v = zall[i];
+      int rank = 0;
+      for (int j = 0; j < S; ++j) {
+        const float o = zall[j];
+        rank += (o < v) || (o == v && j < i);
+      }
+      a.z_vals[ray * S + rank] = v;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------
+// host launchers
+// --------------------------------------------------------------------------------------
+int launch_prep(const PrepArgs& a, cudaStream_t st) {
+  const int blocks = (int)((a.N + kPrepThreads - 1) / kPrepThreads);
+  const size_t smem = kPrepThreads * kRayRec * sizeof(float) + kPrepThreads * a.hb * sizeof(int);
+  k_prep_rays<<<blocks, kPrepThreads, smem, st>>>(a);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+int launch_raybias(const float* extra, int ld, int64_t N, const NetPack& np, bool with_transient, float* rb,
+                   int rb_ld, cudaStream_t st) {
+  const int Hh = np.W / 2, nd = np.in_dir + np.a_dim, nt = with_transient ? np.t_dim : 0;
+  const int n_rb = with_transient ? 2 * Hh : Hh;
+  const int blocks = (int)((N + 7) / 8);
+  const int threads = round_up(n_rb, 32);
+  const size_t smem = 8 * (nd + nt) * sizeof(float);
+  const float* b = np.blob32;
+  k_raybias<<<blocks, threads, smem, st>>>(extra, ld, N, nd, nt, Hh, b + np.dirx_w, b + np.dirx_b,
+                                            with_transient ? b + np.tx_w : nullptr,
+                                            with_transient ? b + np.tx_b : nullptr, rb, n_rb, rb_ld);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+int launch_composite(const CompositeArgs& a, cudaStream_t st) {
+  const int blocks = (int)((a.N + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  const size_t smem = (size_t)kWarpsPerBlock * 4 * a.S * sizeof(float);
+  DFB_REQUIRE(smem <= 48 * 1024, DFB_ERR_UNSUPPORTED, "samples per ray %d too large for the compositing kernel", a.S);
+  k_composite<<<blocks, kWarpsPerBlock * 32, smem, st>>>(a);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+int launch_sample(const SampleArgs& a, cudaStream_t st) {
+  const bool modeA = a.z_c != nullptr;
+  const int nb = modeA ? a.Nc - 1 : a.nb;
+  DFB_REQUIRE(nb >= 2 && a.Nf >= 1, DFB_ERR_INVALID, "sample_pdf needs >= 2 bins and >= 1 sample");
+  const int per_warp = 3 * nb + 8 + (modeA ? a.Nc + a.Nf : a.Nf);
+  const size_t smem = (size_t)kWarpsPerBlock * per_warp * sizeof(float);
+  DFB_REQUIRE(smem <= 48 * 1024, DFB_ERR_UNSUPPORTED, "N_samples/N_importance too large for the sampling kernel");
+  const int blocks = (int)((a.N + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  k_sample_pdf<<<blocks, kWarpsPerBlock * 32, smem, st>>>(a);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+}  // namespace dfb

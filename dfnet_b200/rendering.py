@@ -1,0 +1,146 @@
+"""Host mirror of the reference's models/rendering.py call surface.
+
+Same names, arguments and return structure as the reference (render, batchify_rays,
+render_rays, raw2outputs_NeRFW, sample_pdf); the arithmetic runs in libdfnet_b200 through
+dfnet_b200.ops.  Options no shipped config reaches (ndc, c2w_staticcam, white_bkgd,
+raw_noise_std > 0) raise instead of silently diverging.
+"""
+import torch
+
+from . import ops
+from .ray_utils import get_rays  # noqa: F401  (re-exported like `from models.ray_utils import *`)
+
+DEFAULT_MMA = "f16"
+
+
+def sample_pdf(bins, weights, N_samples, det=False, pytest=False):
+    """Hierarchical inverse-CDF sampling (reference rendering.py:24-65)."""
+    u = None
+    if pytest and not det:
+        import numpy as np
+        np.random.seed(0)
+        u = torch.tensor(np.random.rand(bins.shape[0], N_samples), dtype=torch.float32)
+    samples, _ = ops.sample_pdf(bins, weights, N_samples, det=det, u=u)
+    return samples
+
+
+def raw2outputs_NeRFW(raw, z_vals, rays_d=None, raw_noise_std=0, output_transient=False, beta_min=0.1,
+                      white_bkgd=False, test_time=False, static_only=True, typ="coarse"):
+    """Volumetric compositing (reference rendering.py:132-243) ->
+    (rgb_map, disp_map, acc_map, weights, depth_map, transient_sigmas, beta)."""
+    if raw_noise_std != 0 or white_bkgd:
+        raise NotImplementedError("raw_noise_std / white_bkgd are not on the B200 hot path")
+    if not static_only:
+        raise NotImplementedError("static_only=False is never used by the reference")
+    if typ == "coarse" and test_time and raw.shape[-1] != 1:
+        raw = raw[..., :1]
+    o = ops.raw2outputs(raw, z_vals, typ, test_time, beta_min)
+    if typ == "coarse" and test_time:
+        return None, None, o["acc"], o["weights"], None, None, None
+    return o["rgb"], o["disp"], o["acc"], o["weights"], o["depth"], o["transient_sigmas"], o["beta"]
+
+
+def _handle(kw):
+    return ops.handle_for(kw["network_fn"], kw.get("network_fine"), kw.get("embedding_a"), kw.get("embedding_t"))
+
+
+def _check_kwargs(kw):
+    if kw.get("white_bkgd"):
+        raise NotImplementedError("white_bkgd is dropped by the reference itself (rendering.py:295) and unsupported here")
+    if kw.get("raw_noise_std", 0.0):
+        raise NotImplementedError("raw_noise_std > 0 (NeRF training noise) is not on the B200 hot path yet")
+
+
+def render_rays(ray_batch, network_fn, network_query_fn=None, N_samples=64, retraw=False, lindisp=False, perturb=0.,
+                N_importance=0, network_fine=None, white_bkgd=False, raw_noise_std=0., verbose=False, pytest=False,
+                i_epoch=-1, embedding_a=None, embedding_t=None, test_time=False, mma=None):
+    """Render a batch of ray records [N, 11+hist_bin] (reference rendering.py:245-337)."""
+    kw = dict(network_fn=network_fn, network_fine=network_fine, embedding_a=embedding_a, embedding_t=embedding_t,
+              white_bkgd=white_bkgd, raw_noise_std=raw_noise_std)
+    _check_kwargs(kw)
+    h = _handle(kw)
+    N = ray_batch.shape[0]
+    t_rand = u = None
+    if perturb > 0.:
+        # same draws, shapes and order as the reference (:282 then sample_pdf :36)
+        t_rand = torch.rand(N, N_samples, device=ray_batch.device)
+        if N_importance > 0:
+            if pytest:
+                import numpy as np
+                np.random.seed(0)
+                u = torch.tensor(np.random.rand(N, N_importance), dtype=torch.float32)
+            else:
+                u = torch.rand(N, N_importance, device=ray_batch.device)
+    want = []
+    if N_importance > 0 and not test_time:
+        want += ["rgb0", "disp0", "acc0", "z_std", "transient_sigmas", "beta"]
+    if retraw:
+        want.append("raw")
+    o = h.render(N_samples, N_importance, test_time, rays=ray_batch, perturb=perturb > 0., t_rand=t_rand, u=u,
+                 mma=mma or DEFAULT_MMA, lindisp=lindisp, want=want)
+    ret = {"rgb_map": o["rgb"], "disp_map": o["disp"], "acc_map": o["acc"]}
+    for k in want:
+        ret[k] = o[k]
+    return ret
+
+
+def batchify_rays(rays_flat, chunk=1024 * 32, **kwargs):
+    """Reference rendering.py:339-351.  The kernels bound their own workspace, so `chunk`
+    only controls how the torch.rand draws are grouped when perturb > 0."""
+    if kwargs.get("perturb", 0.) > 0.:
+        outs = {}
+        for i in range(0, rays_flat.shape[0], chunk):
+            r = render_rays(rays_flat[i:i + chunk], **kwargs)
+            for k, v in r.items():
+                outs.setdefault(k, []).append(v)
+        return {k: torch.cat(v, 0) for k, v in outs.items()}
+    return render_rays(rays_flat, **kwargs)
+
+
+def render(H, W, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far=1., use_viewdirs=False,
+           c2w_staticcam=None, img_idx=torch.Tensor(0), **kwargs):
+    """Reference rendering.py:353-400 -> [rgb_map, disp_map, acc_map, extras]."""
+    if ndc:
+        raise NotImplementedError("ndc=True: create_nerf forces ndc=False for every shipped dataset (nerfw.py:492-495)")
+    if not use_viewdirs or c2w_staticcam is not None:
+        raise NotImplementedError("NeRF-Hist always renders with use_viewdirs=True and no static camera")
+    kwargs.pop("network_query_fn", None)
+    _check_kwargs(kwargs)
+    mma = kwargs.pop("mma", None) or DEFAULT_MMA
+    test_time = kwargs.get("test_time", False)
+    Nc, Nf = kwargs["N_samples"], kwargs.get("N_importance", 0)
+    perturb = kwargs.get("perturb", 0.)
+    if c2w is not None and not perturb:
+        # whole image from one pose: rays are generated in-kernel
+        h = _handle(kwargs)
+        want = []
+        if Nf > 0 and not test_time:
+            want += ["rgb0", "disp0", "acc0", "z_std", "transient_sigmas", "beta"]
+        if kwargs.get("retraw"):
+            want.append("raw")
+        o = h.render(Nc, Nf, test_time, c2w=c2w, H=int(H), W=int(W), focal=float(focal), near=float(near),
+                     far=float(far), hist=img_idx.to(c2w.device), mma=mma, lindisp=kwargs.get("lindisp", False),
+                     want=want)
+        sh = [int(H), int(W)]
+        all_ret = {"rgb_map": o["rgb"], "disp_map": o["disp"], "acc_map": o["acc"], **{k: o[k] for k in want}}
+    else:
+        if c2w is not None:
+            rays_o, rays_d = get_rays(H, W, focal, c2w)
+        else:
+            rays_o, rays_d = rays
+        viewdirs = rays_d / torch.norm(rays_d, dim=-1, keepdim=True)
+        viewdirs = torch.reshape(viewdirs, [-1, 3]).float()
+        sh = list(rays_d.shape[:-1])
+        rays_o = torch.reshape(rays_o, [-1, 3]).float()
+        rays_d = torch.reshape(rays_d, [-1, 3]).float()
+        nf = torch.ones_like(rays_d[..., :1])
+        img_idx = img_idx.to(rays_d.device).float()
+        if img_idx.shape[0] != rays_d.shape[0]:
+            img_idx = img_idx.reshape(1, -1).repeat(rays_d.shape[0], 1)
+        rec = torch.cat([rays_o, rays_d, near * nf, far * nf, viewdirs, img_idx], -1)
+        kwargs.pop("use_viewdirs", None), kwargs.pop("ndc", None)
+        all_ret = batchify_rays(rec, chunk, mma=mma, **{k: v for k, v in kwargs.items() if k not in ("ndc",)})
+    for k in all_ret:
+        all_ret[k] = torch.reshape(all_ret[k], sh + list(all_ret[k].shape[1:]))
+    k_extract = ["rgb_map", "disp_map", "acc_map"]
+    return [all_ret[k] for k in k_extract] + [{k: v for k, v in all_ret.items() if k not in k_extract}]

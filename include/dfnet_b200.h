@@ -1,0 +1,168 @@
+/*
+ * dfnet_b200 — C ABI of the B200-native NeRF-Hist render / DFNet feature hot path.
+ *
+ * The reference (ActiveVisionLab/DFNet) is pure Python/PyTorch and has no FFI; its
+ * boundary for this path is the Python call surface listed in SURVEY.md §8(b).  Every
+ * entry point below cites the reference function (path relative to script/) whose
+ * arithmetic it replaces.  The Python shims that keep the reference's signatures live in
+ * dfnet_b200/ (rendering.py, nerfw.py, ...) and bind these symbols through ctypes; see
+ * INTEGRATION.md for the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every call returns 0 on success, <0 on error; dfb_last_error() gives the message
+ *     (thread-local, valid until the next failing call on the thread);
+ *   - no exceptions, no allocations and no torch types cross the boundary;
+ *   - device buffers (inputs, outputs, workspace) are owned by the caller and passed as
+ *     raw pointers + sizes; the library owns only the opaque handles (repacked weights);
+ *   - launches are asynchronous on the `stream` argument (a cudaStream_t passed as void*);
+ *   - handles are bound to the device that was current at creation; not thread-safe.
+ */
+#ifndef DFNET_B200_H_
+#define DFNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFB_OK 0
+#define DFB_ERR_INVALID (-1)
+#define DFB_ERR_CUDA (-2)
+#define DFB_ERR_UNSUPPORTED (-3)
+#define DFB_ERR_WORKSPACE (-4)
+
+/* How the 256-wide contractions are computed. */
+#define DFB_MMA_FP32_SIMT 0 /* fp32 FFMA, any width (exact-order fallback for odd sizes)   */
+#define DFB_MMA_F16 1       /* tcgen05.mma kind::f16, fp16 operands, fp32 accumulate in TMEM */
+#define DFB_MMA_BF16 2      /* tcgen05.mma kind::f16, bf16 operands, fp32 accumulate in TMEM */
+
+const char* dfb_last_error(void);
+int dfb_version(void);
+/* 1 when a CUDA device of compute capability 10.x is current, else 0 (never fails). */
+int dfb_device_ok(void);
+
+/* torch.linspace(start,end,steps) float32 exactly as ATen-CPU evaluates it (host helper;
+ * models/rendering.py:32,269 build u and t_vals with it). */
+int dfb_linspace_f32(float start, float end, int steps, float* out_host);
+
+/* ------------------------------------------------------------------------------------
+ * NeRF-W / NeRF-Hist networks  (models/nerfw.py:220-354 NeRFW, :356-502 create_nerf)
+ * ---------------------------------------------------------------------------------- */
+typedef struct DfbNerf DfbNerf;
+
+typedef struct DfbNerfDesc {
+  int32_t D;        /* trunk depth   (args.netdepth, 8)                      */
+  int32_t W;        /* trunk width   (args.netwidth, 256 / 128 / 64)         */
+  int32_t skip;     /* trunk layer index that concatenates input_xyz (4); <0 = none */
+  int32_t L_xyz;    /* positional-encoding bands for xyz (multires, 10)      */
+  int32_t L_dir;    /* bands for view directions (multires_views, 4)         */
+  int32_t a_dim;    /* appearance code width = hist_bin*5 (in_channels_a, 50) */
+  int32_t t_dim;    /* transient code width  = hist_bin*2 (in_channels_t, 20) */
+  int32_t hist_bin; /* histogram bins (10)                                   */
+  int32_t n_vocab;  /* rows of embedding_a / embedding_t (1000)              */
+  float beta_min;   /* NeRFW.beta_min (0.1)                                  */
+  int32_t has_fine; /* 1: coarse + fine networks, 0: coarse only (N_importance == 0) */
+} DfbNerfDesc;
+
+int dfb_nerf_create(const DfbNerfDesc* desc, DfbNerf** out);
+void dfb_nerf_destroy(DfbNerf* nerf);
+
+/* Load one network's parameters.  which: 0 = network_fn (coarse), 1 = network_fine.
+ * params[i] points to the i-th tensor of NeRFW.state_dict() (fp32, contiguous, host or
+ * device memory), numel[i] is its element count; order and sizes are checked against the
+ * descriptor.  Weights are repacked into the kernels' layouts (fp32 K-major for SIMT,
+ * fp16/bf16 core-matrix panels for tcgen05). */
+int dfb_nerf_load(DfbNerf* nerf, int which, const float* const* params, const int64_t* numel, int n_params);
+/* embedding_a.weight [n_vocab,5] and embedding_t.weight [n_vocab,2] (nerfw.py:386-394). */
+int dfb_nerf_set_embeddings(DfbNerf* nerf, const float* emb_a, const float* emb_t);
+
+/* NeRFW.forward on already-embedded points (models/nerfw.py:297-354).
+ * mode: 0 sigma_only (x [P,63] -> out [P,1]); 1 static (x [P,63+27+a] -> [P,4], a = a_dim
+ * for the fine net, 0 for coarse); 2 full (x [P,63+27+a+t] -> [P,9], fine net only).
+ * fp32 SIMT path; op-level seam used by NeRFW.forward and the parity tests. */
+int dfb_nerfw_forward(DfbNerf* nerf, int which, int mode, const float* x, int64_t P, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Rendering  (models/rendering.py:245-400 render_rays / batchify_rays / render,
+ *             models/ray_utils.py:5-15 get_rays, models/nerfw.py:15-95 run_network_NeRFW)
+ * ---------------------------------------------------------------------------------- */
+typedef struct DfbRenderCfg {
+  int32_t N_samples;    /* coarse samples per ray                                     */
+  int32_t N_importance; /* extra fine samples per ray (0 = coarse only)               */
+  int32_t test_time;    /* render_kwargs_test: sigma-only coarse pass, static-only depth */
+  int32_t perturb;      /* 1: stratified jitter; t_rand and u must be supplied         */
+  int32_t mma_kind;     /* DFB_MMA_*                                                   */
+  int32_t lindisp;      /* sample linearly in disparity (rendering.py:272-273)         */
+  float raw_noise_std;  /* must be 0: the reference's noise is randn()*std             */
+  int32_t reserved;
+} DfbRenderCfg;
+
+/* Optional outputs (NULL = not wanted).  Train-mode extras follow rendering.py:318-331. */
+typedef struct DfbRenderExtras {
+  float* rgb0;             /* [N,3]  coarse composite (train mode)                      */
+  float* disp0;            /* [N]                                                       */
+  float* acc0;             /* [N]                                                       */
+  float* z_std;            /* [N]    std of the fine samples, unbiased=False            */
+  float* beta;             /* [N]                                                       */
+  float* transient_sigmas; /* [N,S]                                                     */
+  float* raw;              /* [N,S,9] fine raw (or [N,Nc,4] when N_importance == 0)     */
+  float* weights_coarse;   /* [N,Nc]  seam: coarse weights fed to sample_pdf            */
+  float* z_vals;           /* [N,S]   seam: sorted union of coarse and fine depths      */
+  float* z_samples;        /* [N,Nf]  seam: sample_pdf output                           */
+  int32_t* inds;           /* [N,Nf]  seam: searchsorted indices (int64 in the reference) */
+  float* depth;            /* [N]                                                       */
+} DfbRenderExtras;
+
+/* Bytes of device workspace dfb_render_fwd needs for n_rays rays. */
+int dfb_render_workspace_bytes(const DfbNerf* nerf, const DfbRenderCfg* cfg, int64_t n_rays, size_t* out);
+
+/* render() (rendering.py:353-400) for N rays.
+ * Ray source, exactly one of:
+ *   rays  != NULL : device [N, 11+hist_bin] records [o3,d3,near,far,viewdir3,hist] (:382-389)
+ *   c2w   != NULL : device [3,4] (or [4,4]) pose; rays are generated in-kernel like get_rays
+ *                   for an H x W image with N == H*W; near/far scalars; hist device [hist_bin].
+ * t_rand [N,Nc] / u [N,Nf]: uniform draws the reference takes from torch.rand when
+ * perturb > 0 (:282, :36); NULL when perturb == 0.
+ * Outputs rgb [N,3], disp [N], acc [N] (device). */
+int dfb_render_fwd(DfbNerf* nerf, const DfbRenderCfg* cfg, const float* rays, const float* c2w, int H, int W,
+                   float focal, float near, float far, const float* hist, int64_t N, const float* t_rand,
+                   const float* u, float* rgb, float* disp, float* acc, const DfbRenderExtras* extras, void* ws,
+                   size_t ws_bytes, void* stream);
+
+/* Same as dfb_render_fwd with c2w/hist and the three outputs in HOST memory (pinned for
+ * true asynchrony): the pose/histogram upload and the image download are enqueued on
+ * `stream` around the kernels.  This is the call render_path() makes per image
+ * (rendering.py:420-424: render + .cpu()). The caller synchronises the stream. */
+int dfb_render_image_host(DfbNerf* nerf, const DfbRenderCfg* cfg, const float* c2w_host, int H, int W, float focal,
+                          float near, float far, const float* hist_host, float* rgb_host, float* disp_host,
+                          float* acc_host, void* ws, size_t ws_bytes, void* stream);
+
+/* Op-level seams (same arguments as the reference functions). */
+/* sample_pdf (rendering.py:24-65): bins [N,nb], weights [N,nb-1], u [N,Nf] or NULL (det). */
+int dfb_sample_pdf(const float* bins, const float* weights, const float* u, int64_t N, int n_bins, int Nf,
+                   float* samples, int32_t* inds, void* stream);
+/* raw2outputs_NeRFW (rendering.py:132-243).  typ: 0 coarse, 1 fine.  raw [N,S,C] with
+ * C = 1 (coarse+test), 4 (coarse train) or 9 (fine).  Any output may be NULL. */
+int dfb_raw2outputs(const float* raw, const float* z_vals, int64_t N, int S, int C, int typ, int test_time,
+                    float beta_min, float* rgb, float* disp, float* acc, float* weights, float* depth,
+                    float* transient_sigmas, float* beta, void* stream);
+/* get_rays (ray_utils.py:5-15): c2w device [3,4] -> rays_o, rays_d device [H*W,3]. */
+int dfb_get_rays(const float* c2w, int row_stride, int H, int W, float focal, float* rays_o, float* rays_d,
+                 void* stream);
+
+/* Number of kernel launches issued by this library since load (bench.py gpu_launches). */
+int64_t dfb_launch_count(void);
+
+/* Per-kernel timing of the coarse / fine MLP launches with CUDA events on the launching
+ * stream (measurement hook for bench.py's roofline line; off by default).  dfb_profile_read
+ * waits for the recorded events, returns summed milliseconds and launch counts since the
+ * previous read, and clears the records. */
+int dfb_profile_enable(int on);
+int dfb_profile_read(double* coarse_ms, double* fine_ms, int64_t* coarse_launches, int64_t* fine_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFNET_B200_H_ */

@@ -161,12 +161,33 @@ def embed(x, L):
 # --------------------------------------------------------------------------------------
 # a7: NeRFW MLP
 # --------------------------------------------------------------------------------------
+_LINEAR_BACKEND = "numpy"
+
+
+def set_linear_backend(name):
+    """"numpy" (default, used by every parity test) or "torch": run the Linear layers through
+    torch-CPU addmm (MKL/oneDNN), the library the reference itself executes them with.  Only
+    bench.py's CPU-baseline timing selects "torch", so that the baseline is not handicapped by
+    numpy's BLAS; all other arithmetic is unchanged."""
+    global _LINEAR_BACKEND
+    assert name in ("numpy", "torch")
+    _LINEAR_BACKEND = name
+
+
 def _linear(x, w, b):
+    if _LINEAR_BACKEND == "torch":
+        import torch
+        return torch.addmm(torch.from_numpy(b), torch.from_numpy(np.ascontiguousarray(x)),
+                           torch.from_numpy(w).t()).numpy()
     return (x @ w.T + b).astype(f32)
 
 
 def _relu(x):
-    return np.maximum(x, f32(0))
+    if _LINEAR_BACKEND == "torch":
+        import torch
+        torch.relu_(torch.from_numpy(x))  # in place, multi-threaded, as nn.ReLU(True) in the reference
+        return x
+    return np.maximum(x, f32(0), out=x if x.flags.writeable and x.dtype == f32 else None)
 
 
 def _softplus(x):

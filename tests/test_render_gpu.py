@@ -1,0 +1,196 @@
+"""GPU parity tests of the render hot path, through the C ABI, against the oracle and the
+reference-generated golden vectors.  Tolerances: bit-exact for indices and for op-level
+float results whose operation order is pinned; 1e-3 relative (north star) for the tensor-core
+paths; 1e-4 for the fp32 path."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_err, synthetic_nets
+from oracle import nerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def T(x):
+    return torch.as_tensor(np.ascontiguousarray(x)).to(dev())
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from dfnet_b200 import ops as _ops
+    return _ops
+
+
+def to_dev(mods):
+    return [m.to(dev()) if m is not None else None for m in mods]
+
+
+def test_get_rays_bit_exact(ops, golden):
+    H, W, f = golden["rays_hwf"]
+    o, d = ops.get_rays(int(H), int(W), float(f), T(golden["rays_c2w"]))
+    assert np.array_equal(o.cpu().numpy(), golden["rays_o"])
+    assert np.array_equal(d.cpu().numpy(), golden["rays_d"])
+
+
+def test_sample_pdf_bit_exact(ops, golden):
+    s, i = ops.sample_pdf(T(golden["pdf_bins"]), T(golden["pdf_w"]), 128, det=True)
+    assert np.array_equal(i.cpu().numpy(), golden["pdf_det_inds"])
+    assert np.array_equal(s.cpu().numpy(), golden["pdf_det_samples"])
+    s, i = ops.sample_pdf(T(golden["pdf_bins"]), T(golden["pdf_w"]), 128, det=False, u=T(golden["pdf_u_rand"]))
+    assert np.array_equal(i.cpu().numpy(), golden["pdf_rand_inds"])
+    assert np.array_equal(s.cpu().numpy(), golden["pdf_rand_samples"])
+
+
+@pytest.mark.parametrize("nb,nf", [(63, 128), (63, 192), (15, 24), (127, 64), (600, 33), (2, 5)])
+def test_sample_pdf_vs_oracle_sizes(ops, nb, nf):
+    rng = np.random.RandomState(nb * 1000 + nf)
+    N = 257
+    bins = np.sort(rng.rand(N, nb).astype(np.float32) * 3, -1)
+    w = rng.rand(N, nb - 1).astype(np.float32) ** 5
+    w[0] = 0
+    w[1, : (nb - 1) // 2] = 0
+    u = rng.rand(N, nf).astype(np.float32)
+    u[2, :3] = [0.0, 1.0, 0.5][: min(3, nf)] + [0.5] * max(0, 3 - nf) if nf >= 3 else u[2, :3]
+    for det in (True, False):
+        so, io = O.sample_pdf(bins, w, nf, det=det, u=u)
+        s, i = ops.sample_pdf(T(bins), T(w), nf, det=det, u=T(u))
+        assert np.array_equal(i.cpu().numpy(), io), (nb, nf, det)
+        assert np.array_equal(s.cpu().numpy(), so), (nb, nf, det)
+
+
+def test_sample_pdf_empty(ops):
+    s, i = ops.sample_pdf(torch.zeros(0, 63, device=dev()), torch.zeros(0, 62, device=dev()), 16, det=True)
+    assert s.shape == (0, 16) and i.shape == (0, 16)
+
+
+@pytest.mark.parametrize("case", ["coarse_test", "coarse_train", "fine_test", "fine_train"])
+def test_raw2outputs(ops, golden, case):
+    raw, z = golden["r2o_raw"], golden["r2o_z"]
+    sel = dict(coarse_test=raw[..., 3:4], coarse_train=raw[..., :4], fine_test=raw, fine_train=raw)[case]
+    o = ops.raw2outputs(T(sel), T(z), "fine" if case.startswith("fine") else "coarse", case.endswith("test"))
+    n = 0
+    for nm in ["rgb", "disp", "acc", "weights", "depth", "transient_sigmas", "beta"]:
+        key = f"r2o_{case}_{nm}"
+        if key in golden:
+            assert np.allclose(o[nm].cpu().numpy(), golden[key], rtol=2e-5, atol=2e-6), nm
+            n += 1
+    assert n >= 2
+
+
+def test_raw2outputs_transmittance_matches_f64_scan(ops):
+    """Weights must follow ATen's float64-accumulated cumprod exactly given identical alphas:
+    a long ray (S=256) with small alphas exposes float32-scan drift."""
+    rng = np.random.RandomState(5)
+    S = 256
+    raw = np.abs(rng.randn(64, S, 1)).astype(np.float32) * 0.05
+    z = np.sort(rng.rand(64, S).astype(np.float32) * 20, -1)
+    want = O.raw2outputs_nerfw(raw, z, test_time=True, typ="coarse")["weights"]
+    got = ops.raw2outputs(T(raw), T(z), "coarse", True)["weights"].cpu().numpy()
+    assert np.allclose(got, want, rtol=3e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("tag,D,W", [("s", 4, 64), ("b", 8, 256)])
+def test_nerfw_forward_fp32(ops, golden, tag, D, W):
+    (c, f, ea, et), _ = synthetic_nets(D, W)
+    h = ops.NerfHandle(*to_dev([c, f, ea, et]))
+    x = T(golden[f"mlp_{tag}_x"])
+    s = h.nerfw_forward(0, 0, x[:, :63].contiguous())
+    assert rel_err(s.cpu().numpy(), golden[f"mlp_{tag}_sigma_only"]) < 5e-5
+    st = h.nerfw_forward(0, 1, x[:, :90].contiguous())
+    assert rel_err(st.cpu().numpy(), golden[f"mlp_{tag}_coarse_static"]) < 5e-5
+    full = h.nerfw_forward(1, 2, x)
+    assert rel_err(full.cpu().numpy(), golden[f"mlp_{tag}_fine_full"]) < 5e-5
+
+
+def test_nerfw_module_forward_uses_cuda_path(ops, golden):
+    (c, f, ea, et), _ = synthetic_nets(4, 64)
+    c, f = to_dev([c, f])
+    x = T(golden["mlp_s_x"])
+    before = ops.lib.dfb_launch_count()
+    out = f(x, output_transient=True)
+    assert ops.lib.dfb_launch_count() > before
+    assert rel_err(out.cpu().numpy(), golden["mlp_s_fine_full"]) < 5e-5
+    out = c(x[:, :63].contiguous(), sigma_only=True)
+    assert rel_err(out.cpu().numpy(), golden["mlp_s_sigma_only"]) < 5e-5
+
+
+def _render_kwargs(mods, Nc, Nf, test_time, perturb=0.0):
+    c, f, ea, et = to_dev(mods)
+    return dict(network_query_fn=None, perturb=perturb, N_importance=Nf, network_fine=f, N_samples=Nc, network_fn=c,
+                use_viewdirs=True, white_bkgd=False, raw_noise_std=0.0, embedding_a=ea, embedding_t=et,
+                test_time=test_time, ndc=False, lindisp=False)
+
+
+def test_render_cfg1_shape_fp32(golden):
+    """BASELINE config[0] shape: coarse-only 4x64 network, train-mode path."""
+    from dfnet_b200 import rendering
+    mods, _ = synthetic_nets(4, 64, fine=False)
+    kw = _render_kwargs(mods, 64, 0, False)
+    rgb, disp, acc, ex = rendering.render(8, 8, 8.0, c2w=T(golden["e2e_a_c2w"]), img_idx=T(golden["hist"]),
+                                          near=0.0, far=2.5, mma="fp32", **kw)
+    assert rgb.shape == (8, 8, 3) and disp.shape == (8, 8)
+    assert rel_err(rgb.cpu().numpy(), golden["e2e_a_rgb"]) < 1e-4
+    assert rel_err(disp.cpu().numpy(), golden["e2e_a_disp"]) < 1e-4
+    assert rel_err(acc.cpu().numpy(), golden["e2e_a_acc"]) < 1e-4
+
+
+@pytest.mark.parametrize("mma,tol,flip_tol", [("fp32", 1e-4, 0.01), ("f16", 1e-3, 0.05), ("bf16", 1e-2, 0.2)])
+def test_render_cfg2_shape(ops, golden, mma, tol, flip_tol):
+    """BASELINE config[1] shape (8x256, 64+128, test_time) on a 6x8 image, all precisions."""
+    mods, _ = synthetic_nets(8, 256)
+    h = ops.NerfHandle(*to_dev(mods))
+    o = h.render(64, 128, True, c2w=T(golden["e2e_b_c2w"]), H=6, W=8, focal=7.3125, near=0.0, far=2.5,
+                 hist=T(golden["hist"]), mma=mma, want=("inds", "z_samples", "weights_coarse", "z_vals"))
+    torch.cuda.synchronize()
+    assert rel_err(o["rgb"].cpu().numpy().reshape(6, 8, 3), golden["e2e_b_rgb"]) < tol
+    assert rel_err(o["disp"].cpu().numpy().reshape(6, 8), golden["e2e_b_disp"]) < tol
+    assert rel_err(o["acc"].cpu().numpy().reshape(6, 8), golden["e2e_b_acc"]) < tol
+    inds = o["inds"].cpu().numpy()
+    flips = (inds != golden["e2e_b_inds"]).mean()
+    assert flips < flip_tol, flips
+    # the sampler must be bit-exact on ITS OWN coarse weights (op-level gate for the index claim)
+    zc = np.broadcast_to(O.linspace_f32(0, 1, 64)[None] * np.float32(2.5), (48, 64))
+    _, io = O.sample_pdf(0.5 * (zc[:, 1:] + zc[:, :-1]), o["weights_coarse"].cpu().numpy()[:, 1:-1], 128, det=True)
+    assert np.array_equal(inds, io)
+    z = o["z_vals"].cpu().numpy()
+    assert (np.diff(z, axis=-1) >= 0).all()
+
+
+def test_render_train_mode_extras_fp32(golden):
+    from dfnet_b200 import rendering
+    mods, _ = synthetic_nets(8, 64)
+    kw = _render_kwargs(mods, 16, 24, False)
+    rays = T(golden["e2e_c_rays"])
+    rgb, disp, acc, ex = rendering.render(4, 6, 5.0, rays=(rays[0], rays[1]), img_idx=T(golden["hist"]), near=0.0,
+                                          far=2.5, retraw=True, mma="fp32", **kw)
+    got = dict(rgb=rgb, disp=disp, acc=acc, **ex)
+    for k in ["rgb", "disp", "acc", "rgb0", "disp0", "acc0", "z_std", "transient_sigmas", "beta", "raw"]:
+        assert rel_err(got[k].cpu().numpy(), golden[f"e2e_c_{k}"]) < 1e-4, k
+
+
+def test_render_stratified_with_reference_draws(ops, golden):
+    mods, _ = synthetic_nets(8, 64)
+    h = ops.NerfHandle(*to_dev(mods))
+    rays = golden["e2e_c_rays"]
+    rec = O.make_ray_records(rays[0], rays[1], 0.0, 2.5, golden["hist"])
+    o = h.render(16, 24, False, rays=T(rec), perturb=True, t_rand=T(golden["e2e_d_t_rand"]), u=T(golden["e2e_d_u"]),
+                 mma="fp32", want=("rgb0", "beta", "z_std", "inds"))
+    for k, g in [("rgb", "rgb"), ("disp", "disp"), ("acc", "acc"), ("rgb0", "rgb0"), ("beta", "beta"),
+                 ("z_std", "z_std")]:
+        assert rel_err(o[k].cpu().numpy(), golden[f"e2e_d_{g}"]) < 1e-4, k
+    assert (o["inds"].cpu().numpy() != golden["e2e_d_inds"]).mean() < 0.01
+
+
+def test_render_error_behaviour(ops):
+    mods, _ = synthetic_nets(4, 64, fine=False)
+    h = ops.NerfHandle(*to_dev(mods))
+    from dfnet_b200._lib import DfbError
+    with pytest.raises(DfbError):  # reference returns rgb_map=None here and crashes
+        h.render(64, 0, True, c2w=torch.eye(4, device=dev())[:3], H=2, W=2, focal=1.0, hist=torch.zeros(10), mma="fp32")
+    with pytest.raises(DfbError):  # no fine network loaded
+        h.render(64, 16, True, c2w=torch.eye(4, device=dev())[:3], H=2, W=2, focal=1.0, hist=torch.zeros(10), mma="fp32")
