@@ -254,8 +254,8 @@ extern "C" int dfb_render_image_host(DfbNerf* n, const DfbRenderCfg* c, const fl
 
 extern "C" int dfb_sample_pdf(const float* bins, const float* weights, const float* u, int64_t N, int n_bins, int Nf,
                               float* samples, int32_t* inds, void* stream) {
-  DFB_REQUIRE(bins && weights && (samples || inds), DFB_ERR_INVALID, "null argument");
   if (N == 0) return DFB_OK;
+  DFB_REQUIRE(bins && weights && (samples || inds), DFB_ERR_INVALID, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
   float* d_lin = nullptr;
   if (!u) {
@@ -276,6 +276,7 @@ extern "C" int dfb_sample_pdf(const float* bins, const float* weights, const flo
 extern "C" int dfb_raw2outputs(const float* raw, const float* z_vals, int64_t N, int S, int C, int typ, int test_time,
                                float beta_min, float* rgb, float* disp, float* acc, float* weights, float* depth,
                                float* transient_sigmas, float* beta, void* stream) {
+  if (N == 0) return DFB_OK;
   DFB_REQUIRE(raw && z_vals, DFB_ERR_INVALID, "null argument");
   DFB_REQUIRE(C == 1 || C == 4 || C == 9, DFB_ERR_INVALID, "raw must have 1, 4 or 9 channels");
   DFB_REQUIRE((typ == 1) == (C == 9), DFB_ERR_INVALID, "fine compositing takes 9 channels, coarse 1 or 4");

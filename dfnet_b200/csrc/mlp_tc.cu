@@ -1,11 +1,646 @@
-// tcgen05 NeRF-W MLP — placeholder until the tensor-core kernel lands.
+// tcgen05 NeRF-W MLP for the 8x256 networks (BASELINE config[1]/[4]): a persistent,
+// warp-specialised kernel.  Each CTA owns all 512 TMEM columns and works on two 128-sample
+// tiles ("slots") that alternate between the tensor pipe and the epilogue warps:
+//
+//   warp 12      weight producer : cp.async.bulk (TMA) of pre-packed 16 KB weight chunks from
+//                                  L2 into a 4-stage shared-memory ring, mbarrier complete_tx
+//   warp 13      MMA issuer      : one thread issues tcgen05.mma.cta_group::1.kind::f16
+//                                  (M=128, N=256|128, K=16) with A = activations in shared memory,
+//                                  B = weight chunk, D = fp32 accumulators in TMEM; tcgen05.commit
+//                                  releases ring stages and publishes finished layers
+//   warps 0-3    epilogue slot 0 : tcgen05.ld 32x32b (thread = sample row), bias/ReLU in fp32,
+//   warps 4-7    epilogue slot 1   pack to fp16/bf16 and store the next layer's A operand in place;
+//                                  sigma / rgb / transient heads are fp32 dot products in registers
+//   warps 8-11   encoder         : pts = o + d*z and the 63-wide positional encoding of the NEXT
+//                                  pass's tiles, written straight into the A-operand layout
+//
+// Operand layout (both A and B): K-major, no swizzle, "core-matrix panels": a panel holds 8
+// consecutive K elements for every row, 16 bytes per row, rows contiguous (SBO = 128 B between
+// 8-row groups, LBO = rows*16 B between the two K-halves of one K=16 MMA).  An epilogue thread
+// therefore stores 16 B at panel*2048 + row*16: consecutive rows -> consecutive addresses, no
+// bank conflicts, and the host packs weights into the identical image so a chunk is ONE linear
+// bulk copy (no tensor map needed).
+//
+// Reference arithmetic: models/nerfw.py:297-354 (NeRFW.forward), :105-133 (embedding),
+// models/rendering.py:287,305 (pts).  Per-ray constant inputs (view-direction encoding,
+// appearance and transient codes) enter as a per-ray bias computed by k_raybias.
+#include <string.h>
+
+#include <algorithm>
+#include <type_traits>
+
 #include "common.cuh"
+
 namespace dfb {
-bool tc_supported(const DfbNerf*, int, int) { return false; }
-int pack_tc_weights(DfbNerf*, int, const std::vector<std::vector<float>>&) { return DFB_OK; }
-int launch_mlp_tc_rays(const DfbNerf*, int, int, int, const float*, const float*, const float*, int64_t, int, float*,
-                       cudaStream_t) {
-  set_error("tcgen05 MLP not built");
-  return DFB_ERR_UNSUPPORTED;
+namespace tc {
+
+constexpr int kTileM = 128;
+constexpr int kStages = 4;
+constexpr int kChunkBytes = 16384;
+constexpr int kPanelBytes = kTileM * 16;  // 2048
+constexpr int kHPanels = 32;              // 256 hidden columns
+constexpr int kPePanels = 8;              // 64 positional-encoding columns (63 + zero pad)
+constexpr int kSlotBytes = (kHPanels + kPePanels) * kPanelBytes;  // 81920
+constexpr int kSmemA = 2 * kSlotBytes;
+constexpr int kSmemW = kStages * kChunkBytes;
+constexpr int kSmemBar = 256;
+constexpr int kSmemTotal = kSmemA + kSmemW + kSmemBar;  // 229632 B
+constexpr int kThreads = 448;
+constexpr int kMaxSteps = 13;
+
+// barrier slots (8 bytes each) inside the kSmemBar region
+enum Bar { W_FULL = 0, W_EMPTY = 4, D_FULL = 8, A_READY = 10, PASS_DONE = 12, PE_READY = 14, PE_FREE = 16, N_BARS = 18 };
+
+struct Step {
+  int n_chunks;    // 16 KB weight chunks streamed for this step
+  int ksteps;      // K=16 MMA steps per chunk
+  int n;           // MMA N (256 or 128)
+  int a_panel0;    // first A-operand panel of the step
+  int chunk_base;  // index of the step's first chunk in the packed weight image
+};
+
+struct TcArgs {
+  Step steps[kMaxSteps];
+  int n_steps;
+  int last_pe_step;       // last step that reads the PE panels (skip layer)
+  const void* wimg;       // packed 16-bit weight image, chunk i at wimg + i*16 KB
+  const float* blob;      // fp32 biases / head weights (NetPack::blob32)
+  uint32_t bias_off[kMaxSteps];  // float offsets into blob; 0xffffffff = none (ray bias instead)
+  uint32_t sigma_w, sigma_b, rgb_w, rgb_b, tsig_w, tsig_b, trgb_w, trgb_b, tbeta_w, tbeta_b;
+  const float* rayrec;    // [n_rays,12]
+  const float* z;         // [n_rays,S]
+  const float* raybias;   // [n_rays,256] (fine) or null
+  int S;
+  int64_t P;              // n_rays * S
+  int64_t n_pass;         // ceil(tiles / 2)
+  float* raw;             // [P,1] or [P,9]
+  int* error_flag;
+};
+
+// ---------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ uint64_t globaltimer() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a protocol bug must fail the launch, not hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* error_flag) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = globaltimer();
+  while (!mbar_try_wait(bar, parity)) {
+    if (globaltimer() - t0 > 4000000000ull) {  // 4 s
+      if (error_flag) atomicExch(error_flag, 1 + (int)(bar & 0xff));
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16 (fp16 or bf16 operands, fp32 accumulate)
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1).
+//   lbo: byte distance between the two 8-element K halves of a K=16 slice
+//   sbo: byte distance between consecutive 8-row groups
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version for sm_100
+  return d;                // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
+}
+// cute::UMMA::InstrDescriptor: fp32 accumulate, A/B K-major, dense
+__device__ __forceinline__ uint32_t make_idesc(int fmt /*0 f16, 1 bf16*/, int n, int m) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+// ---------------------------------------------------------------------------------------
+// epilogue building block: one 32-column block of the accumulator row of this thread
+// ---------------------------------------------------------------------------------------
+enum EpiKind { EPI_HIDDEN, EPI_HIDDEN_SIGMA, EPI_SIGMA_ONLY, EPI_FINAL, EPI_DT, EPI_T, EPI_T_LAST };
+
+template <typename T, int FULL>
+__global__ void __launch_bounds__(kThreads, 1) k_mlp_tc(const __grid_constant__ TcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sA = smem_u32(smem);
+  const uint32_t sW = sA + kSmemA;
+  const uint32_t sBar = sW + kSmemW;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmemA + kSmemW + N_BARS * 8);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  auto bar = [&](int i) { return sBar + 8u * i; };
+  const int fmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
+
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) mbar_init(bar(W_FULL + i), 1), mbar_init(bar(W_EMPTY + i), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar(D_FULL + s), 1);
+      mbar_init(bar(A_READY + s), 128);
+      mbar_init(bar(PASS_DONE + s), 128);
+      mbar_init(bar(PE_READY + s), 128);
+      mbar_init(bar(PE_FREE + s), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 13) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_steps = a.n_steps;
+
+  if (warp == 12) {
+    // ===== weight producer ================================================================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int64_t p = blockIdx.x; p < a.n_pass; p += gridDim.x)
+        for (int s = 0; s < n_steps; ++s)
+          for (int slot = 0; slot < 2; ++slot)
+            for (int c = 0; c < a.steps[s].n_chunks; ++c) {
+              mbar_wait(bar(W_EMPTY + stage), phase ^ 1, a.error_flag);
+              mbar_expect_tx(bar(W_FULL + stage), kChunkBytes);
+              bulk_g2s(sW + stage * kChunkBytes,
+                       reinterpret_cast<const uint8_t*>(a.wimg) + (size_t)(a.steps[s].chunk_base + c) * kChunkBytes,
+                       kChunkBytes, bar(W_FULL + stage));
+              if (++stage == kStages) stage = 0, phase ^= 1;
+            }
+    }
+  } else if (warp == 13) {
+    // ===== MMA issuer =======================================================================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      int lp = 0;
+      for (int64_t p = blockIdx.x; p < a.n_pass; p += gridDim.x, ++lp)
+        for (int s = 0; s < n_steps; ++s) {
+          const Step st = a.steps[s];
+          const uint32_t idesc = make_idesc(fmt, st.n, kTileM);
+          const uint32_t b_lbo = st.n * 16;
+          for (int slot = 0; slot < 2; ++slot) {
+            if (s == 0) {
+              if (lp > 0) mbar_wait(bar(PASS_DONE + slot), (lp - 1) & 1, a.error_flag);
+              mbar_wait(bar(PE_READY + slot), lp & 1, a.error_flag);
+            } else {
+              mbar_wait(bar(A_READY + slot), (lp * (n_steps - 1) + s - 1) & 1, a.error_flag);
+            }
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + slot * 256;
+            const uint32_t a_base = sA + slot * kSlotBytes + st.a_panel0 * kPanelBytes;
+            int kg = 0;
+            for (int c = 0; c < st.n_chunks; ++c) {
+              mbar_wait(bar(W_FULL + stage), phase, a.error_flag);
+              tc_fence_after();
+              const uint32_t b_base = sW + stage * kChunkBytes;
+              for (int ks = 0; ks < st.ksteps; ++ks, ++kg) {
+                const uint64_t ad = make_desc(a_base + kg * 2 * kPanelBytes, kPanelBytes, 128);
+                const uint64_t bd = make_desc(b_base + ks * 2 * b_lbo, b_lbo, 128);
+                umma_f16(d_tmem, ad, bd, idesc, kg > 0 ? 1u : 0u);
+              }
+              umma_commit(bar(W_EMPTY + stage));
+              if (++stage == kStages) stage = 0, phase ^= 1;
+            }
+            umma_commit(bar(D_FULL + slot));
+            if (s == a.last_pe_step) umma_commit(bar(PE_FREE + slot));
+          }
+        }
+    }
+  } else if (warp >= 8) {
+    // ===== encoder: positional encoding of the next pass (nerfw.py:128-133) =================
+    const int r = tid - 256;
+    int lp = 0;
+    for (int64_t p = blockIdx.x; p < a.n_pass; p += gridDim.x, ++lp)
+      for (int slot = 0; slot < 2; ++slot) {
+        if (lp > 0) mbar_wait(bar(PE_FREE + slot), (lp - 1) & 1, a.error_flag);
+        int64_t g = (2 * p + slot) * kTileM + r;
+        g = g < a.P ? g : a.P - 1;
+        const int64_t ray = g / a.S;
+        const float* rr = a.rayrec + ray * kRayRec;
+        const float zz = __ldg(a.z + g);
+        float pt[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) pt[c] = __fadd_rn(__ldg(rr + c), __fmul_rn(__ldg(rr + 3 + c), zz));
+        float e[64];
+        e[0] = pt[0], e[1] = pt[1], e[2] = pt[2], e[63] = 0.f;
+#pragma unroll
+        for (int l = 0; l < 10; ++l)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float sn, cs;
+            sincosf(__fmul_rn(pt[c], (float)(1 << l)), &sn, &cs);
+            e[3 + 6 * l + c] = sn;
+            e[3 + 6 * l + 3 + c] = cs;
+          }
+        const uint32_t dst = sA + slot * kSlotBytes + kHPanels * kPanelBytes + r * 16;
+#pragma unroll
+        for (int q = 0; q < kPePanels; ++q)
+          st_shared_v4(dst + q * kPanelBytes, pack2<T>(e[8 * q], e[8 * q + 1]), pack2<T>(e[8 * q + 2], e[8 * q + 3]),
+                       pack2<T>(e[8 * q + 4], e[8 * q + 5]), pack2<T>(e[8 * q + 6], e[8 * q + 7]));
+        fence_proxy_async();
+        mbar_arrive(bar(PE_READY + slot));
+      }
+  } else {
+    // ===== epilogue warpgroups (thread = accumulator row = sample) ===========================
+    const int slot = warp >> 2;
+    const int r = tid & 127;
+    const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + slot * 256;
+    const uint32_t h_row = sA + slot * kSlotBytes + r * 16;
+    const float* B = a.blob;
+    uint32_t nd = 0;
+    for (int64_t p = blockIdx.x; p < a.n_pass; p += gridDim.x) {
+      const int64_t g = (2 * p + slot) * kTileM + r;
+      const bool valid = g < a.P;
+      const int64_t ray = (valid ? g : a.P - 1) / a.S;
+      const float* rb = FULL ? a.raybias + ray * 256 : nullptr;
+      float sig = 0.f, rgb[3] = {0.f, 0.f, 0.f}, hd[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int s = 0; s < n_steps; ++s) {
+        EpiKind kind;
+        if (!FULL) kind = s == 7 ? EPI_SIGMA_ONLY : EPI_HIDDEN;
+        else kind = s < 7 ? EPI_HIDDEN : s == 7 ? EPI_HIDDEN_SIGMA : s == 8 ? EPI_FINAL : s == 9 ? EPI_DT
+                    : s < 12 ? EPI_T : EPI_T_LAST;
+        const int nblk = a.steps[s].n / 32;
+        const float* bias = a.bias_off[s] != 0xffffffffu ? B + a.bias_off[s] : nullptr;
+        mbar_wait(bar(D_FULL + slot), nd & 1, a.error_flag);
+        ++nd;
+        tc_fence_after();
+        for (int cb = 0; cb < nblk; ++cb) {
+          uint32_t v[32];
+          tmem_ld32(t_row + cb * 32, v);
+          tmem_ld_wait();
+          float x[32];
+          const float4* b4 = reinterpret_cast<const float4*>((kind == EPI_DT ? rb : bias) + cb * 32);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 bb = __ldg(b4 + q);
+            x[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + bb.x;
+            x[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + bb.y;
+            x[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bb.z;
+            x[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bb.w;
+          }
+          if (kind != EPI_FINAL) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+          }
+          if (kind == EPI_HIDDEN_SIGMA || kind == EPI_SIGMA_ONLY) {
+            const float4* w4 = reinterpret_cast<const float4*>(B + a.sigma_w + cb * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 w = __ldg(w4 + q);
+              sig = fmaf(x[4 * q], w.x, sig), sig = fmaf(x[4 * q + 1], w.y, sig);
+              sig = fmaf(x[4 * q + 2], w.z, sig), sig = fmaf(x[4 * q + 3], w.w, sig);
+            }
+          }
+          if (kind == EPI_DT && cb < 4) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const float4* w4 = reinterpret_cast<const float4*>(B + a.rgb_w + c * 128 + cb * 32);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 w = __ldg(w4 + q);
+                rgb[c] = fmaf(x[4 * q], w.x, rgb[c]), rgb[c] = fmaf(x[4 * q + 1], w.y, rgb[c]);
+                rgb[c] = fmaf(x[4 * q + 2], w.z, rgb[c]), rgb[c] = fmaf(x[4 * q + 3], w.w, rgb[c]);
+              }
+            }
+          }
+          if (kind == EPI_T_LAST) {
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+              const uint32_t off = c < 3 ? a.trgb_w + c * 128 : (c == 3 ? a.tsig_w : a.tbeta_w);
+              const float4* w4 = reinterpret_cast<const float4*>(B + off + cb * 32);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 w = __ldg(w4 + q);
+                hd[c] = fmaf(x[4 * q], w.x, hd[c]), hd[c] = fmaf(x[4 * q + 1], w.y, hd[c]);
+                hd[c] = fmaf(x[4 * q + 2], w.z, hd[c]), hd[c] = fmaf(x[4 * q + 3], w.w, hd[c]);
+              }
+            }
+          }
+          const bool store = kind == EPI_HIDDEN || kind == EPI_HIDDEN_SIGMA || kind == EPI_FINAL || kind == EPI_T ||
+                             (kind == EPI_DT && cb >= 4);
+          if (store) {
+            const int panel0 = (kind == EPI_DT ? cb - 4 : cb) * 4;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              st_shared_v4(h_row + (panel0 + q) * kPanelBytes, pack2<T>(x[8 * q], x[8 * q + 1]),
+                           pack2<T>(x[8 * q + 2], x[8 * q + 3]), pack2<T>(x[8 * q + 4], x[8 * q + 5]),
+                           pack2<T>(x[8 * q + 6], x[8 * q + 7]));
+          }
+        }
+        if (kind == EPI_HIDDEN_SIGMA || kind == EPI_SIGMA_ONLY) sig = softplus_f(sig + __ldg(B + a.sigma_b));
+        if (kind == EPI_SIGMA_ONLY && valid) a.raw[g] = sig;
+        if (kind == EPI_T_LAST && valid) {
+          float* o = a.raw + g * 9;
+          o[0] = sigmoid_f(rgb[0] + __ldg(B + a.rgb_b)), o[1] = sigmoid_f(rgb[1] + __ldg(B + a.rgb_b + 1));
+          o[2] = sigmoid_f(rgb[2] + __ldg(B + a.rgb_b + 2)), o[3] = sig;
+          o[4] = sigmoid_f(hd[0] + __ldg(B + a.trgb_b)), o[5] = sigmoid_f(hd[1] + __ldg(B + a.trgb_b + 1));
+          o[6] = sigmoid_f(hd[2] + __ldg(B + a.trgb_b + 2));
+          o[7] = softplus_f(hd[3] + __ldg(B + a.tsig_b)), o[8] = softplus_f(hd[4] + __ldg(B + a.tbeta_b));
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        mbar_arrive(bar((s + 1 < n_steps ? A_READY : PASS_DONE) + slot));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 13) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// single-tile UMMA self test: D[128,N] = A[128,K] * B[N,K]^T through the same descriptors
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128, 1) k_umma_selftest(const float* A, const float* Bm, int N, int K, int variant,
+                                                            float* D, int* error_flag) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t tslot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  T* sAm = reinterpret_cast<T*>(smem);                       // [K/8 panels][128 rows][8]
+  T* sBm = reinterpret_cast<T*>(smem + (size_t)K * 128 * 2);  // [K/8 panels][N rows][8]
+  for (int i = tid; i < 128 * K; i += 128) {
+    const int row = i / K, k = i % K;
+    sAm[(size_t)(k / 8) * 128 * 8 + row * 8 + k % 8] = (T)A[i];
+  }
+  for (int i = tid; i < N * K; i += 128) {
+    const int row = i / K, k = i % K;
+    sBm[(size_t)(k / 8) * N * 8 + row * 8 + k % 8] = (T)Bm[i];
+  }
+  if (tid == 0) { mbar_init(smem_u32(&mbar), 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(smem_u32(&tslot), 256);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tslot;
+  const int fmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc(fmt, N, 128);
+    for (int ks = 0; ks < K / 16; ++ks) {
+      const uint32_t a_addr = smem_u32(sAm) + ks * 2 * 2048, b_addr = smem_u32(sBm) + ks * 2 * (N * 16);
+      uint64_t ad, bd;
+      if (variant == 0) ad = make_desc(a_addr, 2048, 128), bd = make_desc(b_addr, N * 16, 128);
+      else ad = make_desc(a_addr, 128, 2048), bd = make_desc(b_addr, 128, N * 16);
+      umma_f16(tb, ad, bd, idesc, ks > 0);
+    }
+    umma_commit(smem_u32(&mbar));
+  }
+  mbar_wait(smem_u32(&mbar), 0, error_flag);
+  tc_fence_after();
+  for (int cb = 0; cb < N / 32; ++cb) {
+    uint32_t v[32];
+    tmem_ld32(tb + ((uint32_t)(warp * 32) << 16) + cb * 32, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j) D[(size_t)tid * N + cb * 32 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tb, 256); }
+}
+
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------------
+// host side: weight image, step tables, launch
+// ---------------------------------------------------------------------------------------
+namespace {
+
+struct HostStep { int K, N, a_panel0; };
+
+// 16-bit conversions on the host (round to nearest even), independent of device intrinsics
+uint16_t f2h(float f) { __half h = __float2half_rn(f); uint16_t u; memcpy(&u, &h, 2); return u; }
+uint16_t f2b(float f) { __nv_bfloat16 h = __float2bfloat16_rn(f); uint16_t u; memcpy(&u, &h, 2); return u; }
+
+}  // namespace
+
+bool tc_supported(const DfbNerf* n, int which, int mode) {
+  const NetPack& np = n->net[which];
+  if (!np.loaded || np.W != 256 || np.D != 8 || np.skip != 4 || np.pek != 64) return false;
+  if (np.blob16[0] == nullptr || np.blob16[1] == nullptr) return false;
+  if (mode == MLP_SIGMA) return true;
+  if (mode == MLP_FULL) return np.fine;
+  return false;  // MLP_STATIC (train-mode coarse pass) runs on the fp32 path
+}
+
+// Pack the network into the streaming order of the kernel: for every step, K is cut into
+// 16 KB chunks ([K/8 panels][N rows][8 elements]); see the layout note at the top of the file.
+int pack_tc_weights(DfbNerf* n, int which, const std::vector<std::vector<float>>& P) {
+  NetPack& np = n->net[which];
+  for (int k = 0; k < 2; ++k)
+    if (np.blob16[k]) { cudaFree(np.blob16[k]); np.blob16[k] = nullptr; }
+  if (np.W != 256 || np.D != 8 || np.skip != 4 || np.pek != 64) return DFB_OK;  // SIMT only
+  const int W = 256, H = 128, in_xyz = np.in_xyz;
+  const bool fine = np.fine;
+  // value of the logical weight matrix of step s at (n, k)
+  auto wval = [&](int s, int nn, int k) -> float {
+    if (s == 0) return k < in_xyz ? P[0][(size_t)nn * in_xyz + k] : 0.f;
+    if (s < 8) {
+      if (s == 4) {  // K order [h(256) | pe(64)]; torch order is cat([input_xyz, h])
+        if (k < W) return P[8][(size_t)nn * (W + in_xyz) + in_xyz + k];
+        const int c = k - W;
+        return c < in_xyz ? P[8][(size_t)nn * (W + in_xyz) + c] : 0.f;
+      }
+      return P[2 * s][(size_t)nn * W + k];
+    }
+    if (s == 8) return P[16][(size_t)nn * W + k];  // xyz_encoding_final
+    if (s == 9) {                                  // dir_encoding[:, :W] | transient_encoding.0[:, :W]
+      if (nn < H) return P[18][(size_t)nn * (W + np.in_dir + np.a_dim) + k];
+      return P[24][(size_t)(nn - H) * (W + np.t_dim) + k];
+    }
+    return P[26 + 2 * (s - 10)][(size_t)nn * H + k];  // transient_encoding.{2,4,6}
+  };
+  const int n_steps = fine ? 13 : 8;
+  std::vector<HostStep> hs;
+  for (int s = 0; s < n_steps; ++s) {
+    HostStep h;
+    h.K = s == 0 ? 64 : (s == 4 ? 320 : (s >= 10 ? 128 : 256));
+    h.N = s >= 10 ? 128 : 256;
+    h.a_panel0 = s == 0 ? 32 : 0;
+    hs.push_back(h);
+  }
+  size_t total_chunks = 0;
+  for (auto& h : hs) total_chunks += (size_t)h.K * h.N * 2 / tc::kChunkBytes;
+  std::vector<uint16_t> img16[2];
+  img16[0].assign(total_chunks * tc::kChunkBytes / 2, 0);
+  img16[1].assign(total_chunks * tc::kChunkBytes / 2, 0);
+  size_t chunk = 0;
+  for (int s = 0; s < n_steps; ++s) {
+    const HostStep& h = hs[s];
+    const int kc = tc::kChunkBytes / (h.N * 2);  // K columns per chunk: 32 (N=256) or 64 (N=128)
+    for (int k0 = 0; k0 < h.K; k0 += kc, ++chunk) {
+      const size_t base = chunk * (tc::kChunkBytes / 2);
+      for (int kk = 0; kk < kc; ++kk)
+        for (int nn = 0; nn < h.N; ++nn) {
+          const float v = wval(s, nn, k0 + kk);
+          const size_t idx = base + (size_t)(kk / 8) * h.N * 8 + (size_t)nn * 8 + kk % 8;
+          img16[0][idx] = f2h(v);
+          img16[1][idx] = f2b(v);
+        }
+    }
+  }
+  np.blob16_bytes = total_chunks * tc::kChunkBytes;
+  for (int k = 0; k < 2; ++k) {
+    DFB_CHECK_CUDA(cudaMalloc(&np.blob16[k], np.blob16_bytes));
+    DFB_CHECK_CUDA(cudaMemcpy(np.blob16[k], img16[k].data(), np.blob16_bytes, cudaMemcpyHostToDevice));
+  }
+  return DFB_OK;
+}
+
+static int* g_error_flag = nullptr;
+
+int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const float* rayrec, const float* z,
+                       const float* raybias, int64_t n_rays, int S, float* raw, cudaStream_t st) {
+  const NetPack& np = nerf->net[which];
+  DFB_REQUIRE(tc_supported(nerf, which, mode), DFB_ERR_UNSUPPORTED, "network shape not supported by the tcgen05 kernel");
+  DFB_REQUIRE(kind == DFB_MMA_F16 || kind == DFB_MMA_BF16, DFB_ERR_INVALID, "bad mma kind");
+  const bool full = mode == MLP_FULL;
+  DFB_REQUIRE(!full || raybias, DFB_ERR_INVALID, "ray-constant inputs missing");
+  if (!g_error_flag) {
+    DFB_CHECK_CUDA(cudaMalloc(&g_error_flag, sizeof(int)));
+    DFB_CHECK_CUDA(cudaMemset(g_error_flag, 0, sizeof(int)));
+  }
+  tc::TcArgs a = {};
+  a.n_steps = full ? 13 : 8;
+  a.last_pe_step = 4;
+  int cb = 0;
+  for (int s = 0; s < a.n_steps; ++s) {
+    const int K = s == 0 ? 64 : (s == 4 ? 320 : (s >= 10 ? 128 : 256));
+    const int N = s >= 10 ? 128 : 256;
+    const int kc = tc::kChunkBytes / (N * 2);
+    a.steps[s].n_chunks = K / kc;
+    a.steps[s].ksteps = kc / 16;
+    a.steps[s].n = N;
+    a.steps[s].a_panel0 = s == 0 ? 32 : 0;
+    a.steps[s].chunk_base = cb;
+    cb += K / kc;
+    a.bias_off[s] = s < 8 ? (uint32_t)np.trunk_b[s] : s == 8 ? (uint32_t)np.final_b : s == 9 ? 0xffffffffu
+                                                                                            : (uint32_t)np.t_b[s - 10];
+  }
+  a.wimg = np.blob16[kind == DFB_MMA_F16 ? 0 : 1];
+  a.blob = np.blob32;
+  a.sigma_w = np.sigma_w, a.sigma_b = np.sigma_b, a.rgb_w = np.rgb_w, a.rgb_b = np.rgb_b;
+  a.tsig_w = np.tsig_w, a.tsig_b = np.tsig_b, a.trgb_w = np.trgb_w, a.trgb_b = np.trgb_b;
+  a.tbeta_w = np.tbeta_w, a.tbeta_b = np.tbeta_b;
+  a.rayrec = rayrec, a.z = z, a.raybias = raybias, a.S = S, a.P = n_rays * S, a.raw = raw;
+  a.error_flag = g_error_flag;
+  if (a.P == 0) return DFB_OK;
+  const int64_t tiles = (a.P + tc::kTileM - 1) / tc::kTileM;
+  a.n_pass = (tiles + 1) / 2;
+  const int grid = (int)std::min<int64_t>(a.n_pass, nerf->num_sms);
+  auto launch = [&](auto kern) -> int {
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal));
+    kern<<<grid, tc::kThreads, tc::kSmemTotal, st>>>(a);
+    DFB_LAUNCH_CHECK();
+    return DFB_OK;
+  };
+  if (kind == DFB_MMA_F16) return full ? launch(tc::k_mlp_tc<__half, 1>) : launch(tc::k_mlp_tc<__half, 0>);
+  return full ? launch(tc::k_mlp_tc<__nv_bfloat16, 1>) : launch(tc::k_mlp_tc<__nv_bfloat16, 0>);
+}
+
 }  // namespace dfb
+
+// Debug seam (not used by the product path): single-tile UMMA GEMM through the same descriptor
+// and TMEM code as the MLP kernel.  variant 0 is the layout the kernel uses.
+extern "C" int dfb_debug_umma_gemm(const float* A, const float* B, int N, int K, int kind, int variant, float* D,
+                                   void* stream) {
+  using namespace dfb;
+  DFB_REQUIRE(A && B && D, DFB_ERR_INVALID, "null argument");
+  DFB_REQUIRE(N % 32 == 0 && N >= 32 && N <= 256 && K % 16 == 0 && K >= 16 && K <= 320, DFB_ERR_INVALID, "bad N/K");
+  int* flag = nullptr;
+  DFB_CHECK_CUDA(cudaMalloc(&flag, 4));
+  DFB_CHECK_CUDA(cudaMemset(flag, 0, 4));
+  const size_t smem = (size_t)K * 128 * 2 + (size_t)K * N * 2;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (kind == DFB_MMA_BF16) {
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(tc::k_umma_selftest<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc::k_umma_selftest<__nv_bfloat16><<<1, 128, smem, st>>>(A, B, N, K, variant, D, flag);
+  } else {
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(tc::k_umma_selftest<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc::k_umma_selftest<__half><<<1, 128, smem, st>>>(A, B, N, K, variant, D, flag);
+  }
+  DFB_LAUNCH_CHECK();
+  DFB_CHECK_CUDA(cudaStreamSynchronize(st));
+  cudaFree(flag);
+  return DFB_OK;
+}

@@ -162,6 +162,11 @@ int64_t dfb_launch_count(void);
 int dfb_profile_enable(int on);
 int dfb_profile_read(double* coarse_ms, double* fine_ms, int64_t* coarse_launches, int64_t* fine_launches);
 
+/* Debug seam, not on the product path: D[128,N] = A[128,K] * B[N,K]^T on one CTA through the
+ * same shared-memory descriptors, tcgen05.mma and TMEM loads as the MLP kernel (fp32 in/out,
+ * operands rounded to `kind`).  variant 0 = the descriptor convention the kernel uses. */
+int dfb_debug_umma_gemm(const float* A, const float* B, int N, int K, int kind, int variant, float* D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

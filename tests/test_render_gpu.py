@@ -91,7 +91,11 @@ def test_raw2outputs_transmittance_matches_f64_scan(ops):
     z = np.sort(rng.rand(64, S).astype(np.float32) * 20, -1)
     want = O.raw2outputs_nerfw(raw, z, test_time=True, typ="coarse")["weights"]
     got = ops.raw2outputs(T(raw), T(z), "coarse", True)["weights"].cpu().numpy()
-    assert np.allclose(got, want, rtol=3e-6, atol=1e-9)
+    # alpha itself carries 1-ulp exp differences (relative 1e-5 at alpha ~ 4e-3); a float32 scan
+    # would add a drift that grows with the sample index instead
+    assert np.allclose(got, want, rtol=1e-4, atol=1e-8)
+    err = np.abs(got - want) / np.maximum(np.abs(want), 1e-8)
+    assert err[:, 192:].mean() < 2 * err[:, :64].mean() + 1e-6
 
 
 @pytest.mark.parametrize("tag,D,W", [("s", 4, 64), ("b", 8, 256)])
@@ -194,3 +198,25 @@ def test_render_error_behaviour(ops):
         h.render(64, 0, True, c2w=torch.eye(4, device=dev())[:3], H=2, W=2, focal=1.0, hist=torch.zeros(10), mma="fp32")
     with pytest.raises(DfbError):  # no fine network loaded
         h.render(64, 16, True, c2w=torch.eye(4, device=dev())[:3], H=2, W=2, focal=1.0, hist=torch.zeros(10), mma="fp32")
+
+
+@pytest.mark.parametrize("kind,N,K", [(1, 256, 64), (1, 256, 256), (1, 128, 128), (2, 256, 320), (1, 32, 16)])
+def test_umma_descriptor_selftest(ops, kind, N, K):
+    """One-tile tcgen05 GEMM through the kernel's shared-memory descriptors / TMEM loads."""
+    import ctypes as C
+    rng = np.random.RandomState(N + K)
+    A = rng.randn(128, K).astype(np.float32)
+    B = rng.randn(N, K).astype(np.float32)
+    dt = torch.float16 if kind == 1 else torch.bfloat16
+    Ar = torch.tensor(A).to(dt).float().numpy()
+    Br = torch.tensor(B).to(dt).float().numpy()
+    want = Ar.astype(np.float64) @ Br.astype(np.float64).T
+    errs = {}
+    for variant in (0, 1):
+        D = torch.zeros(128, N, device=dev())
+        ops.check(ops.lib.dfb_debug_umma_gemm(C.c_void_p(T(A).data_ptr()), C.c_void_p(T(B).data_ptr()), N, K, kind,
+                                              variant, C.c_void_p(D.data_ptr()), None))
+        torch.cuda.synchronize()
+        errs[variant] = float(np.abs(D.cpu().numpy() - want).max())
+    print("umma selftest max abs err by descriptor variant:", errs)
+    assert errs[0] < 1e-3 * np.sqrt(K), errs
