@@ -149,6 +149,17 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
       : "memory");
 }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint64_t mk64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
 // K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1).
 //   lbo: byte distance between the two 8-element K halves of a K=16 slice
 //   sbo: byte distance between consecutive 8-row groups
@@ -177,6 +188,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Same, but ties the destination registers of the outstanding load to the wait so that the
+// compiler cannot schedule their consumers above it.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+                 "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                 "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
 
 template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
 template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
@@ -198,6 +220,87 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-
 // epilogue building block: one 32-column block of the accumulator row of this thread
 // ---------------------------------------------------------------------------------------
 enum EpiKind { EPI_HIDDEN, EPI_HIDDEN_SIGMA, EPI_SIGMA_ONLY, EPI_FINAL, EPI_DT, EPI_T, EPI_T_LAST };
+
+struct EpiCtx {
+  const float* B;
+  uint32_t sigma_w, rgb_w, trgb_w, tsig_w, tbeta_w;
+  float sig, rgb[3], hd[5];
+};
+
+__device__ __forceinline__ float dot32(const float (&x)[32], const float* __restrict__ w, float acc) {
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 ww = __ldg(w4 + q);
+    acc = fmaf(x[4 * q], ww.x, acc), acc = fmaf(x[4 * q + 1], ww.y, acc);
+    acc = fmaf(x[4 * q + 2], ww.z, acc), acc = fmaf(x[4 * q + 3], ww.w, acc);
+  }
+  return acc;
+}
+
+// One 32-column block of this thread's accumulator row: add bias (or the per-ray bias),
+// activation, fp32 head dot products, and the 16-bit store of the next layer's A operand.
+template <typename T, int KIND, int CB>
+__device__ __forceinline__ void epi_block(const uint32_t (&v)[32], const float* __restrict__ badd, uint32_t h_row, EpiCtx& cx) {
+  float x[32];
+  const float4* b4 = reinterpret_cast<const float4*>(badd + CB * 32);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 bb = __ldg(b4 + q);
+    x[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + bb.x;
+    x[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + bb.y;
+    x[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bb.z;
+    x[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bb.w;
+  }
+  if (KIND != EPI_FINAL) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+  }
+  if (KIND == EPI_HIDDEN_SIGMA || KIND == EPI_SIGMA_ONLY) cx.sig = dot32(x, cx.B + cx.sigma_w + CB * 32, cx.sig);
+  if (KIND == EPI_DT && CB < 4) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) cx.rgb[c] = dot32(x, cx.B + cx.rgb_w + c * 128 + CB * 32, cx.rgb[c]);
+  }
+  if (KIND == EPI_T_LAST) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) cx.hd[c] = dot32(x, cx.B + cx.trgb_w + c * 128 + CB * 32, cx.hd[c]);
+    cx.hd[3] = dot32(x, cx.B + cx.tsig_w + CB * 32, cx.hd[3]);
+    cx.hd[4] = dot32(x, cx.B + cx.tbeta_w + CB * 32, cx.hd[4]);
+  }
+  constexpr bool kStore = KIND == EPI_HIDDEN || KIND == EPI_HIDDEN_SIGMA || KIND == EPI_FINAL || KIND == EPI_T ||
+                          (KIND == EPI_DT && CB >= 4);
+  if (kStore) {
+    constexpr int panel0 = (KIND == EPI_DT ? CB - 4 : CB) * 4;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      st_shared_v4(h_row + (panel0 + q) * kPanelBytes, pack2<T>(x[8 * q], x[8 * q + 1]), pack2<T>(x[8 * q + 2], x[8 * q + 3]),
+                   pack2<T>(x[8 * q + 4], x[8 * q + 5]), pack2<T>(x[8 * q + 6], x[8 * q + 7]));
+  }
+}
+
+template <typename T, int KIND, int CB, int NBLK>
+struct EpiLoop {
+  // v_cur holds block CB (load already issued); v_nxt receives block CB+1 while CB is processed
+  static __device__ __forceinline__ void run(uint32_t t_row, uint32_t h_row, const float* badd, EpiCtx& cx,
+                                             uint32_t (&v_cur)[32], uint32_t (&v_nxt)[32]) {
+    tmem_ld_wait(v_cur);
+    if (CB + 1 < NBLK) tmem_ld32(t_row + (CB + 1) * 32, v_nxt);
+    epi_block<T, KIND, CB>(v_cur, badd, h_row, cx);
+    EpiLoop<T, KIND, CB + 1, NBLK>::run(t_row, h_row, badd, cx, v_nxt, v_cur);
+  }
+};
+template <typename T, int KIND, int NBLK>
+struct EpiLoop<T, KIND, NBLK, NBLK> {
+  static __device__ __forceinline__ void run(uint32_t, uint32_t, const float*, EpiCtx&, uint32_t (&)[32], uint32_t (&)[32]) {}
+};
+
+// A whole step: software-pipelined TMEM reads (block CB+1 in flight while CB is processed).
+template <typename T, int KIND, int NBLK>
+__device__ __forceinline__ void epi_step(uint32_t t_row, uint32_t h_row, const float* badd, EpiCtx& cx) {
+  uint32_t v0[32], v1[32];
+  tmem_ld32(t_row, v0);
+  EpiLoop<T, KIND, 0, NBLK>::run(t_row, h_row, badd, cx, v0, v1);
+}
 
 template <typename T, int FULL>
 __global__ void __launch_bounds__(kThreads, 1) k_mlp_tc(const __grid_constant__ TcArgs a) {
@@ -229,59 +332,76 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_tc(const __grid_constant__ 
   const int n_steps = a.n_steps;
 
   if (warp == 12) {
-    // ===== weight producer ================================================================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int64_t p = blockIdx.x; p < a.n_pass; p += gridDim.x)
-        for (int s = 0; s < n_steps; ++s)
-          for (int slot = 0; slot < 2; ++slot)
-            for (int c = 0; c < a.steps[s].n_chunks; ++c) {
-              mbar_wait(bar(W_EMPTY + stage), phase ^ 1, a.error_flag);
+    // ===== weight producer (warp-uniform control flow, one elected lane issues) ============
+    uint32_t stage = 0, phase = 0;
+    const uint8_t* wimg = reinterpret_cast<const uint8_t*>(a.wimg);
+    for (int64_t p = blockIdx.x; p < a.n_pass; p += gridDim.x)
+      for (int s = 0; s < n_steps; ++s) {
+        const int nch = a.steps[s].n_chunks;
+        const uint8_t* src0 = wimg + (size_t)a.steps[s].chunk_base * kChunkBytes;
+        for (int slot = 0; slot < 2; ++slot) {
+          const uint8_t* src = src0;
+          for (int c = 0; c < nch; ++c, src += kChunkBytes) {
+            mbar_wait(bar(W_EMPTY + stage), phase ^ 1, a.error_flag);
+            if (elect_one()) {
               mbar_expect_tx(bar(W_FULL + stage), kChunkBytes);
-              bulk_g2s(sW + stage * kChunkBytes,
-                       reinterpret_cast<const uint8_t*>(a.wimg) + (size_t)(a.steps[s].chunk_base + c) * kChunkBytes,
-                       kChunkBytes, bar(W_FULL + stage));
-              if (++stage == kStages) stage = 0, phase ^= 1;
+              bulk_g2s(sW + stage * kChunkBytes, src, kChunkBytes, bar(W_FULL + stage));
             }
-    }
-  } else if (warp == 13) {
-    // ===== MMA issuer =======================================================================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      int lp = 0;
-      for (int64_t p = blockIdx.x; p < a.n_pass; p += gridDim.x, ++lp)
-        for (int s = 0; s < n_steps; ++s) {
-          const Step st = a.steps[s];
-          const uint32_t idesc = make_idesc(fmt, st.n, kTileM);
-          const uint32_t b_lbo = st.n * 16;
-          for (int slot = 0; slot < 2; ++slot) {
-            if (s == 0) {
-              if (lp > 0) mbar_wait(bar(PASS_DONE + slot), (lp - 1) & 1, a.error_flag);
-              mbar_wait(bar(PE_READY + slot), lp & 1, a.error_flag);
-            } else {
-              mbar_wait(bar(A_READY + slot), (lp * (n_steps - 1) + s - 1) & 1, a.error_flag);
-            }
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + slot * 256;
-            const uint32_t a_base = sA + slot * kSlotBytes + st.a_panel0 * kPanelBytes;
-            int kg = 0;
-            for (int c = 0; c < st.n_chunks; ++c) {
-              mbar_wait(bar(W_FULL + stage), phase, a.error_flag);
-              tc_fence_after();
-              const uint32_t b_base = sW + stage * kChunkBytes;
-              for (int ks = 0; ks < st.ksteps; ++ks, ++kg) {
-                const uint64_t ad = make_desc(a_base + kg * 2 * kPanelBytes, kPanelBytes, 128);
-                const uint64_t bd = make_desc(b_base + ks * 2 * b_lbo, b_lbo, 128);
-                umma_f16(d_tmem, ad, bd, idesc, kg > 0 ? 1u : 0u);
-              }
-              umma_commit(bar(W_EMPTY + stage));
-              if (++stage == kStages) stage = 0, phase ^= 1;
-            }
-            umma_commit(bar(D_FULL + slot));
-            if (s == a.last_pe_step) umma_commit(bar(PE_FREE + slot));
+            __syncwarp();
+            if (++stage == kStages) stage = 0, phase ^= 1;
           }
         }
-    }
+      }
+  } else if (warp == 13) {
+    // ===== MMA issuer (warp-uniform control flow, one elected lane issues) ===================
+    uint32_t stage = 0, phase = 0;
+    int lp = 0;
+    // descriptor high word: SBO = 128 B (bits 32..45), version 1 (bit 46), no swizzle
+    const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+    for (int64_t p = blockIdx.x; p < a.n_pass; p += gridDim.x, ++lp)
+      for (int s = 0; s < n_steps; ++s) {
+        const int nch = a.steps[s].n_chunks, ksteps = a.steps[s].ksteps, nn = a.steps[s].n;
+        const uint32_t idesc = make_idesc(fmt, nn, kTileM);
+        const uint32_t b_step = 2u * nn;  // (2 panels * n*16 B) >> 4
+        for (int slot = 0; slot < 2; ++slot) {
+          if (s == 0) {
+            if (lp > 0) mbar_wait(bar(PASS_DONE + slot), (lp - 1) & 1, a.error_flag);
+            mbar_wait(bar(PE_READY + slot), lp & 1, a.error_flag);
+          } else {
+            mbar_wait(bar(A_READY + slot), (lp * (n_steps - 1) + s - 1) & 1, a.error_flag);
+          }
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + slot * 256;
+          // low word: start address >> 4 | LBO (2048 B >> 4) << 16; one K=16 step advances by 2 panels
+          uint32_t a_lo = ((sA + slot * kSlotBytes + a.steps[s].a_panel0 * kPanelBytes) >> 4) | ((kPanelBytes >> 4) << 16);
+          uint32_t acc = 0;
+          for (int c = 0; c < nch; ++c) {
+            mbar_wait(bar(W_FULL + stage), phase, a.error_flag);
+            tc_fence_after();
+            const uint32_t b_lo = ((sW + stage * kChunkBytes) >> 4) | ((uint32_t)nn << 16);
+            if (elect_one()) {
+              if (ksteps == 2) {
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)
+                  umma_f16(d_tmem, mk64(a_lo + ks * 256, desc_hi), mk64(b_lo + ks * b_step, desc_hi), idesc, acc | ks);
+              } else {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  umma_f16(d_tmem, mk64(a_lo + ks * 256, desc_hi), mk64(b_lo + ks * b_step, desc_hi), idesc, acc | ks);
+              }
+              umma_commit(bar(W_EMPTY + stage));
+              if (c == nch - 1) {
+                umma_commit(bar(D_FULL + slot));
+                if (s == a.last_pe_step) umma_commit(bar(PE_FREE + slot));
+              }
+            }
+            __syncwarp();
+            a_lo += 256u * ksteps;
+            acc = 1;
+            if (++stage == kStages) stage = 0, phase ^= 1;
+          }
+        }
+      }
   } else if (warp >= 8) {
     // ===== encoder: positional encoding of the next pass (nerfw.py:128-133) =================
     const int r = tid - 256;
@@ -323,95 +443,46 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_tc(const __grid_constant__ 
     const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + slot * 256;
     const uint32_t h_row = sA + slot * kSlotBytes + r * 16;
     const float* B = a.blob;
+    EpiCtx cx;
+    cx.B = B, cx.sigma_w = a.sigma_w, cx.rgb_w = a.rgb_w, cx.trgb_w = a.trgb_w, cx.tsig_w = a.tsig_w, cx.tbeta_w = a.tbeta_w;
     uint32_t nd = 0;
     for (int64_t p = blockIdx.x; p < a.n_pass; p += gridDim.x) {
       const int64_t g = (2 * p + slot) * kTileM + r;
       const bool valid = g < a.P;
       const int64_t ray = (valid ? g : a.P - 1) / a.S;
       const float* rb = FULL ? a.raybias + ray * 256 : nullptr;
-      float sig = 0.f, rgb[3] = {0.f, 0.f, 0.f}, hd[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      cx.sig = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) cx.rgb[c] = 0.f;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) cx.hd[c] = 0.f;
       for (int s = 0; s < n_steps; ++s) {
-        EpiKind kind;
-        if (!FULL) kind = s == 7 ? EPI_SIGMA_ONLY : EPI_HIDDEN;
-        else kind = s < 7 ? EPI_HIDDEN : s == 7 ? EPI_HIDDEN_SIGMA : s == 8 ? EPI_FINAL : s == 9 ? EPI_DT
-                    : s < 12 ? EPI_T : EPI_T_LAST;
-        const int nblk = a.steps[s].n / 32;
-        const float* bias = a.bias_off[s] != 0xffffffffu ? B + a.bias_off[s] : nullptr;
+        const float* bias = B + a.bias_off[s];
         mbar_wait(bar(D_FULL + slot), nd & 1, a.error_flag);
         ++nd;
         tc_fence_after();
-        for (int cb = 0; cb < nblk; ++cb) {
-          uint32_t v[32];
-          tmem_ld32(t_row + cb * 32, v);
-          tmem_ld_wait();
-          float x[32];
-          const float4* b4 = reinterpret_cast<const float4*>((kind == EPI_DT ? rb : bias) + cb * 32);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 bb = __ldg(b4 + q);
-            x[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + bb.x;
-            x[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + bb.y;
-            x[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bb.z;
-            x[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bb.w;
-          }
-          if (kind != EPI_FINAL) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
-          }
-          if (kind == EPI_HIDDEN_SIGMA || kind == EPI_SIGMA_ONLY) {
-            const float4* w4 = reinterpret_cast<const float4*>(B + a.sigma_w + cb * 32);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 w = __ldg(w4 + q);
-              sig = fmaf(x[4 * q], w.x, sig), sig = fmaf(x[4 * q + 1], w.y, sig);
-              sig = fmaf(x[4 * q + 2], w.z, sig), sig = fmaf(x[4 * q + 3], w.w, sig);
-            }
-          }
-          if (kind == EPI_DT && cb < 4) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              const float4* w4 = reinterpret_cast<const float4*>(B + a.rgb_w + c * 128 + cb * 32);
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 w = __ldg(w4 + q);
-                rgb[c] = fmaf(x[4 * q], w.x, rgb[c]), rgb[c] = fmaf(x[4 * q + 1], w.y, rgb[c]);
-                rgb[c] = fmaf(x[4 * q + 2], w.z, rgb[c]), rgb[c] = fmaf(x[4 * q + 3], w.w, rgb[c]);
-              }
-            }
-          }
-          if (kind == EPI_T_LAST) {
-#pragma unroll
-            for (int c = 0; c < 5; ++c) {
-              const uint32_t off = c < 3 ? a.trgb_w + c * 128 : (c == 3 ? a.tsig_w : a.tbeta_w);
-              const float4* w4 = reinterpret_cast<const float4*>(B + off + cb * 32);
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 w = __ldg(w4 + q);
-                hd[c] = fmaf(x[4 * q], w.x, hd[c]), hd[c] = fmaf(x[4 * q + 1], w.y, hd[c]);
-                hd[c] = fmaf(x[4 * q + 2], w.z, hd[c]), hd[c] = fmaf(x[4 * q + 3], w.w, hd[c]);
-              }
-            }
-          }
-          const bool store = kind == EPI_HIDDEN || kind == EPI_HIDDEN_SIGMA || kind == EPI_FINAL || kind == EPI_T ||
-                             (kind == EPI_DT && cb >= 4);
-          if (store) {
-            const int panel0 = (kind == EPI_DT ? cb - 4 : cb) * 4;
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              st_shared_v4(h_row + (panel0 + q) * kPanelBytes, pack2<T>(x[8 * q], x[8 * q + 1]),
-                           pack2<T>(x[8 * q + 2], x[8 * q + 3]), pack2<T>(x[8 * q + 4], x[8 * q + 5]),
-                           pack2<T>(x[8 * q + 6], x[8 * q + 7]));
-          }
+        if (!FULL) {
+          if (s < 7) epi_step<T, EPI_HIDDEN, 8>(t_row, h_row, bias, cx);
+          else epi_step<T, EPI_SIGMA_ONLY, 8>(t_row, h_row, bias, cx);
+        } else {
+          if (s < 7) epi_step<T, EPI_HIDDEN, 8>(t_row, h_row, bias, cx);
+          else if (s == 7) epi_step<T, EPI_HIDDEN_SIGMA, 8>(t_row, h_row, bias, cx);
+          else if (s == 8) epi_step<T, EPI_FINAL, 8>(t_row, h_row, bias, cx);
+          else if (s == 9) epi_step<T, EPI_DT, 8>(t_row, h_row, rb, cx);
+          else if (s < 12) epi_step<T, EPI_T, 4>(t_row, h_row, bias, cx);
+          else epi_step<T, EPI_T_LAST, 4>(t_row, h_row, bias, cx);
         }
-        if (kind == EPI_HIDDEN_SIGMA || kind == EPI_SIGMA_ONLY) sig = softplus_f(sig + __ldg(B + a.sigma_b));
-        if (kind == EPI_SIGMA_ONLY && valid) a.raw[g] = sig;
-        if (kind == EPI_T_LAST && valid) {
+        if (s == 7) {
+          cx.sig = softplus_f(cx.sig + __ldg(B + a.sigma_b));
+          if (!FULL && valid) a.raw[g] = cx.sig;
+        }
+        if (FULL && s == 12 && valid) {
           float* o = a.raw + g * 9;
-          o[0] = sigmoid_f(rgb[0] + __ldg(B + a.rgb_b)), o[1] = sigmoid_f(rgb[1] + __ldg(B + a.rgb_b + 1));
-          o[2] = sigmoid_f(rgb[2] + __ldg(B + a.rgb_b + 2)), o[3] = sig;
-          o[4] = sigmoid_f(hd[0] + __ldg(B + a.trgb_b)), o[5] = sigmoid_f(hd[1] + __ldg(B + a.trgb_b + 1));
-          o[6] = sigmoid_f(hd[2] + __ldg(B + a.trgb_b + 2));
-          o[7] = softplus_f(hd[3] + __ldg(B + a.tsig_b)), o[8] = softplus_f(hd[4] + __ldg(B + a.tbeta_b));
+          o[0] = sigmoid_f(cx.rgb[0] + __ldg(B + a.rgb_b)), o[1] = sigmoid_f(cx.rgb[1] + __ldg(B + a.rgb_b + 1));
+          o[2] = sigmoid_f(cx.rgb[2] + __ldg(B + a.rgb_b + 2)), o[3] = cx.sig;
+          o[4] = sigmoid_f(cx.hd[0] + __ldg(B + a.trgb_b)), o[5] = sigmoid_f(cx.hd[1] + __ldg(B + a.trgb_b + 1));
+          o[6] = sigmoid_f(cx.hd[2] + __ldg(B + a.trgb_b + 2));
+          o[7] = softplus_f(cx.hd[3] + __ldg(B + a.tsig_b)), o[8] = softplus_f(cx.hd[4] + __ldg(B + a.tbeta_b));
         }
         tc_fence_before();
         fence_proxy_async();
