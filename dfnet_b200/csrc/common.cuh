@@ -72,6 +72,7 @@ struct NetPack {
   // ---- tcgen05 layout (W == 256 only): 16-bit core-matrix panels, see mlp_tc.cu ------
   void* blob16[2] = {nullptr, nullptr};  // [0] fp16, [1] bf16
   size_t blob16_bytes = 0;
+  std::vector<float> tc_tbl;  // host copy of the bias / head-weight table passed as kernel parameter
 };
 
 }  // namespace dfb

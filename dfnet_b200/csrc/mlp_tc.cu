@@ -47,6 +47,13 @@ constexpr int kSmemBar = 256;
 constexpr int kSmemTotal = kSmemA + kSmemW + kSmemBar;  // 229632 B
 constexpr int kThreads = 448;
 constexpr int kMaxSteps = 13;
+constexpr int kTblSigmaW = kMaxSteps * 256;
+constexpr int kTblRgbW = kTblSigmaW + 256;
+constexpr int kTblTrgbW = kTblRgbW + 384;
+constexpr int kTblTsigW = kTblTrgbW + 384;
+constexpr int kTblTbetaW = kTblTsigW + 128;
+constexpr int kTblScal = kTblTbetaW + 128;
+constexpr int kTblFloats = kTblScal + 16;
 
 // barrier slots (8 bytes each) inside the kSmemBar region
 enum Bar { W_FULL = 0, W_EMPTY = 4, D_FULL = 8, A_READY = 10, PASS_DONE = 12, PE_READY = 14, PE_FREE = 16, N_BARS = 18 };
@@ -64,9 +71,6 @@ struct TcArgs {
   int n_steps;
   int last_pe_step;       // last step that reads the PE panels (skip layer)
   const void* wimg;       // packed 16-bit weight image, chunk i at wimg + i*16 KB
-  const float* blob;      // fp32 biases / head weights (NetPack::blob32)
-  uint32_t bias_off[kMaxSteps];  // float offsets into blob; 0xffffffff = none (ray bias instead)
-  uint32_t sigma_w, sigma_b, rgb_w, rgb_b, tsig_w, tsig_b, trgb_w, trgb_b, tbeta_w, tbeta_b;
   const float* rayrec;    // [n_rays,12]
   const float* z;         // [n_rays,S]
   const float* raybias;   // [n_rays,256] (fine) or null
@@ -75,6 +79,10 @@ struct TcArgs {
   int64_t n_pass;         // ceil(tiles / 2)
   float* raw;             // [P,1] or [P,9]
   int* error_flag;
+  // fp32 biases and head weights, read through the constant bank (warp-uniform addresses):
+  // bias[s][256] for every step, then sigma_w[256], rgb_w[3][128], trgb_w[3][128], tsig_w[128],
+  // tbeta_w[128], scalars {sigma_b, rgb_b[3], trgb_b[3], tsig_b, tbeta_b}
+  float tbl[kTblFloats];
 };
 
 // ---------------------------------------------------------------------------------------
@@ -222,50 +230,50 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-
 enum EpiKind { EPI_HIDDEN, EPI_HIDDEN_SIGMA, EPI_SIGMA_ONLY, EPI_FINAL, EPI_DT, EPI_T, EPI_T_LAST };
 
 struct EpiCtx {
-  const float* B;
-  uint32_t sigma_w, rgb_w, trgb_w, tsig_w, tbeta_w;
   float sig, rgb[3], hd[5];
 };
 
-__device__ __forceinline__ float dot32(const float (&x)[32], const float* __restrict__ w, float acc) {
-  const float4* w4 = reinterpret_cast<const float4*>(w);
+// dot of 32 activations with 32 table entries (constant bank, warp-uniform)
+__device__ __forceinline__ float dot32c(const float (&x)[32], const TcArgs& a, int off, float acc) {
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const float4 ww = __ldg(w4 + q);
-    acc = fmaf(x[4 * q], ww.x, acc), acc = fmaf(x[4 * q + 1], ww.y, acc);
-    acc = fmaf(x[4 * q + 2], ww.z, acc), acc = fmaf(x[4 * q + 3], ww.w, acc);
-  }
+  for (int j = 0; j < 32; ++j) acc = fmaf(x[j], a.tbl[off + j], acc);
   return acc;
 }
 
-// One 32-column block of this thread's accumulator row: add bias (or the per-ray bias),
-// activation, fp32 head dot products, and the 16-bit store of the next layer's A operand.
+// One 32-column block of this thread's accumulator row: add bias (constant bank) or the per-ray
+// bias (global), activation, fp32 head dot products, 16-bit store of the next layer's A operand.
 template <typename T, int KIND, int CB>
-__device__ __forceinline__ void epi_block(const uint32_t (&v)[32], const float* __restrict__ badd, uint32_t h_row, EpiCtx& cx) {
+__device__ __forceinline__ void epi_block(const uint32_t (&v)[32], const TcArgs& a, int bias_off,
+                                          const float* __restrict__ rb, uint32_t h_row, EpiCtx& cx) {
   float x[32];
-  const float4* b4 = reinterpret_cast<const float4*>(badd + CB * 32);
+  if (KIND == EPI_DT) {
+    const float4* b4 = reinterpret_cast<const float4*>(rb + CB * 32);
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const float4 bb = __ldg(b4 + q);
-    x[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + bb.x;
-    x[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + bb.y;
-    x[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bb.z;
-    x[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bb.w;
+    for (int q = 0; q < 8; ++q) {
+      const float4 bb = __ldg(b4 + q);
+      x[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + bb.x;
+      x[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + bb.y;
+      x[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bb.z;
+      x[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bb.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + a.tbl[bias_off + CB * 32 + j];
   }
   if (KIND != EPI_FINAL) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
   }
-  if (KIND == EPI_HIDDEN_SIGMA || KIND == EPI_SIGMA_ONLY) cx.sig = dot32(x, cx.B + cx.sigma_w + CB * 32, cx.sig);
+  if (KIND == EPI_HIDDEN_SIGMA || KIND == EPI_SIGMA_ONLY) cx.sig = dot32c(x, a, kTblSigmaW + CB * 32, cx.sig);
   if (KIND == EPI_DT && CB < 4) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) cx.rgb[c] = dot32(x, cx.B + cx.rgb_w + c * 128 + CB * 32, cx.rgb[c]);
+    for (int c = 0; c < 3; ++c) cx.rgb[c] = dot32c(x, a, kTblRgbW + c * 128 + CB * 32, cx.rgb[c]);
   }
   if (KIND == EPI_T_LAST) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) cx.hd[c] = dot32(x, cx.B + cx.trgb_w + c * 128 + CB * 32, cx.hd[c]);
-    cx.hd[3] = dot32(x, cx.B + cx.tsig_w + CB * 32, cx.hd[3]);
-    cx.hd[4] = dot32(x, cx.B + cx.tbeta_w + CB * 32, cx.hd[4]);
+    for (int c = 0; c < 3; ++c) cx.hd[c] = dot32c(x, a, kTblTrgbW + c * 128 + CB * 32, cx.hd[c]);
+    cx.hd[3] = dot32c(x, a, kTblTsigW + CB * 32, cx.hd[3]);
+    cx.hd[4] = dot32c(x, a, kTblTbetaW + CB * 32, cx.hd[4]);
   }
   constexpr bool kStore = KIND == EPI_HIDDEN || KIND == EPI_HIDDEN_SIGMA || KIND == EPI_FINAL || KIND == EPI_T ||
                           (KIND == EPI_DT && CB >= 4);
@@ -281,25 +289,27 @@ __device__ __forceinline__ void epi_block(const uint32_t (&v)[32], const float* 
 template <typename T, int KIND, int CB, int NBLK>
 struct EpiLoop {
   // v_cur holds block CB (load already issued); v_nxt receives block CB+1 while CB is processed
-  static __device__ __forceinline__ void run(uint32_t t_row, uint32_t h_row, const float* badd, EpiCtx& cx,
-                                             uint32_t (&v_cur)[32], uint32_t (&v_nxt)[32]) {
+  static __device__ __forceinline__ void run(uint32_t t_row, uint32_t h_row, const TcArgs& a, int bias_off,
+                                             const float* rb, EpiCtx& cx, uint32_t (&v_cur)[32], uint32_t (&v_nxt)[32]) {
     tmem_ld_wait(v_cur);
     if (CB + 1 < NBLK) tmem_ld32(t_row + (CB + 1) * 32, v_nxt);
-    epi_block<T, KIND, CB>(v_cur, badd, h_row, cx);
-    EpiLoop<T, KIND, CB + 1, NBLK>::run(t_row, h_row, badd, cx, v_nxt, v_cur);
+    epi_block<T, KIND, CB>(v_cur, a, bias_off, rb, h_row, cx);
+    EpiLoop<T, KIND, CB + 1, NBLK>::run(t_row, h_row, a, bias_off, rb, cx, v_nxt, v_cur);
   }
 };
 template <typename T, int KIND, int NBLK>
 struct EpiLoop<T, KIND, NBLK, NBLK> {
-  static __device__ __forceinline__ void run(uint32_t, uint32_t, const float*, EpiCtx&, uint32_t (&)[32], uint32_t (&)[32]) {}
+  static __device__ __forceinline__ void run(uint32_t, uint32_t, const TcArgs&, int, const float*, EpiCtx&, uint32_t (&)[32],
+                                             uint32_t (&)[32]) {}
 };
 
 // A whole step: software-pipelined TMEM reads (block CB+1 in flight while CB is processed).
 template <typename T, int KIND, int NBLK>
-__device__ __forceinline__ void epi_step(uint32_t t_row, uint32_t h_row, const float* badd, EpiCtx& cx) {
+__device__ __forceinline__ void epi_step(uint32_t t_row, uint32_t h_row, const TcArgs& a, int bias_off, const float* rb,
+                                         EpiCtx& cx) {
   uint32_t v0[32], v1[32];
   tmem_ld32(t_row, v0);
-  EpiLoop<T, KIND, 0, NBLK>::run(t_row, h_row, badd, cx, v0, v1);
+  EpiLoop<T, KIND, 0, NBLK>::run(t_row, h_row, a, bias_off, rb, cx, v0, v1);
 }
 
 template <typename T, int FULL>
@@ -442,9 +452,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_tc(const __grid_constant__ 
     const int r = tid & 127;
     const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + slot * 256;
     const uint32_t h_row = sA + slot * kSlotBytes + r * 16;
-    const float* B = a.blob;
     EpiCtx cx;
-    cx.B = B, cx.sigma_w = a.sigma_w, cx.rgb_w = a.rgb_w, cx.trgb_w = a.trgb_w, cx.tsig_w = a.tsig_w, cx.tbeta_w = a.tbeta_w;
     uint32_t nd = 0;
     for (int64_t p = blockIdx.x; p < a.n_pass; p += gridDim.x) {
       const int64_t g = (2 * p + slot) * kTileM + r;
@@ -457,32 +465,32 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_tc(const __grid_constant__ 
 #pragma unroll
       for (int c = 0; c < 5; ++c) cx.hd[c] = 0.f;
       for (int s = 0; s < n_steps; ++s) {
-        const float* bias = B + a.bias_off[s];
+        const int boff = s * 256;
         mbar_wait(bar(D_FULL + slot), nd & 1, a.error_flag);
         ++nd;
         tc_fence_after();
         if (!FULL) {
-          if (s < 7) epi_step<T, EPI_HIDDEN, 8>(t_row, h_row, bias, cx);
-          else epi_step<T, EPI_SIGMA_ONLY, 8>(t_row, h_row, bias, cx);
+          if (s < 7) epi_step<T, EPI_HIDDEN, 8>(t_row, h_row, a, boff, rb, cx);
+          else epi_step<T, EPI_SIGMA_ONLY, 8>(t_row, h_row, a, boff, rb, cx);
         } else {
-          if (s < 7) epi_step<T, EPI_HIDDEN, 8>(t_row, h_row, bias, cx);
-          else if (s == 7) epi_step<T, EPI_HIDDEN_SIGMA, 8>(t_row, h_row, bias, cx);
-          else if (s == 8) epi_step<T, EPI_FINAL, 8>(t_row, h_row, bias, cx);
-          else if (s == 9) epi_step<T, EPI_DT, 8>(t_row, h_row, rb, cx);
-          else if (s < 12) epi_step<T, EPI_T, 4>(t_row, h_row, bias, cx);
-          else epi_step<T, EPI_T_LAST, 4>(t_row, h_row, bias, cx);
+          if (s < 7) epi_step<T, EPI_HIDDEN, 8>(t_row, h_row, a, boff, rb, cx);
+          else if (s == 7) epi_step<T, EPI_HIDDEN_SIGMA, 8>(t_row, h_row, a, boff, rb, cx);
+          else if (s == 8) epi_step<T, EPI_FINAL, 8>(t_row, h_row, a, boff, rb, cx);
+          else if (s == 9) epi_step<T, EPI_DT, 8>(t_row, h_row, a, boff, rb, cx);
+          else if (s < 12) epi_step<T, EPI_T, 4>(t_row, h_row, a, boff, rb, cx);
+          else epi_step<T, EPI_T_LAST, 4>(t_row, h_row, a, boff, rb, cx);
         }
         if (s == 7) {
-          cx.sig = softplus_f(cx.sig + __ldg(B + a.sigma_b));
+          cx.sig = softplus_f(cx.sig + a.tbl[kTblScal]);
           if (!FULL && valid) a.raw[g] = cx.sig;
         }
         if (FULL && s == 12 && valid) {
           float* o = a.raw + g * 9;
-          o[0] = sigmoid_f(cx.rgb[0] + __ldg(B + a.rgb_b)), o[1] = sigmoid_f(cx.rgb[1] + __ldg(B + a.rgb_b + 1));
-          o[2] = sigmoid_f(cx.rgb[2] + __ldg(B + a.rgb_b + 2)), o[3] = cx.sig;
-          o[4] = sigmoid_f(cx.hd[0] + __ldg(B + a.trgb_b)), o[5] = sigmoid_f(cx.hd[1] + __ldg(B + a.trgb_b + 1));
-          o[6] = sigmoid_f(cx.hd[2] + __ldg(B + a.trgb_b + 2));
-          o[7] = softplus_f(cx.hd[3] + __ldg(B + a.tsig_b)), o[8] = softplus_f(cx.hd[4] + __ldg(B + a.tbeta_b));
+          o[0] = sigmoid_f(cx.rgb[0] + a.tbl[kTblScal + 1]), o[1] = sigmoid_f(cx.rgb[1] + a.tbl[kTblScal + 2]);
+          o[2] = sigmoid_f(cx.rgb[2] + a.tbl[kTblScal + 3]), o[3] = cx.sig;
+          o[4] = sigmoid_f(cx.hd[0] + a.tbl[kTblScal + 4]), o[5] = sigmoid_f(cx.hd[1] + a.tbl[kTblScal + 5]);
+          o[6] = sigmoid_f(cx.hd[2] + a.tbl[kTblScal + 6]);
+          o[7] = softplus_f(cx.hd[3] + a.tbl[kTblScal + 7]), o[8] = softplus_f(cx.hd[4] + a.tbl[kTblScal + 8]);
         }
         tc_fence_before();
         fence_proxy_async();
@@ -630,6 +638,22 @@ int pack_tc_weights(DfbNerf* n, int which, const std::vector<std::vector<float>>
         }
     }
   }
+  // fp32 table read through the constant bank by the epilogue (see TcArgs::tbl)
+  np.tc_tbl.assign(tc::kTblFloats, 0.f);
+  float* tb = np.tc_tbl.data();
+  for (int s = 0; s < 8; ++s) memcpy(tb + s * 256, P[2 * s + 1].data(), 256 * sizeof(float));
+  memcpy(tb + tc::kTblSigmaW, P[20].data(), 256 * sizeof(float));
+  tb[tc::kTblScal] = P[21][0];
+  if (fine) {
+    memcpy(tb + 8 * 256, P[17].data(), 256 * sizeof(float));  // xyz_encoding_final bias; step 9 uses the ray bias
+    for (int i = 0; i < 3; ++i) memcpy(tb + (10 + i) * 256, P[27 + 2 * i].data(), H * sizeof(float));
+    memcpy(tb + tc::kTblRgbW, P[22].data(), 3 * H * sizeof(float));
+    memcpy(tb + tc::kTblTrgbW, P[34].data(), 3 * H * sizeof(float));
+    memcpy(tb + tc::kTblTsigW, P[32].data(), H * sizeof(float));
+    memcpy(tb + tc::kTblTbetaW, P[36].data(), H * sizeof(float));
+    for (int c = 0; c < 3; ++c) tb[tc::kTblScal + 1 + c] = P[23][c], tb[tc::kTblScal + 4 + c] = P[35][c];
+    tb[tc::kTblScal + 7] = P[33][0], tb[tc::kTblScal + 8] = P[37][0];
+  }
   np.blob16_bytes = total_chunks * tc::kChunkBytes;
   for (int k = 0; k < 2; ++k) {
     DFB_CHECK_CUDA(cudaMalloc(&np.blob16[k], np.blob16_bytes));
@@ -665,14 +689,13 @@ int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const
     a.steps[s].a_panel0 = s == 0 ? 32 : 0;
     a.steps[s].chunk_base = cb;
     cb += K / kc;
-    a.bias_off[s] = s < 8 ? (uint32_t)np.trunk_b[s] : s == 8 ? (uint32_t)np.final_b : s == 9 ? 0xffffffffu
-                                                                                            : (uint32_t)np.t_b[s - 10];
   }
   a.wimg = np.blob16[kind == DFB_MMA_F16 ? 0 : 1];
-  a.blob = np.blob32;
-  a.sigma_w = np.sigma_w, a.sigma_b = np.sigma_b, a.rgb_w = np.rgb_w, a.rgb_b = np.rgb_b;
-  a.tsig_w = np.tsig_w, a.tsig_b = np.tsig_b, a.trgb_w = np.trgb_w, a.trgb_b = np.trgb_b;
-  a.tbeta_w = np.tbeta_w, a.tbeta_b = np.tbeta_b;
+  if (np.tc_tbl.empty()) {
+    set_error("tcgen05 bias table missing");
+    return DFB_ERR_INVALID;
+  }
+  memcpy(a.tbl, np.tc_tbl.data(), sizeof(a.tbl));
   a.rayrec = rayrec, a.z = z, a.raybias = raybias, a.S = S, a.P = n_rays * S, a.raw = raw;
   a.error_flag = g_error_flag;
   if (a.P == 0) return DFB_OK;
