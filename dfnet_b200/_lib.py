@@ -7,14 +7,14 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdfnet_b200.so")
+LIB_PATH = os.environ.get("DFB_LIB_PATH", os.path.join(_HERE, "libdfnet_b200.so"))  # override: profiling builds only
 
 # every symbol include/dfnet_b200.h declares (tests check that the library exports them all)
 SYMBOLS = [
     "dfb_last_error", "dfb_version", "dfb_device_ok", "dfb_linspace_f32", "dfb_nerf_create", "dfb_nerf_destroy",
     "dfb_nerf_load", "dfb_nerf_set_embeddings", "dfb_nerfw_forward", "dfb_render_workspace_bytes",
     "dfb_render_fwd", "dfb_render_image_host", "dfb_sample_pdf", "dfb_raw2outputs", "dfb_get_rays",
-    "dfb_launch_count", "dfb_profile_enable", "dfb_profile_read", "dfb_debug_umma_gemm",
+    "dfb_launch_count", "dfb_profile_enable", "dfb_profile_read", "dfb_debug_umma_gemm", "dfb_debug_tc_prof",
 ]
 
 MMA_FP32_SIMT, MMA_F16, MMA_BF16 = 0, 1, 2
@@ -72,6 +72,7 @@ def _load():
     lib.dfb_raw2outputs.argtypes = [vp, vp, i64, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.dfb_get_rays.argtypes = [vp, i32, i32, i32, f32, vp, vp, vp]
     lib.dfb_debug_umma_gemm.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
+    lib.dfb_debug_tc_prof.argtypes = [vp, i32]
     lib.dfb_profile_enable.argtypes = [i32]
     lib.dfb_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(i64)]
     return lib

@@ -70,7 +70,7 @@ struct NetPack {
   size_t tbeta_w = 0, tbeta_b = 0;  // [W/2], [1]
 
   // ---- tcgen05 layout (W == 256 only): 16-bit core-matrix panels, see mlp_tc.cu ------
-  void* blob16[2] = {nullptr, nullptr};  // [0] fp16, [1] bf16
+  void* blob16[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [fp16|bf16][cta_group 1|2 chunking]
   size_t blob16_bytes = 0;
   std::vector<float> tc_tbl;  // host copy of the bias / head-weight table passed as kernel parameter
 };

@@ -24,6 +24,7 @@
 // Reference arithmetic: models/nerfw.py:297-354 (NeRFW.forward), :105-133 (embedding),
 // models/rendering.py:287,305 (pts).  Per-ray constant inputs (view-direction encoding,
 // appearance and transient codes) enter as a per-ray bias computed by k_raybias.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -56,7 +57,7 @@ constexpr int kTblScal = kTblTbetaW + 128;
 constexpr int kTblFloats = kTblScal + 16;
 
 // barrier slots (8 bytes each) inside the kSmemBar region
-enum Bar { W_FULL = 0, W_EMPTY = 4, D_FULL = 8, A_READY = 10, PASS_DONE = 12, PE_READY = 14, PE_FREE = 16, N_BARS = 18 };
+enum Bar { W_FULL = 0, W_EMPTY = 4, D_FULL = 8, A_READY = 10, PASS_DONE = 12, PE_READY = 14, PE_FREE = 16, W_FULLP = 18, N_BARS = 22 };
 
 struct Step {
   int n_chunks;    // 16 KB weight chunks streamed for this step
@@ -79,10 +80,14 @@ struct TcArgs {
   int64_t n_pass;         // ceil(tiles / 2)
   float* raw;             // [P,1] or [P,9]
   int* error_flag;
+  unsigned long long* prof;  // optional [gridDim.x][16] cycle counters (DFB_TC_PROF builds)
   // fp32 biases and head weights, read through the constant bank (warp-uniform addresses):
   // bias[s][256] for every step, then sigma_w[256], rgb_w[3][128], trgb_w[3][128], tsig_w[128],
   // tbeta_w[128], scalars {sigma_b, rgb_b[3], trgb_b[3], tsig_b, tbeta_b}
   float tbl[kTblFloats];
+  // the same per-step biases as packed 16-bit pairs (fp16 or bf16, matching the MMA kind) for the
+  // packed-math epilogue of the plain hidden layers: btbl[s*128 + j] = {bias[2j], bias[2j+1]}
+  uint32_t btbl[kMaxSteps * 128];
 };
 
 // ---------------------------------------------------------------------------------------
@@ -115,12 +120,52 @@ __device__ __forceinline__ uint64_t globaltimer() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+#ifdef DFB_TC_PROF
+#define PROF_DECL unsigned long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long prof_t0 = clock64();
+#define PROF_WAIT(slot, stmt) { const long long _t = clock64(); stmt; prof_acc[slot] += clock64() - _t; }
+#define PROF_PTR prof_acc
+#define PROF_FLUSH(base)                                                                   \
+  if (a.prof && (threadIdx.x & 31) == 0) {                                                 \
+    for (int _i = 0; _i < 3; ++_i) a.prof[(size_t)blockIdx.x * 16 + (base) + _i] = prof_acc[_i]; \
+    a.prof[(size_t)blockIdx.x * 16 + (base) + 3] = clock64() - prof_t0;                    \
+  }
+#else
+#define PROF_DECL
+#define PROF_WAIT(slot, stmt) { stmt; }
+#define PROF_PTR nullptr
+#define PROF_FLUSH(base)
+#endif
+
 // Bounded wait: a protocol bug must fail the launch, not hang the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* error_flag) {
   if (mbar_try_wait(bar, parity)) return;
   const uint64_t t0 = globaltimer();
   while (!mbar_try_wait(bar, parity)) {
     if (globaltimer() - t0 > 4000000000ull) {  // 4 s
+      if (error_flag) atomicExch(error_flag, 1 + (int)(bar & 0xff));
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// wait on a barrier that threads of the peer CTA arrive on (acquire at cluster scope)
+template <int CG>
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int* error_flag) {
+  if (CG == 1) { mbar_wait(bar, parity, error_flag); return; }
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const uint64_t t0 = globaltimer();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (globaltimer() - t0 > 4000000000ull) {
       if (error_flag) atomicExch(error_flag, 1 + (int)(bar & 0xff));
       __trap();
     }
@@ -137,24 +182,77 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                : "memory");
 }
 
+template <int CG = 1>
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (CG == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
 }
+template <int CG = 1>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+  if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+  else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
+// All previously issued MMAs of this thread complete -> one arrival on `bar`
+// (CG 2: on the barrier at the same offset in BOTH CTAs of the pair).
+template <int CG = 1>
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  if (CG == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  } else {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
+  }
 }
 // D[tmem] (+)= A[smem] * B[smem]^T, kind::f16 (fp16 or bf16 operands, fp32 accumulate)
+template <int CG = 1>
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  if (CG == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+  }
+}
+
+// ---- cluster helpers (CTA pair) ----------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at local address `bar` of CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+      "r"(cta)
       : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void arrive_leader(uint32_t bar) {
+  if (CG == 1) mbar_arrive(bar);
+  else mbar_arrive_cluster(bar, 0);
 }
 
 __device__ __forceinline__ bool elect_one() {
@@ -217,8 +315,33 @@ template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, fl
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// packed 16-bit epilogue math: relu(x + b) and x + b on two lanes at once
+template <typename T> __device__ __forceinline__ uint32_t add_relu2(uint32_t x, uint32_t b);
+template <> __device__ __forceinline__ uint32_t add_relu2<__half>(uint32_t x, uint32_t b) {
+  const __half2 one = __floats2half2_rn(1.f, 1.f);
+  __half2 r = __hfma2_relu(*reinterpret_cast<__half2*>(&x), one, *reinterpret_cast<__half2*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+template <> __device__ __forceinline__ uint32_t add_relu2<__nv_bfloat16>(uint32_t x, uint32_t b) {
+  const __nv_bfloat162 one = __floats2bfloat162_rn(1.f, 1.f);
+  __nv_bfloat162 r = __hfma2_relu(*reinterpret_cast<__nv_bfloat162*>(&x), one, *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+template <typename T> __device__ __forceinline__ uint32_t add2(uint32_t x, uint32_t b);
+template <> __device__ __forceinline__ uint32_t add2<__half>(uint32_t x, uint32_t b) {
+  __half2 r = __hadd2(*reinterpret_cast<__half2*>(&x), *reinterpret_cast<__half2*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+template <> __device__ __forceinline__ uint32_t add2<__nv_bfloat16>(uint32_t x, uint32_t b) {
+  __nv_bfloat162 r = __hadd2(*reinterpret_cast<__nv_bfloat162*>(&x), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+__device__ __forceinline__ void st_shared_b16(uint32_t addr, uint16_t v) {
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
 }
 
 __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
@@ -227,7 +350,7 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-
 // ---------------------------------------------------------------------------------------
 // epilogue building block: one 32-column block of the accumulator row of this thread
 // ---------------------------------------------------------------------------------------
-enum EpiKind { EPI_HIDDEN, EPI_HIDDEN_SIGMA, EPI_SIGMA_ONLY, EPI_FINAL, EPI_DT, EPI_T, EPI_T_LAST };
+enum EpiKind { EPI_HIDDEN, EPI_HIDDEN_SIGMA, EPI_SIGMA_ONLY, EPI_FINAL, EPI_DT_HEAD, EPI_DT_STORE, EPI_T, EPI_T_LAST };
 
 struct EpiCtx {
   float sig, rgb[3], hd[5];
@@ -240,14 +363,31 @@ __device__ __forceinline__ float dot32c(const float (&x)[32], const TcArgs& a, i
   return acc;
 }
 
-// One 32-column block of this thread's accumulator row: add bias (constant bank) or the per-ray
-// bias (global), activation, fp32 head dot products, 16-bit store of the next layer's A operand.
-template <typename T, int KIND, int CB>
-__device__ __forceinline__ void epi_block(const uint32_t (&v)[32], const TcArgs& a, int bias_off,
+// One 32-column block (columns cb*32 .. cb*32+31) of this thread's accumulator row: add bias
+// (constant bank) or the per-ray bias (global), activation, fp32 head dot products, 16-bit store
+// of the next layer's A operand.
+template <typename T, int KIND>
+__device__ __forceinline__ void epi_block(const uint32_t (&v)[32], const TcArgs& a, int bias_off, int cb,
                                           const float* __restrict__ rb, uint32_t h_row, EpiCtx& cx) {
+  if (KIND == EPI_HIDDEN || KIND == EPI_T || KIND == EPI_FINAL) {
+    // Plain hidden layer: round the fp32 accumulators to the 16-bit operand type first, then
+    // bias + ReLU as ONE packed HFMA2.RELU per column pair (the rounding this adds is of the same
+    // size as the operand rounding the next MMA applies anyway).
+    const int off = (bias_off >> 1) + cb * 16;
+    uint32_t pk[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const uint32_t xx = pack2<T>(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
+      pk[q] = KIND == EPI_FINAL ? add2<T>(xx, a.btbl[off + q]) : add_relu2<T>(xx, a.btbl[off + q]);
+    }
+    const uint32_t dst = h_row + (uint32_t)(cb * 4) * kPanelBytes;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) st_shared_v4(dst + q * kPanelBytes, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+    return;
+  }
   float x[32];
-  if (KIND == EPI_DT) {
-    const float4* b4 = reinterpret_cast<const float4*>(rb + CB * 32);
+  if (KIND == EPI_DT_HEAD || KIND == EPI_DT_STORE) {
+    const float4* b4 = reinterpret_cast<const float4*>(rb + cb * 32);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const float4 bb = __ldg(b4 + q);
@@ -257,169 +397,235 @@ __device__ __forceinline__ void epi_block(const uint32_t (&v)[32], const TcArgs&
       x[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bb.w;
     }
   } else {
+    const int off = bias_off + cb * 32;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + a.tbl[bias_off + CB * 32 + j];
+    for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + a.tbl[off + j];
   }
   if (KIND != EPI_FINAL) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
   }
-  if (KIND == EPI_HIDDEN_SIGMA || KIND == EPI_SIGMA_ONLY) cx.sig = dot32c(x, a, kTblSigmaW + CB * 32, cx.sig);
-  if (KIND == EPI_DT && CB < 4) {
+  if (KIND == EPI_HIDDEN_SIGMA || KIND == EPI_SIGMA_ONLY) cx.sig = dot32c(x, a, kTblSigmaW + cb * 32, cx.sig);
+  if (KIND == EPI_DT_HEAD) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) cx.rgb[c] = dot32c(x, a, kTblRgbW + c * 128 + CB * 32, cx.rgb[c]);
+    for (int c = 0; c < 3; ++c) cx.rgb[c] = dot32c(x, a, kTblRgbW + c * 128 + cb * 32, cx.rgb[c]);
   }
   if (KIND == EPI_T_LAST) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) cx.hd[c] = dot32c(x, a, kTblTrgbW + c * 128 + CB * 32, cx.hd[c]);
-    cx.hd[3] = dot32c(x, a, kTblTsigW + CB * 32, cx.hd[3]);
-    cx.hd[4] = dot32c(x, a, kTblTbetaW + CB * 32, cx.hd[4]);
+    for (int c = 0; c < 3; ++c) cx.hd[c] = dot32c(x, a, kTblTrgbW + c * 128 + cb * 32, cx.hd[c]);
+    cx.hd[3] = dot32c(x, a, kTblTsigW + cb * 32, cx.hd[3]);
+    cx.hd[4] = dot32c(x, a, kTblTbetaW + cb * 32, cx.hd[4]);
   }
   constexpr bool kStore = KIND == EPI_HIDDEN || KIND == EPI_HIDDEN_SIGMA || KIND == EPI_FINAL || KIND == EPI_T ||
-                          (KIND == EPI_DT && CB >= 4);
+                          KIND == EPI_DT_STORE;
   if (kStore) {
-    constexpr int panel0 = (KIND == EPI_DT ? CB - 4 : CB) * 4;
+    const uint32_t dst = h_row + (uint32_t)((KIND == EPI_DT_STORE ? cb - 4 : cb) * 4) * kPanelBytes;
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-      st_shared_v4(h_row + (panel0 + q) * kPanelBytes, pack2<T>(x[8 * q], x[8 * q + 1]), pack2<T>(x[8 * q + 2], x[8 * q + 3]),
+      st_shared_v4(dst + q * kPanelBytes, pack2<T>(x[8 * q], x[8 * q + 1]), pack2<T>(x[8 * q + 2], x[8 * q + 3]),
                    pack2<T>(x[8 * q + 4], x[8 * q + 5]), pack2<T>(x[8 * q + 6], x[8 * q + 7]));
   }
 }
 
-template <typename T, int KIND, int CB, int NBLK>
-struct EpiLoop {
-  // v_cur holds block CB (load already issued); v_nxt receives block CB+1 while CB is processed
-  static __device__ __forceinline__ void run(uint32_t t_row, uint32_t h_row, const TcArgs& a, int bias_off,
-                                             const float* rb, EpiCtx& cx, uint32_t (&v_cur)[32], uint32_t (&v_nxt)[32]) {
-    tmem_ld_wait(v_cur);
-    if (CB + 1 < NBLK) tmem_ld32(t_row + (CB + 1) * 32, v_nxt);
-    epi_block<T, KIND, CB>(v_cur, a, bias_off, rb, h_row, cx);
-    EpiLoop<T, KIND, CB + 1, NBLK>::run(t_row, h_row, a, bias_off, rb, cx, v_nxt, v_cur);
-  }
-};
-template <typename T, int KIND, int NBLK>
-struct EpiLoop<T, KIND, NBLK, NBLK> {
-  static __device__ __forceinline__ void run(uint32_t, uint32_t, const TcArgs&, int, const float*, EpiCtx&, uint32_t (&)[32],
-                                             uint32_t (&)[32]) {}
-};
-
-// A whole step: software-pipelined TMEM reads (block CB+1 in flight while CB is processed).
-template <typename T, int KIND, int NBLK>
-__device__ __forceinline__ void epi_step(uint32_t t_row, uint32_t h_row, const TcArgs& a, int bias_off, const float* rb,
-                                         EpiCtx& cx) {
+// Blocks [cb0, cb1) of a step (cb1 - cb0 even): software-pipelined TMEM reads, block cb+1 is in
+// flight while block cb is processed.  A runtime loop (two blocks per trip) keeps the code small
+// enough for the instruction cache, which the MMA issuer shares.
+template <typename T, int KIND>
+__device__ __forceinline__ void epi_blocks(uint32_t t_row, uint32_t h_row, const TcArgs& a, int bias_off, int cb0, int cb1,
+                                           const float* rb, EpiCtx& cx) {
   uint32_t v0[32], v1[32];
-  tmem_ld32(t_row, v0);
-  EpiLoop<T, KIND, 0, NBLK>::run(t_row, h_row, a, bias_off, rb, cx, v0, v1);
+  tmem_ld32(t_row + cb0 * 32, v0);
+#pragma unroll 1
+  for (int cb = cb0; cb < cb1; cb += 2) {
+    tmem_ld_wait(v0);
+    tmem_ld32(t_row + (cb + 1) * 32, v1);
+    epi_block<T, KIND>(v0, a, bias_off, cb, rb, h_row, cx);
+    tmem_ld_wait(v1);
+    if (cb + 2 < cb1) tmem_ld32(t_row + (cb + 2) * 32, v0);
+    epi_block<T, KIND>(v1, a, bias_off, cb + 1, rb, h_row, cx);
+  }
 }
 
-template <typename T, int FULL>
-__global__ void __launch_bounds__(kThreads, 1) k_mlp_tc(const __grid_constant__ TcArgs a) {
+// MMA issue for one (step, slot): KS K=16 MMAs per weight stage.  Kept as lean as possible:
+// this single warp paces the tensor pipe.
+template <int CG, int KS>
+__device__ __forceinline__ void issue_step(uint32_t& stage, uint32_t& phase, int nch, uint32_t a_lo, uint32_t b_rows,
+                                           uint32_t d_tmem, uint32_t idesc, uint32_t sW, uint32_t sBar, int* err,
+                                           unsigned long long* prof_acc) {
+  const uint32_t desc_hi = (128u >> 4) | (1u << 14);  // SBO 128 B, descriptor version 1, no swizzle
+  const uint32_t b_step = 2u * b_rows;                // (2 panels * b_rows * 16 B) >> 4
+  uint32_t acc = 0;
+  if (CG == 1) {
+    // Stages are filled and waited for in PAIRS (one "full" barrier per two 16 KB stages, see the
+    // producer) but released one by one: half the mbarrier waits / elect blocks per MMA.
+#pragma unroll 1
+    for (int c = 0; c < nch; c += 2) {
+      PROF_WAIT(0, mbar_wait(sBar + 8u * (W_FULL + stage), phase, err));
+      tc_fence_after();
+      const uint32_t b_lo = ((sW + stage * kChunkBytes) >> 4) | (b_rows << 16);
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+          umma_f16<CG>(d_tmem, mk64(a_lo + ks * 256, desc_hi), mk64(b_lo + ks * b_step, desc_hi), idesc, acc | ks);
+        umma_commit<CG>(sBar + 8u * (W_EMPTY + stage));
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+          umma_f16<CG>(d_tmem, mk64(a_lo + (KS + ks) * 256, desc_hi),
+                       mk64(b_lo + (kChunkBytes >> 4) + ks * b_step, desc_hi), idesc, 1u);
+        umma_commit<CG>(sBar + 8u * (W_EMPTY + stage + 1));
+      }
+      __syncwarp();
+      a_lo += 512u * KS;
+      acc = 1;
+      stage += 2;
+      if (stage == kStages) stage = 0, phase ^= 1;
+    }
+    return;
+  }
+#pragma unroll 1
+  for (int c = 0; c < nch; ++c) {
+    PROF_WAIT(0, mbar_wait(sBar + 8u * (W_FULL + stage), phase, err));
+    if (CG == 2) PROF_WAIT(1, mbar_wait_cluster<CG>(sBar + 8u * (W_FULLP + stage), phase, err));
+    tc_fence_after();
+    const uint32_t b_lo = ((sW + stage * kChunkBytes) >> 4) | (b_rows << 16);
+    if (elect_one()) {
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks)
+        umma_f16<CG>(d_tmem, mk64(a_lo + ks * 256, desc_hi), mk64(b_lo + ks * b_step, desc_hi), idesc, acc | ks);
+      umma_commit<CG>(sBar + 8u * (W_EMPTY + stage));
+    }
+    __syncwarp();
+    a_lo += 256u * KS;
+    acc = 1;
+    if (++stage == kStages) stage = 0, phase ^= 1;
+  }
+}
+
+// Kernel body, shared by the 1-CTA (CG = 1) and CTA-pair (CG = 2, cta_group::2) variants.
+//
+// CG = 2: two CTAs of a cluster work on one 256-row tile per slot.  Each CTA keeps its own 128
+// rows (A operand, TMEM accumulators, epilogue) and HALF of every weight chunk (its N/2 rows of
+// B); the leader CTA issues tcgen05.mma.cta_group::2 for the pair, so one instruction feeds both
+// SMs' tensor cores, every weight byte is fetched from L2 once per 256 rows, and the MMA issue
+// overhead per row halves.  Cross-CTA signalling: tcgen05.commit multicasts to the barriers of
+// both CTAs; epilogue / encoder threads of the peer arrive remotely on the leader's barriers
+// (mapa + mbarrier.arrive.release.cluster); the peer's otherwise idle MMA warp relays its local
+// weight-stage "full" barriers to the leader.
+template <typename T, int FULL, int CG>
+__device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sA = smem_u32(smem);
   const uint32_t sW = sA + kSmemA;
   const uint32_t sBar = sW + kSmemW;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmemA + kSmemW + N_BARS * 8);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
   auto bar = [&](int i) { return sBar + 8u * i; };
   const int fmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  const int64_t unit0 = blockIdx.x / CG, n_units = gridDim.x / CG;  // a unit = CTA (CG 1) or CTA pair (CG 2)
 
   if (tid == 0) {
-    for (int i = 0; i < kStages; ++i) mbar_init(bar(W_FULL + i), 1), mbar_init(bar(W_EMPTY + i), 1);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(bar(W_FULL + i), 1), mbar_init(bar(W_EMPTY + i), 1);
+      mbar_init(bar(W_FULLP + i), 1);
+    }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar(D_FULL + s), 1);
-      mbar_init(bar(A_READY + s), 128);
-      mbar_init(bar(PASS_DONE + s), 128);
-      mbar_init(bar(PE_READY + s), 128);
+      mbar_init(bar(A_READY + s), 128 * CG);
+      mbar_init(bar(PASS_DONE + s), 128 * CG);
+      mbar_init(bar(PE_READY + s), 128 * CG);
       mbar_init(bar(PE_FREE + s), 1);
     }
     fence_barrier_init();
   }
-  if (warp == 13) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (warp == 13) tmem_alloc<CG>(smem_u32(tmem_slot), 512);
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int n_steps = a.n_steps;
 
   if (warp == 12) {
     // ===== weight producer (warp-uniform control flow, one elected lane issues) ============
+    PROF_DECL
     uint32_t stage = 0, phase = 0;
-    const uint8_t* wimg = reinterpret_cast<const uint8_t*>(a.wimg);
-    for (int64_t p = blockIdx.x; p < a.n_pass; p += gridDim.x)
+    const uint8_t* wimg = reinterpret_cast<const uint8_t*>(a.wimg) + (size_t)rank * kChunkBytes;
+    for (int64_t p = unit0; p < a.n_pass; p += n_units)
       for (int s = 0; s < n_steps; ++s) {
         const int nch = a.steps[s].n_chunks;
-        const uint8_t* src0 = wimg + (size_t)a.steps[s].chunk_base * kChunkBytes;
+        const uint8_t* src0 = wimg + (size_t)a.steps[s].chunk_base * (kChunkBytes * CG);
         for (int slot = 0; slot < 2; ++slot) {
           const uint8_t* src = src0;
-          for (int c = 0; c < nch; ++c, src += kChunkBytes) {
-            mbar_wait(bar(W_EMPTY + stage), phase ^ 1, a.error_flag);
+          for (int c = 0; c < nch; ++c, src += kChunkBytes * CG) {
+            PROF_WAIT(0, mbar_wait(bar(W_EMPTY + stage), phase ^ 1, a.error_flag));
             if (elect_one()) {
-              mbar_expect_tx(bar(W_FULL + stage), kChunkBytes);
-              bulk_g2s(sW + stage * kChunkBytes, src, kChunkBytes, bar(W_FULL + stage));
+              if (CG == 1) {
+                // one "full" barrier per stage pair: armed with both stages' bytes by the even stage
+                if ((stage & 1) == 0) mbar_expect_tx(bar(W_FULL + stage), 2 * kChunkBytes);
+                bulk_g2s(sW + stage * kChunkBytes, src, kChunkBytes, bar(W_FULL + (stage & ~1u)));
+              } else {
+                mbar_expect_tx(bar(W_FULL + stage), kChunkBytes);
+                bulk_g2s(sW + stage * kChunkBytes, src, kChunkBytes, bar(W_FULL + stage));
+              }
             }
             __syncwarp();
             if (++stage == kStages) stage = 0, phase ^= 1;
           }
+        }
+      }
+    PROF_FLUSH(0)
+  } else if (warp == 13 && rank != 0) {
+    // ===== peer CTA: relay "my half of the weight stage has landed" to the leader ============
+    uint32_t stage = 0, phase = 0;
+    for (int64_t p = unit0; p < a.n_pass; p += n_units)
+      for (int s = 0; s < n_steps; ++s) {
+        const int nch = 2 * a.steps[s].n_chunks;
+        for (int c = 0; c < nch; ++c) {
+          mbar_wait(bar(W_FULL + stage), phase, a.error_flag);
+          if (elect_one()) mbar_arrive_cluster(bar(W_FULLP + stage), 0);
+          __syncwarp();
+          if (++stage == kStages) stage = 0, phase ^= 1;
         }
       }
   } else if (warp == 13) {
     // ===== MMA issuer (warp-uniform control flow, one elected lane issues) ===================
+    PROF_DECL
     uint32_t stage = 0, phase = 0;
     int lp = 0;
-    // descriptor high word: SBO = 128 B (bits 32..45), version 1 (bit 46), no swizzle
-    const uint32_t desc_hi = (128u >> 4) | (1u << 14);
-    for (int64_t p = blockIdx.x; p < a.n_pass; p += gridDim.x, ++lp)
+    for (int64_t p = unit0; p < a.n_pass; p += n_units, ++lp)
       for (int s = 0; s < n_steps; ++s) {
-        const int nch = a.steps[s].n_chunks, ksteps = a.steps[s].ksteps, nn = a.steps[s].n;
-        const uint32_t idesc = make_idesc(fmt, nn, kTileM);
-        const uint32_t b_step = 2u * nn;  // (2 panels * n*16 B) >> 4
+        const int nch = a.steps[s].n_chunks, nn = a.steps[s].n;
+        const uint32_t idesc = make_idesc(fmt, nn, kTileM * CG);
+        const uint32_t b_rows = nn / CG;  // B rows held by each CTA; LBO = b_rows * 16 B
         for (int slot = 0; slot < 2; ++slot) {
           if (s == 0) {
-            if (lp > 0) mbar_wait(bar(PASS_DONE + slot), (lp - 1) & 1, a.error_flag);
-            mbar_wait(bar(PE_READY + slot), lp & 1, a.error_flag);
+            if (lp > 0) PROF_WAIT(2, mbar_wait_cluster<CG>(bar(PASS_DONE + slot), (lp - 1) & 1, a.error_flag));
+            PROF_WAIT(2, mbar_wait_cluster<CG>(bar(PE_READY + slot), lp & 1, a.error_flag));
           } else {
-            mbar_wait(bar(A_READY + slot), (lp * (n_steps - 1) + s - 1) & 1, a.error_flag);
+            PROF_WAIT(2, mbar_wait_cluster<CG>(bar(A_READY + slot), (lp * (n_steps - 1) + s - 1) & 1, a.error_flag));
           }
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + slot * 256;
           // low word: start address >> 4 | LBO (2048 B >> 4) << 16; one K=16 step advances by 2 panels
-          uint32_t a_lo = ((sA + slot * kSlotBytes + a.steps[s].a_panel0 * kPanelBytes) >> 4) | ((kPanelBytes >> 4) << 16);
-          uint32_t acc = 0;
-          for (int c = 0; c < nch; ++c) {
-            mbar_wait(bar(W_FULL + stage), phase, a.error_flag);
-            tc_fence_after();
-            const uint32_t b_lo = ((sW + stage * kChunkBytes) >> 4) | ((uint32_t)nn << 16);
-            if (elect_one()) {
-              if (ksteps == 2) {
-#pragma unroll
-                for (int ks = 0; ks < 2; ++ks)
-                  umma_f16(d_tmem, mk64(a_lo + ks * 256, desc_hi), mk64(b_lo + ks * b_step, desc_hi), idesc, acc | ks);
-              } else {
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                  umma_f16(d_tmem, mk64(a_lo + ks * 256, desc_hi), mk64(b_lo + ks * b_step, desc_hi), idesc, acc | ks);
-              }
-              umma_commit(bar(W_EMPTY + stage));
-              if (c == nch - 1) {
-                umma_commit(bar(D_FULL + slot));
-                if (s == a.last_pe_step) umma_commit(bar(PE_FREE + slot));
-              }
-            }
-            __syncwarp();
-            a_lo += 256u * ksteps;
-            acc = 1;
-            if (++stage == kStages) stage = 0, phase ^= 1;
+          const uint32_t a_lo = ((sA + slot * kSlotBytes + a.steps[s].a_panel0 * kPanelBytes) >> 4) | ((kPanelBytes >> 4) << 16);
+          if (nn == 256) issue_step<CG, 2 * CG>(stage, phase, nch, a_lo, b_rows, d_tmem, idesc, sW, sBar, a.error_flag, PROF_PTR);
+          else issue_step<CG, 4 * CG>(stage, phase, nch, a_lo, b_rows, d_tmem, idesc, sW, sBar, a.error_flag, PROF_PTR);
+          if (elect_one()) {
+            umma_commit<CG>(bar(D_FULL + slot));
+            if (s == a.last_pe_step) umma_commit<CG>(bar(PE_FREE + slot));
           }
+          __syncwarp();
         }
       }
-  } else if (warp >= 8) {
+    PROF_FLUSH(4)
+  } else if (warp >= 8 && warp < 12) {
     // ===== encoder: positional encoding of the next pass (nerfw.py:128-133) =================
     const int r = tid - 256;
     int lp = 0;
-    for (int64_t p = blockIdx.x; p < a.n_pass; p += gridDim.x, ++lp)
+    for (int64_t p = unit0; p < a.n_pass; p += n_units, ++lp)
       for (int slot = 0; slot < 2; ++slot) {
         if (lp > 0) mbar_wait(bar(PE_FREE + slot), (lp - 1) & 1, a.error_flag);
-        int64_t g = (2 * p + slot) * kTileM + r;
+        int64_t g = ((2 * p + slot) * CG + rank) * kTileM + r;
         g = g < a.P ? g : a.P - 1;
         const int64_t ray = g / a.S;
         const float* rr = a.rayrec + ray * kRayRec;
@@ -427,35 +633,38 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_tc(const __grid_constant__ 
         float pt[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) pt[c] = __fadd_rn(__ldg(rr + c), __fmul_rn(__ldg(rr + 3 + c), zz));
-        float e[64];
-        e[0] = pt[0], e[1] = pt[1], e[2] = pt[2], e[63] = 0.f;
-#pragma unroll
-        for (int l = 0; l < 10; ++l)
+        // column c of the encoding lives at panel c/8, byte (c%8)*2 of this row's 16-byte slot
+        const uint32_t dst = sA + slot * kSlotBytes + kHPanels * kPanelBytes + r * 16;
+        auto put = [&](int col, float v) {
+          T h = (T)v;
+          st_shared_b16(dst + (uint32_t)(col >> 3) * kPanelBytes + (col & 7) * 2, *reinterpret_cast<uint16_t*>(&h));
+        };
+        put(0, pt[0]), put(1, pt[1]), put(2, pt[2]), put(63, 0.f);
+#pragma unroll 1
+        for (int l = 0; l < 10; ++l) {
+          const float fr = (float)(1 << l);
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             float sn, cs;
-            sincosf(__fmul_rn(pt[c], (float)(1 << l)), &sn, &cs);
-            e[3 + 6 * l + c] = sn;
-            e[3 + 6 * l + 3 + c] = cs;
+            sincosf(__fmul_rn(pt[c], fr), &sn, &cs);
+            put(3 + 6 * l + c, sn);
+            put(3 + 6 * l + 3 + c, cs);
           }
-        const uint32_t dst = sA + slot * kSlotBytes + kHPanels * kPanelBytes + r * 16;
-#pragma unroll
-        for (int q = 0; q < kPePanels; ++q)
-          st_shared_v4(dst + q * kPanelBytes, pack2<T>(e[8 * q], e[8 * q + 1]), pack2<T>(e[8 * q + 2], e[8 * q + 3]),
-                       pack2<T>(e[8 * q + 4], e[8 * q + 5]), pack2<T>(e[8 * q + 6], e[8 * q + 7]));
+        }
         fence_proxy_async();
-        mbar_arrive(bar(PE_READY + slot));
+        arrive_leader<CG>(bar(PE_READY + slot));
       }
-  } else {
+  } else if (warp < 8) {
     // ===== epilogue warpgroups (thread = accumulator row = sample) ===========================
     const int slot = warp >> 2;
     const int r = tid & 127;
     const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + slot * 256;
     const uint32_t h_row = sA + slot * kSlotBytes + r * 16;
     EpiCtx cx;
+    PROF_DECL
     uint32_t nd = 0;
-    for (int64_t p = blockIdx.x; p < a.n_pass; p += gridDim.x) {
-      const int64_t g = (2 * p + slot) * kTileM + r;
+    for (int64_t p = unit0; p < a.n_pass; p += n_units) {
+      const int64_t g = ((2 * p + slot) * CG + rank) * kTileM + r;
       const bool valid = g < a.P;
       const int64_t ray = (valid ? g : a.P - 1) / a.S;
       const float* rb = FULL ? a.raybias + ray * 256 : nullptr;
@@ -466,19 +675,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_tc(const __grid_constant__ 
       for (int c = 0; c < 5; ++c) cx.hd[c] = 0.f;
       for (int s = 0; s < n_steps; ++s) {
         const int boff = s * 256;
-        mbar_wait(bar(D_FULL + slot), nd & 1, a.error_flag);
+        PROF_WAIT(0, mbar_wait(bar(D_FULL + slot), nd & 1, a.error_flag));
         ++nd;
         tc_fence_after();
         if (!FULL) {
-          if (s < 7) epi_step<T, EPI_HIDDEN, 8>(t_row, h_row, a, boff, rb, cx);
-          else epi_step<T, EPI_SIGMA_ONLY, 8>(t_row, h_row, a, boff, rb, cx);
+          if (s < 7) epi_blocks<T, EPI_HIDDEN>(t_row, h_row, a, boff, 0, 8, rb, cx);
+          else epi_blocks<T, EPI_SIGMA_ONLY>(t_row, h_row, a, boff, 0, 8, rb, cx);
         } else {
-          if (s < 7) epi_step<T, EPI_HIDDEN, 8>(t_row, h_row, a, boff, rb, cx);
-          else if (s == 7) epi_step<T, EPI_HIDDEN_SIGMA, 8>(t_row, h_row, a, boff, rb, cx);
-          else if (s == 8) epi_step<T, EPI_FINAL, 8>(t_row, h_row, a, boff, rb, cx);
-          else if (s == 9) epi_step<T, EPI_DT, 8>(t_row, h_row, a, boff, rb, cx);
-          else if (s < 12) epi_step<T, EPI_T, 4>(t_row, h_row, a, boff, rb, cx);
-          else epi_step<T, EPI_T_LAST, 4>(t_row, h_row, a, boff, rb, cx);
+          if (s < 7) epi_blocks<T, EPI_HIDDEN>(t_row, h_row, a, boff, 0, 8, rb, cx);
+          else if (s == 7) epi_blocks<T, EPI_HIDDEN_SIGMA>(t_row, h_row, a, boff, 0, 8, rb, cx);
+          else if (s == 8) epi_blocks<T, EPI_FINAL>(t_row, h_row, a, boff, 0, 8, rb, cx);
+          else if (s == 9) {
+            epi_blocks<T, EPI_DT_HEAD>(t_row, h_row, a, boff, 0, 4, rb, cx);
+            epi_blocks<T, EPI_DT_STORE>(t_row, h_row, a, boff, 4, 8, rb, cx);
+          } else if (s < 12) epi_blocks<T, EPI_T>(t_row, h_row, a, boff, 0, 4, rb, cx);
+          else epi_blocks<T, EPI_T_LAST>(t_row, h_row, a, boff, 0, 4, rb, cx);
         }
         if (s == 7) {
           cx.sig = softplus_f(cx.sig + a.tbl[kTblScal]);
@@ -494,16 +705,28 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_tc(const __grid_constant__ 
         }
         tc_fence_before();
         fence_proxy_async();
-        mbar_arrive(bar((s + 1 < n_steps ? A_READY : PASS_DONE) + slot));
+        arrive_leader<CG>(bar((s + 1 < n_steps ? A_READY : PASS_DONE) + slot));
       }
     }
+    if (warp == 0) { PROF_FLUSH(8) }
+    if (warp == 4) { PROF_FLUSH(12) }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync(); else __syncthreads();
   if (warp == 13) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc<CG>(tmem_base, 512);
   }
+}
+
+template <typename T, int FULL>
+__global__ void __launch_bounds__(kThreads, 1) k_mlp_tc(const __grid_constant__ TcArgs a) {
+  mlp_tc_body<T, FULL, 1>(a);
+}
+
+template <typename T, int FULL>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_mlp_tc2(const __grid_constant__ TcArgs a) {
+  mlp_tc_body<T, FULL, 2>(a);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -565,8 +788,6 @@ __global__ void __launch_bounds__(128, 1) k_umma_selftest(const float* A, const 
 // ---------------------------------------------------------------------------------------
 namespace {
 
-struct HostStep { int K, N, a_panel0; };
-
 // 16-bit conversions on the host (round to nearest even), independent of device intrinsics
 uint16_t f2h(float f) { __half h = __float2half_rn(f); uint16_t u; memcpy(&u, &h, 2); return u; }
 uint16_t f2b(float f) { __nv_bfloat16 h = __float2bfloat16_rn(f); uint16_t u; memcpy(&u, &h, 2); return u; }
@@ -576,18 +797,30 @@ uint16_t f2b(float f) { __nv_bfloat16 h = __float2bfloat16_rn(f); uint16_t u; me
 bool tc_supported(const DfbNerf* n, int which, int mode) {
   const NetPack& np = n->net[which];
   if (!np.loaded || np.W != 256 || np.D != 8 || np.skip != 4 || np.pek != 64) return false;
-  if (np.blob16[0] == nullptr || np.blob16[1] == nullptr) return false;
+  if (np.blob16[0][0] == nullptr || np.tc_tbl.empty()) return false;
   if (mode == MLP_SIGMA) return true;
   if (mode == MLP_FULL) return np.fine;
   return false;  // MLP_STATIC (train-mode coarse pass) runs on the fp32 path
 }
 
-// Pack the network into the streaming order of the kernel: for every step, K is cut into
-// 16 KB chunks ([K/8 panels][N rows][8 elements]); see the layout note at the top of the file.
+namespace {
+// logical K / N / first A panel of step s
+void step_shape(int s, int& K, int& N, int& a_panel0) {
+  K = s == 0 ? 64 : (s == 4 ? 320 : (s >= 10 ? 128 : 256));
+  N = s >= 10 ? 128 : 256;
+  a_panel0 = s == 0 ? 32 : 0;
+}
+}  // namespace
+
+// Pack the network into the streaming order of the kernel.  For every step, K is cut into
+// chunks; a chunk is stored as `cg` consecutive 16 KB images, image h holding rows
+// [h*N/cg, (h+1)*N/cg) of B as [K/8 panels][N/cg rows][8 elements] (see the layout note above).
 int pack_tc_weights(DfbNerf* n, int which, const std::vector<std::vector<float>>& P) {
   NetPack& np = n->net[which];
   for (int k = 0; k < 2; ++k)
-    if (np.blob16[k]) { cudaFree(np.blob16[k]); np.blob16[k] = nullptr; }
+    for (int g = 0; g < 2; ++g)
+      if (np.blob16[k][g]) { cudaFree(np.blob16[k][g]); np.blob16[k][g] = nullptr; }
+  np.tc_tbl.clear();
   if (np.W != 256 || np.D != 8 || np.skip != 4 || np.pek != 64) return DFB_OK;  // SIMT only
   const int W = 256, H = 128, in_xyz = np.in_xyz;
   const bool fine = np.fine;
@@ -610,32 +843,38 @@ int pack_tc_weights(DfbNerf* n, int which, const std::vector<std::vector<float>>
     return P[26 + 2 * (s - 10)][(size_t)nn * H + k];  // transient_encoding.{2,4,6}
   };
   const int n_steps = fine ? 13 : 8;
-  std::vector<HostStep> hs;
-  for (int s = 0; s < n_steps; ++s) {
-    HostStep h;
-    h.K = s == 0 ? 64 : (s == 4 ? 320 : (s >= 10 ? 128 : 256));
-    h.N = s >= 10 ? 128 : 256;
-    h.a_panel0 = s == 0 ? 32 : 0;
-    hs.push_back(h);
-  }
-  size_t total_chunks = 0;
-  for (auto& h : hs) total_chunks += (size_t)h.K * h.N * 2 / tc::kChunkBytes;
-  std::vector<uint16_t> img16[2];
-  img16[0].assign(total_chunks * tc::kChunkBytes / 2, 0);
-  img16[1].assign(total_chunks * tc::kChunkBytes / 2, 0);
-  size_t chunk = 0;
-  for (int s = 0; s < n_steps; ++s) {
-    const HostStep& h = hs[s];
-    const int kc = tc::kChunkBytes / (h.N * 2);  // K columns per chunk: 32 (N=256) or 64 (N=128)
-    for (int k0 = 0; k0 < h.K; k0 += kc, ++chunk) {
-      const size_t base = chunk * (tc::kChunkBytes / 2);
-      for (int kk = 0; kk < kc; ++kk)
-        for (int nn = 0; nn < h.N; ++nn) {
-          const float v = wval(s, nn, k0 + kk);
-          const size_t idx = base + (size_t)(kk / 8) * h.N * 8 + (size_t)nn * 8 + kk % 8;
-          img16[0][idx] = f2h(v);
-          img16[1][idx] = f2b(v);
+  for (int cg = 1; cg <= 2; ++cg) {
+    size_t total_imgs = 0;
+    for (int s = 0; s < n_steps; ++s) {
+      int K, N, ap;
+      step_shape(s, K, N, ap);
+      total_imgs += (size_t)K * N * 2 / tc::kChunkBytes;
+    }
+    std::vector<uint16_t> img16[2];
+    img16[0].assign(total_imgs * tc::kChunkBytes / 2, 0);
+    img16[1].assign(total_imgs * tc::kChunkBytes / 2, 0);
+    size_t img = 0;
+    for (int s = 0; s < n_steps; ++s) {
+      int K, N, ap;
+      step_shape(s, K, N, ap);
+      const int rows = N / cg;
+      const int kc = tc::kChunkBytes / (rows * 2);  // K columns per chunk
+      for (int k0 = 0; k0 < K; k0 += kc)
+        for (int h = 0; h < cg; ++h, ++img) {
+          const size_t base = img * (tc::kChunkBytes / 2);
+          for (int kk = 0; kk < kc; ++kk)
+            for (int r = 0; r < rows; ++r) {
+              const float v = wval(s, h * rows + r, k0 + kk);
+              const size_t idx = base + (size_t)(kk / 8) * rows * 8 + (size_t)r * 8 + kk % 8;
+              img16[0][idx] = f2h(v);
+              img16[1][idx] = f2b(v);
+            }
         }
+    }
+    np.blob16_bytes = total_imgs * tc::kChunkBytes;
+    for (int k = 0; k < 2; ++k) {
+      DFB_CHECK_CUDA(cudaMalloc(&np.blob16[k][cg - 1], np.blob16_bytes));
+      DFB_CHECK_CUDA(cudaMemcpy(np.blob16[k][cg - 1], img16[k].data(), np.blob16_bytes, cudaMemcpyHostToDevice));
     }
   }
   // fp32 table read through the constant bank by the epilogue (see TcArgs::tbl)
@@ -654,15 +893,22 @@ int pack_tc_weights(DfbNerf* n, int which, const std::vector<std::vector<float>>
     for (int c = 0; c < 3; ++c) tb[tc::kTblScal + 1 + c] = P[23][c], tb[tc::kTblScal + 4 + c] = P[35][c];
     tb[tc::kTblScal + 7] = P[33][0], tb[tc::kTblScal + 8] = P[37][0];
   }
-  np.blob16_bytes = total_chunks * tc::kChunkBytes;
-  for (int k = 0; k < 2; ++k) {
-    DFB_CHECK_CUDA(cudaMalloc(&np.blob16[k], np.blob16_bytes));
-    DFB_CHECK_CUDA(cudaMemcpy(np.blob16[k], img16[k].data(), np.blob16_bytes, cudaMemcpyHostToDevice));
-  }
   return DFB_OK;
 }
 
 static int* g_error_flag = nullptr;
+static unsigned long long* g_prof = nullptr;
+
+// cta_group used by the tcgen05 kernel.  1 (default) is the faster variant today: with CTA pairs
+// the peer's weight-stage relay sits on the critical path ("cta_group::2").
+// DFB_TC_CTA_GROUP=2 selects the pair kernel.
+static int tc_cta_group() {
+  static int cg = [] {
+    const char* e = getenv("DFB_TC_CTA_GROUP");
+    return (e && e[0] == '2') ? 2 : 1;
+  }();
+  return cg;
+}
 
 int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const float* rayrec, const float* z,
                        const float* raybias, int64_t n_rays, int S, float* raw, cudaStream_t st) {
@@ -675,44 +921,72 @@ int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const
     DFB_CHECK_CUDA(cudaMalloc(&g_error_flag, sizeof(int)));
     DFB_CHECK_CUDA(cudaMemset(g_error_flag, 0, sizeof(int)));
   }
+  const int cg = tc_cta_group();
   tc::TcArgs a = {};
   a.n_steps = full ? 13 : 8;
   a.last_pe_step = 4;
   int cb = 0;
   for (int s = 0; s < a.n_steps; ++s) {
-    const int K = s == 0 ? 64 : (s == 4 ? 320 : (s >= 10 ? 128 : 256));
-    const int N = s >= 10 ? 128 : 256;
-    const int kc = tc::kChunkBytes / (N * 2);
+    int K, N, ap;
+    step_shape(s, K, N, ap);
+    const int kc = tc::kChunkBytes / ((N / cg) * 2);
     a.steps[s].n_chunks = K / kc;
     a.steps[s].ksteps = kc / 16;
     a.steps[s].n = N;
-    a.steps[s].a_panel0 = s == 0 ? 32 : 0;
+    a.steps[s].a_panel0 = ap;
     a.steps[s].chunk_base = cb;
     cb += K / kc;
   }
-  a.wimg = np.blob16[kind == DFB_MMA_F16 ? 0 : 1];
-  if (np.tc_tbl.empty()) {
-    set_error("tcgen05 bias table missing");
-    return DFB_ERR_INVALID;
-  }
+  a.wimg = np.blob16[kind == DFB_MMA_F16 ? 0 : 1][cg - 1];
   memcpy(a.tbl, np.tc_tbl.data(), sizeof(a.tbl));
+  for (int i = 0; i < tc::kMaxSteps * 128; ++i) {
+    const float lo = a.tbl[2 * i], hi = a.tbl[2 * i + 1];
+    a.btbl[i] = kind == DFB_MMA_F16 ? ((uint32_t)f2h(hi) << 16 | f2h(lo)) : ((uint32_t)f2b(hi) << 16 | f2b(lo));
+  }
   a.rayrec = rayrec, a.z = z, a.raybias = raybias, a.S = S, a.P = n_rays * S, a.raw = raw;
   a.error_flag = g_error_flag;
+#ifdef DFB_TC_PROF
+  if (!g_prof) {
+    DFB_CHECK_CUDA(cudaMalloc(&g_prof, 256 * 16 * sizeof(unsigned long long)));
+  }
+  {
+    const char* w = getenv("DFB_TC_PROF_WHICH");
+    if (!w || atoi(w) == which) {
+      DFB_CHECK_CUDA(cudaMemsetAsync(g_prof, 0, 256 * 16 * sizeof(unsigned long long), st));
+      a.prof = g_prof;
+    }
+  }
+#endif
   if (a.P == 0) return DFB_OK;
   const int64_t tiles = (a.P + tc::kTileM - 1) / tc::kTileM;
-  a.n_pass = (tiles + 1) / 2;
-  const int grid = (int)std::min<int64_t>(a.n_pass, nerf->num_sms);
+  a.n_pass = (tiles + 2 * cg - 1) / (2 * cg);
+  const int grid = cg * (int)std::min<int64_t>(a.n_pass, nerf->num_sms / cg);
   auto launch = [&](auto kern) -> int {
     DFB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal));
     kern<<<grid, tc::kThreads, tc::kSmemTotal, st>>>(a);
     DFB_LAUNCH_CHECK();
     return DFB_OK;
   };
-  if (kind == DFB_MMA_F16) return full ? launch(tc::k_mlp_tc<__half, 1>) : launch(tc::k_mlp_tc<__half, 0>);
+  const bool f16 = kind == DFB_MMA_F16;
+  if (cg == 2) {
+    if (f16) return full ? launch(tc::k_mlp_tc2<__half, 1>) : launch(tc::k_mlp_tc2<__half, 0>);
+    return full ? launch(tc::k_mlp_tc2<__nv_bfloat16, 1>) : launch(tc::k_mlp_tc2<__nv_bfloat16, 0>);
+  }
+  if (f16) return full ? launch(tc::k_mlp_tc<__half, 1>) : launch(tc::k_mlp_tc<__half, 0>);
   return full ? launch(tc::k_mlp_tc<__nv_bfloat16, 1>) : launch(tc::k_mlp_tc<__nv_bfloat16, 0>);
 }
 
 }  // namespace dfb
+
+// Debug seam: cycle counters of the last tcgen05 MLP launch (DFB_TC_PROF builds only).
+// out[cta][16]: producer {wait W_EMPTY,-,-,total}, MMA {wait W_FULL, wait W_FULLP, wait A_READY, total},
+// epilogue slot0 {wait D_FULL,-,-,total}, epilogue slot1 {...}.
+extern "C" int dfb_debug_tc_prof(unsigned long long* out_host, int n_cta) {
+  if (!dfb::g_prof) return DFB_ERR_UNSUPPORTED;
+  cudaDeviceSynchronize();
+  cudaMemcpy(out_host, dfb::g_prof, (size_t)n_cta * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  return DFB_OK;
+}
 
 // Debug seam (not used by the product path): single-tile UMMA GEMM through the same descriptor
 // and TMEM code as the MLP kernel.  variant 0 is the layout the kernel uses.

@@ -78,7 +78,8 @@ extern "C" void dfb_nerf_destroy(DfbNerf* n) {
   for (int i = 0; i < 2; ++i) {
     if (n->net[i].blob32) cudaFree(n->net[i].blob32);
     for (int k = 0; k < 2; ++k)
-      if (n->net[i].blob16[k]) cudaFree(n->net[i].blob16[k]);
+      for (int g = 0; g < 2; ++g)
+        if (n->net[i].blob16[k][g]) cudaFree(n->net[i].blob16[k][g]);
   }
   if (n->emb_a) cudaFree(n->emb_a);
   if (n->emb_t) cudaFree(n->emb_t);

@@ -165,6 +165,10 @@ int dfb_profile_read(double* coarse_ms, double* fine_ms, int64_t* coarse_launche
 /* Debug seam, not on the product path: D[128,N] = A[128,K] * B[N,K]^T on one CTA through the
  * same shared-memory descriptors, tcgen05.mma and TMEM loads as the MLP kernel (fp32 in/out,
  * operands rounded to `kind`).  variant 0 = the descriptor convention the kernel uses. */
+/* Debug seam: per-CTA cycle counters of the last tcgen05 MLP launch; only libraries built with
+ * -DDFB_TC_PROF record them (returns DFB_ERR_UNSUPPORTED otherwise). out_host: [n_cta][16] u64. */
+int dfb_debug_tc_prof(unsigned long long* out_host, int n_cta);
+
 int dfb_debug_umma_gemm(const float* A, const float* B, int N, int K, int kind, int variant, float* D, void* stream);
 
 #ifdef __cplusplus
