@@ -1,0 +1,53 @@
+"""Multi-GPU plumbing for the render path: one process per GPU, images (or ray blocks) sharded
+across ranks, no data-path collective (rays are independent; weights are replicated).
+torch.distributed is used only for rendezvous, barriers and gathering small results."""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def dist_info():
+    """(rank, world_size, local_rank) from the torchrun environment (1-process defaults)."""
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
+            int(os.environ.get("LOCAL_RANK", "0")))
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous, balanced partition of range(n_items): the first n_items % world ranks get one
+    extra item.  Returns (start, stop)."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    base, extra = divmod(n_items, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def render_images_sharded(render_one, poses, rank=None, world=None, gather=True):
+    """Render `poses[i]` for the images of this rank with `render_one(i, pose) -> Tensor[H,W,C]`
+    and (optionally) all-gather the results so that every rank returns the full stack in image
+    order (the reference's render_path returns all images, rendering.py:403-458).
+    Ranks may hold different numbers of images; padding keeps the collective shapes equal."""
+    if rank is None or world is None:
+        rank, world, _ = dist_info()
+    start, stop = shard_range(len(poses), rank, world)
+    mine = [render_one(i, poses[i]) for i in range(start, stop)]
+    if world == 1 or not gather:
+        return torch.stack(mine) if mine else None
+    counts = [shard_range(len(poses), r, world) for r in range(world)]
+    max_n = max(b - a for a, b in counts)
+    shape = None
+    if mine:
+        shape = torch.tensor(list(mine[0].shape), device=mine[0].device)
+    shapes = [torch.zeros(3, dtype=torch.long, device=poses[0].device if hasattr(poses[0], "device") else "cpu")
+              for _ in range(world)]
+    me = shape.to(shapes[0].device) if shape is not None else torch.zeros_like(shapes[0])
+    dist.all_gather(shapes, me)
+    full = next(s for s in shapes if int(s.sum()) > 0).tolist()
+    dev, dt = (mine[0].device, mine[0].dtype) if mine else (shapes[0].device, torch.float32)
+    pad = torch.zeros([max_n] + full, device=dev, dtype=dt)
+    for k, m in enumerate(mine):
+        pad[k] = m
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad)
+    return torch.cat([out[r][: b - a] for r, (a, b) in enumerate(counts)], 0)
