@@ -152,6 +152,43 @@ int dfb_raw2outputs(const float* raw, const float* z_vals, int64_t N, int S, int
 int dfb_get_rays(const float* c2w, int row_stride, int H, int W, float focal, float* rays_o, float* rays_d,
                  void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * DFNet feature extractor and feature losses
+ *   (feature/dfnet.py:42-172 AdaptLayers + DFNet/DFNet_s, feature/direct_feature_matching.py:114-136)
+ * ---------------------------------------------------------------------------------- */
+typedef struct DfbConv DfbConv;
+typedef struct DfbDfnet DfbDfnet;
+
+/* One convolution layer (nn.Conv2d, stride 1, "same" padding, kernel 1/3/5, Cout % 64 == 0) with an
+ * optional folded eval-mode BatchNorm (y = scale * (conv + bias) + shift).  weight [Cout,Cin,KH,KW]. */
+int dfb_conv_create(int Cin, int Cout, int KH, int KW, const float* weight, const float* bias, const float* bn_scale,
+                    const float* bn_shift, DfbConv** out);
+void dfb_conv_destroy(DfbConv* conv);
+/* in: NHWC fp16 [B,H,W,round_up(Cin,8)].  Outputs (any subset, NULL = skip): out NHWC fp16 after the
+ * optional ReLU, tap NHWC fp16 before it, out_nchw32 fp32 [B,Cout,H,W] before it. */
+int dfb_conv_fwd(DfbConv* conv, const void* in_nhwc16, int B, int H, int W, int relu, void* out_nhwc16, void* tap_nhwc16,
+                 float* out_nchw32, void* stream);
+
+/* n_levels: 3 = DFNet (taps conv1_2, conv3_3, conv5_3), 1 = DFNet_s (conv1_2 only). */
+int dfb_dfnet_create(int n_levels, DfbDfnet** out);
+void dfb_dfnet_destroy(DfbDfnet* net);
+/* params (fp32, host or device): 13 x (encoder conv weight, bias) in VGG-16 order, then per level
+ * (conv1x1 w, b, conv5x5 w, b, bn weight, bn bias, bn running_mean, bn running_var), then fc_pose w, b.
+ * BatchNorm is folded in eval mode (freezeBN / model.eval(), feature/dfnet.py heads). */
+int dfb_dfnet_load(DfbDfnet* net, const float* const* params, const int64_t* numel, int n_params, float bn_eps);
+int dfb_dfnet_workspace_bytes(const DfbDfnet* net, int B, int H, int W, int upH, int upW, size_t* out);
+/* DFNet.forward (feature/dfnet.py:106-172).  x [B,3,H,W] fp32 in [0,1].
+ * flags: bit0 return_feature, bit1 isSingleStream, bit2 return_pose.
+ * feats_t / feats_r: [L, Bs, 128, upH, upW] fp32, Bs = B (single stream; feats_r unused) or B/2
+ * (siamese: first half of the batch -> feats_t, second half -> feats_r).  pose: [B,12]. */
+int dfb_dfnet_fwd(DfbDfnet* net, const float* x, int B, int H, int W, uint32_t flags, int upH, int upW, float* feats_t,
+                  float* feats_r, float* pose, void* ws, size_t ws_bytes, void* stream);
+/* feature_loss: fr, ft fp32 [C,HW]; 1 - mean(cosine) with the cosine over HW per channel
+ * (per_channel = 0, the reference default) or over C per pixel (per_channel = 1).  *loss is a device
+ * scalar; ws needs max(C*64*3, ceil(HW/256)) floats. */
+int dfb_cosine_loss(const float* fr, const float* ft, int C, int64_t HW, int per_channel, float eps, float* loss, void* ws,
+                    size_t ws_bytes, void* stream);
+
 /* Number of kernel launches issued by this library since load (bench.py gpu_launches). */
 int64_t dfb_launch_count(void);
 

@@ -41,3 +41,24 @@ def rel_err(a, b, floor=1e-3):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor))) if a.size else 0.0
+
+
+def synthetic_dfnet(cls_name="DFNet", seed=0):
+    """dfnet_b200 DFNet/DFNet_s with the weights the reference constructor produces under `seed`
+    when torchvision's vgg16 is built without pretrained weights (test infrastructure: pretrained
+    ImageNet weights are not available offline)."""
+    import torchvision
+    from dfnet_b200 import dfnet as my_dfnet
+    state = torch.get_rng_state()
+    torch.manual_seed(seed)
+    vgg = torchvision.models.vgg16(weights=None)
+    net = getattr(my_dfnet, cls_name)()          # builds encoder / heads / fc in the reference's order
+    # the reference takes the encoder from torchvision and only then creates heads and fc_pose:
+    # rebuild those so that they consume the RNG stream exactly like the reference constructor
+    torch.manual_seed(seed)
+    vgg = torchvision.models.vgg16(weights=None)
+    net.encoder.load_state_dict(vgg.features.state_dict())
+    net.adaptation_layers = my_dfnet.AdaptLayers(net.hypercolumn_layers, 128)
+    net.fc_pose = torch.nn.Linear(512, 12)
+    torch.set_rng_state(state)
+    return net.eval()

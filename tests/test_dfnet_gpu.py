@@ -1,0 +1,123 @@
+"""GPU parity tests of the DFNet feature path (tcgen05 implicit-GEMM convolutions, fused losses)
+through the C ABI.  Floating-point kernels: compared with a plain PyTorch fp32 reference of the same
+op and with the reference-generated golden vectors; tolerance 1e-3 of the tensor's magnitude for a
+single layer and for losses, 5e-3 of the feature magnitude through the 13+2-layer fp16 network."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import synthetic_dfnet
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def g():
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "dfnet_golden.npz"))
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def relmax(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-12))
+
+
+@pytest.mark.parametrize("cin,cout,k,B,H,W,relu", [
+    (3, 64, 3, 2, 48, 64, 1), (64, 128, 3, 1, 37, 53, 1), (256, 64, 1, 2, 12, 16, 1), (64, 128, 5, 1, 48, 64, 0),
+    (512, 512, 3, 1, 30, 40, 1), (128, 256, 3, 3, 9, 7, 0)])
+def test_conv_layer_vs_torch_fp32(cin, cout, k, B, H, W, relu):
+    from dfnet_b200._lib import lib, check
+    torch.manual_seed(cin * 7 + cout + k)
+    w = torch.randn(cout, cin, k, k, device=dev()) * (2.0 / (cin * k * k)) ** 0.5
+    b = torch.randn(cout, device=dev()) * 0.1
+    x = torch.randn(B, cin, H, W, device=dev())
+    cin_pad = (cin + 7) // 8 * 8
+    xh = torch.zeros(B, H, W, cin_pad, device=dev(), dtype=torch.float16)
+    xh[..., :cin] = x.permute(0, 2, 3, 1).half()
+    xr = xh[..., :cin].float().permute(0, 3, 1, 2)            # the values the kernel actually sees
+    want_pre = F.conv2d(xr, w.half().float(), b, padding=k // 2)
+    want = F.relu(want_pre) if relu else want_pre
+    h = C.c_void_p()
+    check(lib.dfb_conv_create(cin, cout, k, k, C.c_void_p(w.data_ptr()), C.c_void_p(b.data_ptr()), None, None, C.byref(h)))
+    out = torch.empty(B, H, W, cout, device=dev(), dtype=torch.float16)
+    tap = torch.empty_like(out)
+    nchw = torch.empty(B, cout, H, W, device=dev())
+    check(lib.dfb_conv_fwd(h, C.c_void_p(xh.data_ptr()), B, H, W, relu, C.c_void_p(out.data_ptr()),
+                           C.c_void_p(tap.data_ptr()), C.c_void_p(nchw.data_ptr()), None))
+    torch.cuda.synchronize()
+    lib.dfb_conv_destroy(h)
+    assert relmax(nchw.cpu().numpy(), want_pre.cpu().numpy()) < 1e-4        # fp32 output: accumulation order only
+    assert relmax(out.float().permute(0, 3, 1, 2).cpu().numpy(), want.cpu().numpy()) < 1e-3
+    assert relmax(tap.float().permute(0, 3, 1, 2).cpu().numpy(), want_pre.cpu().numpy()) < 1e-3
+
+
+@pytest.mark.parametrize("tag,cls,L", [("dfnet", "DFNet", 3), ("dfnet_s", "DFNet_s", 1)])
+def test_dfnet_forward_vs_reference_golden(g, tag, cls, L):
+    net = synthetic_dfnet(cls).to(dev())
+    x = torch.tensor(g[f"{tag}_x"], device=dev())
+    feats, pose = net(x, return_feature=True, isSingleStream=False, return_pose=True, upsampleH=48, upsampleW=64)
+    torch.cuda.synchronize()
+    assert feats[0].shape == (L, 1, 128, 48, 64) and pose.shape == (2, 12)
+    assert relmax(pose.cpu().numpy(), g[f"{tag}_pose"]) < 5e-3
+    for nm, f in (("t", feats[0]), ("r", feats[1])):
+        got = f[:, :, ::8, ::4, ::4].cpu().numpy()
+        want = g[f"{tag}_feat_{nm}_sub"]
+        for l in range(L):   # per level: the three levels have different magnitudes
+            assert relmax(got[l], want[l]) < 5e-3, (nm, l)
+        st = g[f"{tag}_feat_{nm}_stats"]
+        assert abs(float(f.abs().sum().double()) - st[1]) / st[1] < 2e-3
+    fs, none = net(x, return_feature=True, isSingleStream=True, return_pose=False, upsampleH=30, upsampleW=40)
+    torch.cuda.synchronize()
+    assert none is None and len(fs) == 1 and fs[0].shape == (L, 2, 128, 30, 40)
+    got, want = fs[0][:, :, ::8, ::4, ::4].cpu().numpy(), g[f"{tag}_feat_s_sub"]
+    for l in range(L):
+        assert relmax(got[l], want[l]) < 5e-3, l
+    none2, pose_only = net(x, return_feature=False)
+    assert none2 is None and torch.equal(pose_only, pose)
+
+
+def test_feature_loss_vs_reference_golden(g):
+    from dfnet_b200.dfnet import feature_loss, preprocess_features_for_loss
+    from oracle import dfnet_oracle as DO
+    net = synthetic_dfnet("DFNet")
+    P = {k: v.numpy() for k, v in net.state_dict().items()}
+    feats, _ = DO.dfnet_forward(P, g["dfnet_x"], single=False, return_pose=False, upH=48, upW=64)  # fp32 features
+    ft = preprocess_features_for_loss(torch.tensor(feats[0]))[0].to(dev())
+    fr = preprocess_features_for_loss(torch.tensor(feats[1]))[0].to(dev())
+    for pc, key in ((False, "loss_per_channel_false"), (True, "loss_per_channel_true")):
+        got = float(feature_loss(fr, ft, per_channel=pc))
+        assert abs(got - float(g[key])) < 1e-5 + 1e-3 * abs(float(g[key])), (pc, got, float(g[key]))
+    got = float(feature_loss(fr[:128].contiguous(), ft[:128].contiguous()))
+    assert abs(got - float(g["loss_lvl0_false"])) < 1e-5 + 1e-3 * abs(float(g["loss_lvl0_false"]))
+    # near-zero-norm rows: each norm is clamped to eps separately (torch >= 1.12 semantics)
+    a = torch.zeros(4, 1000, device=dev())
+    b = torch.randn(4, 1000, device=dev())
+    assert abs(float(feature_loss(a, b, img_in=False)) - 1.0) < 1e-6
+
+
+def test_dfnet_full_size_pair_properties():
+    """BASELINE config[2] shape: a 640x480 target/render pair, level-0 cosine loss."""
+    from dfnet_b200.dfnet import feature_loss
+    net = synthetic_dfnet("DFNet").to(dev())
+    torch.manual_seed(3)
+    img = torch.rand(1, 3, 480, 640, device=dev())
+    x = torch.cat([img, img], 0)
+    feats, pose = net(x, return_feature=True, isSingleStream=False, return_pose=True, upsampleH=480, upsampleW=640)
+    torch.cuda.synchronize()
+    assert feats[0].shape == (3, 1, 128, 480, 640)
+    assert torch.isfinite(feats[0]).all() and torch.isfinite(pose).all()
+    assert torch.equal(feats[0], feats[1])                       # identical images -> identical streams
+    assert torch.equal(pose[0], pose[1])
+    l0 = float(feature_loss(feats[1][0, 0], feats[0][0, 0]))
+    assert abs(l0) < 1e-6                                        # cosine of a tensor with itself
+    y = torch.cat([img, torch.rand(1, 3, 480, 640, device=dev())], 0)
+    f2, _ = net(y, return_feature=True, isSingleStream=False, return_pose=False, upsampleH=480, upsampleW=640)
+    l1 = float(feature_loss(f2[1][0, 0], f2[0][0, 0]))
+    assert 0.0 < l1 < 2.0
