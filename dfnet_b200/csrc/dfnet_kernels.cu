@@ -429,3 +429,149 @@ extern "C" int dfb_cosine_loss(const float* fr, const float* ft, int C, int64_t 
   }
   return DFB_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// triplet loss with in-triplet hard negative mining (feature/misc.py:399-435) and MSE
+// ------------------------------------------------------------------------------------------
+namespace dfb {
+
+__device__ __forceinline__ float block_sum(float v, float* sm) {
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  v = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.f;
+  if (threadIdx.x < 32)
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;  // valid in thread 0
+}
+
+// f1, f2: [L,B,inner]; negatives are the batch-rolled tensors (roll(shifts=1, dims=1): b -> b-1).
+// partial sums of the four squared distances {|f1-roll f2|, |f2-roll f1|, |f1-roll f1|, |f2-roll f2|}
+__global__ void k_triplet_mse_partial(const float* __restrict__ f1, const float* __restrict__ f2, int L, int B, int64_t inner,
+                                      float* __restrict__ ws) {
+  const int64_t n = (int64_t)L * B * inner;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t in = i % inner, lb = i / inner;
+    const int b = (int)(lb % B);
+    const int64_t l = lb / B;
+    const int64_t j = (l * B + (b + B - 1) % B) * inner + in;  // rolled index
+    const float a = f1[i], p = f2[i], an = f1[j], ng = f2[j];
+    s[0] = fmaf(a - ng, a - ng, s[0]), s[1] = fmaf(p - an, p - an, s[1]);
+    s[2] = fmaf(a - an, a - an, s[2]), s[3] = fmaf(p - ng, p - ng, s[3]);
+  }
+  __shared__ float sm[32];
+  for (int k = 0; k < 4; ++k) {
+    const float v = block_sum(s[k], sm);
+    if (threadIdx.x == 0) ws[blockIdx.x * 4 + k] = v;
+  }
+}
+
+// sums[4] (deterministic order) and the chosen case (torch.argmin: first minimum)
+__global__ void k_triplet_case(const float* __restrict__ ws, int nblocks, float* __restrict__ sums, int* __restrict__ chosen) {
+  __shared__ float sm[32];
+  float tot[4];
+  for (int k = 0; k < 4; ++k) {
+    float v = 0.f;
+    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) v += ws[i * 4 + k];
+    tot[k] = block_sum(v, sm);
+  }
+  if (threadIdx.x == 0) {
+    int best = 0;
+    for (int k = 0; k < 4; ++k) { sums[k] = tot[k]; if (tot[k] < tot[best]) best = k; }
+    *chosen = best;
+  }
+}
+
+// TripletMarginLoss(margin, p=2, eps=1e-6, reduction='mean') on [L,B,C,H,W]: pairwise_distance over W.
+// one warp per row (l,b,c,h); block partial sums of the hinge -> ws[block]
+__global__ void k_triplet_hinge_partial(const float* __restrict__ f1, const float* __restrict__ f2, int B, int64_t rows_per_b,
+                                        int W, int64_t n_rows, float margin, const int* __restrict__ chosen,
+                                        float* __restrict__ ws) {
+  const int cs = *chosen;
+  // case 0: (a,p,n) = (f1, f2, roll f2); 1: (f2, f1, roll f1); 2: (f1, f2, roll f1); 3: (f2, f1, roll f2)
+  const float* A = (cs == 0 || cs == 2) ? f1 : f2;
+  const float* P = (cs == 0 || cs == 2) ? f2 : f1;
+  const float* N = (cs == 0 || cs == 3) ? f2 : f1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  float acc = 0.f;
+  for (int64_t row = (int64_t)blockIdx.x * wpb + warp; row < n_rows; row += (int64_t)gridDim.x * wpb) {
+    const int64_t lb = row / rows_per_b, rin = row % rows_per_b;
+    const int b = (int)(lb % B);
+    const int64_t l = lb / B;
+    const int64_t rrow = (l * B + (b + B - 1) % B) * rows_per_b + rin;
+    const float* a = A + row * W;
+    const float* p = P + row * W;
+    const float* ng = N + rrow * W;
+    float dap = 0.f, dan = 0.f;
+    for (int x = lane; x < W; x += 32) {
+      const float av = a[x];
+      const float u = av - p[x] + 1e-6f, v = av - ng[x] + 1e-6f;
+      dap = fmaf(u, u, dap), dan = fmaf(v, v, dan);
+    }
+    for (int d = 16; d > 0; d >>= 1) dap += __shfl_xor_sync(0xffffffffu, dap, d), dan += __shfl_xor_sync(0xffffffffu, dan, d);
+    if (lane == 0) acc += fmaxf(sqrtf(dap) - sqrtf(dan) + margin, 0.f);
+  }
+  __shared__ float sm[32];
+  const float v = block_sum(acc, sm);
+  if (threadIdx.x == 0) ws[blockIdx.x] = v;
+}
+
+__global__ void k_scaled_sum(const float* __restrict__ ws, int n, float scale, float* __restrict__ out) {
+  __shared__ float sm[32];
+  float v = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v += ws[i];
+  v = block_sum(v, sm);
+  if (threadIdx.x == 0) *out = v * scale;
+}
+
+__global__ void k_sqdiff_partial(const float* __restrict__ a, const float* __restrict__ b, int64_t n, float* __restrict__ ws) {
+  float s = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float d = a[i] - b[i];
+    s = fmaf(d, d, s);
+  }
+  __shared__ float sm[32];
+  s = block_sum(s, sm);
+  if (threadIdx.x == 0) ws[blockIdx.x] = s;
+}
+
+}  // namespace dfb
+
+// triplet_loss_hard_negative_mining_plus (feature/misc.py:399-435).  f1, f2 fp32 [L,B,C,H,W];
+// *loss and *chosen_case are device scalars; ws >= 8192 floats.
+extern "C" int dfb_triplet_loss(const float* f1, const float* f2, int L, int B, int Cc, int H, int W, float margin, float* loss,
+                                int* chosen_case, void* ws, size_t ws_bytes, void* stream) {
+  DFB_REQUIRE(f1 && f2 && loss && chosen_case && ws, DFB_ERR_INVALID, "null argument");
+  DFB_REQUIRE(L >= 1 && B >= 1 && Cc >= 1 && H >= 1 && W >= 1, DFB_ERR_INVALID, "empty feature stack");
+  DFB_REQUIRE(ws_bytes >= 8192 * 4, DFB_ERR_WORKSPACE, "workspace too small (8192 floats)");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* w = (float*)ws;
+  const int64_t inner = (int64_t)Cc * H * W, n = (int64_t)L * B * inner;
+  const int nb = (int)std::min<int64_t>(1024, (n + 255) / 256);
+  k_triplet_mse_partial<<<nb, 256, 0, st>>>(f1, f2, L, B, inner, w);
+  DFB_LAUNCH_CHECK();
+  k_triplet_case<<<1, 256, 0, st>>>(w, nb, w + 4096, chosen_case);
+  DFB_LAUNCH_CHECK();
+  const int64_t rows_per_b = (int64_t)Cc * H, n_rows = (int64_t)L * B * rows_per_b;
+  const int nb2 = (int)std::min<int64_t>(2048, (n_rows + 7) / 8);
+  k_triplet_hinge_partial<<<nb2, 256, 0, st>>>(f1, f2, B, rows_per_b, W, n_rows, margin, chosen_case, w + 4104);
+  DFB_LAUNCH_CHECK();
+  k_scaled_sum<<<1, 256, 0, st>>>(w + 4104, nb2, 1.f / (float)n_rows, loss);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+// mean((a-b)^2): nn.MSELoss / img2mse (models/nerfw.py:11, feature/direct_feature_matching.py:138-142).
+extern "C" int dfb_mse(const float* a, const float* b, int64_t n, float* out, void* ws, size_t ws_bytes, void* stream) {
+  DFB_REQUIRE(a && b && out && ws && n >= 1, DFB_ERR_INVALID, "null or empty argument");
+  DFB_REQUIRE(ws_bytes >= 1024 * 4, DFB_ERR_WORKSPACE, "workspace too small (1024 floats)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nb = (int)std::min<int64_t>(1024, (n + 255) / 256);
+  k_sqdiff_partial<<<nb, 256, 0, st>>>(a, b, n, (float*)ws);
+  DFB_LAUNCH_CHECK();
+  k_scaled_sum<<<1, 256, 0, st>>>((const float*)ws, nb, 1.f / (float)n, out);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}

@@ -1,0 +1,56 @@
+"""Host mirrors of the loss helpers on the feature path (reference feature/misc.py,
+feature/direct_feature_matching.py, models/nerfw.py)."""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def triplet_loss_hard_negative_mining_plus(f1, f2, margin=1.):
+    """Reference feature/misc.py:399-435.  f1, f2: [lvl, B, C, H, W] -> scalar loss.
+    `.chosen_case` of the returned tensor's companion is available through `last_triplet_case`."""
+    if not f1.is_cuda:
+        raise _lib.DfbError("triplet loss inputs must be CUDA tensors")
+    a, b = f1.detach().float().contiguous(), f2.detach().float().contiguous()
+    L, B, Cc, H, W = a.shape
+    loss = torch.empty((), device=a.device)
+    case = torch.empty((), device=a.device, dtype=torch.int32)
+    ws = torch.empty(8192, device=a.device)
+    check(lib.dfb_triplet_loss(_p(a), _p(b), L, B, Cc, H, W, float(margin), _p(loss), _p(case), _p(ws), ws.numel() * 4, _stream()))
+    triplet_loss_hard_negative_mining_plus.last_case = case
+    return loss
+
+
+def mse(x, y):
+    """nn.MSELoss()(x, y) / img2mse (reference models/nerfw.py:11)."""
+    if not x.is_cuda:
+        raise _lib.DfbError("mse inputs must be CUDA tensors")
+    a, b = x.detach().float().contiguous(), y.detach().float().contiguous()
+    out = torch.empty((), device=a.device)
+    ws = torch.empty(1024, device=a.device)
+    check(lib.dfb_mse(_p(a), _p(b), a.numel(), _p(out), _p(ws), ws.numel() * 4, _stream()))
+    return out
+
+
+img2mse = mse
+
+
+def mse2psnr(x):
+    """-10 * ln(x) / ln(10) (reference models/nerfw.py:12)."""
+    return -10. * torch.log(x) / math.log(10.)
+
+
+def PoseLoss(args, pose_, pose, device=None):
+    """Reference feature/direct_feature_matching.py:138-142."""
+    return mse(pose_.reshape(args.batch_size, 12), pose)

@@ -189,6 +189,16 @@ int dfb_dfnet_fwd(DfbDfnet* net, const float* x, int B, int H, int W, uint32_t f
 int dfb_cosine_loss(const float* fr, const float* ft, int C, int64_t HW, int per_channel, float eps, float* loss, void* ws,
                     size_t ws_bytes, void* stream);
 
+/* triplet_loss_hard_negative_mining_plus (feature/misc.py:399-435): f1, f2 fp32 [L,B,C,H,W];
+ * negatives are the batch-rolled stacks, the in-triplet case is argmin of four MSE distances,
+ * TripletMarginLoss(margin, p=2, eps=1e-6, mean) reduces over W.  *loss, *chosen_case: device
+ * scalars; ws >= 8192 floats. */
+int dfb_triplet_loss(const float* f1, const float* f2, int L, int B, int C, int H, int W, float margin, float* loss,
+                     int* chosen_case, void* ws, size_t ws_bytes, void* stream);
+/* mean((a-b)^2): nn.MSELoss in PoseLoss (feature/direct_feature_matching.py:138-142) and img2mse
+ * (models/nerfw.py:11).  ws >= 1024 floats. */
+int dfb_mse(const float* a, const float* b, int64_t n, float* out, void* ws, size_t ws_bytes, void* stream);
+
 /* Number of kernel launches issued by this library since load (bench.py gpu_launches). */
 int64_t dfb_launch_count(void);
 

@@ -93,3 +93,16 @@ def feature_loss(fr, ft, per_channel=False, eps=1e-6):
     ax = 0 if per_channel else 1
     cos = (a * b).sum(ax) / (np.maximum(np.sqrt((a * a).sum(ax)), eps) * np.maximum(np.sqrt((b * b).sum(ax)), eps))
     return f32(1.0 - cos.mean())
+
+
+def triplet_loss_hnm_plus(f1, f2, margin=1.0):
+    """feature/misc.py:399-435 -> (loss, chosen_case).  TripletMarginLoss(p=2, eps=1e-6, mean):
+    pairwise_distance adds eps to the difference and reduces the LAST dim (W)."""
+    f1 = np.asarray(f1, np.float64)
+    f2 = np.asarray(f2, np.float64)
+    an, ng = np.roll(f1, 1, 1), np.roll(f2, 1, 1)
+    cases = [((f1 - ng) ** 2).mean(), ((f2 - an) ** 2).mean(), ((f1 - an) ** 2).mean(), ((f2 - ng) ** 2).mean()]
+    c = int(np.argmin(np.asarray(cases, np.float32)))
+    a, p, n = [(f1, f2, ng), (f2, f1, an), (f1, f2, an), (f2, f1, ng)][c]
+    d = lambda u, v: np.sqrt(((u - v + 1e-6) ** 2).sum(-1))
+    return f32(np.maximum(d(a, p) - d(a, n) + margin, 0).mean()), c

@@ -69,6 +69,21 @@ def main():
             put("loss_per_channel_false", feature_loss(fr, ft, per_channel=False))
             put("loss_per_channel_true", feature_loss(fr, ft, per_channel=True))
             put("loss_lvl0_false", feature_loss(fr[:128], ft[:128], per_channel=False))
+    # triplet loss with in-triplet hard negative mining (feature/misc.py:399-435), all four cases
+    from feature.misc import triplet_loss_hard_negative_mining_plus as ref_triplet
+    rng = np.random.RandomState(11)
+    base = rng.randn(3, 4, 8, 6, 10).astype(np.float32)
+    variants = {
+        0: (base, np.roll(base, -1, 1) + 0.01 * rng.randn(*base.shape).astype(np.float32)),   # f1 ~ roll(f2): case 0
+        1: (np.roll(base, -1, 1) + 0.01 * rng.randn(*base.shape).astype(np.float32), base),   # f2 ~ roll(f1): case 1
+        2: (np.broadcast_to(base[:, :1], base.shape).copy() + 0.01 * rng.randn(*base.shape).astype(np.float32),
+            rng.randn(*base.shape).astype(np.float32)),                                       # f1 constant over b: case 2
+        3: (rng.randn(*base.shape).astype(np.float32),
+            np.broadcast_to(base[:, :1], base.shape).copy() + 0.01 * rng.randn(*base.shape).astype(np.float32)),
+    }
+    for k, (a, b) in variants.items():
+        put(f"trip_{k}_f1", a), put(f"trip_{k}_f2", b)
+        put(f"trip_{k}_loss", ref_triplet(torch.from_numpy(a), torch.from_numpy(b), margin=1.0))
     out = os.path.join(HERE, "dfnet_golden.npz")
     np.savez_compressed(out, **G)
     print("wrote", out, os.path.getsize(out) / 1e3, "KB")

@@ -121,3 +121,26 @@ def test_dfnet_full_size_pair_properties():
     f2, _ = net(y, return_feature=True, isSingleStream=False, return_pose=False, upsampleH=480, upsampleW=640)
     l1 = float(feature_loss(f2[1][0, 0], f2[0][0, 0]))
     assert 0.0 < l1 < 2.0
+
+
+@pytest.mark.parametrize("k", [0, 1, 2, 3])
+def test_triplet_loss_vs_reference_golden(g, k):
+    from dfnet_b200.misc import triplet_loss_hard_negative_mining_plus as trip
+    loss = trip(torch.tensor(g[f"trip_{k}_f1"], device=dev()), torch.tensor(g[f"trip_{k}_f2"], device=dev()), margin=1.0)
+    assert int(trip.last_case) == k
+    assert abs(float(loss) - float(g[f"trip_{k}_loss"])) < 1e-5 + 1e-4 * abs(float(g[f"trip_{k}_loss"]))
+
+
+def test_triplet_and_mse_run_feature_shapes():
+    """run_feature.py shapes: [3, B=4, 128, 60, 80] feature stacks; checked against the oracle."""
+    from dfnet_b200.misc import mse, mse2psnr, triplet_loss_hard_negative_mining_plus as trip
+    from oracle import dfnet_oracle as DO
+    torch.manual_seed(1)
+    f1 = torch.randn(3, 4, 128, 60, 80, device=dev())
+    f2 = f1 + 0.3 * torch.randn_like(f1)
+    want, case = DO.triplet_loss_hnm_plus(f1.cpu().numpy(), f2.cpu().numpy(), 1.0)
+    got = trip(f1, f2, 1.0)
+    assert int(trip.last_case) == case and abs(float(got) - float(want)) < 1e-4 * max(1.0, abs(float(want)))
+    m = mse(f1, f2)
+    assert abs(float(m) - float(((f1 - f2) ** 2).mean())) < 1e-5
+    assert abs(float(mse2psnr(m)) + 10 * np.log10(float(m))) < 1e-4

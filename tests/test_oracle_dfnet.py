@@ -37,3 +37,10 @@ def test_dfnet_forward_oracle(g, tag, cls, L):
         assert abs(DO.feature_loss(fr, ft, False) - g["loss_per_channel_false"]) < 2e-5
         assert abs(DO.feature_loss(fr, ft, True) - g["loss_per_channel_true"]) < 2e-5
         assert abs(DO.feature_loss(fr[:128], ft[:128], False) - g["loss_lvl0_false"]) < 2e-5
+
+
+@pytest.mark.parametrize("k", [0, 1, 2, 3])
+def test_triplet_loss_oracle(g, k):
+    loss, case = DO.triplet_loss_hnm_plus(g[f"trip_{k}_f1"], g[f"trip_{k}_f2"], 1.0)
+    assert case == k                      # the four constructed inputs exercise the four cases
+    assert abs(float(loss) - float(g[f"trip_{k}_loss"])) < 1e-5
