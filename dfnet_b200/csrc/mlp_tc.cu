@@ -57,6 +57,8 @@ constexpr int kTblTbetaW = kTblTsigW + 128;
 constexpr int kTblScal = kTblTbetaW + 128;
 constexpr int kTblFloats = kTblScal + 16;
 
+enum EpiKind { EPI_HIDDEN, EPI_HIDDEN_SIGMA, EPI_SIGMA_ONLY, EPI_FINAL, EPI_DT_HEAD, EPI_DT_STORE, EPI_T, EPI_T_LAST, EPI_DT };
+
 // barrier slots (8 bytes each) inside the kSmemBar region
 enum Bar { W_FULL = 0, W_EMPTY = 4, D_FULL = 8, A_READY = 10, PASS_DONE = 12, PE_READY = 14, PE_FREE = 16, W_FULLP = 18, N_BARS = 22 };
 
@@ -71,6 +73,7 @@ struct Step {
 struct TcArgs {
   Step steps[kMaxSteps];
   int n_steps;
+  int kind[kMaxSteps];    // EpiKind of every step (EPI_DT = head + store halves)
   int last_pe_step;       // last step that reads the PE panels (skip layer)
   const void* wimg;       // packed 16-bit weight image, chunk i at wimg + i*16 KB
   const float* rayrec;    // [n_rays,12]
@@ -111,7 +114,6 @@ struct TcArgs {
 // ---------------------------------------------------------------------------------------
 // epilogue building block: one 32-column block of the accumulator row of this thread
 // ---------------------------------------------------------------------------------------
-enum EpiKind { EPI_HIDDEN, EPI_HIDDEN_SIGMA, EPI_SIGMA_ONLY, EPI_FINAL, EPI_DT_HEAD, EPI_DT_STORE, EPI_T, EPI_T_LAST };
 
 struct EpiCtx {
   float sig, rgb[3], hd[5];
@@ -152,10 +154,11 @@ __device__ __forceinline__ void epi_block(const uint32_t (&v)[32], const TcArgs&
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const float4 bb = __ldg(b4 + q);
-      x[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + bb.x;
-      x[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + bb.y;
-      x[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bb.z;
-      x[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bb.w;
+      // per-ray bias (global) + the step's constant bias (non-zero when xyz_encoding_final is folded in)
+      x[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + (bb.x + a.tbl[bias_off + cb * 32 + 4 * q + 0]);
+      x[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + (bb.y + a.tbl[bias_off + cb * 32 + 4 * q + 1]);
+      x[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + (bb.z + a.tbl[bias_off + cb * 32 + 4 * q + 2]);
+      x[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + (bb.w + a.tbl[bias_off + cb * 32 + 4 * q + 3]);
     }
   } else {
     const int off = bias_off + cb * 32;
@@ -439,24 +442,21 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
         PROF_WAIT(0, mbar_wait(bar(D_FULL + slot), nd & 1, a.error_flag));
         ++nd;
         tc_fence_after();
-        if (!FULL) {
-          if (s < 7) epi_blocks<T, EPI_HIDDEN>(t_row, h_row, a, boff, 0, 8, rb, cx);
-          else epi_blocks<T, EPI_SIGMA_ONLY>(t_row, h_row, a, boff, 0, 8, rb, cx);
-        } else {
-          if (s < 7) epi_blocks<T, EPI_HIDDEN>(t_row, h_row, a, boff, 0, 8, rb, cx);
-          else if (s == 7) epi_blocks<T, EPI_HIDDEN_SIGMA>(t_row, h_row, a, boff, 0, 8, rb, cx);
-          else if (s == 8) epi_blocks<T, EPI_FINAL>(t_row, h_row, a, boff, 0, 8, rb, cx);
-          else if (s == 9) {
-            epi_blocks<T, EPI_DT_HEAD>(t_row, h_row, a, boff, 0, 4, rb, cx);
-            epi_blocks<T, EPI_DT_STORE>(t_row, h_row, a, boff, 4, 8, rb, cx);
-          } else if (s < 12) epi_blocks<T, EPI_T>(t_row, h_row, a, boff, 0, 4, rb, cx);
-          else epi_blocks<T, EPI_T_LAST>(t_row, h_row, a, boff, 0, 4, rb, cx);
-        }
-        if (s == 7) {
+        const int kd = a.kind[s];
+        if (kd == EPI_HIDDEN) epi_blocks<T, EPI_HIDDEN>(t_row, h_row, a, boff, 0, 8, rb, cx);
+        else if (!FULL || kd == EPI_SIGMA_ONLY) epi_blocks<T, EPI_SIGMA_ONLY>(t_row, h_row, a, boff, 0, 8, rb, cx);
+        else if (kd == EPI_HIDDEN_SIGMA) epi_blocks<T, EPI_HIDDEN_SIGMA>(t_row, h_row, a, boff, 0, 8, rb, cx);
+        else if (kd == EPI_FINAL) epi_blocks<T, EPI_FINAL>(t_row, h_row, a, boff, 0, 8, rb, cx);
+        else if (kd == EPI_DT) {
+          epi_blocks<T, EPI_DT_HEAD>(t_row, h_row, a, boff, 0, 4, rb, cx);
+          epi_blocks<T, EPI_DT_STORE>(t_row, h_row, a, boff, 4, 8, rb, cx);
+        } else if (kd == EPI_T) epi_blocks<T, EPI_T>(t_row, h_row, a, boff, 0, 4, rb, cx);
+        else epi_blocks<T, EPI_T_LAST>(t_row, h_row, a, boff, 0, 4, rb, cx);
+        if (kd == EPI_HIDDEN_SIGMA || kd == EPI_SIGMA_ONLY) {
           cx.sig = softplus_f(cx.sig + a.tbl[kTblScal]);
           if (!FULL && valid) a.raw[g] = cx.sig;
         }
-        if (FULL && s == 12 && valid) {
+        if (FULL && kd == EPI_T_LAST && valid) {
           float* o = a.raw + g * 9;
           o[0] = sigmoid_f(cx.rgb[0] + a.tbl[kTblScal + 1]), o[1] = sigmoid_f(cx.rgb[1] + a.tbl[kTblScal + 2]);
           o[2] = sigmoid_f(cx.rgb[2] + a.tbl[kTblScal + 3]), o[3] = cx.sig;
@@ -565,11 +565,36 @@ bool tc_supported(const DfbNerf* n, int which, int mode) {
 }
 
 namespace {
-// logical K / N / first A panel of step s
-void step_shape(int s, int& K, int& N, int& a_panel0) {
-  K = s == 0 ? 64 : (s == 4 ? 320 : (s >= 10 ? 128 : 256));
-  N = s >= 10 ? 128 : 256;
-  a_panel0 = s == 0 ? 32 : 0;
+
+// One MMA step of the streamed program.  `logical`: 0..7 trunk layer, 8 xyz_encoding_final,
+// 9 dir_encoding | transient_encoding.0 (on xyz_encoding_final), 19 the same two layers with
+// xyz_encoding_final folded in (on the trunk output), 10..12 transient_encoding.{2,4,6}.
+struct LStep { int logical, K, N, a_panel0, kind; };
+
+// xyz_encoding_final has no activation, so W_dir*(W_f h + b_f) = (W_dir W_f) h + W_dir b_f: folding it
+// removes one 256x256 layer per fine sample (DFB_TC_FOLD_FINAL=0 keeps the literal layer sequence).
+bool fold_final() {
+  static int f = [] {
+    const char* e = getenv("DFB_TC_FOLD_FINAL");
+    return (e && e[0] == '0') ? 0 : 1;
+  }();
+  return f != 0;
+}
+
+std::vector<LStep> build_program(bool fine) {
+  std::vector<LStep> pr;
+  for (int i = 0; i < 8; ++i)
+    pr.push_back({i, i == 0 ? 64 : (i == 4 ? 320 : 256), 256, i == 0 ? 32 : 0,
+                  i < 7 ? tc::EPI_HIDDEN : (fine ? tc::EPI_HIDDEN_SIGMA : tc::EPI_SIGMA_ONLY)});
+  if (!fine) return pr;
+  if (fold_final()) {
+    pr.push_back({19, 256, 256, 0, tc::EPI_DT});
+  } else {
+    pr.push_back({8, 256, 256, 0, tc::EPI_FINAL});
+    pr.push_back({9, 256, 256, 0, tc::EPI_DT});
+  }
+  for (int i = 0; i < 3; ++i) pr.push_back({10 + i, 128, 128, 0, i < 2 ? tc::EPI_T : tc::EPI_T_LAST});
+  return pr;
 }
 }  // namespace
 
@@ -585,47 +610,58 @@ int pack_tc_weights(DfbNerf* n, int which, const std::vector<std::vector<float>>
   if (np.W != 256 || np.D != 8 || np.skip != 4 || np.pek != 64) return DFB_OK;  // SIMT only
   const int W = 256, H = 128, in_xyz = np.in_xyz;
   const bool fine = np.fine;
-  // value of the logical weight matrix of step s at (n, k)
-  auto wval = [&](int s, int nn, int k) -> float {
-    if (s == 0) return k < in_xyz ? P[0][(size_t)nn * in_xyz + k] : 0.f;
-    if (s < 8) {
-      if (s == 4) {  // K order [h(256) | pe(64)]; torch order is cat([input_xyz, h])
+  const std::vector<LStep> prog = build_program(fine);
+  // dir_encoding[:, :W] stacked on transient_encoding.0[:, :W] (row nn, column k)
+  auto wdt = [&](int nn, int k) -> double {
+    if (nn < H) return P[18][(size_t)nn * (W + np.in_dir + np.a_dim) + k];
+    return P[24][(size_t)(nn - H) * (W + np.t_dim) + k];
+  };
+  std::vector<float> folded_w, folded_b;
+  if (fine && fold_final()) {
+    folded_w.resize((size_t)W * W), folded_b.resize(W);
+    for (int nn = 0; nn < W; ++nn) {
+      double bacc = 0.0;
+      for (int j = 0; j < W; ++j) bacc += wdt(nn, j) * (double)P[17][j];
+      folded_b[nn] = (float)bacc;
+      for (int k = 0; k < W; ++k) {
+        double acc = 0.0;
+        for (int j = 0; j < W; ++j) acc += wdt(nn, j) * (double)P[16][(size_t)j * W + k];
+        folded_w[(size_t)nn * W + k] = (float)acc;
+      }
+    }
+  }
+  // value of the logical weight matrix at (n, k)
+  auto wval = [&](int lg, int nn, int k) -> float {
+    if (lg == 0) return k < in_xyz ? P[0][(size_t)nn * in_xyz + k] : 0.f;
+    if (lg < 8) {
+      if (lg == 4) {  // K order [h(256) | pe(64)]; torch order is cat([input_xyz, h])
         if (k < W) return P[8][(size_t)nn * (W + in_xyz) + in_xyz + k];
         const int c = k - W;
         return c < in_xyz ? P[8][(size_t)nn * (W + in_xyz) + c] : 0.f;
       }
-      return P[2 * s][(size_t)nn * W + k];
+      return P[2 * lg][(size_t)nn * W + k];
     }
-    if (s == 8) return P[16][(size_t)nn * W + k];  // xyz_encoding_final
-    if (s == 9) {                                  // dir_encoding[:, :W] | transient_encoding.0[:, :W]
-      if (nn < H) return P[18][(size_t)nn * (W + np.in_dir + np.a_dim) + k];
-      return P[24][(size_t)(nn - H) * (W + np.t_dim) + k];
-    }
-    return P[26 + 2 * (s - 10)][(size_t)nn * H + k];  // transient_encoding.{2,4,6}
+    if (lg == 8) return P[16][(size_t)nn * W + k];  // xyz_encoding_final
+    if (lg == 9) return (float)wdt(nn, k);
+    if (lg == 19) return folded_w[(size_t)nn * W + k];
+    return P[26 + 2 * (lg - 10)][(size_t)nn * H + k];  // transient_encoding.{2,4,6}
   };
-  const int n_steps = fine ? 13 : 8;
   for (int cg = 1; cg <= 2; ++cg) {
     size_t total_imgs = 0;
-    for (int s = 0; s < n_steps; ++s) {
-      int K, N, ap;
-      step_shape(s, K, N, ap);
-      total_imgs += (size_t)K * N * 2 / tc::kChunkBytes;
-    }
+    for (const LStep& st : prog) total_imgs += (size_t)st.K * st.N * 2 / tc::kChunkBytes;
     std::vector<uint16_t> img16[2];
     img16[0].assign(total_imgs * tc::kChunkBytes / 2, 0);
     img16[1].assign(total_imgs * tc::kChunkBytes / 2, 0);
     size_t img = 0;
-    for (int s = 0; s < n_steps; ++s) {
-      int K, N, ap;
-      step_shape(s, K, N, ap);
-      const int rows = N / cg;
+    for (const LStep& st : prog) {
+      const int rows = st.N / cg;
       const int kc = tc::kChunkBytes / (rows * 2);  // K columns per chunk
-      for (int k0 = 0; k0 < K; k0 += kc)
+      for (int k0 = 0; k0 < st.K; k0 += kc)
         for (int h = 0; h < cg; ++h, ++img) {
           const size_t base = img * (tc::kChunkBytes / 2);
           for (int kk = 0; kk < kc; ++kk)
             for (int r = 0; r < rows; ++r) {
-              const float v = wval(s, h * rows + r, k0 + kk);
+              const float v = wval(st.logical, h * rows + r, k0 + kk);
               const size_t idx = base + (size_t)(kk / 8) * rows * 8 + (size_t)r * 8 + kk % 8;
               img16[0][idx] = f2h(v);
               img16[1][idx] = f2b(v);
@@ -638,15 +674,21 @@ int pack_tc_weights(DfbNerf* n, int which, const std::vector<std::vector<float>>
       DFB_CHECK_CUDA(cudaMemcpy(np.blob16[k][cg - 1], img16[k].data(), np.blob16_bytes, cudaMemcpyHostToDevice));
     }
   }
-  // fp32 table read through the constant bank by the epilogue (see TcArgs::tbl)
+  // fp32 table read through the constant bank by the epilogue (see TcArgs::tbl); biases by program step
   np.tc_tbl.assign(tc::kTblFloats, 0.f);
   float* tb = np.tc_tbl.data();
-  for (int s = 0; s < 8; ++s) memcpy(tb + s * 256, P[2 * s + 1].data(), 256 * sizeof(float));
+  for (size_t s = 0; s < prog.size(); ++s) {
+    const int lg = prog[s].logical;
+    float* dst = tb + s * 256;
+    if (lg < 8) memcpy(dst, P[2 * lg + 1].data(), 256 * sizeof(float));
+    else if (lg == 8) memcpy(dst, P[17].data(), 256 * sizeof(float));
+    else if (lg == 19) memcpy(dst, folded_b.data(), 256 * sizeof(float));
+    else if (lg >= 10) memcpy(dst, P[27 + 2 * (lg - 10)].data(), H * sizeof(float));
+    // lg == 9: the bias of dir_encoding / transient_encoding.0 is part of the per-ray bias
+  }
   memcpy(tb + tc::kTblSigmaW, P[20].data(), 256 * sizeof(float));
   tb[tc::kTblScal] = P[21][0];
   if (fine) {
-    memcpy(tb + 8 * 256, P[17].data(), 256 * sizeof(float));  // xyz_encoding_final bias; step 9 uses the ray bias
-    for (int i = 0; i < 3; ++i) memcpy(tb + (10 + i) * 256, P[27 + 2 * i].data(), H * sizeof(float));
     memcpy(tb + tc::kTblRgbW, P[22].data(), 3 * H * sizeof(float));
     memcpy(tb + tc::kTblTrgbW, P[34].data(), 3 * H * sizeof(float));
     memcpy(tb + tc::kTblTsigW, P[32].data(), H * sizeof(float));
@@ -684,19 +726,20 @@ int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const
   }
   const int cg = tc_cta_group();
   tc::TcArgs a = {};
-  a.n_steps = full ? 13 : 8;
+  const std::vector<LStep> prog = build_program(full);
+  a.n_steps = (int)prog.size();
   a.last_pe_step = 4;
   int cb = 0;
   for (int s = 0; s < a.n_steps; ++s) {
-    int K, N, ap;
-    step_shape(s, K, N, ap);
-    const int kc = tc::kChunkBytes / ((N / cg) * 2);
-    a.steps[s].n_chunks = K / kc;
+    const LStep& ls = prog[s];
+    const int kc = tc::kChunkBytes / ((ls.N / cg) * 2);
+    a.steps[s].n_chunks = ls.K / kc;
     a.steps[s].ksteps = kc / 16;
-    a.steps[s].n = N;
-    a.steps[s].a_panel0 = ap;
+    a.steps[s].n = ls.N;
+    a.steps[s].a_panel0 = ls.a_panel0;
     a.steps[s].chunk_base = cb;
-    cb += K / kc;
+    a.kind[s] = ls.kind;
+    cb += ls.K / kc;
   }
   a.wimg = np.blob16[kind == DFB_MMA_F16 ? 0 : 1][cg - 1];
   memcpy(a.tbl, np.tc_tbl.data(), sizeof(a.tbl));

@@ -336,14 +336,37 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_sample_pdf(SampleArgs a
     if (lane == 0) a.z_std[ray] = sqrtf(s2 / (float)Nf);
   }
   if (modeA && a.z_vals) {  // torch.sort(torch.cat([z_vals, z_samples], -1), -1) values
-    for (int i = lane; i < S; i += 32) {
-      const float v = zall[i];
-      int rank = 0;
-      for (int j = 0; j < S; ++j) {
-        const float o = zall[j];
-        rank += (o < v) || (o == v && j < i);
+    // Both lists are normally already sorted (coarse depths always; samples when u is the
+    // deterministic grid): then the union is a merge, each element's rank is its own index plus a
+    // binary search in the other list.  Otherwise (random u) fall back to an O(S^2) rank sort.
+    const int Nc = a.Nc;
+    bool sorted = true;
+    for (int k = lane + 1; k < Nf; k += 32) sorted &= smp[k - 1] <= smp[k];
+    for (int i = lane + 1; i < Nc; i += 32) sorted &= zall[i - 1] <= zall[i];
+    sorted = __all_sync(0xffffffffu, sorted);
+    if (sorted) {
+      for (int i = lane; i < Nc; i += 32) {  // coarse element: samples strictly below it come first
+        const float v = zall[i];
+        int lo = 0, hi = Nf;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (smp[mid] < v) lo = mid + 1; else hi = mid; }
+        a.z_vals[ray * S + i + lo] = v;
       }
-      a.z_vals[ray * S + rank] = v;
+      for (int k = lane; k < Nf; k += 32) {  // sample: coarse elements <= it come first
+        const float v = smp[k];
+        int lo = 0, hi = Nc;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (zall[mid] <= v) lo = mid + 1; else hi = mid; }
+        a.z_vals[ray * S + k + lo] = v;
+      }
+    } else {
+      for (int i = lane; i < S; i += 32) {
+        const float v = zall[i];
+        int rank = 0;
+        for (int j = 0; j < S; ++j) {
+          const float o = zall[j];
+          rank += (o < v) || (o == v && j < i);
+        }
+        a.z_vals[ray * S + rank] = v;
+      }
     }
   }
 }
