@@ -3,15 +3,18 @@
 //
 //   out[b,y,x,n] = act( bias[n] + sum_{ky,kx,c} in[b, y+ky-pad, x+kx-pad, c] * w[n,c,ky,kx] )
 //
-// GEMM view: M = B*H*W pixels (tiles of 128), N = Cout (tiles of <= 256), K = KH*KW*Cin ordered
-// (ky,kx,c).  Activations are NHWC 16-bit with Cin % 8 == 0, so the 8 channels of one K panel of
-// one pixel are 16 contiguous bytes: the A operand is gathered straight into the core-matrix
-// panel layout of tc_common (no im2col buffer) with 16-byte cp.async (zero-filled at the image
-// border), weights arrive as pre-packed chunks through cp.async.bulk, tcgen05.mma accumulates in
-// TMEM (double buffered across tiles), and the epilogue applies bias / ReLU and writes NHWC 16-bit
-// (next layer), an optional pre-activation tap, or fp32 NCHW (the layout the reference returns).
+// im2col-free: an M tile is a 16 x 8 pixel patch.  For every 64-channel slice the patch PLUS ITS
+// HALO is loaded once into shared memory as [8-channel panel][patch row][patch col][16 B]
+// (16-byte cp.async from NHWC, coalesced 128 B per pixel, zero fill outside the image).  The A
+// operand of filter tap (ky,kx) is then just a shifted window of that patch: 8 consecutive pixels
+// of a row are one 8x16B core matrix, the next row is SBO = patch_width*16 B away and the next
+// 8-channel panel LBO = patch_rows*patch_width*16 B away, so tcgen05.mma reads all KH*KW taps
+// straight from the same bytes (9x / 25x fewer loads than gathering per tap).  Weights stream as
+// pre-packed 8-panel chunks (one tap of one channel slice) through cp.async.bulk; accumulators
+// are double-buffered in TMEM; the epilogue applies bias / ReLU and writes NHWC 16-bit (next
+// layer), an optional pre-activation tap, or fp32 NCHW (the layout the reference returns).
 //
-// Warps: 0-3 epilogue, 4-7 A gather (thread = pixel row), 8 weight producer, 9 MMA issuer.
+// Warps: 0-3 epilogue (thread = pixel), 4-7 patch loader, 8 weight producer, 9 MMA issuer.
 #include <stdlib.h>
 #include <string.h>
 
@@ -26,14 +29,12 @@ namespace conv {
 
 using namespace dfb::tc;
 
-constexpr int kTileM = 128;
-constexpr int kStages = 4;
-constexpr int kPanelsPerChunk = 8;               // K = 64 per stage
-constexpr int kABytes = kPanelsPerChunk * 2048;  // 16 KB
+constexpr int kTH = 16, kTW = 8;  // pixel patch of one M tile (128 pixels)
+constexpr int kBStages = 4;       // weight ring
+constexpr int kAStages = 2;       // patch ring
 constexpr int kThreads = 320;
-constexpr int kLookahead = 2;                    // cp.async groups in flight per gather thread
 
-enum Bar { A_FULL = 0, B_FULL = 4, EMPTY = 8, D_FULL = 12, D_EMPTY = 14, N_BARS = 16 };
+enum Bar { A_FULL = 0, A_EMPTY = 2, B_FULL = 4, B_EMPTY = 8, D_FULL = 12, D_EMPTY = 14, N_BARS = 16 };
 
 struct ConvArgs {
   const __half* in;   // NHWC [B,H,W,Cin]
@@ -44,11 +45,13 @@ struct ConvArgs {
   float* out_nchw;    // fp32 [B,Cout,H,W], before activation (nullable)
   int B, H, W, Cin, Cout, KH, KW, pad, relu;
   int nt;             // N tile (64, 128, 256)
-  int n_ntiles, n_mtiles;
-  int n_panels;       // K / 8 rounded up to even
-  int real_panels;    // KH*KW*Cin/8
-  int n_chunks;
-  int64_t M;
+  int n_ntiles;
+  int tiles_x, tiles_y;
+  int n_cc;           // channel slices of <= 64 channels
+  int cpp;            // Cin / 8
+  int PH, PW;         // patch rows / cols incl. halo
+  uint32_t a_bytes;   // patch buffer size (8 panels)
+  uint32_t b_bytes;   // weight stage size (8 panels x nt rows)
   int* error_flag;
 };
 
@@ -101,18 +104,16 @@ __device__ __forceinline__ void epi_store(const ConvArgs& a, const uint32_t (&v)
 __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__ ConvArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int nt = a.nt;
-  const uint32_t b_bytes = (uint32_t)nt * 16u * kPanelsPerChunk;
-  const uint32_t stage_bytes = kABytes + b_bytes;
-  const uint32_t s0 = smem_u32(smem);
-  const uint32_t sBar = s0 + kStages * stage_bytes;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kStages * stage_bytes + N_BARS * 8);
+  const uint32_t sA = smem_u32(smem);
+  const uint32_t sB = sA + kAStages * a.a_bytes;
+  const uint32_t sBar = sB + kBStages * a.b_bytes;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kAStages * a.a_bytes + kBStages * a.b_bytes + N_BARS * 8);
   const int tid = threadIdx.x, warp = tid >> 5;
   auto bar = [&](int i) { return sBar + 8u * i; };
 
   if (tid == 0) {
-    for (int i = 0; i < kStages; ++i) {
-      mbar_init(bar(A_FULL + i), 128), mbar_init(bar(B_FULL + i), 1), mbar_init(bar(EMPTY + i), 1);
-    }
+    for (int i = 0; i < kAStages; ++i) mbar_init(bar(A_FULL + i), 128), mbar_init(bar(A_EMPTY + i), 1);
+    for (int i = 0; i < kBStages; ++i) mbar_init(bar(B_FULL + i), 1), mbar_init(bar(B_EMPTY + i), 1);
     for (int i = 0; i < 2; ++i) mbar_init(bar(D_FULL + i), 1), mbar_init(bar(D_EMPTY + i), 128);
     fence_barrier_init();
   }
@@ -121,115 +122,129 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int n_tiles = a.n_mtiles * a.n_ntiles;
-  const int cpp = a.Cin >> 3;  // 8-channel panels per filter tap
+  const int tiles_img = a.tiles_x * a.tiles_y;
+  const int n_mtiles = tiles_img * a.B;
+  const int n_tiles = n_mtiles * a.n_ntiles;
+  const int n_taps = a.KH * a.KW;
+  const uint32_t panel_stride = (uint32_t)a.PH * a.PW * 16u;
 
   if (warp >= 4 && warp < 8) {
-    // ===== A gather: thread = pixel row, 16-byte cp.async per (row, K panel) ==================
-    const int r = tid - 128;
-    uint32_t it = 0;  // global chunk counter -> stage / phase
+    // ===== patch loader: [panel][patch row][patch col][16 B] for every 64-channel slice =========
+    const int lt = tid - 128;
+    const int c8l = lt & 7;          // panel within the slice: 8 consecutive threads = 128 contiguous bytes
+    const int e0 = lt >> 3;          // first patch entry of this thread (16 entries per pass)
+    const int n_ent = a.PH * a.PW;
+    // flat sequence over (tile, channel slice) so that the next patch (also the next tile's) loads
+    // while the tensor pipe works on the current one
+    uint32_t seq = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       const int mt = t / a.n_ntiles;
-      const int64_t m = (int64_t)mt * kTileM + r;
-      const bool mvalid = m < a.M;
-      const int64_t mm = mvalid ? m : 0;
-      const int x = (int)(mm % a.W);
-      const int y = (int)((mm / a.W) % a.H);
-      const int b = (int)(mm / ((int64_t)a.W * a.H));
+      const int b = mt / tiles_img, ti = mt % tiles_img;
+      const int y0 = (ti / a.tiles_x) * kTH - a.pad, x0 = (ti % a.tiles_x) * kTW - a.pad;
       const __half* base = a.in + ((int64_t)b * a.H * a.W) * a.Cin;
-      int tap = 0, c8 = 0;  // decomposition of the running panel index
-      for (int c = 0; c < a.n_chunks + kLookahead; ++c) {
-        if (c < a.n_chunks) {
-          const uint32_t stage = (it + c) % kStages, ph = ((it + c) / kStages) & 1;
-          mbar_wait(bar(EMPTY + stage), ph ^ 1, a.error_flag);
-          const uint32_t dst = s0 + stage * stage_bytes + r * 16;
-          const int np = min(kPanelsPerChunk, a.n_panels - c * kPanelsPerChunk);
-          for (int p = 0; p < np; ++p) {
-            const int ky = tap / a.KW, kx = tap - ky * a.KW;
-            const int yy = y + ky - a.pad, xx = x + kx - a.pad;
-            const bool ok = mvalid && tap < a.KH * a.KW && yy >= 0 && yy < a.H && xx >= 0 && xx < a.W;
-            const __half* src = ok ? base + ((int64_t)yy * a.W + xx) * a.Cin + c8 * 8 : a.in;
-            cp_async16(dst + p * 2048, src, ok ? 16u : 0u);
-            if (++c8 == cpp) c8 = 0, ++tap;
-          }
-          cp_async_commit();
-        } else {
-          cp_async_commit();  // empty group keeps the wait_group arithmetic uniform
+      for (int cc = 0; cc < a.n_cc; ++cc, ++seq) {
+        const uint32_t st = seq % kAStages, ph = (seq / kAStages) & 1;
+        mbar_wait(bar(A_EMPTY + st), ph ^ 1, a.error_flag);
+        const int c8 = cc * 8 + c8l;
+        const bool cok = c8 < a.cpp;
+        const uint32_t dst0 = sA + st * a.a_bytes + c8l * panel_stride;
+        for (int e = e0; e < n_ent; e += 16) {
+          const int pr = e / a.PW, pc = e - pr * a.PW;
+          const int yy = y0 + pr, xx = x0 + pc;
+          const bool ok = cok && yy >= 0 && yy < a.H && xx >= 0 && xx < a.W;
+          const __half* src = ok ? base + ((int64_t)yy * a.W + xx) * a.Cin + c8 * 8 : a.in;
+          cp_async16(dst0 + e * 16, src, ok ? 16u : 0u);
         }
-        if (c >= kLookahead) {
-          cp_async_wait<kLookahead>();
+        cp_async_commit();
+        if (seq >= 1) {
+          cp_async_wait<1>();
           fence_proxy_async();
-          mbar_arrive(bar(A_FULL + (it + c - kLookahead) % kStages));
+          mbar_arrive(bar(A_FULL + (seq - 1) % kAStages));
         }
       }
-      it += a.n_chunks;
+    }
+    if (seq >= 1) {
+      cp_async_wait<0>();
+      fence_proxy_async();
+      mbar_arrive(bar(A_FULL + (seq - 1) % kAStages));
     }
   } else if (warp == 8) {
-    // ===== weight producer ======================================================================
+    // ===== weight producer: one stage = one tap of one channel slice ============================
     uint32_t it = 0;
+    const int per_tile = a.n_cc * n_taps;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       const int ntile = t % a.n_ntiles;
-      const uint8_t* src = a.wimg + (size_t)ntile * a.n_chunks * b_bytes;
-      for (int c = 0; c < a.n_chunks; ++c, ++it) {
-        const uint32_t stage = it % kStages, ph = (it / kStages) & 1;
-        mbar_wait(bar(EMPTY + stage), ph ^ 1, a.error_flag);
+      const uint8_t* src = a.wimg + (size_t)ntile * per_tile * a.b_bytes;
+      for (int c = 0; c < per_tile; ++c, ++it) {
+        const uint32_t stage = it % kBStages, ph = (it / kBStages) & 1;
+        mbar_wait(bar(B_EMPTY + stage), ph ^ 1, a.error_flag);
         if (elect_one()) {
-          mbar_expect_tx(bar(B_FULL + stage), b_bytes);
-          bulk_g2s(s0 + stage * stage_bytes + kABytes, src + (size_t)c * b_bytes, b_bytes, bar(B_FULL + stage));
+          mbar_expect_tx(bar(B_FULL + stage), a.b_bytes);
+          bulk_g2s(sB + stage * a.b_bytes, src + (size_t)c * a.b_bytes, a.b_bytes, bar(B_FULL + stage));
         }
         __syncwarp();
       }
     }
   } else if (warp == 9) {
     // ===== MMA issuer =============================================================================
-    const uint32_t idesc = make_idesc(0, nt, kTileM);
-    const uint32_t desc_hi = (128u >> 4) | (1u << 14);
-    const uint32_t b_step = 2u * nt;
-    uint32_t it = 0, tl = 0;
+    const uint32_t idesc = make_idesc(0, nt, 128);
+    // A: SBO = patch row pitch, LBO = panel stride.  B: SBO = 128 B, LBO = nt*16 B.
+    const uint32_t a_hi = ((uint32_t)(a.PW * 16) >> 4) | (1u << 14);
+    const uint32_t b_hi = (128u >> 4) | (1u << 14);
+    const uint32_t a_lbo = (panel_stride >> 4) << 16, b_lbo = (uint32_t)nt << 16;
+    const uint32_t b_step = 2u * nt;                  // two weight panels per K=16 step
+    const uint32_t a_step = 2u * (panel_stride >> 4);  // two patch panels per K=16 step
+    uint32_t ita = 0, itb = 0, tl = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tl) {
       const uint32_t buf = tl & 1;
       mbar_wait(bar(D_EMPTY + buf), ((tl >> 1) & 1) ^ 1, a.error_flag);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + buf * 256;
       uint32_t acc = 0;
-      for (int c = 0; c < a.n_chunks; ++c, ++it) {
-        const uint32_t stage = it % kStages, ph = (it / kStages) & 1;
-        mbar_wait(bar(A_FULL + stage), ph, a.error_flag);
-        mbar_wait(bar(B_FULL + stage), ph, a.error_flag);
-        tc_fence_after();
-        const uint32_t a_lo = ((s0 + stage * stage_bytes) >> 4) | ((2048u >> 4) << 16);
-        const uint32_t b_lo = ((s0 + stage * stage_bytes + kABytes) >> 4) | ((uint32_t)nt << 16);
-        const int ks_n = min(kPanelsPerChunk, a.n_panels - c * kPanelsPerChunk) >> 1;
-        if (elect_one()) {
+      for (int cc = 0; cc < a.n_cc; ++cc, ++ita) {
+        const uint32_t ast = ita % kAStages, aph = (ita / kAStages) & 1;
+        mbar_wait(bar(A_FULL + ast), aph, a.error_flag);
+        const int np = min(8, a.cpp - cc * 8);
+        const int ks_n = (np + 1) >> 1;
+        const uint32_t patch = (sA + ast * a.a_bytes) >> 4;
+        for (int tp = 0; tp < n_taps; ++tp, ++itb) {
+          const uint32_t stage = itb % kBStages, ph = (itb / kBStages) & 1;
+          mbar_wait(bar(B_FULL + stage), ph, a.error_flag);
+          tc_fence_after();
+          const int ky = tp / a.KW, kx = tp - ky * a.KW;
+          const uint32_t a_lo = (patch + (uint32_t)(ky * a.PW + kx)) | a_lbo;
+          const uint32_t b_lo = ((sB + stage * a.b_bytes) >> 4) | b_lbo;
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            if (ks < ks_n) umma_f16<1>(d_tmem, mk64(a_lo + ks * 256, desc_hi), mk64(b_lo + ks * b_step, desc_hi), idesc, acc | ks);
-          umma_commit<1>(bar(EMPTY + stage));
-          if (c == a.n_chunks - 1) umma_commit<1>(bar(D_FULL + buf));
+            for (int ks = 0; ks < 4; ++ks)
+              if (ks < ks_n) umma_f16<1>(d_tmem, mk64(a_lo + ks * a_step, a_hi), mk64(b_lo + ks * b_step, b_hi), idesc, acc | ks);
+            umma_commit<1>(bar(B_EMPTY + stage));
+            if (tp == n_taps - 1) {
+              umma_commit<1>(bar(A_EMPTY + ast));
+              if (cc == a.n_cc - 1) umma_commit<1>(bar(D_FULL + buf));
+            }
+          }
+          __syncwarp();
+          acc = 1;
         }
-        __syncwarp();
-        acc = 1;
       }
     }
   } else if (warp < 4) {
-    // ===== epilogue (thread = pixel) ===============================================================
+    // ===== epilogue (thread = pixel of the 16x8 patch) ===============================================
     const int r = tid;
     uint32_t tl = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tl) {
       const uint32_t buf = tl & 1;
       const int mt = t / a.n_ntiles, n0 = (t % a.n_ntiles) * nt;
-      const int64_t m = (int64_t)mt * kTileM + r;
-      const bool valid = m < a.M;
+      const int b = mt / tiles_img, ti = mt % tiles_img;
+      const int y = (ti / a.tiles_x) * kTH + (r >> 3), x = (ti % a.tiles_x) * kTW + (r & 7);
+      const bool valid = y < a.H && x < a.W;
+      const int64_t m = ((int64_t)b * a.H + y) * a.W + x;
       mbar_wait(bar(D_FULL + buf), (tl >> 1) & 1, a.error_flag);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 256;
-      int64_t nchw_base = 0;
-      if (a.out_nchw && valid) {
-        const int x = (int)(m % a.W), y = (int)((m / a.W) % a.H);
-        const int b = (int)(m / ((int64_t)a.W * a.H));
-        nchw_base = ((int64_t)b * a.Cout * a.H + y) * a.W + x;
-      }
       const int64_t plane = (int64_t)a.H * a.W;
+      const int64_t nchw_base = ((int64_t)b * a.Cout * a.H + y) * a.W + x;
       uint32_t v0[32], v1[32];
       tmem_ld32(t_row, v0);
 #pragma unroll 1
@@ -260,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
 // host: handle, weight packing, launch
 // ------------------------------------------------------------------------------------------
 struct DfbConv {
-  int Cin, Cin_pad, Cout, KH, KW, pad, nt, n_ntiles, n_panels, real_panels, n_chunks;
+  int Cin, Cin_pad, Cout, KH, KW, pad, nt, n_ntiles, n_cc, cpp;
   uint8_t* wimg = nullptr;
   float* bias = nullptr;
   int num_sms = 0;
@@ -279,9 +294,8 @@ extern "C" int dfb_conv_create(int Cin, int Cout, int KH, int KW, const float* w
   c->Cin = Cin, c->Cin_pad = round_up(Cin, 8), c->Cout = Cout, c->KH = KH, c->KW = KW, c->pad = KH / 2;
   c->nt = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
   c->n_ntiles = Cout / c->nt;
-  c->real_panels = KH * KW * c->Cin_pad / 8;
-  c->n_panels = round_up(c->real_panels, 2);
-  c->n_chunks = (c->n_panels + conv::kPanelsPerChunk - 1) / conv::kPanelsPerChunk;
+  c->cpp = c->Cin_pad / 8;
+  c->n_cc = (c->cpp + 7) / 8;
   int dev = 0;
   DFB_CHECK_CUDA(cudaGetDevice(&dev));
   cudaDeviceProp p;
@@ -297,20 +311,22 @@ extern "C" int dfb_conv_create(int Cin, int Cout, int KH, int KW, const float* w
   // eval-mode BatchNorm folded into the conv: y = scale * (conv + bias) + shift
   std::vector<float> bf(Cout);
   for (int n = 0; n < Cout; ++n) bf[n] = sc[n] * b[n] + sh[n];
-  const size_t b_bytes = (size_t)c->nt * 16 * conv::kPanelsPerChunk;
-  std::vector<uint16_t> img((size_t)c->n_ntiles * c->n_chunks * b_bytes / 2, 0);
+  // weight image: [n tile][channel slice][tap][8 panels][nt rows][8 halfs]
+  const size_t b_bytes = (size_t)c->nt * 16 * 8;
+  const int n_taps = KH * KW;
+  std::vector<uint16_t> img((size_t)c->n_ntiles * c->n_cc * n_taps * b_bytes / 2, 0);
   for (int t = 0; t < c->n_ntiles; ++t)
-    for (int ch = 0; ch < c->n_chunks; ++ch)
-      for (int pp = 0; pp < conv::kPanelsPerChunk; ++pp) {
-        const int P = ch * conv::kPanelsPerChunk + pp;
-        if (P >= c->real_panels) continue;
-        const int cpp = c->Cin_pad / 8, tap = P / cpp, c8 = P % cpp, ky = tap / KW, kx = tap % KW;
-        for (int rr = 0; rr < c->nt; ++rr)
-          for (int e = 0; e < 8; ++e) {
-            const int ci = c8 * 8 + e, n = t * c->nt + rr;
-            const float v = ci < Cin ? sc[n] * w[(((size_t)n * Cin + ci) * KH + ky) * KW + kx] : 0.f;
-            img[((size_t)(t * c->n_chunks + ch) * b_bytes) / 2 + (size_t)pp * c->nt * 8 + (size_t)rr * 8 + e] = f2h16(v);
-          }
+    for (int cc = 0; cc < c->n_cc; ++cc)
+      for (int tp = 0; tp < n_taps; ++tp) {
+        const size_t base = ((size_t)(t * c->n_cc + cc) * n_taps + tp) * b_bytes / 2;
+        const int ky = tp / KW, kx = tp % KW;
+        for (int pp = 0; pp < 8; ++pp)
+          for (int rr = 0; rr < c->nt; ++rr)
+            for (int e = 0; e < 8; ++e) {
+              const int ci = (cc * 8 + pp) * 8 + e, n = t * c->nt + rr;
+              const float v = ci < Cin ? sc[n] * w[(((size_t)n * Cin + ci) * KH + ky) * KW + kx] : 0.f;
+              img[base + (size_t)pp * c->nt * 8 + (size_t)rr * 8 + e] = f2h16(v);
+            }
       }
   DFB_CHECK_CUDA(cudaMalloc(&c->wimg, img.size() * 2));
   DFB_CHECK_CUDA(cudaMemcpy(c->wimg, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
@@ -341,13 +357,17 @@ extern "C" int dfb_conv_fwd(DfbConv* c, const void* in_nhwc16, int B, int H, int
   a.in = (const __half*)in_nhwc16, a.wimg = c->wimg, a.bias = c->bias;
   a.out = (__half*)out_nhwc16, a.tap = (__half*)tap_nhwc16, a.out_nchw = out_nchw32;
   a.B = B, a.H = H, a.W = W, a.Cin = c->Cin_pad, a.Cout = c->Cout, a.KH = c->KH, a.KW = c->KW, a.pad = c->pad, a.relu = relu;
-  a.nt = c->nt, a.n_ntiles = c->n_ntiles, a.n_panels = c->n_panels, a.real_panels = c->real_panels, a.n_chunks = c->n_chunks;
-  a.M = (int64_t)B * H * W;
-  a.n_mtiles = (int)((a.M + conv::kTileM - 1) / conv::kTileM);
+  a.nt = c->nt, a.n_ntiles = c->n_ntiles, a.n_cc = c->n_cc, a.cpp = c->cpp;
+  a.tiles_x = (W + conv::kTW - 1) / conv::kTW, a.tiles_y = (H + conv::kTH - 1) / conv::kTH;
+  a.PH = conv::kTH + 2 * c->pad, a.PW = conv::kTW + 2 * c->pad;
+  a.a_bytes = (uint32_t)a.PH * a.PW * 16u * 8u;
+  a.b_bytes = (uint32_t)c->nt * 16u * 8u;
   a.error_flag = g_conv_error_flag;
-  const int n_tiles = a.n_mtiles * a.n_ntiles;
-  const int grid = std::min(n_tiles, c->num_sms);
-  const size_t smem = (size_t)conv::kStages * (conv::kABytes + (size_t)c->nt * 16 * conv::kPanelsPerChunk) + 256;
+  const int64_t n_tiles = (int64_t)a.tiles_x * a.tiles_y * B * a.n_ntiles;
+  DFB_REQUIRE(n_tiles < (1ll << 30), DFB_ERR_INVALID, "image too large");
+  const int grid = (int)std::min<int64_t>(n_tiles, c->num_sms);
+  const size_t smem = (size_t)conv::kAStages * a.a_bytes + (size_t)conv::kBStages * a.b_bytes + 256;
+  DFB_REQUIRE(smem <= 232448, DFB_ERR_UNSUPPORTED, "shared memory budget exceeded");
   DFB_CHECK_CUDA(cudaFuncSetAttribute(conv::k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   conv::k_conv_tc<<<grid, conv::kThreads, smem, (cudaStream_t)stream>>>(a);
   DFB_LAUNCH_CHECK();
