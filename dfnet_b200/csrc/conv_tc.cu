@@ -51,7 +51,9 @@ struct ConvArgs {
   int cpp;            // Cin / 8
   int PH, PW;         // patch rows / cols incl. halo
   uint32_t a_bytes;   // patch buffer size (8 panels)
-  uint32_t b_bytes;   // weight stage size (8 panels x nt rows)
+  uint32_t b_bytes;   // weight stage size (tps taps x 8 panels x nt rows)
+  int tps;            // filter taps per weight stage (256 / nt): narrow layers get more MMA work per stage
+  int n_wst;          // weight stages per channel slice = ceil(KH*KW / tps)
   int* error_flag;
 };
 
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
   } else if (warp == 8) {
     // ===== weight producer: one stage = one tap of one channel slice ============================
     uint32_t it = 0;
-    const int per_tile = a.n_cc * n_taps;
+    const int per_tile = a.n_cc * a.n_wst;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       const int ntile = t % a.n_ntiles;
       const uint8_t* src = a.wimg + (size_t)ntile * per_tile * a.b_bytes;
@@ -207,19 +209,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
         const int np = min(8, a.cpp - cc * 8);
         const int ks_n = (np + 1) >> 1;
         const uint32_t patch = (sA + ast * a.a_bytes) >> 4;
-        for (int tp = 0; tp < n_taps; ++tp, ++itb) {
+        for (int ws = 0; ws < a.n_wst; ++ws, ++itb) {
           const uint32_t stage = itb % kBStages, ph = (itb / kBStages) & 1;
           mbar_wait(bar(B_FULL + stage), ph, a.error_flag);
           tc_fence_after();
-          const int ky = tp / a.KW, kx = tp - ky * a.KW;
-          const uint32_t a_lo = (patch + (uint32_t)(ky * a.PW + kx)) | a_lbo;
-          const uint32_t b_lo = ((sB + stage * a.b_bytes) >> 4) | b_lbo;
+          const int tp0 = ws * a.tps, tpn = min(a.tps, n_taps - tp0);
+          const uint32_t b_lo0 = ((sB + stage * a.b_bytes) >> 4) | b_lbo;
           if (elect_one()) {
+            for (int tt = 0; tt < tpn; ++tt) {
+              const int tp = tp0 + tt, ky = tp / a.KW, kx = tp - ky * a.KW;
+              const uint32_t a_lo = (patch + (uint32_t)(ky * a.PW + kx)) | a_lbo;
+              const uint32_t b_lo = b_lo0 + (uint32_t)tt * 8u * nt;  // 8 panels * nt*16 B per tap, in 16 B units
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              if (ks < ks_n) umma_f16<1>(d_tmem, mk64(a_lo + ks * a_step, a_hi), mk64(b_lo + ks * b_step, b_hi), idesc, acc | ks);
+              for (int ks = 0; ks < 4; ++ks)
+                if (ks < ks_n)
+                  umma_f16<1>(d_tmem, mk64(a_lo + ks * a_step, a_hi), mk64(b_lo + ks * b_step, b_hi), idesc, acc | (uint32_t)(tt | ks));
+              acc = 1;
+            }
             umma_commit<1>(bar(B_EMPTY + stage));
-            if (tp == n_taps - 1) {
+            if (ws == a.n_wst - 1) {
               umma_commit<1>(bar(A_EMPTY + ast));
               if (cc == a.n_cc - 1) umma_commit<1>(bar(D_FULL + buf));
             }
@@ -275,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
 // host: handle, weight packing, launch
 // ------------------------------------------------------------------------------------------
 struct DfbConv {
-  int Cin, Cin_pad, Cout, KH, KW, pad, nt, n_ntiles, n_cc, cpp;
+  int Cin, Cin_pad, Cout, KH, KW, pad, nt, n_ntiles, n_cc, cpp, tps, n_wst;
   uint8_t* wimg = nullptr;
   float* bias = nullptr;
   int num_sms = 0;
@@ -296,6 +304,8 @@ extern "C" int dfb_conv_create(int Cin, int Cout, int KH, int KW, const float* w
   c->n_ntiles = Cout / c->nt;
   c->cpp = c->Cin_pad / 8;
   c->n_cc = (c->cpp + 7) / 8;
+  c->tps = 256 / c->nt;
+  c->n_wst = (KH * KW + c->tps - 1) / c->tps;
   int dev = 0;
   DFB_CHECK_CUDA(cudaGetDevice(&dev));
   cudaDeviceProp p;
@@ -311,14 +321,15 @@ extern "C" int dfb_conv_create(int Cin, int Cout, int KH, int KW, const float* w
   // eval-mode BatchNorm folded into the conv: y = scale * (conv + bias) + shift
   std::vector<float> bf(Cout);
   for (int n = 0; n < Cout; ++n) bf[n] = sc[n] * b[n] + sh[n];
-  // weight image: [n tile][channel slice][tap][8 panels][nt rows][8 halfs]
-  const size_t b_bytes = (size_t)c->nt * 16 * 8;
+  // weight image: [n tile][channel slice][weight stage][tap in stage][8 panels][nt rows][8 halfs]
+  const size_t tap_bytes = (size_t)c->nt * 16 * 8;
+  const size_t b_bytes = tap_bytes * c->tps;
   const int n_taps = KH * KW;
-  std::vector<uint16_t> img((size_t)c->n_ntiles * c->n_cc * n_taps * b_bytes / 2, 0);
+  std::vector<uint16_t> img((size_t)c->n_ntiles * c->n_cc * c->n_wst * b_bytes / 2, 0);
   for (int t = 0; t < c->n_ntiles; ++t)
     for (int cc = 0; cc < c->n_cc; ++cc)
       for (int tp = 0; tp < n_taps; ++tp) {
-        const size_t base = ((size_t)(t * c->n_cc + cc) * n_taps + tp) * b_bytes / 2;
+        const size_t base = (((size_t)(t * c->n_cc + cc) * c->n_wst + tp / c->tps) * b_bytes + (tp % c->tps) * tap_bytes) / 2;
         const int ky = tp / KW, kx = tp % KW;
         for (int pp = 0; pp < 8; ++pp)
           for (int rr = 0; rr < c->nt; ++rr)
@@ -361,7 +372,8 @@ extern "C" int dfb_conv_fwd(DfbConv* c, const void* in_nhwc16, int B, int H, int
   a.tiles_x = (W + conv::kTW - 1) / conv::kTW, a.tiles_y = (H + conv::kTH - 1) / conv::kTH;
   a.PH = conv::kTH + 2 * c->pad, a.PW = conv::kTW + 2 * c->pad;
   a.a_bytes = (uint32_t)a.PH * a.PW * 16u * 8u;
-  a.b_bytes = (uint32_t)c->nt * 16u * 8u;
+  a.b_bytes = (uint32_t)c->nt * 16u * 8u * (uint32_t)c->tps;
+  a.tps = c->tps, a.n_wst = c->n_wst;
   a.error_flag = g_conv_error_flag;
   const int64_t n_tiles = (int64_t)a.tiles_x * a.tiles_y * B * a.n_ntiles;
   DFB_REQUIRE(n_tiles < (1ll << 30), DFB_ERR_INVALID, "image too large");

@@ -58,32 +58,42 @@ __global__ void k_maxpool2x2_nhwc(const __half* __restrict__ in, __half* __restr
 }
 
 // bilinear resize, align_corners=True, fp32 NCHW planes: src [P,h,w] -> dst [P,Ho,Wo].
-// grid (ceil(Wo/4/64), Ho, P): 4 outputs along x per thread, one 16-byte store (HBM-write bound:
-// the sources are L2-resident).  Interpolation weights follow ATen: src = scale * dst_index,
-// scale = (in-1)/(out-1) in float, lambda from the fractional part.
-__global__ void k_resize_bilinear_ac(const float* __restrict__ src, float* __restrict__ dst, int h, int w, int Ho, int Wo) {
+// grid (ceil(Wo/4/128), Ho, P/8): every thread owns 4 outputs along x and loops over 8 planes, so
+// the interpolation coordinates are computed once per 32 outputs and every store is 16 bytes
+// (HBM-write bound; the sources are L2-resident).  Weights follow ATen: src = scale * dst_index,
+// scale = (in-1)/(out-1) in float, lambda = fractional part.
+constexpr int kResizePlanes = 8;
+__global__ void __launch_bounds__(128) k_resize_bilinear_ac(const float* __restrict__ src, float* __restrict__ dst, int planes,
+                                                            int h, int w, int Ho, int Wo) {
   const int xq = (blockIdx.x * blockDim.x + threadIdx.x) * 4, yo = blockIdx.y;
   if (xq >= Wo) return;
-  const int64_t pl = blockIdx.z;
   const float sy = Ho > 1 ? (float)(h - 1) / (float)(Ho - 1) : 0.f, sx = Wo > 1 ? (float)(w - 1) / (float)(Wo - 1) : 0.f;
   const float fy = sy * yo;
   const int y0 = (int)fy, y1 = y0 + (y0 < h - 1);
   const float ly = fy - y0;
-  const float* r0 = src + (pl * h + y0) * w;
-  const float* r1 = src + (pl * h + y1) * w;
-  float o[4];
+  int x0[4], x1[4];
+  float lx[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int xo = min(xq + k, Wo - 1);
     const float fx = sx * xo;
-    const int x0 = (int)fx, x1 = x0 + (x0 < w - 1);
-    const float lx = fx - x0;
-    o[k] = (1.f - ly) * ((1.f - lx) * __ldg(r0 + x0) + lx * __ldg(r0 + x1)) + ly * ((1.f - lx) * __ldg(r1 + x0) + lx * __ldg(r1 + x1));
+    x0[k] = (int)fx, x1[k] = x0[k] + (x0[k] < w - 1), lx[k] = fx - x0[k];
   }
-  float* d = dst + (pl * Ho + yo) * Wo + xq;
-  if (xq + 3 < Wo && (Wo & 3) == 0) *reinterpret_cast<float4*>(d) = make_float4(o[0], o[1], o[2], o[3]);
-  else
-    for (int k = 0; k < 4 && xq + k < Wo; ++k) d[k] = o[k];
+  const bool vec = xq + 3 < Wo && (Wo & 3) == 0;
+  const int p0 = blockIdx.z * kResizePlanes, p1 = min(planes, p0 + kResizePlanes);
+  for (int pl = p0; pl < p1; ++pl) {
+    const float* r0 = src + ((int64_t)pl * h + y0) * w;
+    const float* r1 = src + ((int64_t)pl * h + y1) * w;
+    float o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      o[k] = (1.f - ly) * ((1.f - lx[k]) * __ldg(r0 + x0[k]) + lx[k] * __ldg(r0 + x1[k])) +
+             ly * ((1.f - lx[k]) * __ldg(r1 + x0[k]) + lx[k] * __ldg(r1 + x1[k]));
+    float* d = dst + ((int64_t)pl * Ho + yo) * Wo + xq;
+    if (vec) __stcs(reinterpret_cast<float4*>(d), make_float4(o[0], o[1], o[2], o[3]));
+    else
+      for (int k = 0; k < 4 && xq + k < Wo; ++k) d[k] = o[k];
+  }
 }
 
 // adaptive average pool to 1x1 over NHWC fp16 -> fp32 [B,C]; one block per (b, 64 channels)
@@ -394,11 +404,12 @@ extern "C" int dfb_dfnet_fwd(DfbDfnet* d, const float* x, int B, int H, int W, u
       rc = dfb_conv_fwd(d->head5[l], mid, B, fh, fw, 0, nullptr, nullptr, featbuf, stream);
       if (rc) return rc;
       const int planes_s = Bs * 128;
-      const dim3 rg((upW + 255) / 256, upH, planes_s);
-      k_resize_bilinear_ac<<<rg, 64, 0, st>>>(featbuf, feats_t + l * lvl_stride, fh, fw, upH, upW);
+      const dim3 rg((upW + 511) / 512, upH, (planes_s + kResizePlanes - 1) / kResizePlanes);
+      k_resize_bilinear_ac<<<rg, 128, 0, st>>>(featbuf, feats_t + l * lvl_stride, planes_s, fh, fw, upH, upW);
       DFB_LAUNCH_CHECK();
       if (!single) {
-        k_resize_bilinear_ac<<<rg, 64, 0, st>>>(featbuf + (size_t)planes_s * fh * fw, feats_r + l * lvl_stride, fh, fw, upH, upW);
+        k_resize_bilinear_ac<<<rg, 128, 0, st>>>(featbuf + (size_t)planes_s * fh * fw, feats_r + l * lvl_stride, planes_s, fh, fw,
+                                                 upH, upW);
         DFB_LAUNCH_CHECK();
       }
     }
