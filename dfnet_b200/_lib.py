@@ -16,7 +16,7 @@ SYMBOLS = [
     "dfb_render_fwd", "dfb_render_image_host", "dfb_sample_pdf", "dfb_raw2outputs", "dfb_get_rays",
     "dfb_launch_count", "dfb_profile_enable", "dfb_profile_read", "dfb_debug_umma_gemm", "dfb_debug_tc_prof", "dfb_conv_create", "dfb_conv_destroy", "dfb_conv_fwd",
     "dfb_dfnet_create", "dfb_dfnet_destroy", "dfb_dfnet_load", "dfb_dfnet_workspace_bytes", "dfb_dfnet_fwd",
-    "dfb_cosine_loss", "dfb_triplet_loss", "dfb_mse",
+    "dfb_cosine_loss", "dfb_triplet_loss", "dfb_mse", "dfb_resize_bicubic", "dfb_resize_bilinear_ac",
 ]
 
 MMA_FP32_SIMT, MMA_F16, MMA_BF16 = 0, 1, 2
@@ -88,6 +88,8 @@ def _load():
     lib.dfb_cosine_loss.argtypes = [vp, vp, i32, i64, i32, f32, vp, vp, C.c_size_t, vp]
     lib.dfb_triplet_loss.argtypes = [vp, vp, i32, i32, i32, i32, i32, f32, vp, vp, vp, C.c_size_t, vp]
     lib.dfb_mse.argtypes = [vp, vp, i64, vp, vp, C.c_size_t, vp]
+    lib.dfb_resize_bicubic.argtypes = [vp, i64, i32, i32, i32, i32, vp, vp]
+    lib.dfb_resize_bilinear_ac.argtypes = [vp, i64, i32, i32, i32, i32, vp, vp]
     lib.dfb_profile_enable.argtypes = [i32]
     lib.dfb_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(i64)]
     return lib

@@ -62,11 +62,10 @@ std::vector<ProfRec> g_prof;
 
 int run_mlp_inner(const DfbNerf* n, const DfbRenderCfg* c, int which, int mode, const float* rayrec, const float* z,
                   const float* rb, int64_t rays, int S, float* raw, cudaStream_t st) {
-  if (c->mma_kind != DFB_MMA_FP32_SIMT) {
-    DFB_REQUIRE(tc_supported(n, which, mode), DFB_ERR_UNSUPPORTED,
-                "tcgen05 path supports netwidth 256 / netdepth 8 test-time networks; use DFB_MMA_FP32_SIMT");
+  // The tcgen05 kernel covers the 8x256 networks (sigma-only coarse pass and full fine pass); every
+  // other shape or mode (other widths, the train-mode coarse pass) runs on the fp32 CUDA kernel.
+  if (c->mma_kind != DFB_MMA_FP32_SIMT && tc_supported(n, which, mode))
     return launch_mlp_tc_rays(n, which, mode, c->mma_kind, rayrec, z, rb, rays, S, raw, st);
-  }
   return launch_mlp_simt_rays(n, which, mode, rayrec, z, rb, rays, S, raw, st);
 }
 

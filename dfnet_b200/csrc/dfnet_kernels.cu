@@ -586,3 +586,65 @@ extern "C" int dfb_mse(const float* a, const float* b, int64_t n, float* out, vo
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// bicubic resize (torch.nn.Upsample(size, mode='bicubic'), align_corners=False, A = -0.75,
+// border-clamped taps, no output clamp) — feature/direct_feature_matching.py:346, feature/misc.py:233
+// ------------------------------------------------------------------------------------------
+namespace dfb {
+
+__device__ __forceinline__ void cubic_coeffs(float t, float (&c)[4]) {
+  const float A = -0.75f;
+  auto c1 = [&](float x) { return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; };           // |x| <= 1
+  auto c2 = [&](float x) { return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; };    // 1 < |x| < 2
+  c[0] = c2(t + 1.f), c[1] = c1(t), c[2] = c1(1.f - t), c[3] = c2(2.f - t);
+}
+
+// src [P,h,w] fp32 -> dst [P,Ho,Wo] fp32; one thread per output pixel, grid.z = plane
+__global__ void k_resize_bicubic(const float* __restrict__ src, float* __restrict__ dst, int h, int w, int Ho, int Wo) {
+  const int xo = blockIdx.x * blockDim.x + threadIdx.x, yo = blockIdx.y;
+  if (xo >= Wo) return;
+  const int64_t pl = blockIdx.z;
+  // area_pixel_compute_source_index(scale, dst, align_corners=False, cubic=True): scale*(dst+0.5)-0.5, not clamped
+  const float sy = (float)h / (float)Ho, sx = (float)w / (float)Wo;
+  const float fy = sy * (yo + 0.5f) - 0.5f, fx = sx * (xo + 0.5f) - 0.5f;
+  const int iy = (int)floorf(fy), ix = (int)floorf(fx);
+  float cy[4], cx[4];
+  cubic_coeffs(fy - iy, cy);
+  cubic_coeffs(fx - ix, cx);
+  const float* s = src + pl * h * w;
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int yy = min(max(iy - 1 + i, 0), h - 1);
+    float row = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int xx = min(max(ix - 1 + j, 0), w - 1);
+      row = fmaf(cx[j], __ldg(s + yy * w + xx), row);
+    }
+    acc = fmaf(cy[i], row, acc);
+  }
+  dst[(pl * Ho + yo) * Wo + xo] = acc;
+}
+
+}  // namespace dfb
+
+// torch.nn.Upsample(size=(Ho,Wo), mode='bicubic') on fp32 [P,h,w] planes (P = B*C).
+extern "C" int dfb_resize_bicubic(const float* src, int64_t planes, int h, int w, int Ho, int Wo, float* dst, void* stream) {
+  DFB_REQUIRE(src && dst && planes >= 1 && h >= 1 && w >= 1 && Ho >= 1 && Wo >= 1, DFB_ERR_INVALID, "bad arguments");
+  DFB_REQUIRE(planes <= 65535, DFB_ERR_INVALID, "too many planes");
+  k_resize_bicubic<<<dim3((Wo + 127) / 128, Ho, (unsigned)planes), 128, 0, (cudaStream_t)stream>>>(src, dst, h, w, Ho, Wo);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+// torch.nn.UpsamplingBilinear2d(size=(Ho,Wo)) (align_corners=True) on fp32 [P,h,w] planes.
+extern "C" int dfb_resize_bilinear_ac(const float* src, int64_t planes, int h, int w, int Ho, int Wo, float* dst, void* stream) {
+  DFB_REQUIRE(src && dst && planes >= 1 && h >= 1 && w >= 1 && Ho >= 1 && Wo >= 1, DFB_ERR_INVALID, "bad arguments");
+  const dim3 rg((Wo + 511) / 512, Ho, (unsigned)((planes + kResizePlanes - 1) / kResizePlanes));
+  DFB_REQUIRE(rg.z <= 65535, DFB_ERR_INVALID, "too many planes");
+  k_resize_bilinear_ac<<<rg, 128, 0, (cudaStream_t)stream>>>(src, dst, (int)planes, h, w, Ho, Wo);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}

@@ -54,3 +54,26 @@ def mse2psnr(x):
 def PoseLoss(args, pose_, pose, device=None):
     """Reference feature/direct_feature_matching.py:138-142."""
     return mse(pose_.reshape(args.batch_size, 12), pose)
+
+
+def upsample_bicubic(x, size):
+    """torch.nn.Upsample(size=size, mode='bicubic')(x) for x [B,C,h,w] (reference
+    feature/direct_feature_matching.py:346): align_corners=False, output not clamped."""
+    if not x.is_cuda:
+        raise _lib.DfbError("upsample input must be a CUDA tensor")
+    a = x.detach().float().contiguous()
+    B, Cc, h, w = a.shape
+    out = torch.empty(B, Cc, size[0], size[1], device=a.device)
+    check(lib.dfb_resize_bicubic(_p(a), B * Cc, h, w, size[0], size[1], _p(out), _stream()))
+    return out
+
+
+def upsample_bilinear_ac(x, size):
+    """torch.nn.UpsamplingBilinear2d(size=size)(x) (align_corners=True; reference feature/dfnet.py:145)."""
+    if not x.is_cuda:
+        raise _lib.DfbError("upsample input must be a CUDA tensor")
+    a = x.detach().float().contiguous()
+    B, Cc, h, w = a.shape
+    out = torch.empty(B, Cc, size[0], size[1], device=a.device)
+    check(lib.dfb_resize_bilinear_ac(_p(a), B * Cc, h, w, size[0], size[1], _p(out), _stream()))
+    return out

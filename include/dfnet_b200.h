@@ -189,6 +189,13 @@ int dfb_dfnet_fwd(DfbDfnet* net, const float* x, int B, int H, int W, uint32_t f
 int dfb_cosine_loss(const float* fr, const float* ft, int C, int64_t HW, int per_channel, float eps, float* loss, void* ws,
                     size_t ws_bytes, void* stream);
 
+/* Resampling of fp32 [planes,h,w] -> [planes,Ho,Wo]:
+ *   bicubic     = torch.nn.Upsample(size, mode='bicubic') (align_corners=False, A=-0.75, clamped taps,
+ *                 output not clamped) used on the rendered image, feature/direct_feature_matching.py:346;
+ *   bilinear_ac = torch.nn.UpsamplingBilinear2d(size) (align_corners=True), feature/dfnet.py:145. */
+int dfb_resize_bicubic(const float* src, int64_t planes, int h, int w, int Ho, int Wo, float* dst, void* stream);
+int dfb_resize_bilinear_ac(const float* src, int64_t planes, int h, int w, int Ho, int Wo, float* dst, void* stream);
+
 /* triplet_loss_hard_negative_mining_plus (feature/misc.py:399-435): f1, f2 fp32 [L,B,C,H,W];
  * negatives are the batch-rolled stacks, the in-triplet case is argmin of four MSE distances,
  * TripletMarginLoss(margin, p=2, eps=1e-6, mean) reduces over W.  *loss, *chosen_case: device

@@ -144,3 +144,36 @@ def test_triplet_and_mse_run_feature_shapes():
     m = mse(f1, f2)
     assert abs(float(m) - float(((f1 - f2) ** 2).mean())) < 1e-5
     assert abs(float(mse2psnr(m)) + 10 * np.log10(float(m))) < 1e-4
+
+
+@pytest.mark.parametrize("h,w,Ho,Wo", [(120, 160, 480, 640), (60, 106, 240, 427), (7, 5, 13, 31), (30, 40, 30, 40)])
+def test_resize_kernels_vs_torch(h, w, Ho, Wo):
+    """Resampling kernels vs the torch fp32 ops the reference calls (bicubic may overshoot [0,1])."""
+    from dfnet_b200.misc import upsample_bicubic, upsample_bilinear_ac
+    torch.manual_seed(h * w)
+    x = torch.rand(2, 3, h, w, device=dev())
+    want = torch.nn.Upsample(size=(Ho, Wo), mode="bicubic")(x)
+    got = upsample_bicubic(x, (Ho, Wo))
+    assert float((got - want).abs().max()) < 2e-5
+    want = torch.nn.UpsamplingBilinear2d(size=(Ho, Wo))(x)
+    got = upsample_bilinear_ac(x, (Ho, Wo))
+    assert float((got - want).abs().max()) < 2e-5
+
+
+def test_dfnet_cambridge_shape_ragged_pooling():
+    """Cambridge df=2 shape 240x427 (odd widths through the max-pools: 427 -> 213 -> 106 -> 53 -> 26)
+    against the numpy oracle; siamese, all three levels upsampled to 240x427."""
+    from oracle import dfnet_oracle as DO
+    net = synthetic_dfnet("DFNet")
+    P = {k: v.numpy() for k, v in net.state_dict().items()}
+    rng = np.random.RandomState(9)
+    x = rng.rand(2, 3, 240, 427).astype(np.float32)
+    want, wpose = DO.dfnet_forward(P, x, single=False, return_pose=True, upH=240, upW=427)
+    feats, pose = net.to(dev())(torch.tensor(x, device=dev()), return_feature=True, isSingleStream=False, return_pose=True,
+                                upsampleH=240, upsampleW=427)
+    torch.cuda.synchronize()
+    assert feats[0].shape == (3, 1, 128, 240, 427)
+    assert relmax(pose.cpu().numpy(), wpose) < 5e-3
+    for s in range(2):
+        for l in range(3):
+            assert relmax(feats[s][l].cpu().numpy(), want[s][l]) < 5e-3, (s, l)

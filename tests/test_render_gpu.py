@@ -222,3 +222,24 @@ def test_umma_descriptor_selftest(ops, kind, N, K):
         errs[variant] = float(np.abs(D.cpu().numpy() - want).max())
     print("umma selftest max abs err by descriptor variant:", errs)
     assert errs[0] < 1e-3 * np.sqrt(K), errs
+
+
+def test_render_cfg5_shape_and_default_width(ops):
+    """BASELINE config[4] sampling (64+192 -> S=256, far=20) on the tensor-core path and the reference's
+    default network width 128 (models/options.py:30-33, fp32 path) against the oracle."""
+    hist = np.array([[5, 10, 20, 30, 15, 10, 5, 3, 1, 1]], np.float32)
+    c2w = np.array([[0.9848, 0.0, 0.1736, 0.2], [0.0, 1.0, 0.0, -0.1], [-0.1736, 0.0, 0.9848, 1.0]], np.float32)
+    mods, nets = synthetic_nets(8, 256)
+    h = ops.NerfHandle(*to_dev(mods))
+    want = O.render(5, 7, 9.0, nets, 64, 192, 0.0, 20.0, c2w=c2w, hist=hist, test_time=True)
+    got = h.render(64, 192, True, c2w=T(c2w), H=5, W=7, focal=9.0, near=0.0, far=20.0, hist=T(hist), mma="f16")
+    torch.cuda.synchronize()
+    assert rel_err(got["rgb"].cpu().numpy().reshape(5, 7, 3), want["rgb_map"]) < 1e-3
+    assert rel_err(got["acc"].cpu().numpy().reshape(5, 7), want["acc_map"]) < 1e-3
+    mods, nets = synthetic_nets(8, 128)
+    h = ops.NerfHandle(*to_dev(mods))
+    want = O.render(5, 7, 9.0, nets, 64, 64, 0.0, 2.5, c2w=c2w, hist=hist, test_time=True)
+    got = h.render(64, 64, True, c2w=T(c2w), H=5, W=7, focal=9.0, near=0.0, far=2.5, hist=T(hist), mma="f16")  # falls to fp32: W != 256
+    torch.cuda.synchronize()
+    assert rel_err(got["rgb"].cpu().numpy().reshape(5, 7, 3), want["rgb_map"]) < 1e-4
+    assert rel_err(got["disp"].cpu().numpy().reshape(5, 7), want["disp_map"]) < 1e-4
