@@ -95,7 +95,9 @@ struct TcArgs {
 };
 
 #ifdef DFB_TC_PROF
-#define PROF_DECL unsigned long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long prof_t0 = clock64();
+#define PROF_DECL unsigned long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; unsigned long long prof_step[16] = {0}; const long long prof_t0 = clock64();
+#define PROF_STEP(s, stmt) { const long long _t = clock64(); stmt; prof_step[s] += clock64() - _t; }
+#define PROF_FLUSH_STEPS if (a.prof && (threadIdx.x & 31) == 0) { for (int _i = 0; _i < 16; ++_i) a.prof[(size_t)(256 + blockIdx.x) * 16 + _i] = prof_step[_i]; }
 #define PROF_WAIT(slot, stmt) { const long long _t = clock64(); stmt; prof_acc[slot] += clock64() - _t; }
 #define PROF_PTR prof_acc
 #define PROF_FLUSH(base)                                                                   \
@@ -106,6 +108,8 @@ struct TcArgs {
 #else
 #define PROF_DECL
 #define PROF_WAIT(slot, stmt) { stmt; }
+#define PROF_STEP(s, stmt) { stmt; }
+#define PROF_FLUSH_STEPS
 #define PROF_PTR nullptr
 #define PROF_FLUSH(base)
 #endif
@@ -366,7 +370,7 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
             if (lp > 0) PROF_WAIT(2, mbar_wait_cluster<CG>(bar(PASS_DONE + slot), (lp - 1) & 1, a.error_flag));
             PROF_WAIT(2, mbar_wait_cluster<CG>(bar(PE_READY + slot), lp & 1, a.error_flag));
           } else {
-            PROF_WAIT(2, mbar_wait_cluster<CG>(bar(A_READY + slot), (lp * (n_steps - 1) + s - 1) & 1, a.error_flag));
+            PROF_STEP(s, mbar_wait_cluster<CG>(bar(A_READY + slot), (lp * (n_steps - 1) + s - 1) & 1, a.error_flag));
           }
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + slot * 256;
@@ -382,6 +386,7 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
         }
       }
     PROF_FLUSH(4)
+    PROF_FLUSH_STEPS
   } else if (warp >= 8 && warp < 12) {
     // ===== encoder: positional encoding of the next pass (nerfw.py:128-133) =================
     const int r = tid - 256;
@@ -432,6 +437,9 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
       const bool valid = g < a.P;
       const int64_t ray = (valid ? g : a.P - 1) / a.S;
       const float* rb = FULL ? a.raybias + ray * 256 : nullptr;
+      // the per-ray bias row (1 KB) is read by the dir/transient layer much later in the pass: pull it
+      // into L1 now so that those loads do not pay eight serial L2 round trips
+      if (FULL) asm volatile("prefetch.global.L1 [%0];" ::"l"(rb + (tid & 7) * 32));
       cx.sig = 0.f;
 #pragma unroll
       for (int c = 0; c < 3; ++c) cx.rgb[c] = 0.f;
@@ -751,12 +759,12 @@ int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const
   a.error_flag = g_error_flag;
 #ifdef DFB_TC_PROF
   if (!g_prof) {
-    DFB_CHECK_CUDA(cudaMalloc(&g_prof, 256 * 16 * sizeof(unsigned long long)));
+    DFB_CHECK_CUDA(cudaMalloc(&g_prof, 512 * 16 * sizeof(unsigned long long)));
   }
   {
     const char* w = getenv("DFB_TC_PROF_WHICH");
     if (!w || atoi(w) == which) {
-      DFB_CHECK_CUDA(cudaMemsetAsync(g_prof, 0, 256 * 16 * sizeof(unsigned long long), st));
+      DFB_CHECK_CUDA(cudaMemsetAsync(g_prof, 0, 512 * 16 * sizeof(unsigned long long), st));
       a.prof = g_prof;
     }
   }
@@ -788,7 +796,7 @@ int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const
 extern "C" int dfb_debug_tc_prof(unsigned long long* out_host, int n_cta) {
   if (!dfb::g_prof) return DFB_ERR_UNSUPPORTED;
   cudaDeviceSynchronize();
-  cudaMemcpy(out_host, dfb::g_prof, (size_t)n_cta * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaMemcpy(out_host, dfb::g_prof, (size_t)n_cta * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);  // n_cta up to 512: rows 256.. hold the issuer's per-step A_READY waits
   return DFB_OK;
 }
 

@@ -20,8 +20,9 @@ for which in (0, 1):
     for _ in range(2):
         h.render(64, 128, True, c2w=c2w, H=256, W=256, focal=300.0, near=0.0, far=2.5, hist=hist, mma="f16")
     torch.cuda.synchronize()
-    buf = np.zeros((148, 16), np.uint64)
-    rc = ops.lib.dfb_debug_tc_prof(buf.ctypes.data_as(C.c_void_p), 148)
+    big = np.zeros((512, 16), np.uint64)
+    rc = ops.lib.dfb_debug_tc_prof(big.ctypes.data_as(C.c_void_p), 512)
+    buf = big[:148]
     assert rc == 0, rc
     b = buf.astype(np.float64)
     names = {0: ("producer", ["wait W_EMPTY"]), 4: ("mma", ["wait W_FULL", "wait W_FULLP", "wait A_READY/PE"]),
@@ -36,3 +37,6 @@ for which in (0, 1):
         for i, lb in enumerate(labels):
             line += f" | {lb} {b[act, base + i].mean():12.0f} ({100 * b[act, base + i].mean() / tot[act].mean():.1f}%)"
         print(line)
+    steps = big[256:256 + 148].astype(np.float64).mean(0)
+    tot = b[:, 7].mean()
+    print("issuer wait for A_READY by step (% of kernel):", " ".join(f"{i}:{100 * v / tot:.1f}" for i, v in enumerate(steps) if v > 0))
