@@ -30,6 +30,9 @@
 #include <algorithm>
 #include <type_traits>
 
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -71,6 +74,9 @@ struct Step {
 };
 
 struct TcArgs {
+  // cta_group::2 only: 3-D tensor map over the weight image ([images][64 rows][256 B]); 2-SM TMA loads let
+  // BOTH CTAs' halves of a stage complete on the LEADER's mbarrier (no relay hop)
+  alignas(64) CUtensorMap tmap;
   Step steps[kMaxSteps];
   int n_steps;
   int kind[kMaxSteps];    // EpiKind of every step (EPI_DT = head + store halves)
@@ -216,6 +222,15 @@ __device__ __forceinline__ void epi_blocks(uint32_t t_row, uint32_t h_row, const
 
 // MMA issue for one (step, slot): KS K=16 MMAs per weight stage.  Kept as lean as possible:
 // this single warp paces the tensor pipe.
+// 2-SM TMA load of one 16 KB weight image (box [1][64][128 x 16-bit]) into this CTA's shared memory;
+// the transaction bytes are credited to the barrier at `bar_leader` in the LEADER CTA's shared memory.
+__device__ __forceinline__ void tma_load_img_2sm(uint32_t dst, const CUtensorMap* tmap, int img, uint32_t bar_leader) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_leader), "r"(0), "r"(0), "r"(img)
+      : "memory");
+}
+
 template <int CG, int KS>
 __device__ __forceinline__ void issue_step(uint32_t& stage, uint32_t& phase, int nch, uint32_t a_lo, uint32_t b_rows,
                                            uint32_t d_tmem, uint32_t idesc, uint32_t sW, uint32_t sBar, int* err,
@@ -252,8 +267,7 @@ __device__ __forceinline__ void issue_step(uint32_t& stage, uint32_t& phase, int
   }
 #pragma unroll 1
   for (int c = 0; c < nch; ++c) {
-    PROF_WAIT(0, mbar_wait(sBar + 8u * (W_FULL + stage), phase, err));
-    if (CG == 2) PROF_WAIT(1, mbar_wait_cluster<CG>(sBar + 8u * (W_FULLP + stage), phase, err));
+    PROF_WAIT(0, mbar_wait_cluster<CG>(sBar + 8u * (W_FULL + stage), phase, err));  // both CTAs' halves landed
     tc_fence_after();
     const uint32_t b_lo = ((sW + stage * kChunkBytes) >> 4) | (b_rows << 16);
     if (elect_one()) {
@@ -277,8 +291,8 @@ __device__ __forceinline__ void issue_step(uint32_t& stage, uint32_t& phase, int
 // SMs' tensor cores, every weight byte is fetched from L2 once per 256 rows, and the MMA issue
 // overhead per row halves.  Cross-CTA signalling: tcgen05.commit multicasts to the barriers of
 // both CTAs; epilogue / encoder threads of the peer arrive remotely on the leader's barriers
-// (mapa + mbarrier.arrive.release.cluster); the peer's otherwise idle MMA warp relays its local
-// weight-stage "full" barriers to the leader.
+// (mapa + mbarrier.arrive.release.cluster); weight stages are filled by 2-SM TMA loads
+// (cp.async.bulk.tensor...cta_group::2) that credit both CTAs' bytes to the leader's "full" barrier.
 template <typename T, int FULL, int CG>
 __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -295,7 +309,6 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
   if (tid == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(bar(W_FULL + i), 1), mbar_init(bar(W_EMPTY + i), 1);
-      mbar_init(bar(W_FULLP + i), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar(D_FULL + s), 1);
@@ -322,6 +335,7 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
       for (int s = 0; s < n_steps; ++s) {
         const int nch = a.steps[s].n_chunks;
         const uint8_t* src0 = wimg + (size_t)a.steps[s].chunk_base * (kChunkBytes * CG);
+        const int img0 = a.steps[s].chunk_base * CG + (int)rank;  // image index of chunk 0 for this CTA (CG 2)
         for (int slot = 0; slot < 2; ++slot) {
           const uint8_t* src = src0;
           for (int c = 0; c < nch; ++c, src += kChunkBytes * CG) {
@@ -332,8 +346,11 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
                 if ((stage & 1) == 0) mbar_expect_tx(bar(W_FULL + stage), 2 * kChunkBytes);
                 bulk_g2s(sW + stage * kChunkBytes, src, kChunkBytes, bar(W_FULL + (stage & ~1u)));
               } else {
-                mbar_expect_tx(bar(W_FULL + stage), kChunkBytes);
-                bulk_g2s(sW + stage * kChunkBytes, src, kChunkBytes, bar(W_FULL + stage));
+                // CTA pair: the leader arms ITS barrier with both halves' bytes; each CTA loads its own half
+                // with a 2-SM TMA whose completion is credited to the leader's barrier
+                const uint32_t bar_leader = bar(W_FULL + stage) & 0xFEFFFFFFu;  // same offset in cluster rank 0
+                if (rank == 0) mbar_expect_tx(bar(W_FULL + stage), 2 * kChunkBytes);
+                tma_load_img_2sm(sW + stage * kChunkBytes, &a.tmap, img0 + c * CG, bar_leader);
               }
             }
             __syncwarp();
@@ -343,18 +360,7 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
       }
     PROF_FLUSH(0)
   } else if (warp == 13 && rank != 0) {
-    // ===== peer CTA: relay "my half of the weight stage has landed" to the leader ============
-    uint32_t stage = 0, phase = 0;
-    for (int64_t p = unit0; p < a.n_pass; p += n_units)
-      for (int s = 0; s < n_steps; ++s) {
-        const int nch = 2 * a.steps[s].n_chunks;
-        for (int c = 0; c < nch; ++c) {
-          mbar_wait(bar(W_FULL + stage), phase, a.error_flag);
-          if (elect_one()) mbar_arrive_cluster(bar(W_FULLP + stage), 0);
-          __syncwarp();
-          if (++stage == kStages) stage = 0, phase ^= 1;
-        }
-      }
+    // peer CTA of a pair: the leader issues every MMA
   } else if (warp == 13) {
     // ===== MMA issuer (warp-uniform control flow, one elected lane issues) ===================
     PROF_DECL
@@ -550,6 +556,45 @@ __global__ void __launch_bounds__(128, 1) k_umma_selftest(const float* A, const 
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tb, 256); }
 }
 
+// Tensor-pipe rate probe: every CTA issues `iters` x 16 back-to-back MMAs (M=128, N=n, K=16) on resident
+// shared-memory operands in the kernel's no-swizzle panel layout and reports cycles per MMA.
+__global__ void __launch_bounds__(128, 1) k_umma_rate(int iters, int n, unsigned long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t tslot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (65536 + 32768) / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) { mbar_init(smem_u32(&mbar), 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc<1>(smem_u32(&tslot), 256);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tslot;
+  if (warp == 0) {
+    const uint32_t idesc = make_idesc(0, n, 128);
+    const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+    const uint32_t a_lo = (smem_u32(smem) >> 4) | ((2048u >> 4) << 16);
+    const uint32_t b_lo = ((smem_u32(smem) + 65536) >> 4) | ((uint32_t)n << 16);
+    const long long t0 = clock64();
+    if (elect_one()) {
+      for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int ks = 0; ks < 16; ++ks)
+          umma_f16<1>(tb, mk64(a_lo + ks * 256, desc_hi), mk64(b_lo + (ks & 1) * 2 * n, desc_hi), idesc, 1u);
+      }
+      umma_commit<1>(smem_u32(&mbar));
+    }
+    __syncwarp();
+    mbar_wait(smem_u32(&mbar), 0, nullptr);
+    const long long t1 = clock64();
+    if (tid == 0) out[blockIdx.x] = (unsigned long long)(t1 - t0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc<1>(tb, 256); }
+}
+
 }  // namespace tc
 
 // ---------------------------------------------------------------------------------------
@@ -708,6 +753,26 @@ int pack_tc_weights(DfbNerf* n, int which, const std::vector<std::vector<float>>
 }
 
 static int* g_error_flag = nullptr;
+
+// 3-D tensor map over a packed weight image: [n_img][64][128 x u16], one box = one 16 KB image.
+static int make_weight_tmap(void* base, size_t bytes, CUtensorMap* out) {
+  static PFN_cuTensorMapEncodeTiled encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    DFB_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    DFB_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, DFB_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    encode = (PFN_cuTensorMapEncodeTiled)fn;
+  }
+  const cuuint64_t dims[3] = {128, 64, (cuuint64_t)(bytes / tc::kChunkBytes)};
+  const cuuint64_t strides[2] = {256, (cuuint64_t)tc::kChunkBytes};
+  const cuuint32_t box[3] = {128, 64, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DFB_REQUIRE(r == CUDA_SUCCESS, DFB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return DFB_OK;
+}
 static unsigned long long* g_prof = nullptr;
 
 // cta_group used by the tcgen05 kernel.  1 (default) is the faster variant today: with CTA pairs
@@ -750,6 +815,10 @@ int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const
     cb += ls.K / kc;
   }
   a.wimg = np.blob16[kind == DFB_MMA_F16 ? 0 : 1][cg - 1];
+  if (cg == 2) {
+    int rc = make_weight_tmap(const_cast<void*>(a.wimg), np.blob16_bytes, &a.tmap);
+    if (rc) return rc;
+  }
   memcpy(a.tbl, np.tc_tbl.data(), sizeof(a.tbl));
   for (int i = 0; i < tc::kMaxSteps * 128; ++i) {
     const float lo = a.tbl[2 * i], hi = a.tbl[2 * i + 1];
@@ -797,6 +866,25 @@ extern "C" int dfb_debug_tc_prof(unsigned long long* out_host, int n_cta) {
   if (!dfb::g_prof) return DFB_ERR_UNSUPPORTED;
   cudaDeviceSynchronize();
   cudaMemcpy(out_host, dfb::g_prof, (size_t)n_cta * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);  // n_cta up to 512: rows 256.. hold the issuer's per-step A_READY waits
+  return DFB_OK;
+}
+
+// Debug seam: tensor-pipe rate with the kernel's operand layout; returns mean cycles per MMA over all CTAs.
+extern "C" int dfb_debug_umma_rate(int iters, int n, int grid, double* cycles_per_mma) {
+  using namespace dfb;
+  DFB_REQUIRE(cycles_per_mma && iters >= 1 && n >= 16 && n <= 256 && n % 16 == 0 && grid >= 1 && grid <= 1024, DFB_ERR_INVALID, "bad arguments");
+  unsigned long long* d = nullptr;
+  DFB_CHECK_CUDA(cudaMalloc(&d, grid * 8));
+  const int smem = 65536 + 32768;
+  DFB_CHECK_CUDA(cudaFuncSetAttribute(tc::k_umma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  tc::k_umma_rate<<<grid, 128, smem>>>(iters, n, d);
+  DFB_LAUNCH_CHECK();
+  std::vector<unsigned long long> h(grid);
+  DFB_CHECK_CUDA(cudaMemcpy(h.data(), d, grid * 8, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  double s = 0;
+  for (auto v : h) s += (double)v;
+  *cycles_per_mma = s / grid / ((double)iters * 16.0);
   return DFB_OK;
 }
 

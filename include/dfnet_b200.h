@@ -223,6 +223,10 @@ int dfb_profile_read(double* coarse_ms, double* fine_ms, int64_t* coarse_launche
  * -DDFB_TC_PROF record them (returns DFB_ERR_UNSUPPORTED otherwise). out_host: [n_cta][16] u64. */
 int dfb_debug_tc_prof(unsigned long long* out_host, int n_cta);
 
+/* Debug seam: measured tensor-pipe cycles per tcgen05.mma (M=128, N=n, K=16) with the kernels' no-swizzle
+ * panel layout, `grid` CTAs issuing back to back. */
+int dfb_debug_umma_rate(int iters, int n, int grid, double* cycles_per_mma);
+
 int dfb_debug_umma_gemm(const float* A, const float* B, int N, int K, int kind, int variant, float* D, void* stream);
 
 #ifdef __cplusplus

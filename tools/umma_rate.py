@@ -1,0 +1,16 @@
+"""Tensor-pipe rate probe: cycles per tcgen05.mma (M=128, K=16) for several N and grid sizes."""
+import ctypes as C
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+from dfnet_b200._lib import lib, check  # noqa: E402
+
+torch.cuda.init()
+torch.zeros(1, device="cuda")
+for grid in (1, 148):
+    for n in (64, 128, 256):
+        v = C.c_double()
+        check(lib.dfb_debug_umma_rate(2000, n, grid, C.byref(v)))
+        print(f"grid={grid:4d} N={n:3d}: {v.value:7.1f} cycles/MMA  (nominal {n // 2})")
