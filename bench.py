@@ -191,13 +191,10 @@ def main():
 
     def step_device(i):
         c2w = poses_d[i % len(poses_d)]
-        try:
-            _lib.check(lib.dfb_render_fwd(h._h, C.byref(cfg), None, C.c_void_p(c2w.data_ptr()), H, W, FOCAL, NEAR, FAR,
-                                          C.c_void_p(hist_d.data_ptr()), N, None, None, C.c_void_p(rgb.data_ptr()),
-                                          C.c_void_p(disp.data_ptr()), C.c_void_p(acc.data_ptr()), None,
-                                          C.c_void_p(ws.data_ptr()), ws_bytes, sp))
-        except _lib.DfbError:
-            raise
+        _lib.check(lib.dfb_render_fwd(h._h, C.byref(cfg), None, C.c_void_p(c2w.data_ptr()), H, W, FOCAL, NEAR, FAR,
+                                      C.c_void_p(hist_d.data_ptr()), N, None, None, C.c_void_p(rgb.data_ptr()),
+                                      C.c_void_p(disp.data_ptr()), C.c_void_p(acc.data_ptr()), None,
+                                      C.c_void_p(ws.data_ptr()), ws_bytes, sp))
 
     n_poses = 8
     poses_h = [torch.tensor(pose(rank * 1000 + i)).pin_memory() for i in range(n_poses)]
@@ -214,16 +211,7 @@ def main():
                                              C.c_void_p(acc_h.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(), sp))
         stream.synchronize()  # render_path consumes the image on the host every step (rendering.py:423)
 
-    try:
-        step_device(0)
-    except _lib.DfbError as e:
-        if args.mma == "auto":
-            mma = "fp32"
-            cfg.mma_kind = _lib.MMA_KINDS[mma]
-            ws, ws_bytes = h.workspace(cfg, N, dev, extra_bytes=stage)
-            step_device(0)
-        else:
-            raise e
+    step_device(0)
     args.mma = mma
     torch.cuda.synchronize()
 

@@ -50,6 +50,7 @@ class _DfnetHandle:
         self._fin = weakref.finalize(self, lib.dfb_dfnet_destroy, h)
         self._versions = None
         self._ws = None
+        self.n_levels = len(module.hypercolumn_layers)
 
     def refresh(self, module):
         sd = module.state_dict()
@@ -82,17 +83,17 @@ class _DfnetHandle:
         check(lib.dfb_dfnet_workspace_bytes(self._h, B, H, W, upH, upW, C.byref(need)))
         if self._ws is None or self._ws.numel() < need.value or self._ws.device != dev:
             self._ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
-        L = lib_levels = None
         flags = (1 if return_feature else 0) | (2 if single else 0) | (4 if return_pose else 0)
         ft = fr = pose = None
         if return_feature:
-            L = self.n_levels
             Bs = B if single else B // 2
-            ft = torch.empty(L, Bs, 128, upH, upW, device=dev)
-            fr = None if single else torch.empty(L, Bs, 128, upH, upW, device=dev)
+            ft = torch.empty(self.n_levels, Bs, 128, upH, upW, device=dev)
+            fr = None if single else torch.empty(self.n_levels, Bs, 128, upH, upW, device=dev)
         if return_pose:
             pose = torch.empty(B, 12, device=dev)
-        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+        def p(t):
+            return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
         check(lib.dfb_dfnet_fwd(self._h, p(x), B, H, W, flags, upH, upW, p(ft), p(fr), p(pose), p(self._ws),
                                 self._ws.numel(), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         return ft, fr, pose
@@ -125,7 +126,6 @@ class DFNet(nn.Module):
                                       "is not on the B200 hot path yet; call .eval() / freeze_bn_layer_train")
         if self._handle is None:
             self._handle = _DfnetHandle(self)
-            self._handle.n_levels = len(self.hypercolumn_layers)
         self._handle.refresh(self)
         ft, fr, pose = self._handle.forward(x, return_feature, isSingleStream, return_pose, int(upsampleH), int(upsampleW))
         if not return_feature:

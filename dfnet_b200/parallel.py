@@ -36,16 +36,12 @@ def render_images_sharded(render_one, poses, rank=None, world=None, gather=True)
         return torch.stack(mine) if mine else None
     counts = [shard_range(len(poses), r, world) for r in range(world)]
     max_n = max(b - a for a, b in counts)
-    shape = None
-    if mine:
-        shape = torch.tensor(list(mine[0].shape), device=mine[0].device)
-    shapes = [torch.zeros(3, dtype=torch.long, device=poses[0].device if hasattr(poses[0], "device") else "cpu")
-              for _ in range(world)]
-    me = shape.to(shapes[0].device) if shape is not None else torch.zeros_like(shapes[0])
-    dist.all_gather(shapes, me)
-    full = next(s for s in shapes if int(s.sum()) > 0).tolist()
-    dev, dt = (mine[0].device, mine[0].dtype) if mine else (shapes[0].device, torch.float32)
-    pad = torch.zeros([max_n] + full, device=dev, dtype=dt)
+    # rank 0 always owns image 0: it tells ranks without images (len(poses) < world) the image shape
+    meta = [(list(mine[0].shape), mine[0].dtype) if rank == 0 else None]
+    dist.broadcast_object_list(meta, src=0)
+    shape, dt = meta[0]
+    dev = mine[0].device if mine else (poses[0].device if isinstance(poses[0], torch.Tensor) else torch.device("cpu"))
+    pad = torch.zeros([max_n] + shape, device=dev, dtype=dt)
     for k, m in enumerate(mine):
         pad[k] = m
     out = [torch.empty_like(pad) for _ in range(world)]

@@ -93,9 +93,9 @@ def test_feature_loss_vs_reference_golden(g):
     fr = preprocess_features_for_loss(torch.tensor(feats[1]))[0].to(dev())
     for pc, key in ((False, "loss_per_channel_false"), (True, "loss_per_channel_true")):
         got = float(feature_loss(fr, ft, per_channel=pc))
-        assert abs(got - float(g[key])) < 1e-5 + 1e-3 * abs(float(g[key])), (pc, got, float(g[key]))
+        assert abs(got - float(np.asarray(g[key]).reshape(-1)[0])) < 1e-5 + 1e-3 * abs(float(np.asarray(g[key]).reshape(-1)[0])), (pc, got, float(np.asarray(g[key]).reshape(-1)[0]))
     got = float(feature_loss(fr[:128].contiguous(), ft[:128].contiguous()))
-    assert abs(got - float(g["loss_lvl0_false"])) < 1e-5 + 1e-3 * abs(float(g["loss_lvl0_false"]))
+    assert abs(got - float(np.asarray(g["loss_lvl0_false"]).reshape(-1)[0])) < 1e-5 + 1e-3 * abs(float(np.asarray(g["loss_lvl0_false"]).reshape(-1)[0]))
     # near-zero-norm rows: each norm is clamped to eps separately (torch >= 1.12 semantics)
     a = torch.zeros(4, 1000, device=dev())
     b = torch.randn(4, 1000, device=dev())
@@ -128,7 +128,7 @@ def test_triplet_loss_vs_reference_golden(g, k):
     from dfnet_b200.misc import triplet_loss_hard_negative_mining_plus as trip
     loss = trip(torch.tensor(g[f"trip_{k}_f1"], device=dev()), torch.tensor(g[f"trip_{k}_f2"], device=dev()), margin=1.0)
     assert int(trip.last_case) == k
-    assert abs(float(loss) - float(g[f"trip_{k}_loss"])) < 1e-5 + 1e-4 * abs(float(g[f"trip_{k}_loss"]))
+    assert abs(float(loss) - float(np.asarray(g[f"trip_{k}_loss"]).reshape(-1)[0])) < 1e-5 + 1e-4 * abs(float(np.asarray(g[f"trip_{k}_loss"]).reshape(-1)[0]))
 
 
 def test_triplet_and_mse_run_feature_shapes():

@@ -43,4 +43,4 @@ def test_dfnet_forward_oracle(g, tag, cls, L):
 def test_triplet_loss_oracle(g, k):
     loss, case = DO.triplet_loss_hnm_plus(g[f"trip_{k}_f1"], g[f"trip_{k}_f2"], 1.0)
     assert case == k                      # the four constructed inputs exercise the four cases
-    assert abs(float(loss) - float(g[f"trip_{k}_loss"])) < 1e-5
+    assert abs(float(loss) - float(np.asarray(g[f"trip_{k}_loss"]).reshape(-1)[0])) < 1e-5

@@ -47,7 +47,7 @@ def _worker(rank, world, port, n_img, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_img", [4, 5])
+@pytest.mark.parametrize("n_img", [4, 5, 1])
 def test_sharded_render_gloo_world2(n_img):
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
