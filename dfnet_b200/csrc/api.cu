@@ -344,3 +344,70 @@ extern "C" int dfb_profile_read(double* coarse_ms, double* fine_ms, int64_t* coa
   if (fine_launches) *fine_launches = cnt[1];
   return DFB_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// render backward w.r.t. the rays (test-time compositing, gradient of rgb only)
+// ------------------------------------------------------------------------------------------
+namespace dfb {
+int launch_render_bwd(const DfbNerf* nerf, const float* rayrec, const float* z, const float* raybias, const float* raw,
+                      const float* g_rgb, int64_t n_rays, int S, float* g_raw, float* g_samp, float* g_o, float* g_d,
+                      float* g_vd, cudaStream_t st);
+}
+
+namespace {
+constexpr int64_t kBwdChunk = 1 << 14;
+struct BwdWs { size_t rayrec, extra, zdummy, rb, g_raw, g_samp, total; };
+BwdWs bwd_layout(const DfbNerf* n, int64_t rays, int S) {
+  const DfbNerfDesc& d = n->desc;
+  BwdWs L;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
+  L.rayrec = take((size_t)rays * kRayRec * 4);
+  L.extra = take((size_t)rays * (27 + d.a_dim + d.t_dim) * 4);
+  L.zdummy = take((size_t)rays * 4 + 256);
+  L.rb = take((size_t)rays * d.W * 4);
+  L.g_raw = take((size_t)rays * S * 9 * 4);
+  L.g_samp = take((size_t)rays * S * 32 * 4);
+  L.total = off;
+  return L;
+}
+}  // namespace
+
+extern "C" int dfb_render_bwd_workspace_bytes(const DfbNerf* n, int64_t n_rays, int S, size_t* out) {
+  DFB_REQUIRE(n && out && n_rays >= 0 && S >= 1, DFB_ERR_INVALID, "bad arguments");
+  *out = bwd_layout(n, std::min<int64_t>(std::max<int64_t>(n_rays, 1), kBwdChunk), S).total;
+  return DFB_OK;
+}
+
+extern "C" int dfb_render_bwd(DfbNerf* n, const float* rays, int64_t N, int S, const float* z_vals, const float* raw,
+                              const float* g_rgb, float* g_rays_o, float* g_rays_d, float* g_viewdirs, void* ws,
+                              size_t ws_bytes, void* stream) {
+  DFB_REQUIRE(n && rays && z_vals && raw && g_rgb && g_rays_o && g_rays_d && g_viewdirs, DFB_ERR_INVALID, "null argument");
+  DFB_REQUIRE(n->desc.has_fine && n->net[1].loaded && n->has_emb, DFB_ERR_INVALID, "fine network / embeddings not loaded");
+  if (N == 0) return DFB_OK;
+  DFB_CHECK_CUDA(cudaSetDevice(n->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const DfbNerfDesc& d = n->desc;
+  const int64_t chunk = std::min<int64_t>(N, kBwdChunk);
+  const BwdWs L = bwd_layout(n, chunk, S);
+  DFB_REQUIRE(ws && ws_bytes >= L.total, DFB_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", L.total, ws_bytes);
+  char* base = (char*)ws;
+  auto P = [&](size_t off) { return (float*)(base + off); };
+  const int hb = d.hist_bin, n_extra = 27 + d.a_dim + d.t_dim;
+  for (int64_t r0 = 0; r0 < N; r0 += chunk) {
+    const int64_t nr = std::min<int64_t>(chunk, N - r0);
+    PrepArgs pa = {};
+    pa.rays = rays + r0 * (11 + hb), pa.hb = hb, pa.n_vocab = d.n_vocab, pa.emb_a = n->emb_a, pa.emb_t = n->emb_t;
+    pa.N = nr, pa.Nc = 1, pa.t_vals = P(L.zdummy) + nr, pa.rayrec = P(L.rayrec), pa.z = P(L.zdummy);
+    pa.extra = P(L.extra), pa.n_extra = n_extra, pa.a_dim = d.a_dim, pa.t_dim = d.t_dim;
+    DFB_CHECK_CUDA(cudaMemsetAsync(P(L.zdummy) + nr, 0, 4, st));
+    int rc = launch_prep(pa, st);
+    if (rc) return rc;
+    rc = launch_raybias(pa.extra, n_extra, nr, n->net[1], true, P(L.rb), n->net[1].n_dt, st);
+    if (rc) return rc;
+    rc = launch_render_bwd(n, P(L.rayrec), z_vals + r0 * S, P(L.rb), raw + r0 * S * 9, g_rgb + r0 * 3, nr, S, P(L.g_raw),
+                           P(L.g_samp), g_rays_o + r0 * 3, g_rays_d + r0 * 3, g_viewdirs + r0 * 3, st);
+    if (rc) return rc;
+  }
+  return DFB_OK;
+}

@@ -69,6 +69,15 @@ struct NetPack {
   size_t trgb_w = 0, trgb_b = 0;    // [3][W/2], [3]
   size_t tbeta_w = 0, tbeta_b = 0;  // [W/2], [1]
 
+  // ---- fp32 backward layout (fine network): torch's [out][in] rows, `in` padded so that the input-
+  // gradient GEMMs g_in = W^T g_out run with the same kernel structure (mlp_simt_bwd.cu) -------------
+  float* blob32b = nullptr;
+  std::vector<size_t> bw_trunk;     // D entries: [W][in_pad]; layer 0: in_pad = pek; skip layer: [pe(pek) | h(W)]
+  size_t bw_final = 0;              // [W][W]
+  size_t bw_dt = 0;                 // [W][W]: rows 0..W/2 dir_encoding[:, :W], rows W/2..W transient_encoding.0[:, :W]
+  size_t bw_dtx = 0;                // [W/2][32]: dir_encoding[:, W:W+27] (view-direction encoding columns)
+  size_t bw_t[3] = {0, 0, 0};       // transient_encoding.{2,4,6}: [W/2][W/2]
+
   // ---- tcgen05 layout (W == 256 only): 16-bit core-matrix panels, see mlp_tc.cu ------
   void* blob16[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [fp16|bf16][cta_group 1|2 chunking]
   size_t blob16_bytes = 0;

@@ -77,6 +77,7 @@ extern "C" void dfb_nerf_destroy(DfbNerf* n) {
   if (!n) return;
   for (int i = 0; i < 2; ++i) {
     if (n->net[i].blob32) cudaFree(n->net[i].blob32);
+    if (n->net[i].blob32b) cudaFree(n->net[i].blob32b);
     for (int k = 0; k < 2; ++k)
       for (int g = 0; g < 2; ++g)
         if (n->net[i].blob16[k][g]) cudaFree(n->net[i].blob16[k][g]);
@@ -227,6 +228,47 @@ extern "C" int dfb_nerf_load(DfbNerf* n, int which, const float* const* params, 
   DFB_CHECK_CUDA(cudaMalloc(&np.blob32, blob.size() * sizeof(float)));
   DFB_CHECK_CUDA(cudaMemcpy(np.blob32, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
 
+  if (fine) {
+    // backward layout: rows = outputs (torch layout), input dimension padded / reordered like the forward K order
+    std::vector<float> bb;
+    auto balloc = [&](size_t cnt) { size_t off = (bb.size() + 3) / 4 * 4; bb.resize(off + cnt, 0.f); return off; };
+    np.bw_trunk.assign(D, 0);
+    for (int i = 0; i < D; ++i) {
+      const std::vector<float>& w = P[2 * i];
+      const bool is_skip = (i == d.skip);
+      const int kin = i == 0 ? in_xyz : (is_skip ? W + in_xyz : W);
+      const int kp = i == 0 ? pek : (is_skip ? pek + W : W);
+      const size_t o = balloc((size_t)W * kp);
+      for (int nn = 0; nn < W; ++nn)
+        for (int k = 0; k < kin; ++k) {
+          int kk = k;
+          if (is_skip) kk = k < in_xyz ? k : pek + (k - in_xyz);
+          bb[o + (size_t)nn * kp + kk] = w[(size_t)nn * kin + k];
+        }
+      np.bw_trunk[i] = o;
+    }
+    np.bw_final = balloc((size_t)W * W);
+    memcpy(&bb[np.bw_final], wf.data(), (size_t)W * W * sizeof(float));
+    const std::vector<float>& wt0 = P[pi + 8];
+    const int kdd = W + in_dir + a_dim, ktt = W + t_dim;
+    np.bw_dt = balloc((size_t)W * W);
+    for (int nn = 0; nn < H; ++nn)
+      for (int k = 0; k < W; ++k) {
+        bb[np.bw_dt + (size_t)nn * W + k] = wd[(size_t)nn * kdd + k];
+        bb[np.bw_dt + (size_t)(H + nn) * W + k] = wt0[(size_t)nn * ktt + k];
+      }
+    np.bw_dtx = balloc((size_t)H * 32);
+    for (int nn = 0; nn < H; ++nn)
+      for (int j = 0; j < in_dir; ++j) bb[np.bw_dtx + (size_t)nn * 32 + j] = wd[(size_t)nn * kdd + W + j];
+    for (int i = 0; i < 3; ++i) {
+      np.bw_t[i] = balloc((size_t)H * H);
+      memcpy(&bb[np.bw_t[i]], P[pi + 10 + 2 * i].data(), (size_t)H * H * sizeof(float));
+    }
+    if (np.blob32b) cudaFree(np.blob32b);
+    np.blob32b = nullptr;
+    DFB_CHECK_CUDA(cudaMalloc(&np.blob32b, bb.size() * sizeof(float)));
+    DFB_CHECK_CUDA(cudaMemcpy(np.blob32b, bb.data(), bb.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
   int rc = pack_tc_weights(n, which, P);
   if (rc != DFB_OK) return rc;
   np.loaded = true;

@@ -40,6 +40,39 @@ def raw2outputs_NeRFW(raw, z_vals, rays_d=None, raw_noise_std=0, output_transien
     return o["rgb"], o["disp"], o["acc"], o["weights"], o["depth"], o["transient_sigmas"], o["beta"]
 
 
+class _RenderRaysFn(torch.autograd.Function):
+    """Test-time render of explicit rays with a hand-written backward w.r.t. rays_o, rays_d and viewdirs
+    (dfb_render_bwd).  Only rgb_map carries gradient (what train.py back-propagates, reference
+    feature/direct_feature_matching.py:342-378); disp_map and acc_map are marked non-differentiable."""
+
+    @staticmethod
+    def forward(ctx, rays_o, rays_d, viewdirs, near_far_hist, handle, N_samples, N_importance, mma):
+        rec = torch.cat([rays_o, rays_d, near_far_hist[:, :2], viewdirs, near_far_hist[:, 2:]], -1)
+        o = handle.render(N_samples, N_importance, True, rays=rec, mma=mma, want=("z_vals", "raw"))
+        ctx.handle = handle
+        ctx.save_for_backward(rec, o["z_vals"], o["raw"])
+        ctx.mark_non_differentiable(o["disp"], o["acc"])
+        return o["rgb"], o["disp"], o["acc"]
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_disp, g_acc):
+        rec, z_vals, raw = ctx.saved_tensors
+        g_o, g_d, g_vd = ctx.handle.render_backward(rec, z_vals, raw, g_rgb)
+        return g_o, g_d, g_vd, None, None, None, None, None
+
+
+def _get_rays_torch(H, W, focal, c2w):
+    """Differentiable get_rays (reference models/ray_utils.py:5-15) for the training path, where the
+    pose carries gradient; a handful of tiny torch ops."""
+    dev = c2w.device
+    i, j = torch.meshgrid(torch.linspace(0, W - 1, W, device=dev), torch.linspace(0, H - 1, H, device=dev), indexing="ij")
+    i, j = i.t(), j.t()
+    dirs = torch.stack([(i - W * .5) / focal, -(j - H * .5) / focal, -torch.ones_like(i)], -1)
+    rays_d = torch.sum(dirs[..., None, :] * c2w[:3, :3], -1)
+    rays_o = c2w[:3, -1].expand(rays_d.shape)
+    return rays_o, rays_d
+
+
 def _handle(kw):
     return ops.handle_for(kw["network_fn"], kw.get("network_fine"), kw.get("embedding_a"), kw.get("embedding_t"))
 
@@ -110,6 +143,26 @@ def render(H, W, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0.,
     test_time = kwargs.get("test_time", False)
     Nc, Nf = kwargs["N_samples"], kwargs.get("N_importance", 0)
     perturb = kwargs.get("perturb", 0.)
+    needs_grad = torch.is_grad_enabled() and ((c2w is not None and c2w.requires_grad) or
+                                              (rays is not None and any(t.requires_grad for t in rays)))
+    if needs_grad:
+        # training path of train.py: gradient of rgb_map w.r.t. the pose / rays through the fine network
+        if not test_time or perturb or Nf == 0:
+            raise NotImplementedError("the differentiable render covers the test-time configuration train.py uses "
+                                      "(render_kwargs_test with N_importance > 0)")
+        h = _handle(kwargs)
+        rays_o, rays_d = _get_rays_torch(int(H), int(W), float(focal), c2w) if c2w is not None else rays
+        sh = list(rays_d.shape[:-1])
+        rays_o, rays_d = rays_o.reshape(-1, 3).float(), rays_d.reshape(-1, 3).float()
+        viewdirs = rays_d / torch.norm(rays_d, dim=-1, keepdim=True)
+        n = rays_d.shape[0]
+        hist = img_idx.to(rays_d.device).float().reshape(-1, img_idx.shape[-1])
+        if hist.shape[0] != n:
+            hist = hist[:1].expand(n, -1)
+        nfh = torch.cat([torch.full((n, 1), float(near), device=rays_d.device),
+                         torch.full((n, 1), float(far), device=rays_d.device), hist], -1)
+        rgb, disp, acc = _RenderRaysFn.apply(rays_o, rays_d, viewdirs, nfh, h, Nc, Nf, mma)
+        return [rgb.reshape(sh + [3]), disp.reshape(sh), acc.reshape(sh), {}]
     if c2w is not None and not perturb:
         # whole image from one pose: rays are generated in-kernel
         h = _handle(kwargs)

@@ -139,6 +139,18 @@ int dfb_render_image_host(DfbNerf* nerf, const DfbRenderCfg* cfg, const float* c
                           float near, float far, const float* hist_host, float* rgb_host, float* disp_host,
                           float* acc_host, void* ws, size_t ws_bytes, void* stream);
 
+/* Backward of the test-time render w.r.t. the rays — what train.py needs from the renderer
+ * (feature/direct_feature_matching.py:342-378: the NeRF weights are frozen and z_samples detached,
+ * models/rendering.py:302, so only the fine network's inputs carry gradient).
+ * rays [N,11+hist_bin] as in the forward; z_vals [N,S] and raw [N,S,9] are the forward's extras
+ * (S = N_samples + N_importance); g_rgb [N,3] is dLoss/d rgb_map.  Outputs: gradients w.r.t. rays_o,
+ * rays_d (through pts = o + d*z) and the view directions (through the direction encoding), each [N,3].
+ * fp32 kernels (forward recompute + input-gradient chain); all device pointers. */
+int dfb_render_bwd_workspace_bytes(const DfbNerf* nerf, int64_t n_rays, int S, size_t* out);
+int dfb_render_bwd(DfbNerf* nerf, const float* rays, int64_t N, int S, const float* z_vals, const float* raw,
+                   const float* g_rgb, float* g_rays_o, float* g_rays_d, float* g_viewdirs, void* ws, size_t ws_bytes,
+                   void* stream);
+
 /* Op-level seams (same arguments as the reference functions). */
 /* sample_pdf (rendering.py:24-65): bins [N,nb], weights [N,nb-1], u [N,Nf] or NULL (det). */
 int dfb_sample_pdf(const float* bins, const float* weights, const float* u, int64_t N, int n_bins, int Nf,

@@ -243,3 +243,76 @@ def test_render_cfg5_shape_and_default_width(ops):
     torch.cuda.synchronize()
     assert rel_err(got["rgb"].cpu().numpy().reshape(5, 7, 3), want["rgb_map"]) < 1e-4
     assert rel_err(got["disp"].cpu().numpy().reshape(5, 7), want["disp_map"]) < 1e-4
+
+
+def _torch_render_rgb(mods, rays_o, rays_d, z_vals, hist):
+    """Differentiable float64 restatement of the test-time fine render for FIXED depths z_vals (the
+    reference detaches z_samples, models/rendering.py:302): nerfw.py:62-95,297-354 and rendering.py:169-212."""
+    import torch.nn.functional as F
+    c, f, ea, et = mods
+    P = {k: v.double() for k, v in f.state_dict().items()}
+
+    def embed(x, L):
+        out = [x]
+        for l in range(L):
+            out += [torch.sin(x * 2.0 ** l), torch.cos(x * 2.0 ** l)]
+        return torch.cat(out, -1)
+    N, S = z_vals.shape
+    vd = rays_d / rays_d.norm(dim=-1, keepdim=True)
+    pts = rays_o[:, None] + rays_d[:, None] * z_vals[..., None]
+    idx = hist.long()
+    a = ea.weight.double()[idx].reshape(1, -1).expand(N * S, -1)
+    tt = et.weight.double()[idx].reshape(1, -1).expand(N * S, -1)
+    xyz = embed(pts.reshape(-1, 3), 10)
+    dirs = embed(vd, 4)[:, None].expand(N, S, 27).reshape(-1, 27)
+    h = xyz
+    for i in range(f.D):
+        if i in f.skips:
+            h = torch.cat([xyz, h], 1)
+        h = F.relu(F.linear(h, P[f"xyz_encoding_{i+1}.0.weight"], P[f"xyz_encoding_{i+1}.0.bias"]))
+    sig = F.softplus(F.linear(h, P["static_sigma.0.weight"], P["static_sigma.0.bias"]))[:, 0]
+    fin = F.linear(h, P["xyz_encoding_final.weight"], P["xyz_encoding_final.bias"])
+    de = F.relu(F.linear(torch.cat([fin, dirs, a], 1), P["dir_encoding.0.weight"], P["dir_encoding.0.bias"]))
+    rgb = torch.sigmoid(F.linear(de, P["static_rgb.0.weight"], P["static_rgb.0.bias"]))
+    t = torch.cat([fin, tt], 1)
+    for k in (0, 2, 4, 6):
+        t = F.relu(F.linear(t, P[f"transient_encoding.{k}.weight"], P[f"transient_encoding.{k}.bias"]))
+    tsig = F.softplus(F.linear(t, P["transient_sigma.0.weight"], P["transient_sigma.0.bias"]))[:, 0]
+    trgb = torch.sigmoid(F.linear(t, P["transient_rgb.0.weight"], P["transient_rgb.0.bias"]))
+    sig, tsig, rgb, trgb = sig.reshape(N, S), tsig.reshape(N, S), rgb.reshape(N, S, 3), trgb.reshape(N, S, 3)
+    deltas = torch.cat([z_vals[:, 1:] - z_vals[:, :-1], torch.full_like(z_vals[:, :1], 1e2)], -1)
+    a_s, a_t = 1 - torch.exp(-deltas * sig), 1 - torch.exp(-deltas * tsig)
+    al = 1 - torch.exp(-deltas * (sig + tsig))
+    T = torch.cumprod(torch.cat([torch.ones_like(al[:, :1]), 1 - al], -1)[:, :-1], -1)
+    return ((a_s * T)[..., None] * rgb).sum(1) + ((a_t * T)[..., None] * trgb).sum(1)
+
+
+@pytest.mark.parametrize("D,W,Nc,Nf", [(8, 64, 16, 24), (8, 256, 64, 128)])
+def test_render_backward_wrt_rays_matches_autograd(ops, golden, D, W, Nc, Nf):
+    """dfb_render_bwd against float64 autograd of a torch restatement (fixed depths, as the reference detaches them)."""
+    from dfnet_b200 import rendering
+    mods, _ = synthetic_nets(D, W)
+    dmods = to_dev(mods)
+    rays = golden["e2e_c_rays"]
+    hist = T(golden["hist"])
+    ro = T(rays[0]).clone().requires_grad_(True)
+    rd = T(rays[1]).clone().requires_grad_(True)
+    kw = _render_kwargs(mods, Nc, Nf, True)
+    kw["network_fn"], kw["network_fine"], kw["embedding_a"], kw["embedding_t"] = dmods
+    rgb, disp, acc, _ = rendering.render(4, 6, 5.0, rays=(ro, rd), img_idx=hist, near=0.0, far=2.5, mma="fp32", **kw)
+    torch.manual_seed(0)
+    wgt = torch.randn_like(rgb)
+    (rgb * wgt).sum().backward()
+    g_o, g_d = ro.grad.clone(), rd.grad.clone()
+    # reference gradient: same depths, float64 autograd
+    h = ops.handle_for(*dmods)
+    rec = O.make_ray_records(rays[0], rays[1], 0.0, 2.5, golden["hist"])
+    z = h.render(Nc, Nf, True, rays=T(rec), mma="fp32", want=("z_vals",))["z_vals"].double()
+    ro64 = T(rays[0]).double().requires_grad_(True)
+    rd64 = T(rays[1]).double().requires_grad_(True)
+    rgb64 = _torch_render_rgb(dmods, ro64, rd64, z, hist.reshape(-1))
+    assert rel_err(rgb.detach().cpu().numpy(), rgb64.detach().cpu().numpy()) < 1e-4
+    (rgb64 * wgt.double()).sum().backward()
+    for got, want in ((g_o, ro64.grad), (g_d, rd64.grad)):
+        scale = float(want.abs().max())
+        assert float((got.double() - want).abs().max()) < 2e-3 * scale, (float((got.double() - want).abs().max()), scale)
