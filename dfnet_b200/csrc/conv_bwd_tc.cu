@@ -1,0 +1,335 @@
+// Weight-gradient convolution on tcgen05 for the DFNet pose regressor (reference
+// feature/direct_feature_matching.py:378 `loss.backward()` through feature/dfnet.py:74-172):
+//
+//   dW[n, c, ky, kx] = sum_{b,y,x} gO[b,y,x,n] * X[b, y+ky-pad, x+kx-pad, c]
+//
+// Both operands are NHWC, i.e. the contraction index (pixel) is the SLOW one: they are MN-major
+// tcgen05 operands.  With the im2col-free patch layout of conv_tc.cu,
+// [8-channel panel][patch row][patch col][16 B], eight consecutive pixels of a patch row form one
+// 8(K) x 16 B(MN) core matrix, the next channel panel is SBO away and the next patch row (the next
+// 8 pixels of the K dimension) LBO away, so again every filter tap is only a shifted start address.
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace dfb {
+namespace wg {
+
+using namespace dfb::tc;
+
+// instruction descriptor with explicit operand formats and major-ness (bit 15 / 16: 1 = MN-major)
+__device__ __forceinline__ uint32_t make_idesc_ex(int fmt_a, int fmt_b, int a_mn, int b_mn, int n, int m) {
+  return (1u << 4) | ((uint32_t)fmt_a << 7) | ((uint32_t)fmt_b << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ uint16_t cvt16(float v, int fmt) {
+  if (fmt) return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+  return __half_as_ushort(__float2half_rn(v));
+}
+
+
+// ------------------------------------------------------------------------------------------
+// weight-gradient kernel
+// ------------------------------------------------------------------------------------------
+constexpr int kTH = 16, kTW = 8;   // pixel tile = 128 contraction steps
+constexpr int kStages = 2;
+constexpr int kThreads = 160;      // warps 0-3: tile loaders, then epilogue; warp 4: MMA issuer
+constexpr uint32_t kGBytes = 16u * kTH * kTW * 16u;  // gO tile: 16 channel panels x 128 pixels x 16 B
+
+enum Bar { FULL = 0, EMPTY = 2, DONE = 4, N_BARS = 5 };
+
+struct WgArgs {
+  const uint16_t* gO;  // NHWC [B,H,W,Cout]
+  const uint16_t* X;   // NHWC [B,H,W,Cin_pad]
+  float* dW;           // [Cout][Cin][KH][KW], accumulated with atomics (zeroed by the caller)
+  int B, H, W, Cin, Cin_pad, Cout, KH, KW, pad;
+  int NB;              // input-channel block = N of the MMA (multiple of 16, NB * KW <= 512 TMEM columns)
+  int n_cib, n_cob, n_split;
+  int tiles_x, tiles_y, n_tiles;
+  int PW;              // patch columns incl. halo
+  uint32_t x_bytes;    // X patch: NB/8 panels x 16 rows x PW cols x 16 B
+  int fmt;
+  int* error_flag;
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// One CTA = (128 output channels, NB input channels, one filter row ky, one share of the pixel tiles).
+// D[co][kx*NB + ci] accumulates in TMEM over all the CTA's tiles; A = gO tile, B = X patch shifted by kx.
+__global__ void __launch_bounds__(kThreads, 1) k_conv_wgrad(const __grid_constant__ WgArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sG = smem_u32(smem);
+  const uint32_t sX = sG + kStages * kGBytes;
+  const uint32_t sBar = sX + kStages * a.x_bytes;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kStages * kGBytes + kStages * a.x_bytes + N_BARS * 8);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  auto bar = [&](int i) { return sBar + 8u * i; };
+
+  int u = blockIdx.x;
+  const int split = u % a.n_split; u /= a.n_split;
+  const int ky = u % a.KH; u /= a.KH;
+  const int cib = u % a.n_cib;
+  const int cob = u / a.n_cib;
+  const int t0 = (int)((int64_t)split * a.n_tiles / a.n_split), t1 = (int)((int64_t)(split + 1) * a.n_tiles / a.n_split);
+  if (t0 >= t1) return;  // uniform per CTA
+
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) mbar_init(bar(FULL + i), 128), mbar_init(bar(EMPTY + i), 1);
+    mbar_init(bar(DONE), 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc<1>(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int tiles_img = a.tiles_x * a.tiles_y;
+  const int npan = a.NB / 8;
+  const uint32_t xpanel = (uint32_t)kTH * a.PW * 16u;
+
+  if (warp < 4) {
+    const int cpo = a.Cout / 8, cpp = a.Cin_pad / 8;
+    uint32_t seq = 0;
+    for (int t = t0; t < t1; ++t, ++seq) {
+      const uint32_t st = seq % kStages, ph = (seq / kStages) & 1;
+      mbar_wait(bar(EMPTY + st), ph ^ 1, a.error_flag);
+      const int b = t / tiles_img, ti = t % tiles_img;
+      const int y0 = (ti / a.tiles_x) * kTH, x0 = (ti % a.tiles_x) * kTW;
+      // gO tile: 16 consecutive threads read the 256 contiguous bytes of one pixel's 128 channels
+      {
+        const uint16_t* base = a.gO + (int64_t)b * a.H * a.W * a.Cout;
+        const uint32_t dst0 = sG + st * kGBytes;
+        const int panel = tid & 15, c8 = cob * 16 + panel;
+        for (int pix = tid >> 4; pix < kTH * kTW; pix += 8) {
+          const int y = y0 + (pix >> 3), x = x0 + (pix & 7);
+          const bool ok = c8 < cpo && y < a.H && x < a.W;
+          const uint16_t* src = ok ? base + ((int64_t)y * a.W + x) * a.Cout + c8 * 8 : a.gO;
+          cp_async16(dst0 + panel * 2048u + pix * 16u, src, ok ? 16u : 0u);
+        }
+      }
+      // X patch for filter row ky: rows y0+ky-pad .. +15, cols x0-pad .. x0+7+pad
+      {
+        const uint16_t* base = a.X + (int64_t)b * a.H * a.W * a.Cin_pad;
+        const uint32_t dst0 = sX + st * a.x_bytes;
+        const int n_ent = kTH * a.PW;
+        for (int q = tid; q < n_ent * npan; q += 128) {
+          const int panel = q % npan, e = q / npan;
+          const int pr = e / a.PW, pc = e - pr * a.PW;
+          const int yy = y0 + pr + ky - a.pad, xx = x0 + pc - a.pad;
+          const int c8 = cib * npan + panel;
+          const bool ok = c8 < cpp && yy >= 0 && yy < a.H && xx >= 0 && xx < a.W;
+          const uint16_t* src = ok ? base + ((int64_t)yy * a.W + xx) * a.Cin_pad + c8 * 8 : a.X;
+          cp_async16(dst0 + panel * xpanel + e * 16u, src, ok ? 16u : 0u);
+        }
+      }
+      cp_async_commit();
+      if (seq >= 1) {
+        cp_async_wait<1>();
+        fence_proxy_async();
+        mbar_arrive(bar(FULL + (seq - 1) % kStages));
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    mbar_arrive(bar(FULL + (seq - 1) % kStages));
+
+    // ===== epilogue: thread = output channel; columns = (kx, ci) ==================================
+    mbar_wait(bar(DONE), 0, a.error_flag);
+    tc_fence_after();
+    const int co = cob * 128 + tid;
+    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int kx = 0; kx < a.KW; ++kx)
+      for (int c0 = 0; c0 < a.NB; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(t_row + kx * a.NB + c0, v);
+        tmem_ld_wait(v);
+        if (co < a.Cout) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int ci = cib * a.NB + c0 + j;
+            if (c0 + j < a.NB && ci < a.Cin)
+              atomicAdd(a.dW + (((int64_t)co * a.Cin + ci) * a.KH + ky) * a.KW + kx, __uint_as_float(v[j]));
+          }
+        }
+      }
+    tc_fence_before();
+  } else {
+    // ===== MMA issuer ===============================================================================
+    const uint32_t idesc = make_idesc_ex(a.fmt, a.fmt, 1, 1, a.NB, 128);
+    // MN-major, no swizzle: LBO = distance between 8-pixel K groups (next patch row), SBO = panel stride
+    const uint32_t a_hi = (2048u >> 4) | (1u << 14), a_lbo = (128u >> 4) << 16;
+    const uint32_t b_hi = (xpanel >> 4) | (1u << 14), b_lbo = ((uint32_t)(a.PW * 16) >> 4) << 16;
+    uint32_t seq = 0;
+    for (int t = t0; t < t1; ++t, ++seq) {
+      const uint32_t st = seq % kStages, ph = (seq / kStages) & 1;
+      mbar_wait(bar(FULL + st), ph, a.error_flag);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t g_lo = ((sG + st * kGBytes) >> 4) | a_lbo;
+        const uint32_t x_lo = ((sX + st * a.x_bytes) >> 4) | b_lbo;
+        for (int kx = 0; kx < a.KW; ++kx) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)  // K = 16 pixels = two patch rows
+            umma_f16<1>(tmem_base + kx * a.NB, mk64(g_lo + ks * 16u, a_hi), mk64(x_lo + (uint32_t)(ks * 2 * a.PW + kx), b_hi), idesc,
+                        (uint32_t)(seq | ks));
+        }
+        umma_commit<1>(bar(EMPTY + st));
+        if (t == t1 - 1) umma_commit<1>(bar(DONE));
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+// gB[n] += sum over pixels of gO[pix][n]   (bias gradient); grid (Cout/64, splits), 256 threads
+template <typename T>
+__global__ void k_bias_grad(const uint16_t* __restrict__ gO, int64_t npix, int C, float* __restrict__ gB) {
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63), part = threadIdx.x >> 6;
+  float s = 0.f;
+  for (int64_t p = (int64_t)blockIdx.y * 4 + part; p < npix; p += (int64_t)gridDim.y * 4)
+    s += std::is_same<T, __nv_bfloat16>::value ? __uint_as_float((uint32_t)gO[p * C + c] << 16)
+                                               : __half2float(__ushort_as_half(gO[p * C + c]));
+  __shared__ float sm[256];
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  if (part == 0) atomicAdd(gB + c, sm[threadIdx.x] + sm[threadIdx.x + 64] + sm[threadIdx.x + 128] + sm[threadIdx.x + 192]);
+}
+
+// Single-tile self test of MN-major operands: D[128,N] = sum_k A[k][m] * B[k][n].
+// smem image: [MN panel of 8][k][16 B]  (element (mn,k) at (mn/8)*K*16 + k*16 + (mn%8)*2).
+__global__ void __launch_bounds__(128, 1) k_umma_selftest_mn(const float* A, const float* Bm, int N, int K, int fmt_a, int fmt_b,
+                                                               int variant, float* D, int* error_flag) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t tslot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  uint16_t* sAm = reinterpret_cast<uint16_t*>(smem);
+  uint16_t* sBm = reinterpret_cast<uint16_t*>(smem + (size_t)K * 128 * 2);
+  for (int i = tid; i < 128 * K; i += 128) {
+    const int k = i / 128, m = i % 128;
+    sAm[(size_t)(m / 8) * K * 8 + k * 8 + m % 8] = cvt16(A[i], fmt_a);
+  }
+  for (int i = tid; i < N * K; i += 128) {
+    const int k = i / N, n = i % N;
+    sBm[(size_t)(n / 8) * K * 8 + k * 8 + n % 8] = cvt16(Bm[i], fmt_b);
+  }
+  if (tid == 0) { mbar_init(smem_u32(&mbar), 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(smem_u32(&tslot), 256);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tslot;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc_ex(fmt_a, fmt_b, 1, 1, N, 128);
+    for (int ks = 0; ks < K / 16; ++ks) {
+      const uint32_t a_addr = smem_u32(sAm) + ks * 256, b_addr = smem_u32(sBm) + ks * 256;
+      uint64_t ad, bd;
+      // variant 0: LBO = K-group stride (128 B), SBO = MN-panel stride (K*16 B); variant 1: swapped
+      if (variant == 0) ad = make_desc(a_addr, 128, K * 16), bd = make_desc(b_addr, 128, K * 16);
+      else ad = make_desc(a_addr, K * 16, 128), bd = make_desc(b_addr, K * 16, 128);
+      umma_f16(tb, ad, bd, idesc, ks > 0);
+    }
+    umma_commit(smem_u32(&mbar));
+  }
+  mbar_wait(smem_u32(&mbar), 0, error_flag);
+  tc_fence_after();
+  for (int cb = 0; cb < N / 32; ++cb) {
+    uint32_t v[32];
+    tmem_ld32(tb + ((uint32_t)(warp * 32) << 16) + cb * 32, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j) D[(size_t)tid * N + cb * 32 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tb, 256); }
+}
+
+}  // namespace wg
+}  // namespace dfb
+
+using namespace dfb;
+
+
+static int* g_wg_error_flag = nullptr;
+
+// dW [Cout,Cin,KH,KW] (+ optional dB [Cout]) from gO NHWC [B,H,W,Cout] and X NHWC [B,H,W,Cin_pad] (16-bit, fmt 0 f16 / 1 bf16).
+// Both outputs are overwritten.
+extern "C" int dfb_conv_wgrad(const void* gO, const void* X, int B, int H, int W, int Cin, int Cin_pad, int Cout, int KH, int fmt,
+                              float* dW, float* dB, void* stream) {
+  DFB_REQUIRE(gO && X && dW, DFB_ERR_INVALID, "dfb_conv_wgrad: null argument");
+  DFB_REQUIRE(B >= 1 && H >= 1 && W >= 1 && Cin >= 1 && Cin_pad % 8 == 0 && Cin_pad >= Cin && Cout % 64 == 0 && Cout >= 64,
+              DFB_ERR_INVALID, "dfb_conv_wgrad: bad shape");
+  DFB_REQUIRE(KH == 1 || KH == 3 || KH == 5, DFB_ERR_UNSUPPORTED, "kernel size must be 1, 3 or 5");
+  if (!g_wg_error_flag) {
+    DFB_CHECK_CUDA(cudaMalloc(&g_wg_error_flag, 4));
+    DFB_CHECK_CUDA(cudaMemset(g_wg_error_flag, 0, 4));
+  }
+  int dev = 0, sms = 0;
+  DFB_CHECK_CUDA(cudaGetDevice(&dev));
+  DFB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  cudaStream_t st = (cudaStream_t)stream;
+  wg::WgArgs a = {};
+  a.gO = (const uint16_t*)gO, a.X = (const uint16_t*)X, a.dW = dW;
+  a.B = B, a.H = H, a.W = W, a.Cin = Cin, a.Cin_pad = Cin_pad, a.Cout = Cout, a.KH = KH, a.KW = KH, a.pad = KH / 2;
+  const int nb_max = KH <= 3 ? 128 : 64;
+  a.NB = std::min(nb_max, round_up(Cin_pad, 16));
+  a.n_cib = (Cin_pad + a.NB - 1) / a.NB;
+  a.n_cob = (Cout + 127) / 128;
+  a.tiles_x = (W + wg::kTW - 1) / wg::kTW, a.tiles_y = (H + wg::kTH - 1) / wg::kTH;
+  a.n_tiles = a.tiles_x * a.tiles_y * B;
+  const int units = a.n_cib * a.n_cob * KH;
+  a.n_split = std::max(1, std::min(a.n_tiles, sms / units));
+  a.PW = wg::kTW + 2 * a.pad;
+  a.x_bytes = (uint32_t)(a.NB / 8) * wg::kTH * a.PW * 16u;
+  a.fmt = fmt, a.error_flag = g_wg_error_flag;
+  const size_t smem = (size_t)wg::kStages * (wg::kGBytes + a.x_bytes) + 256;
+  DFB_REQUIRE(smem <= 232448, DFB_ERR_UNSUPPORTED, "shared memory budget exceeded");
+  DFB_CHECK_CUDA(cudaMemsetAsync(dW, 0, (size_t)Cout * Cin * KH * KH * 4, st));
+  DFB_CHECK_CUDA(cudaFuncSetAttribute(wg::k_conv_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  wg::k_conv_wgrad<<<units * a.n_split, wg::kThreads, smem, st>>>(a);
+  DFB_LAUNCH_CHECK();
+  if (dB) {
+    DFB_CHECK_CUDA(cudaMemsetAsync(dB, 0, (size_t)Cout * 4, st));
+    const int64_t npix = (int64_t)B * H * W;
+    const int splits = (int)std::max<int64_t>(1, std::min<int64_t>(64, npix / 256));
+    if (fmt) wg::k_bias_grad<__nv_bfloat16><<<dim3(Cout / 64, splits), 256, 0, st>>>((const uint16_t*)gO, npix, Cout, dB);
+    else wg::k_bias_grad<__half><<<dim3(Cout / 64, splits), 256, 0, st>>>((const uint16_t*)gO, npix, Cout, dB);
+    DFB_LAUNCH_CHECK();
+  }
+  return DFB_OK;
+}
+
+extern "C" int dfb_debug_umma_gemm_mn(const float* A, const float* B, int N, int K, int fmt_a, int fmt_b, int variant, float* D,
+                                      void* stream) {
+  DFB_REQUIRE(A && B && D, DFB_ERR_INVALID, "null argument");
+  DFB_REQUIRE(N % 32 == 0 && N >= 32 && N <= 256 && K % 16 == 0 && K >= 16 && K <= 128, DFB_ERR_INVALID, "bad N / K");
+  int* flag = nullptr;
+  DFB_CHECK_CUDA(cudaMalloc(&flag, 4));
+  DFB_CHECK_CUDA(cudaMemset(flag, 0, 4));
+  const size_t smem = (size_t)K * 128 * 2 + (size_t)K * 256 * 2;
+  cudaStream_t st = (cudaStream_t)stream;
+  DFB_CHECK_CUDA(cudaFuncSetAttribute(wg::k_umma_selftest_mn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  wg::k_umma_selftest_mn<<<1, 128, smem, st>>>(A, B, N, K, fmt_a, fmt_b, variant, D, flag);
+  DFB_LAUNCH_CHECK();
+  DFB_CHECK_CUDA(cudaStreamSynchronize(st));
+  cudaFree(flag);
+  return DFB_OK;
+}

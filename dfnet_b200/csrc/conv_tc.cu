@@ -42,8 +42,11 @@ struct ConvArgs {
   const float* bias;  // [Cout]
   __half* out;        // NHWC [B,H,W,Cout], after activation (nullable)
   __half* tap;        // NHWC [B,H,W,Cout], before activation (nullable)
-  float* out_nchw;    // fp32 [B,Cout,H,W], before activation (nullable)
+  float* out_nchw;    // fp32 [B,nchw_C,H,W], before activation (nullable)
+  const uint16_t* mask;    // NHWC 16-bit [B,H,W,Cout]: result zeroed where mask <= 0 (ReLU backward; nullable)
+  const uint16_t* addend;  // NHWC 16-bit [B,H,W,Cout] added after masking (gradient of a second consumer; nullable)
   int B, H, W, Cin, Cout, KH, KW, pad, relu;
+  int nchw_C;         // channels written to out_nchw (<= Cout: the data gradient of conv1_1 has 3)
   int nt;             // N tile (64, 128, 256)
   int n_ntiles;
   int tiles_x, tiles_y;
@@ -65,6 +68,14 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // bias / activation / stores of one 32-channel block of one pixel
+template <typename T>
+__device__ __forceinline__ float ld16f(uint16_t u);
+template <>
+__device__ __forceinline__ float ld16f<__half>(uint16_t u) { return __half2float(__ushort_as_half(u)); }
+template <>
+__device__ __forceinline__ float ld16f<__nv_bfloat16>(uint16_t u) { return __uint_as_float((uint32_t)u << 16); }
+
+template <typename T>
 __device__ __forceinline__ void epi_store(const ConvArgs& a, const uint32_t (&v)[32], int64_t m, bool valid, int n,
                                           int64_t nchw_base, int64_t plane) {
   float xv[32];
@@ -79,16 +90,44 @@ __device__ __forceinline__ void epi_store(const ConvArgs& a, const uint32_t (&v)
   }
   if (!valid) return;
   const int64_t o = m * a.Cout + n;
+  if (a.mask) {  // ReLU backward: post-activation values are >= 0, so "active" == a non-zero, non-negative pattern
+    const uint4* mk = reinterpret_cast<const uint4*>(a.mask + o);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 mm = __ldg(mk + q);
+      const uint32_t w4[4] = {mm.x, mm.y, mm.z, mm.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t lo = w4[e] & 0xffffu, hi = w4[e] >> 16;
+        if (lo == 0u || (lo & 0x8000u)) xv[8 * q + 2 * e] = 0.f;
+        if (hi == 0u || (hi & 0x8000u)) xv[8 * q + 2 * e + 1] = 0.f;
+      }
+    }
+  }
+  if (a.addend) {
+    const uint4* ad = reinterpret_cast<const uint4*>(a.addend + o);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 mm = __ldg(ad + q);
+      const uint32_t w4[4] = {mm.x, mm.y, mm.z, mm.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        xv[8 * q + 2 * e] += ld16f<T>((uint16_t)(w4[e] & 0xffffu));
+        xv[8 * q + 2 * e + 1] += ld16f<T>((uint16_t)(w4[e] >> 16));
+      }
+    }
+  }
   if (a.out_nchw) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) a.out_nchw[nchw_base + (int64_t)(n + j) * plane] = xv[j];
+    for (int j = 0; j < 32; ++j)
+      if (n + j < a.nchw_C) a.out_nchw[nchw_base + (int64_t)(n + j) * plane] = xv[j];
   }
   if (a.tap) {
     uint4* d = reinterpret_cast<uint4*>(a.tap + o);
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-      d[q] = make_uint4(pack2<__half>(xv[8 * q], xv[8 * q + 1]), pack2<__half>(xv[8 * q + 2], xv[8 * q + 3]),
-                        pack2<__half>(xv[8 * q + 4], xv[8 * q + 5]), pack2<__half>(xv[8 * q + 6], xv[8 * q + 7]));
+      d[q] = make_uint4(pack2<T>(xv[8 * q], xv[8 * q + 1]), pack2<T>(xv[8 * q + 2], xv[8 * q + 3]),
+                        pack2<T>(xv[8 * q + 4], xv[8 * q + 5]), pack2<T>(xv[8 * q + 6], xv[8 * q + 7]));
   }
   if (a.out) {
     if (a.relu) {
@@ -98,11 +137,12 @@ __device__ __forceinline__ void epi_store(const ConvArgs& a, const uint32_t (&v)
     uint4* d = reinterpret_cast<uint4*>(a.out + o);
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-      d[q] = make_uint4(pack2<__half>(xv[8 * q], xv[8 * q + 1]), pack2<__half>(xv[8 * q + 2], xv[8 * q + 3]),
-                        pack2<__half>(xv[8 * q + 4], xv[8 * q + 5]), pack2<__half>(xv[8 * q + 6], xv[8 * q + 7]));
+      d[q] = make_uint4(pack2<T>(xv[8 * q], xv[8 * q + 1]), pack2<T>(xv[8 * q + 2], xv[8 * q + 3]),
+                        pack2<T>(xv[8 * q + 4], xv[8 * q + 5]), pack2<T>(xv[8 * q + 6], xv[8 * q + 7]));
   }
 }
 
+template <typename T>
 __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__ ConvArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int nt = a.nt;
@@ -189,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
     }
   } else if (warp == 9) {
     // ===== MMA issuer =============================================================================
-    const uint32_t idesc = make_idesc(0, nt, 128);
+    const uint32_t idesc = make_idesc(std::is_same<T, __nv_bfloat16>::value ? 1 : 0, nt, 128);
     // A: SBO = patch row pitch, LBO = panel stride.  B: SBO = 128 B, LBO = nt*16 B.
     const uint32_t a_hi = ((uint32_t)(a.PW * 16) >> 4) | (1u << 14);
     const uint32_t b_hi = (128u >> 4) | (1u << 14);
@@ -252,17 +292,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 256;
       const int64_t plane = (int64_t)a.H * a.W;
-      const int64_t nchw_base = ((int64_t)b * a.Cout * a.H + y) * a.W + x;
+      const int64_t nchw_base = ((int64_t)b * a.nchw_C * a.H + y) * a.W + x;
       uint32_t v0[32], v1[32];
       tmem_ld32(t_row, v0);
 #pragma unroll 1
       for (int cb = 0; cb < nt / 32; cb += 2) {  // nt is a multiple of 64: two blocks per trip
         tmem_ld_wait(v0);
         tmem_ld32(t_row + (cb + 1) * 32, v1);
-        epi_store(a, v0, m, valid, n0 + cb * 32, nchw_base, plane);
+        epi_store<T>(a, v0, m, valid, n0 + cb * 32, nchw_base, plane);
         tmem_ld_wait(v1);
         if (cb + 2 < nt / 32) tmem_ld32(t_row + (cb + 2) * 32, v0);
-        epi_store(a, v1, m, valid, n0 + (cb + 1) * 32, nchw_base, plane);
+        epi_store<T>(a, v1, m, valid, n0 + (cb + 1) * 32, nchw_base, plane);
       }
       tc_fence_before();
       mbar_arrive(bar(D_EMPTY + buf));
@@ -284,6 +324,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
 // ------------------------------------------------------------------------------------------
 struct DfbConv {
   int Cin, Cin_pad, Cout, KH, KW, pad, nt, n_ntiles, n_cc, cpp, tps, n_wst;
+  int fmt = 0;     // 0: fp16 operands, 1: bf16 operands
+  int dgrad = 0;   // 1: data-gradient convolution of the layer (Cin0, Cout0)
+  int Cin0 = 0, Cout0 = 0;
+  int nchw_C = 0;  // channels of the fp32 NCHW output (real output channels)
+  size_t wimg_bytes = 0;
   uint8_t* wimg = nullptr;
   float* bias = nullptr;
   int num_sms = 0;
@@ -291,14 +336,104 @@ struct DfbConv {
 
 using namespace dfb;
 
-static uint16_t f2h16(float f) { __half h = __float2half_rn(f); uint16_t u; memcpy(&u, &h, 2); return u; }
+extern "C" void dfb_conv_destroy(DfbConv* c);
 
-extern "C" int dfb_conv_create(int Cin, int Cout, int KH, int KW, const float* weight, const float* bias,
-                               const float* bn_scale, const float* bn_shift, DfbConv** out) {
+namespace dfb {
+namespace conv {
+
+struct PackArgs {
+  const float* w;   // [Cout0, Cin0, KH, KW] fp32 (device)
+  const float* b;   // [Cout0] or null
+  const float* sc;  // [Cout0] or null (eval-mode BatchNorm scale)
+  const float* sh;  // [Cout0] or null
+  uint16_t* img;
+  float* bias;      // [Cout] folded bias of this launch
+  int Cin0, Cout0, KH, KW, Cin, Cout, nt, n_ntiles, n_cc, tps, n_wst, fmt, dgrad;
+  int64_t total;    // elements of the image
+};
+
+// weight image: [n tile][channel slice][weight stage][tap in stage][8 panels][nt rows][8 elements]; one thread = one element
+__global__ void k_pack_conv_weights(const PackArgs a) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < a.Cout) {
+    float bf = 0.f;
+    if (!a.dgrad) {  // y = scale * (conv + bias) + shift
+      const float scn = a.sc ? a.sc[i] : 1.f;
+      bf = scn * (a.b ? a.b[i] : 0.f) + (a.sh ? a.sh[i] : 0.f);
+    }
+    a.bias[i] = bf;
+  }
+  if (i >= a.total) return;
+  int64_t r = i;
+  const int e = (int)(r % 8); r /= 8;
+  const int rr = (int)(r % a.nt); r /= a.nt;
+  const int pp = (int)(r % 8); r /= 8;
+  const int tis = (int)(r % a.tps); r /= a.tps;
+  const int ws = (int)(r % a.n_wst); r /= a.n_wst;
+  const int cc = (int)(r % a.n_cc); r /= a.n_cc;
+  const int t = (int)r;
+  const int tp = ws * a.tps + tis;
+  float v = 0.f;
+  if (tp < a.KH * a.KW) {
+    const int ky = tp / a.KW, kx = tp % a.KW;
+    const int ci = (cc * 8 + pp) * 8 + e, n = t * a.nt + rr;
+    if (!a.dgrad) {
+      if (ci < a.Cin0) v = (a.sc ? a.sc[n] : 1.f) * a.w[(((int64_t)n * a.Cin0 + ci) * a.KH + ky) * a.KW + kx];
+    } else if (n < a.Cin0 && ci < a.Cout0) {
+      // data gradient: n = input channel of the layer, ci = its output channel, filter flipped
+      v = (a.sc ? a.sc[ci] : 1.f) * a.w[(((int64_t)ci * a.Cin0 + n) * a.KH + (a.KH - 1 - ky)) * a.KW + (a.KW - 1 - kx)];
+    }
+  }
+  a.img[i] = a.fmt ? __bfloat16_as_ushort(__float2bfloat16_rn(v)) : __half_as_ushort(__float2half_rn(v));
+}
+
+}  // namespace conv
+}  // namespace dfb
+
+// (Re)pack the filter of an existing handle from fp32 tensors in host or device memory.
+int dfb_conv_update_impl(DfbConv* c, const float* weight, const float* bias, const float* bn_scale, const float* bn_shift,
+                         void* stream) {
+  DFB_REQUIRE(c && weight, DFB_ERR_INVALID, "dfb_conv_update: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t wn = (size_t)c->Cout0 * c->Cin0 * c->KH * c->KW;
+  // stage host tensors on the device (cudaMemcpyDefault accepts either side)
+  float* stage = nullptr;
+  const size_t need = (wn + 3 * (size_t)c->Cout0) * 4;
+  DFB_CHECK_CUDA(cudaMallocAsync((void**)&stage, need, st));
+  float* dw = stage, *db = stage + wn, *dsc = db + c->Cout0, *dsh = dsc + c->Cout0;
+  DFB_CHECK_CUDA(cudaMemcpyAsync(dw, weight, wn * 4, cudaMemcpyDefault, st));
+  if (bias) DFB_CHECK_CUDA(cudaMemcpyAsync(db, bias, c->Cout0 * 4, cudaMemcpyDefault, st));
+  if (bn_scale) DFB_CHECK_CUDA(cudaMemcpyAsync(dsc, bn_scale, c->Cout0 * 4, cudaMemcpyDefault, st));
+  if (bn_shift) DFB_CHECK_CUDA(cudaMemcpyAsync(dsh, bn_shift, c->Cout0 * 4, cudaMemcpyDefault, st));
+  conv::PackArgs a = {};
+  a.w = dw, a.b = bias ? db : nullptr, a.sc = bn_scale ? dsc : nullptr, a.sh = bn_shift ? dsh : nullptr;
+  a.img = (uint16_t*)c->wimg, a.bias = c->bias;
+  a.Cin0 = c->Cin0, a.Cout0 = c->Cout0, a.KH = c->KH, a.KW = c->KW, a.Cin = c->Cin, a.Cout = c->Cout, a.nt = c->nt;
+  a.n_ntiles = c->n_ntiles, a.n_cc = c->n_cc, a.tps = c->tps, a.n_wst = c->n_wst, a.fmt = c->fmt, a.dgrad = c->dgrad;
+  a.total = (int64_t)c->wimg_bytes / 2;
+  conv::k_pack_conv_weights<<<(unsigned)((a.total + 255) / 256), 256, 0, st>>>(a);
+  DFB_LAUNCH_CHECK();
+  DFB_CHECK_CUDA(cudaFreeAsync(stage, st));
+  return DFB_OK;
+}
+
+// fmt: 0 fp16 / 1 bf16 operands.  dgrad != 0 builds the DATA-GRADIENT convolution of the layer described by
+// (Cin0, Cout0, weight [Cout0,Cin0,KH,KW], bn_scale): gI[b,y,x,c] = sum_{n,ky,kx} gO[b,y+pad-ky,x+pad-kx,n] * scale[n] * w[n,c,ky,kx],
+// i.e. the same kernel run on the transposed, spatially flipped filter (its "Cin" is Cout0, its "Cout" is Cin0
+// rounded up to 64, no bias).
+int dfb_conv_create_impl(int Cin0, int Cout0, int KH, int KW, const float* weight, const float* bias, const float* bn_scale,
+                         const float* bn_shift, int fmt, int dgrad, DfbConv** out) {
+  const int Cin = dgrad ? Cout0 : Cin0, Cout = dgrad ? round_up(Cin0, 64) : Cout0;
   DFB_REQUIRE(weight && out && Cin >= 1 && Cout >= 64 && Cout % 64 == 0, DFB_ERR_INVALID,
               "dfb_conv_create: Cout must be a positive multiple of 64");
   DFB_REQUIRE(KH == KW && (KH == 1 || KH == 3 || KH == 5), DFB_ERR_UNSUPPORTED, "kernel size must be 1, 3 or 5");
+  int dev = 0, major = 0, sms = 0;
+  DFB_CHECK_CUDA(cudaGetDevice(&dev));
+  DFB_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  DFB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  DFB_REQUIRE(major == 10, DFB_ERR_UNSUPPORTED, "sm_100a code only");
   DfbConv* c = new DfbConv();
+  c->fmt = fmt, c->dgrad = dgrad, c->Cin0 = Cin0, c->Cout0 = Cout0, c->nchw_C = dgrad ? Cin0 : Cout0;
   c->Cin = Cin, c->Cin_pad = round_up(Cin, 8), c->Cout = Cout, c->KH = KH, c->KW = KW, c->pad = KH / 2;
   c->nt = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
   c->n_ntiles = Cout / c->nt;
@@ -306,45 +441,22 @@ extern "C" int dfb_conv_create(int Cin, int Cout, int KH, int KW, const float* w
   c->n_cc = (c->cpp + 7) / 8;
   c->tps = 256 / c->nt;
   c->n_wst = (KH * KW + c->tps - 1) / c->tps;
-  int dev = 0;
-  DFB_CHECK_CUDA(cudaGetDevice(&dev));
-  cudaDeviceProp p;
-  DFB_CHECK_CUDA(cudaGetDeviceProperties(&p, dev));
-  DFB_REQUIRE(p.major == 10, DFB_ERR_UNSUPPORTED, "sm_100a code only");
-  c->num_sms = p.multiProcessorCount;
-  const size_t wn = (size_t)Cout * Cin * KH * KW;
-  std::vector<float> w(wn), b(Cout, 0.f), sc(Cout, 1.f), sh(Cout, 0.f);
-  DFB_CHECK_CUDA(cudaMemcpy(w.data(), weight, wn * 4, cudaMemcpyDefault));
-  if (bias) DFB_CHECK_CUDA(cudaMemcpy(b.data(), bias, Cout * 4, cudaMemcpyDefault));
-  if (bn_scale) DFB_CHECK_CUDA(cudaMemcpy(sc.data(), bn_scale, Cout * 4, cudaMemcpyDefault));
-  if (bn_shift) DFB_CHECK_CUDA(cudaMemcpy(sh.data(), bn_shift, Cout * 4, cudaMemcpyDefault));
-  // eval-mode BatchNorm folded into the conv: y = scale * (conv + bias) + shift
-  std::vector<float> bf(Cout);
-  for (int n = 0; n < Cout; ++n) bf[n] = sc[n] * b[n] + sh[n];
-  // weight image: [n tile][channel slice][weight stage][tap in stage][8 panels][nt rows][8 halfs]
-  const size_t tap_bytes = (size_t)c->nt * 16 * 8;
-  const size_t b_bytes = tap_bytes * c->tps;
-  const int n_taps = KH * KW;
-  std::vector<uint16_t> img((size_t)c->n_ntiles * c->n_cc * c->n_wst * b_bytes / 2, 0);
-  for (int t = 0; t < c->n_ntiles; ++t)
-    for (int cc = 0; cc < c->n_cc; ++cc)
-      for (int tp = 0; tp < n_taps; ++tp) {
-        const size_t base = (((size_t)(t * c->n_cc + cc) * c->n_wst + tp / c->tps) * b_bytes + (tp % c->tps) * tap_bytes) / 2;
-        const int ky = tp / KW, kx = tp % KW;
-        for (int pp = 0; pp < 8; ++pp)
-          for (int rr = 0; rr < c->nt; ++rr)
-            for (int e = 0; e < 8; ++e) {
-              const int ci = (cc * 8 + pp) * 8 + e, n = t * c->nt + rr;
-              const float v = ci < Cin ? sc[n] * w[(((size_t)n * Cin + ci) * KH + ky) * KW + kx] : 0.f;
-              img[base + (size_t)pp * c->nt * 8 + (size_t)rr * 8 + e] = f2h16(v);
-            }
-      }
-  DFB_CHECK_CUDA(cudaMalloc(&c->wimg, img.size() * 2));
-  DFB_CHECK_CUDA(cudaMemcpy(c->wimg, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
-  DFB_CHECK_CUDA(cudaMalloc(&c->bias, Cout * 4));
-  DFB_CHECK_CUDA(cudaMemcpy(c->bias, bf.data(), Cout * 4, cudaMemcpyHostToDevice));
+  c->num_sms = sms;
+  c->wimg_bytes = (size_t)c->n_ntiles * c->n_cc * c->n_wst * c->tps * c->nt * 16 * 8;
+  if (cudaMalloc(&c->wimg, c->wimg_bytes) != cudaSuccess || cudaMalloc(&c->bias, Cout * 4) != cudaSuccess) {
+    dfb_conv_destroy(c);
+    DFB_REQUIRE(false, DFB_ERR_CUDA, "dfb_conv_create: out of device memory");
+  }
+  const int rc = dfb_conv_update_impl(c, weight, bias, bn_scale, bn_shift, nullptr);
+  if (rc) { dfb_conv_destroy(c); return rc; }
+  DFB_CHECK_CUDA(cudaStreamSynchronize(nullptr));  // the source tensors may be released by the caller on return
   *out = c;
   return DFB_OK;
+}
+
+extern "C" int dfb_conv_create(int Cin, int Cout, int KH, int KW, const float* weight, const float* bias,
+                               const float* bn_scale, const float* bn_shift, DfbConv** out) {
+  return dfb_conv_create_impl(Cin, Cout, KH, KW, weight, bias, bn_scale, bn_shift, 0, 0, out);
 }
 
 extern "C" void dfb_conv_destroy(DfbConv* c) {
@@ -356,8 +468,16 @@ extern "C" void dfb_conv_destroy(DfbConv* c) {
 
 static int* g_conv_error_flag = nullptr;
 
+int dfb_conv_run(DfbConv* c, const void* in_nhwc16, int B, int H, int W, int relu, void* out_nhwc16, void* tap_nhwc16,
+                 float* out_nchw32, const void* mask_nhwc16, const void* addend_nhwc16, void* stream);
+
 extern "C" int dfb_conv_fwd(DfbConv* c, const void* in_nhwc16, int B, int H, int W, int relu, void* out_nhwc16,
                             void* tap_nhwc16, float* out_nchw32, void* stream) {
+  return dfb_conv_run(c, in_nhwc16, B, H, W, relu, out_nhwc16, tap_nhwc16, out_nchw32, nullptr, nullptr, stream);
+}
+
+int dfb_conv_run(DfbConv* c, const void* in_nhwc16, int B, int H, int W, int relu, void* out_nhwc16, void* tap_nhwc16,
+                 float* out_nchw32, const void* mask_nhwc16, const void* addend_nhwc16, void* stream) {
   DFB_REQUIRE(c && in_nhwc16 && (out_nhwc16 || tap_nhwc16 || out_nchw32), DFB_ERR_INVALID, "dfb_conv_fwd: null argument");
   DFB_REQUIRE(B >= 1 && H >= 1 && W >= 1, DFB_ERR_INVALID, "bad image size");
   if (!g_conv_error_flag) {
@@ -367,6 +487,7 @@ extern "C" int dfb_conv_fwd(DfbConv* c, const void* in_nhwc16, int B, int H, int
   conv::ConvArgs a = {};
   a.in = (const __half*)in_nhwc16, a.wimg = c->wimg, a.bias = c->bias;
   a.out = (__half*)out_nhwc16, a.tap = (__half*)tap_nhwc16, a.out_nchw = out_nchw32;
+  a.mask = (const uint16_t*)mask_nhwc16, a.addend = (const uint16_t*)addend_nhwc16, a.nchw_C = c->nchw_C;
   a.B = B, a.H = H, a.W = W, a.Cin = c->Cin_pad, a.Cout = c->Cout, a.KH = c->KH, a.KW = c->KW, a.pad = c->pad, a.relu = relu;
   a.nt = c->nt, a.n_ntiles = c->n_ntiles, a.n_cc = c->n_cc, a.cpp = c->cpp;
   a.tiles_x = (W + conv::kTW - 1) / conv::kTW, a.tiles_y = (H + conv::kTH - 1) / conv::kTH;
@@ -380,8 +501,25 @@ extern "C" int dfb_conv_fwd(DfbConv* c, const void* in_nhwc16, int B, int H, int
   const int grid = (int)std::min<int64_t>(n_tiles, c->num_sms);
   const size_t smem = (size_t)conv::kAStages * a.a_bytes + (size_t)conv::kBStages * a.b_bytes + 256;
   DFB_REQUIRE(smem <= 232448, DFB_ERR_UNSUPPORTED, "shared memory budget exceeded");
-  DFB_CHECK_CUDA(cudaFuncSetAttribute(conv::k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  conv::k_conv_tc<<<grid, conv::kThreads, smem, (cudaStream_t)stream>>>(a);
+  if (c->fmt) {
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(conv::k_conv_tc<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv::k_conv_tc<__nv_bfloat16><<<grid, conv::kThreads, smem, (cudaStream_t)stream>>>(a);
+  } else {
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(conv::k_conv_tc<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv::k_conv_tc<__half><<<grid, conv::kThreads, smem, (cudaStream_t)stream>>>(a);
+  }
   DFB_LAUNCH_CHECK();
   return DFB_OK;
+}
+
+extern "C" int dfb_conv_create_ex(int Cin, int Cout, int KH, int KW, const float* weight, const float* bias, const float* bn_scale,
+                                  const float* bn_shift, int fmt, int dgrad, DfbConv** out) {
+  DFB_REQUIRE(fmt == 0 || fmt == 1, DFB_ERR_INVALID, "fmt must be 0 (fp16) or 1 (bf16)");
+  return dfb_conv_create_impl(Cin, Cout, KH, KW, weight, bias, bn_scale, bn_shift, fmt, dgrad ? 1 : 0, out);
+}
+
+extern "C" int dfb_conv_fwd_ex(DfbConv* c, const void* in_nhwc16, int B, int H, int W, int relu, void* out_nhwc16,
+                               void* tap_nhwc16, float* out_nchw32, const void* mask_nhwc16, const void* addend_nhwc16,
+                               void* stream) {
+  return dfb_conv_run(c, in_nhwc16, B, H, W, relu, out_nhwc16, tap_nhwc16, out_nchw32, mask_nhwc16, addend_nhwc16, stream);
 }

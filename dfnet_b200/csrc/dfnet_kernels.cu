@@ -12,17 +12,14 @@
 
 #include "common.cuh"
 
-struct DfbConv;
-extern "C" int dfb_conv_create(int Cin, int Cout, int KH, int KW, const float* weight, const float* bias,
-                               const float* bn_scale, const float* bn_shift, DfbConv** out);
-extern "C" void dfb_conv_destroy(DfbConv* c);
-extern "C" int dfb_conv_fwd(DfbConv* c, const void* in_nhwc16, int B, int H, int W, int relu, void* out_nhwc16,
-                            void* tap_nhwc16, float* out_nchw32, void* stream);
+#include "dfnet_handle.cuh"
+#include "tc_common.cuh"
 
 namespace dfb {
 
 // x [B,3,H,W] fp32 in [0,1] -> NHWC fp16 [B,H,W,8]: (x - mean) / std, channels 3..7 zero
-__global__ void k_input_norm_nhwc8(const float* __restrict__ x, __half* __restrict__ out, int64_t npix, int64_t plane) {
+template <typename T>
+__global__ void k_input_norm_nhwc8(const float* __restrict__ x, T* __restrict__ out, int64_t npix, int64_t plane) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix) return;
   const int64_t b = i / plane, p = i % plane;
@@ -30,14 +27,14 @@ __global__ void k_input_norm_nhwc8(const float* __restrict__ x, __half* __restri
   const float r = __fdiv_rn(__fsub_rn(s[0], 0.485f), 0.229f);
   const float g = __fdiv_rn(__fsub_rn(s[plane], 0.456f), 0.224f);
   const float bl = __fdiv_rn(__fsub_rn(s[2 * plane], 0.406f), 0.225f);
-  __half2 h0 = __floats2half2_rn(r, g), h1 = __floats2half2_rn(bl, 0.f);
   uint4 v;
-  v.x = *reinterpret_cast<uint32_t*>(&h0), v.y = *reinterpret_cast<uint32_t*>(&h1), v.z = 0u, v.w = 0u;
+  v.x = tc::pack2<T>(r, g), v.y = tc::pack2<T>(bl, 0.f), v.z = 0u, v.w = 0u;
   reinterpret_cast<uint4*>(out)[i] = v;
 }
 
 // 2x2 / stride 2 max pool (floor), NHWC fp16, 8 channels (16 B) per thread
-__global__ void k_maxpool2x2_nhwc(const __half* __restrict__ in, __half* __restrict__ out, int B, int H, int W, int C) {
+template <typename T>
+__global__ void k_maxpool2x2_nhwc(const T* __restrict__ in, T* __restrict__ out, int B, int H, int W, int C) {
   const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
   const int64_t n = (int64_t)B * Ho * Wo * C8;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -47,9 +44,15 @@ __global__ void k_maxpool2x2_nhwc(const __half* __restrict__ in, __half* __restr
   const uint4* p = reinterpret_cast<const uint4*>(in + (((int64_t)b * H + 2 * yo) * W + 2 * xo) * C) + c8;
   const int64_t rs = (int64_t)W * C8;
   uint4 a = p[0], bq = p[C8], c = p[rs], d = p[rs + C8];
+  // post-ReLU activations are >= 0 (or -0 / NaN-free), so the 15-bit magnitude patterns order like the values
   auto mx = [](uint32_t u, uint32_t v) {
-    __half2 r = __hmax2(*reinterpret_cast<__half2*>(&u), *reinterpret_cast<__half2*>(&v));
-    return *reinterpret_cast<uint32_t*>(&r);
+    const uint32_t ul = u & 0xffffu, vl = v & 0xffffu, uh = u >> 16, vh = v >> 16;
+    auto m1 = [](uint32_t p, uint32_t q) {  // max of two 16-bit floats by value (sign-magnitude compare)
+      const int32_t ps = (p & 0x8000u) ? -(int32_t)(p & 0x7fffu) : (int32_t)p;
+      const int32_t qs = (q & 0x8000u) ? -(int32_t)(q & 0x7fffu) : (int32_t)q;
+      return qs > ps ? q : p;
+    };
+    return m1(ul, vl) | (m1(uh, vh) << 16);
   };
   uint4 o;
   o.x = mx(mx(a.x, bq.x), mx(c.x, d.x)), o.y = mx(mx(a.y, bq.y), mx(c.y, d.y));
@@ -97,10 +100,11 @@ __global__ void __launch_bounds__(128) k_resize_bilinear_ac(const float* __restr
 }
 
 // adaptive average pool to 1x1 over NHWC fp16 -> fp32 [B,C]; one block per (b, 64 channels)
-__global__ void k_avgpool_nhwc(const __half* __restrict__ in, float* __restrict__ out, int HW, int C) {
+template <typename T>
+__global__ void k_avgpool_nhwc(const T* __restrict__ in, float* __restrict__ out, int HW, int C) {
   const int b = blockIdx.y, c = blockIdx.x * 64 + (threadIdx.x & 63), part = threadIdx.x >> 6;  // 256 threads: 4 pixel lanes
   float s = 0.f;
-  for (int p = part; p < HW; p += 4) s += __half2float(in[((int64_t)b * HW + p) * C + c]);
+  for (int p = part; p < HW; p += 4) s += (float)in[((int64_t)b * HW + p) * C + c];
   __shared__ float sm[256];
   sm[threadIdx.x] = s;
   __syncthreads();
@@ -220,22 +224,6 @@ using namespace dfb;
 // ------------------------------------------------------------------------------------------
 // DFNet handle
 // ------------------------------------------------------------------------------------------
-struct DfbDfnet {
-  int n_levels = 3;
-  DfbConv* enc[13] = {};
-  DfbConv* head1[3] = {};
-  DfbConv* head5[3] = {};
-  float* fc_w = nullptr;
-  float* fc_b = nullptr;
-  bool loaded = false;
-};
-
-static const int kEncCin[13] = {3, 64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512};
-static const int kEncCout[13] = {64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512, 512};
-static const bool kPoolAfter[13] = {false, true, false, true, false, false, true, false, false, true, false, false, false};
-static const int kTapConv[3] = {1, 6, 12};   // conv1_2, conv3_3, conv5_3
-static const int kTapCh[3] = {64, 256, 512};
-
 extern "C" int dfb_dfnet_create(int n_levels, DfbDfnet** out) {
   DFB_REQUIRE(out && (n_levels == 1 || n_levels == 3), DFB_ERR_INVALID, "n_levels must be 3 (DFNet) or 1 (DFNet_s)");
   DfbDfnet* d = new DfbDfnet();
@@ -247,47 +235,81 @@ extern "C" int dfb_dfnet_create(int n_levels, DfbDfnet** out) {
 extern "C" void dfb_dfnet_destroy(DfbDfnet* d) {
   if (!d) return;
   for (auto c : d->enc) dfb_conv_destroy(c);
+  for (auto c : d->enc_bf) dfb_conv_destroy(c);
+  for (auto c : d->enc_dg) dfb_conv_destroy(c);
   for (auto c : d->head1) dfb_conv_destroy(c);
   for (auto c : d->head5) dfb_conv_destroy(c);
+  for (auto c : d->head1_dg) dfb_conv_destroy(c);
+  for (auto c : d->head5_dg) dfb_conv_destroy(c);
+  if (d->bn_sc) cudaFree(d->bn_sc);
+  if (d->bn_sh) cudaFree(d->bn_sh);
   if (d->fc_w) cudaFree(d->fc_w);
   if (d->fc_b) cudaFree(d->fc_b);
   delete d;
 }
 
+namespace dfb {
+// eval-mode BatchNorm2d: y = (x - mean) / sqrt(var + eps) * gamma + beta  ->  scale, shift
+__global__ void k_bn_fold(const float* g, const float* be, const float* mu, const float* var, float eps, float* sc, float* sh) {
+  const int c = threadIdx.x;
+  const float s = g[c] / sqrtf(var[c] + eps);
+  sc[c] = s, sh[c] = be[c] - mu[c] * s;
+}
+}  // namespace dfb
+
+// create on first use, repack in place afterwards (every optimizer step re-loads the parameters)
+static int conv_set(DfbConv** slot, int Cin, int Cout, int K, const float* w, const float* b, const float* sc, const float* sh,
+                    int fmt, int dgrad) {
+  if (*slot) return dfb_conv_update_impl(*slot, w, b, sc, sh, nullptr);
+  return dfb_conv_create_impl(Cin, Cout, K, K, w, b, sc, sh, fmt, dgrad, slot);
+}
+
 // params: 13 x (conv weight, bias), then per level (w1x1, b1x1, w5x5, b5x5, bn_weight, bn_bias,
 // bn_running_mean, bn_running_var), then fc_pose weight, bias — fp32, host or device memory.
-extern "C" int dfb_dfnet_load(DfbDfnet* d, const float* const* params, const int64_t* numel, int n_params, float bn_eps) {
+// flags bit0: also (re)build the training variants (bf16 forward and data-gradient convolutions).
+extern "C" int dfb_dfnet_load_ex(DfbDfnet* d, const float* const* params, const int64_t* numel, int n_params, float bn_eps,
+                                 uint32_t flags) {
   DFB_REQUIRE(d && params && numel, DFB_ERR_INVALID, "null argument");
   const int expect = 26 + 8 * d->n_levels + 2;
   DFB_REQUIRE(n_params == expect, DFB_ERR_INVALID, "expected %d tensors, got %d", expect, n_params);
+  const bool train = flags & 1;
   for (int i = 0; i < 13; ++i) {
     DFB_REQUIRE(numel[2 * i] == (int64_t)kEncCout[i] * kEncCin[i] * 9 && numel[2 * i + 1] == kEncCout[i], DFB_ERR_INVALID,
                 "encoder conv %d has the wrong size", i);
-    if (d->enc[i]) dfb_conv_destroy(d->enc[i]);
-    int rc = dfb_conv_create(kEncCin[i], kEncCout[i], 3, 3, params[2 * i], params[2 * i + 1], nullptr, nullptr, &d->enc[i]);
+    int rc = conv_set(&d->enc[i], kEncCin[i], kEncCout[i], 3, params[2 * i], params[2 * i + 1], nullptr, nullptr, 0, 0);
     if (rc) return rc;
+    if (train) {
+      rc = conv_set(&d->enc_bf[i], kEncCin[i], kEncCout[i], 3, params[2 * i], params[2 * i + 1], nullptr, nullptr, 1, 0);
+      if (rc) return rc;
+      rc = conv_set(&d->enc_dg[i], kEncCin[i], kEncCout[i], 3, params[2 * i], nullptr, nullptr, nullptr, 1, 1);
+      if (rc) return rc;
+    }
   }
+  if (!d->bn_sc) DFB_CHECK_CUDA(cudaMalloc(&d->bn_sc, 3 * 128 * 4));
+  if (!d->bn_sh) DFB_CHECK_CUDA(cudaMalloc(&d->bn_sh, 3 * 128 * 4));
   for (int l = 0; l < d->n_levels; ++l) {
     const float* const* p = params + 26 + 8 * l;
     const int64_t* ne = numel + 26 + 8 * l;
     DFB_REQUIRE(ne[0] == 64 * kTapCh[l] && ne[1] == 64 && ne[2] == 128 * 64 * 25 && ne[3] == 128 && ne[4] == 128 &&
                     ne[5] == 128 && ne[6] == 128 && ne[7] == 128,
                 DFB_ERR_INVALID, "adaptation layer %d has the wrong size", l);
-    std::vector<float> g(128), be(128), mu(128), var(128), sc(128), sh(128);
-    DFB_CHECK_CUDA(cudaMemcpy(g.data(), p[4], 512, cudaMemcpyDefault));
-    DFB_CHECK_CUDA(cudaMemcpy(be.data(), p[5], 512, cudaMemcpyDefault));
-    DFB_CHECK_CUDA(cudaMemcpy(mu.data(), p[6], 512, cudaMemcpyDefault));
-    DFB_CHECK_CUDA(cudaMemcpy(var.data(), p[7], 512, cudaMemcpyDefault));
-    for (int c = 0; c < 128; ++c) {  // eval-mode BatchNorm2d: y = (x - mean) / sqrt(var + eps) * gamma + beta
-      sc[c] = g[c] / sqrtf(var[c] + bn_eps);
-      sh[c] = be[c] - mu[c] * sc[c];
+    float* bn = nullptr;  // the four BatchNorm vectors may live on the host: stage them
+    DFB_CHECK_CUDA(cudaMallocAsync((void**)&bn, 4 * 128 * 4, nullptr));
+    for (int k = 0; k < 4; ++k) DFB_CHECK_CUDA(cudaMemcpyAsync(bn + 128 * k, p[4 + k], 512, cudaMemcpyDefault, nullptr));
+    float* sc = d->bn_sc + 128 * l, *sh = d->bn_sh + 128 * l;
+    k_bn_fold<<<1, 128>>>(bn, bn + 128, bn + 256, bn + 384, bn_eps, sc, sh);
+    DFB_LAUNCH_CHECK();
+    DFB_CHECK_CUDA(cudaFreeAsync(bn, nullptr));
+    int rc = conv_set(&d->head1[l], kTapCh[l], 64, 1, p[0], p[1], nullptr, nullptr, 0, 0);
+    if (rc) return rc;
+    rc = conv_set(&d->head5[l], 64, 128, 5, p[2], p[3], sc, sh, 0, 0);
+    if (rc) return rc;
+    if (train) {
+      rc = conv_set(&d->head1_dg[l], kTapCh[l], 64, 1, p[0], nullptr, nullptr, nullptr, 1, 1);
+      if (rc) return rc;
+      rc = conv_set(&d->head5_dg[l], 64, 128, 5, p[2], nullptr, sc, nullptr, 1, 1);
+      if (rc) return rc;
     }
-    if (d->head1[l]) dfb_conv_destroy(d->head1[l]);
-    if (d->head5[l]) dfb_conv_destroy(d->head5[l]);
-    int rc = dfb_conv_create(kTapCh[l], 64, 1, 1, p[0], p[1], nullptr, nullptr, &d->head1[l]);
-    if (rc) return rc;
-    rc = dfb_conv_create(64, 128, 5, 5, p[2], p[3], sc.data(), sh.data(), &d->head5[l]);
-    if (rc) return rc;
   }
   const int o = 26 + 8 * d->n_levels;
   DFB_REQUIRE(numel[o] == 12 * 512 && numel[o + 1] == 12, DFB_ERR_INVALID, "fc_pose has the wrong size");
@@ -295,34 +317,43 @@ extern "C" int dfb_dfnet_load(DfbDfnet* d, const float* const* params, const int
   if (!d->fc_b) DFB_CHECK_CUDA(cudaMalloc(&d->fc_b, 12 * 4));
   DFB_CHECK_CUDA(cudaMemcpy(d->fc_w, params[o], 12 * 512 * 4, cudaMemcpyDefault));
   DFB_CHECK_CUDA(cudaMemcpy(d->fc_b, params[o + 1], 12 * 4, cudaMemcpyDefault));
+  DFB_CHECK_CUDA(cudaStreamSynchronize(nullptr));
   d->loaded = true;
   return DFB_OK;
 }
 
-static size_t al256(size_t x) { return (x + 255) / 256 * 256; }
+extern "C" int dfb_dfnet_load(DfbDfnet* d, const float* const* params, const int64_t* numel, int n_params, float bn_eps) {
+  return dfb_dfnet_load_ex(d, params, numel, n_params, bn_eps, 0);
+}
 
-struct DfWs { size_t in8, bufA, bufB, tap[3], mid, feat, pooled, total; };
-
-static DfWs dfnet_ws(int B, int H, int W, int n_levels, int upH, int upW) {
-  DfWs w;
+// Workspace layout.  tape = false: two ping-pong activation buffers (inference).  tape = true: every
+// activation has its own buffer, which is what dfb_dfnet_bwd reads back (training).
+DfWs dfnet_ws(int B, int H, int W, int n_levels, int upH, int upW, bool tape) {
+  DfWs w = {};
   size_t off = 0;
+  auto al256 = [](size_t x) { return (x + 255) / 256 * 256; };
   auto take = [&](size_t b) { size_t o = off; off += al256(b); return o; };
   const size_t px = (size_t)B * H * W;
   w.in8 = take(px * 8 * 2);
-  w.bufA = take(px * 64 * 2);
-  w.bufB = take(px * 64 * 2);
-  int h = H, wd = W;
-  int lv = 0;
+  const size_t bufA = tape ? 0 : take(px * 64 * 2), bufB = tape ? 0 : take(px * 64 * 2);
+  int h = H, wd = W, lv = 0, flip = 0;
   size_t stage = 256;  // fp32 NCHW staging of the largest level that needs resampling
   for (int i = 0; i < 13; ++i) {
+    w.h[i] = h, w.w[i] = wd;
+    w.act[i] = tape ? take((size_t)B * h * wd * kEncCout[i] * 2) : (flip ? bufB : bufA);
+    flip ^= 1;
     if (lv < 3 && kTapConv[lv] == i) {
       w.tap[lv] = take((size_t)B * h * wd * kTapCh[lv] * 2);
+      w.mid[lv] = (tape || lv == 0) ? take((size_t)B * h * wd * 64 * 2) : w.mid[0];
       if (lv < n_levels && (h != upH || wd != upW)) stage = std::max(stage, (size_t)B * h * wd * 128 * 4);
       ++lv;
     }
-    if (kPoolAfter[i]) h /= 2, wd /= 2;
+    if (kPoolAfter[i]) {
+      h /= 2, wd /= 2;
+      w.pool[i] = tape ? take((size_t)B * h * wd * kEncCout[i] * 2) : (flip ? bufB : bufA);
+      flip ^= 1;
+    }
   }
-  w.mid = take(px * 64 * 2);
   w.feat = take(stage);
   w.pooled = take((size_t)B * 512 * 4 + 256);
   w.total = off;
@@ -331,51 +362,55 @@ static DfWs dfnet_ws(int B, int H, int W, int n_levels, int upH, int upW) {
 
 extern "C" int dfb_dfnet_workspace_bytes(const DfbDfnet* d, int B, int H, int W, int upH, int upW, size_t* out) {
   DFB_REQUIRE(d && out && B >= 1 && H >= 32 && W >= 32, DFB_ERR_INVALID, "bad arguments (image must be at least 32x32)");
-  *out = dfnet_ws(B, H, W, d->n_levels, upH, upW).total;
+  *out = dfnet_ws(B, H, W, d->n_levels, upH, upW, false).total;
   return DFB_OK;
 }
 
-// flags: bit0 return_feature, bit1 single_stream, bit2 return_pose.
+extern "C" int dfb_dfnet_tape_bytes(const DfbDfnet* d, int B, int H, int W, int upH, int upW, size_t* out) {
+  DFB_REQUIRE(d && out && B >= 1 && H >= 32 && W >= 32, DFB_ERR_INVALID, "bad arguments (image must be at least 32x32)");
+  *out = dfnet_ws(B, H, W, d->n_levels, upH, upW, true).total;
+  return DFB_OK;
+}
+
+// flags: bit0 return_feature, bit1 single_stream, bit2 return_pose, bit3 keep the tape (ws = tape buffer of
+// dfb_dfnet_tape_bytes, read back by dfb_dfnet_bwd), bit4 bf16 operands in the encoder (pose-only training).
 // feats_t / feats_r: [L, Bs, 128, upH, upW] fp32 with Bs = B (single stream, feats_r unused) or B/2.
-extern "C" int dfb_dfnet_fwd(DfbDfnet* d, const float* x, int B, int H, int W, uint32_t flags, int upH, int upW,
-                             float* feats_t, float* feats_r, float* pose, void* ws, size_t ws_bytes, void* stream) {
-  DFB_REQUIRE(d && d->loaded && x, DFB_ERR_INVALID, "DFNet handle not loaded or null input");
-  const bool ret_feat = flags & 1, single = flags & 2, ret_pose = flags & 4;
-  DFB_REQUIRE(!ret_feat || feats_t, DFB_ERR_INVALID, "feature output missing");
-  DFB_REQUIRE(!ret_feat || single || (feats_r && B % 2 == 0), DFB_ERR_INVALID, "siamese mode needs an even batch and feats_r");
-  DFB_REQUIRE(!ret_pose || pose, DFB_ERR_INVALID, "pose output missing");
-  DFB_REQUIRE(H >= 32 && W >= 32, DFB_ERR_INVALID, "image must be at least 32x32");
-  const DfWs L = dfnet_ws(B, H, W, d->n_levels, upH, upW);
+template <typename T>
+static int dfnet_fwd_impl(DfbDfnet* d, const float* x, int B, int H, int W, uint32_t flags, int upH, int upW, float* feats_t,
+                          float* feats_r, float* pose, void* ws, size_t ws_bytes, void* stream) {
+  const bool ret_feat = flags & 1, single = flags & 2, ret_pose = flags & 4, tape = flags & 8;
+  const bool bf = std::is_same<T, __nv_bfloat16>::value;
+  const DfWs L = dfnet_ws(B, H, W, d->n_levels, upH, upW, tape);
   DFB_REQUIRE(ws && ws_bytes >= L.total, DFB_ERR_WORKSPACE, "workspace too small: need %zu bytes", L.total);
   cudaStream_t st = (cudaStream_t)stream;
   char* base = (char*)ws;
   const int64_t plane = (int64_t)H * W, npix = (int64_t)B * plane;
-  k_input_norm_nhwc8<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(x, (__half*)(base + L.in8), npix, plane);
+  k_input_norm_nhwc8<T><<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(x, (T*)(base + L.in8), npix, plane);
   DFB_LAUNCH_CHECK();
   const void* cur = base + L.in8;
-  void* bufs[2] = {base + L.bufA, base + L.bufB};
-  int flip = 0, h = H, w = W, lv = 0;
-  int tap_h[3] = {0, 0, 0}, tap_w[3] = {0, 0, 0};
+  int h = H, w = W, lv = 0;
   const int last_conv = d->n_levels == 1 && !ret_pose ? 1 : 12;  // DFNet_s stops after conv1_2 when no pose is needed
   for (int i = 0; i <= last_conv; ++i) {
     void* tap = nullptr;
-    if (lv < d->n_levels && kTapConv[lv] == i) { tap = base + L.tap[lv]; tap_h[lv] = h, tap_w[lv] = w; ++lv; }
-    const bool need_out = i < last_conv || ret_pose;
-    void* o = need_out ? bufs[flip] : nullptr;
-    int rc = dfb_conv_fwd(d->enc[i], cur, B, h, w, 1, o, tap, nullptr, stream);
+    if (ret_feat && lv < d->n_levels && kTapConv[lv] == i) { tap = base + L.tap[lv]; ++lv; }
+    const bool need_out = i < last_conv || ret_pose || tape;
+    void* o = need_out ? base + L.act[i] : nullptr;
+    DfbConv* cv = bf ? d->enc_bf[i] : d->enc[i];
+    DFB_REQUIRE(cv, DFB_ERR_INVALID, "training variants not loaded (dfb_dfnet_load_ex flags bit0)");
+    int rc = dfb_conv_fwd(cv, cur, B, h, w, 1, o, tap, nullptr, stream);
     if (rc) return rc;
-    if (!need_out) break;
-    cur = o, flip ^= 1;
-    if (kPoolAfter[i] || i == 12) {
+    if (i == last_conv && !ret_pose) break;
+    cur = o;
+    if (kPoolAfter[i]) {
       const int64_t n = (int64_t)B * (h / 2) * (w / 2) * (kEncCout[i] / 8);
-      k_maxpool2x2_nhwc<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const __half*)cur, (__half*)bufs[flip], B, h, w, kEncCout[i]);
+      k_maxpool2x2_nhwc<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const T*)cur, (T*)(base + L.pool[i]), B, h, w, kEncCout[i]);
       DFB_LAUNCH_CHECK();
-      cur = bufs[flip], flip ^= 1, h /= 2, w /= 2;
+      cur = base + L.pool[i], h /= 2, w /= 2;
     }
   }
   if (ret_pose) {  // cur = pool5 output [B,h,w,512]
     float* pooled = (float*)(base + L.pooled);
-    k_avgpool_nhwc<<<dim3(512 / 64, B), 256, 0, st>>>((const __half*)cur, pooled, h * w, 512);
+    k_avgpool_nhwc<T><<<dim3(512 / 64, B), 256, 0, st>>>((const T*)cur, pooled, h * w, 512);
     DFB_LAUNCH_CHECK();
     k_fc_small<<<B, 12 * 32, 0, st>>>(pooled, d->fc_w, d->fc_b, pose, 512, 12);
     DFB_LAUNCH_CHECK();
@@ -383,11 +418,11 @@ extern "C" int dfb_dfnet_fwd(DfbDfnet* d, const float* x, int B, int H, int W, u
   if (ret_feat) {
     const int Bs = single ? B : B / 2;
     for (int l = 0; l < d->n_levels; ++l) {
-      const int fh = tap_h[l], fw = tap_w[l];
-      int rc = dfb_conv_fwd(d->head1[l], base + L.tap[l], B, fh, fw, 1, base + L.mid, nullptr, nullptr, stream);
+      const int fh = L.h[kTapConv[l]], fw = L.w[kTapConv[l]];
+      int rc = dfb_conv_fwd(d->head1[l], base + L.tap[l], B, fh, fw, 1, base + L.mid[l], nullptr, nullptr, stream);
       if (rc) return rc;
       const size_t lvl_stride = (size_t)Bs * 128 * upH * upW;
-      const __half* mid = (const __half*)(base + L.mid);
+      const __half* mid = (const __half*)(base + L.mid[l]);
       if (fh == upH && fw == upW) {
         // align_corners resampling to the same size is the identity (level 0 at full resolution):
         // the 5x5 conv writes fp32 NCHW straight into the stacks; siamese split = two half batches
@@ -415,6 +450,19 @@ extern "C" int dfb_dfnet_fwd(DfbDfnet* d, const float* x, int B, int H, int W, u
     }
   }
   return DFB_OK;
+}
+
+extern "C" int dfb_dfnet_fwd(DfbDfnet* d, const float* x, int B, int H, int W, uint32_t flags, int upH, int upW,
+                             float* feats_t, float* feats_r, float* pose, void* ws, size_t ws_bytes, void* stream) {
+  DFB_REQUIRE(d && d->loaded && x, DFB_ERR_INVALID, "DFNet handle not loaded or null input");
+  const bool ret_feat = flags & 1, single = flags & 2, ret_pose = flags & 4, bf = flags & 16;
+  DFB_REQUIRE(!ret_feat || feats_t, DFB_ERR_INVALID, "feature output missing");
+  DFB_REQUIRE(!ret_feat || single || (feats_r && B % 2 == 0), DFB_ERR_INVALID, "siamese mode needs an even batch and feats_r");
+  DFB_REQUIRE(!ret_pose || pose, DFB_ERR_INVALID, "pose output missing");
+  DFB_REQUIRE(H >= 32 && W >= 32, DFB_ERR_INVALID, "image must be at least 32x32");
+  DFB_REQUIRE(!(bf && ret_feat), DFB_ERR_UNSUPPORTED, "bf16 operands cover the pose-only path (the adaptation heads run in fp16)");
+  if (bf) return dfnet_fwd_impl<__nv_bfloat16>(d, x, B, H, W, flags, upH, upW, feats_t, feats_r, pose, ws, ws_bytes, stream);
+  return dfnet_fwd_impl<__half>(d, x, B, H, W, flags, upH, upW, feats_t, feats_r, pose, ws, ws_bytes, stream);
 }
 
 // feature_loss (direct_feature_matching.py:114-136): fr, ft fp32 [C, HW] -> *loss (device scalar).
@@ -645,6 +693,107 @@ extern "C" int dfb_resize_bilinear_ac(const float* src, int64_t planes, int h, i
   const dim3 rg((Wo + 511) / 512, Ho, (unsigned)((planes + kResizePlanes - 1) / kResizePlanes));
   DFB_REQUIRE(rg.z <= 65535, DFB_ERR_INVALID, "too many planes");
   k_resize_bilinear_ac<<<rg, 128, 0, (cudaStream_t)stream>>>(src, dst, (int)planes, h, w, Ho, Wo);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// backward of the losses and of the bicubic resampling (train_on_batch, direct_feature_matching.py:342-378)
+// ------------------------------------------------------------------------------------------
+namespace dfb {
+
+// d/d fa of  1 - mean_rows cos(fa_r, fb_r):  -(g/rows) * ( fb/(na*nb) - ab*fa/(na^3*nb) ), with the eps clamps of the
+// forward (a clamped norm is a constant).  stats: ws[row][split][3] from k_cos_rows_partial.
+__global__ void k_cos_rows_bwd(const float* __restrict__ fa, const float* __restrict__ fb, const float* __restrict__ ws, int splits,
+                               int64_t cols, int rows, float eps, const float* __restrict__ g_loss, float* __restrict__ g_fa) {
+  const int row = blockIdx.y;
+  float ab = 0.f, aa = 0.f, bb = 0.f;
+  for (int s = 0; s < splits; ++s) {
+    const float* o = ws + ((int64_t)row * splits + s) * 3;
+    ab += o[0], aa += o[1], bb += o[2];
+  }
+  const float na = sqrtf(aa), nb = sqrtf(bb);
+  const float ca = fmaxf(na, eps), cb = fmaxf(nb, eps);
+  const float g = -__ldg(g_loss) / (float)rows;
+  const float k1 = g / (ca * cb);
+  const float k2 = na > eps ? g * ab / (ca * ca * ca * cb) : 0.f;
+  const float4* a4 = reinterpret_cast<const float4*>(fa + (int64_t)row * cols);
+  const float4* b4 = reinterpret_cast<const float4*>(fb + (int64_t)row * cols);
+  float4* o4 = reinterpret_cast<float4*>(g_fa + (int64_t)row * cols);
+  const int64_t n4 = (cols % 4 == 0 && ((int64_t)row * cols) % 4 == 0) ? cols / 4 : 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 x = __ldg(a4 + i), y = __ldg(b4 + i);
+    o4[i] = make_float4(k1 * y.x - k2 * x.x, k1 * y.y - k2 * x.y, k1 * y.z - k2 * x.z, k1 * y.w - k2 * x.w);
+  }
+  for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cols; i += (int64_t)gridDim.x * blockDim.x)
+    g_fa[(int64_t)row * cols + i] = k1 * fb[(int64_t)row * cols + i] - k2 * fa[(int64_t)row * cols + i];
+}
+
+// g_a = g * 2 (a - b) / n
+__global__ void k_mse_bwd(const float* __restrict__ a, const float* __restrict__ b, int64_t n, const float* __restrict__ g_loss,
+                          float* __restrict__ g_a) {
+  const float k = 2.f * __ldg(g_loss) / (float)n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    g_a[i] = k * (a[i] - b[i]);
+}
+
+// adjoint of k_resize_bicubic: every output gradient is scattered to its 16 (border-clamped) taps
+__global__ void k_resize_bicubic_bwd(const float* __restrict__ gdst, float* __restrict__ gsrc, int h, int w, int Ho, int Wo) {
+  const int xo = blockIdx.x * blockDim.x + threadIdx.x, yo = blockIdx.y;
+  if (xo >= Wo) return;
+  const int64_t pl = blockIdx.z;
+  const float sy = (float)h / (float)Ho, sx = (float)w / (float)Wo;
+  const float fy = sy * (yo + 0.5f) - 0.5f, fx = sx * (xo + 0.5f) - 0.5f;
+  const int iy = (int)floorf(fy), ix = (int)floorf(fx);
+  float cy[4], cx[4];
+  cubic_coeffs(fy - iy, cy);
+  cubic_coeffs(fx - ix, cx);
+  float* s = gsrc + pl * h * w;
+  const float g = __ldg(gdst + (pl * Ho + yo) * Wo + xo);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int yy = min(max(iy - 1 + i, 0), h - 1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int xx = min(max(ix - 1 + j, 0), w - 1);
+      atomicAdd(s + yy * w + xx, cy[i] * cx[j] * g);
+    }
+  }
+}
+
+}  // namespace dfb
+
+// gradient of dfb_cosine_loss w.r.t. fr; g_loss: device scalar (upstream gradient); ws as in the forward.
+extern "C" int dfb_cosine_loss_bwd(const float* fr, const float* ft, int C, int64_t HW, int per_channel, float eps,
+                                   const float* g_loss, float* g_fr, void* ws, size_t ws_bytes, void* stream) {
+  DFB_REQUIRE(fr && ft && g_loss && g_fr && ws && C >= 1 && HW >= 1, DFB_ERR_INVALID, "null or empty argument");
+  DFB_REQUIRE(!per_channel, DFB_ERR_UNSUPPORTED, "the backward covers the reference default per_channel=False");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int splits = (int)std::min<int64_t>(64, std::max<int64_t>(1, HW / 4096));
+  DFB_REQUIRE(ws_bytes >= (size_t)C * splits * 3 * 4, DFB_ERR_WORKSPACE, "workspace too small");
+  k_cos_rows_partial<<<dim3(splits, C), 256, 0, st>>>(fr, ft, HW, splits, (float*)ws);
+  DFB_LAUNCH_CHECK();
+  const int bx = (int)std::min<int64_t>(64, std::max<int64_t>(1, HW / 2048));
+  k_cos_rows_bwd<<<dim3(bx, C), 256, 0, st>>>(fr, ft, (const float*)ws, splits, HW, C, eps, g_loss, g_fr);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+// gradient of dfb_mse w.r.t. a
+extern "C" int dfb_mse_bwd(const float* a, const float* b, int64_t n, const float* g_loss, float* g_a, void* stream) {
+  DFB_REQUIRE(a && b && g_loss && g_a && n >= 1, DFB_ERR_INVALID, "null or empty argument");
+  const int blocks = (int)std::min<int64_t>(1184, (n + 255) / 256);
+  k_mse_bwd<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, b, n, g_loss, g_a);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+// adjoint of dfb_resize_bicubic: g_dst [P,Ho,Wo] -> g_src [P,h,w] (overwritten)
+extern "C" int dfb_resize_bicubic_bwd(const float* g_dst, int64_t planes, int h, int w, int Ho, int Wo, float* g_src, void* stream) {
+  DFB_REQUIRE(g_dst && g_src && planes >= 1 && h >= 1 && w >= 1 && Ho >= 1 && Wo >= 1, DFB_ERR_INVALID, "bad arguments");
+  DFB_REQUIRE(planes <= 65535, DFB_ERR_INVALID, "too many planes");
+  DFB_CHECK_CUDA(cudaMemsetAsync(g_src, 0, (size_t)planes * h * w * 4, (cudaStream_t)stream));
+  k_resize_bicubic_bwd<<<dim3((Wo + 127) / 128, Ho, (unsigned)planes), 128, 0, (cudaStream_t)stream>>>(g_dst, g_src, h, w, Ho, Wo);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }

@@ -50,12 +50,13 @@ class _DfnetHandle:
         self._fin = weakref.finalize(self, lib.dfb_dfnet_destroy, h)
         self._versions = None
         self._ws = None
+        self._bwd_ws = None
         self.n_levels = len(module.hypercolumn_layers)
 
-    def refresh(self, module):
+    def refresh(self, module, train=False):
         sd = module.state_dict()
-        v = [(t.data_ptr(), t._version) for t in sd.values()]
-        if v == self._versions:
+        v = [(t.data_ptr(), t._version) for t in sd.values()] + [bool(train)]
+        if v[:-1] == (self._versions or [None])[:-1] and (self._versions[-1] or not train):
             return
         names = [f"encoder.{i}" for i, m in enumerate(module.encoder) if isinstance(m, nn.Conv2d)]
         ts = []
@@ -70,20 +71,28 @@ class _DfnetHandle:
         ptrs = (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
         numel = (C.c_int64 * len(ts))(*[t.numel() for t in ts])
         eps = module.adaptation_layers.adapt_layer_0[3].eps
-        check(lib.dfb_dfnet_load(self._h, ptrs, numel, len(ts), eps))
+        check(lib.dfb_dfnet_load_ex(self._h, ptrs, numel, len(ts), eps, 1 if train else 0))
         self._versions = v
+        self.n_params = len(ts)
 
-    def forward(self, x, return_feature, single, return_pose, upH, upW):
+    def forward(self, x, return_feature, single, return_pose, upH, upW, tape=False, bf16=False):
+        """tape=True keeps every activation in a fresh buffer (returned as 4th value) for `backward`."""
         if not x.is_cuda:
             raise _lib.DfbError("DFNet input must be a CUDA tensor: the dfnet_b200 hot path has no CPU fallback")
         x = x.detach().float().contiguous()
         B, _, H, W = x.shape
         dev = x.device
         need = C.c_size_t()
-        check(lib.dfb_dfnet_workspace_bytes(self._h, B, H, W, upH, upW, C.byref(need)))
-        if self._ws is None or self._ws.numel() < need.value or self._ws.device != dev:
-            self._ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
         flags = (1 if return_feature else 0) | (2 if single else 0) | (4 if return_pose else 0)
+        if tape:
+            check(lib.dfb_dfnet_tape_bytes(self._h, B, H, W, upH, upW, C.byref(need)))
+            ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
+            flags |= 8 | (16 if bf16 else 0)
+        else:
+            check(lib.dfb_dfnet_workspace_bytes(self._h, B, H, W, upH, upW, C.byref(need)))
+            if self._ws is None or self._ws.numel() < need.value or self._ws.device != dev:
+                self._ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
+            ws = self._ws
         ft = fr = pose = None
         if return_feature:
             Bs = B if single else B // 2
@@ -94,9 +103,88 @@ class _DfnetHandle:
 
         def p(t):
             return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
-        check(lib.dfb_dfnet_fwd(self._h, p(x), B, H, W, flags, upH, upW, p(ft), p(fr), p(pose), p(self._ws),
-                                self._ws.numel(), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        check(lib.dfb_dfnet_fwd(self._h, p(x), B, H, W, flags, upH, upW, p(ft), p(fr), p(pose), p(ws),
+                                ws.numel(), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        if tape:
+            return ft, fr, pose, (ws, flags)
         return ft, fr, pose
+
+    def backward(self, tape, shape, upH, upW, g_ft, g_fr, level_mask, g_pose, want_gx, param_shapes):
+        """dfb_dfnet_bwd.  Returns (g_x [B,3,H,W] or None, list of parameter gradients in load order or None)."""
+        ws, flags = tape
+        B, H, W = shape
+        dev = ws.device
+        need = C.c_size_t()
+        check(lib.dfb_dfnet_bwd_workspace_bytes(self._h, B, H, W, C.byref(need)))
+        if self._bwd_ws is None or self._bwd_ws.numel() < need.value or self._bwd_ws.device != dev:
+            self._bwd_ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
+
+        def p(t):
+            return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+        g_x = gx_sub = None
+        if want_gx:
+            g_x = torch.zeros(B, 3, H, W, device=dev)
+            gx_sub = g_x
+            if not (flags & 2) and (g_ft is None) != (g_fr is None):  # siamese, one stream differentiated
+                gx_sub = g_x[B // 2:] if g_ft is None else g_x[:B // 2]
+        grads = ptrs = None
+        if param_shapes is not None:
+            # one flat buffer: a data-parallel step all-reduces it in a single NCCL call (parallel.py)
+            sizes = [int(torch.Size(sh).numel()) for sh in param_shapes]
+            flat = torch.zeros(sum(sizes), device=dev)
+            grads, off = [], 0
+            for sh, n in zip(param_shapes, sizes):
+                grads.append(flat[off:off + n].view(sh))
+                off += n
+            head = range(26, 26 + 8 * self.n_levels)
+            ptrs = (C.c_void_p * len(grads))(*[None if i in head else g.data_ptr() for i, g in enumerate(grads)])
+            self.last_flat_grad = flat
+        check(lib.dfb_dfnet_bwd(self._h, B, H, W, flags, upH, upW, p(g_ft), p(g_fr), level_mask, p(g_pose), p(ws), p(gx_sub),
+                                ptrs, 0 if grads is None else len(grads), p(self._bwd_ws), self._bwd_ws.numel(),
+                                C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return g_x, grads
+
+
+class _DfnetFn(torch.autograd.Function):
+    """DFNet forward with the hand-written backward (dfb_dfnet_bwd): gradient of the feature stacks w.r.t. the input
+    images (feature net of train_on_batch, frozen) or of the pose w.r.t. the encoder / fc_pose parameters (pose
+    regressor).  Reference: autograd through feature/dfnet.py:106-172."""
+
+    @staticmethod
+    def forward(ctx, x, handle, cfg, *params):
+        return_feature, single, return_pose, upH, upW, level_mask = cfg
+        need_p = any(t.requires_grad for t in params)
+        if need_p and return_feature:
+            raise NotImplementedError("parameter gradients cover the pose path (train.py); training the adaptation heads "
+                                      "(run_feature.py) is not on the B200 path yet")
+        ft, fr, pose, tape = handle.forward(x, return_feature, single, return_pose, upH, upW, tape=True, bf16=need_p)
+        ctx.handle, ctx.tape, ctx.cfg, ctx.need_p = handle, tape, cfg, need_p
+        ctx.xshape = (x.shape[0], x.shape[2], x.shape[3])
+        ctx.pshapes = [t.shape for t in params]
+        ctx.want_gx = x.requires_grad
+        ctx.set_materialize_grads(False)
+        outs = [t for t in (ft, fr, pose) if t is not None]
+        ctx.slots = [n for n, t in (("ft", ft), ("fr", fr), ("pose", pose)) if t is not None]
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        g = dict(zip(ctx.slots, gs))
+        g_ft, g_fr, g_pose = (None if g.get(k) is None else g[k].float().contiguous() for k in ("ft", "fr", "pose"))
+        return_feature, single, return_pose, upH, upW, level_mask = ctx.cfg
+        n_out = 3 + len(ctx.pshapes)
+        if g_ft is None and g_fr is None and g_pose is None:
+            return (None,) * n_out
+        if (g_ft is not None or g_fr is not None) and g_pose is not None:
+            raise NotImplementedError("feature and pose gradients through one DFNet forward are not on the B200 path yet")
+        g_x, grads = ctx.handle.backward(ctx.tape, ctx.xshape, upH, upW, g_ft, g_fr, level_mask, g_pose, ctx.want_gx,
+                                         ctx.pshapes if ctx.need_p else None)
+        ctx.tape = None
+        pg = [None] * len(ctx.pshapes)
+        if grads is not None:
+            head = range(26, len(grads) - 2)
+            pg = [None if i in head else t for i, t in enumerate(grads)]
+        return (g_x, None, None, *pg)
 
 
 class DFNet(nn.Module):
@@ -126,8 +214,19 @@ class DFNet(nn.Module):
                                       "is not on the B200 hot path yet; call .eval() / freeze_bn_layer_train")
         if self._handle is None:
             self._handle = _DfnetHandle(self)
-        self._handle.refresh(self)
-        ft, fr, pose = self._handle.forward(x, return_feature, isSingleStream, return_pose, int(upsampleH), int(upsampleW))
+        params = self._load_order_params()
+        train = torch.is_grad_enabled() and (x.requires_grad or any(t.requires_grad for t in params))
+        self._handle.refresh(self, train=train)
+        if train:
+            levels = getattr(self, "grad_levels", None)
+            mask = sum(1 << l for l in (range(len(self.hypercolumn_layers)) if levels is None else levels))
+            cfg = (bool(return_feature), bool(isSingleStream), bool(return_pose), int(upsampleH), int(upsampleW), mask)
+            outs = list(_DfnetFn.apply(x, self._handle, cfg, *params))
+            ft = outs.pop(0) if return_feature else None
+            fr = outs.pop(0) if return_feature and not isSingleStream else None
+            pose = outs.pop(0) if return_pose else None
+        else:
+            ft, fr, pose = self._handle.forward(x, return_feature, isSingleStream, return_pose, int(upsampleH), int(upsampleW))
         if not return_feature:
             feature_maps = None
         elif isSingleStream:
@@ -137,9 +236,52 @@ class DFNet(nn.Module):
         return feature_maps, pose
 
 
+    def _load_order_params(self):
+        """Parameters in dfb_dfnet_load order (BatchNorm running statistics are passed as plain tensors)."""
+        ts = []
+        for m in self.encoder:
+            if isinstance(m, nn.Conv2d):
+                ts += [m.weight, m.bias]
+        for l in range(len(self.hypercolumn_layers)):
+            seq = getattr(self.adaptation_layers, f"adapt_layer_{l}")
+            ts += [seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias, seq[3].weight, seq[3].bias, seq[3].running_mean,
+                   seq[3].running_var]
+        return ts + [self.fc_pose.weight, self.fc_pose.bias]
+
+
+
 class DFNet_s(DFNet):
     """DFNet_s (reference feature/dfnet.py:174-273): only the conv1_2 hyper-column."""
     hypercolumn_layers = ["conv1_2"]
+
+
+class _CosineLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fr, ft, per_channel):
+        a, b = fr.detach().float().contiguous(), ft.detach().float().contiguous()
+        Cc = a.shape[0]
+        HW = a.numel() // Cc
+        loss = torch.empty((), device=a.device)
+        ws = torch.empty(max(Cc * 64 * 3, (HW + 255) // 256), device=a.device)
+        check(lib.dfb_cosine_loss(C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), Cc, HW, int(bool(per_channel)), 1e-6,
+                                  C.c_void_p(loss.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel() * 4,
+                                  C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        ctx.save_for_backward(a, b)
+        ctx.per_channel = bool(per_channel)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        Cc = a.shape[0]
+        HW = a.numel() // Cc
+        g = g.float().contiguous()
+        ga = torch.empty_like(a)
+        ws = torch.empty(Cc * 64 * 3, device=a.device)
+        check(lib.dfb_cosine_loss_bwd(C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), Cc, HW, int(ctx.per_channel), 1e-6,
+                                      C.c_void_p(g.data_ptr()), C.c_void_p(ga.data_ptr()), C.c_void_p(ws.data_ptr()),
+                                      ws.numel() * 4, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return ga, None, None  # the target stream is a constant of the step (its inputs carry no gradient)
 
 
 def feature_loss(feature_rgb, feature_target, img_in=True, per_channel=False):
@@ -148,6 +290,8 @@ def feature_loss(feature_rgb, feature_target, img_in=True, per_channel=False):
     inverted w.r.t. its behaviour); per_channel=True gives the per-pixel cosine."""
     if not feature_rgb.is_cuda:
         raise _lib.DfbError("feature_loss inputs must be CUDA tensors")
+    if torch.is_grad_enabled() and feature_rgb.requires_grad:
+        return _CosineLossFn.apply(feature_rgb, feature_target, per_channel)
     fr = feature_rgb.detach().float().contiguous()
     ft = feature_target.detach().float().contiguous()
     Cc = fr.shape[0]

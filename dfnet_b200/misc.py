@@ -32,10 +32,54 @@ def triplet_loss_hard_negative_mining_plus(f1, f2, margin=1.):
     return loss
 
 
+class _MseFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y):
+        a, b = x.detach().float().contiguous(), y.detach().float().contiguous()
+        out = torch.empty((), device=a.device)
+        ws = torch.empty(1024, device=a.device)
+        check(lib.dfb_mse(_p(a), _p(b), a.numel(), _p(out), _p(ws), ws.numel() * 4, _stream()))
+        ctx.save_for_backward(a, b)
+        ctx.shapes = (x.shape, y.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        ga = torch.empty_like(a)
+        g = g.float().contiguous()
+        check(lib.dfb_mse_bwd(_p(a), _p(b), a.numel(), _p(g), _p(ga), _stream()))
+        return (ga.view(ctx.shapes[0]) if ctx.needs_input_grad[0] else None,
+                (-ga).view(ctx.shapes[1]) if ctx.needs_input_grad[1] else None)
+
+
+class _ResizeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, size, kind):
+        a = x.detach().float().contiguous()
+        B, Cc, h, w = a.shape
+        out = torch.empty(B, Cc, size[0], size[1], device=a.device)
+        fwd = lib.dfb_resize_bicubic if kind == "bicubic" else lib.dfb_resize_bilinear_ac
+        check(fwd(_p(a), B * Cc, h, w, size[0], size[1], _p(out), _stream()))
+        ctx.kind, ctx.dims = kind, (B, Cc, h, w, size[0], size[1])
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, Cc, h, w, Ho, Wo = ctx.dims
+        g = g.float().contiguous()
+        gx = torch.empty(B, Cc, h, w, device=g.device)
+        bwd = lib.dfb_resize_bicubic_bwd if ctx.kind == "bicubic" else lib.dfb_resize_bilinear_ac_bwd
+        check(bwd(_p(g), B * Cc, h, w, Ho, Wo, _p(gx), _stream()))
+        return gx, None, None
+
+
 def mse(x, y):
     """nn.MSELoss()(x, y) / img2mse (reference models/nerfw.py:11)."""
     if not x.is_cuda:
         raise _lib.DfbError("mse inputs must be CUDA tensors")
+    if torch.is_grad_enabled() and (x.requires_grad or y.requires_grad):
+        return _MseFn.apply(x, y)
     a, b = x.detach().float().contiguous(), y.detach().float().contiguous()
     out = torch.empty((), device=a.device)
     ws = torch.empty(1024, device=a.device)
@@ -61,6 +105,8 @@ def upsample_bicubic(x, size):
     feature/direct_feature_matching.py:346): align_corners=False, output not clamped."""
     if not x.is_cuda:
         raise _lib.DfbError("upsample input must be a CUDA tensor")
+    if torch.is_grad_enabled() and x.requires_grad:
+        return _ResizeFn.apply(x, (int(size[0]), int(size[1])), "bicubic")
     a = x.detach().float().contiguous()
     B, Cc, h, w = a.shape
     out = torch.empty(B, Cc, size[0], size[1], device=a.device)
@@ -72,6 +118,8 @@ def upsample_bilinear_ac(x, size):
     """torch.nn.UpsamplingBilinear2d(size=size)(x) (align_corners=True; reference feature/dfnet.py:145)."""
     if not x.is_cuda:
         raise _lib.DfbError("upsample input must be a CUDA tensor")
+    if torch.is_grad_enabled() and x.requires_grad:
+        return _ResizeFn.apply(x, (int(size[0]), int(size[1])), "bilinear_ac")
     a = x.detach().float().contiguous()
     B, Cc, h, w = a.shape
     out = torch.empty(B, Cc, size[0], size[1], device=a.device)

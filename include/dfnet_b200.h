@@ -241,6 +241,55 @@ int dfb_debug_umma_rate(int iters, int n, int grid, double* cycles_per_mma);
 
 int dfb_debug_umma_gemm(const float* A, const float* B, int N, int K, int kind, int variant, float* D, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training step of the direct-feature-matching loop (row a15; reference
+ * feature/direct_feature_matching.py:322-390 `train_on_batch`, `loss.backward()` at :378).
+ * Gradients travel as NHWC bf16 with fp32 accumulation.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* dfb_conv_create with explicit operand format (fmt 0 fp16 / 1 bf16).  dgrad != 0 builds the DATA-GRADIENT convolution
+ * of the layer (Cin, Cout, weight [Cout,Cin,KH,KW], bn_scale): its input has Cout channels, its output round_up(Cin,64)
+ * (replaces the conv backward of torch autograd w.r.t. the input). */
+int dfb_conv_create_ex(int Cin, int Cout, int KH, int KW, const float* weight, const float* bias, const float* bn_scale,
+                       const float* bn_shift, int fmt, int dgrad, DfbConv** out);
+/* dfb_conv_fwd plus the backward epilogue: result zeroed where mask_nhwc16 <= 0 (ReLU'), then addend_nhwc16 added. */
+int dfb_conv_fwd_ex(DfbConv* c, const void* in_nhwc16, int B, int H, int W, int relu, void* out_nhwc16, void* tap_nhwc16,
+                    float* out_nchw32, const void* mask_nhwc16, const void* addend_nhwc16, void* stream);
+/* Weight (and optional bias) gradient of a KHxKH convolution, stride 1, pad KH/2 (torch autograd conv backward w.r.t.
+ * weight): gO NHWC [B,H,W,Cout], X NHWC [B,H,W,Cin_pad] 16-bit (fmt 0 f16 / 1 bf16) -> dW fp32 [Cout,Cin,KH,KH], dB [Cout]. */
+int dfb_conv_wgrad(const void* gO, const void* X, int B, int H, int W, int Cin, int Cin_pad, int Cout, int KH, int fmt,
+                   float* dW, float* dB, void* stream);
+
+/* dfb_dfnet_load, flags bit0: also build the training variants (bf16 encoder, data-gradient convolutions). */
+int dfb_dfnet_load_ex(DfbDfnet* d, const float* const* params, const int64_t* numel, int n_params, float bn_eps,
+                      uint32_t flags);
+/* Bytes of the tape a forward with flags bit3 writes (every activation kept) and of the backward scratch. */
+int dfb_dfnet_tape_bytes(const DfbDfnet* d, int B, int H, int W, int upH, int upW, size_t* out);
+int dfb_dfnet_bwd_workspace_bytes(const DfbDfnet* d, int B, int H, int W, size_t* out);
+/* Backward of dfb_dfnet_fwd (flags as in that call: bit0 return_feature, bit1 single_stream, bit2 return_pose, bit3 tape,
+ * bit4 bf16 encoder operands — required for parameter gradients).
+ *   g_feats_t / g_feats_r: gradients of the feature stacks [L,Bs,128,upH,upW]; a null stack skips that stream
+ *   level_mask: bit l set = level l carries gradient;  g_pose [B,12] (nullable)
+ *   g_x: gradient w.r.t. the images of the differentiated sub-batch, fp32 [nb,3,H,W] (nullable)
+ *   g_params: n_params pointers in dfb_dfnet_load order (nullable entries); encoder and fc_pose entries are written. */
+int dfb_dfnet_bwd(DfbDfnet* d, int B, int H, int W, uint32_t flags, int upH, int upW, const float* g_feats_t,
+                  const float* g_feats_r, uint32_t level_mask, const float* g_pose, const void* tape, float* g_x,
+                  float* const* g_params, int n_params, void* scratch, size_t scratch_bytes, void* stream);
+
+/* Backward of dfb_cosine_loss w.r.t. fr (g_loss: device scalar), of dfb_mse w.r.t. a, and the adjoints of the two
+ * resampling operators (outputs overwritten). */
+int dfb_cosine_loss_bwd(const float* fr, const float* ft, int C, int64_t HW, int per_channel, float eps, const float* g_loss,
+                        float* g_fr, void* ws, size_t ws_bytes, void* stream);
+int dfb_mse_bwd(const float* a, const float* b, int64_t n, const float* g_loss, float* g_a, void* stream);
+int dfb_resize_bicubic_bwd(const float* g_dst, int64_t planes, int h, int w, int Ho, int Wo, float* g_src, void* stream);
+int dfb_resize_bilinear_ac_bwd(const float* g_dst, int64_t planes, int h, int w, int Ho, int Wo, float* g_src, void* stream);
+
+/* Debug seam: one tcgen05 tile with MN-major operands, D[128,N] = sum_k A[k][m] * B[k][n] (A [K,128], B [K,N] fp32 on
+ * the device, rounded to fmt_a / fmt_b: 0 = f16, 1 = bf16).  Pins the descriptor convention the weight-gradient
+ * kernel relies on. */
+int dfb_debug_umma_gemm_mn(const float* A, const float* B, int N, int K, int fmt_a, int fmt_b, int variant, float* D,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,227 @@
+"""GPU parity of the training-step kernels (row a15: reference feature/direct_feature_matching.py:322-390).
+
+Checker: torch autograd in fp32/fp64 on the same tensors (a floating-point kernel family, so a torch reference is the
+oracle here), plus the golden gradients generated from the reference's own `train_on_batch` on the CPU
+(tests/golden/make_golden_train.py).  Tolerances: the gradient path is bf16 with fp32 accumulation (BASELINE config[3]
+names bf16 for the training loop), so tensor-core gradients are compared at 3e-2 of the tensor's max and a cosine
+similarity above 0.999; fp32 kernels (losses, resampling adjoints) at 1e-4.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import synthetic_dfnet
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def _ops():
+    from dfnet_b200 import ops
+    return ops
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def close_grad(got, want, tol=3e-2, cos_min=0.999):
+    got, want = got.double().flatten(), want.double().flatten()
+    scale = float(want.abs().max()) + 1e-30
+    err = float((got - want).abs().max()) / scale
+    cos = float(F.cosine_similarity(got, want, dim=0))
+    assert err < tol and cos > cos_min, (err, cos)
+    return err, cos
+
+
+@pytest.mark.parametrize("cin,cout,k,B,H,W", [(64, 128, 3, 2, 37, 45), (3, 64, 3, 1, 40, 56), (256, 512, 3, 1, 20, 24),
+                                               (128, 64, 3, 3, 16, 8), (64, 128, 5, 1, 33, 20), (256, 64, 1, 1, 24, 24)])
+def test_conv_wgrad_vs_torch(cin, cout, k, B, H, W):
+    ops = _ops()
+    torch.manual_seed(1)
+    cpad = (cin + 7) // 8 * 8
+    x = torch.randn(B, cin, H, W, device=dev()).bfloat16()
+    go = (torch.randn(B, cout, H, W, device=dev()) * 0.1).bfloat16()
+    x_nhwc = torch.zeros(B, H, W, cpad, device=dev(), dtype=torch.bfloat16)
+    x_nhwc[..., :cin] = x.permute(0, 2, 3, 1)
+    go_nhwc = go.permute(0, 2, 3, 1).contiguous()
+    dW = torch.full((cout, cin, k, k), 7.0, device=dev())
+    dB = torch.full((cout,), 7.0, device=dev())
+    ops.check(ops.lib.dfb_conv_wgrad(_p(go_nhwc), _p(x_nhwc), B, H, W, cin, cpad, cout, k, 1, _p(dW), _p(dB), None))
+    torch.cuda.synchronize()
+    want = torch.nn.grad.conv2d_weight(x.double(), (cout, cin, k, k), go.double(), padding=k // 2)
+    assert float((dW.double() - want).abs().max()) < 2e-4 * float(want.abs().max()) + 1e-5
+    wb = go.double().sum((0, 2, 3))
+    assert float((dB.double() - wb).abs().max()) < 1e-4 * float(wb.abs().max()) + 1e-5
+
+
+@pytest.mark.parametrize("cin,cout,k,B,H,W", [(64, 128, 3, 2, 37, 45), (3, 64, 3, 1, 40, 56), (512, 512, 3, 1, 20, 24),
+                                               (64, 128, 5, 1, 33, 20), (256, 64, 1, 1, 24, 24)])
+def test_conv_dgrad_vs_torch(cin, cout, k, B, H, W):
+    """Data-gradient convolution (transposed + flipped filter through the forward kernel) with the ReLU mask epilogue."""
+    ops = _ops()
+    torch.manual_seed(2)
+    w = torch.randn(cout, cin, k, k, device=dev()) * 0.05
+    sc = torch.rand(cout, device=dev()) + 0.5
+    go = (torch.randn(B, cout, H, W, device=dev()) * 0.1).bfloat16()
+    act = torch.relu(torch.randn(B, cin, H, W, device=dev())).half()
+    h = C.c_void_p()
+    ops.check(ops.lib.dfb_conv_create_ex(cin, cout, k, k, _p(w), None, _p(sc), None, 1, 1, C.byref(h)))
+    try:
+        go_nhwc = go.permute(0, 2, 3, 1).contiguous()
+        cpo = (cin + 63) // 64 * 64
+        want = torch.nn.grad.conv2d_input((B, cin, H, W), (w * sc.view(-1, 1, 1, 1)).bfloat16().double(), go.double(), padding=k // 2)
+        if cin >= 64:
+            mask = act.permute(0, 2, 3, 1).contiguous()
+            out = torch.empty(B, H, W, cpo, device=dev(), dtype=torch.bfloat16)
+            ops.check(ops.lib.dfb_conv_fwd_ex(h, _p(go_nhwc), B, H, W, 0, _p(out), None, None, _p(mask), None, None))
+            torch.cuda.synchronize()
+            want = want * (act > 0)
+            got = out.permute(0, 3, 1, 2).double()
+            assert float((got - want).abs().max()) < 1e-2 * float(want.abs().max())
+        else:  # conv1_1: fp32 NCHW image gradient, 3 real channels
+            out = torch.empty(B, cin, H, W, device=dev())
+            ops.check(ops.lib.dfb_conv_fwd_ex(h, _p(go_nhwc), B, H, W, 0, None, None, _p(out), None, None, None))
+            torch.cuda.synchronize()
+            assert float((out.double() - want).abs().max()) < 2e-4 * float(want.abs().max())
+    finally:
+        ops.lib.dfb_conv_destroy(h)
+
+
+def test_loss_and_resample_backward_vs_torch():
+    from dfnet_b200 import dfnet as D, misc
+    torch.manual_seed(3)
+    # cosine feature loss (per_channel=False: cosine over the pixels of each channel)
+    fr = torch.randn(128, 60 * 80, device=dev(), requires_grad=True)
+    ft = torch.randn(128, 60 * 80, device=dev())
+    D.feature_loss(fr, ft).backward()
+    fr2 = fr.detach().clone().requires_grad_(True)
+    (1 - torch.nn.CosineSimilarity(dim=1, eps=1e-6)(fr2, ft).mean()).backward()
+    assert float((fr.grad - fr2.grad).abs().max()) < 1e-4 * float(fr2.grad.abs().max())
+    # MSE
+    a = torch.rand(1, 3, 48, 64, device=dev(), requires_grad=True)
+    b = torch.rand(1, 3, 48, 64, device=dev())
+    (misc.img2mse(a, b) * 3.0).backward()
+    a2 = a.detach().clone().requires_grad_(True)
+    (F.mse_loss(a2, b) * 3.0).backward()
+    assert float((a.grad - a2.grad).abs().max()) < 1e-5 * float(a2.grad.abs().max())
+    # bicubic x4 (train_on_batch half_res) and bilinear align_corners
+    for fn, ref in ((misc.upsample_bicubic, lambda t, s: F.interpolate(t, size=s, mode="bicubic", align_corners=False)),
+                    (misc.upsample_bilinear_ac, lambda t, s: F.interpolate(t, size=s, mode="bilinear", align_corners=True))):
+        x = torch.rand(1, 3, 15, 20, device=dev(), requires_grad=True)
+        w = torch.randn(1, 3, 60, 83, device=dev())
+        (fn(x, (60, 83)) * w).sum().backward()
+        x2 = x.detach().clone().requires_grad_(True)
+        (ref(x2, (60, 83)) * w).sum().backward()
+        assert float((x.grad - x2.grad).abs().max()) < 1e-4 * float(x2.grad.abs().max())
+
+
+def torch_dfnet_forward(net, x, return_feature, single, return_pose, upH, upW):
+    """torch restatement of reference feature/dfnet.py:106-172 on the mirror's own nn layers (eval BatchNorm)."""
+    mean = torch.tensor(net.mean, device=x.device).view(1, 3, 1, 1)
+    std = torch.tensor(net.std, device=x.device).view(1, 3, 1, 1)
+    h = (x - mean) / std
+    taps = {2: 0, 14: 1, 28: 2}
+    feats = []
+    for i, m in enumerate(net.encoder):
+        if isinstance(m, torch.nn.ReLU):
+            h = F.relu(h)
+        else:
+            h = m(h)
+        if i in taps and taps[i] < len(net.hypercolumn_layers):
+            feats.append(h)
+    pose = net.fc_pose(h.mean((2, 3))) if return_pose else None
+    if not return_feature:
+        return None, pose
+    outs = []
+    for l, f in enumerate(feats):
+        a = getattr(net.adaptation_layers, f"adapt_layer_{l}")(f)
+        outs.append(F.interpolate(a, size=(upH, upW), mode="bilinear", align_corners=True))
+    st = torch.stack(outs)
+    if single:
+        return [st], pose
+    B = x.shape[0] // 2
+    return [st[:, :B], st[:, B:]], pose
+
+
+def _randomise_bn(net, seed):
+    g = torch.Generator().manual_seed(seed)
+    for l in range(len(net.hypercolumn_layers)):
+        bn = getattr(net.adaptation_layers, f"adapt_layer_{l}")[3]
+        bn.running_mean.copy_(torch.randn(128, generator=g) * 0.1)
+        bn.running_var.copy_(torch.rand(128, generator=g) + 0.5)
+        bn.weight.data.copy_(torch.rand(128, generator=g) + 0.5)
+        bn.bias.data.copy_(torch.randn(128, generator=g) * 0.1)
+
+
+@pytest.mark.parametrize("cls,levels,H,W", [("DFNet", [0, 1, 2], 64, 96), ("DFNet", [0], 48, 80), ("DFNet_s", [0], 50, 70),
+                                             ("DFNet", [1, 2], 64, 64)])
+def test_feature_loss_gradient_wrt_rendered_image(cls, levels, H, W):
+    """d feature_loss / d rgb through the frozen feature net (siamese forward on cat([data, rgb]), only the rendered
+    stream differentiated): the gradient train_on_batch sends back into the renderer."""
+    from dfnet_b200 import dfnet as D
+    net = synthetic_dfnet(cls, seed=4).to(dev()).eval()
+    _randomise_bn(net, 5)
+    for p in net.parameters():
+        p.requires_grad_(False)
+    net.grad_levels = levels
+    torch.manual_seed(6)
+    data = torch.rand(1, 3, H, W, device=dev())
+    rgb0 = (data + 0.1 * torch.randn_like(data)).clamp(0, 1)
+
+    def loss_of(fwd, rgb):
+        feats, _ = fwd(torch.cat([data, rgb]))
+        idx = torch.tensor(levels, device=dev())
+        fr = D.preprocess_features_for_loss(torch.index_select(feats[1], 0, idx))
+        ft = D.preprocess_features_for_loss(torch.index_select(feats[0], 0, idx))
+        return fr, ft
+
+    rgb = rgb0.clone().requires_grad_(True)
+    fr, ft = loss_of(lambda x: net(x, return_feature=True, isSingleStream=False, return_pose=False, upsampleH=H, upsampleW=W), rgb)
+    loss = D.feature_loss(fr[0], ft[0])
+    loss.backward()
+    rgb_t = rgb0.clone().requires_grad_(True)
+    fr_t, ft_t = loss_of(lambda x: torch_dfnet_forward(net, x, True, False, False, H, W), rgb_t)
+    loss_t = 1 - torch.nn.CosineSimilarity(dim=1, eps=1e-6)(fr_t[0].reshape(fr_t.shape[1], -1), ft_t[0].reshape(ft_t.shape[1], -1)).mean()
+    loss_t.backward()
+    assert abs(float(loss) - float(loss_t)) < 2e-3 * abs(float(loss_t)) + 1e-5
+    print("feature-loss grad err/cos:", close_grad(rgb.grad, rgb_t.grad, tol=5e-2, cos_min=0.998))
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 64, 96), (2, 60, 80)])
+def test_pose_regressor_parameter_gradients(B, H, W):
+    """d PoseLoss / d (encoder, fc_pose parameters) of the pose regressor: weight, bias and data-gradient kernels
+    chained through all 13 convolutions and 5 poolings."""
+    from dfnet_b200 import misc
+    net = synthetic_dfnet("DFNet", seed=7).to(dev())
+    net.train()
+    for m in net.modules():  # freeze_bn_layer_train (reference feature/direct_feature_matching.py:52-61)
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.eval()
+            m.weight.requires_grad_(False), m.bias.requires_grad_(False)
+    torch.manual_seed(8)
+    x = torch.rand(B, 3, H, W, device=dev())
+    target = torch.randn(B, 12, device=dev())
+    _, pose = net(x, return_feature=False, isSingleStream=True, return_pose=True, upsampleH=H, upsampleW=W)
+    misc.mse(pose, target).backward()
+    got = {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
+    net.zero_grad()
+    _, pose_t = torch_dfnet_forward(net, x, False, True, True, H, W)
+    F.mse_loss(pose_t, target).backward()
+    assert float((pose - pose_t).abs().max()) < 2e-2 * float(pose_t.abs().max())
+    names = [n for n, p in net.named_parameters() if p.grad is not None]
+    assert set(names) == set(got), (set(names) ^ set(got))
+    worst = (0.0, 1.0, "")
+    for n, p in net.named_parameters():
+        if p.grad is None:
+            continue
+        err, cos = close_grad(got[n], p.grad, tol=8e-2, cos_min=0.995)
+        if err > worst[0]:
+            worst = (err, cos, n)
+    print("pose-regressor parameter gradients, worst (err, cos, name):", worst)
