@@ -366,6 +366,21 @@ extern "C" int dfb_dfnet_workspace_bytes(const DfbDfnet* d, int B, int H, int W,
   return DFB_OK;
 }
 
+// Debug seam: byte offsets inside the tape, so that tests can read the stored activations back.
+// out[0] = in8; then for every encoder conv i: out[1+4i..] = {act offset, pool offset or -1, h, w}; then tap[3], mid[3], pooled.
+extern "C" int dfb_debug_dfnet_tape_layout(const DfbDfnet* d, int B, int H, int W, int upH, int upW, int64_t* out) {
+  DFB_REQUIRE(d && out && B >= 1 && H >= 32 && W >= 32, DFB_ERR_INVALID, "bad arguments");
+  const DfWs L = dfnet_ws(B, H, W, d->n_levels, upH, upW, true);
+  out[0] = (int64_t)L.in8;
+  for (int i = 0; i < 13; ++i) {
+    out[1 + 4 * i] = (int64_t)L.act[i], out[2 + 4 * i] = kPoolAfter[i] ? (int64_t)L.pool[i] : -1;
+    out[3 + 4 * i] = L.h[i], out[4 + 4 * i] = L.w[i];
+  }
+  for (int l = 0; l < 3; ++l) out[53 + l] = (int64_t)L.tap[l], out[56 + l] = (int64_t)L.mid[l];
+  out[59] = (int64_t)L.pooled;
+  return DFB_OK;
+}
+
 extern "C" int dfb_dfnet_tape_bytes(const DfbDfnet* d, int B, int H, int W, int upH, int upW, size_t* out) {
   DFB_REQUIRE(d && out && B >= 1 && H >= 32 && W >= 32, DFB_ERR_INVALID, "bad arguments (image must be at least 32x32)");
   *out = dfnet_ws(B, H, W, d->n_levels, upH, upW, true).total;

@@ -106,8 +106,29 @@ class _DfnetHandle:
         check(lib.dfb_dfnet_fwd(self._h, p(x), B, H, W, flags, upH, upW, p(ft), p(fr), p(pose), p(ws),
                                 ws.numel(), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         if tape:
+            self.last_tape = (ws, flags, (B, H, W, upH, upW))  # debug: tests read the stored activations back
             return ft, fr, pose, (ws, flags)
         return ft, fr, pose
+
+    def tape_activations(self):
+        """Debug: the stored activations of the last taped forward as NCHW fp32 tensors
+        {'in', 'act{i}', 'tap{l}', 'mid{l}'} (dfb_debug_dfnet_tape_layout)."""
+        ws, flags, (B, H, W, upH, upW) = self.last_tape
+        out = (C.c_int64 * 60)()
+        check(lib.dfb_debug_dfnet_tape_layout(self._h, B, H, W, upH, upW, out))
+        dt = torch.bfloat16 if flags & 16 else torch.float16
+        cout = [64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512, 512]
+
+        def view(off, h, w, c, dtype):
+            n = B * h * w * c * 2
+            return ws[off:off + n].view(dtype).view(B, h, w, c).permute(0, 3, 1, 2).float()
+        acts = {"in": view(out[0], H, W, 8, dt)[:, :3]}
+        for i in range(13):
+            acts[f"act{i}"] = view(out[1 + 4 * i], out[3 + 4 * i], out[4 + 4 * i], cout[i], dt)
+        for l, (ci, c) in enumerate(((1, 64), (6, 256), (12, 512))[: self.n_levels]):
+            acts[f"tap{l}"] = view(out[53 + l], out[3 + 4 * ci], out[4 + 4 * ci], c, torch.float16)
+            acts[f"mid{l}"] = view(out[56 + l], out[3 + 4 * ci], out[4 + 4 * ci], 64, torch.float16)
+        return acts
 
     def backward(self, tape, shape, upH, upW, g_ft, g_fr, level_mask, g_pose, want_gx, param_shapes):
         """dfb_dfnet_bwd.  Returns (g_x [B,3,H,W] or None, list of parameter gradients in load order or None)."""

@@ -265,6 +265,8 @@ int dfb_dfnet_load_ex(DfbDfnet* d, const float* const* params, const int64_t* nu
                       uint32_t flags);
 /* Bytes of the tape a forward with flags bit3 writes (every activation kept) and of the backward scratch. */
 int dfb_dfnet_tape_bytes(const DfbDfnet* d, int B, int H, int W, int upH, int upW, size_t* out);
+/* Debug seam: byte offsets inside the tape (out[60]): in8; per encoder conv {act, pool or -1, h, w}; tap[3]; mid[3]; pooled. */
+int dfb_debug_dfnet_tape_layout(const DfbDfnet* d, int B, int H, int W, int upH, int upW, int64_t* out);
 int dfb_dfnet_bwd_workspace_bytes(const DfbDfnet* d, int B, int H, int W, size_t* out);
 /* Backward of dfb_dfnet_fwd (flags as in that call: bit0 return_feature, bit1 single_stream, bit2 return_pose, bit3 tape,
  * bit4 bf16 encoder operands — required for parameter gradients).

@@ -16,6 +16,8 @@ import torch.nn.functional as F
 from helpers import synthetic_dfnet
 
 pytestmark = pytest.mark.gpu
+torch.backends.cudnn.allow_tf32 = False  # the checker runs in true fp32
+torch.backends.cuda.matmul.allow_tf32 = False
 
 
 def dev():
@@ -122,16 +124,34 @@ def test_loss_and_resample_backward_vs_torch():
         assert float((x.grad - x2.grad).abs().max()) < 1e-4 * float(x2.grad.abs().max())
 
 
-def torch_dfnet_forward(net, x, return_feature, single, return_pose, upH, upW):
-    """torch restatement of reference feature/dfnet.py:106-172 on the mirror's own nn layers (eval BatchNorm)."""
+def _ste(t, dt):
+    """Round to the kernel's storage type in the forward, identity in the backward."""
+    return t if dt is None else t + (t.to(dt).float() - t).detach()
+
+
+def _pin(t, acts, key):
+    """Substitute the value the GPU forward stored (identity in the backward): the torch graph is then differentiated at
+    exactly the kernels' forward state (same ReLU masks, same max-pool arg-maxima)."""
+    return t if acts is None or key not in acts else t + (acts[key] - t).detach()
+
+
+def torch_dfnet_forward(net, x, return_feature, single, return_pose, upH, upW, quant=None, acts=None):
+    """torch restatement of reference feature/dfnet.py:106-172 on the mirror's own nn layers (eval BatchNorm).
+    quant=torch.float16 / torch.bfloat16 additionally rounds weights and stored activations exactly where the kernels
+    do (straight-through), so that ReLU masks and max-pool arg-maxima are those of the function the GPU path actually
+    evaluates; quant=None is the plain fp32 reference."""
     mean = torch.tensor(net.mean, device=x.device).view(1, 3, 1, 1)
     std = torch.tensor(net.std, device=x.device).view(1, 3, 1, 1)
-    h = (x - mean) / std
+    h = _pin(_ste((x - mean) / std, quant), acts, "in")
     taps = {2: 0, 14: 1, 28: 2}
     feats = []
+    ci = 0
     for i, m in enumerate(net.encoder):
         if isinstance(m, torch.nn.ReLU):
-            h = F.relu(h)
+            h = _pin(_ste(F.relu(h), quant), acts, f"act{ci}")
+            ci += 1
+        elif isinstance(m, torch.nn.Conv2d):
+            h = F.conv2d(h, _ste(m.weight, quant), m.bias, padding=1)
         else:
             h = m(h)
         if i in taps and taps[i] < len(net.hypercolumn_layers):
@@ -141,7 +161,10 @@ def torch_dfnet_forward(net, x, return_feature, single, return_pose, upH, upW):
         return None, pose
     outs = []
     for l, f in enumerate(feats):
-        a = getattr(net.adaptation_layers, f"adapt_layer_{l}")(f)
+        seq = getattr(net.adaptation_layers, f"adapt_layer_{l}")
+        a = F.conv2d(_pin(_ste(f, quant), acts, f"tap{l}"), _ste(seq[0].weight, quant), seq[0].bias)
+        a = _pin(_ste(F.relu(a), quant), acts, f"mid{l}")
+        a = seq[3](F.conv2d(a, _ste(seq[2].weight, quant), seq[2].bias, padding=2))
         outs.append(F.interpolate(a, size=(upH, upW), mode="bilinear", align_corners=True))
     st = torch.stack(outs)
     if single:
@@ -186,12 +209,18 @@ def test_feature_loss_gradient_wrt_rendered_image(cls, levels, H, W):
     fr, ft = loss_of(lambda x: net(x, return_feature=True, isSingleStream=False, return_pose=False, upsampleH=H, upsampleW=W), rgb)
     loss = D.feature_loss(fr[0], ft[0])
     loss.backward()
-    rgb_t = rgb0.clone().requires_grad_(True)
-    fr_t, ft_t = loss_of(lambda x: torch_dfnet_forward(net, x, True, False, False, H, W), rgb_t)
-    loss_t = 1 - torch.nn.CosineSimilarity(dim=1, eps=1e-6)(fr_t[0].reshape(fr_t.shape[1], -1), ft_t[0].reshape(ft_t.shape[1], -1)).mean()
-    loss_t.backward()
-    assert abs(float(loss) - float(loss_t)) < 2e-3 * abs(float(loss_t)) + 1e-5
-    print("feature-loss grad err/cos:", close_grad(rgb.grad, rgb_t.grad, tol=5e-2, cos_min=0.998))
+    # (a) differentiated at the kernels' own forward state (stored activations pinned): tight, this is the kernel check;
+    # (b) fp16-rounded and (c) plain fp32 torch forwards: ReLU-mask / arg-max flips of the independently rounded
+    #     forwards accumulate with depth, so these are sanity bounds on the end-to-end gradient
+    acts = net._handle.tape_activations()
+    for quant, pin, tol, cos_min in ((torch.float16, acts, 3e-2, 0.9998), (torch.float16, None, 0.5, 0.995), (None, None, 0.5, 0.99)):
+        rgb_t = rgb0.clone().requires_grad_(True)
+        fr_t, ft_t = loss_of(lambda x: torch_dfnet_forward(net, x, True, False, False, H, W, quant, pin), rgb_t)
+        loss_t = 1 - torch.nn.CosineSimilarity(dim=1, eps=1e-6)(fr_t[0].reshape(fr_t.shape[1], -1),
+                                                                ft_t[0].reshape(ft_t.shape[1], -1)).mean()
+        loss_t.backward()
+        assert abs(float(loss.detach()) - float(loss_t.detach())) < 2e-3 * abs(float(loss_t.detach())) + 1e-5
+        print("feature-loss grad err/cos vs", quant, "pinned" if pin else "free", close_grad(rgb.grad, rgb_t.grad, tol=tol, cos_min=cos_min))
 
 
 @pytest.mark.parametrize("B,H,W", [(1, 64, 96), (2, 60, 80)])
@@ -211,17 +240,21 @@ def test_pose_regressor_parameter_gradients(B, H, W):
     _, pose = net(x, return_feature=False, isSingleStream=True, return_pose=True, upsampleH=H, upsampleW=W)
     misc.mse(pose, target).backward()
     got = {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
-    net.zero_grad()
-    _, pose_t = torch_dfnet_forward(net, x, False, True, True, H, W)
-    F.mse_loss(pose_t, target).backward()
-    assert float((pose - pose_t).abs().max()) < 2e-2 * float(pose_t.abs().max())
-    names = [n for n, p in net.named_parameters() if p.grad is not None]
-    assert set(names) == set(got), (set(names) ^ set(got))
-    worst = (0.0, 1.0, "")
-    for n, p in net.named_parameters():
-        if p.grad is None:
-            continue
-        err, cos = close_grad(got[n], p.grad, tol=8e-2, cos_min=0.995)
-        if err > worst[0]:
-            worst = (err, cos, n)
-    print("pose-regressor parameter gradients, worst (err, cos, name):", worst)
+    # (a) differentiated at the kernels' own forward state (stored bf16 activations pinned): tight, the kernel check;
+    # (b) plain fp32: arg-max / mask flips of the bf16 forward accumulate with depth, so only a sanity bound
+    acts = net._handle.tape_activations()
+    for quant, pin, tol, cos_min in ((torch.bfloat16, acts, 5e-2, 0.9995), (None, None, 1.0, 0.85)):
+        net.zero_grad()
+        _, pose_t = torch_dfnet_forward(net, x, False, True, True, H, W, quant, pin)
+        F.mse_loss(pose_t, target).backward()
+        assert float((pose - pose_t).abs().max()) < 2e-2 * float(pose_t.abs().max())
+        names = [n for n, p in net.named_parameters() if p.grad is not None]
+        assert set(names) == set(got), (set(names) ^ set(got))
+        worst = (0.0, 1.0, "")
+        for n, p in net.named_parameters():
+            if p.grad is None:
+                continue
+            err, cos = close_grad(got[n], p.grad, tol=tol, cos_min=cos_min)
+            if 1 - cos > 1 - worst[1]:
+                worst = (err, cos, n)
+        print("pose-regressor parameter gradients vs", quant, "worst (err, cos, name):", worst)
