@@ -114,6 +114,21 @@ __global__ void k_maxpool2x2_bwd(const uint16_t* __restrict__ act, const uint16_
   }
 }
 
+// fp16 -> bf16 copy of an activation (the weight-gradient MMA needs both operands in one format)
+__global__ void k_f16_to_bf16(const uint4* __restrict__ in, uint4* __restrict__ out, int64_t n16) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n16) return;
+  const uint4 v = in[i];
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
+    o[q] = tc::pack2<__nv_bfloat16>(f.x, f.y);
+  }
+  out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 // AdaptiveAvgPool2d(1) backward: g[b,p,c] = g_pooled[b,c] / HW, bf16 NHWC
 __global__ void k_avgpool_bwd(const float* __restrict__ g_pooled, uint16_t* __restrict__ out, int HW, int C, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -157,7 +172,7 @@ __global__ void k_unnorm_grad(float* __restrict__ g, int64_t plane, int64_t n) {
 using namespace dfb;
 
 namespace {
-struct BwdWs { size_t gA, gB, gC, gtap[3], gmid, g16, fstage, gpooled, total; };
+struct BwdWs { size_t gA, gB, gC, gtap[3], gmid, g16, fstage, gpooled, xcvt, total; };
 
 BwdWs bwd_ws(int nb, int H, int W) {
   BwdWs w = {};
@@ -172,6 +187,7 @@ BwdWs bwd_ws(int nb, int H, int W) {
   w.g16 = take(px * 128 * 2);
   w.fstage = take(px * 128 * 4);  // level 0 is resampled too when upsampleH/W differ from the input size
   w.gpooled = take((size_t)nb * 512 * 4 + 256);
+  w.xcvt = take(px * 64 * 2);
   w.total = off;
   return w;
 }
@@ -188,7 +204,7 @@ extern "C" int dfb_dfnet_bwd_workspace_bytes(const DfbDfnet* d, int B, int H, in
 //   skipped entirely — train_on_batch only differentiates the rendered stream); level_mask bit l = level l carries gradient.
 // g_pose [B,12] (nullable).  g_x [nb,3,H,W] fp32 (nullable): gradient w.r.t. the images of the differentiated sub-batch
 //   (both streams: all B; one stream: its B/2 images).  g_params: n_params pointers in dfb_dfnet_load order (nullable
-//   entries); only the encoder and fc_pose entries are written (weight gradients need the bf16 tape).
+//   entries); only the encoder and fc_pose entries are written.
 extern "C" int dfb_dfnet_bwd(DfbDfnet* d, int B, int H, int W, uint32_t flags, int upH, int upW, const float* g_feats_t,
                              const float* g_feats_r, uint32_t level_mask, const float* g_pose, const void* tape, float* g_x,
                              float* const* g_params, int n_params, void* scratch, size_t scratch_bytes, void* stream) {
@@ -199,7 +215,7 @@ extern "C" int dfb_dfnet_bwd(DfbDfnet* d, int B, int H, int W, uint32_t flags, i
   DFB_REQUIRE(feat_grad || pose_grad, DFB_ERR_INVALID, "no gradient given");
   DFB_REQUIRE(!(feat_grad && pose_grad), DFB_ERR_UNSUPPORTED, "feature and pose gradients in one call are not supported");
   DFB_REQUIRE(d->enc_dg[0], DFB_ERR_INVALID, "training variants not loaded (dfb_dfnet_load_ex flags bit0)");
-  DFB_REQUIRE(!g_params || (bf && pose_grad), DFB_ERR_UNSUPPORTED, "weight gradients are implemented for the pose path on a bf16 tape");
+  DFB_REQUIRE(!g_params || pose_grad, DFB_ERR_UNSUPPORTED, "weight gradients are implemented for the pose path");
   DFB_REQUIRE(!g_params || n_params == 26 + 8 * d->n_levels + 2, DFB_ERR_INVALID, "g_params has the wrong length");
   cudaStream_t st = (cudaStream_t)stream;
   const DfWs L = dfnet_ws(B, H, W, d->n_levels, upH, upW, true);
@@ -293,6 +309,12 @@ extern "C" int dfb_dfnet_bwd(DfbDfnet* d, int B, int H, int W, uint32_t flags, i
     if (g_params && (g_params[2 * i] || g_params[2 * i + 1])) {
       DFB_REQUIRE(g_params[2 * i], DFB_ERR_INVALID, "bias gradient without weight gradient");
       const void* X = i == 0 ? tp + L.in8 : (kPoolAfter[i - 1] ? tp + L.pool[i - 1] : tp + L.act[i - 1]);
+      if (!bf) {  // fp16 tape: the gradient is bf16, so hand the MMA a bf16 copy of the layer input
+        const int64_t n16 = (int64_t)B * h * w * (i == 0 ? 8 : kEncCin[i]) / 8;
+        k_f16_to_bf16<<<(unsigned)((n16 + 255) / 256), 256, 0, st>>>((const uint4*)X, (uint4*)(sc + S.xcvt), n16);
+        DFB_LAUNCH_CHECK();
+        X = sc + S.xcvt;
+      }
       int rc = dfb_conv_wgrad(cur, X, B, h, w, kEncCin[i], i == 0 ? 8 : kEncCin[i], kEncCout[i], 3, 1, g_params[2 * i],
                               g_params[2 * i + 1], stream);
       if (rc) return rc;

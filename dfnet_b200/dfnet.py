@@ -173,12 +173,12 @@ class _DfnetFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, handle, cfg, *params):
-        return_feature, single, return_pose, upH, upW, level_mask = cfg
+        return_feature, single, return_pose, upH, upW, level_mask, _bf16 = cfg
         need_p = any(t.requires_grad for t in params)
         if need_p and return_feature:
             raise NotImplementedError("parameter gradients cover the pose path (train.py); training the adaptation heads "
                                       "(run_feature.py) is not on the B200 path yet")
-        ft, fr, pose, tape = handle.forward(x, return_feature, single, return_pose, upH, upW, tape=True, bf16=need_p)
+        ft, fr, pose, tape = handle.forward(x, return_feature, single, return_pose, upH, upW, tape=True, bf16=bool(cfg[6]))
         ctx.handle, ctx.tape, ctx.cfg, ctx.need_p = handle, tape, cfg, need_p
         ctx.xshape = (x.shape[0], x.shape[2], x.shape[3])
         ctx.pshapes = [t.shape for t in params]
@@ -192,7 +192,7 @@ class _DfnetFn(torch.autograd.Function):
     def backward(ctx, *gs):
         g = dict(zip(ctx.slots, gs))
         g_ft, g_fr, g_pose = (None if g.get(k) is None else g[k].float().contiguous() for k in ("ft", "fr", "pose"))
-        return_feature, single, return_pose, upH, upW, level_mask = ctx.cfg
+        return_feature, single, return_pose, upH, upW, level_mask, _bf16 = ctx.cfg
         n_out = 3 + len(ctx.pshapes)
         if g_ft is None and g_fr is None and g_pose is None:
             return (None,) * n_out
@@ -241,7 +241,10 @@ class DFNet(nn.Module):
         if train:
             levels = getattr(self, "grad_levels", None)
             mask = sum(1 << l for l in (range(len(self.hypercolumn_layers)) if levels is None else levels))
-            cfg = (bool(return_feature), bool(isSingleStream), bool(return_pose), int(upsampleH), int(upsampleW), mask)
+            # train_dtype: "f16" (default: the inference kernels' fp16 forward, bf16 gradients) or "bf16" (BASELINE config[3]:
+            # bf16 storage in the pose regressor's forward as well)
+            bf16 = getattr(self, "train_dtype", "f16") == "bf16" and not return_feature
+            cfg = (bool(return_feature), bool(isSingleStream), bool(return_pose), int(upsampleH), int(upsampleW), mask, bf16)
             outs = list(_DfnetFn.apply(x, self._handle, cfg, *params))
             ft = outs.pop(0) if return_feature else None
             fr = outs.pop(0) if return_feature and not isSingleStream else None

@@ -47,3 +47,22 @@ def render_images_sharded(render_one, poses, rank=None, world=None, gather=True)
     out = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(out, pad)
     return torch.cat([out[r][: b - a] for r, (a, b) in enumerate(counts)], 0)
+
+
+def allreduce_gradients_(params, group=None):
+    """Data-parallel training step: average the gradients of `params` over the ranks with ONE
+    all-reduce of a flat fp32 bucket (the pose regressor's 15.4 M parameters = 61.6 MB; NeRF and feature net are
+    frozen).  In place; parameters without gradient are skipped identically on every rank."""
+    import torch.distributed as dist
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return 0
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat /= dist.get_world_size(group)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+    return flat.numel()

@@ -269,7 +269,7 @@ int dfb_dfnet_tape_bytes(const DfbDfnet* d, int B, int H, int W, int upH, int up
 int dfb_debug_dfnet_tape_layout(const DfbDfnet* d, int B, int H, int W, int upH, int upW, int64_t* out);
 int dfb_dfnet_bwd_workspace_bytes(const DfbDfnet* d, int B, int H, int W, size_t* out);
 /* Backward of dfb_dfnet_fwd (flags as in that call: bit0 return_feature, bit1 single_stream, bit2 return_pose, bit3 tape,
- * bit4 bf16 encoder operands — required for parameter gradients).
+ * bit4 bf16 encoder operands).
  *   g_feats_t / g_feats_r: gradients of the feature stacks [L,Bs,128,upH,upW]; a null stack skips that stream
  *   level_mask: bit l set = level l carries gradient;  g_pose [B,12] (nullable)
  *   g_x: gradient w.r.t. the images of the differentiated sub-batch, fp32 [nb,3,H,W] (nullable)

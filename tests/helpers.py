@@ -62,3 +62,30 @@ def synthetic_dfnet(cls_name="DFNet", seed=0):
     net.fc_pose = torch.nn.Linear(512, 12)
     torch.set_rng_state(state)
     return net.eval()
+
+
+def pose_head_init_(net):
+    """Deterministic fc_pose so that a randomly initialised pose regressor predicts a camera that looks at the
+    synthetic scene: small weights, bias = a slightly non-orthogonal [R | t] (svd_reg has something to fix)."""
+    g = torch.Generator().manual_seed(123)
+    with torch.no_grad():
+        net.fc_pose.weight.copy_(torch.randn(12, 512, generator=g) * 2e-3)
+        net.fc_pose.bias.copy_(torch.tensor([0.98, 0.02, 0.15, 0.2, -0.03, 1.01, 0.04, -0.1, -0.16, -0.02, 0.97, 1.9]))
+    return net
+
+
+def train_case(case):
+    """Inputs of the train_on_batch golden cases (shared by tests/golden/make_golden_train.py and the GPU test)."""
+    import types
+    rng = np.random.RandomState(21)
+    H, W = 64, 96
+    args = types.SimpleNamespace(
+        DFNet=True, preprocess_ImgNet=False, svd_reg=True, combine_loss=True, per_channel=False, chunk=32768, batch_size=1,
+        combine_loss_w=[0.3, 0.2, 1.0] if case == "lvl012" else [0.0, 0.0, 1.0],
+        feature_matching_lvl=[0, 1, 2] if case == "lvl012" else [0])
+    data = torch.from_numpy(rng.rand(1, 3, H, W).astype(np.float32))
+    pose = torch.from_numpy(np.array([[1, 0, 0, 0.1, 0, 1, 0, -0.05, 0, 0, 1, 2.0]], np.float32))
+    hist = torch.from_numpy(np.array([[5, 10, 20, 30, 15, 10, 5, 3, 1, 1]], np.float32))
+    world = dict(pose_scale=0.5, pose_scale2=1.0, move_all_cam_vec=[0.0, 0.0, 0.05])
+    return dict(args=args, data=data, pose=pose, hist=hist, hwf=(H, W, 80.0), world=world, D=8, W=64, Nc=16, Nf=24,
+                near=0.0, far=2.5)

@@ -66,3 +66,38 @@ def test_sharded_render_gloo_world2(n_img):
     want = torch.stack([torch.full((2, 3, 3), 12.0 * i + i) for i in range(n_img)])
     for _, _, out in res:
         assert torch.equal(out, want)                 # gathered in image order on every rank
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dfnet_b200.parallel import allreduce_gradients_
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3), torch.nn.Linear(5, 2))
+    net[1].bias.requires_grad_(False)  # a frozen parameter is skipped on every rank alike
+    for i, p in enumerate(net.parameters()):
+        if p.requires_grad:
+            p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    n = allreduce_gradients_(net.parameters())
+    q.put((rank, n, [None if p.grad is None else p.grad.clone() for p in net.parameters()]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_gloo_world2():
+    """train_on_batch data-parallel: one flat all-reduce averages the pose regressor's gradients."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_grad_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=120) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+    assert all(p.exitcode == 0 for p in ps)
+    for rank, n, grads in res:
+        assert n == 4 * 3 * 9 + 4 + 2 * 5
+        assert grads[3] is None
+        for i, g in enumerate(grads[:3]):
+            assert torch.allclose(g, torch.full_like(g, 1.5 * (i + 1)))  # mean of (1, 2) * (i + 1)
