@@ -351,7 +351,22 @@ extern "C" int dfb_profile_read(double* coarse_ms, double* fine_ms, int64_t* coa
 namespace dfb {
 int launch_render_bwd(const DfbNerf* nerf, const float* rayrec, const float* z, const float* raybias, const float* raw,
                       const float* g_rgb, int64_t n_rays, int S, float* g_raw, float* g_samp, float* g_o, float* g_d,
-                      float* g_vd, cudaStream_t st);
+                      float* g_vd, int kind, cudaStream_t st);
+}
+
+namespace dfb {
+extern uint32_t* g_dbg_simt_mask_dump;
+extern const uint32_t* g_dbg_tc_mask_in;
+extern uint32_t* g_dbg_tc_mask_out;
+}
+// Debug seam (tests only): ReLU masks of the render backward's forward recompute, per sample [P][12][8] words
+// (fine 8x256 network, one workspace chunk: N <= 16384 rays).  simt_dump: written by the fp32 kernels (ballot
+// layout: word j bit l = column 32j+l).  tc_out: written by the tcgen05 kernel (bit 16*(c&1) + (c>>1)%16 of word
+// c/32 = column c).  tc_in: replaces the tcgen05 kernel's own masks, so that its gradient chain can be compared
+// with the fp32 chain on IDENTICAL ReLU patterns.  Null pointers switch the seam off.
+extern "C" int dfb_debug_bwd_masks(uint32_t* simt_dump, const uint32_t* tc_in, uint32_t* tc_out) {
+  dfb::g_dbg_simt_mask_dump = simt_dump, dfb::g_dbg_tc_mask_in = tc_in, dfb::g_dbg_tc_mask_out = tc_out;
+  return DFB_OK;
 }
 
 namespace {
@@ -382,6 +397,14 @@ extern "C" int dfb_render_bwd_workspace_bytes(const DfbNerf* n, int64_t n_rays, 
 extern "C" int dfb_render_bwd(DfbNerf* n, const float* rays, int64_t N, int S, const float* z_vals, const float* raw,
                               const float* g_rgb, float* g_rays_o, float* g_rays_d, float* g_viewdirs, void* ws,
                               size_t ws_bytes, void* stream) {
+  return dfb_render_bwd_mma(n, DFB_MMA_FP32_SIMT, rays, N, S, z_vals, raw, g_rgb, g_rays_o, g_rays_d, g_viewdirs, ws, ws_bytes,
+                            stream);
+}
+
+extern "C" int dfb_render_bwd_mma(DfbNerf* n, int mma_kind, const float* rays, int64_t N, int S, const float* z_vals,
+                                  const float* raw, const float* g_rgb, float* g_rays_o, float* g_rays_d, float* g_viewdirs,
+                                  void* ws, size_t ws_bytes, void* stream) {
+  DFB_REQUIRE(mma_kind == DFB_MMA_FP32_SIMT || mma_kind == DFB_MMA_F16 || mma_kind == DFB_MMA_BF16, DFB_ERR_INVALID, "bad mma kind");
   DFB_REQUIRE(n && rays && z_vals && raw && g_rgb && g_rays_o && g_rays_d && g_viewdirs, DFB_ERR_INVALID, "null argument");
   DFB_REQUIRE(n->desc.has_fine && n->net[1].loaded && n->has_emb, DFB_ERR_INVALID, "fine network / embeddings not loaded");
   if (N == 0) return DFB_OK;
@@ -406,7 +429,7 @@ extern "C" int dfb_render_bwd(DfbNerf* n, const float* rays, int64_t N, int S, c
     rc = launch_raybias(pa.extra, n_extra, nr, n->net[1], true, P(L.rb), n->net[1].n_dt, st);
     if (rc) return rc;
     rc = launch_render_bwd(n, P(L.rayrec), z_vals + r0 * S, P(L.rb), raw + r0 * S * 9, g_rgb + r0 * 3, nr, S, P(L.g_raw),
-                           P(L.g_samp), g_rays_o + r0 * 3, g_rays_d + r0 * 3, g_viewdirs + r0 * 3, st);
+                           P(L.g_samp), g_rays_o + r0 * 3, g_rays_d + r0 * 3, g_viewdirs + r0 * 3, mma_kind, st);
     if (rc) return rc;
   }
   return DFB_OK;

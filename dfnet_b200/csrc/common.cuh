@@ -82,6 +82,11 @@ struct NetPack {
   void* blob16[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [fp16|bf16][cta_group 1|2 chunking]
   size_t blob16_bytes = 0;
   std::vector<float> tc_tbl;  // host copy of the bias / head-weight table passed as kernel parameter
+
+  // ---- tcgen05 backward layout (fine 8x256 network): the 26-step image of mlp_tc_bwd.cu ------
+  void* blob16b[2] = {nullptr, nullptr};  // [fp16|bf16]
+  size_t blob16b_bytes = 0;
+  std::vector<float> tcb_tbl;
 };
 
 }  // namespace dfb
@@ -114,6 +119,11 @@ int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const
                        const float* raybias, int64_t n_rays, int S, float* raw, cudaStream_t st);
 bool tc_supported(const DfbNerf* nerf, int which, int mode);
 int pack_tc_weights(DfbNerf* nerf, int which, const std::vector<std::vector<float>>& P);
+// tcgen05 backward of the fine network w.r.t. its inputs (mlp_tc_bwd.cu)
+int pack_tc_bwd_weights(DfbNerf* nerf, int which, const std::vector<std::vector<float>>& P);
+bool tc_bwd_supported(const DfbNerf* nerf);
+int launch_mlp_tc_bwd(const DfbNerf* nerf, int kind, const float* rayrec, const float* z, const float* raybias,
+                      const float* raw, const float* g_raw, int64_t n_rays, int S, float* g_samp, cudaStream_t st);
 
 
 // ---- argument blocks of the non-MLP render kernels (render_kernels.cu) ----------------

@@ -94,6 +94,7 @@ struct BwdArgs {
   uint32_t sigma_w, final_w, final_b, dt_w, rgb_w, t_w[3], t_b[3], tsig_w, trgb_w, tbeta_w;
   uint32_t bw_final, bw_dt, bw_dtx, bw_t[3];
   float* g_samp;         // [P,32]: d pts (3), d dirPE (27), pad
+  uint32_t* mask_dump;   // debug seam: [P][D+4][8] ballot words of the forward recompute, or null
 };
 
 // out[s][n] = act(bias[n] + rb[s][n] + sum_k in[s][k] W[k][n]); optionally records the ReLU mask
@@ -230,6 +231,12 @@ __global__ void __launch_bounds__(kBThreads) k_mlp_simt_bwd(BwdArgs a) {
   bgemm_n(Hh, cur, W, Hh, nullptr, 0, 0, B + a.t_w[2], Hh, B + a.t_b[2], nullptr, true, mk(a.D + 3), nullptr, MW, nxt, W, lane);
   __syncwarp();
 
+  if (a.mask_dump) {
+    for (int i = lane; i < (a.D + 4) * kBRows * MW; i += 32) {
+      const int layer = i / (kBRows * MW), s = (i / MW) % kBRows, j = i % MW;
+      if (g0 + s0 + s < a.P) a.mask_dump[((g0 + s0 + s) * (a.D + 4) + layer) * 8 + j] = mk(layer)[s * MW + j];
+    }
+  }
   // ---- head derivatives from the saved forward outputs ----------------------------------------------
   // lane s (< 8) owns sample s of this warp: d pre-activation of rgb(3), sigma, t_rgb(3), t_sigma, t_beta
   float gh[9];
@@ -395,6 +402,8 @@ __global__ void __launch_bounds__(128) k_ray_grad(const float* __restrict__ g_sa
   }
 }
 
+uint32_t* g_dbg_simt_mask_dump = nullptr;
+
 template <int W>
 static int launch_bwd_w(const BwdArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)kBT * (2 * a.pek + 2 * W) * sizeof(float) + (size_t)(a.D + 4) * kBT * (W / 32) * sizeof(uint32_t);
@@ -408,12 +417,20 @@ static int launch_bwd_w(const BwdArgs& a, cudaStream_t st) {
 
 int launch_render_bwd(const DfbNerf* nerf, const float* rayrec, const float* z, const float* raybias, const float* raw,
                       const float* g_rgb, int64_t n_rays, int S, float* g_raw, float* g_samp, float* g_o, float* g_d,
-                      float* g_vd, cudaStream_t st) {
+                      float* g_vd, int kind, cudaStream_t st) {
   const NetPack& np = nerf->net[1];
   DFB_REQUIRE(np.loaded && np.fine && np.blob32b, DFB_ERR_INVALID, "fine network not loaded");
   DFB_REQUIRE((size_t)4 * 3 * S * sizeof(float) <= 48 * 1024, DFB_ERR_UNSUPPORTED, "too many samples per ray for the backward");
   k_composite_bwd<<<(unsigned)((n_rays + 3) / 4), 128, (size_t)4 * 3 * S * sizeof(float), st>>>(raw, z, g_rgb, n_rays, S, g_raw);
   DFB_LAUNCH_CHECK();
+  if (kind != DFB_MMA_FP32_SIMT && tc_bwd_supported(nerf)) {
+    // 8x256 network: forward recompute + input-gradient chain on tcgen05 (mlp_tc_bwd.cu)
+    int rc = launch_mlp_tc_bwd(nerf, kind, rayrec, z, raybias, raw, g_raw, n_rays, S, g_samp, st);
+    if (rc) return rc;
+    k_ray_grad<<<(unsigned)((n_rays + 3) / 4), 128, 0, st>>>(g_samp, z, rayrec, n_rays, S, g_o, g_d, g_vd);
+    DFB_LAUNCH_CHECK();
+    return DFB_OK;
+  }
   BwdArgs a = {};
   a.rayrec = rayrec, a.z = z, a.raybias = raybias, a.raw = raw, a.g_raw = g_raw, a.S = S, a.P = n_rays * S;
   a.D = np.D, a.skip = np.skip, a.pek = np.pek, a.in_xyz = np.in_xyz, a.blob = np.blob32, a.blobb = np.blob32b;
@@ -424,6 +441,7 @@ int launch_render_bwd(const DfbNerf* nerf, const float* rayrec, const float* z, 
   a.tsig_w = np.tsig_w, a.trgb_w = np.trgb_w, a.tbeta_w = np.tbeta_w;
   a.bw_final = np.bw_final, a.bw_dt = np.bw_dt, a.bw_dtx = np.bw_dtx;
   a.g_samp = g_samp;
+  a.mask_dump = g_dbg_simt_mask_dump;
   int rc;
   switch (np.W) {
     case 64: rc = launch_bwd_w<64>(a, st); break;

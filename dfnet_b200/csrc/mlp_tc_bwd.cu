@@ -1,0 +1,665 @@
+// tcgen05 backward of the fine NeRF-W MLP w.r.t. its inputs (8x256 network): what train.py needs from the
+// renderer (reference feature/direct_feature_matching.py:342-378 -> autograd through models/nerfw.py:297-354
+// and models/rendering.py:287,305; the NeRF weights are frozen and the depths detached, rendering.py:302).
+//
+// Same machine as the forward kernel (mlp_tc.cu): persistent CTAs, two 128-sample tiles ("slots") that
+// alternate between the tensor pipe and the epilogue warps, weights streamed as pre-packed 16 KB chunks
+// through a 4-stage shared-memory ring, accumulators in TMEM.  One pass over a tile runs 26 MMA steps:
+//
+//   0..11   forward recompute (trunk 0..7, dir|transient.0 with xyz_encoding_final folded in, transient 2,4,6);
+//           the epilogues keep ONLY the ReLU masks, one bit per activation, in a per-CTA scratch that the same
+//           thread reads back later (L2-resident, 32 B per row and layer)
+//   11      + head derivatives from the saved forward outputs `raw` and d raw, g_T3 = heads^T d heads
+//   12..14  transient branch:  g_in = (g_out W) . mask, W^T streamed as the B operand
+//   15      d dirPE = g_dir W_dir[:, 256:283]            -> g_samp[:, 3:30]
+//   16      g_h7 = [g_dir | g_t0] (W_dt W_final) + d sigma * w_sigma
+//   17..24  trunk (the skip layer splits into a 64-wide positional-encoding part, parked in the scratch, and
+//           the 256-wide hidden part)
+//   25      d PE = g_h0 W_0 + skip part, contracted with the encoding's Jacobian -> d pts -> g_samp[:, 0:3]
+//
+// Gradients are carried as 16-bit MMA operands (same kind as the forward: fp16 or bf16) with fp32
+// accumulation.  A mean-reduced loss gives |g| ~ 1e-8, far below fp16's range, so every row (sample) is
+// scaled by a power of two chosen from its head derivatives; the chain is linear in g, the scale is undone
+// exactly on the two outputs.
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <type_traits>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace dfb {
+namespace tcb {
+
+using namespace dfb::tc;
+
+constexpr int kTileM = 128;
+constexpr int kStages = 4;
+constexpr int kChunkBytes = 16384;
+constexpr int kPanelBytes = kTileM * 16;
+constexpr int kHPanels = 32;
+constexpr int kPePanels = 8;
+constexpr int kSlotBytes = (kHPanels + kPePanels) * kPanelBytes;
+constexpr int kSmemA = 2 * kSlotBytes;
+constexpr int kSmemW = kStages * kChunkBytes;
+constexpr int kSmemBar = 256;
+constexpr int kSmemTotal = kSmemA + kSmemW + kSmemBar;
+constexpr int kThreads = 448;
+constexpr int kSteps = 26;
+constexpr int kMaskLayers = 12;
+// per-CTA scratch, in 32-bit words
+constexpr int kScrMask = 0;                                   // [slot][layer][8 words][128 rows]
+constexpr int kScrSkip = kScrMask + 2 * kMaskLayers * 8 * 128;  // [slot][64][128]  fp32
+constexpr int kScrJac = kScrSkip + 2 * 64 * 128;              // [parity][slot][64][128] fp32
+constexpr int kScrWords = kScrJac + 2 * 2 * 64 * 128;
+
+enum Bar { W_FULL = 0, W_EMPTY = 4, D_FULL = 8, A_READY = 10, PASS_DONE = 12, PE_READY = 14, PE_FREE = 16, N_BARS = 18 };
+
+enum Kind { F_HID, F_DT, F_T3, B_MASK, B_T0, B_DIRPE, B_SIGMA, B_PESKIP, B_PE0 };
+
+struct Step {
+  int n_chunks;    // 16 KB weight chunks (even)
+  int n;           // MMA N
+  int a_panel0;    // first A panel
+  int chunk_base;  // first chunk in the packed image
+  int kind;
+  int ml;          // mask layer written (forward) / applied (backward)
+  int brow;        // row of the packed bias table (forward hidden layers)
+};
+
+struct BtArgs {
+  Step steps[kSteps];
+  const void* wimg;
+  const float* rayrec;   // [n_rays,12]
+  const float* z;        // [n_rays,S]
+  const float* raybias;  // [n_rays,256]
+  const float* raw;      // [P,9] forward outputs
+  const float* g_raw;    // [P,9]
+  float* g_samp;         // [P,32]: d pts (3) | d dirPE (27) | pad
+  uint32_t* scratch;     // [gridDim.x][kScrWords]
+  int S;
+  int64_t P, n_pass;
+  int* error_flag;
+  // debug seam (dfb_debug_bwd_masks): ReLU masks per sample, [P][12 layers][8 words] in this kernel's bit layout;
+  // mask_out receives the masks of the forward recompute, mask_in (if set) replaces them before they are used
+  const uint32_t* mask_in;
+  uint32_t* mask_out;
+  float dt_bias[256];    // constant part of the dir|transient.0 bias (W_dt b_final)
+  float t3_bias[128];
+  float sigma_w[256], rgb_w[384], trgb_w[384], tsig_w[128], tbeta_w[128];
+  uint32_t btbl[10 * 128];  // packed 16-bit bias pairs: rows 0..7 trunk, 8/9 transient_encoding.2/.4
+};
+
+template <typename T> __device__ __forceinline__ uint32_t gt0_mask2(uint32_t pk);
+template <> __device__ __forceinline__ uint32_t gt0_mask2<__half>(uint32_t pk) {
+  return __hgt2_mask(*reinterpret_cast<__half2*>(&pk), __floats2half2_rn(0.f, 0.f));
+}
+template <> __device__ __forceinline__ uint32_t gt0_mask2<__nv_bfloat16>(uint32_t pk) {
+  return __hgt2_mask(*reinterpret_cast<__nv_bfloat162*>(&pk), __floats2bfloat162_rn(0.f, 0.f));
+}
+// Mask word of a 32-column block: bit q (q = 0..15) = column 2q, bit 16+q = column 2q+1, i.e. the two 16-bit
+// lanes of packed pair q.  expand2 turns the pair's two bits into 0xFFFF lanes: shift them to the sign bits of
+// bytes 1 and 3, then PRMT in sign-replicate mode.
+__device__ __forceinline__ uint32_t expand2(uint32_t w, int q) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, 0, 0xBB99;" : "=r"(r) : "r"(w << (15 - q)));
+  return r;
+}
+__device__ __forceinline__ int mask_pos(int j) { return (j & 1) * 16 + (j >> 1); }
+
+// Two 32-column blocks per trip, the next block's TMEM read in flight while the current one is processed.
+// f(v, cb, w): v = 32 fp32 accumulators of block cb, w = mask word of the block (0 if mrow == null).
+template <typename F>
+__device__ __forceinline__ void for_blocks(uint32_t t_row, int ncb, const uint32_t* mrow, F&& f) {
+  uint32_t v0[32], v1[32];
+  tmem_ld32(t_row, v0);
+#pragma unroll 1
+  for (int cb = 0; cb < ncb; cb += 2) {
+    const uint32_t w0 = mrow ? mrow[cb * 128] : 0u, w1 = mrow ? mrow[(cb + 1) * 128] : 0u;
+    tmem_ld_wait(v0);
+    tmem_ld32(t_row + (cb + 1) * 32, v1);
+    f(v0, cb, w0);
+    tmem_ld_wait(v1);
+    if (cb + 2 < ncb) tmem_ld32(t_row + (cb + 2) * 32, v0);
+    f(v1, cb + 1, w1);
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void store_block(uint32_t dst, const uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) st_shared_v4(dst + q * kPanelBytes, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+}
+
+template <int KS>
+__device__ __forceinline__ void issue_step(uint32_t& stage, uint32_t& phase, int nch, uint32_t a_lo, uint32_t b_rows,
+                                           uint32_t d_tmem, uint32_t idesc, uint32_t sW, uint32_t sBar, int* err) {
+  const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+  const uint32_t b_step = 2u * b_rows;
+  uint32_t acc = 0;
+#pragma unroll 1
+  for (int c = 0; c < nch; c += 2) {
+    mbar_wait(sBar + 8u * (W_FULL + stage), phase, err);
+    tc_fence_after();
+    const uint32_t b_lo = ((sW + stage * kChunkBytes) >> 4) | (b_rows << 16);
+    if (elect_one()) {
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks)
+        umma_f16<1>(d_tmem, mk64(a_lo + ks * 256, desc_hi), mk64(b_lo + ks * b_step, desc_hi), idesc, acc | ks);
+      umma_commit<1>(sBar + 8u * (W_EMPTY + stage));
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks)
+        umma_f16<1>(d_tmem, mk64(a_lo + (KS + ks) * 256, desc_hi), mk64(b_lo + (kChunkBytes >> 4) + ks * b_step, desc_hi),
+                    idesc, 1u);
+      umma_commit<1>(sBar + 8u * (W_EMPTY + stage + 1));
+    }
+    __syncwarp();
+    a_lo += 512u * KS;
+    acc = 1;
+    stage += 2;
+    if (stage == kStages) stage = 0, phase ^= 1;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1) k_mlp_tc_bwd(const __grid_constant__ BtArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sA = smem_u32(smem);
+  const uint32_t sW = sA + kSmemA;
+  const uint32_t sBar = sW + kSmemW;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmemA + kSmemW + N_BARS * 8);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  auto bar = [&](int i) { return sBar + 8u * i; };
+  const int fmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
+  uint32_t* scr = a.scratch + (size_t)blockIdx.x * kScrWords;
+
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) mbar_init(bar(W_FULL + i), 1), mbar_init(bar(W_EMPTY + i), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar(D_FULL + s), 1);
+      mbar_init(bar(A_READY + s), 128);
+      mbar_init(bar(PASS_DONE + s), 128);
+      mbar_init(bar(PE_READY + s), 128);
+      mbar_init(bar(PE_FREE + s), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 13) tmem_alloc<1>(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 12) {
+    // ===== weight producer =====================================================================
+    uint32_t stage = 0, phase = 0;
+    const uint8_t* wimg = reinterpret_cast<const uint8_t*>(a.wimg);
+    for (int64_t p = blockIdx.x; p < a.n_pass; p += gridDim.x)
+      for (int s = 0; s < kSteps; ++s) {
+        const int nch = a.steps[s].n_chunks;
+        const uint8_t* src0 = wimg + (size_t)a.steps[s].chunk_base * kChunkBytes;
+        for (int slot = 0; slot < 2; ++slot) {
+          const uint8_t* src = src0;
+          for (int c = 0; c < nch; ++c, src += kChunkBytes) {
+            mbar_wait(bar(W_EMPTY + stage), phase ^ 1, a.error_flag);
+            if (elect_one()) {
+              if ((stage & 1) == 0) mbar_expect_tx(bar(W_FULL + stage), 2 * kChunkBytes);
+              bulk_g2s(sW + stage * kChunkBytes, src, kChunkBytes, bar(W_FULL + (stage & ~1u)));
+            }
+            __syncwarp();
+            if (++stage == kStages) stage = 0, phase ^= 1;
+          }
+        }
+      }
+  } else if (warp == 13) {
+    // ===== MMA issuer ==========================================================================
+    uint32_t stage = 0, phase = 0;
+    int lp = 0;
+    for (int64_t p = blockIdx.x; p < a.n_pass; p += gridDim.x, ++lp)
+      for (int s = 0; s < kSteps; ++s) {
+        const int nch = a.steps[s].n_chunks, nn = a.steps[s].n;
+        const uint32_t idesc = make_idesc(fmt, nn, kTileM);
+        for (int slot = 0; slot < 2; ++slot) {
+          if (s == 0) {
+            if (lp > 0) mbar_wait(bar(PASS_DONE + slot), (lp - 1) & 1, a.error_flag);
+            mbar_wait(bar(PE_READY + slot), lp & 1, a.error_flag);
+          } else {
+            mbar_wait(bar(A_READY + slot), (lp * (kSteps - 1) + s - 1) & 1, a.error_flag);
+          }
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + slot * 256;
+          const uint32_t a_lo = ((sA + slot * kSlotBytes + a.steps[s].a_panel0 * kPanelBytes) >> 4) | ((kPanelBytes >> 4) << 16);
+          if (nn == 256) issue_step<2>(stage, phase, nch, a_lo, nn, d_tmem, idesc, sW, sBar, a.error_flag);
+          else if (nn == 128) issue_step<4>(stage, phase, nch, a_lo, nn, d_tmem, idesc, sW, sBar, a.error_flag);
+          else issue_step<8>(stage, phase, nch, a_lo, nn, d_tmem, idesc, sW, sBar, a.error_flag);
+          if (elect_one()) {
+            umma_commit<1>(bar(D_FULL + slot));
+            if (s == 4) umma_commit<1>(bar(PE_FREE + slot));  // the skip layer is the last reader of the PE panels
+          }
+          __syncwarp();
+        }
+      }
+  } else if (warp >= 8 && warp < 12) {
+    // ===== encoder: positional encoding of the next pass + its Jacobian for step 25 ================
+    const int r = tid - 256;
+    int lp = 0;
+    for (int64_t p = blockIdx.x; p < a.n_pass; p += gridDim.x, ++lp)
+      for (int slot = 0; slot < 2; ++slot) {
+        if (lp > 0) mbar_wait(bar(PE_FREE + slot), (lp - 1) & 1, a.error_flag);
+        int64_t g = (2 * p + slot) * kTileM + r;
+        g = g < a.P ? g : a.P - 1;
+        const int64_t ray = g / a.S;
+        const float* rr = a.rayrec + ray * kRayRec;
+        const float zz = __ldg(a.z + g);
+        float pt[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) pt[c] = __fadd_rn(__ldg(rr + c), __fmul_rn(__ldg(rr + 3 + c), zz));
+        const uint32_t dst = sA + slot * kSlotBytes + kHPanels * kPanelBytes + r * 16;
+        float* jac = reinterpret_cast<float*>(scr + kScrJac + ((lp & 1) * 2 + slot) * 64 * 128) + r;
+        auto put = [&](int col, float v, float j) {
+          T h = (T)v;
+          st_shared_b16(dst + (uint32_t)(col >> 3) * kPanelBytes + (col & 7) * 2, *reinterpret_cast<uint16_t*>(&h));
+          jac[col * 128] = j;
+        };
+        put(0, pt[0], 1.f), put(1, pt[1], 1.f), put(2, pt[2], 1.f), put(63, 0.f, 0.f);
+#pragma unroll 1
+        for (int l = 0; l < 10; ++l) {
+          const float fr = (float)(1 << l);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float sn, cs;
+            sincosf(__fmul_rn(pt[c], fr), &sn, &cs);
+            put(3 + 6 * l + c, sn, fr * cs);
+            put(3 + 6 * l + 3 + c, cs, -fr * sn);
+          }
+        }
+        __threadfence_block();
+        fence_proxy_async();
+        mbar_arrive(bar(PE_READY + slot));
+      }
+  } else if (warp < 8) {
+    // ===== epilogue warpgroups (thread = accumulator row = sample) ================================
+    const int slot = warp >> 2;
+    const int r = tid & 127;
+    const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + slot * 256;
+    const uint32_t h_row = sA + slot * kSlotBytes + r * 16;
+    uint32_t* mbase = scr + kScrMask + slot * kMaskLayers * 8 * 128 + r;
+    float* skip = reinterpret_cast<float*>(scr + kScrSkip + slot * 64 * 128) + r;
+    uint32_t nd = 0;
+    int lp = 0;
+    for (int64_t p = blockIdx.x; p < a.n_pass; p += gridDim.x, ++lp) {
+      const int64_t g = (2 * p + slot) * kTileM + r;
+      const bool valid = g < a.P;
+      const int64_t gc = valid ? g : a.P - 1;
+      const float* rb = a.raybias + (gc / a.S) * 256;
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(rb + (tid & 7) * 32));
+      float gh[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, isc = 1.f;
+      for (int s = 0; s < kSteps; ++s) {
+        mbar_wait(bar(D_FULL + slot), nd & 1, a.error_flag);
+        ++nd;
+        tc_fence_after();
+        const int kd = a.steps[s].kind, ncb = a.steps[s].n >> 5;
+        uint32_t* mrow = mbase + a.steps[s].ml * 8 * 128;
+        const int64_t mdbg = (gc * kMaskLayers + a.steps[s].ml) * 8;
+        auto put_mask = [&](int cb, uint32_t m) {
+          if (a.mask_out && valid) a.mask_out[mdbg + cb] = m;
+          if (a.mask_in) m = a.mask_in[mdbg + cb];
+          mrow[cb * 128] = m;
+        };
+        if (kd == F_HID) {
+          // relu(acc + b) in packed 16-bit math exactly like the forward kernel; mask bit = result > 0
+          const int boff = a.steps[s].brow * 128;
+          for_blocks(t_row, ncb, nullptr, [&](const uint32_t (&v)[32], int cb, uint32_t) {
+            uint32_t pk[16], m = 0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              pk[q] = add_relu2<T>(pack2<T>(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), a.btbl[boff + cb * 16 + q]);
+              m |= gt0_mask2<T>(pk[q]) & (0x00010001u << q);
+            }
+            store_block<T>(h_row + (uint32_t)(cb * 4) * kPanelBytes, pk);
+            put_mask(cb, m);
+          });
+        } else if (kd == F_DT) {
+          // dir_encoding | transient_encoding.0: per-ray bias in fp32; only the transient half feeds a later layer
+          for_blocks(t_row, 8, nullptr, [&](const uint32_t (&v)[32], int cb, uint32_t) {
+            const float4* b4 = reinterpret_cast<const float4*>(rb + cb * 32);
+            float x[32];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 bb = __ldg(b4 + q);
+              x[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + (bb.x + a.dt_bias[cb * 32 + 4 * q + 0]);
+              x[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + (bb.y + a.dt_bias[cb * 32 + 4 * q + 1]);
+              x[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + (bb.z + a.dt_bias[cb * 32 + 4 * q + 2]);
+              x[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + (bb.w + a.dt_bias[cb * 32 + 4 * q + 3]);
+            }
+            uint32_t m = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) m |= x[j] > 0.f ? (1u << mask_pos(j)) : 0u;
+            put_mask(cb, m);
+            if (cb >= 4) {
+              uint32_t pk[16];
+#pragma unroll
+              for (int q = 0; q < 16; ++q) pk[q] = pack2<T>(fmaxf(x[2 * q], 0.f), fmaxf(x[2 * q + 1], 0.f));
+              store_block<T>(h_row + (uint32_t)((cb - 4) * 4) * kPanelBytes, pk);
+            }
+          });
+        } else if (kd == F_T3) {
+          // last transient layer: only its mask is needed; then the head derivatives and g_T3
+          for_blocks(t_row, 4, nullptr, [&](const uint32_t (&v)[32], int cb, uint32_t) {
+            uint32_t m = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) m |= (__uint_as_float(v[j]) + a.t3_bias[cb * 32 + j]) > 0.f ? (1u << mask_pos(j)) : 0u;
+            put_mask(cb, m);
+          });
+          float mx = 0.f;
+#pragma unroll
+          for (int c = 0; c < 9; ++c) {
+            const float o = __ldg(a.raw + gc * 9 + c), gr = valid ? __ldg(a.g_raw + gc * 9 + c) : 0.f;
+            const bool sg = c < 3 || (c >= 4 && c < 7);  // sigmoid outputs; the others are softplus
+            gh[c] = sg ? gr * o * (1.f - o) : gr * (1.f - expf(-o));
+            mx = fmaxf(mx, fabsf(gh[c]));
+          }
+          float sc = 1.f;
+          isc = 1.f;
+          if (mx > 0.f && mx < 3.0e38f) {
+            int e;
+            frexpf(mx, &e);
+            e = max(-100, min(100, e));
+            sc = exp2f((float)(8 - e)), isc = exp2f((float)(e - 8));
+          } else {
+#pragma unroll
+            for (int c = 0; c < 9; ++c) gh[c] = 0.f;
+          }
+#pragma unroll
+          for (int c = 0; c < 9; ++c) gh[c] *= sc;
+#pragma unroll 1
+          for (int cb = 0; cb < 4; ++cb) {
+            const uint32_t w = mrow[cb * 128];
+            uint32_t pk[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              float t[2];
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int k = cb * 32 + 2 * q + h;
+                t[h] = gh[4] * a.trgb_w[k] + gh[5] * a.trgb_w[128 + k] + gh[6] * a.trgb_w[256 + k] + gh[7] * a.tsig_w[k] +
+                       gh[8] * a.tbeta_w[k];
+              }
+              pk[q] = pack2<T>(t[0], t[1]) & expand2(w, q);
+            }
+            store_block<T>(h_row + (uint32_t)(cb * 4) * kPanelBytes, pk);
+          }
+        } else if (kd == B_MASK || kd == B_T0 || kd == B_SIGMA) {
+          // g_in = (g_out W) . relu'(producer); B_T0 writes the transient half of [g_dir | g_t0], B_SIGMA adds the
+          // sigma head's contribution before the mask
+          const int wofs = kd == B_T0 ? 4 : 0, pofs = kd == B_T0 ? 16 : 0;
+          const float gs = kd == B_SIGMA ? gh[3] : 0.f;
+          for_blocks(t_row, ncb, mrow + wofs * 128, [&](const uint32_t (&v)[32], int cb, uint32_t w) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              float x0 = __uint_as_float(v[2 * q]), x1 = __uint_as_float(v[2 * q + 1]);
+              if (kd == B_SIGMA) x0 = fmaf(gs, a.sigma_w[cb * 32 + 2 * q], x0), x1 = fmaf(gs, a.sigma_w[cb * 32 + 2 * q + 1], x1);
+              pk[q] = pack2<T>(x0, x1) & expand2(w, q);
+            }
+            store_block<T>(h_row + (uint32_t)(pofs + cb * 4) * kPanelBytes, pk);
+          });
+          if (kd == B_T0) {
+            // g_dir = rgb head^T d rgb, masked with the dir_encoding half of the same layer
+#pragma unroll 1
+            for (int cb = 0; cb < 4; ++cb) {
+              const uint32_t w = mrow[cb * 128];
+              uint32_t pk[16];
+#pragma unroll
+              for (int q = 0; q < 16; ++q) {
+                const int k = cb * 32 + 2 * q;
+                const float t0 = gh[0] * a.rgb_w[k] + gh[1] * a.rgb_w[128 + k] + gh[2] * a.rgb_w[256 + k];
+                const float t1 = gh[0] * a.rgb_w[k + 1] + gh[1] * a.rgb_w[128 + k + 1] + gh[2] * a.rgb_w[256 + k + 1];
+                pk[q] = pack2<T>(t0, t1) & expand2(w, q);
+              }
+              store_block<T>(h_row + (uint32_t)(cb * 4) * kPanelBytes, pk);
+            }
+          }
+        } else if (kd == B_DIRPE) {
+          uint32_t v[32];
+          tmem_ld32(t_row, v);
+          tmem_ld_wait(v);
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 27; ++j) a.g_samp[g * 32 + 3 + j] = __uint_as_float(v[j]) * isc;
+          }
+        } else if (kd == B_PESKIP) {
+          for_blocks(t_row, 2, nullptr, [&](const uint32_t (&v)[32], int cb, uint32_t) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) skip[(cb * 32 + j) * 128] = __uint_as_float(v[j]);
+          });
+        } else {  // B_PE0
+          const float* jac = reinterpret_cast<const float*>(scr + kScrJac + ((lp & 1) * 2 + slot) * 64 * 128) + r;
+          float d[3] = {0.f, 0.f, 0.f};
+          for_blocks(t_row, 2, nullptr, [&](const uint32_t (&v)[32], int cb, uint32_t) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = cb * 32 + j;  // cb is 0 or 1; the component of a column is periodic in 3 from column 0
+              const float gj = (__uint_as_float(v[j]) + skip[col * 128]) * jac[col * 128];
+              const int c0 = j % 3, c1 = (32 + j) % 3;
+              const int c = cb == 0 ? c0 : c1;
+              d[0] += c == 0 ? gj : 0.f, d[1] += c == 1 ? gj : 0.f, d[2] += c == 2 ? gj : 0.f;
+            }
+          });
+          if (valid) {
+            a.g_samp[g * 32 + 0] = d[0] * isc, a.g_samp[g * 32 + 1] = d[1] * isc, a.g_samp[g * 32 + 2] = d[2] * isc;
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        mbar_arrive(bar((s + 1 < kSteps ? A_READY : PASS_DONE) + slot));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 13) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+}  // namespace tcb
+
+// ---------------------------------------------------------------------------------------
+// host side: packed weight image of the 26 steps, tables, launch
+// ---------------------------------------------------------------------------------------
+namespace {
+
+uint16_t f2h(float f) { __half h = __float2half_rn(f); uint16_t u; memcpy(&u, &h, 2); return u; }
+uint16_t f2b(float f) { __nv_bfloat16 h = __float2bfloat16_rn(f); uint16_t u; memcpy(&u, &h, 2); return u; }
+
+// logical matrices: 0..7 trunk forward, 8 dir|transient.0 (folded), 9..11 transient 2,4,6 forward;
+// 20+i: transpose of transient_encoding.{2,4,6}[i]; 30 dirPE columns of dir_encoding; 31 folded^T;
+// 40+i trunk layer i transposed (hidden part), 50 skip layer's PE part, 51 layer 0 transposed
+struct BStep { int logical, K, N, a_panel0, kind, ml, brow; };
+
+std::vector<BStep> bwd_program() {
+  using namespace tcb;
+  std::vector<BStep> pr;
+  for (int i = 0; i < 8; ++i) pr.push_back({i, i == 0 ? 64 : (i == 4 ? 320 : 256), 256, i == 0 ? 32 : 0, F_HID, i, i});
+  pr.push_back({8, 256, 256, 0, F_DT, 8, 0});
+  pr.push_back({9, 128, 128, 0, F_HID, 9, 8});
+  pr.push_back({10, 128, 128, 0, F_HID, 10, 9});
+  pr.push_back({11, 128, 128, 0, F_T3, 11, 0});
+  pr.push_back({22, 128, 128, 0, B_MASK, 10, 0});   // g_T2
+  pr.push_back({21, 128, 128, 0, B_MASK, 9, 0});    // g_T1
+  pr.push_back({20, 128, 128, 0, B_T0, 8, 0});      // g_t0 (+ g_dir)
+  pr.push_back({30, 128, 128, 0, B_DIRPE, 0, 0});   // d dirPE
+  pr.push_back({31, 256, 256, 0, B_SIGMA, 7, 0});   // g_h7
+  pr.push_back({47, 256, 256, 0, B_MASK, 6, 0});    // g_h6 = g_h7 W_7
+  pr.push_back({46, 256, 256, 0, B_MASK, 5, 0});
+  pr.push_back({45, 256, 256, 0, B_MASK, 4, 0});    // g_h4 = g_h5 W_5
+  pr.push_back({50, 256, 64, 0, B_PESKIP, 0, 0});   // skip layer, PE columns
+  pr.push_back({44, 256, 256, 0, B_MASK, 3, 0});    // g_h3 = g_h4 W_4[:, h]
+  pr.push_back({43, 256, 256, 0, B_MASK, 2, 0});
+  pr.push_back({42, 256, 256, 0, B_MASK, 1, 0});
+  pr.push_back({41, 256, 256, 0, B_MASK, 0, 0});    // g_h0 = g_h1 W_1
+  pr.push_back({51, 256, 64, 0, B_PE0, 0, 0});
+  return pr;
+}
+
+}  // namespace
+
+int pack_tc_bwd_weights(DfbNerf* n, int which, const std::vector<std::vector<float>>& P) {
+  NetPack& np = n->net[which];
+  for (int k = 0; k < 2; ++k)
+    if (np.blob16b[k]) { cudaFree(np.blob16b[k]); np.blob16b[k] = nullptr; }
+  np.tcb_tbl.clear();
+  if (!np.fine || np.W != 256 || np.D != 8 || np.skip != 4 || np.pek != 64) return DFB_OK;
+  const int W = 256, H = 128, in_xyz = np.in_xyz;
+  const int kdd = W + np.in_dir + np.a_dim, ktt = W + np.t_dim;
+  auto wdt = [&](int nn, int k) -> double {
+    if (nn < H) return P[18][(size_t)nn * kdd + k];
+    return P[24][(size_t)(nn - H) * ktt + k];
+  };
+  std::vector<float> fw((size_t)W * W), fb(W);
+  for (int nn = 0; nn < W; ++nn) {
+    double bacc = 0.0;
+    for (int j = 0; j < W; ++j) bacc += wdt(nn, j) * (double)P[17][j];
+    fb[nn] = (float)bacc;
+    for (int k = 0; k < W; ++k) {
+      double acc = 0.0;
+      for (int j = 0; j < W; ++j) acc += wdt(nn, j) * (double)P[16][(size_t)j * W + k];
+      fw[(size_t)nn * W + k] = (float)acc;
+    }
+  }
+  // B[n][k] of every logical matrix (D = A B^T: k runs over the A operand's columns)
+  auto wval = [&](int lg, int nn, int k) -> float {
+    if (lg == 0) return k < in_xyz ? P[0][(size_t)nn * in_xyz + k] : 0.f;
+    if (lg == 4) {  // K order [h(256) | pe(64)]; torch order is cat([input_xyz, h])
+      if (k < W) return P[8][(size_t)nn * (W + in_xyz) + in_xyz + k];
+      return k - W < in_xyz ? P[8][(size_t)nn * (W + in_xyz) + (k - W)] : 0.f;
+    }
+    if (lg < 8) return P[2 * lg][(size_t)nn * W + k];
+    if (lg == 8) return fw[(size_t)nn * W + k];
+    if (lg <= 11) return P[26 + 2 * (lg - 9)][(size_t)nn * H + k];
+    if (lg >= 20 && lg <= 22) return P[26 + 2 * (lg - 20)][(size_t)k * H + nn];
+    if (lg == 30) return nn < np.in_dir ? P[18][(size_t)k * kdd + W + nn] : 0.f;
+    if (lg == 31) return fw[(size_t)k * W + nn];
+    if (lg == 44) return P[8][(size_t)k * (W + in_xyz) + in_xyz + nn];
+    if (lg >= 41 && lg <= 47) return P[2 * (lg - 40)][(size_t)k * W + nn];
+    if (lg == 50) return nn < in_xyz ? P[8][(size_t)k * (W + in_xyz) + nn] : 0.f;
+    if (lg == 51) return nn < in_xyz ? P[0][(size_t)k * in_xyz + nn] : 0.f;
+    return 0.f;
+  };
+  const std::vector<BStep> prog = bwd_program();
+  size_t total = 0;
+  for (const BStep& st : prog) total += (size_t)st.K * st.N * 2 / tcb::kChunkBytes;
+  std::vector<uint16_t> img16[2];
+  img16[0].assign(total * tcb::kChunkBytes / 2, 0);
+  img16[1].assign(total * tcb::kChunkBytes / 2, 0);
+  size_t img = 0;
+  for (const BStep& st : prog) {
+    const int kc = tcb::kChunkBytes / (st.N * 2);
+    for (int k0 = 0; k0 < st.K; k0 += kc, ++img) {
+      const size_t base = img * (tcb::kChunkBytes / 2);
+      for (int kk = 0; kk < kc; ++kk)
+        for (int r = 0; r < st.N; ++r) {
+          const float v = wval(st.logical, r, k0 + kk);
+          const size_t idx = base + (size_t)(kk / 8) * st.N * 8 + (size_t)r * 8 + kk % 8;
+          img16[0][idx] = f2h(v);
+          img16[1][idx] = f2b(v);
+        }
+    }
+  }
+  np.blob16b_bytes = total * tcb::kChunkBytes;
+  for (int k = 0; k < 2; ++k) {
+    DFB_CHECK_CUDA(cudaMalloc(&np.blob16b[k], np.blob16b_bytes));
+    DFB_CHECK_CUDA(cudaMemcpy(np.blob16b[k], img16[k].data(), np.blob16b_bytes, cudaMemcpyHostToDevice));
+  }
+  // fp32 table: [10][256] biases of the packed rows | dt_bias 256 | t3_bias 128 | sigma_w 256 | rgb_w 384 |
+  // trgb_w 384 | tsig_w 128 | tbeta_w 128
+  np.tcb_tbl.assign(10 * 256 + 256 + 128 + 256 + 384 + 384 + 128 + 128, 0.f);
+  float* tb = np.tcb_tbl.data();
+  for (int i = 0; i < 8; ++i) memcpy(tb + i * 256, P[2 * i + 1].data(), 256 * sizeof(float));
+  memcpy(tb + 8 * 256, P[27].data(), H * sizeof(float));
+  memcpy(tb + 9 * 256, P[29].data(), H * sizeof(float));
+  float* q = tb + 10 * 256;
+  memcpy(q, fb.data(), 256 * sizeof(float)), q += 256;
+  memcpy(q, P[31].data(), H * sizeof(float)), q += 128;
+  memcpy(q, P[20].data(), 256 * sizeof(float)), q += 256;
+  memcpy(q, P[22].data(), 384 * sizeof(float)), q += 384;
+  memcpy(q, P[34].data(), 384 * sizeof(float)), q += 384;
+  memcpy(q, P[32].data(), H * sizeof(float)), q += 128;
+  memcpy(q, P[36].data(), H * sizeof(float));
+  return DFB_OK;
+}
+
+bool tc_bwd_supported(const DfbNerf* n) {
+  const NetPack& np = n->net[1];
+  return np.loaded && np.fine && np.blob16b[0] != nullptr && !np.tcb_tbl.empty();
+}
+
+static int* g_bwd_error_flag = nullptr;
+const uint32_t* g_dbg_tc_mask_in = nullptr;
+uint32_t* g_dbg_tc_mask_out = nullptr;
+static uint32_t* g_bwd_scratch = nullptr;
+static int g_bwd_scratch_ctas = 0;
+
+// Fine-network backward for P = n_rays*S samples: g_samp[P,32] from raw / g_raw (see the header comment).
+int launch_mlp_tc_bwd(const DfbNerf* nerf, int kind, const float* rayrec, const float* z, const float* raybias,
+                      const float* raw, const float* g_raw, int64_t n_rays, int S, float* g_samp, cudaStream_t st) {
+  const NetPack& np = nerf->net[1];
+  DFB_REQUIRE(tc_bwd_supported(nerf), DFB_ERR_UNSUPPORTED, "network shape not supported by the tcgen05 backward kernel");
+  DFB_REQUIRE(kind == DFB_MMA_F16 || kind == DFB_MMA_BF16, DFB_ERR_INVALID, "bad mma kind");
+  if (!g_bwd_error_flag) {
+    DFB_CHECK_CUDA(cudaMalloc(&g_bwd_error_flag, sizeof(int)));
+    DFB_CHECK_CUDA(cudaMemset(g_bwd_error_flag, 0, sizeof(int)));
+  }
+  tcb::BtArgs a;
+  memset(&a, 0, sizeof(a));
+  const std::vector<BStep> prog = bwd_program();
+  int cb = 0;
+  for (int s = 0; s < tcb::kSteps; ++s) {
+    const BStep& ls = prog[s];
+    const int kc = tcb::kChunkBytes / (ls.N * 2);
+    a.steps[s] = {ls.K / kc, ls.N, ls.a_panel0, cb, ls.kind, ls.ml, ls.brow};
+    cb += ls.K / kc;
+  }
+  a.wimg = np.blob16b[kind == DFB_MMA_F16 ? 0 : 1];
+  const float* tb = np.tcb_tbl.data();
+  for (int i = 0; i < 10 * 128; ++i) {
+    const float lo = tb[2 * i], hi = tb[2 * i + 1];
+    a.btbl[i] = kind == DFB_MMA_F16 ? ((uint32_t)f2h(hi) << 16 | f2h(lo)) : ((uint32_t)f2b(hi) << 16 | f2b(lo));
+  }
+  const float* q = tb + 10 * 256;
+  memcpy(a.dt_bias, q, sizeof(a.dt_bias)), q += 256;
+  memcpy(a.t3_bias, q, sizeof(a.t3_bias)), q += 128;
+  memcpy(a.sigma_w, q, sizeof(a.sigma_w)), q += 256;
+  memcpy(a.rgb_w, q, sizeof(a.rgb_w)), q += 384;
+  memcpy(a.trgb_w, q, sizeof(a.trgb_w)), q += 384;
+  memcpy(a.tsig_w, q, sizeof(a.tsig_w)), q += 128;
+  memcpy(a.tbeta_w, q, sizeof(a.tbeta_w));
+  a.rayrec = rayrec, a.z = z, a.raybias = raybias, a.raw = raw, a.g_raw = g_raw, a.g_samp = g_samp;
+  a.S = S, a.P = n_rays * S, a.error_flag = g_bwd_error_flag;
+  a.mask_in = g_dbg_tc_mask_in, a.mask_out = g_dbg_tc_mask_out;
+  if (a.P == 0) return DFB_OK;
+  const int64_t tiles = (a.P + tcb::kTileM - 1) / tcb::kTileM;
+  a.n_pass = (tiles + 1) / 2;
+  const int grid = (int)std::min<int64_t>(a.n_pass, nerf->num_sms);
+  if (g_bwd_scratch_ctas < grid) {
+    if (g_bwd_scratch) cudaFree(g_bwd_scratch);
+    g_bwd_scratch = nullptr, g_bwd_scratch_ctas = 0;
+    DFB_CHECK_CUDA(cudaMalloc(&g_bwd_scratch, (size_t)nerf->num_sms * tcb::kScrWords * 4));
+    g_bwd_scratch_ctas = nerf->num_sms;
+  }
+  a.scratch = g_bwd_scratch;
+  auto launch = [&](auto kern) -> int {
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tcb::kSmemTotal));
+    kern<<<grid, tcb::kThreads, tcb::kSmemTotal, st>>>(a);
+    DFB_LAUNCH_CHECK();
+    return DFB_OK;
+  };
+  if (kind == DFB_MMA_F16) return launch(tcb::k_mlp_tc_bwd<__half>);
+  return launch(tcb::k_mlp_tc_bwd<__nv_bfloat16>);
+}
+
+}  // namespace dfb

@@ -81,6 +81,8 @@ extern "C" void dfb_nerf_destroy(DfbNerf* n) {
     for (int k = 0; k < 2; ++k)
       for (int g = 0; g < 2; ++g)
         if (n->net[i].blob16[k][g]) cudaFree(n->net[i].blob16[k][g]);
+    for (int k = 0; k < 2; ++k)
+      if (n->net[i].blob16b[k]) cudaFree(n->net[i].blob16b[k]);
   }
   if (n->emb_a) cudaFree(n->emb_a);
   if (n->emb_t) cudaFree(n->emb_t);
@@ -270,6 +272,8 @@ extern "C" int dfb_nerf_load(DfbNerf* n, int which, const float* const* params, 
     DFB_CHECK_CUDA(cudaMemcpy(np.blob32b, bb.data(), bb.size() * sizeof(float), cudaMemcpyHostToDevice));
   }
   int rc = pack_tc_weights(n, which, P);
+  if (rc != DFB_OK) return rc;
+  rc = pack_tc_bwd_weights(n, which, P);
   if (rc != DFB_OK) return rc;
   np.loaded = true;
   return DFB_OK;

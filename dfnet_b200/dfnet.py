@@ -175,9 +175,6 @@ class _DfnetFn(torch.autograd.Function):
     def forward(ctx, x, handle, cfg, *params):
         return_feature, single, return_pose, upH, upW, level_mask, _bf16 = cfg
         need_p = any(t.requires_grad for t in params)
-        if need_p and return_feature:
-            raise NotImplementedError("parameter gradients cover the pose path (train.py); training the adaptation heads "
-                                      "(run_feature.py) is not on the B200 path yet")
         ft, fr, pose, tape = handle.forward(x, return_feature, single, return_pose, upH, upW, tape=True, bf16=bool(cfg[6]))
         ctx.handle, ctx.tape, ctx.cfg, ctx.need_p = handle, tape, cfg, need_p
         ctx.xshape = (x.shape[0], x.shape[2], x.shape[3])
@@ -196,6 +193,9 @@ class _DfnetFn(torch.autograd.Function):
         n_out = 3 + len(ctx.pshapes)
         if g_ft is None and g_fr is None and g_pose is None:
             return (None,) * n_out
+        if (g_ft is not None or g_fr is not None) and ctx.need_p:
+            raise NotImplementedError("parameter gradients cover the pose path (train.py); training the adaptation heads "
+                                      "(run_feature.py) is not on the B200 path yet")
         if (g_ft is not None or g_fr is not None) and g_pose is not None:
             raise NotImplementedError("feature and pose gradients through one DFNet forward are not on the B200 path yet")
         g_x, grads = ctx.handle.backward(ctx.tape, ctx.xshape, upH, upW, g_ft, g_fr, level_mask, g_pose, ctx.want_gx,

@@ -138,8 +138,9 @@ class NerfHandle:
                                         _ptr(rgb_host), _ptr(disp_host), _ptr(acc_host), _ptr(ws), ws.numel(),
                                         _stream()))
 
-    def render_backward(self, rays, z_vals, raw, g_rgb):
-        """dfb_render_bwd: gradients of a test-time render w.r.t. rays_o, rays_d and viewdirs, each [N,3]."""
+    def render_backward(self, rays, z_vals, raw, g_rgb, mma="fp32"):
+        """dfb_render_bwd_mma: gradients of a test-time render w.r.t. rays_o, rays_d and viewdirs, each [N,3].
+        mma = the kind the forward ran with; "f16"/"bf16" run the 8x256 fine network's backward on tcgen05."""
         _require_cuda(rays, "rays")
         rays, z_vals, raw, g_rgb = _f32c(rays), _f32c(z_vals), _f32c(raw), _f32c(g_rgb)
         N, S = z_vals.shape
@@ -148,8 +149,8 @@ class NerfHandle:
         check(lib.dfb_render_bwd_workspace_bytes(self._h, N, S, C.byref(need)))
         ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
         g_o, g_d, g_vd = (torch.empty(N, 3, device=dev) for _ in range(3))
-        check(lib.dfb_render_bwd(self._h, _ptr(rays), N, S, _ptr(z_vals), _ptr(raw), _ptr(g_rgb), _ptr(g_o), _ptr(g_d),
-                                 _ptr(g_vd), _ptr(ws), need.value, _stream()))
+        check(lib.dfb_render_bwd_mma(self._h, _lib.MMA_KINDS[mma], _ptr(rays), N, S, _ptr(z_vals), _ptr(raw), _ptr(g_rgb),
+                                     _ptr(g_o), _ptr(g_d), _ptr(g_vd), _ptr(ws), need.value, _stream()))
         return g_o, g_d, g_vd
 
     def nerfw_forward(self, which, mode, x):

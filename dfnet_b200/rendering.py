@@ -49,7 +49,7 @@ class _RenderRaysFn(torch.autograd.Function):
     def forward(ctx, rays_o, rays_d, viewdirs, near_far_hist, handle, N_samples, N_importance, mma):
         rec = torch.cat([rays_o, rays_d, near_far_hist[:, :2], viewdirs, near_far_hist[:, 2:]], -1)
         o = handle.render(N_samples, N_importance, True, rays=rec, mma=mma, want=("z_vals", "raw"))
-        ctx.handle = handle
+        ctx.handle, ctx.mma = handle, mma
         ctx.save_for_backward(rec, o["z_vals"], o["raw"])
         ctx.mark_non_differentiable(o["disp"], o["acc"])
         return o["rgb"], o["disp"], o["acc"]
@@ -57,7 +57,7 @@ class _RenderRaysFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_rgb, g_disp, g_acc):
         rec, z_vals, raw = ctx.saved_tensors
-        g_o, g_d, g_vd = ctx.handle.render_backward(rec, z_vals, raw, g_rgb)
+        g_o, g_d, g_vd = ctx.handle.render_backward(rec, z_vals, raw, g_rgb, mma=ctx.mma)
         return g_o, g_d, g_vd, None, None, None, None, None
 
 

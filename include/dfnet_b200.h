@@ -150,6 +150,12 @@ int dfb_render_bwd_workspace_bytes(const DfbNerf* nerf, int64_t n_rays, int S, s
 int dfb_render_bwd(DfbNerf* nerf, const float* rays, int64_t N, int S, const float* z_vals, const float* raw,
                    const float* g_rgb, float* g_rays_o, float* g_rays_d, float* g_viewdirs, void* ws, size_t ws_bytes,
                    void* stream);
+/* Same with the fine network's forward recompute and input-gradient chain on the tensor cores (tcgen05, 8x256
+ * networks; mma_kind as in DfbRenderCfg: the kind the forward ran with).  DFB_MMA_FP32_SIMT = dfb_render_bwd;
+ * other network shapes fall back to the fp32 kernels. */
+int dfb_render_bwd_mma(DfbNerf* nerf, int mma_kind, const float* rays, int64_t N, int S, const float* z_vals,
+                       const float* raw, const float* g_rgb, float* g_rays_o, float* g_rays_d, float* g_viewdirs, void* ws,
+                       size_t ws_bytes, void* stream);
 
 /* Op-level seams (same arguments as the reference functions). */
 /* sample_pdf (rendering.py:24-65): bins [N,nb], weights [N,nb-1], u [N,Nf] or NULL (det). */
@@ -234,6 +240,11 @@ int dfb_profile_read(double* coarse_ms, double* fine_ms, int64_t* coarse_launche
 /* Debug seam: per-CTA cycle counters of the last tcgen05 MLP launch; only libraries built with
  * -DDFB_TC_PROF record them (returns DFB_ERR_UNSUPPORTED otherwise). out_host: [n_cta][16] u64. */
 int dfb_debug_tc_prof(unsigned long long* out_host, int n_cta);
+/* Debug seam (tests only): ReLU masks of the render backward's forward recompute, device buffers [P][12][8] uint32
+ * (fine 8x256 network, N <= 16384 rays).  simt_dump <- fp32 kernels (word j bit l = column 32j+l); tc_out <- tcgen05
+ * kernel (bit 16*(c&1) + (c>>1)%16 of word c/32 = column c); tc_in replaces the tcgen05 kernel's own masks so that its
+ * gradient chain can be compared with the fp32 chain on identical ReLU patterns.  NULLs switch the seam off. */
+int dfb_debug_bwd_masks(uint32_t* simt_dump, const uint32_t* tc_in, uint32_t* tc_out);
 
 /* Debug seam: measured tensor-pipe cycles per tcgen05.mma (M=128, N=n, K=16) with the kernels' no-swizzle
  * panel layout, `grid` CTAs issuing back to back. */
