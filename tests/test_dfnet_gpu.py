@@ -62,7 +62,10 @@ def test_conv_layer_vs_torch_fp32(cin, cout, k, B, H, W, relu):
 def test_dfnet_forward_vs_reference_golden(g, tag, cls, L):
     net = synthetic_dfnet(cls).to(dev())
     x = torch.tensor(g[f"{tag}_x"], device=dev())
+    # parameters require grad (fresh module): the forward runs through the taped autograd path, as it would for a
+    # reference user who calls the network outside torch.no_grad()
     feats, pose = net(x, return_feature=True, isSingleStream=False, return_pose=True, upsampleH=48, upsampleW=64)
+    feats, pose = [f.detach() for f in feats], pose.detach()
     torch.cuda.synchronize()
     assert feats[0].shape == (L, 1, 128, 48, 64) and pose.shape == (2, 12)
     assert relmax(pose.cpu().numpy(), g[f"{tag}_pose"]) < 5e-3
@@ -73,14 +76,15 @@ def test_dfnet_forward_vs_reference_golden(g, tag, cls, L):
             assert relmax(got[l], want[l]) < 5e-3, (nm, l)
         st = g[f"{tag}_feat_{nm}_stats"]
         assert abs(float(f.abs().sum().double()) - st[1]) / st[1] < 2e-3
-    fs, none = net(x, return_feature=True, isSingleStream=True, return_pose=False, upsampleH=30, upsampleW=40)
+    with torch.no_grad():   # inference path (no tape)
+        fs, none = net(x, return_feature=True, isSingleStream=True, return_pose=False, upsampleH=30, upsampleW=40)
     torch.cuda.synchronize()
     assert none is None and len(fs) == 1 and fs[0].shape == (L, 2, 128, 30, 40)
     got, want = fs[0][:, :, ::8, ::4, ::4].cpu().numpy(), g[f"{tag}_feat_s_sub"]
     for l in range(L):
         assert relmax(got[l], want[l]) < 5e-3, l
     none2, pose_only = net(x, return_feature=False)
-    assert none2 is None and torch.equal(pose_only, pose)
+    assert none2 is None and torch.equal(pose_only.detach(), pose)
 
 
 def test_feature_loss_vs_reference_golden(g):
@@ -115,7 +119,7 @@ def test_dfnet_full_size_pair_properties():
     assert torch.isfinite(feats[0]).all() and torch.isfinite(pose).all()
     assert torch.equal(feats[0], feats[1])                       # identical images -> identical streams
     assert torch.equal(pose[0], pose[1])
-    l0 = float(feature_loss(feats[1][0, 0], feats[0][0, 0]))
+    l0 = float(feature_loss(feats[1][0, 0], feats[0][0, 0]).detach())
     assert abs(l0) < 1e-6                                        # cosine of a tensor with itself
     y = torch.cat([img, torch.rand(1, 3, 480, 640, device=dev())], 0)
     f2, _ = net(y, return_feature=True, isSingleStream=False, return_pose=False, upsampleH=480, upsampleW=640)
@@ -171,6 +175,7 @@ def test_dfnet_cambridge_shape_ragged_pooling():
     want, wpose = DO.dfnet_forward(P, x, single=False, return_pose=True, upH=240, upW=427)
     feats, pose = net.to(dev())(torch.tensor(x, device=dev()), return_feature=True, isSingleStream=False, return_pose=True,
                                 upsampleH=240, upsampleW=427)
+    feats, pose = [f.detach() for f in feats], pose.detach()   # taped forward (the fresh module's parameters require grad)
     torch.cuda.synchronize()
     assert feats[0].shape == (3, 1, 128, 240, 427)
     assert relmax(pose.cpu().numpy(), wpose) < 5e-3
