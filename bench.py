@@ -34,6 +34,20 @@ F_FINE_EXECUTED = F_FINE - 2 * 256 * 256
 FLOP_PER_RAY = NC * F_COARSE + (NC + NF) * F_FINE
 
 
+WORKLOADS = {
+    # name -> (H, W, focal, near, far, Nc, Nf, label)
+    "cfg2": (480, 640, 585.0, 0.0, 2.5, 64, 128, "BASELINE config[1]: 640x480 7-Scenes-heads-shaped image, 64+128 samples"),
+    "cfg5": (1080, 1920, 1674.0, 0.0, 20.0, 64, 192, "BASELINE config[4]: 1920x1080 Cambridge-ShopFacade-shaped image, 64+192 samples"),
+}
+LABEL = WORKLOADS["cfg2"][7]
+
+
+def set_workload(name):
+    global H, W, FOCAL, NEAR, FAR, NC, NF, FLOP_PER_RAY, LABEL
+    H, W, FOCAL, NEAR, FAR, NC, NF, LABEL = WORKLOADS[name]
+    FLOP_PER_RAY = NC * F_COARSE + (NC + NF) * F_FINE
+
+
 def pose(i):
     rng = np.random.RandomState(100 + i)
     ax = rng.randn(3)
@@ -42,6 +56,18 @@ def pose(i):
     K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
     R = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
     return np.concatenate([R, np.array([[0.0], [0.0], [1.0]])], 1).astype(np.float32)
+
+
+def ncu_traffic_per_launch(avg_rays_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the fine tcgen05 MLP kernel from the committed `ncu --set full`
+    capture (profiles/r01_ncu_mlp_tc_summary.csv, one launch of 65 536 rays), scaled to this run's average launch."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_mlp_tc_summary.csv")
+    try:
+        rows = {r.split(",")[0]: r.strip().split(",") for r in open(p)}
+        mb = sum(float(rows[k][3].strip('"')) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        return mb * 1e6 * avg_rays_per_launch / 65536.0
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def peaks():
@@ -131,18 +157,17 @@ def run_reference(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_cfg(args), "gpu_launches": 0,
             "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
-                             "sample": f"{n_rays} rays of the 640x480 image per step (oracle port of render_rays, Linear layers via "
-                                       "torch-CPU addmm on all cores, 64+128 samples, 8x256 NeRF-W)"},
+                             "sample": f"{n_rays} rays of the {W}x{H} image per step (oracle port of render_rays, Linear layers via "
+                                       f"torch-CPU addmm on all cores, {NC}+{NF} samples, 8x256 NeRF-W)"},
             "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 def workload_cfg(args):
-    return {"workload": "BASELINE config[1]: 640x480 7-Scenes-heads-shaped image, 64+128 samples, 8x256 NeRF-W "
-                        "coarse+fine, test-time render_path step (1 image = 307200 rays per step)",
+    return {"workload": f"{LABEL}, 8x256 NeRF-W coarse+fine, test-time render_path step (1 image = {H * W} rays per step)",
             "H": H, "W": W, "N_samples": NC, "N_importance": NF, "netdepth": 8, "netwidth": 256,
             "mma": args.mma, "parallelism": f"images sharded over {args.gpus} rank(s), no collective",
-            "l2": "per-chunk working set (~0.65 GB of intermediates) exceeds the 126 MB L2; no extra flush"}
+            "l2": "per-chunk working set (~0.65 GB of intermediates per 65 536 rays) exceeds the 126 MB L2; no extra flush"}
 
 
 def main():
@@ -154,7 +179,10 @@ def main():
     ap.add_argument("--mma", default=os.environ.get("DFB_MMA", "auto"), choices=["auto", "f16", "bf16", "fp32"])
     ap.add_argument("--cpu-rays", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS),
+                    help="cfg2 = BASELINE config[1] (the headline, default); cfg5 = BASELINE config[4] (1920x1080, 64+192)")
     args = ap.parse_args()
+    set_workload(args.workload)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
@@ -269,7 +297,10 @@ def main():
         peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
         roof = {"bound": "tensor", "kernel": "fine NeRF-W MLP (k_mlp_*), %d launches, %.3f ms avg" % (fl, fine_ms / max(fl, 1)),
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "peak_source": f"{pk_kind} bf16_tflops_sustained (kernel timed inside a long step)", "traffic": None,
+                "peak_source": f"{pk_kind} bf16_tflops_sustained (kernel timed inside a long step)",
+                "traffic": ncu_traffic_per_launch(N * args.steps / max(fl, 1)) if mma != "fp32" and args.workload == "cfg2" else None,
+                "traffic_note": "DRAM bytes per launch from profiles/r01_ncu_mlp_tc_summary.csv (ncu --set full, 65 536-ray "
+                                "launch) scaled to this run's average launch; dominated by the [P,9] fp32 raw output",
                 "kernel_share_of_step": (fine_ms + coarse_ms) / ms,
                 "coarse_mlp_tflops": (N * args.steps * NC * F_COARSE) / (coarse_ms * 1e-3) / 1e12 if coarse_ms > 0 else 0.0,
                 "whole_step_tflops": value * FLOP_PER_RAY / 1e12,
@@ -287,7 +318,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             v, dt = cpu_oracle_rays_per_s(args.cpu_rays)
             line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
-                                    "sample": f"{args.cpu_rays} rays of the same 640x480 image, {dt:.1f} s "
+                                    "sample": f"{args.cpu_rays} rays of the same {W}x{H} image, {dt:.1f} s "
                                               "(oracle port of render_rays; Linear layers via torch-CPU addmm, all cores)"}
         print(json.dumps(line))
     if world > 1:

@@ -595,6 +595,41 @@ __global__ void __launch_bounds__(128, 1) k_umma_rate(int iters, int n, unsigned
   if (warp == 0) { tc_fence_after(); tmem_dealloc<1>(tb, 256); }
 }
 
+// TMEM read-rate probe: `nwarps` warps of one CTA each issue `iters` x 8 tcgen05.ld.32x32b.x32 (4 KB per
+// instruction) on their own 32 lanes, two loads in flight; reports cycles per load instruction per warp.
+__global__ void __launch_bounds__(128, 1) k_tmem_rate(int iters, int nwarps, unsigned long long* out) {
+  __shared__ uint32_t tslot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tmem_alloc<1>(smem_u32(&tslot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tslot + ((uint32_t)(warp * 32) << 16);
+  uint32_t sink = 0;
+  if (warp < nwarps) {
+    uint32_t v0[32], v1[32];
+    const long long t0 = clock64();
+    tmem_ld32(tb, v0);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int cb = 0; cb < 8; cb += 2) {
+        tmem_ld_wait(v0);
+        tmem_ld32(tb + (cb + 1) * 32, v1);
+        sink ^= v0[cb];
+        tmem_ld_wait(v1);
+        tmem_ld32(tb + ((cb + 2) & 7) * 32, v0);
+        sink ^= v1[cb];
+      }
+    }
+    tmem_ld_wait(v0);
+    const long long t1 = clock64();
+    if ((tid & 31) == 0) out[blockIdx.x * 4 + warp] = (unsigned long long)(t1 - t0) + (sink == 0x12345678u ? 1 : 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc<1>(tslot, 512); }
+}
+
 }  // namespace tc
 
 // ---------------------------------------------------------------------------------------
@@ -885,6 +920,25 @@ extern "C" int dfb_debug_umma_rate(int iters, int n, int grid, double* cycles_pe
   double s = 0;
   for (auto v : h) s += (double)v;
   *cycles_per_mma = s / grid / ((double)iters * 16.0);
+  return DFB_OK;
+}
+
+// Debug seam: TMEM read rate; returns mean cycles per tcgen05.ld.32x32b.x32 (4 KB) per warp with `nwarps` warps reading.
+extern "C" int dfb_debug_tmem_rate(int iters, int nwarps, int grid, double* cycles_per_ld) {
+  using namespace dfb;
+  DFB_REQUIRE(cycles_per_ld && iters >= 1 && nwarps >= 1 && nwarps <= 4 && grid >= 1 && grid <= 1024, DFB_ERR_INVALID, "bad arguments");
+  unsigned long long* d = nullptr;
+  DFB_CHECK_CUDA(cudaMalloc(&d, grid * 4 * 8));
+  DFB_CHECK_CUDA(cudaMemset(d, 0, grid * 4 * 8));
+  tc::k_tmem_rate<<<grid, 128>>>(iters, nwarps, d);
+  DFB_LAUNCH_CHECK();
+  std::vector<unsigned long long> h(grid * 4);
+  DFB_CHECK_CUDA(cudaMemcpy(h.data(), d, grid * 4 * 8, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  double s = 0;
+  for (int b = 0; b < grid; ++b)
+    for (int w = 0; w < nwarps; ++w) s += (double)h[b * 4 + w];
+  *cycles_per_ld = s / ((double)grid * nwarps) / ((double)iters * 8.0);
   return DFB_OK;
 }
 

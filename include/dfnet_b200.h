@@ -249,6 +249,8 @@ int dfb_debug_bwd_masks(uint32_t* simt_dump, const uint32_t* tc_in, uint32_t* tc
 /* Debug seam: measured tensor-pipe cycles per tcgen05.mma (M=128, N=n, K=16) with the kernels' no-swizzle
  * panel layout, `grid` CTAs issuing back to back. */
 int dfb_debug_umma_rate(int iters, int n, int grid, double* cycles_per_mma);
+/* Debug seam: TMEM read rate, mean cycles per tcgen05.ld.32x32b.x32 (4 KB) per warp with nwarps (1..4) warps of a CTA reading. */
+int dfb_debug_tmem_rate(int iters, int nwarps, int grid, double* cycles_per_ld);
 
 int dfb_debug_umma_gemm(const float* A, const float* B, int N, int K, int kind, int variant, float* D, void* stream);
 

@@ -1,6 +1,6 @@
 """Time one `train_on_batch` step (BASELINE config[3] / SURVEY cfg4 shape) on the GPU.
 
-    python tools/bench_train.py [--H 240 --W 320 --netw 128 --Nc 64 --Nf 64 --steps 10 --warmup 3]
+    python tools/bench_train.py [--H 480 --W 640 --netw 256 --Nc 64 --Nf 128 --levels 0 --steps 10 --warmup 3]   (defaults = SURVEY 8d cfg4)
     torchrun --nproc-per-node 2 tools/bench_train.py ...      (data-parallel: one image per rank, gradient all-reduce)
 
 Prints one JSON line: steps/s over all ranks, ms/step, and a per-phase split measured with CUDA events.
@@ -26,11 +26,11 @@ from dfnet_b200.dfnet import DFNet  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--H", type=int, default=240)
-    ap.add_argument("--W", type=int, default=320)
-    ap.add_argument("--netw", type=int, default=128)
+    ap.add_argument("--H", type=int, default=480)
+    ap.add_argument("--W", type=int, default=640)
+    ap.add_argument("--netw", type=int, default=256)
     ap.add_argument("--Nc", type=int, default=64)
-    ap.add_argument("--Nf", type=int, default=64)
+    ap.add_argument("--Nf", type=int, default=128)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--levels", type=int, nargs="+", default=[0])

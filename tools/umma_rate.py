@@ -14,3 +14,8 @@ for grid in (1, 148):
         v = C.c_double()
         check(lib.dfb_debug_umma_rate(2000, n, grid, C.byref(v)))
         print(f"grid={grid:4d} N={n:3d}: {v.value:7.1f} cycles/MMA  (nominal {n // 2})")
+for grid in (1, 148):
+    for nw in (1, 2, 4):
+        v = C.c_double()
+        check(lib.dfb_debug_tmem_rate(2000, nw, grid, C.byref(v)))
+        print(f"grid={grid:4d} warps={nw}: {v.value:7.1f} cycles per tcgen05.ld.32x32b.x32 (4 KB) per warp -> {nw * 4096 / v.value:6.1f} B/clk/SM")
