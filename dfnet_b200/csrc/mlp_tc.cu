@@ -91,6 +91,7 @@ struct TcArgs {
   float* raw;             // [P,1] or [P,9]
   int* error_flag;
   unsigned long long* prof;  // optional [gridDim.x][16] cycle counters (DFB_TC_PROF builds)
+  float* xchg;               // [gridDim.x][2 slots][6][128]: head partial sums passed between the epilogue warpgroups
   // fp32 biases and head weights, read through the constant bank (warp-uniform addresses):
   // bias[s][256] for every step, then sigma_w[256], rgb_w[3][128], trgb_w[3][128], tsig_w[128],
   // tbeta_w[128], scalars {sigma_b, rgb_b[3], trgb_b[3], tsig_b, tbeta_b}
@@ -312,8 +313,8 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar(D_FULL + s), 1);
-      mbar_init(bar(A_READY + s), 128 * CG);
-      mbar_init(bar(PASS_DONE + s), 128 * CG);
+      mbar_init(bar(A_READY + s), 256 * CG);   // both epilogue warpgroups arrive for every slot
+      mbar_init(bar(PASS_DONE + s), 256 * CG);
       mbar_init(bar(PE_READY + s), 128 * CG);
       mbar_init(bar(PE_FREE + s), 1);
     }
@@ -430,57 +431,99 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
         arrive_leader<CG>(bar(PE_READY + slot));
       }
   } else if (warp < 8) {
-    // ===== epilogue warpgroups (thread = accumulator row = sample) ===========================
-    const int slot = warp >> 2;
+    // ===== epilogue: BOTH warpgroups work on every (slot, step) ===================================
+    // thread = accumulator row (sample) r of BOTH slots; warpgroup `wg` owns one half of the step's
+    // columns (warps w and w+4 reach the same 32 TMEM lanes).  The two slots' epilogues alternate in
+    // time anyway (each overlaps the other slot's MMAs), so splitting every epilogue over all eight
+    // warps halves the MMA -> epilogue -> MMA chain of a slot and gives every scheduler two working
+    // warps instead of one.  Head dot products that span both halves (sigma, transient heads) are
+    // completed through a small exchange buffer + a 256-thread named barrier.
+    const int wg = warp >> 2;
     const int r = tid & 127;
-    const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + slot * 256;
-    const uint32_t h_row = sA + slot * kSlotBytes + r * 16;
-    EpiCtx cx;
+    EpiCtx cx[2];
     PROF_DECL
     uint32_t nd = 0;
+    float* xb = a.xchg + (size_t)blockIdx.x * (2 * 6 * 128) + r;  // [slot][6][128 rows]
     for (int64_t p = unit0; p < a.n_pass; p += n_units) {
-      const int64_t g = ((2 * p + slot) * CG + rank) * kTileM + r;
-      const bool valid = g < a.P;
-      const int64_t ray = (valid ? g : a.P - 1) / a.S;
-      const float* rb = FULL ? a.raybias + ray * 256 : nullptr;
-      // the per-ray bias row (1 KB) is read by the dir/transient layer much later in the pass: pull it
-      // into L1 now so that those loads do not pay eight serial L2 round trips
-      if (FULL) asm volatile("prefetch.global.L1 [%0];" ::"l"(rb + (tid & 7) * 32));
-      cx.sig = 0.f;
+      // row of slot `sl` in the flattened [ray][sample] array (recomputed where needed: registers are scarce here)
+      auto row_of = [&](int sl) { return ((2 * p + sl) * CG + rank) * kTileM + r; };
+      int rayi[2];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) cx.rgb[c] = 0.f;
+      for (int slot = 0; slot < 2; ++slot) {
+        const int64_t gg = row_of(slot);
+        rayi[slot] = (int)((gg < a.P ? gg : a.P - 1) / a.S);
+        // the per-ray bias row (1 KB) is read by the dir/transient layer much later in the pass: pull it
+        // into L1 now so that those loads do not pay eight serial L2 round trips
+        if (FULL) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.raybias + (size_t)rayi[slot] * 256 + (tid & 7) * 32));
+        cx[slot].sig = 0.f;
 #pragma unroll
-      for (int c = 0; c < 5; ++c) cx.hd[c] = 0.f;
-      for (int s = 0; s < n_steps; ++s) {
+        for (int c = 0; c < 3; ++c) cx[slot].rgb[c] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) cx[slot].hd[c] = 0.f;
+      }
+      for (int s = 0; s < n_steps; ++s, ++nd) {
         const int boff = s * 256;
-        PROF_WAIT(0, mbar_wait(bar(D_FULL + slot), nd & 1, a.error_flag));
-        ++nd;
-        tc_fence_after();
         const int kd = a.kind[s];
-        if (kd == EPI_HIDDEN) epi_blocks<T, EPI_HIDDEN>(t_row, h_row, a, boff, 0, 8, rb, cx);
-        else if (!FULL || kd == EPI_SIGMA_ONLY) epi_blocks<T, EPI_SIGMA_ONLY>(t_row, h_row, a, boff, 0, 8, rb, cx);
-        else if (kd == EPI_HIDDEN_SIGMA) epi_blocks<T, EPI_HIDDEN_SIGMA>(t_row, h_row, a, boff, 0, 8, rb, cx);
-        else if (kd == EPI_FINAL) epi_blocks<T, EPI_FINAL>(t_row, h_row, a, boff, 0, 8, rb, cx);
-        else if (kd == EPI_DT) {
-          epi_blocks<T, EPI_DT_HEAD>(t_row, h_row, a, boff, 0, 4, rb, cx);
-          epi_blocks<T, EPI_DT_STORE>(t_row, h_row, a, boff, 4, 8, rb, cx);
-        } else if (kd == EPI_T) epi_blocks<T, EPI_T>(t_row, h_row, a, boff, 0, 4, rb, cx);
-        else epi_blocks<T, EPI_T_LAST>(t_row, h_row, a, boff, 0, 4, rb, cx);
+#pragma unroll
+        for (int slot = 0; slot < 2; ++slot) {
+          const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + slot * 256;
+          const uint32_t h_row = sA + slot * kSlotBytes + r * 16;
+          EpiCtx& c = cx[slot];
+          const float* rbs = FULL ? a.raybias + (size_t)rayi[slot] * 256 : nullptr;
+          PROF_WAIT(0, mbar_wait(bar(D_FULL + slot), nd & 1, a.error_flag));
+          tc_fence_after();
+          const int w0 = 4 * wg, n0 = 2 * wg;  // first 32-column block of this warpgroup (256- / 128-wide steps)
+          if (kd == EPI_HIDDEN) epi_blocks<T, EPI_HIDDEN>(t_row, h_row, a, boff, w0, w0 + 4, rbs, c);
+          else if (!FULL || kd == EPI_SIGMA_ONLY) epi_blocks<T, EPI_SIGMA_ONLY>(t_row, h_row, a, boff, w0, w0 + 4, rbs, c);
+          else if (kd == EPI_HIDDEN_SIGMA) epi_blocks<T, EPI_HIDDEN_SIGMA>(t_row, h_row, a, boff, w0, w0 + 4, rbs, c);
+          else if (kd == EPI_FINAL) epi_blocks<T, EPI_FINAL>(t_row, h_row, a, boff, w0, w0 + 4, rbs, c);
+          else if (kd == EPI_DT) {
+            if (wg == 0) epi_blocks<T, EPI_DT_HEAD>(t_row, h_row, a, boff, 0, 4, rbs, c);
+            else epi_blocks<T, EPI_DT_STORE>(t_row, h_row, a, boff, 4, 8, rbs, c);
+          } else if (kd == EPI_T) epi_blocks<T, EPI_T>(t_row, h_row, a, boff, n0, n0 + 2, rbs, c);
+          else epi_blocks<T, EPI_T_LAST>(t_row, h_row, a, boff, n0, n0 + 2, rbs, c);
+          tc_fence_before();
+          fence_proxy_async();
+          arrive_leader<CG>(bar((s + 1 < n_steps ? A_READY : PASS_DONE) + slot));
+        }
+        // ---- heads: combine the two column halves (after the arrivals: off the MMA critical path) ----
         if (kd == EPI_HIDDEN_SIGMA || kd == EPI_SIGMA_ONLY) {
-          cx.sig = softplus_f(cx.sig + a.tbl[kTblScal]);
-          if (!FULL && valid) a.raw[g] = cx.sig;
+          if (wg == 1) xb[0] = cx[0].sig, xb[6 * 128] = cx[1].sig;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (wg == 0) {
+#pragma unroll
+            for (int slot = 0; slot < 2; ++slot) {
+              cx[slot].sig = softplus_f(cx[slot].sig + xb[slot * 6 * 128] + a.tbl[kTblScal]);
+              if (!FULL && row_of(slot) < a.P) a.raw[row_of(slot)] = cx[slot].sig;
+            }
+          }
         }
-        if (FULL && kd == EPI_T_LAST && valid) {
-          float* o = a.raw + g * 9;
-          o[0] = sigmoid_f(cx.rgb[0] + a.tbl[kTblScal + 1]), o[1] = sigmoid_f(cx.rgb[1] + a.tbl[kTblScal + 2]);
-          o[2] = sigmoid_f(cx.rgb[2] + a.tbl[kTblScal + 3]), o[3] = cx.sig;
-          o[4] = sigmoid_f(cx.hd[0] + a.tbl[kTblScal + 4]), o[5] = sigmoid_f(cx.hd[1] + a.tbl[kTblScal + 5]);
-          o[6] = sigmoid_f(cx.hd[2] + a.tbl[kTblScal + 6]);
-          o[7] = softplus_f(cx.hd[3] + a.tbl[kTblScal + 7]), o[8] = softplus_f(cx.hd[4] + a.tbl[kTblScal + 8]);
+        if (FULL && kd == EPI_T_LAST) {
+          if (wg == 1) {
+#pragma unroll
+            for (int slot = 0; slot < 2; ++slot)
+#pragma unroll
+              for (int c = 0; c < 5; ++c) xb[(slot * 6 + 1 + c) * 128] = cx[slot].hd[c];
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (wg == 0) {
+#pragma unroll
+            for (int slot = 0; slot < 2; ++slot) {
+              const int64_t gg = row_of(slot);
+              if (gg >= a.P) continue;
+              const EpiCtx& c = cx[slot];
+              float hd[5];
+#pragma unroll
+              for (int k = 0; k < 5; ++k) hd[k] = c.hd[k] + xb[(slot * 6 + 1 + k) * 128];
+              float* o = a.raw + gg * 9;
+              o[0] = sigmoid_f(c.rgb[0] + a.tbl[kTblScal + 1]), o[1] = sigmoid_f(c.rgb[1] + a.tbl[kTblScal + 2]);
+              o[2] = sigmoid_f(c.rgb[2] + a.tbl[kTblScal + 3]), o[3] = c.sig;
+              o[4] = sigmoid_f(hd[0] + a.tbl[kTblScal + 4]), o[5] = sigmoid_f(hd[1] + a.tbl[kTblScal + 5]);
+              o[6] = sigmoid_f(hd[2] + a.tbl[kTblScal + 6]);
+              o[7] = softplus_f(hd[3] + a.tbl[kTblScal + 7]), o[8] = softplus_f(hd[4] + a.tbl[kTblScal + 8]);
+            }
+          }
         }
-        tc_fence_before();
-        fence_proxy_async();
-        arrive_leader<CG>(bar((s + 1 < n_steps ? A_READY : PASS_DONE) + slot));
       }
     }
     if (warp == 0) { PROF_FLUSH(8) }
@@ -788,6 +831,7 @@ int pack_tc_weights(DfbNerf* n, int which, const std::vector<std::vector<float>>
 }
 
 static int* g_error_flag = nullptr;
+static float* g_xchg = nullptr;
 
 // 3-D tensor map over a packed weight image: [n_img][64][128 x u16], one box = one 16 KB image.
 static int make_weight_tmap(void* base, size_t bytes, CUtensorMap* out) {
@@ -861,6 +905,8 @@ int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const
   }
   a.rayrec = rayrec, a.z = z, a.raybias = raybias, a.S = S, a.P = n_rays * S, a.raw = raw;
   a.error_flag = g_error_flag;
+  if (!g_xchg) DFB_CHECK_CUDA(cudaMalloc(&g_xchg, (size_t)1024 * 2 * 6 * 128 * sizeof(float)));
+  a.xchg = g_xchg;
 #ifdef DFB_TC_PROF
   if (!g_prof) {
     DFB_CHECK_CUDA(cudaMalloc(&g_prof, 512 * 16 * sizeof(unsigned long long)));
