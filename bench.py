@@ -28,9 +28,10 @@ NC, NF = 64, 128
 HIST = np.array([5, 10, 20, 30, 15, 10, 5, 3, 1, 1], np.float32)
 # Algorithmic FLOPs: 2*MACs of every Linear on the path, W=256, D=8
 F_COARSE, F_FINE = 982528, 1369856          # per sample
-# FLOPs the tcgen05 kernel actually executes per fine sample: xyz_encoding_final (2*256*256) is folded
-# into the two layers that consume it; the roofline uses the algorithmic figure above.
-F_FINE_EXECUTED = F_FINE - 2 * 256 * 256
+# FLOPs the tcgen05 kernel actually issues per fine sample: xyz_encoding_final (2*256*256) is folded into the
+# two layers that consume it and the output heads run as two zero-padded N=64 steps: trunk,
+# sigma step, dir|transient.0, transient 2/4/6, heads step.  The roofline uses the algorithmic figure above.
+F_FINE_EXECUTED = 2 * (64 * 256 + 6 * 256 * 256 + 320 * 256 + 256 * 64 + 256 * 256 + 3 * 128 * 128 + 256 * 64)
 FLOP_PER_RAY = NC * F_COARSE + (NC + NF) * F_FINE
 
 

@@ -51,16 +51,15 @@ constexpr int kSmemW = kStages * kChunkBytes;
 constexpr int kSmemBar = 256;
 constexpr int kSmemTotal = kSmemA + kSmemW + kSmemBar;  // 229632 B
 constexpr int kThreads = 448;
-constexpr int kMaxSteps = 13;
-constexpr int kTblSigmaW = kMaxSteps * 256;
-constexpr int kTblRgbW = kTblSigmaW + 256;
-constexpr int kTblTrgbW = kTblRgbW + 384;
-constexpr int kTblTsigW = kTblTrgbW + 384;
-constexpr int kTblTbetaW = kTblTsigW + 128;
-constexpr int kTblScal = kTblTbetaW + 128;
+constexpr int kMaxSteps = 16;
+constexpr int kTblScal = kMaxSteps * 256;
 constexpr int kTblFloats = kTblScal + 16;
 
-enum EpiKind { EPI_HIDDEN, EPI_HIDDEN_SIGMA, EPI_SIGMA_ONLY, EPI_FINAL, EPI_DT_HEAD, EPI_DT_STORE, EPI_T, EPI_T_LAST, EPI_DT };
+// EPI_SIGMA / EPI_HEADS: the output heads run on the tensor pipe as N=64 steps (sigma on the trunk output; the
+// transient heads on transient_encoding.6 and static_rgb on dir_encoding as ONE block-structured K=256 step);
+// their epilogues read a handful of accumulator columns.  As fp32 dot products in the epilogue they were 60 %
+// of its instructions, and the epilogue warps - not the tensor pipe - bounded the kernel.
+enum EpiKind { EPI_HIDDEN, EPI_FINAL, EPI_T, EPI_DT, EPI_SIGMA, EPI_HEADS };
 
 // barrier slots (8 bytes each) inside the kSmemBar region
 enum Bar { W_FULL = 0, W_EMPTY = 4, D_FULL = 8, A_READY = 10, PASS_DONE = 12, PE_READY = 14, PE_FREE = 16, W_FULLP = 18, N_BARS = 22 };
@@ -91,10 +90,8 @@ struct TcArgs {
   float* raw;             // [P,1] or [P,9]
   int* error_flag;
   unsigned long long* prof;  // optional [gridDim.x][16] cycle counters (DFB_TC_PROF builds)
-  float* xchg;               // [gridDim.x][2 slots][6][128]: head partial sums passed between the epilogue warpgroups
-  // fp32 biases and head weights, read through the constant bank (warp-uniform addresses):
-  // bias[s][256] for every step, then sigma_w[256], rgb_w[3][128], trgb_w[3][128], tsig_w[128],
-  // tbeta_w[128], scalars {sigma_b, rgb_b[3], trgb_b[3], tsig_b, tbeta_b}
+  // fp32 biases, read through the constant bank (warp-uniform addresses): bias[s][256] for every step, then
+  // the head scalars {sigma_b, rgb_b[3], trgb_b[3], tsig_b, tbeta_b}
   float tbl[kTblFloats];
   // the same per-step biases as packed 16-bit pairs (fp16 or bf16, matching the MMA kind) for the
   // packed-math epilogue of the plain hidden layers: btbl[s*128 + j] = {bias[2j], bias[2j+1]}
@@ -127,22 +124,14 @@ struct TcArgs {
 // ---------------------------------------------------------------------------------------
 
 struct EpiCtx {
-  float sig, rgb[3], hd[5];
+  float sig;
 };
 
-// dot of 32 activations with 32 table entries (constant bank, warp-uniform)
-__device__ __forceinline__ float dot32c(const float (&x)[32], const TcArgs& a, int off, float acc) {
-#pragma unroll
-  for (int j = 0; j < 32; ++j) acc = fmaf(x[j], a.tbl[off + j], acc);
-  return acc;
-}
-
-// One 32-column block (columns cb*32 .. cb*32+31) of this thread's accumulator row: add bias
-// (constant bank) or the per-ray bias (global), activation, fp32 head dot products, 16-bit store
-// of the next layer's A operand.
+// One 32-column block (columns cb*32 .. cb*32+31) of this thread's accumulator row: bias + activation and the
+// 16-bit store of the next layer's A operand.
 template <typename T, int KIND>
 __device__ __forceinline__ void epi_block(const uint32_t (&v)[32], const TcArgs& a, int bias_off, int cb,
-                                          const float* __restrict__ rb, uint32_t h_row, EpiCtx& cx) {
+                                          const float* __restrict__ rb, uint32_t h_row) {
   if (KIND == EPI_HIDDEN || KIND == EPI_T || KIND == EPI_FINAL) {
     // Plain hidden layer: round the fp32 accumulators to the 16-bit operand type first, then
     // bias + ReLU as ONE packed HFMA2.RELU per column pair (the rounding this adds is of the same
@@ -159,47 +148,24 @@ __device__ __forceinline__ void epi_block(const uint32_t (&v)[32], const TcArgs&
     for (int q = 0; q < 4; ++q) st_shared_v4(dst + q * kPanelBytes, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
     return;
   }
+  // EPI_DT: dir_encoding | transient_encoding.0 with the per-ray bias (global, fp32) + the step's constant bias
+  // (non-zero when xyz_encoding_final is folded in).  transient_encoding.0 (columns 128..255) goes to panels
+  // 0..15 (input of transient_encoding.2), dir_encoding (columns 0..127) to panels 16..31 (input of static_rgb).
   float x[32];
-  if (KIND == EPI_DT_HEAD || KIND == EPI_DT_STORE) {
-    const float4* b4 = reinterpret_cast<const float4*>(rb + cb * 32);
+  const float4* b4 = reinterpret_cast<const float4*>(rb + cb * 32);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 bb = __ldg(b4 + q);
-      // per-ray bias (global) + the step's constant bias (non-zero when xyz_encoding_final is folded in)
-      x[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + (bb.x + a.tbl[bias_off + cb * 32 + 4 * q + 0]);
-      x[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + (bb.y + a.tbl[bias_off + cb * 32 + 4 * q + 1]);
-      x[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + (bb.z + a.tbl[bias_off + cb * 32 + 4 * q + 2]);
-      x[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + (bb.w + a.tbl[bias_off + cb * 32 + 4 * q + 3]);
-    }
-  } else {
-    const int off = bias_off + cb * 32;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + a.tbl[off + j];
+  for (int q = 0; q < 8; ++q) {
+    const float4 bb = __ldg(b4 + q);
+    x[4 * q + 0] = fmaxf(__uint_as_float(v[4 * q + 0]) + (bb.x + a.tbl[bias_off + cb * 32 + 4 * q + 0]), 0.f);
+    x[4 * q + 1] = fmaxf(__uint_as_float(v[4 * q + 1]) + (bb.y + a.tbl[bias_off + cb * 32 + 4 * q + 1]), 0.f);
+    x[4 * q + 2] = fmaxf(__uint_as_float(v[4 * q + 2]) + (bb.z + a.tbl[bias_off + cb * 32 + 4 * q + 2]), 0.f);
+    x[4 * q + 3] = fmaxf(__uint_as_float(v[4 * q + 3]) + (bb.w + a.tbl[bias_off + cb * 32 + 4 * q + 3]), 0.f);
   }
-  if (KIND != EPI_FINAL) {
+  const uint32_t dst = h_row + (uint32_t)(((cb + 4) & 7) * 4) * kPanelBytes;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
-  }
-  if (KIND == EPI_HIDDEN_SIGMA || KIND == EPI_SIGMA_ONLY) cx.sig = dot32c(x, a, kTblSigmaW + cb * 32, cx.sig);
-  if (KIND == EPI_DT_HEAD) {
-#pragma unroll
-    for (int c = 0; c < 3; ++c) cx.rgb[c] = dot32c(x, a, kTblRgbW + c * 128 + cb * 32, cx.rgb[c]);
-  }
-  if (KIND == EPI_T_LAST) {
-#pragma unroll
-    for (int c = 0; c < 3; ++c) cx.hd[c] = dot32c(x, a, kTblTrgbW + c * 128 + cb * 32, cx.hd[c]);
-    cx.hd[3] = dot32c(x, a, kTblTsigW + cb * 32, cx.hd[3]);
-    cx.hd[4] = dot32c(x, a, kTblTbetaW + cb * 32, cx.hd[4]);
-  }
-  constexpr bool kStore = KIND == EPI_HIDDEN || KIND == EPI_HIDDEN_SIGMA || KIND == EPI_FINAL || KIND == EPI_T ||
-                          KIND == EPI_DT_STORE;
-  if (kStore) {
-    const uint32_t dst = h_row + (uint32_t)((KIND == EPI_DT_STORE ? cb - 4 : cb) * 4) * kPanelBytes;
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      st_shared_v4(dst + q * kPanelBytes, pack2<T>(x[8 * q], x[8 * q + 1]), pack2<T>(x[8 * q + 2], x[8 * q + 3]),
-                   pack2<T>(x[8 * q + 4], x[8 * q + 5]), pack2<T>(x[8 * q + 6], x[8 * q + 7]));
-  }
+  for (int q = 0; q < 4; ++q)
+    st_shared_v4(dst + q * kPanelBytes, pack2<T>(x[8 * q], x[8 * q + 1]), pack2<T>(x[8 * q + 2], x[8 * q + 3]),
+                 pack2<T>(x[8 * q + 4], x[8 * q + 5]), pack2<T>(x[8 * q + 6], x[8 * q + 7]));
 }
 
 // Blocks [cb0, cb1) of a step (cb1 - cb0 even): software-pipelined TMEM reads, block cb+1 is in
@@ -207,17 +173,17 @@ __device__ __forceinline__ void epi_block(const uint32_t (&v)[32], const TcArgs&
 // enough for the instruction cache, which the MMA issuer shares.
 template <typename T, int KIND>
 __device__ __forceinline__ void epi_blocks(uint32_t t_row, uint32_t h_row, const TcArgs& a, int bias_off, int cb0, int cb1,
-                                           const float* rb, EpiCtx& cx) {
+                                           const float* rb) {
   uint32_t v0[32], v1[32];
   tmem_ld32(t_row + cb0 * 32, v0);
 #pragma unroll 1
   for (int cb = cb0; cb < cb1; cb += 2) {
     tmem_ld_wait(v0);
     tmem_ld32(t_row + (cb + 1) * 32, v1);
-    epi_block<T, KIND>(v0, a, bias_off, cb, rb, h_row, cx);
+    epi_block<T, KIND>(v0, a, bias_off, cb, rb, h_row);
     tmem_ld_wait(v1);
     if (cb + 2 < cb1) tmem_ld32(t_row + (cb + 2) * 32, v0);
-    epi_block<T, KIND>(v1, a, bias_off, cb + 1, rb, h_row, cx);
+    epi_block<T, KIND>(v1, a, bias_off, cb + 1, rb, h_row);
   }
 }
 
@@ -384,7 +350,8 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
           // low word: start address >> 4 | LBO (2048 B >> 4) << 16; one K=16 step advances by 2 panels
           const uint32_t a_lo = ((sA + slot * kSlotBytes + a.steps[s].a_panel0 * kPanelBytes) >> 4) | ((kPanelBytes >> 4) << 16);
           if (nn == 256) issue_step<CG, 2 * CG>(stage, phase, nch, a_lo, b_rows, d_tmem, idesc, sW, sBar, a.error_flag, PROF_PTR);
-          else issue_step<CG, 4 * CG>(stage, phase, nch, a_lo, b_rows, d_tmem, idesc, sW, sBar, a.error_flag, PROF_PTR);
+          else if (nn == 128) issue_step<CG, 4 * CG>(stage, phase, nch, a_lo, b_rows, d_tmem, idesc, sW, sBar, a.error_flag, PROF_PTR);
+          else issue_step<CG, 8 * CG>(stage, phase, nch, a_lo, b_rows, d_tmem, idesc, sW, sBar, a.error_flag, PROF_PTR);
           if (elect_one()) {
             umma_commit<CG>(bar(D_FULL + slot));
             if (s == a.last_pe_step) umma_commit<CG>(bar(PE_FREE + slot));
@@ -436,14 +403,13 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
     // columns (warps w and w+4 reach the same 32 TMEM lanes).  The two slots' epilogues alternate in
     // time anyway (each overlaps the other slot's MMAs), so splitting every epilogue over all eight
     // warps halves the MMA -> epilogue -> MMA chain of a slot and gives every scheduler two working
-    // warps instead of one.  Head dot products that span both halves (sigma, transient heads) are
-    // completed through a small exchange buffer + a 256-thread named barrier.
+    // warps instead of one.  The head steps (EPI_SIGMA, EPI_HEADS) only read a few accumulator columns:
+    // warpgroup 0 finishes them, warpgroup 1 just arrives.
     const int wg = warp >> 2;
     const int r = tid & 127;
     EpiCtx cx[2];
     PROF_DECL
     uint32_t nd = 0;
-    float* xb = a.xchg + (size_t)blockIdx.x * (2 * 6 * 128) + r;  // [slot][6][128 rows]
     for (int64_t p = unit0; p < a.n_pass; p += n_units) {
       // row of slot `sl` in the flattened [ray][sample] array (recomputed where needed: registers are scarce here)
       auto row_of = [&](int sl) { return ((2 * p + sl) * CG + rank) * kTileM + r; };
@@ -456,10 +422,6 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
         // into L1 now so that those loads do not pay eight serial L2 round trips
         if (FULL) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.raybias + (size_t)rayi[slot] * 256 + (tid & 7) * 32));
         cx[slot].sig = 0.f;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) cx[slot].rgb[c] = 0.f;
-#pragma unroll
-        for (int c = 0; c < 5; ++c) cx[slot].hd[c] = 0.f;
       }
       for (int s = 0; s < n_steps; ++s, ++nd) {
         const int boff = s * 256;
@@ -468,61 +430,40 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
         for (int slot = 0; slot < 2; ++slot) {
           const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + slot * 256;
           const uint32_t h_row = sA + slot * kSlotBytes + r * 16;
-          EpiCtx& c = cx[slot];
           const float* rbs = FULL ? a.raybias + (size_t)rayi[slot] * 256 : nullptr;
           PROF_WAIT(0, mbar_wait(bar(D_FULL + slot), nd & 1, a.error_flag));
           tc_fence_after();
           const int w0 = 4 * wg, n0 = 2 * wg;  // first 32-column block of this warpgroup (256- / 128-wide steps)
-          if (kd == EPI_HIDDEN) epi_blocks<T, EPI_HIDDEN>(t_row, h_row, a, boff, w0, w0 + 4, rbs, c);
-          else if (!FULL || kd == EPI_SIGMA_ONLY) epi_blocks<T, EPI_SIGMA_ONLY>(t_row, h_row, a, boff, w0, w0 + 4, rbs, c);
-          else if (kd == EPI_HIDDEN_SIGMA) epi_blocks<T, EPI_HIDDEN_SIGMA>(t_row, h_row, a, boff, w0, w0 + 4, rbs, c);
-          else if (kd == EPI_FINAL) epi_blocks<T, EPI_FINAL>(t_row, h_row, a, boff, w0, w0 + 4, rbs, c);
-          else if (kd == EPI_DT) {
-            if (wg == 0) epi_blocks<T, EPI_DT_HEAD>(t_row, h_row, a, boff, 0, 4, rbs, c);
-            else epi_blocks<T, EPI_DT_STORE>(t_row, h_row, a, boff, 4, 8, rbs, c);
-          } else if (kd == EPI_T) epi_blocks<T, EPI_T>(t_row, h_row, a, boff, n0, n0 + 2, rbs, c);
-          else epi_blocks<T, EPI_T_LAST>(t_row, h_row, a, boff, n0, n0 + 2, rbs, c);
+          if (kd == EPI_HIDDEN) epi_blocks<T, EPI_HIDDEN>(t_row, h_row, a, boff, w0, w0 + 4, rbs);
+          else if (kd == EPI_T) epi_blocks<T, EPI_T>(t_row, h_row, a, boff, n0, n0 + 2, rbs);
+          else if (kd == EPI_DT) epi_blocks<T, EPI_DT>(t_row, h_row, a, boff, w0, w0 + 4, rbs);
+          else if (kd == EPI_FINAL) epi_blocks<T, EPI_FINAL>(t_row, h_row, a, boff, w0, w0 + 4, rbs);
+          else if (wg == 0) {
+            // head steps: column 0 = sigma (EPI_SIGMA); columns 0..4 = transient rgb(3), sigma, beta and
+            // columns 8..10 = static rgb (EPI_HEADS)
+            uint32_t v[32];
+            tmem_ld32(t_row, v);
+            tmem_ld_wait(v);
+            const int64_t gg = row_of(slot);
+            if (kd == EPI_SIGMA) {
+              cx[slot].sig = softplus_f(__uint_as_float(v[0]) + a.tbl[kTblScal]);
+              if (!FULL && gg < a.P) a.raw[gg] = cx[slot].sig;
+            } else if (gg < a.P) {
+              float* o = a.raw + gg * 9;
+              o[0] = sigmoid_f(__uint_as_float(v[8]) + a.tbl[kTblScal + 1]);
+              o[1] = sigmoid_f(__uint_as_float(v[9]) + a.tbl[kTblScal + 2]);
+              o[2] = sigmoid_f(__uint_as_float(v[10]) + a.tbl[kTblScal + 3]);
+              o[3] = cx[slot].sig;
+              o[4] = sigmoid_f(__uint_as_float(v[0]) + a.tbl[kTblScal + 4]);
+              o[5] = sigmoid_f(__uint_as_float(v[1]) + a.tbl[kTblScal + 5]);
+              o[6] = sigmoid_f(__uint_as_float(v[2]) + a.tbl[kTblScal + 6]);
+              o[7] = softplus_f(__uint_as_float(v[3]) + a.tbl[kTblScal + 7]);
+              o[8] = softplus_f(__uint_as_float(v[4]) + a.tbl[kTblScal + 8]);
+            }
+          }
           tc_fence_before();
           fence_proxy_async();
           arrive_leader<CG>(bar((s + 1 < n_steps ? A_READY : PASS_DONE) + slot));
-        }
-        // ---- heads: combine the two column halves (after the arrivals: off the MMA critical path) ----
-        if (kd == EPI_HIDDEN_SIGMA || kd == EPI_SIGMA_ONLY) {
-          if (wg == 1) xb[0] = cx[0].sig, xb[6 * 128] = cx[1].sig;
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (wg == 0) {
-#pragma unroll
-            for (int slot = 0; slot < 2; ++slot) {
-              cx[slot].sig = softplus_f(cx[slot].sig + xb[slot * 6 * 128] + a.tbl[kTblScal]);
-              if (!FULL && row_of(slot) < a.P) a.raw[row_of(slot)] = cx[slot].sig;
-            }
-          }
-        }
-        if (FULL && kd == EPI_T_LAST) {
-          if (wg == 1) {
-#pragma unroll
-            for (int slot = 0; slot < 2; ++slot)
-#pragma unroll
-              for (int c = 0; c < 5; ++c) xb[(slot * 6 + 1 + c) * 128] = cx[slot].hd[c];
-          }
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (wg == 0) {
-#pragma unroll
-            for (int slot = 0; slot < 2; ++slot) {
-              const int64_t gg = row_of(slot);
-              if (gg >= a.P) continue;
-              const EpiCtx& c = cx[slot];
-              float hd[5];
-#pragma unroll
-              for (int k = 0; k < 5; ++k) hd[k] = c.hd[k] + xb[(slot * 6 + 1 + k) * 128];
-              float* o = a.raw + gg * 9;
-              o[0] = sigmoid_f(c.rgb[0] + a.tbl[kTblScal + 1]), o[1] = sigmoid_f(c.rgb[1] + a.tbl[kTblScal + 2]);
-              o[2] = sigmoid_f(c.rgb[2] + a.tbl[kTblScal + 3]), o[3] = c.sig;
-              o[4] = sigmoid_f(hd[0] + a.tbl[kTblScal + 4]), o[5] = sigmoid_f(hd[1] + a.tbl[kTblScal + 5]);
-              o[6] = sigmoid_f(hd[2] + a.tbl[kTblScal + 6]);
-              o[7] = softplus_f(hd[3] + a.tbl[kTblScal + 7]), o[8] = softplus_f(hd[4] + a.tbl[kTblScal + 8]);
-            }
-          }
         }
       }
     }
@@ -699,7 +640,10 @@ namespace {
 
 // One MMA step of the streamed program.  `logical`: 0..7 trunk layer, 8 xyz_encoding_final,
 // 9 dir_encoding | transient_encoding.0 (on xyz_encoding_final), 19 the same two layers with
-// xyz_encoding_final folded in (on the trunk output), 10..12 transient_encoding.{2,4,6}.
+// xyz_encoding_final folded in (on the trunk output), 10..12 transient_encoding.{2,4,6},
+// 20 static_sigma as an N=64 step (row 0) on the trunk output, 21 the remaining heads as ONE block-structured
+// K=256, N=64 step: rows 0..4 = transient_rgb(3), transient_sigma, transient_beta on k < 128
+// (transient_encoding.6 output, panels 0..15), rows 8..10 = static_rgb on k >= 128 (dir_encoding, panels 16..31).
 struct LStep { int logical, K, N, a_panel0, kind; };
 
 // xyz_encoding_final has no activation, so W_dir*(W_f h + b_f) = (W_dir W_f) h + W_dir b_f: folding it
@@ -714,9 +658,8 @@ bool fold_final() {
 
 std::vector<LStep> build_program(bool fine) {
   std::vector<LStep> pr;
-  for (int i = 0; i < 8; ++i)
-    pr.push_back({i, i == 0 ? 64 : (i == 4 ? 320 : 256), 256, i == 0 ? 32 : 0,
-                  i < 7 ? tc::EPI_HIDDEN : (fine ? tc::EPI_HIDDEN_SIGMA : tc::EPI_SIGMA_ONLY)});
+  for (int i = 0; i < 8; ++i) pr.push_back({i, i == 0 ? 64 : (i == 4 ? 320 : 256), 256, i == 0 ? 32 : 0, tc::EPI_HIDDEN});
+  pr.push_back({20, 256, 64, 0, tc::EPI_SIGMA});
   if (!fine) return pr;
   if (fold_final()) {
     pr.push_back({19, 256, 256, 0, tc::EPI_DT});
@@ -724,7 +667,8 @@ std::vector<LStep> build_program(bool fine) {
     pr.push_back({8, 256, 256, 0, tc::EPI_FINAL});
     pr.push_back({9, 256, 256, 0, tc::EPI_DT});
   }
-  for (int i = 0; i < 3; ++i) pr.push_back({10 + i, 128, 128, 0, i < 2 ? tc::EPI_T : tc::EPI_T_LAST});
+  for (int i = 0; i < 3; ++i) pr.push_back({10 + i, 128, 128, 0, tc::EPI_T});
+  pr.push_back({21, 256, 64, 0, tc::EPI_HEADS});
   return pr;
 }
 }  // namespace
@@ -775,6 +719,16 @@ int pack_tc_weights(DfbNerf* n, int which, const std::vector<std::vector<float>>
     if (lg == 8) return P[16][(size_t)nn * W + k];  // xyz_encoding_final
     if (lg == 9) return (float)wdt(nn, k);
     if (lg == 19) return folded_w[(size_t)nn * W + k];
+    if (lg == 20) return nn == 0 ? P[20][k] : 0.f;  // static_sigma
+    if (lg == 21) {
+      if (k < H) {
+        if (nn < 3) return P[34][(size_t)nn * H + k];  // transient_rgb
+        if (nn == 3) return P[32][k];                  // transient_sigma
+        if (nn == 4) return P[36][k];                  // transient_beta
+        return 0.f;
+      }
+      return (nn >= 8 && nn < 11) ? P[22][(size_t)(nn - 8) * H + (k - H)] : 0.f;  // static_rgb
+    }
     return P[26 + 2 * (lg - 10)][(size_t)nn * H + k];  // transient_encoding.{2,4,6}
   };
   for (int cg = 1; cg <= 2; ++cg) {
@@ -814,16 +768,11 @@ int pack_tc_weights(DfbNerf* n, int which, const std::vector<std::vector<float>>
     if (lg < 8) memcpy(dst, P[2 * lg + 1].data(), 256 * sizeof(float));
     else if (lg == 8) memcpy(dst, P[17].data(), 256 * sizeof(float));
     else if (lg == 19) memcpy(dst, folded_b.data(), 256 * sizeof(float));
-    else if (lg >= 10) memcpy(dst, P[27 + 2 * (lg - 10)].data(), H * sizeof(float));
+    else if (lg >= 10 && lg <= 12) memcpy(dst, P[27 + 2 * (lg - 10)].data(), H * sizeof(float));
     // lg == 9: the bias of dir_encoding / transient_encoding.0 is part of the per-ray bias
   }
-  memcpy(tb + tc::kTblSigmaW, P[20].data(), 256 * sizeof(float));
   tb[tc::kTblScal] = P[21][0];
   if (fine) {
-    memcpy(tb + tc::kTblRgbW, P[22].data(), 3 * H * sizeof(float));
-    memcpy(tb + tc::kTblTrgbW, P[34].data(), 3 * H * sizeof(float));
-    memcpy(tb + tc::kTblTsigW, P[32].data(), H * sizeof(float));
-    memcpy(tb + tc::kTblTbetaW, P[36].data(), H * sizeof(float));
     for (int c = 0; c < 3; ++c) tb[tc::kTblScal + 1 + c] = P[23][c], tb[tc::kTblScal + 4 + c] = P[35][c];
     tb[tc::kTblScal + 7] = P[33][0], tb[tc::kTblScal + 8] = P[37][0];
   }
@@ -831,7 +780,6 @@ int pack_tc_weights(DfbNerf* n, int which, const std::vector<std::vector<float>>
 }
 
 static int* g_error_flag = nullptr;
-static float* g_xchg = nullptr;
 
 // 3-D tensor map over a packed weight image: [n_img][64][128 x u16], one box = one 16 KB image.
 static int make_weight_tmap(void* base, size_t bytes, CUtensorMap* out) {
@@ -905,8 +853,6 @@ int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const
   }
   a.rayrec = rayrec, a.z = z, a.raybias = raybias, a.S = S, a.P = n_rays * S, a.raw = raw;
   a.error_flag = g_error_flag;
-  if (!g_xchg) DFB_CHECK_CUDA(cudaMalloc(&g_xchg, (size_t)1024 * 2 * 6 * 128 * sizeof(float)));
-  a.xchg = g_xchg;
 #ifdef DFB_TC_PROF
   if (!g_prof) {
     DFB_CHECK_CUDA(cudaMalloc(&g_prof, 512 * 16 * sizeof(unsigned long long)));
