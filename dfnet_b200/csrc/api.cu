@@ -200,7 +200,10 @@ extern "C" int dfb_render_fwd(DfbNerf* n, const DfbRenderCfg* c, const float* ra
     const float* z_all = sa.z_vals;
     // ---- fine network (rendering.py:307-316) -------------------------------------------------
     float* rb_f = P(L.rb_f);
-    rc = launch_raybias(pa.extra, pa.n_extra, nr, n->net[1], true, rb_f, n->net[1].n_dt, st);
+    // tcgen05 path: the per-ray bias carries the step's constant bias and is stored as packed 16-bit pairs
+    const bool tc_f = c->mma_kind != DFB_MMA_FP32_SIMT && tc_supported(n, 1, MLP_FULL);
+    rc = launch_raybias(pa.extra, pa.n_extra, nr, n->net[1], true, rb_f, n->net[1].n_dt, st,
+                        tc_f ? n->net[1].tc_dtbias_dev : nullptr, tc_f ? (c->mma_kind == DFB_MMA_F16 ? 1 : 2) : 0);
     if (rc) return rc;
     float* raw_f = ex && ex->raw ? ex->raw + r0 * S * 9 : P(L.raw_f);
     rc = run_mlp(n, c, 1, MLP_FULL, rayrec, z_all, rb_f, nr, S, raw_f, st);

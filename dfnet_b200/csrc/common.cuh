@@ -82,6 +82,7 @@ struct NetPack {
   void* blob16[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [fp16|bf16][cta_group 1|2 chunking]
   size_t blob16_bytes = 0;
   std::vector<float> tc_tbl;  // host copy of the bias / head-weight table passed as kernel parameter
+  float* tc_dtbias_dev = nullptr;  // [W] constant bias of the dir|transient.0 step (W_dt b_final when folded), added by k_raybias
 
   // ---- tcgen05 backward layout (fine 8x256 network): the 26-step image of mlp_tc_bwd.cu ------
   void* blob16b[2] = {nullptr, nullptr};  // [fp16|bf16]
@@ -179,8 +180,10 @@ struct SampleArgs {
 };
 
 int launch_prep(const PrepArgs& a, cudaStream_t st);
+// add_bias [n_rb] (nullable): constant added to every row; pack_kind: 0 fp32 rows, 1 / 2 = fp16 / bf16 pairs
+// packed into the first n_rb/2 words of each row (what the tcgen05 forward kernel consumes)
 int launch_raybias(const float* extra, int ld, int64_t N, const NetPack& np, bool with_transient, float* rb,
-                   int rb_ld, cudaStream_t st);
+                   int rb_ld, cudaStream_t st, const float* add_bias = nullptr, int pack_kind = 0);
 int launch_composite(const CompositeArgs& a, cudaStream_t st);
 int launch_sample(const SampleArgs& a, cudaStream_t st);
 

@@ -148,24 +148,25 @@ __device__ __forceinline__ void epi_block(const uint32_t (&v)[32], const TcArgs&
     for (int q = 0; q < 4; ++q) st_shared_v4(dst + q * kPanelBytes, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
     return;
   }
-  // EPI_DT: dir_encoding | transient_encoding.0 with the per-ray bias (global, fp32) + the step's constant bias
-  // (non-zero when xyz_encoding_final is folded in).  transient_encoding.0 (columns 128..255) goes to panels
-  // 0..15 (input of transient_encoding.2), dir_encoding (columns 0..127) to panels 16..31 (input of static_rgb).
-  float x[32];
-  const float4* b4 = reinterpret_cast<const float4*>(rb + cb * 32);
+  // EPI_DT: dir_encoding | transient_encoding.0.  The per-ray bias (view direction, appearance / transient codes
+  // and the step's constant bias, k_raybias) arrives as packed 16-bit pairs in global memory: same packed
+  // HFMA2.RELU as above.  transient_encoding.0 (columns 128..255) goes to panels 0..15 (input of
+  // transient_encoding.2), dir_encoding (columns 0..127) to panels 16..31 (input of static_rgb).
+  const uint4* b4 = reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(rb) + cb * 16);
+  uint32_t pk[16];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const float4 bb = __ldg(b4 + q);
-    x[4 * q + 0] = fmaxf(__uint_as_float(v[4 * q + 0]) + (bb.x + a.tbl[bias_off + cb * 32 + 4 * q + 0]), 0.f);
-    x[4 * q + 1] = fmaxf(__uint_as_float(v[4 * q + 1]) + (bb.y + a.tbl[bias_off + cb * 32 + 4 * q + 1]), 0.f);
-    x[4 * q + 2] = fmaxf(__uint_as_float(v[4 * q + 2]) + (bb.z + a.tbl[bias_off + cb * 32 + 4 * q + 2]), 0.f);
-    x[4 * q + 3] = fmaxf(__uint_as_float(v[4 * q + 3]) + (bb.w + a.tbl[bias_off + cb * 32 + 4 * q + 3]), 0.f);
+  for (int q4 = 0; q4 < 4; ++q4) {
+    const uint4 bb = __ldg(b4 + q4);
+    const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int q = 4 * q4 + e;
+      pk[q] = add_relu2<T>(pack2<T>(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), bw[e]);
+    }
   }
   const uint32_t dst = h_row + (uint32_t)(((cb + 4) & 7) * 4) * kPanelBytes;
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
-    st_shared_v4(dst + q * kPanelBytes, pack2<T>(x[8 * q], x[8 * q + 1]), pack2<T>(x[8 * q + 2], x[8 * q + 3]),
-                 pack2<T>(x[8 * q + 4], x[8 * q + 5]), pack2<T>(x[8 * q + 6], x[8 * q + 7]));
+  for (int q = 0; q < 4; ++q) st_shared_v4(dst + q * kPanelBytes, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
 }
 
 // Blocks [cb0, cb1) of a step (cb1 - cb0 even): software-pipelined TMEM reads, block cb+1 is in
@@ -772,6 +773,14 @@ int pack_tc_weights(DfbNerf* n, int which, const std::vector<std::vector<float>>
     // lg == 9: the bias of dir_encoding / transient_encoding.0 is part of the per-ray bias
   }
   tb[tc::kTblScal] = P[21][0];
+  if (fine) {
+    std::vector<float> dtb(W, 0.f);
+    if (fold_final()) dtb = folded_b;
+    if (np.tc_dtbias_dev) cudaFree(np.tc_dtbias_dev);
+    np.tc_dtbias_dev = nullptr;
+    DFB_CHECK_CUDA(cudaMalloc(&np.tc_dtbias_dev, W * sizeof(float)));
+    DFB_CHECK_CUDA(cudaMemcpy(np.tc_dtbias_dev, dtb.data(), W * sizeof(float), cudaMemcpyHostToDevice));
+  }
   if (fine) {
     for (int c = 0; c < 3; ++c) tb[tc::kTblScal + 1 + c] = P[23][c], tb[tc::kTblScal + 4 + c] = P[35][c];
     tb[tc::kTblScal + 7] = P[33][0], tb[tc::kTblScal + 8] = P[37][0];

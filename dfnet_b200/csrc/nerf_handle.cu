@@ -83,6 +83,7 @@ extern "C" void dfb_nerf_destroy(DfbNerf* n) {
         if (n->net[i].blob16[k][g]) cudaFree(n->net[i].blob16[k][g]);
     for (int k = 0; k < 2; ++k)
       if (n->net[i].blob16b[k]) cudaFree(n->net[i].blob16b[k]);
+    if (n->net[i].tc_dtbias_dev) cudaFree(n->net[i].tc_dtbias_dev);
   }
   if (n->emb_a) cudaFree(n->emb_a);
   if (n->emb_t) cudaFree(n->emb_t);

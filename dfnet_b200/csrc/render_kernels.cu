@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(kPrepThreads) k_prep_rays(PrepArgs a) {
 __global__ void k_raybias(const float* __restrict__ extra, int ld, int64_t N, int nd, int nt, int Hh,
                           const float* __restrict__ dirx_w, const float* __restrict__ dirx_b,
                           const float* __restrict__ tx_w, const float* __restrict__ tx_b, float* __restrict__ rb,
-                          int n_rb, int rb_ld) {
+                          int n_rb, int rb_ld, const float* __restrict__ add_bias, int pack_kind) {
   // block = n_rb threads (one output column each), 8 rays per block
   extern __shared__ float sm[];
   const int64_t r0 = (int64_t)blockIdx.x * 8;
@@ -120,8 +120,7 @@ __global__ void k_raybias(const float* __restrict__ extra, int ld, int64_t N, in
   const int ne = nd + nt;
   for (int i = threadIdx.x; i < nloc * ne; i += blockDim.x) sm[i] = extra[(r0 + i / ne) * ld + i % ne];
   __syncthreads();
-  const int n = threadIdx.x;
-  if (n >= n_rb) return;
+  const int n = min((int)threadIdx.x, n_rb - 1);
   const bool tr = n >= Hh;
   const int col = tr ? n - Hh : n;
   const float* w = tr ? tx_w : dirx_w;
@@ -130,7 +129,21 @@ __global__ void k_raybias(const float* __restrict__ extra, int ld, int64_t N, in
   for (int rl = 0; rl < nloc; ++rl) {
     float acc = 0.f;
     for (int k = 0; k < kn; ++k) acc = fmaf(sm[rl * ne + k0 + k], w[k * Hh + col], acc);
-    rb[(r0 + rl) * rb_ld + n] = acc + b;
+    float v = acc + b;
+    if (add_bias) v += add_bias[n];  // constant part of the consuming layer's bias (tcgen05 path, see mlp_tc.cu)
+    if (pack_kind == 0) {
+      if ((int)threadIdx.x < n_rb) rb[(r0 + rl) * rb_ld + n] = v;
+    } else {
+      // packed 16-bit pairs {column 2j, column 2j+1} in word j of the row: the tcgen05 epilogue adds them with
+      // one HFMA2.RELU per column pair, exactly like the constant biases of the hidden layers
+      const float hi = __shfl_down_sync(0xffffffffu, v, 1);
+      if ((threadIdx.x & 1) == 0 && (int)threadIdx.x < n_rb) {
+        uint32_t w16;
+        if (pack_kind == 1) { __half2 h = __floats2half2_rn(v, hi); w16 = *reinterpret_cast<uint32_t*>(&h); }
+        else { __nv_bfloat162 h = __floats2bfloat162_rn(v, hi); w16 = *reinterpret_cast<uint32_t*>(&h); }
+        reinterpret_cast<uint32_t*>(rb + (r0 + rl) * rb_ld)[n >> 1] = w16;
+      }
+    }
   }
 }
 
@@ -383,7 +396,7 @@ int launch_prep(const PrepArgs& a, cudaStream_t st) {
 }
 
 int launch_raybias(const float* extra, int ld, int64_t N, const NetPack& np, bool with_transient, float* rb,
-                   int rb_ld, cudaStream_t st) {
+                   int rb_ld, cudaStream_t st, const float* add_bias, int pack_kind) {
   const int Hh = np.W / 2, nd = np.in_dir + np.a_dim, nt = with_transient ? np.t_dim : 0;
   const int n_rb = with_transient ? 2 * Hh : Hh;
   const int blocks = (int)((N + 7) / 8);
@@ -392,7 +405,7 @@ int launch_raybias(const float* extra, int ld, int64_t N, const NetPack& np, boo
   const float* b = np.blob32;
   k_raybias<<<blocks, threads, smem, st>>>(extra, ld, N, nd, nt, Hh, b + np.dirx_w, b + np.dirx_b,
                                             with_transient ? b + np.tx_w : nullptr,
-                                            with_transient ? b + np.tx_b : nullptr, rb, n_rb, rb_ld);
+                                            with_transient ? b + np.tx_b : nullptr, rb, n_rb, rb_ld, add_bias, pack_kind);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }
