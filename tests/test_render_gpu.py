@@ -166,6 +166,22 @@ def test_render_cfg2_shape(ops, golden, mma, tol, flip_tol):
     assert (np.diff(z, axis=-1) >= 0).all()
 
 
+@pytest.mark.parametrize("mma,tol", [("f16", 1e-3), ("bf16", 1e-2)])
+def test_render_cfg2_shape_one_cta_kernel(ops, golden, monkeypatch, mma, tol):
+    """The 1-CTA variant of the tcgen05 kernel (DFB_TC_CTA_GROUP=1; the default is the cta_group::2 pair kernel):
+    same gates as above, and both variants agree to rounding."""
+    mods, _ = synthetic_nets(8, 256)
+    h = ops.NerfHandle(*to_dev(mods))
+    kw = dict(c2w=T(golden["e2e_b_c2w"]), H=6, W=8, focal=7.3125, near=0.0, far=2.5, hist=T(golden["hist"]), mma=mma)
+    pair = h.render(64, 128, True, **kw)
+    monkeypatch.setenv("DFB_TC_CTA_GROUP", "1")
+    one = h.render(64, 128, True, **kw)
+    torch.cuda.synchronize()
+    for k, g in (("rgb", "e2e_b_rgb"), ("disp", "e2e_b_disp"), ("acc", "e2e_b_acc")):
+        assert rel_err(one[k].cpu().numpy().reshape(golden[g].shape), golden[g]) < tol, k
+        assert rel_err(one[k].cpu().numpy(), pair[k].cpu().numpy()) < tol, k
+
+
 def test_render_train_mode_extras_fp32(golden):
     from dfnet_b200 import rendering
     mods, _ = synthetic_nets(8, 64)
