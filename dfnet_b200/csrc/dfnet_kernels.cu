@@ -315,9 +315,17 @@ extern "C" int dfb_dfnet_load_ex(DfbDfnet* d, const float* const* params, const 
   DFB_REQUIRE(numel[o] == 12 * 512 && numel[o + 1] == 12, DFB_ERR_INVALID, "fc_pose has the wrong size");
   if (!d->fc_w) DFB_CHECK_CUDA(cudaMalloc(&d->fc_w, 12 * 512 * 4));
   if (!d->fc_b) DFB_CHECK_CUDA(cudaMalloc(&d->fc_b, 12 * 4));
-  DFB_CHECK_CUDA(cudaMemcpy(d->fc_w, params[o], 12 * 512 * 4, cudaMemcpyDefault));
-  DFB_CHECK_CUDA(cudaMemcpy(d->fc_b, params[o + 1], 12 * 4, cudaMemcpyDefault));
-  DFB_CHECK_CUDA(cudaStreamSynchronize(nullptr));
+  // flags bit 1: the caller's work is ordered on the legacy default stream (the stream every packing kernel above
+  // ran on) and the sources stay alive in stream order: no host synchronisation, so a training loop that reloads
+  // the pose regressor every step does not drain the GPU here
+  if (flags & 2) {
+    DFB_CHECK_CUDA(cudaMemcpyAsync(d->fc_w, params[o], 12 * 512 * 4, cudaMemcpyDefault, nullptr));
+    DFB_CHECK_CUDA(cudaMemcpyAsync(d->fc_b, params[o + 1], 12 * 4, cudaMemcpyDefault, nullptr));
+  } else {
+    DFB_CHECK_CUDA(cudaMemcpy(d->fc_w, params[o], 12 * 512 * 4, cudaMemcpyDefault));
+    DFB_CHECK_CUDA(cudaMemcpy(d->fc_b, params[o + 1], 12 * 4, cudaMemcpyDefault));
+    DFB_CHECK_CUDA(cudaStreamSynchronize(nullptr));
+  }
   d->loaded = true;
   return DFB_OK;
 }

@@ -54,7 +54,12 @@ class _DfnetHandle:
         self.n_levels = len(module.hypercolumn_layers)
 
     def refresh(self, module, train=False):
-        sd = module.state_dict()
+        # state_dict() walks and renames every tensor (~ms): cache the tensors themselves, keyed on their identity,
+        # and poll their versions
+        key = (id(module), tuple(id(t) for t in module.parameters()), tuple(id(t) for t in module.buffers()))
+        if getattr(self, "_sd_key", None) != key:
+            self._sd, self._sd_key = dict(module.state_dict(keep_vars=True)), key
+        sd = self._sd
         v = [(t.data_ptr(), t._version) for t in sd.values()] + [bool(train)]
         if v[:-1] == (self._versions or [None])[:-1] and (self._versions[-1] or not train):
             return
@@ -71,7 +76,9 @@ class _DfnetHandle:
         ptrs = (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
         numel = (C.c_int64 * len(ts))(*[t.numel() for t in ts])
         eps = module.adaptation_layers.adapt_layer_0[3].eps
-        check(lib.dfb_dfnet_load_ex(self._h, ptrs, numel, len(ts), eps, 1 if train else 0))
+        # bit 1: everything is ordered on the legacy default stream -> the library skips its host synchronisation
+        on_default = all(t.is_cuda for t in ts) and torch.cuda.current_stream(ts[0].device).cuda_stream == 0
+        check(lib.dfb_dfnet_load_ex(self._h, ptrs, numel, len(ts), eps, (1 if train else 0) | (2 if on_default else 0)))
         self._versions = v
         self.n_params = len(ts)
 

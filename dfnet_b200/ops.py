@@ -59,10 +59,12 @@ class NerfHandle:
         self.refresh(force=True)
 
     def _param_versions(self):
+        # polled on every render: iterate the tensors directly (state_dict() renames and detaches every one of them)
         v = []
         for m in self._mods:
             if m is not None:
-                v += [(p.data_ptr(), p._version) for p in m.state_dict().values()]
+                v += [(p.data_ptr(), p._version) for p in m.parameters()]
+                v += [(p.data_ptr(), p._version) for p in m.buffers()]
         return v
 
     def refresh(self, force=False):
