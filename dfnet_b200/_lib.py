@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("DFB_LIB_PATH", os.path.join(_HERE, "libdfnet_b200.so"
 SYMBOLS = [
     "dfb_last_error", "dfb_version", "dfb_device_ok", "dfb_linspace_f32", "dfb_nerf_create", "dfb_nerf_destroy",
     "dfb_nerf_load", "dfb_nerf_set_embeddings", "dfb_nerfw_forward", "dfb_render_workspace_bytes",
-    "dfb_render_fwd", "dfb_render_image_host", "dfb_render_bwd", "dfb_render_bwd_mma", "dfb_render_bwd_workspace_bytes", "dfb_sample_pdf", "dfb_raw2outputs", "dfb_get_rays",
+    "dfb_render_fwd", "dfb_render_image_host", "dfb_render_bwd", "dfb_render_bwd_mma", "dfb_render_bwd_saved", "dfb_render_bwd_workspace_bytes", "dfb_sample_pdf", "dfb_raw2outputs", "dfb_get_rays",
     "dfb_launch_count", "dfb_profile_enable", "dfb_profile_read", "dfb_debug_umma_gemm", "dfb_debug_umma_gemm_mn", "dfb_debug_tc_prof", "dfb_debug_bwd_masks", "dfb_debug_umma_rate", "dfb_debug_tmem_rate", "dfb_conv_create", "dfb_conv_destroy", "dfb_conv_fwd",
     "dfb_dfnet_create", "dfb_dfnet_destroy", "dfb_dfnet_load", "dfb_dfnet_workspace_bytes", "dfb_dfnet_fwd",
     "dfb_cosine_loss", "dfb_triplet_loss", "dfb_mse", "dfb_resize_bicubic", "dfb_resize_bilinear_ac",
@@ -41,7 +41,7 @@ class RenderCfg(C.Structure):
 class RenderExtras(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in
                 ("rgb0", "disp0", "acc0", "z_std", "beta", "transient_sigmas", "raw", "weights_coarse", "z_vals",
-                 "z_samples", "inds", "depth")]
+                 "z_samples", "inds", "depth", "relu_masks")]
 
 
 class DfbError(RuntimeError):
@@ -76,6 +76,7 @@ def _load():
     lib.dfb_render_bwd_workspace_bytes.argtypes = [vp, i64, i32, C.POINTER(C.c_size_t)]
     lib.dfb_render_bwd.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
     lib.dfb_debug_bwd_masks.argtypes = [vp, vp, vp]
+    lib.dfb_render_bwd_saved.argtypes = [vp, i32, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
     lib.dfb_render_bwd_mma.argtypes = [vp, i32, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
     lib.dfb_sample_pdf.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp, vp]
     lib.dfb_raw2outputs.argtypes = [vp, vp, i64, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp, vp]

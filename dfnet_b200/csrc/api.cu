@@ -61,23 +61,24 @@ bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
 
 int run_mlp_inner(const DfbNerf* n, const DfbRenderCfg* c, int which, int mode, const float* rayrec, const float* z,
-                  const float* rb, int64_t rays, int S, float* raw, cudaStream_t st) {
+                  const float* rb, int64_t rays, int S, float* raw, cudaStream_t st, uint32_t* masks) {
   // The tcgen05 kernel covers the 8x256 networks (sigma-only coarse pass and full fine pass); every
   // other shape or mode (other widths, the train-mode coarse pass) runs on the fp32 CUDA kernel.
   if (c->mma_kind != DFB_MMA_FP32_SIMT && tc_supported(n, which, mode))
-    return launch_mlp_tc_rays(n, which, mode, c->mma_kind, rayrec, z, rb, rays, S, raw, st);
+    return launch_mlp_tc_rays(n, which, mode, c->mma_kind, rayrec, z, rb, rays, S, raw, st, masks);
+  DFB_REQUIRE(!masks, DFB_ERR_UNSUPPORTED, "relu_masks are an output of the tcgen05 path (8x256 fine network, mma f16 / bf16)");
   return launch_mlp_simt_rays(n, which, mode, rayrec, z, rb, rays, S, raw, st);
 }
 
 int run_mlp(const DfbNerf* n, const DfbRenderCfg* c, int which, int mode, const float* rayrec, const float* z,
-            const float* rb, int64_t rays, int S, float* raw, cudaStream_t st) {
-  if (!g_prof_on) return run_mlp_inner(n, c, which, mode, rayrec, z, rb, rays, S, raw, st);
+            const float* rb, int64_t rays, int S, float* raw, cudaStream_t st, uint32_t* masks = nullptr) {
+  if (!g_prof_on) return run_mlp_inner(n, c, which, mode, rayrec, z, rb, rays, S, raw, st, masks);
   ProfRec r;
   r.which = which;
   DFB_CHECK_CUDA(cudaEventCreate(&r.a));
   DFB_CHECK_CUDA(cudaEventCreate(&r.b));
   DFB_CHECK_CUDA(cudaEventRecord(r.a, st));
-  int rc = run_mlp_inner(n, c, which, mode, rayrec, z, rb, rays, S, raw, st);
+  int rc = run_mlp_inner(n, c, which, mode, rayrec, z, rb, rays, S, raw, st, masks);
   DFB_CHECK_CUDA(cudaEventRecord(r.b, st));
   g_prof.push_back(r);
   return rc;
@@ -206,7 +207,12 @@ extern "C" int dfb_render_fwd(DfbNerf* n, const DfbRenderCfg* c, const float* ra
                         tc_f ? n->net[1].tc_dtbias_dev : nullptr, tc_f ? (c->mma_kind == DFB_MMA_F16 ? 1 : 2) : 0);
     if (rc) return rc;
     float* raw_f = ex && ex->raw ? ex->raw + r0 * S * 9 : P(L.raw_f);
-    rc = run_mlp(n, c, 1, MLP_FULL, rayrec, z_all, rb_f, nr, S, raw_f, st);
+    uint32_t* masks = nullptr;
+    if (ex && ex->relu_masks) {
+      DFB_REQUIRE((r0 * S) % 128 == 0, DFB_ERR_INVALID, "relu_masks: chunk start not aligned to a 128-sample tile");
+      masks = ex->relu_masks + (size_t)(r0 * S / 128) * kReluMaskWordsPerTile;
+    }
+    rc = run_mlp(n, c, 1, MLP_FULL, rayrec, z_all, rb_f, nr, S, raw_f, st, masks);
     if (rc) return rc;
     CompositeArgs cf = {};
     cf.raw = raw_f, cf.z = z_all, cf.N = nr, cf.S = S, cf.C = 9, cf.typ_fine = 1, cf.test_time = c->test_time;
@@ -354,7 +360,7 @@ extern "C" int dfb_profile_read(double* coarse_ms, double* fine_ms, int64_t* coa
 namespace dfb {
 int launch_render_bwd(const DfbNerf* nerf, const float* rayrec, const float* z, const float* raybias, const float* raw,
                       const float* g_rgb, int64_t n_rays, int S, float* g_raw, float* g_samp, float* g_o, float* g_d,
-                      float* g_vd, int kind, cudaStream_t st);
+                      float* g_vd, int kind, cudaStream_t st, const uint32_t* saved_masks);
 }
 
 namespace dfb {
@@ -407,6 +413,15 @@ extern "C" int dfb_render_bwd(DfbNerf* n, const float* rays, int64_t N, int S, c
 extern "C" int dfb_render_bwd_mma(DfbNerf* n, int mma_kind, const float* rays, int64_t N, int S, const float* z_vals,
                                   const float* raw, const float* g_rgb, float* g_rays_o, float* g_rays_d, float* g_viewdirs,
                                   void* ws, size_t ws_bytes, void* stream) {
+  return dfb_render_bwd_saved(n, mma_kind, rays, N, S, z_vals, raw, nullptr, g_rgb, g_rays_o, g_rays_d, g_viewdirs, ws, ws_bytes,
+                              stream);
+}
+
+extern "C" int dfb_render_bwd_saved(DfbNerf* n, int mma_kind, const float* rays, int64_t N, int S, const float* z_vals,
+                                    const float* raw, const uint32_t* relu_masks, const float* g_rgb, float* g_rays_o,
+                                    float* g_rays_d, float* g_viewdirs, void* ws, size_t ws_bytes, void* stream) {
+  DFB_REQUIRE(!relu_masks || (mma_kind != DFB_MMA_FP32_SIMT && n && tc_bwd_supported(n)), DFB_ERR_UNSUPPORTED,
+              "saved ReLU masks need the tcgen05 backward (8x256 fine network, mma f16 / bf16)");
   DFB_REQUIRE(mma_kind == DFB_MMA_FP32_SIMT || mma_kind == DFB_MMA_F16 || mma_kind == DFB_MMA_BF16, DFB_ERR_INVALID, "bad mma kind");
   DFB_REQUIRE(n && rays && z_vals && raw && g_rgb && g_rays_o && g_rays_d && g_viewdirs, DFB_ERR_INVALID, "null argument");
   DFB_REQUIRE(n->desc.has_fine && n->net[1].loaded && n->has_emb, DFB_ERR_INVALID, "fine network / embeddings not loaded");
@@ -432,7 +447,8 @@ extern "C" int dfb_render_bwd_mma(DfbNerf* n, int mma_kind, const float* rays, i
     rc = launch_raybias(pa.extra, n_extra, nr, n->net[1], true, P(L.rb), n->net[1].n_dt, st);
     if (rc) return rc;
     rc = launch_render_bwd(n, P(L.rayrec), z_vals + r0 * S, P(L.rb), raw + r0 * S * 9, g_rgb + r0 * 3, nr, S, P(L.g_raw),
-                           P(L.g_samp), g_rays_o + r0 * 3, g_rays_d + r0 * 3, g_viewdirs + r0 * 3, mma_kind, st);
+                           P(L.g_samp), g_rays_o + r0 * 3, g_rays_d + r0 * 3, g_viewdirs + r0 * 3, mma_kind, st,
+                           relu_masks ? relu_masks + (size_t)(r0 * S / 128) * kReluMaskWordsPerTile : nullptr);
     if (rc) return rc;
   }
   return DFB_OK;

@@ -43,6 +43,7 @@ void count_launch(int n = 1);
   } while (0)
 
 constexpr int kRayRec = 12;  // o3 d3 near far vd3 pad
+constexpr size_t kReluMaskWordsPerTile = DFB_RELU_MASK_WORDS_PER_TILE;
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
@@ -116,15 +117,19 @@ int launch_mlp_simt_rays(const DfbNerf* nerf, int which, int mode, const float* 
 int launch_mlp_simt_embedded(const DfbNerf* nerf, int which, int mode, const float* x, int64_t P, float* out,
                              cudaStream_t st);
 // tcgen05 MLP (W == 256).  kind: DFB_MMA_F16 / DFB_MMA_BF16.
+// masks (nullable, fine network only): ReLU masks for the tcgen05 backward, see TcArgs::masks in mlp_tc.cu
 int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const float* rayrec, const float* z,
-                       const float* raybias, int64_t n_rays, int S, float* raw, cudaStream_t st);
+                       const float* raybias, int64_t n_rays, int S, float* raw, cudaStream_t st,
+                       uint32_t* masks = nullptr);
 bool tc_supported(const DfbNerf* nerf, int which, int mode);
 int pack_tc_weights(DfbNerf* nerf, int which, const std::vector<std::vector<float>>& P);
 // tcgen05 backward of the fine network w.r.t. its inputs (mlp_tc_bwd.cu)
 int pack_tc_bwd_weights(DfbNerf* nerf, int which, const std::vector<std::vector<float>>& P);
 bool tc_bwd_supported(const DfbNerf* nerf);
+// saved_masks (nullable): relu_masks of the training forward for these rays -> no forward recompute
 int launch_mlp_tc_bwd(const DfbNerf* nerf, int kind, const float* rayrec, const float* z, const float* raybias,
-                      const float* raw, const float* g_raw, int64_t n_rays, int S, float* g_samp, cudaStream_t st);
+                      const float* raw, const float* g_raw, int64_t n_rays, int S, float* g_samp, cudaStream_t st,
+                      const uint32_t* saved_masks = nullptr);
 
 
 // ---- argument blocks of the non-MLP render kernels (render_kernels.cu) ----------------

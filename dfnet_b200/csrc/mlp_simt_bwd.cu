@@ -417,7 +417,7 @@ static int launch_bwd_w(const BwdArgs& a, cudaStream_t st) {
 
 int launch_render_bwd(const DfbNerf* nerf, const float* rayrec, const float* z, const float* raybias, const float* raw,
                       const float* g_rgb, int64_t n_rays, int S, float* g_raw, float* g_samp, float* g_o, float* g_d,
-                      float* g_vd, int kind, cudaStream_t st) {
+                      float* g_vd, int kind, cudaStream_t st, const uint32_t* saved_masks) {
   const NetPack& np = nerf->net[1];
   DFB_REQUIRE(np.loaded && np.fine && np.blob32b, DFB_ERR_INVALID, "fine network not loaded");
   DFB_REQUIRE((size_t)4 * 3 * S * sizeof(float) <= 48 * 1024, DFB_ERR_UNSUPPORTED, "too many samples per ray for the backward");
@@ -425,12 +425,13 @@ int launch_render_bwd(const DfbNerf* nerf, const float* rayrec, const float* z, 
   DFB_LAUNCH_CHECK();
   if (kind != DFB_MMA_FP32_SIMT && tc_bwd_supported(nerf)) {
     // 8x256 network: forward recompute + input-gradient chain on tcgen05 (mlp_tc_bwd.cu)
-    int rc = launch_mlp_tc_bwd(nerf, kind, rayrec, z, raybias, raw, g_raw, n_rays, S, g_samp, st);
+    int rc = launch_mlp_tc_bwd(nerf, kind, rayrec, z, raybias, raw, g_raw, n_rays, S, g_samp, st, saved_masks);
     if (rc) return rc;
     k_ray_grad<<<(unsigned)((n_rays + 3) / 4), 128, 0, st>>>(g_samp, z, rayrec, n_rays, S, g_o, g_d, g_vd);
     DFB_LAUNCH_CHECK();
     return DFB_OK;
   }
+  DFB_REQUIRE(!saved_masks, DFB_ERR_UNSUPPORTED, "saved ReLU masks belong to the tcgen05 path");
   BwdArgs a = {};
   a.rayrec = rayrec, a.z = z, a.raybias = raybias, a.raw = raw, a.g_raw = g_raw, a.S = S, a.P = n_rays * S;
   a.D = np.D, a.skip = np.skip, a.pek = np.pek, a.in_xyz = np.in_xyz, a.blob = np.blob32, a.blobb = np.blob32b;

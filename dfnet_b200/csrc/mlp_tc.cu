@@ -90,6 +90,12 @@ struct TcArgs {
   float* raw;             // [P,1] or [P,9]
   int* error_flag;
   unsigned long long* prof;  // optional [gridDim.x][16] cycle counters (DFB_TC_PROF builds)
+  // FULL == 2 (training forward): ReLU masks of the 12 hidden layers, one bit per activation, for the tcgen05
+  // backward (mlp_tc_bwd.cu), which then skips its forward recompute.  [tile][12 layers][8 words][128 rows]
+  // uint32, tile = 128 consecutive rows of the flattened [ray][sample] array; bit 16*(c&1) + (c>>1) of word c/32
+  // = column c.  mlayer[s] = mask layer written by step s (-1: none).
+  uint32_t* masks;
+  int mlayer[kMaxSteps];
   // fp32 biases, read through the constant bank (warp-uniform addresses): bias[s][256] for every step, then
   // the head scalars {sigma_b, rgb_b[3], trgb_b[3], tsig_b, tbeta_b}
   float tbl[kTblFloats];
@@ -129,9 +135,18 @@ struct EpiCtx {
 
 // One 32-column block (columns cb*32 .. cb*32+31) of this thread's accumulator row: bias + activation and the
 // 16-bit store of the next layer's A operand.
-template <typename T, int KIND>
+template <typename T> __device__ __forceinline__ uint32_t gt0_mask2(uint32_t pk);
+template <> __device__ __forceinline__ uint32_t gt0_mask2<__half>(uint32_t pk) {
+  return __hgt2_mask(*reinterpret_cast<__half2*>(&pk), __floats2half2_rn(0.f, 0.f));
+}
+template <> __device__ __forceinline__ uint32_t gt0_mask2<__nv_bfloat16>(uint32_t pk) {
+  return __hgt2_mask(*reinterpret_cast<__nv_bfloat162*>(&pk), __floats2bfloat162_rn(0.f, 0.f));
+}
+
+// mrow (MK only): this row's mask words of the step's layer, word cb at mrow[cb * 128]
+template <typename T, int KIND, bool MK>
 __device__ __forceinline__ void epi_block(const uint32_t (&v)[32], const TcArgs& a, int bias_off, int cb,
-                                          const float* __restrict__ rb, uint32_t h_row) {
+                                          const float* __restrict__ rb, uint32_t h_row, uint32_t* mrow) {
   if (KIND == EPI_HIDDEN || KIND == EPI_T || KIND == EPI_FINAL) {
     // Plain hidden layer: round the fp32 accumulators to the 16-bit operand type first, then
     // bias + ReLU as ONE packed HFMA2.RELU per column pair (the rounding this adds is of the same
@@ -142,6 +157,12 @@ __device__ __forceinline__ void epi_block(const uint32_t (&v)[32], const TcArgs&
     for (int q = 0; q < 16; ++q) {
       const uint32_t xx = pack2<T>(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
       pk[q] = KIND == EPI_FINAL ? add2<T>(xx, a.btbl[off + q]) : add_relu2<T>(xx, a.btbl[off + q]);
+    }
+    if (MK && KIND != EPI_FINAL) {
+      uint32_t m = 0;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) m |= gt0_mask2<T>(pk[q]) & (0x00010001u << q);
+      mrow[cb * 128] = m;
     }
     const uint32_t dst = h_row + (uint32_t)(cb * 4) * kPanelBytes;
 #pragma unroll
@@ -164,6 +185,12 @@ __device__ __forceinline__ void epi_block(const uint32_t (&v)[32], const TcArgs&
       pk[q] = add_relu2<T>(pack2<T>(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), bw[e]);
     }
   }
+  if (MK) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) m |= gt0_mask2<T>(pk[q]) & (0x00010001u << q);
+    mrow[cb * 128] = m;
+  }
   const uint32_t dst = h_row + (uint32_t)(((cb + 4) & 7) * 4) * kPanelBytes;
 #pragma unroll
   for (int q = 0; q < 4; ++q) st_shared_v4(dst + q * kPanelBytes, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
@@ -172,19 +199,19 @@ __device__ __forceinline__ void epi_block(const uint32_t (&v)[32], const TcArgs&
 // Blocks [cb0, cb1) of a step (cb1 - cb0 even): software-pipelined TMEM reads, block cb+1 is in
 // flight while block cb is processed.  A runtime loop (two blocks per trip) keeps the code small
 // enough for the instruction cache, which the MMA issuer shares.
-template <typename T, int KIND>
+template <typename T, int KIND, bool MK>
 __device__ __forceinline__ void epi_blocks(uint32_t t_row, uint32_t h_row, const TcArgs& a, int bias_off, int cb0, int cb1,
-                                           const float* rb) {
+                                           const float* rb, uint32_t* mrow) {
   uint32_t v0[32], v1[32];
   tmem_ld32(t_row + cb0 * 32, v0);
 #pragma unroll 1
   for (int cb = cb0; cb < cb1; cb += 2) {
     tmem_ld_wait(v0);
     tmem_ld32(t_row + (cb + 1) * 32, v1);
-    epi_block<T, KIND>(v0, a, bias_off, cb, rb, h_row);
+    epi_block<T, KIND, MK>(v0, a, bias_off, cb, rb, h_row, mrow);
     tmem_ld_wait(v1);
     if (cb + 2 < cb1) tmem_ld32(t_row + (cb + 2) * 32, v0);
-    epi_block<T, KIND>(v1, a, bias_off, cb + 1, rb, h_row);
+    epi_block<T, KIND, MK>(v1, a, bias_off, cb + 1, rb, h_row, mrow);
   }
 }
 
@@ -435,10 +462,13 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
           PROF_WAIT(0, mbar_wait(bar(D_FULL + slot), nd & 1, a.error_flag));
           tc_fence_after();
           const int w0 = 4 * wg, n0 = 2 * wg;  // first 32-column block of this warpgroup (256- / 128-wide steps)
-          if (kd == EPI_HIDDEN) epi_blocks<T, EPI_HIDDEN>(t_row, h_row, a, boff, w0, w0 + 4, rbs);
-          else if (kd == EPI_T) epi_blocks<T, EPI_T>(t_row, h_row, a, boff, n0, n0 + 2, rbs);
-          else if (kd == EPI_DT) epi_blocks<T, EPI_DT>(t_row, h_row, a, boff, w0, w0 + 4, rbs);
-          else if (kd == EPI_FINAL) epi_blocks<T, EPI_FINAL>(t_row, h_row, a, boff, w0, w0 + 4, rbs);
+          constexpr bool MK = FULL == 2;
+          uint32_t* mrow = nullptr;
+          if (MK) mrow = a.masks + ((((2 * p + slot) * CG + rank) * 12 + a.mlayer[s]) * 8) * 128 + r;
+          if (kd == EPI_HIDDEN) epi_blocks<T, EPI_HIDDEN, MK>(t_row, h_row, a, boff, w0, w0 + 4, rbs, mrow);
+          else if (kd == EPI_T) epi_blocks<T, EPI_T, MK>(t_row, h_row, a, boff, n0, n0 + 2, rbs, mrow);
+          else if (kd == EPI_DT) epi_blocks<T, EPI_DT, MK>(t_row, h_row, a, boff, w0, w0 + 4, rbs, mrow);
+          else if (kd == EPI_FINAL) epi_blocks<T, EPI_FINAL, false>(t_row, h_row, a, boff, w0, w0 + 4, rbs, mrow);
           else if (wg == 0) {
             // head steps: column 0 = sigma (EPI_SIGMA); columns 0..4 = transient rgb(3), sigma, beta and
             // columns 8..10 = static rgb (EPI_HEADS)
@@ -820,7 +850,7 @@ static int tc_cta_group() {  // read per launch so that tests can exercise both 
 }
 
 int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const float* rayrec, const float* z,
-                       const float* raybias, int64_t n_rays, int S, float* raw, cudaStream_t st) {
+                       const float* raybias, int64_t n_rays, int S, float* raw, cudaStream_t st, uint32_t* masks) {
   const NetPack& np = nerf->net[which];
   DFB_REQUIRE(tc_supported(nerf, which, mode), DFB_ERR_UNSUPPORTED, "network shape not supported by the tcgen05 kernel");
   DFB_REQUIRE(kind == DFB_MMA_F16 || kind == DFB_MMA_BF16, DFB_ERR_INVALID, "bad mma kind");
@@ -845,6 +875,8 @@ int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const
     a.steps[s].a_panel0 = ls.a_panel0;
     a.steps[s].chunk_base = cb;
     a.kind[s] = ls.kind;
+    // mask layers (see TcArgs::masks): trunk 0..7, dir|transient.0 = 8, transient_encoding.{2,4,6} = 9..11
+    a.mlayer[s] = ls.logical < 8 ? ls.logical : (ls.logical == 9 || ls.logical == 19) ? 8 : (ls.logical >= 10 && ls.logical <= 12) ? ls.logical - 1 : -1;
     cb += ls.K / kc;
   }
   a.wimg = np.blob16[kind == DFB_MMA_F16 ? 0 : 1][cg - 1];
@@ -858,6 +890,8 @@ int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const
     a.btbl[i] = kind == DFB_MMA_F16 ? ((uint32_t)f2h(hi) << 16 | f2h(lo)) : ((uint32_t)f2b(hi) << 16 | f2b(lo));
   }
   a.rayrec = rayrec, a.z = z, a.raybias = raybias, a.S = S, a.P = n_rays * S, a.raw = raw;
+  DFB_REQUIRE(!masks || full, DFB_ERR_INVALID, "ReLU masks are an output of the fine network only");
+  a.masks = masks;
   a.error_flag = g_error_flag;
 #ifdef DFB_TC_PROF
   if (!g_prof) {
@@ -883,9 +917,11 @@ int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const
   };
   const bool f16 = kind == DFB_MMA_F16;
   if (cg == 2) {
+    if (masks) return f16 ? launch(tc::k_mlp_tc2<__half, 2>) : launch(tc::k_mlp_tc2<__nv_bfloat16, 2>);
     if (f16) return full ? launch(tc::k_mlp_tc2<__half, 1>) : launch(tc::k_mlp_tc2<__half, 0>);
     return full ? launch(tc::k_mlp_tc2<__nv_bfloat16, 1>) : launch(tc::k_mlp_tc2<__nv_bfloat16, 0>);
   }
+  if (masks) return f16 ? launch(tc::k_mlp_tc<__half, 2>) : launch(tc::k_mlp_tc<__nv_bfloat16, 2>);
   if (f16) return full ? launch(tc::k_mlp_tc<__half, 1>) : launch(tc::k_mlp_tc<__half, 0>);
   return full ? launch(tc::k_mlp_tc<__nv_bfloat16, 1>) : launch(tc::k_mlp_tc<__nv_bfloat16, 0>);
 }

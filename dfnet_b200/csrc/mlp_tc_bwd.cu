@@ -57,7 +57,8 @@ constexpr int kScrWords = kScrJac + 2 * 2 * 64 * 128;
 
 enum Bar { W_FULL = 0, W_EMPTY = 4, D_FULL = 8, A_READY = 10, PASS_DONE = 12, PE_READY = 14, PE_FREE = 16, N_BARS = 18 };
 
-enum Kind { F_HID, F_DT, F_T3, B_MASK, B_T0, B_DIRPE, B_SIGMA, B_PESKIP, B_PE0 };
+// F_T3S: the head-derivative part of F_T3 alone (no MMA, no accumulator read): first step when the forward saved its masks
+enum Kind { F_HID, F_DT, F_T3, B_MASK, B_T0, B_DIRPE, B_SIGMA, B_PESKIP, B_PE0, F_T3S };
 
 struct Step {
   int n_chunks;    // 16 KB weight chunks (even)
@@ -79,6 +80,11 @@ struct BtArgs {
   const float* g_raw;    // [P,9]
   float* g_samp;         // [P,32]: d pts (3) | d dirPE (27) | pad
   uint32_t* scratch;     // [gridDim.x][kScrWords]
+  // ReLU masks saved by the training forward (mlp_tc.cu, FULL == 2), [tile][12][8][128]; when set, the program is the
+  // 15 backward steps only (no forward recompute) and the masks are read from here instead of the scratch
+  const uint32_t* saved_masks;
+  int n_steps;           // 26 (recompute) or 15
+  int pe_free_step;      // last step whose MMAs read the positional-encoding panels
   int S;
   int64_t P, n_pass;
   int* error_flag;
@@ -197,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_tc_bwd(const __grid_constan
     uint32_t stage = 0, phase = 0;
     const uint8_t* wimg = reinterpret_cast<const uint8_t*>(a.wimg);
     for (int64_t p = blockIdx.x; p < a.n_pass; p += gridDim.x)
-      for (int s = 0; s < kSteps; ++s) {
+      for (int s = 0; s < a.n_steps; ++s) {
         const int nch = a.steps[s].n_chunks;
         const uint8_t* src0 = wimg + (size_t)a.steps[s].chunk_base * kChunkBytes;
         for (int slot = 0; slot < 2; ++slot) {
@@ -218,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_tc_bwd(const __grid_constan
     uint32_t stage = 0, phase = 0;
     int lp = 0;
     for (int64_t p = blockIdx.x; p < a.n_pass; p += gridDim.x, ++lp)
-      for (int s = 0; s < kSteps; ++s) {
+      for (int s = 0; s < a.n_steps; ++s) {
         const int nch = a.steps[s].n_chunks, nn = a.steps[s].n;
         const uint32_t idesc = make_idesc(fmt, nn, kTileM);
         for (int slot = 0; slot < 2; ++slot) {
@@ -226,7 +232,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_tc_bwd(const __grid_constan
             if (lp > 0) mbar_wait(bar(PASS_DONE + slot), (lp - 1) & 1, a.error_flag);
             mbar_wait(bar(PE_READY + slot), lp & 1, a.error_flag);
           } else {
-            mbar_wait(bar(A_READY + slot), (lp * (kSteps - 1) + s - 1) & 1, a.error_flag);
+            mbar_wait(bar(A_READY + slot), (lp * (a.n_steps - 1) + s - 1) & 1, a.error_flag);
           }
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + slot * 256;
@@ -236,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_tc_bwd(const __grid_constan
           else issue_step<8>(stage, phase, nch, a_lo, nn, d_tmem, idesc, sW, sBar, a.error_flag);
           if (elect_one()) {
             umma_commit<1>(bar(D_FULL + slot));
-            if (s == 4) umma_commit<1>(bar(PE_FREE + slot));  // the skip layer is the last reader of the PE panels
+            if (s == a.pe_free_step) umma_commit<1>(bar(PE_FREE + slot));  // the skip layer is the last reader of the PE panels
           }
           __syncwarp();
         }
@@ -296,12 +302,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_tc_bwd(const __grid_constan
       const float* rb = a.raybias + (gc / a.S) * 256;
       asm volatile("prefetch.global.L1 [%0];" ::"l"(rb + (tid & 7) * 32));
       float gh[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, isc = 1.f;
-      for (int s = 0; s < kSteps; ++s) {
+      const uint32_t* mpass = a.saved_masks ? a.saved_masks + (size_t)(2 * p + slot) * (kMaskLayers * 8 * 128) + r : mbase;
+      for (int s = 0; s < a.n_steps; ++s) {
         mbar_wait(bar(D_FULL + slot), nd & 1, a.error_flag);
         ++nd;
         tc_fence_after();
         const int kd = a.steps[s].kind, ncb = a.steps[s].n >> 5;
-        uint32_t* mrow = mbase + a.steps[s].ml * 8 * 128;
+        uint32_t* mrow = const_cast<uint32_t*>(mpass) + a.steps[s].ml * 8 * 128;  // written only by the recompute kinds
         const int64_t mdbg = (gc * kMaskLayers + a.steps[s].ml) * 8;
         auto put_mask = [&](int cb, uint32_t m) {
           if (a.mask_out && valid) a.mask_out[mdbg + cb] = m;
@@ -345,14 +352,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_tc_bwd(const __grid_constan
               store_block<T>(h_row + (uint32_t)((cb - 4) * 4) * kPanelBytes, pk);
             }
           });
-        } else if (kd == F_T3) {
-          // last transient layer: only its mask is needed; then the head derivatives and g_T3
-          for_blocks(t_row, 4, nullptr, [&](const uint32_t (&v)[32], int cb, uint32_t) {
-            uint32_t m = 0;
+        } else if (kd == F_T3 || kd == F_T3S) {
+          // last transient layer: only its mask is needed (F_T3S: saved by the forward); then the head derivatives and g_T3
+          if (kd == F_T3)
+            for_blocks(t_row, 4, nullptr, [&](const uint32_t (&v)[32], int cb, uint32_t) {
+              uint32_t m = 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) m |= (__uint_as_float(v[j]) + a.t3_bias[cb * 32 + j]) > 0.f ? (1u << mask_pos(j)) : 0u;
-            put_mask(cb, m);
-          });
+              for (int j = 0; j < 32; ++j) m |= (__uint_as_float(v[j]) + a.t3_bias[cb * 32 + j]) > 0.f ? (1u << mask_pos(j)) : 0u;
+              put_mask(cb, m);
+            });
           float mx = 0.f;
 #pragma unroll
           for (int c = 0; c < 9; ++c) {
@@ -454,7 +462,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_tc_bwd(const __grid_constan
         }
         tc_fence_before();
         fence_proxy_async();
-        mbar_arrive(bar((s + 1 < kSteps ? A_READY : PASS_DONE) + slot));
+        mbar_arrive(bar((s + 1 < a.n_steps ? A_READY : PASS_DONE) + slot));
       }
     }
   }
@@ -606,7 +614,8 @@ static int g_bwd_scratch_ctas = 0;
 
 // Fine-network backward for P = n_rays*S samples: g_samp[P,32] from raw / g_raw (see the header comment).
 int launch_mlp_tc_bwd(const DfbNerf* nerf, int kind, const float* rayrec, const float* z, const float* raybias,
-                      const float* raw, const float* g_raw, int64_t n_rays, int S, float* g_samp, cudaStream_t st) {
+                      const float* raw, const float* g_raw, int64_t n_rays, int S, float* g_samp, cudaStream_t st,
+                      const uint32_t* saved_masks) {
   const NetPack& np = nerf->net[1];
   DFB_REQUIRE(tc_bwd_supported(nerf), DFB_ERR_UNSUPPORTED, "network shape not supported by the tcgen05 backward kernel");
   DFB_REQUIRE(kind == DFB_MMA_F16 || kind == DFB_MMA_BF16, DFB_ERR_INVALID, "bad mma kind");
@@ -617,13 +626,19 @@ int launch_mlp_tc_bwd(const DfbNerf* nerf, int kind, const float* rayrec, const 
   tcb::BtArgs a;
   memset(&a, 0, sizeof(a));
   const std::vector<BStep> prog = bwd_program();
-  int cb = 0;
+  int cb = 0, ns = 0;
   for (int s = 0; s < tcb::kSteps; ++s) {
     const BStep& ls = prog[s];
     const int kc = tcb::kChunkBytes / (ls.N * 2);
-    a.steps[s] = {ls.K / kc, ls.N, ls.a_panel0, cb, ls.kind, ls.ml, ls.brow};
+    const tcb::Step st_full = {ls.K / kc, ls.N, ls.a_panel0, cb, ls.kind, ls.ml, ls.brow};
     cb += ls.K / kc;
+    if (!saved_masks) a.steps[ns++] = st_full;
+    else if (s == 11) a.steps[ns++] = {0, 128, 0, 0, tcb::F_T3S, 11, 0};  // head derivatives only, no MMA
+    else if (s > 11) a.steps[ns++] = st_full;
   }
+  a.n_steps = ns;
+  a.pe_free_step = saved_masks ? 0 : 4;
+  a.saved_masks = saved_masks;
   a.wimg = np.blob16b[kind == DFB_MMA_F16 ? 0 : 1];
   const float* tb = np.tcb_tbl.data();
   for (int i = 0; i < 10 * 128; ++i) {

@@ -54,6 +54,9 @@ class NerfHandle:
         self._h = h
         self._fin = weakref.finalize(self, lib.dfb_nerf_destroy, h)
         self._mods = (network_fn, network_fine, embedding_a, embedding_t)
+        # shapes the tcgen05 kernels cover (forward with saved ReLU masks + mask-driven backward)
+        self.tc_train = bool(network_fine is not None and net.W == 256 and net.D == 8 and skips == [4] and
+                             net.in_channels_xyz == 63 and net.in_channels_dir == 27)
         self._versions = None
         self._ws = None
         self.refresh(force=True)
@@ -116,10 +119,10 @@ class NerfHandle:
         shapes = {"rgb0": (N, 3), "disp0": (N,), "acc0": (N,), "z_std": (N,), "beta": (N,),
                   "transient_sigmas": (N, S), "raw": (N, S, 9) if N_importance > 0 else (N, N_samples, 4),
                   "weights_coarse": (N, N_samples), "z_vals": (N, S), "z_samples": (N, max(N_importance, 1)),
-                  "inds": (N, max(N_importance, 1)), "depth": (N,)}
+                  "inds": (N, max(N_importance, 1)), "depth": (N,), "relu_masks": ((N * S + 127) // 128, 12, 8, 128)}
         ex = _lib.RenderExtras()
         for k in want:
-            out[k] = torch.empty(shapes[k], device=dev, dtype=torch.int32 if k == "inds" else torch.float32)
+            out[k] = torch.empty(shapes[k], device=dev, dtype=torch.int32 if k in ("inds", "relu_masks") else torch.float32)
             setattr(ex, k, out[k].data_ptr())
         ws, ws_bytes = self.workspace(cfg, N, dev)
         if t_rand is not None:
@@ -140,7 +143,7 @@ class NerfHandle:
                                         _ptr(rgb_host), _ptr(disp_host), _ptr(acc_host), _ptr(ws), ws.numel(),
                                         _stream()))
 
-    def render_backward(self, rays, z_vals, raw, g_rgb, mma="fp32"):
+    def render_backward(self, rays, z_vals, raw, g_rgb, mma="fp32", relu_masks=None):
         """dfb_render_bwd_mma: gradients of a test-time render w.r.t. rays_o, rays_d and viewdirs, each [N,3].
         mma = the kind the forward ran with; "f16"/"bf16" run the 8x256 fine network's backward on tcgen05."""
         _require_cuda(rays, "rays")
@@ -151,8 +154,9 @@ class NerfHandle:
         check(lib.dfb_render_bwd_workspace_bytes(self._h, N, S, C.byref(need)))
         ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
         g_o, g_d, g_vd = (torch.empty(N, 3, device=dev) for _ in range(3))
-        check(lib.dfb_render_bwd_mma(self._h, _lib.MMA_KINDS[mma], _ptr(rays), N, S, _ptr(z_vals), _ptr(raw), _ptr(g_rgb),
-                                     _ptr(g_o), _ptr(g_d), _ptr(g_vd), _ptr(ws), need.value, _stream()))
+        # relu_masks: the forward's saved ReLU masks (render(want=("relu_masks",)), tcgen05 path) -> no forward recompute
+        check(lib.dfb_render_bwd_saved(self._h, _lib.MMA_KINDS[mma], _ptr(rays), N, S, _ptr(z_vals), _ptr(raw), _ptr(relu_masks),
+                                       _ptr(g_rgb), _ptr(g_o), _ptr(g_d), _ptr(g_vd), _ptr(ws), need.value, _stream()))
         return g_o, g_d, g_vd
 
     def nerfw_forward(self, which, mode, x):

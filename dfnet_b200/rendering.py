@@ -48,16 +48,21 @@ class _RenderRaysFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rays_o, rays_d, viewdirs, near_far_hist, handle, N_samples, N_importance, mma):
         rec = torch.cat([rays_o, rays_d, near_far_hist[:, :2], viewdirs, near_far_hist[:, 2:]], -1)
-        o = handle.render(N_samples, N_importance, True, rays=rec, mma=mma, want=("z_vals", "raw"))
-        ctx.handle, ctx.mma = handle, mma
-        ctx.save_for_backward(rec, o["z_vals"], o["raw"])
+        # tcgen05 path: the forward also saves the ReLU masks of the fine network (one bit per activation), so that
+        # the backward kernel does not have to recompute the forward
+        saved = mma in ("f16", "bf16") and handle.tc_train
+        o = handle.render(N_samples, N_importance, True, rays=rec, mma=mma,
+                          want=("z_vals", "raw", "relu_masks") if saved else ("z_vals", "raw"))
+        ctx.handle, ctx.mma, ctx.saved = handle, mma, saved
+        ctx.save_for_backward(rec, o["z_vals"], o["raw"], *([o["relu_masks"]] if saved else []))
         ctx.mark_non_differentiable(o["disp"], o["acc"])
         return o["rgb"], o["disp"], o["acc"]
 
     @staticmethod
     def backward(ctx, g_rgb, g_disp, g_acc):
-        rec, z_vals, raw = ctx.saved_tensors
-        g_o, g_d, g_vd = ctx.handle.render_backward(rec, z_vals, raw, g_rgb, mma=ctx.mma)
+        rec, z_vals, raw = ctx.saved_tensors[:3]
+        masks = ctx.saved_tensors[3] if ctx.saved else None
+        g_o, g_d, g_vd = ctx.handle.render_backward(rec, z_vals, raw, g_rgb, mma=ctx.mma, relu_masks=masks)
         return g_o, g_d, g_vd, None, None, None, None, None
 
 

@@ -113,7 +113,10 @@ typedef struct DfbRenderExtras {
   float* z_samples;        /* [N,Nf]  seam: sample_pdf output                           */
   int32_t* inds;           /* [N,Nf]  seam: searchsorted indices (int64 in the reference) */
   float* depth;            /* [N]                                                       */
+  uint32_t* relu_masks;    /* [ceil(N*S/128), 12, 8, 128] ReLU masks of the fine network's 12 hidden layers, one bit per
+                              activation (tcgen05 path only): input of dfb_render_bwd_saved               */
 } DfbRenderExtras;
+#define DFB_RELU_MASK_WORDS_PER_TILE (12 * 8 * 128)
 
 /* Bytes of device workspace dfb_render_fwd needs for n_rays rays. */
 int dfb_render_workspace_bytes(const DfbNerf* nerf, const DfbRenderCfg* cfg, int64_t n_rays, size_t* out);
@@ -156,6 +159,14 @@ int dfb_render_bwd(DfbNerf* nerf, const float* rays, int64_t N, int S, const flo
 int dfb_render_bwd_mma(DfbNerf* nerf, int mma_kind, const float* rays, int64_t N, int S, const float* z_vals,
                        const float* raw, const float* g_rgb, float* g_rays_o, float* g_rays_d, float* g_viewdirs, void* ws,
                        size_t ws_bytes, void* stream);
+
+/* Same as dfb_render_bwd_mma for a forward that saved its ReLU masks (DfbRenderExtras::relu_masks, same rays, same
+ * mma_kind): the backward kernel skips the forward recompute (15 instead of 26 MMA steps per tile).  relu_masks == NULL
+ * recomputes.  N*S must keep every internal 16384-ray chunk aligned to 128 samples (any S that is a multiple of 1/128
+ * of the chunk, e.g. every S when N <= 16384). */
+int dfb_render_bwd_saved(DfbNerf* nerf, int mma_kind, const float* rays, int64_t N, int S, const float* z_vals,
+                         const float* raw, const uint32_t* relu_masks, const float* g_rgb, float* g_rays_o, float* g_rays_d,
+                         float* g_viewdirs, void* ws, size_t ws_bytes, void* stream);
 
 /* Op-level seams (same arguments as the reference functions). */
 /* sample_pdf (rendering.py:24-65): bins [N,nb], weights [N,nb-1], u [N,Nf] or NULL (det). */

@@ -413,6 +413,52 @@ def test_render_backward_tcgen05_vs_fp32_kernels(ops, golden, mma, tol, flip):
         assert torch.equal(a, c[:n])                          # samples are independent of their tile position
 
 
+@pytest.mark.parametrize("mma", ["f16", "bf16"])
+def test_render_backward_saved_masks(ops, golden, mma):
+    """Training forward that saves its ReLU masks (DfbRenderExtras::relu_masks) + dfb_render_bwd_saved (no forward
+    recompute): bit-identical to the recompute kernel when that one is pinned to the same masks, same direction as the
+    fp32 kernels; the saved masks differ from the recompute's own masks only by rounding-level flips."""
+    import ctypes as C
+    from dfnet_b200._lib import lib, check
+    mods, _ = synthetic_nets(8, 256)
+    h = ops.handle_for(*to_dev(mods))
+    Hh, Ww = 40, 50
+    c2w = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 1.0]], np.float32)
+    o, d = ops.get_rays(Hh, Ww, 45.0, T(c2w))
+    rec = T(O.make_ray_records(o.reshape(-1, 3).cpu().numpy(), d.reshape(-1, 3).cpu().numpy(), 0.0, 2.5, golden["hist"]))
+    plain = h.render(64, 128, True, rays=rec, mma=mma, want=("z_vals", "raw"))
+    out = h.render(64, 128, True, rays=rec, mma=mma, want=("z_vals", "raw", "relu_masks"))
+    assert torch.equal(plain["raw"], out["raw"]) and torch.equal(plain["rgb"], out["rgb"])   # recording changes nothing
+    P = Hh * Ww * 192
+    g_rgb = T((np.random.RandomState(3).randn(Hh * Ww, 3) * 1e-7).astype(np.float32))
+    got = h.render_backward(rec, out["z_vals"], out["raw"], g_rgb, mma=mma, relu_masks=out["relu_masks"])
+    torch.cuda.synchronize()
+    m_in = out["relu_masks"].permute(0, 3, 1, 2).reshape(-1, 12, 8)[:P].contiguous()   # [tile,12,8,128] -> [P,12,8]
+    m_own = torch.zeros(P, 12, 8, dtype=torch.int32, device=dev())
+    vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    try:
+        check(lib.dfb_debug_bwd_masks(None, vp(m_in), vp(m_own)))
+        pinned = h.render_backward(rec, out["z_vals"], out["raw"], g_rgb, mma=mma)
+        torch.cuda.synchronize()
+    finally:
+        check(lib.dfb_debug_bwd_masks(None, None, None))
+    for a, b in zip(got, pinned):
+        assert torch.equal(a, b)
+    valid = torch.ones(12, 8, dtype=torch.bool, device=dev())
+    valid[9:, 4:] = False
+    x = ((m_own ^ m_in).to(torch.int64) & 0xFFFFFFFF)[:, valid]
+    rate = sum(int(((x >> b) & 1).sum()) for b in range(32)) / (P * (9 * 256 + 3 * 128))
+    assert rate < (2e-3 if mma == "f16" else 2e-2), rate
+    want = h.render_backward(rec, out["z_vals"], out["raw"], g_rgb, mma="fp32")
+    for a, b in zip(got, want):
+        assert _cos(a, b) > (0.998 if mma == "f16" else 0.99), _cos(a, b)
+    n = 777   # ragged tail
+    sub = h.render(64, 128, True, rays=rec[:n], mma=mma, want=("z_vals", "raw", "relu_masks"))
+    g2 = h.render_backward(rec[:n], sub["z_vals"], sub["raw"], g_rgb[:n], mma=mma, relu_masks=sub["relu_masks"])
+    for a, b in zip(g2, got):
+        assert torch.equal(a, b[:n])
+
+
 def test_render_backward_tcgen05_matches_autograd(ops, golden):
     """End to end through rendering.render with mma="f16": forward AND backward on tcgen05, against float64 autograd."""
     from dfnet_b200 import rendering

@@ -45,3 +45,18 @@ for mma in ("f16", "bf16"):
         ev[1].record()
         torch.cuda.synchronize()
         print(f"  render_backward mma={kind}: {ev[0].elapsed_time(ev[1]) / 3:.3f} ms for {Hh * Ww} rays x 192 samples")
+
+# saved-mask path (no forward recompute) vs recompute, 19 200 rays (cfg4 render size)
+o2, d2 = ops.get_rays(120, 160, 146.25, c2w)
+rec2 = torch.tensor(O.make_ray_records(o2.reshape(-1, 3).cpu().numpy(), d2.reshape(-1, 3).cpu().numpy(), 0.0, 2.5, hist), device=dev)
+g2 = torch.tensor((rng.randn(120 * 160, 3) * 1e-7).astype(np.float32), device=dev)
+for want in (("z_vals", "raw"), ("z_vals", "raw", "relu_masks")):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    for rep in range(2):
+        ev[0].record()
+        out2 = h.render(64, 128, True, rays=rec2, mma="f16", want=want)
+        ev[1].record()
+        h.render_backward(rec2, out2["z_vals"], out2["raw"], g2, mma="f16", relu_masks=out2.get("relu_masks"))
+        ev[2].record()
+        torch.cuda.synchronize()
+    print(f"19200 rays, extras {want}: forward {ev[0].elapsed_time(ev[1]):.3f} ms, backward {ev[1].elapsed_time(ev[2]):.3f} ms")
