@@ -31,8 +31,8 @@ def main():
     ap.add_argument("--netw", type=int, default=256)
     ap.add_argument("--Nc", type=int, default=64)
     ap.add_argument("--Nf", type=int, default=128)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--levels", type=int, nargs="+", default=[0])
     a = ap.parse_args()
     rank, world, local = parallel.dist_info()
@@ -78,19 +78,26 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    # per-step device times (events around every step; a step ends with the host read of the loss, like the reference):
+    # `ms_per_step` is the mean over the timed steps, `ms_median` the median (robust against allocator / clock hiccups)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(a.steps):
+    for i in range(a.steps):
+        evs[i][0].record()
         loss, psnr = step()
+        evs[i][1].record()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
+    per = sorted(x.elapsed_time(y) for x, y in evs)
+    ms_median = per[len(per) // 2]
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
         print(json.dumps({"metric": "train_on_batch steps/sec", "value": world * 1e3 / float(t[0]), "unit": "steps/s", "n_gpus": world,
-                          "ms_per_step": float(t[0]), "steps": a.steps, "warmup": a.warmup, "loss": float(loss[0]),
+                          "ms_per_step": float(t[0]), "ms_median": ms_median, "ms_min": per[0], "ms_max": per[-1], "steps": a.steps, "warmup": a.warmup, "loss": float(loss[0]),
                           "gpu_launches_per_step": (C_launches() - l0) / a.steps,
                           "config": {"workload": f"train_on_batch {a.H}x{a.W}, render {a.H // 4}x{a.W // 4}, NeRF-W 8x{a.netw} "
                                                  f"{a.Nc}+{a.Nf}, DFNet F+G, levels {a.levels}, Adam", "dtype": "f16 fwd / bf16 grad"}}))
