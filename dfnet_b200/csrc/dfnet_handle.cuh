@@ -30,6 +30,12 @@ struct DfbDfnet {
   DfbConv* head5_dg[3] = {};
   float* bn_sc = nullptr;  // [3][128] eval-mode BatchNorm scale / shift of the heads (device)
   float* bn_sh = nullptr;
+  // train-mode BatchNorm of the heads (run_feature.py without freezeBN: batch statistics over the whole call's batch)
+  DfbConv* head5_raw[3] = {};   // the 5x5 convs without the BatchNorm folded in
+  float* bn_gb = nullptr;       // [3][2][128] gamma, beta (device)
+  float* bn_stat = nullptr;     // [3][4][128] batch mean, biased variance, scale, shift of the last train-mode forward
+  double* bn_part = nullptr;    // [128][64][2] partial sums
+  float bn_eps = 1e-5f;
   float* fc_w = nullptr;
   float* fc_b = nullptr;
   bool loaded = false;

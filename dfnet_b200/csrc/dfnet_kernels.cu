@@ -241,6 +241,10 @@ extern "C" void dfb_dfnet_destroy(DfbDfnet* d) {
   for (auto c : d->head5) dfb_conv_destroy(c);
   for (auto c : d->head1_dg) dfb_conv_destroy(c);
   for (auto c : d->head5_dg) dfb_conv_destroy(c);
+  for (auto c : d->head5_raw) dfb_conv_destroy(c);
+  if (d->bn_gb) cudaFree(d->bn_gb);
+  if (d->bn_stat) cudaFree(d->bn_stat);
+  if (d->bn_part) cudaFree(d->bn_part);
   if (d->bn_sc) cudaFree(d->bn_sc);
   if (d->bn_sh) cudaFree(d->bn_sh);
   if (d->fc_w) cudaFree(d->fc_w);
@@ -254,6 +258,49 @@ __global__ void k_bn_fold(const float* g, const float* be, const float* mu, cons
   const int c = threadIdx.x;
   const float s = g[c] / sqrtf(var[c] + eps);
   sc[c] = s, sh[c] = be[c] - mu[c] * s;
+}
+
+// ---- train-mode BatchNorm2d of the adaptation heads (feature/dfnet.py:57-62 under model.train(), run_feature.py:133) ----
+constexpr int kBnSplits = 64;
+// x: [B,128,plane] fp32 (pre-BatchNorm conv output).  part[c][split] = {sum, sum of squares} in float64.
+__global__ void __launch_bounds__(256) k_bn_partial(const float* __restrict__ x, int B, int64_t plane, double* __restrict__ part) {
+  __shared__ double sh[2][8];
+  const int c = blockIdx.y, sp = blockIdx.x;
+  const int64_t n = (int64_t)B * plane;
+  double s = 0.0, q = 0.0;
+  for (int64_t i = (int64_t)sp * 256 + threadIdx.x; i < n; i += (int64_t)kBnSplits * 256) {
+    const int64_t b = i / plane, p = i - b * plane;
+    const double v = (double)x[(b * 128 + c) * plane + p];
+    s += v, q += v * v;
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o), q += __shfl_xor_sync(0xffffffffu, q, o);
+  if ((threadIdx.x & 31) == 0) sh[0][threadIdx.x >> 5] = s, sh[1][threadIdx.x >> 5] = q;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b2 = 0.0;
+    for (int w = 0; w < 8; ++w) a += sh[0][w], b2 += sh[1][w];
+    part[((size_t)c * kBnSplits + sp) * 2] = a, part[((size_t)c * kBnSplits + sp) * 2 + 1] = b2;
+  }
+}
+// stat[0] mean, stat[1] biased variance (what normalises the batch), stat[2] scale, stat[3] shift; one thread per channel
+__global__ void k_bn_finalize(const double* __restrict__ part, double n, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, float eps, float* __restrict__ stat) {
+  const int c = threadIdx.x;
+  double s = 0.0, q = 0.0;
+  for (int i = 0; i < kBnSplits; ++i) s += part[((size_t)c * kBnSplits + i) * 2], q += part[((size_t)c * kBnSplits + i) * 2 + 1];
+  const double mean = s / n, var = fmax(q / n - mean * mean, 0.0);
+  const float sc = gamma[c] / sqrtf((float)var + eps);
+  stat[c] = (float)mean, stat[128 + c] = (float)var, stat[256 + c] = sc, stat[384 + c] = beta[c] - (float)mean * sc;
+}
+// y = x * scale[c] + shift[c]; images [0,Bs) go to out_t, [Bs,B) to out_r (siamese split; out_r unused when Bs == B)
+__global__ void __launch_bounds__(256) k_bn_apply(const float* __restrict__ x, int B, int Bs, int64_t plane,
+                                                  const float* __restrict__ stat, float* __restrict__ out_t,
+                                                  float* __restrict__ out_r) {
+  const int bc = blockIdx.y, b = bc / 128, c = bc % 128;
+  const float sc = stat[256 + c], shf = stat[384 + c];
+  const float* src = x + (size_t)bc * plane;
+  float* dst = (b < Bs ? out_t + ((size_t)b * 128 + c) * plane : out_r + ((size_t)(b - Bs) * 128 + c) * plane);
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < plane; i += (int64_t)gridDim.x * 256) dst[i] = fmaf(src[i], sc, shf);
 }
 }  // namespace dfb
 
@@ -304,6 +351,16 @@ extern "C" int dfb_dfnet_load_ex(DfbDfnet* d, const float* const* params, const 
     if (rc) return rc;
     rc = conv_set(&d->head5[l], 64, 128, 5, p[2], p[3], sc, sh, 0, 0);
     if (rc) return rc;
+    if (flags & 4) {  // train-mode BatchNorm: the 5x5 conv without the fold, gamma / beta on the device
+      rc = conv_set(&d->head5_raw[l], 64, 128, 5, p[2], p[3], nullptr, nullptr, 0, 0);
+      if (rc) return rc;
+      if (!d->bn_gb) DFB_CHECK_CUDA(cudaMalloc(&d->bn_gb, 3 * 2 * 128 * 4));
+      if (!d->bn_stat) DFB_CHECK_CUDA(cudaMalloc(&d->bn_stat, 3 * 4 * 128 * 4));
+      if (!d->bn_part) DFB_CHECK_CUDA(cudaMalloc(&d->bn_part, (size_t)128 * dfb::kBnSplits * 2 * sizeof(double)));
+      DFB_CHECK_CUDA(cudaMemcpyAsync(d->bn_gb + (l * 2 + 0) * 128, p[4], 512, cudaMemcpyDefault, nullptr));
+      DFB_CHECK_CUDA(cudaMemcpyAsync(d->bn_gb + (l * 2 + 1) * 128, p[5], 512, cudaMemcpyDefault, nullptr));
+      d->bn_eps = bn_eps;
+    }
     if (train) {
       rc = conv_set(&d->head1_dg[l], kTapCh[l], 64, 1, p[0], nullptr, nullptr, nullptr, 1, 1);
       if (rc) return rc;
@@ -330,6 +387,17 @@ extern "C" int dfb_dfnet_load_ex(DfbDfnet* d, const float* const* params, const 
   return DFB_OK;
 }
 
+// Batch statistics of the last train-mode forward (flags bit5): out [n_levels][2][128] = mean, biased variance per head
+// channel (device or host pointer; copied on `stream`).  The caller applies the running-statistics update
+// (momentum, unbiased variance) to its own buffers, as torch.nn.BatchNorm2d does.
+extern "C" int dfb_dfnet_bn_batch_stats(const DfbDfnet* d, float* out, void* stream) {
+  DFB_REQUIRE(d && out && d->bn_stat, DFB_ERR_INVALID, "no train-mode BatchNorm forward has run");
+  for (int l = 0; l < d->n_levels; ++l)
+    DFB_CHECK_CUDA(cudaMemcpyAsync(out + (size_t)l * 256, d->bn_stat + (size_t)l * 512, 256 * sizeof(float), cudaMemcpyDefault,
+                                   (cudaStream_t)stream));
+  return DFB_OK;
+}
+
 extern "C" int dfb_dfnet_load(DfbDfnet* d, const float* const* params, const int64_t* numel, int n_params, float bn_eps) {
   return dfb_dfnet_load_ex(d, params, numel, n_params, bn_eps, 0);
 }
@@ -353,7 +421,9 @@ DfWs dfnet_ws(int B, int H, int W, int n_levels, int upH, int upW, bool tape) {
     if (lv < 3 && kTapConv[lv] == i) {
       w.tap[lv] = take((size_t)B * h * wd * kTapCh[lv] * 2);
       w.mid[lv] = (tape || lv == 0) ? take((size_t)B * h * wd * 64 * 2) : w.mid[0];
-      if (lv < n_levels && (h != upH || wd != upW)) stage = std::max(stage, (size_t)B * h * wd * 128 * 4);
+      // fp32 NCHW staging: levels that need resampling, and every level under train-mode BatchNorm (the batch
+      // statistics need the whole pre-BatchNorm output before anything can be written to the stacks)
+      if (lv < n_levels) stage = std::max(stage, (size_t)B * h * wd * 128 * 4);
       ++lv;
     }
     if (kPoolAfter[i]) {
@@ -446,6 +516,39 @@ static int dfnet_fwd_impl(DfbDfnet* d, const float* x, int B, int H, int W, uint
       if (rc) return rc;
       const size_t lvl_stride = (size_t)Bs * 128 * upH * upW;
       const __half* mid = (const __half*)(base + L.mid[l]);
+      if (flags & 32) {
+        // train-mode BatchNorm: conv without the fold over the WHOLE batch -> batch statistics -> normalise
+        DFB_REQUIRE(d->head5_raw[l] && d->bn_stat, DFB_ERR_INVALID, "train-mode BatchNorm variants not loaded (dfb_dfnet_load_ex flags bit2)");
+        float* featbuf = (float*)(base + L.feat);
+        rc = dfb_conv_fwd(d->head5_raw[l], mid, B, fh, fw, 0, nullptr, nullptr, featbuf, stream);
+        if (rc) return rc;
+        const int64_t fplane = (int64_t)fh * fw;
+        float* stat = d->bn_stat + l * 4 * 128;
+        dfb::k_bn_partial<<<dim3(dfb::kBnSplits, 128), 256, 0, st>>>(featbuf, B, fplane, d->bn_part);
+        DFB_LAUNCH_CHECK();
+        dfb::k_bn_finalize<<<1, 128, 0, st>>>(d->bn_part, (double)B * (double)fplane, d->bn_gb + (l * 2) * 128,
+                                              d->bn_gb + (l * 2 + 1) * 128, d->bn_eps, stat);
+        DFB_LAUNCH_CHECK();
+        const dim3 ag((unsigned)std::min<int64_t>((fplane + 255) / 256, 64), B * 128);
+        if (fh == upH && fw == upW) {
+          dfb::k_bn_apply<<<ag, 256, 0, st>>>(featbuf, B, Bs, fplane, stat, feats_t + l * lvl_stride,
+                                              single ? nullptr : feats_r + l * lvl_stride);
+          DFB_LAUNCH_CHECK();
+          continue;
+        }
+        dfb::k_bn_apply<<<ag, 256, 0, st>>>(featbuf, B, B, fplane, stat, featbuf, nullptr);  // in place, then resample
+        DFB_LAUNCH_CHECK();
+        const int planes_s = Bs * 128;
+        const dim3 rg((upW + 511) / 512, upH, (planes_s + kResizePlanes - 1) / kResizePlanes);
+        k_resize_bilinear_ac<<<rg, 128, 0, st>>>(featbuf, feats_t + l * lvl_stride, planes_s, fh, fw, upH, upW);
+        DFB_LAUNCH_CHECK();
+        if (!single) {
+          k_resize_bilinear_ac<<<rg, 128, 0, st>>>(featbuf + (size_t)planes_s * fh * fw, feats_r + l * lvl_stride, planes_s, fh, fw,
+                                                   upH, upW);
+          DFB_LAUNCH_CHECK();
+        }
+        continue;
+      }
       if (fh == upH && fw == upW) {
         // align_corners resampling to the same size is the identity (level 0 at full resolution):
         // the 5x5 conv writes fp32 NCHW straight into the stacks; siamese split = two half batches

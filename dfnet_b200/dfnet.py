@@ -53,15 +53,17 @@ class _DfnetHandle:
         self._bwd_ws = None
         self.n_levels = len(module.hypercolumn_layers)
 
-    def refresh(self, module, train=False):
+    def refresh(self, module, train=False, bn_train=False):
         # state_dict() walks and renames every tensor (~ms): cache the tensors themselves, keyed on their identity,
         # and poll their versions
         key = (id(module), tuple(id(t) for t in module.parameters()), tuple(id(t) for t in module.buffers()))
         if getattr(self, "_sd_key", None) != key:
             self._sd, self._sd_key = dict(module.state_dict(keep_vars=True)), key
         sd = self._sd
+        # (the BatchNorm running statistics are buffers: a train-mode forward updates them, which bumps their versions)
         v = [(t.data_ptr(), t._version) for t in sd.values()] + [bool(train)]
-        if v[:-1] == (self._versions or [None])[:-1] and (self._versions[-1] or not train):
+        have_bn = getattr(self, "_bn_loaded", False)
+        if v[:-1] == (self._versions or [None])[:-1] and (self._versions[-1] or not train) and (have_bn or not bn_train):
             return
         names = [f"encoder.{i}" for i, m in enumerate(module.encoder) if isinstance(m, nn.Conv2d)]
         ts = []
@@ -78,19 +80,22 @@ class _DfnetHandle:
         eps = module.adaptation_layers.adapt_layer_0[3].eps
         # bit 1: everything is ordered on the legacy default stream -> the library skips its host synchronisation
         on_default = all(t.is_cuda for t in ts) and torch.cuda.current_stream(ts[0].device).cuda_stream == 0
-        check(lib.dfb_dfnet_load_ex(self._h, ptrs, numel, len(ts), eps, (1 if train else 0) | (2 if on_default else 0)))
+        check(lib.dfb_dfnet_load_ex(self._h, ptrs, numel, len(ts), eps,
+                                    (1 if train else 0) | (2 if on_default else 0) | (4 if bn_train else 0)))
+        self._bn_loaded = bool(bn_train)
         self._versions = v
         self.n_params = len(ts)
 
-    def forward(self, x, return_feature, single, return_pose, upH, upW, tape=False, bf16=False):
-        """tape=True keeps every activation in a fresh buffer (returned as 4th value) for `backward`."""
+    def forward(self, x, return_feature, single, return_pose, upH, upW, tape=False, bf16=False, bn_train=False):
+        """tape=True keeps every activation in a fresh buffer (returned as 4th value) for `backward`.
+        bn_train=True: train-mode BatchNorm in the heads (batch statistics, see `bn_batch_stats`)."""
         if not x.is_cuda:
             raise _lib.DfbError("DFNet input must be a CUDA tensor: the dfnet_b200 hot path has no CPU fallback")
         x = x.detach().float().contiguous()
         B, _, H, W = x.shape
         dev = x.device
         need = C.c_size_t()
-        flags = (1 if return_feature else 0) | (2 if single else 0) | (4 if return_pose else 0)
+        flags = (1 if return_feature else 0) | (2 if single else 0) | (4 if return_pose else 0) | (32 if bn_train else 0)
         if tape:
             check(lib.dfb_dfnet_tape_bytes(self._h, B, H, W, upH, upW, C.byref(need)))
             ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
@@ -116,6 +121,12 @@ class _DfnetHandle:
             self.last_tape = (ws, flags, (B, H, W, upH, upW))  # debug: tests read the stored activations back
             return ft, fr, pose, (ws, flags)
         return ft, fr, pose
+
+    def bn_batch_stats(self, device):
+        """[L,2,128]: batch mean and biased variance of every head's BatchNorm input in the last bn_train forward."""
+        out = torch.empty(self.n_levels, 2, 128, device=device)
+        check(lib.dfb_dfnet_bn_batch_stats(self._h, C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return out
 
     def tape_activations(self):
         """Debug: the stored activations of the last taped forward as NCHW fp32 tensors
@@ -180,9 +191,10 @@ class _DfnetFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, handle, cfg, *params):
-        return_feature, single, return_pose, upH, upW, level_mask, _bf16 = cfg
+        return_feature, single, return_pose, upH, upW, level_mask, _bf16, bn_train = cfg
         need_p = any(t.requires_grad for t in params)
-        ft, fr, pose, tape = handle.forward(x, return_feature, single, return_pose, upH, upW, tape=True, bf16=bool(cfg[6]))
+        ft, fr, pose, tape = handle.forward(x, return_feature, single, return_pose, upH, upW, tape=True, bf16=bool(cfg[6]),
+                                            bn_train=bn_train)
         ctx.handle, ctx.tape, ctx.cfg, ctx.need_p = handle, tape, cfg, need_p
         ctx.xshape = (x.shape[0], x.shape[2], x.shape[3])
         ctx.pshapes = [t.shape for t in params]
@@ -196,8 +208,10 @@ class _DfnetFn(torch.autograd.Function):
     def backward(ctx, *gs):
         g = dict(zip(ctx.slots, gs))
         g_ft, g_fr, g_pose = (None if g.get(k) is None else g[k].float().contiguous() for k in ("ft", "fr", "pose"))
-        return_feature, single, return_pose, upH, upW, level_mask, _bf16 = ctx.cfg
+        return_feature, single, return_pose, upH, upW, level_mask, _bf16, bn_train = ctx.cfg
         n_out = 3 + len(ctx.pshapes)
+        if bn_train and (g.get("ft") is not None or g.get("fr") is not None):
+            raise NotImplementedError("the backward through train-mode BatchNorm (run_feature.py training) is not on the B200 path yet")
         if g_ft is None and g_fr is None and g_pose is None:
             return (None,) * n_out
         if (g_ft is not None or g_fr is not None) and ctx.need_p:
@@ -236,28 +250,45 @@ class DFNet(nn.Module):
     def forward(self, x, return_feature=False, isSingleStream=False, return_pose=True, upsampleH=240, upsampleW=427):
         """Reference feature/dfnet.py:106-172 -> (feature_maps, predict): feature_maps is None,
         [stack [L,B,128,H,W]] (single stream) or [target_stack, render_stack] (siamese)."""
-        bn = self.adaptation_layers.adapt_layer_0[3]
-        if return_feature and bn.training:
-            raise NotImplementedError("train-mode BatchNorm (batch statistics, run_feature.py without freezeBN) "
-                                      "is not on the B200 hot path yet; call .eval() / freeze_bn_layer_train")
+        bns = [getattr(self.adaptation_layers, f"adapt_layer_{l}")[3] for l in range(len(self.hypercolumn_layers))]
+        # train-mode BatchNorm (run_feature.py without freezeBN, feature/dfnet.py heads under model.train()): batch
+        # statistics over the whole batch of this call (target and render images together), running statistics updated
+        bn_train = bool(return_feature and bns[0].training)
+        if bn_train and (any(b.training != bns[0].training for b in bns) or any(b.momentum is None or not b.track_running_stats for b in bns)):
+            raise NotImplementedError("train-mode BatchNorm: all heads in the same mode, momentum set, running statistics tracked")
         if self._handle is None:
             self._handle = _DfnetHandle(self)
         params = self._load_order_params()
         train = torch.is_grad_enabled() and (x.requires_grad or any(t.requires_grad for t in params))
-        self._handle.refresh(self, train=train)
+        self._handle.refresh(self, train=train, bn_train=bn_train)
         if train:
             levels = getattr(self, "grad_levels", None)
             mask = sum(1 << l for l in (range(len(self.hypercolumn_layers)) if levels is None else levels))
             # train_dtype: "f16" (default: the inference kernels' fp16 forward, bf16 gradients) or "bf16" (BASELINE config[3]:
             # bf16 storage in the pose regressor's forward as well)
             bf16 = getattr(self, "train_dtype", "f16") == "bf16" and not return_feature
-            cfg = (bool(return_feature), bool(isSingleStream), bool(return_pose), int(upsampleH), int(upsampleW), mask, bf16)
+            cfg = (bool(return_feature), bool(isSingleStream), bool(return_pose), int(upsampleH), int(upsampleW), mask, bf16, bn_train)
             outs = list(_DfnetFn.apply(x, self._handle, cfg, *params))
             ft = outs.pop(0) if return_feature else None
             fr = outs.pop(0) if return_feature and not isSingleStream else None
             pose = outs.pop(0) if return_pose else None
         else:
-            ft, fr, pose = self._handle.forward(x, return_feature, isSingleStream, return_pose, int(upsampleH), int(upsampleW))
+            ft, fr, pose = self._handle.forward(x, return_feature, isSingleStream, return_pose, int(upsampleH), int(upsampleW),
+                                                bn_train=bn_train)
+        if bn_train:
+            # torch.nn.BatchNorm2d bookkeeping: running = (1 - m) running + m stat, with the UNBIASED batch variance
+            stats = self._handle.bn_batch_stats(x.device)
+            B = x.shape[0]
+            with torch.no_grad():
+                for l, b in enumerate(bns):
+                    sc = self.scales[l]
+                    h, w = x.shape[2], x.shape[3]
+                    for _ in range({1: 0, 4: 2, 16: 4}[sc]):
+                        h, w = h // 2, w // 2
+                    n = B * h * w
+                    b.running_mean.mul_(1 - b.momentum).add_(stats[l, 0].to(b.running_mean.device), alpha=b.momentum)
+                    b.running_var.mul_(1 - b.momentum).add_(stats[l, 1].to(b.running_var.device) * (n / max(n - 1, 1)), alpha=b.momentum)
+                    b.num_batches_tracked += 1
         if not return_feature:
             feature_maps = None
         elif isSingleStream:

@@ -207,7 +207,10 @@ void dfb_dfnet_destroy(DfbDfnet* net);
 int dfb_dfnet_load(DfbDfnet* net, const float* const* params, const int64_t* numel, int n_params, float bn_eps);
 int dfb_dfnet_workspace_bytes(const DfbDfnet* net, int B, int H, int W, int upH, int upW, size_t* out);
 /* DFNet.forward (feature/dfnet.py:106-172).  x [B,3,H,W] fp32 in [0,1].
- * flags: bit0 return_feature, bit1 isSingleStream, bit2 return_pose.
+ * flags: bit0 return_feature, bit1 isSingleStream, bit2 return_pose, bit3 keep the tape (training), bit4 bf16
+ * encoder (pose-only training), bit5 train-mode BatchNorm in the heads: batch statistics over the whole batch of this
+ * call (run_feature.py:133,204 without freezeBN; needs dfb_dfnet_load_ex flags bit2; the statistics are read back with
+ * dfb_dfnet_bn_batch_stats for the caller's running-statistics update).
  * feats_t / feats_r: [L, Bs, 128, upH, upW] fp32, Bs = B (single stream; feats_r unused) or B/2
  * (siamese: first half of the batch -> feats_t, second half -> feats_r).  pose: [B,12]. */
 int dfb_dfnet_fwd(DfbDfnet* net, const float* x, int B, int H, int W, uint32_t flags, int upH, int upW, float* feats_t,
@@ -284,9 +287,13 @@ int dfb_conv_fwd_ex(DfbConv* c, const void* in_nhwc16, int B, int H, int W, int 
 int dfb_conv_wgrad(const void* gO, const void* X, int B, int H, int W, int Cin, int Cin_pad, int Cout, int KH, int fmt,
                    float* dW, float* dB, void* stream);
 
-/* dfb_dfnet_load, flags bit0: also build the training variants (bf16 encoder, data-gradient convolutions). */
+/* dfb_dfnet_load, flags bit0: also build the training variants (bf16 encoder, data-gradient convolutions); bit1: the
+ * caller's work is ordered on the legacy default stream and the sources stay alive in stream order (no host
+ * synchronisation); bit2: also build the train-mode BatchNorm variants of the heads (5x5 convs without the fold). */
 int dfb_dfnet_load_ex(DfbDfnet* d, const float* const* params, const int64_t* numel, int n_params, float bn_eps,
                       uint32_t flags);
+/* Batch statistics of the last forward with flags bit5: out [n_levels][2][128] = mean, biased variance per channel. */
+int dfb_dfnet_bn_batch_stats(const DfbDfnet* d, float* out, void* stream);
 /* Bytes of the tape a forward with flags bit3 writes (every activation kept) and of the backward scratch. */
 int dfb_dfnet_tape_bytes(const DfbDfnet* d, int B, int H, int W, int upH, int upW, size_t* out);
 /* Debug seam: byte offsets inside the tape (out[60]): in8; per encoder conv {act, pool or -1, h, w}; tap[3]; mid[3]; pooled. */

@@ -49,8 +49,12 @@ def upsample_bilinear_ac(x, Ho, Wo):
     return ((1 - ly) * ((1 - lx) * g(y0, x0) + lx * g(y0, x1)) + ly * ((1 - lx) * g(y1, x0) + lx * g(y1, x1))).astype(f32)
 
 
-def dfnet_forward(P, x, n_levels=3, return_feature=True, single=False, return_pose=True, upH=None, upW=None, bn_eps=1e-5):
-    """feature/dfnet.py:106-172 with eval-mode BatchNorm.  P: state_dict as numpy arrays."""
+def dfnet_forward(P, x, n_levels=3, return_feature=True, single=False, return_pose=True, upH=None, upW=None, bn_eps=1e-5,
+                  bn_train=False, bn_momentum=0.1, bn_running=None):
+    """feature/dfnet.py:106-172.  P: state_dict as numpy arrays.  bn_train=False: eval-mode BatchNorm (freezeBN /
+    model.eval()); bn_train=True: batch statistics over the whole batch as torch.nn.BatchNorm2d computes them under
+    model.train() (run_feature.py:133,204), and `bn_running` (a dict) receives the updated running_mean / running_var
+    of every head (momentum update with the unbiased batch variance)."""
     x = ((np.asarray(x, f32) - MEAN[None, :, None, None]) / STD[None, :, None, None]).astype(f32)
     taps, idx = [], 0
     tap_idx = [2, 14, 28][:n_levels]
@@ -73,8 +77,19 @@ def dfnet_forward(P, x, n_levels=3, return_feature=True, single=False, return_po
             p = f"adaptation_layers.adapt_layer_{l}."
             h = np.maximum(conv2d(t, P[p + "0.weight"], P[p + "0.bias"], 0), 0)
             h = conv2d(h, P[p + "2.weight"], P[p + "2.bias"], 2)
-            sc = P[p + "3.weight"] / np.sqrt(P[p + "3.running_var"] + f32(bn_eps))
-            h = ((h - P[p + "3.running_mean"][None, :, None, None]) * sc[None, :, None, None]
+            if bn_train:
+                n = h.shape[0] * h.shape[2] * h.shape[3]
+                mu = h.mean((0, 2, 3), dtype=np.float64)
+                var = h.var((0, 2, 3), dtype=np.float64)   # biased: what normalises the batch
+                if bn_running is not None:
+                    bn_running[p + "3.running_mean"] = ((1 - bn_momentum) * P[p + "3.running_mean"] + bn_momentum * mu).astype(f32)
+                    bn_running[p + "3.running_var"] = ((1 - bn_momentum) * P[p + "3.running_var"]
+                                                       + bn_momentum * var * n / max(n - 1, 1)).astype(f32)
+                mu, var = mu.astype(f32), var.astype(f32)
+            else:
+                mu, var = P[p + "3.running_mean"], P[p + "3.running_var"]
+            sc = P[p + "3.weight"] / np.sqrt(var + f32(bn_eps))
+            h = ((h - mu[None, :, None, None]) * sc[None, :, None, None]
                  + P[p + "3.bias"][None, :, None, None]).astype(f32)
             outs.append(upsample_bilinear_ac(h, upH, upW))
         stack = np.stack(outs)  # [L,B,128,H,W]

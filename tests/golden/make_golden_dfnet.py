@@ -62,6 +62,33 @@ def main():
         for nm, f in (("t", feats[0]), ("r", feats[1]), ("s", feats_s[0])):
             put(f"{tag}_feat_{nm}_sub", f[:, :, ::8, ::4, ::4])
             put(f"{tag}_feat_{nm}_stats", torch.stack([f.sum(), f.abs().sum(), f.abs().max(), (f * f).sum()]).double())
+        # train-mode BatchNorm in the heads (run_feature.py without freezeBN): batch statistics over the whole batch,
+        # running statistics updated in place.  Non-trivial BatchNorm state so that the fold is visible.
+        ref_t = cls()
+        ref_t.load_state_dict(ref.state_dict())
+        g = torch.Generator().manual_seed(77)
+        bn_state = {}
+        for l in range(3 if tag == "dfnet" else 1):
+            bn = getattr(ref_t.adaptation_layers, f"adapt_layer_{l}")[3]
+            with torch.no_grad():
+                bn.weight.copy_(0.5 + torch.rand(128, generator=g))
+                bn.bias.copy_(0.2 * torch.randn(128, generator=g))
+                bn.running_mean.copy_(0.1 * torch.randn(128, generator=g))
+                bn.running_var.copy_(0.5 + torch.rand(128, generator=g))
+            for k in ("weight", "bias", "running_mean", "running_var"):
+                bn_state[f"{l}.{k}"] = getattr(bn, k).detach().clone()
+                put(f"{tag}_bntrain_init_{l}_{k}", bn_state[f"{l}.{k}"])
+        ref_t.train()
+        with torch.no_grad():
+            feats_bn, _ = ref_t(x, return_feature=True, isSingleStream=False, return_pose=False, upsampleH=48, upsampleW=64)
+        for nm, f in (("t", feats_bn[0]), ("r", feats_bn[1])):
+            put(f"{tag}_bntrain_feat_{nm}_sub", f[:, :, ::8, ::4, ::4])
+            put(f"{tag}_bntrain_feat_{nm}_stats", torch.stack([f.sum(), f.abs().sum(), f.abs().max(), (f * f).sum()]).double())
+        for l in range(3 if tag == "dfnet" else 1):
+            bn = getattr(ref_t.adaptation_layers, f"adapt_layer_{l}")[3]
+            put(f"{tag}_bntrain_running_mean_{l}", bn.running_mean)
+            put(f"{tag}_bntrain_running_var_{l}", bn.running_var)
+            assert int(bn.num_batches_tracked) == 1
         if tag == "dfnet":
             from feature.direct_feature_matching import feature_loss, preprocess_features_for_loss
             ft = preprocess_features_for_loss(feats[0])[0]

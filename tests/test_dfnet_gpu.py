@@ -87,6 +87,46 @@ def test_dfnet_forward_vs_reference_golden(g, tag, cls, L):
     assert none2 is None and torch.equal(pose_only.detach(), pose)
 
 
+@pytest.mark.parametrize("tag,cls,L", [("dfnet", "DFNet", 3), ("dfnet_s", "DFNet_s", 1)])
+def test_dfnet_train_mode_batchnorm_vs_reference_golden(g, tag, cls, L):
+    """DFNet under model.train() (run_feature.py:133 without freezeBN): the heads' BatchNorm normalises with the
+    statistics of the whole batch of the call and updates running_mean / running_var / num_batches_tracked like
+    torch.nn.BatchNorm2d; against the unmodified reference."""
+    net = synthetic_dfnet(cls).to(dev())
+    for l in range(L):
+        bn = getattr(net.adaptation_layers, f"adapt_layer_{l}")[3]
+        with torch.no_grad():
+            for k in ("weight", "bias", "running_mean", "running_var"):
+                getattr(bn, k).copy_(torch.tensor(g[f"{tag}_bntrain_init_{l}_{k}"]))
+    net.train()
+    x = torch.tensor(g[f"{tag}_x"], device=dev())
+    with torch.no_grad():
+        feats, none = net(x, return_feature=True, isSingleStream=False, return_pose=False, upsampleH=48, upsampleW=64)
+    torch.cuda.synchronize()
+    assert none is None and feats[0].shape == (L, 1, 128, 48, 64)
+    for nm, f in (("t", feats[0]), ("r", feats[1])):
+        got, want = f[:, :, ::8, ::4, ::4].cpu().numpy(), g[f"{tag}_bntrain_feat_{nm}_sub"]
+        for l in range(L):
+            assert relmax(got[l], want[l]) < 5e-3, (nm, l)
+        st = g[f"{tag}_bntrain_feat_{nm}_stats"]
+        assert abs(float(f.abs().sum().double()) - st[1]) / st[1] < 2e-3
+    for l in range(L):
+        bn = getattr(net.adaptation_layers, f"adapt_layer_{l}")[3]
+        assert relmax(bn.running_mean.cpu().numpy(), g[f"{tag}_bntrain_running_mean_{l}"]) < 2e-3
+        assert relmax(bn.running_var.cpu().numpy(), g[f"{tag}_bntrain_running_var_{l}"]) < 2e-3
+        assert int(bn.num_batches_tracked) == 1
+    # a second call sees the updated running statistics in eval mode and still works in train mode
+    net.eval()
+    with torch.no_grad():
+        fe, _ = net(x, return_feature=True, isSingleStream=True, return_pose=False, upsampleH=48, upsampleW=64)
+    assert torch.isfinite(fe[0]).all()
+    # grad-enabled train-mode forward runs (taped); its backward through the heads is the part that is not built
+    net.train()
+    ft, _ = net(x, return_feature=True, isSingleStream=True, return_pose=False, upsampleH=48, upsampleW=64)
+    with pytest.raises(NotImplementedError):
+        ft[0].sum().backward()
+
+
 def test_feature_loss_vs_reference_golden(g):
     from dfnet_b200.dfnet import feature_loss, preprocess_features_for_loss
     from oracle import dfnet_oracle as DO
@@ -123,7 +163,7 @@ def test_dfnet_full_size_pair_properties():
     assert abs(l0) < 1e-6                                        # cosine of a tensor with itself
     y = torch.cat([img, torch.rand(1, 3, 480, 640, device=dev())], 0)
     f2, _ = net(y, return_feature=True, isSingleStream=False, return_pose=False, upsampleH=480, upsampleW=640)
-    l1 = float(feature_loss(f2[1][0, 0], f2[0][0, 0]))
+    l1 = float(feature_loss(f2[1][0, 0], f2[0][0, 0]).detach())
     assert 0.0 < l1 < 2.0
 
 

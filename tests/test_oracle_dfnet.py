@@ -44,3 +44,25 @@ def test_triplet_loss_oracle(g, k):
     loss, case = DO.triplet_loss_hnm_plus(g[f"trip_{k}_f1"], g[f"trip_{k}_f2"], 1.0)
     assert case == k                      # the four constructed inputs exercise the four cases
     assert abs(float(loss) - float(np.asarray(g[f"trip_{k}_loss"]).reshape(-1)[0])) < 1e-5
+
+
+@pytest.mark.parametrize("tag,cls,L", [("dfnet", "DFNet", 3), ("dfnet_s", "DFNet_s", 1)])
+def test_dfnet_forward_oracle_train_mode_batchnorm(g, tag, cls, L):
+    """Heads under model.train() (run_feature.py without freezeBN): batch statistics over the whole (target + render)
+    batch and the running-statistics update, against the unmodified reference."""
+    net = synthetic_dfnet(cls)
+    P = {k: v.numpy().copy() for k, v in net.state_dict().items()}
+    for l in range(L):
+        for k in ("weight", "bias", "running_mean", "running_var"):
+            P[f"adaptation_layers.adapt_layer_{l}.3.{k}"] = g[f"{tag}_bntrain_init_{l}_{k}"]
+    run = {}
+    feats, _ = DO.dfnet_forward(P, g[f"{tag}_x"], n_levels=L, single=False, return_pose=False, upH=48, upW=64,
+                                bn_train=True, bn_running=run)
+    for nm, f in (("t", feats[0]), ("r", feats[1])):
+        assert relmax(f[:, :, ::8, ::4, ::4], g[f"{tag}_bntrain_feat_{nm}_sub"]) < 1e-4
+        st = g[f"{tag}_bntrain_feat_{nm}_stats"]
+        assert abs(np.abs(f).sum(dtype=np.float64) - st[1]) / st[1] < 1e-4
+    for l in range(L):
+        p = f"adaptation_layers.adapt_layer_{l}.3."
+        assert relmax(run[p + "running_mean"], g[f"{tag}_bntrain_running_mean_{l}"]) < 1e-5
+        assert relmax(run[p + "running_var"], g[f"{tag}_bntrain_running_var_{l}"]) < 1e-5

@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--levels", type=int, nargs="+", default=[0])
+    ap.add_argument("--no-gc", action="store_true", help="diagnostic: disable Python's cyclic GC during the timed steps")
     a = ap.parse_args()
     rank, world, local = parallel.dist_info()
     torch.cuda.set_device(local)
@@ -80,6 +81,10 @@ def main():
         dist.barrier()
     # per-step device times (events around every step; a step ends with the host read of the loss, like the reference):
     # `ms_per_step` is the mean over the timed steps, `ms_median` the median (robust against allocator / clock hiccups)
+    if a.no_gc:
+        import gc
+        gc.collect()
+        gc.disable()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -90,14 +95,15 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
-    per = sorted(x.elapsed_time(y) for x, y in evs)
+    per_order = [round(x.elapsed_time(y), 1) for x, y in evs]
+    per = sorted(per_order)
     ms_median = per[len(per) // 2]
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
         print(json.dumps({"metric": "train_on_batch steps/sec", "value": world * 1e3 / float(t[0]), "unit": "steps/s", "n_gpus": world,
-                          "ms_per_step": float(t[0]), "ms_median": ms_median, "ms_min": per[0], "ms_max": per[-1], "steps": a.steps, "warmup": a.warmup, "loss": float(loss[0]),
+                          "ms_per_step": float(t[0]), "ms_median": ms_median, "ms_min": per[0], "ms_max": per[-1], "ms_steps": per_order, "steps": a.steps, "warmup": a.warmup, "loss": float(loss[0]),
                           "gpu_launches_per_step": (C_launches() - l0) / a.steps,
                           "config": {"workload": f"train_on_batch {a.H}x{a.W}, render {a.H // 4}x{a.W // 4}, NeRF-W 8x{a.netw} "
                                                  f"{a.Nc}+{a.Nf}, DFNet F+G, levels {a.levels}, Adam", "dtype": "f16 fwd / bf16 grad"}}))

@@ -19,6 +19,20 @@ c2w = torch.tensor([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 1.0]], device=dev)
 hist = torch.tensor([5, 10, 20, 30, 15, 10, 5, 3, 1, 1.0], device=dev)
 for mma in ("f16", "bf16", "fp32"):
     o = h.render(64, 128, True, c2w=c2w, H=9, W=13, focal=11.0, near=0.0, far=2.5, hist=hist, mma=mma)
+# training forward with saved ReLU masks + tcgen05 backward (saved masks and forward recompute), fp32 backward, 1-CTA kernel
+from oracle import nerf_oracle as O  # noqa: E402
+ro, rd = ops.get_rays(9, 13, 11.0, c2w)
+rec = torch.tensor(O.make_ray_records(ro.reshape(-1, 3).cpu().numpy(), rd.reshape(-1, 3).cpu().numpy(), 0.0, 2.5,
+                                      hist.cpu().numpy()[None]), device=dev)
+g = torch.randn(9 * 13, 3, device=dev) * 1e-6
+for mma in ("f16", "bf16"):
+    t = h.render(64, 128, True, rays=rec, mma=mma, want=("z_vals", "raw", "relu_masks"))
+    h.render_backward(rec, t["z_vals"], t["raw"], g, mma=mma, relu_masks=t["relu_masks"])
+    h.render_backward(rec, t["z_vals"], t["raw"], g, mma=mma)
+h.render_backward(rec, t["z_vals"], t["raw"], g, mma="fp32")
+os.environ["DFB_TC_CTA_GROUP"] = "1"
+h.render(64, 128, True, c2w=c2w, H=9, W=13, focal=11.0, near=0.0, far=2.5, hist=hist, mma="f16")
+del os.environ["DFB_TC_CTA_GROUP"]
 o = h.render(64, 128, False, c2w=c2w, H=5, W=7, focal=11.0, near=0.0, far=2.5, hist=hist, mma="fp32",
              want=("rgb0", "beta", "z_std", "raw"))
 net = synthetic_dfnet("DFNet").to(dev)
