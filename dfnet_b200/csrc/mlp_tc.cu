@@ -645,6 +645,63 @@ __global__ void __launch_bounds__(128, 1) k_tmem_rate(int iters, int nwarps, uns
   if (warp == 0) { tc_fence_after(); tmem_dealloc<1>(tslot, 512); }
 }
 
+// TMEM read rate UNDER tensor-pipe load: warp 4 issues back-to-back MMAs (M=128, N=256, K=16) into columns 256..511
+// while warps 0..nwarps-1 run the tcgen05.ld loop of k_tmem_rate on columns 0..255.
+__global__ void __launch_bounds__(160, 1) k_tmem_rate_mma(int iters, int nwarps, int mma_iters, unsigned long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t tslot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (65536 + 32768) / 16; i += 160) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) { mbar_init(smem_u32(&mbar), 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc<1>(smem_u32(&tslot), 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t sink = 0;
+  if (warp == 4) {
+    const uint32_t idesc = make_idesc(0, 256, 128);
+    const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+    const uint32_t a_lo = (smem_u32(smem) >> 4) | ((2048u >> 4) << 16);
+    const uint32_t b_lo = ((smem_u32(smem) + 65536) >> 4) | (256u << 16);
+    const long long t0 = clock64();
+    if (elect_one()) {
+      for (int it = 0; it < mma_iters; ++it) {
+#pragma unroll
+        for (int ks = 0; ks < 16; ++ks)
+          umma_f16<1>(tslot + 256, mk64(a_lo + ks * 256, desc_hi), mk64(b_lo + (ks & 1) * 512, desc_hi), idesc, 1u);
+      }
+      umma_commit<1>(smem_u32(&mbar));
+    }
+    __syncwarp();
+    mbar_wait(smem_u32(&mbar), 0, nullptr);
+    if ((tid & 31) == 0) out[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - t0);
+  } else if (warp < nwarps) {
+    const uint32_t tb = tslot + ((uint32_t)(warp * 32) << 16);
+    uint32_t v0[32], v1[32];
+    const long long t0 = clock64();
+    tmem_ld32(tb, v0);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int cb = 0; cb < 8; cb += 2) {
+        tmem_ld_wait(v0);
+        tmem_ld32(tb + (cb + 1) * 32, v1);
+        sink ^= v0[cb];
+        tmem_ld_wait(v1);
+        tmem_ld32(tb + ((cb + 2) & 7) * 32, v0);
+        sink ^= v1[cb];
+      }
+    }
+    tmem_ld_wait(v0);
+    const long long t1 = clock64();
+    if ((tid & 31) == 0) out[blockIdx.x * 8 + warp] = (unsigned long long)(t1 - t0) + (sink == 0x12345678u ? 1 : 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc<1>(tslot, 512); }
+}
+
 }  // namespace tc
 
 // ---------------------------------------------------------------------------------------
@@ -973,6 +1030,31 @@ extern "C" int dfb_debug_tmem_rate(int iters, int nwarps, int grid, double* cycl
   for (int b = 0; b < grid; ++b)
     for (int w = 0; w < nwarps; ++w) s += (double)h[b * 4 + w];
   *cycles_per_ld = s / ((double)grid * nwarps) / ((double)iters * 8.0);
+  return DFB_OK;
+}
+
+// Debug seam: the same while a fifth warp keeps the tensor pipe busy with `mma_iters` x 16 MMAs (M=128, N=256, K=16).
+// cycles[0] = mean cycles per tcgen05.ld per warp, cycles[1] = cycles per MMA as seen by the issuing warp.
+extern "C" int dfb_debug_tmem_rate_mma(int iters, int nwarps, int mma_iters, int grid, double* cycles) {
+  using namespace dfb;
+  DFB_REQUIRE(cycles && iters >= 1 && nwarps >= 1 && nwarps <= 4 && mma_iters >= 1 && grid >= 1 && grid <= 1024, DFB_ERR_INVALID, "bad arguments");
+  unsigned long long* d = nullptr;
+  DFB_CHECK_CUDA(cudaMalloc(&d, grid * 8 * 8));
+  DFB_CHECK_CUDA(cudaMemset(d, 0, grid * 8 * 8));
+  const int smem = 65536 + 32768;
+  DFB_CHECK_CUDA(cudaFuncSetAttribute(tc::k_tmem_rate_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  tc::k_tmem_rate_mma<<<grid, 160, smem>>>(iters, nwarps, mma_iters, d);
+  DFB_LAUNCH_CHECK();
+  std::vector<unsigned long long> h(grid * 8);
+  DFB_CHECK_CUDA(cudaMemcpy(h.data(), d, grid * 8 * 8, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  double s = 0, m = 0;
+  for (int b = 0; b < grid; ++b) {
+    for (int w = 0; w < nwarps; ++w) s += (double)h[b * 8 + w];
+    m += (double)h[b * 8 + 4];
+  }
+  cycles[0] = s / ((double)grid * nwarps) / ((double)iters * 8.0);
+  cycles[1] = m / grid / ((double)mma_iters * 16.0);
   return DFB_OK;
 }
 

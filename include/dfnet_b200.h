@@ -265,6 +265,9 @@ int dfb_debug_bwd_masks(uint32_t* simt_dump, const uint32_t* tc_in, uint32_t* tc
 int dfb_debug_umma_rate(int iters, int n, int grid, double* cycles_per_mma);
 /* Debug seam: TMEM read rate, mean cycles per tcgen05.ld.32x32b.x32 (4 KB) per warp with nwarps (1..4) warps of a CTA reading. */
 int dfb_debug_tmem_rate(int iters, int nwarps, int grid, double* cycles_per_ld);
+/* Debug seam: the same under tensor-pipe load (a fifth warp issues mma_iters x 16 MMAs M=128 N=256 K=16 meanwhile):
+ * cycles[0] = cycles per tcgen05.ld per warp, cycles[1] = cycles per MMA. */
+int dfb_debug_tmem_rate_mma(int iters, int nwarps, int mma_iters, int grid, double* cycles);
 
 int dfb_debug_umma_gemm(const float* A, const float* B, int N, int K, int kind, int variant, float* D, void* stream);
 

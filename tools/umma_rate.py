@@ -19,3 +19,8 @@ for grid in (1, 148):
         v = C.c_double()
         check(lib.dfb_debug_tmem_rate(2000, nw, grid, C.byref(v)))
         print(f"grid={grid:4d} warps={nw}: {v.value:7.1f} cycles per tcgen05.ld.32x32b.x32 (4 KB) per warp -> {nw * 4096 / v.value:6.1f} B/clk/SM")
+# TMEM reads while the tensor pipe is busy: 2000 x 8 loads per warp take ~450 k cycles alone; 4000 x 16 MMAs take ~8 M cycles
+for nw in (1, 4):
+    v = (C.c_double * 2)()
+    check(lib.dfb_debug_tmem_rate_mma(20000, nw, 4000, 148, v))
+    print(f"under MMA load, warps={nw}: {v[0]:7.1f} cycles per tcgen05.ld.32x32b.x32 per warp, {v[1]:6.1f} cycles per MMA (N=256)")
