@@ -410,7 +410,86 @@ int launch_raybias(const float* extra, int ld, int64_t N, const NetPack& np, boo
   return DFB_OK;
 }
 
+// Test-time fine compositing (C == 9, rgb / disp / acc only: the render_path step, rendering.py:196-242), one warp per
+// ray.  The ray's raw row (S x 9 floats) is staged in shared memory with coalesced loads and read once; the two
+// exclusive transmittance products (all densities / static only) are float64 warp scans over contiguous per-lane
+// segments instead of a serial loop on one lane.  The association of the products therefore differs from ATen's
+// serial cumprod by float64 rounding; nothing downstream of this kernel decides a sample index (the coarse pass,
+// which does, stays on k_composite), and rgb / disp / acc are gated at 1e-4 relative.
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_composite_fine_tt(CompositeArgs a) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  if (ray >= a.N) return;
+  const int S = a.S;
+  float* rw = sm + (size_t)warp * (10 * S + 4);  // raw [S][9]
+  float* zz = rw + 9 * S;                        // z [S]
+  {
+    const float* src = a.raw + ray * S * 9;
+    for (int i = lane; i < 9 * S; i += 32) rw[i] = __ldcs(src + i);
+    const float* zs = a.z + ray * S;
+    for (int i = lane; i < S; i += 32) zz[i] = zs[i];
+  }
+  __syncwarp();
+  const int per = (S + 31) / 32, i0 = min(lane * per, S), i1 = min(i0 + per, S);
+  // pass 1: this lane's segment products of (1 - alpha) and (1 - alpha_static)
+  double p_all = 1.0, p_st = 1.0;
+  for (int i = i0; i < i1; ++i) {
+    const float delta = (i + 1 < S) ? __fsub_rn(zz[i + 1], zz[i]) : 1e2f;
+    const float ss = rw[i * 9 + 3], st = rw[i * 9 + 7];
+    p_all *= (double)__fsub_rn(1.f, __fsub_rn(1.f, expf(__fmul_rn(-delta, __fadd_rn(ss, st)))));
+    p_st *= (double)__fsub_rn(1.f, __fsub_rn(1.f, expf(__fmul_rn(-delta, ss))));
+  }
+  // exclusive scan over lanes
+  double e_all = p_all, e_st = p_st;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double u = __shfl_up_sync(0xffffffffu, e_all, o), v = __shfl_up_sync(0xffffffffu, e_st, o);
+    if (lane >= o) e_all *= u, e_st *= v;
+  }
+  e_all = __shfl_up_sync(0xffffffffu, e_all, 1), e_st = __shfl_up_sync(0xffffffffu, e_st, 1);
+  if (lane == 0) e_all = 1.0, e_st = 1.0;
+  // pass 2: weights and sums
+  float s_acc = 0.f, s_depth = 0.f, s_r[3] = {0, 0, 0}, t_r[3] = {0, 0, 0};
+  double t_all = e_all, t_st = e_st;
+  for (int i = i0; i < i1; ++i) {
+    const float delta = (i + 1 < S) ? __fsub_rn(zz[i + 1], zz[i]) : 1e2f;
+    const float ss = rw[i * 9 + 3], st = rw[i * 9 + 7];
+    const float ea = expf(__fmul_rn(-delta, __fadd_rn(ss, st))), es = expf(__fmul_rn(-delta, ss));
+    const float al = __fsub_rn(1.f, ea), als = __fsub_rn(1.f, es), alt = __fsub_rn(1.f, expf(__fmul_rn(-delta, st)));
+    const float Ti = (float)t_all, Tsi = (float)t_st;
+    const float w = __fmul_rn(al, Ti), sw = __fmul_rn(als, Ti), tw = __fmul_rn(alt, Ti);
+    s_acc += w;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      s_r[c] += __fmul_rn(sw, rw[i * 9 + c]);
+      t_r[c] += __fmul_rn(tw, rw[i * 9 + 4 + c]);
+    }
+    s_depth += __fmul_rn(__fmul_rn(als, Tsi), zz[i]);
+    t_all *= (double)__fsub_rn(1.f, al), t_st *= (double)__fsub_rn(1.f, als);
+  }
+  s_acc = warp_sum(s_acc);
+  s_depth = warp_sum(s_depth);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) s_r[c] = warp_sum(s_r[c]), t_r[c] = warp_sum(t_r[c]);
+  if (lane == 0) {
+    if (a.acc) a.acc[ray] = s_acc;
+    if (a.rgb)
+      for (int c = 0; c < 3; ++c) a.rgb[ray * 3 + c] = __fadd_rn(s_r[c], t_r[c]);
+    if (a.disp) a.disp[ray] = __fdiv_rn(1.f, fmaxf(1e-10f, __fdiv_rn(s_depth, s_acc)));
+  }
+}
+
 int launch_composite(const CompositeArgs& a, cudaStream_t st) {
+  // render_path step: fine pass at test time with only rgb / disp / acc wanted
+  if (a.C == 9 && a.typ_fine && a.test_time && !a.weights && !a.tsig && !a.beta && !a.depth) {
+    const size_t smem_f = (size_t)kWarpsPerBlock * (10 * a.S + 4) * sizeof(float);
+    if (smem_f <= 48 * 1024) {
+      k_composite_fine_tt<<<(unsigned)((a.N + kWarpsPerBlock - 1) / kWarpsPerBlock), kWarpsPerBlock * 32, smem_f, st>>>(a);
+      DFB_LAUNCH_CHECK();
+      return DFB_OK;
+    }
+  }
   const int blocks = (int)((a.N + kWarpsPerBlock - 1) / kWarpsPerBlock);
   const size_t smem = (size_t)kWarpsPerBlock * 4 * a.S * sizeof(float);
   DFB_REQUIRE(smem <= 48 * 1024, DFB_ERR_UNSUPPORTED, "samples per ray %d too large for the compositing kernel", a.S);

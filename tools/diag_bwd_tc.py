@@ -10,7 +10,15 @@ root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, root)
 sys.path.insert(0, os.path.join(root, "tests"))
 from dfnet_b200 import nerfw, ops  # noqa: E402
-from oracle import nerf_oracle as O  # noqa: E402
+
+def ray_records(o, d, near, far, hist):
+    """[N, 11+hist_bin] records [o3, d3, near, far, viewdir3, hist] (reference rendering.py:366-389)."""
+    o, d = o.reshape(-1, 3).float(), d.reshape(-1, 3).float()
+    n = o.shape[0]
+    vd = d / d.norm(dim=-1, keepdim=True)
+    nf = torch.ones(n, 1, device=o.device)
+    return torch.cat([o, d, near * nf, far * nf, vd, torch.as_tensor(hist, device=o.device).float().reshape(1, -1).expand(n, -1)], -1).contiguous()
+
 
 dev = torch.device("cuda:0")
 mods = nerfw.make_synthetic_nerf(D=8, W=256)
@@ -19,7 +27,7 @@ Hh, Ww = int(os.environ.get("DH", 40)), int(os.environ.get("DW", 50))
 c2w = torch.tensor([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 1.0]], device=dev)
 hist = np.array([[5, 10, 20, 30, 15, 10, 5, 3, 1, 1]], np.float32)
 o, d = ops.get_rays(Hh, Ww, 45.0, c2w)
-rec = torch.tensor(O.make_ray_records(o.reshape(-1, 3).cpu().numpy(), d.reshape(-1, 3).cpu().numpy(), 0.0, 2.5, hist), device=dev)
+rec = ray_records(o, d, 0.0, 2.5, hist)
 rng = np.random.RandomState(7)
 g_rgb = torch.tensor((rng.randn(Hh * Ww, 3) * 1e-7).astype(np.float32), device=dev)
 for mma in ("f16", "bf16"):
@@ -48,7 +56,7 @@ for mma in ("f16", "bf16"):
 
 # saved-mask path (no forward recompute) vs recompute, 19 200 rays (cfg4 render size)
 o2, d2 = ops.get_rays(120, 160, 146.25, c2w)
-rec2 = torch.tensor(O.make_ray_records(o2.reshape(-1, 3).cpu().numpy(), d2.reshape(-1, 3).cpu().numpy(), 0.0, 2.5, hist), device=dev)
+rec2 = ray_records(o2, d2, 0.0, 2.5, hist)
 g2 = torch.tensor((rng.randn(120 * 160, 3) * 1e-7).astype(np.float32), device=dev)
 for want in (("z_vals", "raw"), ("z_vals", "raw", "relu_masks")):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]

@@ -12,6 +12,15 @@ from dfnet_b200.dfnet import feature_loss  # noqa: E402
 from dfnet_b200.misc import mse, triplet_loss_hard_negative_mining_plus, upsample_bicubic  # noqa: E402
 from helpers import synthetic_dfnet  # noqa: E402
 
+def ray_records(o, d, near, far, hist):
+    """[N, 11+hist_bin] records [o3, d3, near, far, viewdir3, hist] (reference rendering.py:366-389)."""
+    o, d = o.reshape(-1, 3).float(), d.reshape(-1, 3).float()
+    n = o.shape[0]
+    vd = d / d.norm(dim=-1, keepdim=True)
+    nf = torch.ones(n, 1, device=o.device)
+    return torch.cat([o, d, near * nf, far * nf, vd, torch.as_tensor(hist, device=o.device).float().reshape(1, -1).expand(n, -1)], -1).contiguous()
+
+
 dev = torch.device("cuda:0")
 mods = nerfw.make_synthetic_nerf(D=8, W=256)
 h = ops.NerfHandle(*[m.to(dev) for m in mods])
@@ -20,10 +29,8 @@ hist = torch.tensor([5, 10, 20, 30, 15, 10, 5, 3, 1, 1.0], device=dev)
 for mma in ("f16", "bf16", "fp32"):
     o = h.render(64, 128, True, c2w=c2w, H=9, W=13, focal=11.0, near=0.0, far=2.5, hist=hist, mma=mma)
 # training forward with saved ReLU masks + tcgen05 backward (saved masks and forward recompute), fp32 backward, 1-CTA kernel
-from oracle import nerf_oracle as O  # noqa: E402
 ro, rd = ops.get_rays(9, 13, 11.0, c2w)
-rec = torch.tensor(O.make_ray_records(ro.reshape(-1, 3).cpu().numpy(), rd.reshape(-1, 3).cpu().numpy(), 0.0, 2.5,
-                                      hist.cpu().numpy()[None]), device=dev)
+rec = ray_records(ro, rd, 0.0, 2.5, hist)
 g = torch.randn(9 * 13, 3, device=dev) * 1e-6
 for mma in ("f16", "bf16"):
     t = h.render(64, 128, True, rays=rec, mma=mma, want=("z_vals", "raw", "relu_masks"))
