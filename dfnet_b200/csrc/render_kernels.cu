@@ -113,22 +113,46 @@ __global__ void k_raybias(const float* __restrict__ extra, int ld, int64_t N, in
                           const float* __restrict__ dirx_w, const float* __restrict__ dirx_b,
                           const float* __restrict__ tx_w, const float* __restrict__ tx_b, float* __restrict__ rb,
                           int n_rb, int rb_ld, const float* __restrict__ add_bias, int pack_kind) {
-  // block = n_rb threads (one output column each), 8 rays per block
+  // block = n_rb threads (one output column each), 8 rays per block.  Every weight is loaded once per block and
+  // applied to the 8 rays from registers; the ray-constant inputs are read from shared memory as float4 over k
+  // (per (ray, column) the accumulation still runs over k in order, so results are unchanged).
   extern __shared__ float sm[];
   const int64_t r0 = (int64_t)blockIdx.x * 8;
   const int nloc = (int)min((int64_t)8, N - r0);
-  const int ne = nd + nt;
-  for (int i = threadIdx.x; i < nloc * ne; i += blockDim.x) sm[i] = extra[(r0 + i / ne) * ld + i % ne];
+  const int ndp = (nd + 3) & ~3, ntp = (nt + 3) & ~3;
+  float* smd = sm;             // [8][ndp] inputs of dir_encoding (zero padded)
+  float* smt = sm + 8 * ndp;   // [8][ntp] inputs of transient_encoding.0
+  for (int i = threadIdx.x; i < 8 * (ndp + ntp); i += blockDim.x) {
+    const bool t = i >= 8 * ndp;
+    const int ii = t ? i - 8 * ndp : i, wdt = t ? ntp : ndp, rl = ii / wdt, k = ii % wdt;
+    sm[i] = (rl < nloc && k < (t ? nt : nd)) ? extra[(r0 + rl) * ld + (t ? nd : 0) + k] : 0.f;
+  }
   __syncthreads();
   const int n = min((int)threadIdx.x, n_rb - 1);
   const bool tr = n >= Hh;
   const int col = tr ? n - Hh : n;
   const float* w = tr ? tx_w : dirx_w;
-  const int k0 = tr ? nd : 0, kn = tr ? nt : nd;
+  const float* xin = tr ? smt : smd;
+  const int kn = tr ? nt : nd, kp = tr ? ntp : ndp;
   const float b = tr ? tx_b[col] : dirx_b[col];
-  for (int rl = 0; rl < nloc; ++rl) {
-    float acc = 0.f;
-    for (int k = 0; k < kn; ++k) acc = fmaf(sm[rl * ne + k0 + k], w[k * Hh + col], acc);
+  float accs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int k = 0; k < kn; k += 4) {
+    float wk[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) wk[e] = k + e < kn ? __ldg(w + (size_t)(k + e) * Hh + col) : 0.f;
+#pragma unroll
+    for (int rl = 0; rl < 8; ++rl) {
+      const float4 x = *reinterpret_cast<const float4*>(xin + rl * kp + k);
+      accs[rl] = fmaf(x.x, wk[0], accs[rl]);
+      if (k + 1 < kn) accs[rl] = fmaf(x.y, wk[1], accs[rl]);
+      if (k + 2 < kn) accs[rl] = fmaf(x.z, wk[2], accs[rl]);
+      if (k + 3 < kn) accs[rl] = fmaf(x.w, wk[3], accs[rl]);
+    }
+  }
+#pragma unroll
+  for (int rl = 0; rl < 8; ++rl) {
+    if (rl >= nloc) break;
+    const float acc = accs[rl];
     float v = acc + b;
     if (add_bias) v += add_bias[n];  // constant part of the consuming layer's bias (tcgen05 path, see mlp_tc.cu)
     if (pack_kind == 0) {
@@ -401,7 +425,7 @@ int launch_raybias(const float* extra, int ld, int64_t N, const NetPack& np, boo
   const int n_rb = with_transient ? 2 * Hh : Hh;
   const int blocks = (int)((N + 7) / 8);
   const int threads = round_up(n_rb, 32);
-  const size_t smem = 8 * (nd + nt) * sizeof(float);
+  const size_t smem = 8 * (((nd + 3) & ~3) + ((nt + 3) & ~3)) * sizeof(float);
   const float* b = np.blob32;
   k_raybias<<<blocks, threads, smem, st>>>(extra, ld, N, nd, nt, Hh, b + np.dirx_w, b + np.dirx_b,
                                             with_transient ? b + np.tx_w : nullptr,
@@ -426,7 +450,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_composite_fine_tt(Compo
   float* zz = rw + 9 * S;                        // z [S]
   {
     const float* src = a.raw + ray * S * 9;
-    for (int i = lane; i < 9 * S; i += 32) rw[i] = __ldcs(src + i);
+    if ((S & 3) == 0) {  // 16-byte copies: the row (S x 36 B) and the shared-memory slot are 16-byte aligned
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      float4* d4 = reinterpret_cast<float4*>(rw);
+      for (int i = lane; i < 9 * S / 4; i += 32) d4[i] = __ldcs(s4 + i);
+    } else {
+      for (int i = lane; i < 9 * S; i += 32) rw[i] = __ldcs(src + i);
+    }
     const float* zs = a.z + ray * S;
     for (int i = lane; i < S; i += 32) zz[i] = zs[i];
   }
