@@ -293,9 +293,8 @@ __global__ void k_bn_finalize(const double* __restrict__ part, double n, const f
   stat[c] = (float)mean, stat[128 + c] = (float)var, stat[256 + c] = sc, stat[384 + c] = beta[c] - (float)mean * sc;
 }
 // y = x * scale[c] + shift[c]; images [0,Bs) go to out_t, [Bs,B) to out_r (siamese split; out_r unused when Bs == B)
-__global__ void __launch_bounds__(256) k_bn_apply(const float* __restrict__ x, int B, int Bs, int64_t plane,
-                                                  const float* __restrict__ stat, float* __restrict__ out_t,
-                                                  float* __restrict__ out_r) {
+__global__ void __launch_bounds__(256) k_bn_apply(const float* x, int B, int Bs, int64_t plane,
+                                                  const float* __restrict__ stat, float* out_t, float* out_r) {  // x may alias out_t
   const int bc = blockIdx.y, b = bc / 128, c = bc % 128;
   const float sc = stat[256 + c], shf = stat[384 + c];
   const float* src = x + (size_t)bc * plane;

@@ -395,7 +395,7 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
     int lp = 0;
     for (int64_t p = unit0; p < a.n_pass; p += n_units, ++lp)
       for (int slot = 0; slot < 2; ++slot) {
-        if (lp > 0) mbar_wait(bar(PE_FREE + slot), (lp - 1) & 1, a.error_flag);
+        if (lp > 0) mbar_wait_relaxed(bar(PE_FREE + slot), (lp - 1) & 1, a.error_flag);
         int64_t g = ((2 * p + slot) * CG + rank) * kTileM + r;
         g = g < a.P ? g : a.P - 1;
         const int64_t ray = g / a.S;

@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_tc_bwd(const __grid_constan
     int lp = 0;
     for (int64_t p = blockIdx.x; p < a.n_pass; p += gridDim.x, ++lp)
       for (int slot = 0; slot < 2; ++slot) {
-        if (lp > 0) mbar_wait(bar(PE_FREE + slot), (lp - 1) & 1, a.error_flag);
+        if (lp > 0) mbar_wait_relaxed(bar(PE_FREE + slot), (lp - 1) & 1, a.error_flag);
         int64_t g = (2 * p + slot) * kTileM + r;
         g = g < a.P ? g : a.P - 1;
         const int64_t ray = g / a.S;

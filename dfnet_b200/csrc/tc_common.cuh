@@ -50,6 +50,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
     }
   }
 }
+// Wait with back-off for roles that have a whole pass of slack (the positional-encoding warps): they sleep between
+// polls instead of competing with the epilogue warps for issue slots (and burning power under the 1 kW cap).
+template <int NS = 200>
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, int* error_flag) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = globaltimer();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(NS);
+    if (globaltimer() - t0 > 4000000000ull) {
+      if (error_flag) atomicExch(error_flag, 1 + (int)(bar & 0xff));
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
