@@ -16,7 +16,7 @@ SYMBOLS = [
     "dfb_render_fwd", "dfb_render_image_host", "dfb_render_bwd", "dfb_render_bwd_mma", "dfb_render_bwd_saved", "dfb_render_bwd_workspace_bytes", "dfb_sample_pdf", "dfb_raw2outputs", "dfb_get_rays",
     "dfb_launch_count", "dfb_profile_enable", "dfb_profile_read", "dfb_debug_umma_gemm", "dfb_debug_umma_gemm_mn", "dfb_debug_tc_prof", "dfb_debug_bwd_masks", "dfb_debug_umma_rate", "dfb_debug_tmem_rate", "dfb_debug_tmem_rate_mma", "dfb_conv_create", "dfb_conv_destroy", "dfb_conv_fwd",
     "dfb_dfnet_create", "dfb_dfnet_destroy", "dfb_dfnet_load", "dfb_dfnet_workspace_bytes", "dfb_dfnet_fwd",
-    "dfb_cosine_loss", "dfb_triplet_loss", "dfb_mse", "dfb_resize_bicubic", "dfb_resize_bilinear_ac",
+    "dfb_cosine_loss", "dfb_triplet_loss", "dfb_triplet_loss_bwd", "dfb_mse", "dfb_resize_bicubic", "dfb_resize_bilinear_ac",
     "dfb_conv_create_ex", "dfb_conv_fwd_ex", "dfb_conv_wgrad", "dfb_dfnet_load_ex", "dfb_dfnet_bn_batch_stats", "dfb_dfnet_tape_bytes", "dfb_debug_dfnet_tape_layout",
     "dfb_dfnet_bwd_workspace_bytes", "dfb_dfnet_bwd", "dfb_cosine_loss_bwd", "dfb_mse_bwd", "dfb_resize_bicubic_bwd",
     "dfb_resize_bilinear_ac_bwd",
@@ -113,6 +113,7 @@ def _load():
     lib.dfb_dfnet_fwd.argtypes = [vp, vp, i32, i32, i32, C.c_uint32, i32, i32, vp, vp, vp, vp, C.c_size_t, vp]
     lib.dfb_cosine_loss.argtypes = [vp, vp, i32, i64, i32, f32, vp, vp, C.c_size_t, vp]
     lib.dfb_triplet_loss.argtypes = [vp, vp, i32, i32, i32, i32, i32, f32, vp, vp, vp, C.c_size_t, vp]
+    lib.dfb_triplet_loss_bwd.argtypes = [vp, vp, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp]
     lib.dfb_mse.argtypes = [vp, vp, i64, vp, vp, C.c_size_t, vp]
     lib.dfb_resize_bicubic.argtypes = [vp, i64, i32, i32, i32, i32, vp, vp]
     lib.dfb_resize_bilinear_ac.argtypes = [vp, i64, i32, i32, i32, i32, vp, vp]

@@ -702,6 +702,51 @@ __global__ void k_triplet_hinge_partial(const float* __restrict__ f1, const floa
   if (threadIdx.x == 0) ws[blockIdx.x] = v;
 }
 
+// adjoint of k_triplet_hinge_partial: d loss / d f1, d f2 for the chosen case (the case selection itself is a
+// no-grad block in the reference, feature/misc.py:414-421).  One warp per row; every element receives at most two
+// contributions (as anchor or positive of its own row, as negative of the row that rolls onto it), so the
+// atomic adds onto the zeroed outputs are order independent.
+__global__ void k_triplet_hinge_bwd(const float* __restrict__ f1, const float* __restrict__ f2, int B, int64_t rows_per_b, int W,
+                                    int64_t n_rows, float margin, const int* __restrict__ chosen, const float* __restrict__ g_loss,
+                                    float* __restrict__ g_f1, float* __restrict__ g_f2) {
+  const int cs = *chosen;
+  const bool a1 = (cs == 0 || cs == 2), n2 = (cs == 0 || cs == 3);
+  const float* A = a1 ? f1 : f2;
+  const float* P = a1 ? f2 : f1;
+  const float* N = n2 ? f2 : f1;
+  float* gA = a1 ? g_f1 : g_f2;
+  float* gP = a1 ? g_f2 : g_f1;
+  float* gN = n2 ? g_f2 : g_f1;
+  const float coef = *g_loss / (float)n_rows;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int64_t row = (int64_t)blockIdx.x * wpb + warp; row < n_rows; row += (int64_t)gridDim.x * wpb) {
+    const int64_t lb = row / rows_per_b, rin = row % rows_per_b;
+    const int b = (int)(lb % B);
+    const int64_t l = lb / B;
+    const int64_t rrow = (l * B + (b + B - 1) % B) * rows_per_b + rin;
+    const float* a = A + row * W;
+    const float* p = P + row * W;
+    const float* ng = N + rrow * W;
+    float dap = 0.f, dan = 0.f;
+    for (int x = lane; x < W; x += 32) {
+      const float av = a[x];
+      const float u = av - p[x] + 1e-6f, v = av - ng[x] + 1e-6f;
+      dap = fmaf(u, u, dap), dan = fmaf(v, v, dan);
+    }
+    for (int d = 16; d > 0; d >>= 1) dap += __shfl_xor_sync(0xffffffffu, dap, d), dan += __shfl_xor_sync(0xffffffffu, dan, d);
+    const float sap = sqrtf(dap), san = sqrtf(dan);
+    if (!(sap - san + margin > 0.f)) continue;   // clamp_min(., 0): no gradient on the flat side
+    const float iap = sap > 0.f ? coef / sap : 0.f, ian = san > 0.f ? coef / san : 0.f;
+    for (int x = lane; x < W; x += 32) {
+      const float av = a[x];
+      const float u = (av - p[x] + 1e-6f) * iap, v = (av - ng[x] + 1e-6f) * ian;
+      atomicAdd(gA + row * W + x, u - v);
+      atomicAdd(gP + row * W + x, -u);
+      atomicAdd(gN + rrow * W + x, v);
+    }
+  }
+}
+
 __global__ void k_scaled_sum(const float* __restrict__ ws, int n, float scale, float* __restrict__ out) {
   __shared__ float sm[32];
   float v = 0.f;
@@ -743,6 +788,22 @@ extern "C" int dfb_triplet_loss(const float* f1, const float* f2, int L, int B, 
   k_triplet_hinge_partial<<<nb2, 256, 0, st>>>(f1, f2, B, rows_per_b, W, n_rows, margin, chosen_case, w + 4104);
   DFB_LAUNCH_CHECK();
   k_scaled_sum<<<1, 256, 0, st>>>(w + 4104, nb2, 1.f / (float)n_rows, loss);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+// Backward of dfb_triplet_loss: chosen_case is the forward's device scalar, g_loss the upstream gradient (device
+// scalar); g_f1, g_f2 [L,B,C,H,W] are overwritten.
+extern "C" int dfb_triplet_loss_bwd(const float* f1, const float* f2, int L, int B, int Cc, int H, int W, float margin,
+                                    const int* chosen_case, const float* g_loss, float* g_f1, float* g_f2, void* stream) {
+  DFB_REQUIRE(f1 && f2 && chosen_case && g_loss && g_f1 && g_f2, DFB_ERR_INVALID, "null argument");
+  DFB_REQUIRE(L >= 1 && B >= 1 && Cc >= 1 && H >= 1 && W >= 1, DFB_ERR_INVALID, "empty feature stack");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t rows_per_b = (int64_t)Cc * H, n_rows = (int64_t)L * B * rows_per_b;
+  DFB_CHECK_CUDA(cudaMemsetAsync(g_f1, 0, (size_t)n_rows * W * 4, st));
+  DFB_CHECK_CUDA(cudaMemsetAsync(g_f2, 0, (size_t)n_rows * W * 4, st));
+  const int nb = (int)std::min<int64_t>(4096, (n_rows + 7) / 8);
+  dfb::k_triplet_hinge_bwd<<<nb, 256, 0, st>>>(f1, f2, B, rows_per_b, W, n_rows, margin, chosen_case, g_loss, g_f1, g_f2);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }

@@ -17,17 +17,46 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def triplet_loss_hard_negative_mining_plus(f1, f2, margin=1.):
-    """Reference feature/misc.py:399-435.  f1, f2: [lvl, B, C, H, W] -> scalar loss.
-    `.chosen_case` of the returned tensor's companion is available through `last_triplet_case`."""
-    if not f1.is_cuda:
-        raise _lib.DfbError("triplet loss inputs must be CUDA tensors")
-    a, b = f1.detach().float().contiguous(), f2.detach().float().contiguous()
+def _triplet_fwd(a, b, margin):
     L, B, Cc, H, W = a.shape
     loss = torch.empty((), device=a.device)
     case = torch.empty((), device=a.device, dtype=torch.int32)
     ws = torch.empty(8192, device=a.device)
     check(lib.dfb_triplet_loss(_p(a), _p(b), L, B, Cc, H, W, float(margin), _p(loss), _p(case), _p(ws), ws.numel() * 4, _stream()))
+    return loss, case
+
+
+class _TripletFn(torch.autograd.Function):
+    """dfb_triplet_loss with dfb_triplet_loss_bwd (the mined case is a constant of the backward, as in the reference,
+    where the four distances are computed under torch.no_grad())."""
+
+    @staticmethod
+    def forward(ctx, f1, f2, margin):
+        a, b = f1.detach().float().contiguous(), f2.detach().float().contiguous()
+        loss, case = _triplet_fwd(a, b, margin)
+        ctx.save_for_backward(a, b, case)
+        ctx.margin = float(margin)
+        triplet_loss_hard_negative_mining_plus.last_case = case
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b, case = ctx.saved_tensors
+        L, B, Cc, H, W = a.shape
+        g = g.float().contiguous()
+        ga, gb = torch.empty_like(a), torch.empty_like(b)
+        check(lib.dfb_triplet_loss_bwd(_p(a), _p(b), L, B, Cc, H, W, ctx.margin, _p(case), _p(g), _p(ga), _p(gb), _stream()))
+        return (ga if ctx.needs_input_grad[0] else None, gb if ctx.needs_input_grad[1] else None, None)
+
+
+def triplet_loss_hard_negative_mining_plus(f1, f2, margin=1.):
+    """Reference feature/misc.py:399-435.  f1, f2: [lvl, B, C, H, W] -> scalar loss (differentiable w.r.t. f1, f2).
+    The mined case of the last call is available as `triplet_loss_hard_negative_mining_plus.last_case`."""
+    if not f1.is_cuda:
+        raise _lib.DfbError("triplet loss inputs must be CUDA tensors")
+    if torch.is_grad_enabled() and (f1.requires_grad or f2.requires_grad):
+        return _TripletFn.apply(f1, f2, margin)
+    loss, case = _triplet_fwd(f1.detach().float().contiguous(), f2.detach().float().contiguous(), margin)
     triplet_loss_hard_negative_mining_plus.last_case = case
     return loss
 

@@ -234,6 +234,10 @@ int dfb_resize_bilinear_ac(const float* src, int64_t planes, int h, int w, int H
  * scalars; ws >= 8192 floats. */
 int dfb_triplet_loss(const float* f1, const float* f2, int L, int B, int C, int H, int W, float margin, float* loss,
                      int* chosen_case, void* ws, size_t ws_bytes, void* stream);
+/* Backward of dfb_triplet_loss (the case selection is a no-grad block in the reference): chosen_case = the forward's
+ * device scalar, g_loss = upstream gradient (device scalar); g_f1, g_f2 [L,B,C,H,W] are overwritten. */
+int dfb_triplet_loss_bwd(const float* f1, const float* f2, int L, int B, int C, int H, int W, float margin,
+                         const int* chosen_case, const float* g_loss, float* g_f1, float* g_f2, void* stream);
 /* mean((a-b)^2): nn.MSELoss in PoseLoss (feature/direct_feature_matching.py:138-142) and img2mse
  * (models/nerfw.py:11).  ws >= 1024 floats. */
 int dfb_mse(const float* a, const float* b, int64_t n, float* out, void* ws, size_t ws_bytes, void* stream);

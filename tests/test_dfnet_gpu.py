@@ -175,6 +175,32 @@ def test_triplet_loss_vs_reference_golden(g, k):
     assert abs(float(loss) - float(np.asarray(g[f"trip_{k}_loss"]).reshape(-1)[0])) < 1e-5 + 1e-4 * abs(float(np.asarray(g[f"trip_{k}_loss"]).reshape(-1)[0]))
 
 
+@pytest.mark.parametrize("k", [0, 1, 2, 3])
+def test_triplet_loss_backward_vs_torch_autograd(g, k):
+    """dfb_triplet_loss_bwd against float64 autograd of a torch restatement of the reference function
+    (feature/misc.py:399-435: roll over the batch, no-grad case mining, TripletMarginLoss over the last dim)."""
+    from dfnet_b200.misc import triplet_loss_hard_negative_mining_plus as trip
+    f1 = torch.tensor(g[f"trip_{k}_f1"], device=dev(), requires_grad=True)
+    f2 = torch.tensor(g[f"trip_{k}_f2"], device=dev(), requires_grad=True)
+    loss = trip(f1, f2, margin=1.0)
+    assert int(trip.last_case) == k
+    (loss * 3.0).backward()
+    a, b = f1.detach().double().requires_grad_(True), f2.detach().double().requires_grad_(True)
+    an, ng = torch.roll(a, 1, 1), torch.roll(b, 1, 1)
+    crit = torch.nn.TripletMarginLoss(margin=1.0, reduction="mean")
+    ref = [crit(a, b, ng), crit(b, a, an), crit(a, b, an), crit(b, a, ng)][k]
+    assert abs(float(loss.detach()) - float(ref.detach())) < 1e-5
+    (ref * 3.0).backward()
+    for got, want in ((f1.grad, a.grad), (f2.grad, b.grad)):
+        assert float((got.double() - want).abs().max()) < 1e-5 * float(want.abs().max()) + 1e-12
+    # B = 1: the roll is the identity (negative == anchor or positive); and no graph when nothing requires grad
+    x = torch.randn(2, 1, 4, 3, 33, device=dev(), requires_grad=True)
+    y = torch.randn(2, 1, 4, 3, 33, device=dev())
+    trip(x, y).backward()
+    assert torch.isfinite(x.grad).all()
+    assert not trip(x.detach(), y).requires_grad
+
+
 def test_triplet_and_mse_run_feature_shapes():
     """run_feature.py shapes: [3, B=4, 128, 60, 80] feature stacks; checked against the oracle."""
     from dfnet_b200.misc import mse, mse2psnr, triplet_loss_hard_negative_mining_plus as trip
