@@ -35,7 +35,7 @@ WsLayout ws_layout(const DfbNerf* n, const DfbRenderCfg* c, int64_t rays) {
   L.z_s = take((size_t)rays * std::max(Nf, 1) * 4);
   L.z_all = take((size_t)rays * S * 4);
   L.raw_f = take(Nf > 0 ? (size_t)rays * S * 9 * 4 : 0);
-  L.rb_f = take(Nf > 0 ? (size_t)rays * W * 4 : 0);
+  L.rb_f = take(Nf > 0 ? (size_t)rays * std::max(W, 256) * 4 : 0);  // 256-wide rows on the tcgen05 path
   L.total = off;
   return L;
 }
@@ -203,8 +203,9 @@ extern "C" int dfb_render_fwd(DfbNerf* n, const DfbRenderCfg* c, const float* ra
     float* rb_f = P(L.rb_f);
     // tcgen05 path: the per-ray bias carries the step's constant bias and is stored as packed 16-bit pairs
     const bool tc_f = c->mma_kind != DFB_MMA_FP32_SIMT && tc_supported(n, 1, MLP_FULL);
-    rc = launch_raybias(pa.extra, pa.n_extra, nr, n->net[1], true, rb_f, n->net[1].n_dt, st,
-                        tc_f ? n->net[1].tc_dtbias_dev : nullptr, tc_f ? (c->mma_kind == DFB_MMA_F16 ? 1 : 2) : 0);
+    rc = launch_raybias(pa.extra, pa.n_extra, nr, n->net[1], true, rb_f, tc_f ? 256 : n->net[1].n_dt, st,
+                        tc_f ? n->net[1].tc_dtbias_dev : nullptr, tc_f ? (c->mma_kind == DFB_MMA_F16 ? 1 : 2) : 0,
+                        tc_f ? 128 : 0);
     if (rc) return rc;
     float* raw_f = ex && ex->raw ? ex->raw + r0 * S * 9 : P(L.raw_f);
     uint32_t* masks = nullptr;
@@ -389,7 +390,7 @@ BwdWs bwd_layout(const DfbNerf* n, int64_t rays, int S) {
   L.rayrec = take((size_t)rays * kRayRec * 4);
   L.extra = take((size_t)rays * (27 + d.a_dim + d.t_dim) * 4);
   L.zdummy = take((size_t)rays * 4 + 256);
-  L.rb = take((size_t)rays * d.W * 4);
+  L.rb = take((size_t)rays * std::max(d.W, 256) * 4);
   L.g_raw = take((size_t)rays * S * 9 * 4);
   L.g_samp = take((size_t)rays * S * 32 * 4);
   L.total = off;
@@ -444,7 +445,9 @@ extern "C" int dfb_render_bwd_saved(DfbNerf* n, int mma_kind, const float* rays,
     DFB_CHECK_CUDA(cudaMemsetAsync(P(L.zdummy) + nr, 0, 4, st));
     int rc = launch_prep(pa, st);
     if (rc) return rc;
-    rc = launch_raybias(pa.extra, n_extra, nr, n->net[1], true, P(L.rb), n->net[1].n_dt, st);
+    const bool tc_b = mma_kind != DFB_MMA_FP32_SIMT && tc_bwd_supported(n);  // 256-wide (zero-padded) rows for the tcgen05 kernel
+    rc = launch_raybias(pa.extra, n_extra, nr, n->net[1], true, P(L.rb), tc_b ? 256 : n->net[1].n_dt, st, nullptr, 0,
+                        tc_b ? 128 : 0);
     if (rc) return rc;
     rc = launch_render_bwd(n, P(L.rayrec), z_vals + r0 * S, P(L.rb), raw + r0 * S * 9, g_rgb + r0 * 3, nr, S, P(L.g_raw),
                            P(L.g_samp), g_rays_o + r0 * 3, g_rays_d + r0 * 3, g_viewdirs + r0 * 3, mma_kind, st,

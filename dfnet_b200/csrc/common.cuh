@@ -122,6 +122,11 @@ int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const
                        const float* raybias, int64_t n_rays, int S, float* raw, cudaStream_t st,
                        uint32_t* masks = nullptr);
 bool tc_supported(const DfbNerf* nerf, int which, int mode);
+// Networks narrower than 256 run on the 256-wide tcgen05 kernels EXACTLY, embedded with zero weights / zero biases
+// (a ReLU unit with zero input weights and bias stays at 0 and feeds nothing): tc_pad_params returns the state dict
+// of the equivalent 8x256 network (state-dict order, hidden units 0..W-1 / 0..W/2-1 live).
+bool tc_padded_shape(const dfb::NetPack& np);
+std::vector<std::vector<float>> tc_pad_params(const dfb::NetPack& np, const std::vector<std::vector<float>>& P);
 int pack_tc_weights(DfbNerf* nerf, int which, const std::vector<std::vector<float>>& P);
 // tcgen05 backward of the fine network w.r.t. its inputs (mlp_tc_bwd.cu)
 int pack_tc_bwd_weights(DfbNerf* nerf, int which, const std::vector<std::vector<float>>& P);
@@ -187,8 +192,9 @@ struct SampleArgs {
 int launch_prep(const PrepArgs& a, cudaStream_t st);
 // add_bias [n_rb] (nullable): constant added to every row; pack_kind: 0 fp32 rows, 1 / 2 = fp16 / bf16 pairs
 // packed into the first n_rb/2 words of each row (what the tcgen05 forward kernel consumes)
+// pad_h (> W/2): row layout of the zero-padded 8x256 embedding: transient half at column pad_h, zeros elsewhere
 int launch_raybias(const float* extra, int ld, int64_t N, const NetPack& np, bool with_transient, float* rb,
-                   int rb_ld, cudaStream_t st, const float* add_bias = nullptr, int pack_kind = 0);
+                   int rb_ld, cudaStream_t st, const float* add_bias = nullptr, int pack_kind = 0, int pad_h = 0);
 int launch_composite(const CompositeArgs& a, cudaStream_t st);
 int launch_sample(const SampleArgs& a, cudaStream_t st);
 

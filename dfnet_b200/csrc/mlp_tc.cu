@@ -158,7 +158,7 @@ __device__ __forceinline__ void epi_block(const uint32_t (&v)[32], const TcArgs&
       const uint32_t xx = pack2<T>(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
       pk[q] = KIND == EPI_FINAL ? add2<T>(xx, a.btbl[off + q]) : add_relu2<T>(xx, a.btbl[off + q]);
     }
-    if (MK && KIND != EPI_FINAL) {
+    if (MK && KIND != EPI_FINAL && mrow) {
       uint32_t m = 0;
 #pragma unroll
       for (int q = 0; q < 16; ++q) m |= gt0_mask2<T>(pk[q]) & (0x00010001u << q);
@@ -185,7 +185,7 @@ __device__ __forceinline__ void epi_block(const uint32_t (&v)[32], const TcArgs&
       pk[q] = add_relu2<T>(pack2<T>(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), bw[e]);
     }
   }
-  if (MK) {
+  if (MK && mrow) {
     uint32_t m = 0;
 #pragma unroll
     for (int q = 0; q < 16; ++q) m |= gt0_mask2<T>(pk[q]) & (0x00010001u << q);
@@ -464,7 +464,10 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
           const int w0 = 4 * wg, n0 = 2 * wg;  // first 32-column block of this warpgroup (256- / 128-wide steps)
           constexpr bool MK = FULL == 2;
           uint32_t* mrow = nullptr;
-          if (MK) mrow = a.masks + ((((2 * p + slot) * CG + rank) * 12 + a.mlayer[s]) * 8) * 128 + r;
+          // (tiles past the end of the sample array exist when the tile count is not a multiple of the tiles per
+          // pass: they are computed on clamped rows but must not write masks — the buffer has ceil(P/128) tiles)
+          if (MK && ((2 * p + slot) * CG + rank) * kTileM < a.P)
+            mrow = a.masks + ((((2 * p + slot) * CG + rank) * 12 + a.mlayer[s]) * 8) * 128 + r;
           if (kd == EPI_HIDDEN) epi_blocks<T, EPI_HIDDEN, MK>(t_row, h_row, a, boff, w0, w0 + 4, rbs, mrow);
           else if (kd == EPI_T) epi_blocks<T, EPI_T, MK>(t_row, h_row, a, boff, n0, n0 + 2, rbs, mrow);
           else if (kd == EPI_DT) epi_blocks<T, EPI_DT, MK>(t_row, h_row, a, boff, w0, w0 + 4, rbs, mrow);
@@ -715,9 +718,56 @@ uint16_t f2b(float f) { __nv_bfloat16 h = __float2bfloat16_rn(f); uint16_t u; me
 
 }  // namespace
 
+bool tc_padded_shape(const NetPack& np) {
+  return np.D == 8 && np.skip == 4 && np.pek == 64 && np.W >= 32 && np.W <= 256 && np.W % 16 == 0;
+}
+
+std::vector<std::vector<float>> tc_pad_params(const NetPack& np, const std::vector<std::vector<float>>& P) {
+  const int W = np.W, H = W / 2, W2 = 256, H2 = 128, in_xyz = np.in_xyz;
+  if (W == W2) return P;
+  std::vector<std::vector<float>> Q(P.size());
+  // [rows x cols] -> [rows2 x cols2]; column c of the source goes to column cmap(c)
+  auto pad2 = [&](const std::vector<float>& src, int rows, int cols, int rows2, int cols2, auto cmap) {
+    std::vector<float> dst((size_t)rows2 * cols2, 0.f);
+    for (int r = 0; r < rows; ++r)
+      for (int c = 0; c < cols; ++c) dst[(size_t)r * cols2 + cmap(c)] = src[(size_t)r * cols + c];
+    return dst;
+  };
+  auto pad1 = [&](const std::vector<float>& src, int n2) {
+    std::vector<float> dst(n2, 0.f);
+    std::copy(src.begin(), src.end(), dst.begin());
+    return dst;
+  };
+  auto ident = [](int c) { return c; };
+  for (int i = 0; i < 8; ++i) {
+    if (i == 0) Q[0] = pad2(P[0], W, in_xyz, W2, in_xyz, ident);
+    else if (i == 4) Q[8] = pad2(P[8], W, in_xyz + W, W2, in_xyz + W2, ident);  // cat([input_xyz, h]): h columns stay adjacent
+    else Q[2 * i] = pad2(P[2 * i], W, W, W2, W2, ident);
+    Q[2 * i + 1] = pad1(P[2 * i + 1], W2);
+  }
+  Q[16] = pad2(P[16], W, W, W2, W2, ident), Q[17] = pad1(P[17], W2);  // xyz_encoding_final
+  const int nd = np.in_dir + np.a_dim;
+  // dir_encoding [H, W + in_dir (+ a)]: the ray-constant columns move behind the 256 hidden columns
+  Q[18] = pad2(P[18], H, W + nd, H2, W2 + nd, [&](int c) { return c < W ? c : W2 + (c - W); });
+  Q[19] = pad1(P[19], H2);
+  Q[20] = pad2(P[20], 1, W, 1, W2, ident), Q[21] = P[21];             // static_sigma
+  Q[22] = pad2(P[22], 3, H, 3, H2, ident), Q[23] = P[23];             // static_rgb
+  if (np.fine) {
+    Q[24] = pad2(P[24], H, W + np.t_dim, H2, W2 + np.t_dim, [&](int c) { return c < W ? c : W2 + (c - W); });
+    Q[25] = pad1(P[25], H2);
+    for (int i = 0; i < 3; ++i) Q[26 + 2 * i] = pad2(P[26 + 2 * i], H, H, H2, H2, ident), Q[27 + 2 * i] = pad1(P[27 + 2 * i], H2);
+    Q[32] = pad2(P[32], 1, H, 1, H2, ident), Q[33] = P[33];           // transient_sigma
+    Q[34] = pad2(P[34], 3, H, 3, H2, ident), Q[35] = P[35];           // transient_rgb
+    Q[36] = pad2(P[36], 1, H, 1, H2, ident), Q[37] = P[37];           // transient_beta
+  }
+  for (size_t i = 0; i < P.size(); ++i)
+    if (Q[i].empty()) Q[i] = P[i];
+  return Q;
+}
+
 bool tc_supported(const DfbNerf* n, int which, int mode) {
   const NetPack& np = n->net[which];
-  if (!np.loaded || np.W != 256 || np.D != 8 || np.skip != 4 || np.pek != 64) return false;
+  if (!np.loaded || !tc_padded_shape(np)) return false;
   if (np.blob16[0][0] == nullptr || np.tc_tbl.empty()) return false;
   if (mode == MLP_SIGMA) return true;
   if (mode == MLP_FULL) return np.fine;
@@ -764,13 +814,14 @@ std::vector<LStep> build_program(bool fine) {
 // Pack the network into the streaming order of the kernel.  For every step, K is cut into
 // chunks; a chunk is stored as `cg` consecutive 16 KB images, image h holding rows
 // [h*N/cg, (h+1)*N/cg) of B as [K/8 panels][N/cg rows][8 elements] (see the layout note above).
-int pack_tc_weights(DfbNerf* n, int which, const std::vector<std::vector<float>>& P) {
+int pack_tc_weights(DfbNerf* n, int which, const std::vector<std::vector<float>>& P_in) {
   NetPack& np = n->net[which];
   for (int k = 0; k < 2; ++k)
     for (int g = 0; g < 2; ++g)
       if (np.blob16[k][g]) { cudaFree(np.blob16[k][g]); np.blob16[k][g] = nullptr; }
   np.tc_tbl.clear();
-  if (np.W != 256 || np.D != 8 || np.skip != 4 || np.pek != 64) return DFB_OK;  // SIMT only
+  if (!tc_padded_shape(np)) return DFB_OK;  // SIMT only
+  const std::vector<std::vector<float>> P = tc_pad_params(np, P_in);  // narrower networks: embedded in 8x256 with zeros
   const int W = 256, H = 128, in_xyz = np.in_xyz;
   const bool fine = np.fine;
   const std::vector<LStep> prog = build_program(fine);

@@ -302,7 +302,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_tc_bwd(const __grid_constan
       const float* rb = a.raybias + (gc / a.S) * 256;
       asm volatile("prefetch.global.L1 [%0];" ::"l"(rb + (tid & 7) * 32));
       float gh[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, isc = 1.f;
-      const uint32_t* mpass = a.saved_masks ? a.saved_masks + (size_t)(2 * p + slot) * (kMaskLayers * 8 * 128) + r : mbase;
+      // saved masks cover ceil(P/128) tiles; a tile past the end (odd tile count) has no rows and reads the scratch
+      const uint32_t* mpass = a.saved_masks && (2 * p + slot) * kTileM < a.P
+                                  ? a.saved_masks + (size_t)(2 * p + slot) * (kMaskLayers * 8 * 128) + r : mbase;
       for (int s = 0; s < a.n_steps; ++s) {
         mbar_wait(bar(D_FULL + slot), nd & 1, a.error_flag);
         ++nd;
@@ -516,12 +518,13 @@ std::vector<BStep> bwd_program() {
 
 }  // namespace
 
-int pack_tc_bwd_weights(DfbNerf* n, int which, const std::vector<std::vector<float>>& P) {
+int pack_tc_bwd_weights(DfbNerf* n, int which, const std::vector<std::vector<float>>& P_in) {
   NetPack& np = n->net[which];
   for (int k = 0; k < 2; ++k)
     if (np.blob16b[k]) { cudaFree(np.blob16b[k]); np.blob16b[k] = nullptr; }
   np.tcb_tbl.clear();
-  if (!np.fine || np.W != 256 || np.D != 8 || np.skip != 4 || np.pek != 64) return DFB_OK;
+  if (!np.fine || !tc_padded_shape(np)) return DFB_OK;
+  const std::vector<std::vector<float>> P = tc_pad_params(np, P_in);  // narrower networks: embedded in 8x256 with zeros
   const int W = 256, H = 128, in_xyz = np.in_xyz;
   const int kdd = W + np.in_dir + np.a_dim, ktt = W + np.t_dim;
   auto wdt = [&](int nn, int k) -> double {

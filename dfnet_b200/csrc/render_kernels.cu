@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(kPrepThreads) k_prep_rays(PrepArgs a) {
 __global__ void k_raybias(const float* __restrict__ extra, int ld, int64_t N, int nd, int nt, int Hh,
                           const float* __restrict__ dirx_w, const float* __restrict__ dirx_b,
                           const float* __restrict__ tx_w, const float* __restrict__ tx_b, float* __restrict__ rb,
-                          int n_rb, int rb_ld, const float* __restrict__ add_bias, int pack_kind) {
+                          int n_rb, int rb_ld, const float* __restrict__ add_bias, int pack_kind, int pad_h) {
   // block = n_rb threads (one output column each), 8 rays per block.  Every weight is loaded once per block and
   // applied to the 8 rays from registers; the ray-constant inputs are read from shared memory as float4 over k
   // (per (ray, column) the accumulation still runs over k in order, so results are unchanged).
@@ -154,9 +154,12 @@ __global__ void k_raybias(const float* __restrict__ extra, int ld, int64_t N, in
     if (rl >= nloc) break;
     const float acc = accs[rl];
     float v = acc + b;
-    if (add_bias) v += add_bias[n];  // constant part of the consuming layer's bias (tcgen05 path, see mlp_tc.cu)
+    // pad_h > 0: output layout of the zero-padded 8x256 embedding (tcgen05 path for narrower networks): the
+    // transient_encoding.0 half starts at column pad_h; the columns in between stay zero (the caller clears rb)
+    const int oc = pad_h > 0 && tr ? pad_h + col : n;
+    if (add_bias) v += add_bias[oc];  // constant part of the consuming layer's bias (tcgen05 path, see mlp_tc.cu)
     if (pack_kind == 0) {
-      if ((int)threadIdx.x < n_rb) rb[(r0 + rl) * rb_ld + n] = v;
+      if ((int)threadIdx.x < n_rb) rb[(r0 + rl) * rb_ld + oc] = v;
     } else {
       // packed 16-bit pairs {column 2j, column 2j+1} in word j of the row: the tcgen05 epilogue adds them with
       // one HFMA2.RELU per column pair, exactly like the constant biases of the hidden layers
@@ -165,7 +168,7 @@ __global__ void k_raybias(const float* __restrict__ extra, int ld, int64_t N, in
         uint32_t w16;
         if (pack_kind == 1) { __half2 h = __floats2half2_rn(v, hi); w16 = *reinterpret_cast<uint32_t*>(&h); }
         else { __nv_bfloat162 h = __floats2bfloat162_rn(v, hi); w16 = *reinterpret_cast<uint32_t*>(&h); }
-        reinterpret_cast<uint32_t*>(rb + (r0 + rl) * rb_ld)[n >> 1] = w16;
+        reinterpret_cast<uint32_t*>(rb + (r0 + rl) * rb_ld)[oc >> 1] = w16;
       }
     }
   }
@@ -420,16 +423,18 @@ int launch_prep(const PrepArgs& a, cudaStream_t st) {
 }
 
 int launch_raybias(const float* extra, int ld, int64_t N, const NetPack& np, bool with_transient, float* rb,
-                   int rb_ld, cudaStream_t st, const float* add_bias, int pack_kind) {
+                   int rb_ld, cudaStream_t st, const float* add_bias, int pack_kind, int pad_h) {
   const int Hh = np.W / 2, nd = np.in_dir + np.a_dim, nt = with_transient ? np.t_dim : 0;
   const int n_rb = with_transient ? 2 * Hh : Hh;
   const int blocks = (int)((N + 7) / 8);
   const int threads = round_up(n_rb, 32);
   const size_t smem = 8 * (((nd + 3) & ~3) + ((nt + 3) & ~3)) * sizeof(float);
   const float* b = np.blob32;
+  if (pad_h > Hh) DFB_CHECK_CUDA(cudaMemsetAsync(rb, 0, (size_t)N * rb_ld * sizeof(float), st));  // zero-padded embedding
   k_raybias<<<blocks, threads, smem, st>>>(extra, ld, N, nd, nt, Hh, b + np.dirx_w, b + np.dirx_b,
                                             with_transient ? b + np.tx_w : nullptr,
-                                            with_transient ? b + np.tx_b : nullptr, rb, n_rb, rb_ld, add_bias, pack_kind);
+                                            with_transient ? b + np.tx_b : nullptr, rb, n_rb, rb_ld, add_bias, pack_kind,
+                                            pad_h > Hh ? pad_h : 0);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }

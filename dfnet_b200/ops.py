@@ -55,8 +55,10 @@ class NerfHandle:
         self._fin = weakref.finalize(self, lib.dfb_nerf_destroy, h)
         self._mods = (network_fn, network_fine, embedding_a, embedding_t)
         # shapes the tcgen05 kernels cover (forward with saved ReLU masks + mask-driven backward)
-        self.tc_train = bool(network_fine is not None and net.W == 256 and net.D == 8 and skips == [4] and
-                             net.in_channels_xyz == 63 and net.in_channels_dir == 27)
+        # (narrower networks run on the same kernels, embedded in 8x256 with zero weights)
+        self.tc_train = bool(network_fine is not None and 32 <= net.W <= 256 and net.W % 16 == 0 and net.D == 8 and
+                             skips == [4] and net.in_channels_xyz == 63 and net.in_channels_dir == 27 and
+                             network_fine.W == net.W and network_fine.D == 8)
         self._versions = None
         self._ws = None
         self.refresh(force=True)
