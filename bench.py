@@ -292,7 +292,7 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     ms, launches, prof = timed(step_device, args.steps, args.warmup, profile=True)
     clocks = sampler.stop() if sampler else None
-    ms_e2e, _, _ = timed(step_host, args.steps, 1)
+    ms_e2e, _, _ = timed(step_host, args.steps, args.warmup)
     bad = sorted(set(clocks["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}) if clocks else []
     if bad and rank == 0:  # re-measure once
         sampler = ClockSampler(local)
