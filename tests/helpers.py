@@ -89,3 +89,47 @@ def train_case(case):
     world = dict(pose_scale=0.5, pose_scale2=1.0, move_all_cam_vec=[0.0, 0.0, 0.05])
     return dict(args=args, data=data, pose=pose, hist=hist, hwf=(H, W, 80.0), world=world, D=8, W=64, Nc=16, Nf=24,
                 near=0.0, far=2.5)
+
+
+def pad_nerfw_state_dict(P, W, W2=256, in_xyz=63):
+    """Python restatement of the library's `tc_pad_params` (csrc/mlp_tc.cu): the state dict of the 8-layer network of
+    width W2 that computes exactly the same function as the width-W network P (extra hidden units have zero input
+    weights and zero bias, so they stay at relu(0) = 0 and feed nothing).  numpy arrays, reference parameter names."""
+    H, H2 = W // 2, W2 // 2
+    Q = {}
+
+    def pad(w, rows2, cols2, col_shift_from=None, shift=0):
+        out = np.zeros((rows2, cols2), np.float32)
+        r, c = w.shape
+        if col_shift_from is None:
+            out[:r, :c] = w
+        else:   # columns >= col_shift_from (the ray-constant inputs) move behind the widened hidden block
+            out[:r, :col_shift_from] = w[:, :col_shift_from]
+            out[:r, col_shift_from + shift:c + shift] = w[:, col_shift_from:]
+        return out
+
+    def pad1(b, n2):
+        out = np.zeros(n2, np.float32)
+        out[:b.shape[0]] = b
+        return out
+
+    for i in range(8):
+        w, b = P[f"xyz_encoding_{i+1}.0.weight"], P[f"xyz_encoding_{i+1}.0.bias"]
+        cols2 = in_xyz if i == 0 else (in_xyz + W2 if i == 4 else W2)
+        Q[f"xyz_encoding_{i+1}.0.weight"], Q[f"xyz_encoding_{i+1}.0.bias"] = pad(w, W2, cols2), pad1(b, W2)
+    Q["xyz_encoding_final.weight"], Q["xyz_encoding_final.bias"] = pad(P["xyz_encoding_final.weight"], W2, W2), pad1(P["xyz_encoding_final.bias"], W2)
+    wd = P["dir_encoding.0.weight"]
+    Q["dir_encoding.0.weight"] = pad(wd, H2, W2 + wd.shape[1] - W, col_shift_from=W, shift=W2 - W)
+    Q["dir_encoding.0.bias"] = pad1(P["dir_encoding.0.bias"], H2)
+    Q["static_sigma.0.weight"], Q["static_sigma.0.bias"] = pad(P["static_sigma.0.weight"], 1, W2), P["static_sigma.0.bias"]
+    Q["static_rgb.0.weight"], Q["static_rgb.0.bias"] = pad(P["static_rgb.0.weight"], 3, H2), P["static_rgb.0.bias"]
+    if "transient_encoding.0.weight" in P:
+        wt = P["transient_encoding.0.weight"]
+        Q["transient_encoding.0.weight"] = pad(wt, H2, W2 + wt.shape[1] - W, col_shift_from=W, shift=W2 - W)
+        Q["transient_encoding.0.bias"] = pad1(P["transient_encoding.0.bias"], H2)
+        for k in (2, 4, 6):
+            Q[f"transient_encoding.{k}.weight"] = pad(P[f"transient_encoding.{k}.weight"], H2, H2)
+            Q[f"transient_encoding.{k}.bias"] = pad1(P[f"transient_encoding.{k}.bias"], H2)
+        for nm, r in (("transient_sigma", 1), ("transient_rgb", 3), ("transient_beta", 1)):
+            Q[f"{nm}.0.weight"], Q[f"{nm}.0.bias"] = pad(P[f"{nm}.0.weight"], r, H2), P[f"{nm}.0.bias"]
+    return Q

@@ -133,3 +133,21 @@ def test_render_stratified(golden):
     for k, g in [("rgb_map", "rgb"), ("disp_map", "disp"), ("acc_map", "acc"), ("rgb0", "rgb0"), ("beta", "beta"),
                  ("z_std", "z_std")]:
         assert rel_err(r[k], golden[f"e2e_d_{g}"], floor=1e-3) < 1e-4, k
+
+
+@pytest.mark.parametrize("W", [64, 128, 192])
+def test_narrow_network_embedded_in_256_is_the_same_function(W):
+    """The tcgen05 kernels run networks narrower than 256 (the reference's default netwidth is 128) embedded in
+    8x256 with zero weights (csrc/mlp_tc.cu::tc_pad_params).  The claim that this is EXACTLY the narrow network's
+    function is checked here on the CPU oracle: same outputs bit for bit, coarse (sigma only) and fine (all 9)."""
+    from helpers import pad_nerfw_state_dict, synthetic_nets
+    _, nets = synthetic_nets(8, W)
+    rng = np.random.RandomState(W)
+    x = rng.randn(257, 63 + 27 + 50 + 20).astype(np.float32)
+    fine, coarse = nets["fine"], nets["coarse"]
+    a = O.nerfw_forward(fine, x, 8, in_a=50, in_t=20)
+    b = O.nerfw_forward(pad_nerfw_state_dict(fine, W), x, 8, in_a=50, in_t=20)
+    assert a.shape == (257, 9) and np.array_equal(a, b)
+    s = O.nerfw_forward(coarse, x[:, :63], 8, sigma_only=True)
+    t = O.nerfw_forward(pad_nerfw_state_dict(coarse, W), x[:, :63], 8, sigma_only=True)
+    assert np.array_equal(s, t)
