@@ -11,7 +11,9 @@ extern "C" int dfb_conv_fwd(DfbConv* c, const void* in_nhwc16, int B, int H, int
 extern "C" int dfb_conv_wgrad(const void* gO, const void* X, int B, int H, int W, int Cin, int Cin_pad, int Cout, int KH, int fmt,
                               float* dW, float* dB, void* stream);
 int dfb_conv_create_impl(int Cin0, int Cout0, int KH, int KW, const float* weight, const float* bias, const float* bn_scale,
-                         const float* bn_shift, int fmt, int dgrad, DfbConv** out);
+                         const float* bn_shift, int fmt, int dgrad, DfbConv** out, int nt_force = 0);
+int64_t dfb_conv_tiles(const DfbConv* c, int B, int H, int W);
+int dfb_conv_num_sms(const DfbConv* c);
 int dfb_conv_update_impl(DfbConv* c, const float* weight, const float* bias, const float* bn_scale, const float* bn_shift,
                          void* stream);
 int dfb_conv_run(DfbConv* c, const void* in_nhwc16, int B, int H, int W, int relu, void* out_nhwc16, void* tap_nhwc16,
@@ -21,6 +23,7 @@ struct DfbDfnet {
   int n_levels = 3;
   // inference: fp16 operands
   DfbConv* enc[13] = {};
+  DfbConv* enc_n128[13] = {};   // 128-wide output-channel tiles of the wide layers, used when 256-wide tiles under-fill the GPU
   DfbConv* head1[3] = {};
   DfbConv* head5[3] = {};
   // training: bf16 forward of the encoder (activations double as wgrad operands) and bf16 data-gradient convs

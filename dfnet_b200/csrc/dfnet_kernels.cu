@@ -235,6 +235,7 @@ extern "C" int dfb_dfnet_create(int n_levels, DfbDfnet** out) {
 extern "C" void dfb_dfnet_destroy(DfbDfnet* d) {
   if (!d) return;
   for (auto c : d->enc) dfb_conv_destroy(c);
+  for (auto c : d->enc_n128) dfb_conv_destroy(c);
   for (auto c : d->enc_bf) dfb_conv_destroy(c);
   for (auto c : d->enc_dg) dfb_conv_destroy(c);
   for (auto c : d->head1) dfb_conv_destroy(c);
@@ -305,9 +306,9 @@ __global__ void __launch_bounds__(256) k_bn_apply(const float* x, int B, int Bs,
 
 // create on first use, repack in place afterwards (every optimizer step re-loads the parameters)
 static int conv_set(DfbConv** slot, int Cin, int Cout, int K, const float* w, const float* b, const float* sc, const float* sh,
-                    int fmt, int dgrad) {
+                    int fmt, int dgrad, int nt_force = 0) {
   if (*slot) return dfb_conv_update_impl(*slot, w, b, sc, sh, nullptr);
-  return dfb_conv_create_impl(Cin, Cout, K, K, w, b, sc, sh, fmt, dgrad, slot);
+  return dfb_conv_create_impl(Cin, Cout, K, K, w, b, sc, sh, fmt, dgrad, slot, nt_force);
 }
 
 // params: 13 x (conv weight, bias), then per level (w1x1, b1x1, w5x5, b5x5, bn_weight, bn_bias,
@@ -324,6 +325,10 @@ extern "C" int dfb_dfnet_load_ex(DfbDfnet* d, const float* const* params, const 
                 "encoder conv %d has the wrong size", i);
     int rc = conv_set(&d->enc[i], kEncCin[i], kEncCout[i], 3, params[2 * i], params[2 * i + 1], nullptr, nullptr, 0, 0);
     if (rc) return rc;
+    if (kEncCout[i] % 256 == 0 && (!train || d->enc_n128[i])) {  // inference handles: second packing with 128-wide tiles (kept current once it exists)
+      rc = conv_set(&d->enc_n128[i], kEncCin[i], kEncCout[i], 3, params[2 * i], params[2 * i + 1], nullptr, nullptr, 0, 0, 128);
+      if (rc) return rc;
+    }
     if (train) {
       rc = conv_set(&d->enc_bf[i], kEncCin[i], kEncCout[i], 3, params[2 * i], params[2 * i + 1], nullptr, nullptr, 1, 0);
       if (rc) return rc;
@@ -489,6 +494,7 @@ static int dfnet_fwd_impl(DfbDfnet* d, const float* x, int B, int H, int W, uint
     void* o = need_out ? base + L.act[i] : nullptr;
     DfbConv* cv = bf ? d->enc_bf[i] : d->enc[i];
     DFB_REQUIRE(cv, DFB_ERR_INVALID, "training variants not loaded (dfb_dfnet_load_ex flags bit0)");
+    if (!bf && !tape && d->enc_n128[i] && 2 * dfb_conv_tiles(cv, B, h, w) <= dfb_conv_num_sms(cv)) cv = d->enc_n128[i];
     int rc = dfb_conv_fwd(cv, cur, B, h, w, 1, o, tap, nullptr, stream);
     if (rc) return rc;
     if (i == last_conv && !ret_pose) break;

@@ -20,6 +20,7 @@ x = torch.rand(2, 3, 480, 640, device=dev)
 steps, warm = int(os.environ.get("STEPS", 10)), 3
 
 
+@torch.no_grad()   # forward-only configuration: the inference path (ping-pong activation buffers, no tape)
 def step():
     feats, _ = net(x, return_feature=True, isSingleStream=False, return_pose=False, upsampleH=480, upsampleW=640)
     return feature_loss(feats[1][0, 0], feats[0][0, 0])
