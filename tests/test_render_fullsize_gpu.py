@@ -83,3 +83,36 @@ def test_chunking_and_ray_source_invariance(ctx):
     again = h.render(NC, NF, True, c2w=c2w, H=Hs, W=Ws, focal=FOCAL, near=NEAR, far=FAR, hist=hist, mma="f16")["rgb"]
     torch.cuda.synchronize()
     assert torch.equal(again, rgb_a)   # deterministic: no atomics, fixed tile order
+
+
+def test_saved_mask_training_path_across_internal_chunks(ctx):
+    """Training forward + dfb_render_bwd_saved with more rays than one internal chunk of either (forward 65 536 rays,
+    backward 16 384 rays): the mask buffer is addressed per chunk, so a prefix of the rays must give bit-identical
+    gradients whether it is rendered alone or as part of the large batch, and the saved-mask gradients must agree with
+    the recompute kernel's."""
+    ops, h, c2w, hist, dev = ctx
+    n = 70000                                       # 2 forward chunks, 5 backward chunks; S = 128 -> one ray per tile
+    rng = np.random.RandomState(3)
+    o = torch.tensor([0.0, 0.0, 1.0], device=dev).expand(n, 3)
+    d = torch.tensor(rng.randn(n, 3).astype(np.float32) * 0.3 + np.array([0, 0, -1], np.float32), device=dev)
+    rec = torch.cat([o, d, torch.zeros(n, 1, device=dev), FAR * torch.ones(n, 1, device=dev),
+                     d / d.norm(dim=-1, keepdim=True), hist.reshape(1, -1).expand(n, -1)], -1).contiguous()
+    g = torch.tensor(rng.randn(n, 3).astype(np.float32) * 1e-6, device=dev)
+    big = h.render(64, 64, True, rays=rec, mma="f16", want=("z_vals", "raw", "relu_masks"))
+    gb = h.render_backward(rec, big["z_vals"], big["raw"], g, mma="f16", relu_masks=big["relu_masks"])
+    torch.cuda.synchronize()
+    assert all(torch.isfinite(t).all() for t in gb)
+    for lo, hi in ((0, 1000), (16384 - 500, 16384 + 500), (65536 - 300, 65536 + 300), (n - 700, n)):
+        # a window that starts at a tile boundary (S = 128: every ray is one tile)
+        sub = h.render(64, 64, True, rays=rec[lo:hi].contiguous(), mma="f16", want=("z_vals", "raw", "relu_masks"))
+        assert torch.equal(sub["raw"], big["raw"][lo:hi])
+        gs = h.render_backward(rec[lo:hi].contiguous(), sub["z_vals"], sub["raw"], g[lo:hi].contiguous(), mma="f16",
+                               relu_masks=sub["relu_masks"])
+        for a, b in zip(gs, gb):
+            assert torch.equal(a, b[lo:hi]), (lo, hi)
+    sel = slice(30000, 36000)
+    gr = h.render_backward(rec[sel].contiguous(), big["z_vals"][sel].contiguous(), big["raw"][sel].contiguous(),
+                           g[sel].contiguous(), mma="f16")
+    for a, b in zip(gr, gb):
+        x, y = a.double().reshape(-1), b[sel].double().reshape(-1)
+        assert float((x * y).sum() / (x.norm() * y.norm())) > 0.999
