@@ -40,6 +40,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the JSON line
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
     Fnet, Gnet = DFNet().to(dev), DFNet().to(dev).eval()
