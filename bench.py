@@ -212,9 +212,18 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # stdout carries exactly ONE JSON line: NCCL's version banner / debug output goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries exactly ONE JSON line: whatever NCCL prints while the communicator comes up (its version
+        # banner) is sent to stderr by pointing file descriptor 1 at stderr for the duration of the initialisation
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     mods = nerfw.make_synthetic_nerf(D=8, W=NETW)
     h = ops.NerfHandle(*[m.to(dev) for m in mods])

@@ -40,8 +40,16 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        sys.stdout.flush()
+        saved_fd = os.dup(1)   # NCCL's version banner -> stderr: stdout stays the JSON line
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     torch.manual_seed(0)
     Fnet, Gnet = DFNet().to(dev), DFNet().to(dev).eval()
     with torch.no_grad():
