@@ -1,5 +1,5 @@
 """Role-level cycle attribution of the tcgen05 MLP kernel (needs the -DDFB_TC_PROF build:
-DFB_LIB_PATH=dfnet_b200/csrc/build_prof/libdfnet_b200_prof.so python tools/tc_prof.py)."""
+make -C dfnet_b200/csrc prof && DFB_LIB_PATH=dfnet_b200/csrc/build_prof/libdfnet_b200_prof.so python tools/tc_prof.py)."""
 import ctypes as C
 import os
 import sys
