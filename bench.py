@@ -231,7 +231,7 @@ def main():
     if mma == "auto":
         mma = "f16"
     cfg = _lib.RenderCfg(N_samples=NC, N_importance=NF, test_time=1, perturb=0, mma_kind=_lib.MMA_KINDS[mma],
-                         lindisp=0, raw_noise_std=0.0)
+                         lindisp=0, raw_noise_std=0.0, hist_len=len(HIST))
     N = H * W
     hist_d = torch.tensor(HIST, device=dev)
     rgb = torch.empty(N, 3, device=dev)
@@ -245,7 +245,7 @@ def main():
     def step_device(i):
         c2w = poses_d[i % len(poses_d)]
         _lib.check(lib.dfb_render_fwd(h._h, C.byref(cfg), None, C.c_void_p(c2w.data_ptr()), H, W, FOCAL, NEAR, FAR,
-                                      C.c_void_p(hist_d.data_ptr()), N, None, None, C.c_void_p(rgb.data_ptr()),
+                                      C.c_void_p(hist_d.data_ptr()), N, None, None, None, C.c_void_p(rgb.data_ptr()),
                                       C.c_void_p(disp.data_ptr()), C.c_void_p(acc.data_ptr()), None,
                                       C.c_void_p(ws.data_ptr()), ws_bytes, sp))
 

@@ -35,7 +35,7 @@ class NerfDesc(C.Structure):
 class RenderCfg(C.Structure):
     _fields_ = [("N_samples", C.c_int32), ("N_importance", C.c_int32), ("test_time", C.c_int32),
                 ("perturb", C.c_int32), ("mma_kind", C.c_int32), ("lindisp", C.c_int32),
-                ("raw_noise_std", C.c_float), ("reserved", C.c_int32)]
+                ("raw_noise_std", C.c_float), ("ray_stride", C.c_int32), ("hist_len", C.c_int32), ("ert_eps", C.c_float)]
 
 
 class RenderExtras(C.Structure):
@@ -69,17 +69,17 @@ def _load():
     lib.dfb_nerf_set_embeddings.argtypes = [vp, vp, vp]
     lib.dfb_nerfw_forward.argtypes = [vp, i32, i32, vp, i64, vp, vp]
     lib.dfb_render_workspace_bytes.argtypes = [vp, C.POINTER(RenderCfg), i64, C.POINTER(C.c_size_t)]
-    lib.dfb_render_fwd.argtypes = [vp, C.POINTER(RenderCfg), vp, vp, i32, i32, f32, f32, f32, vp, i64, vp, vp, vp, vp,
+    lib.dfb_render_fwd.argtypes = [vp, C.POINTER(RenderCfg), vp, vp, i32, i32, f32, f32, f32, vp, i64, vp, vp, vp, vp, vp,
                                    vp, C.POINTER(RenderExtras), vp, C.c_size_t, vp]
     lib.dfb_render_image_host.argtypes = [vp, C.POINTER(RenderCfg), vp, i32, i32, f32, f32, f32, vp, vp, vp, vp, vp,
                                           C.c_size_t, vp]
     lib.dfb_render_bwd_workspace_bytes.argtypes = [vp, i64, i32, C.POINTER(C.c_size_t)]
-    lib.dfb_render_bwd.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
+    lib.dfb_render_bwd.argtypes = [vp, vp, i32, i64, i32, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
     lib.dfb_debug_bwd_masks.argtypes = [vp, vp, vp]
-    lib.dfb_render_bwd_saved.argtypes = [vp, i32, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
-    lib.dfb_render_bwd_mma.argtypes = [vp, i32, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
+    lib.dfb_render_bwd_saved.argtypes = [vp, i32, vp, i32, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
+    lib.dfb_render_bwd_mma.argtypes = [vp, i32, vp, i32, i64, i32, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
     lib.dfb_sample_pdf.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp, vp]
-    lib.dfb_raw2outputs.argtypes = [vp, vp, i64, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.dfb_raw2outputs.argtypes = [vp, vp, i64, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp, vp, f32, vp]
     lib.dfb_get_rays.argtypes = [vp, i32, i32, i32, f32, vp, vp, vp]
     lib.dfb_debug_umma_gemm.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
     lib.dfb_debug_umma_gemm_mn.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp]

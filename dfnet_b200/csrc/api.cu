@@ -44,8 +44,6 @@ int check_cfg(const DfbNerf* n, const DfbRenderCfg* c) {
   DFB_REQUIRE(n && c, DFB_ERR_INVALID, "null handle or config");
   DFB_REQUIRE(c->N_samples >= 4 && c->N_samples <= 1024, DFB_ERR_INVALID, "N_samples %d out of range", c->N_samples);
   DFB_REQUIRE(c->N_importance >= 0 && c->N_importance <= 1024, DFB_ERR_INVALID, "N_importance out of range");
-  DFB_REQUIRE(c->raw_noise_std == 0.f, DFB_ERR_UNSUPPORTED,
-              "raw_noise_std != 0 needs torch.randn draws; pass 0 (render_kwargs_test) or add noise on the host");
   DFB_REQUIRE(!(c->N_importance == 0 && c->test_time), DFB_ERR_INVALID,
               "N_importance == 0 with test_time yields rgb_map = None in the reference (rendering.py:188-193)");
   DFB_REQUIRE(c->N_importance == 0 || n->desc.has_fine, DFB_ERR_INVALID, "N_importance > 0 needs network_fine");
@@ -96,8 +94,8 @@ extern "C" int dfb_render_workspace_bytes(const DfbNerf* n, const DfbRenderCfg* 
 
 extern "C" int dfb_render_fwd(DfbNerf* n, const DfbRenderCfg* c, const float* rays, const float* c2w, int H, int W,
                               float focal, float near, float far, const float* hist, int64_t N, const float* t_rand,
-                              const float* u, float* rgb, float* disp, float* acc, const DfbRenderExtras* ex, void* ws,
-                              size_t ws_bytes, void* stream) {
+                              const float* u, const float* noise, float* rgb, float* disp, float* acc,
+                              const DfbRenderExtras* ex, void* ws, size_t ws_bytes, void* stream) {
   int rc = check_cfg(n, c);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -105,9 +103,18 @@ extern "C" int dfb_render_fwd(DfbNerf* n, const DfbRenderCfg* c, const float* ra
   DFB_REQUIRE(!c2w || ((int64_t)H * W == N && hist), DFB_ERR_INVALID, "c2w mode needs N == H*W and a histogram");
   DFB_REQUIRE(rgb && disp && acc, DFB_ERR_INVALID, "rgb/disp/acc outputs are required");
   const DfbNerfDesc& d = n->desc;
+  // the kernels index rays as r*(11+hist_bin) and hist[0..hist_bin): a record of any other width would be read
+  // misaligned / out of bounds (the reference raises a shape error in torch.cat / Embedding instead)
+  DFB_REQUIRE(!rays || c->ray_stride == 11 + d.hist_bin, DFB_ERR_INVALID,
+              "ray records are %d floats wide, expected 11 + hist_bin = %d ([o3,d3,near,far,viewdir3,hist])", c->ray_stride,
+              11 + d.hist_bin);
+  DFB_REQUIRE(!c2w || c->hist_len == d.hist_bin, DFB_ERR_INVALID, "histogram has %d entries, expected hist_bin = %d",
+              c->hist_len, d.hist_bin);
   const int Nc = c->N_samples, Nf = c->N_importance, S = Nc + Nf;
   DFB_REQUIRE(!c->perturb || (t_rand && (Nf == 0 || u)), DFB_ERR_INVALID,
               "perturb > 0 needs the uniform draws t_rand [N,Nc] and u [N,Nf] (rendering.py:282,36)");
+  DFB_REQUIRE(c->raw_noise_std == 0.f || noise, DFB_ERR_INVALID,
+              "raw_noise_std != 0 needs the standard-normal draws noise [N,Nc] (rendering.py:173)");
   if (N == 0) return DFB_OK;
   DFB_CHECK_CUDA(cudaSetDevice(n->device));
   const int64_t chunk = std::min<int64_t>(N, kChunkRays);
@@ -169,6 +176,7 @@ extern "C" int dfb_render_fwd(DfbNerf* n, const DfbRenderCfg* c, const float* ra
     ca.raw = raw_c, ca.z = P(L.z_c), ca.N = nr, ca.S = Nc, ca.C = Cc, ca.typ_fine = 0, ca.test_time = c->test_time;
     ca.beta_min = d.beta_min;
     ca.weights = P(L.w_c);
+    if (c->raw_noise_std != 0.f) ca.noise = noise + r0 * Nc, ca.noise_std = c->raw_noise_std;
     if (Nf == 0) {
       ca.rgb = rgb + r0 * 3, ca.disp = disp + r0, ca.acc = acc + r0;
       ca.depth = ex && ex->depth ? ex->depth + r0 : nullptr;
@@ -236,6 +244,9 @@ extern "C" int dfb_render_image_host(DfbNerf* n, const DfbRenderCfg* c, const fl
   int rc = check_cfg(n, c);
   if (rc) return rc;
   DFB_REQUIRE(c2w_host && hist_host && rgb_host && disp_host && acc_host, DFB_ERR_INVALID, "null host buffer");
+  DFB_REQUIRE(c->hist_len == n->desc.hist_bin, DFB_ERR_INVALID, "histogram has %d entries, expected hist_bin = %d", c->hist_len,
+              n->desc.hist_bin);
+  DFB_REQUIRE(!c->perturb && c->raw_noise_std == 0.f, DFB_ERR_INVALID, "dfb_render_image_host renders with render_kwargs_test (no perturb, no noise)");
   cudaStream_t st = (cudaStream_t)stream;
   DFB_CHECK_CUDA(cudaSetDevice(n->device));
   const int64_t N = (int64_t)H * W;
@@ -252,8 +263,8 @@ extern "C" int dfb_render_image_host(DfbNerf* n, const DfbRenderCfg* c, const fl
   float* d_out = (float*)(tail + align256(16 * 4) + align256(n->desc.hist_bin * 4));
   DFB_CHECK_CUDA(cudaMemcpyAsync(d_c2w, c2w_host, 12 * 4, cudaMemcpyHostToDevice, st));
   DFB_CHECK_CUDA(cudaMemcpyAsync(d_hist, hist_host, n->desc.hist_bin * 4, cudaMemcpyHostToDevice, st));
-  rc = dfb_render_fwd(n, c, nullptr, d_c2w, H, W, focal, near, far, d_hist, N, nullptr, nullptr, d_out, d_out + 3 * N,
-                      d_out + 4 * N, nullptr, ws, need, stream);
+  rc = dfb_render_fwd(n, c, nullptr, d_c2w, H, W, focal, near, far, d_hist, N, nullptr, nullptr, nullptr, d_out,
+                      d_out + 3 * N, d_out + 4 * N, nullptr, ws, need, stream);
   if (rc) return rc;
   DFB_CHECK_CUDA(cudaMemcpyAsync(rgb_host, d_out, (size_t)N * 3 * 4, cudaMemcpyDeviceToHost, st));
   DFB_CHECK_CUDA(cudaMemcpyAsync(disp_host, d_out + 3 * N, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
@@ -284,7 +295,8 @@ extern "C" int dfb_sample_pdf(const float* bins, const float* weights, const flo
 
 extern "C" int dfb_raw2outputs(const float* raw, const float* z_vals, int64_t N, int S, int C, int typ, int test_time,
                                float beta_min, float* rgb, float* disp, float* acc, float* weights, float* depth,
-                               float* transient_sigmas, float* beta, void* stream) {
+                               float* transient_sigmas, float* beta, const float* noise, float raw_noise_std,
+                               void* stream) {
   if (N == 0) return DFB_OK;
   DFB_REQUIRE(raw && z_vals, DFB_ERR_INVALID, "null argument");
   DFB_REQUIRE(C == 1 || C == 4 || C == 9, DFB_ERR_INVALID, "raw must have 1, 4 or 9 channels");
@@ -294,6 +306,8 @@ extern "C" int dfb_raw2outputs(const float* raw, const float* z_vals, int64_t N,
   ca.raw = raw, ca.z = z_vals, ca.N = N, ca.S = S, ca.C = C, ca.typ_fine = typ, ca.test_time = test_time;
   ca.beta_min = beta_min, ca.rgb = rgb, ca.disp = disp, ca.acc = acc, ca.weights = weights, ca.depth = depth;
   ca.tsig = transient_sigmas, ca.beta = beta;
+  DFB_REQUIRE(raw_noise_std == 0.f || (noise && C != 9), DFB_ERR_INVALID, "raw_noise_std != 0 needs noise [N,S] (coarse pass only)");
+  if (raw_noise_std != 0.f) ca.noise = noise, ca.noise_std = raw_noise_std;
   return launch_composite(ca, (cudaStream_t)stream);
 }
 
@@ -404,21 +418,21 @@ extern "C" int dfb_render_bwd_workspace_bytes(const DfbNerf* n, int64_t n_rays, 
   return DFB_OK;
 }
 
-extern "C" int dfb_render_bwd(DfbNerf* n, const float* rays, int64_t N, int S, const float* z_vals, const float* raw,
+extern "C" int dfb_render_bwd(DfbNerf* n, const float* rays, int ray_stride, int64_t N, int S, const float* z_vals, const float* raw,
                               const float* g_rgb, float* g_rays_o, float* g_rays_d, float* g_viewdirs, void* ws,
                               size_t ws_bytes, void* stream) {
-  return dfb_render_bwd_mma(n, DFB_MMA_FP32_SIMT, rays, N, S, z_vals, raw, g_rgb, g_rays_o, g_rays_d, g_viewdirs, ws, ws_bytes,
+  return dfb_render_bwd_mma(n, DFB_MMA_FP32_SIMT, rays, ray_stride, N, S, z_vals, raw, g_rgb, g_rays_o, g_rays_d, g_viewdirs, ws, ws_bytes,
                             stream);
 }
 
-extern "C" int dfb_render_bwd_mma(DfbNerf* n, int mma_kind, const float* rays, int64_t N, int S, const float* z_vals,
+extern "C" int dfb_render_bwd_mma(DfbNerf* n, int mma_kind, const float* rays, int ray_stride, int64_t N, int S, const float* z_vals,
                                   const float* raw, const float* g_rgb, float* g_rays_o, float* g_rays_d, float* g_viewdirs,
                                   void* ws, size_t ws_bytes, void* stream) {
-  return dfb_render_bwd_saved(n, mma_kind, rays, N, S, z_vals, raw, nullptr, g_rgb, g_rays_o, g_rays_d, g_viewdirs, ws, ws_bytes,
+  return dfb_render_bwd_saved(n, mma_kind, rays, ray_stride, N, S, z_vals, raw, nullptr, g_rgb, g_rays_o, g_rays_d, g_viewdirs, ws, ws_bytes,
                               stream);
 }
 
-extern "C" int dfb_render_bwd_saved(DfbNerf* n, int mma_kind, const float* rays, int64_t N, int S, const float* z_vals,
+extern "C" int dfb_render_bwd_saved(DfbNerf* n, int mma_kind, const float* rays, int ray_stride, int64_t N, int S, const float* z_vals,
                                     const float* raw, const uint32_t* relu_masks, const float* g_rgb, float* g_rays_o,
                                     float* g_rays_d, float* g_viewdirs, void* ws, size_t ws_bytes, void* stream) {
   DFB_REQUIRE(!relu_masks || (mma_kind != DFB_MMA_FP32_SIMT && n && tc_bwd_supported(n)), DFB_ERR_UNSUPPORTED,
@@ -426,6 +440,9 @@ extern "C" int dfb_render_bwd_saved(DfbNerf* n, int mma_kind, const float* rays,
   DFB_REQUIRE(mma_kind == DFB_MMA_FP32_SIMT || mma_kind == DFB_MMA_F16 || mma_kind == DFB_MMA_BF16, DFB_ERR_INVALID, "bad mma kind");
   DFB_REQUIRE(n && rays && z_vals && raw && g_rgb && g_rays_o && g_rays_d && g_viewdirs, DFB_ERR_INVALID, "null argument");
   DFB_REQUIRE(n->desc.has_fine && n->net[1].loaded && n->has_emb, DFB_ERR_INVALID, "fine network / embeddings not loaded");
+  DFB_REQUIRE(ray_stride == 11 + n->desc.hist_bin, DFB_ERR_INVALID,
+              "ray records are %d floats wide, expected 11 + hist_bin = %d ([o3,d3,near,far,viewdir3,hist])", ray_stride,
+              11 + n->desc.hist_bin);
   if (N == 0) return DFB_OK;
   DFB_CHECK_CUDA(cudaSetDevice(n->device));
   cudaStream_t st = (cudaStream_t)stream;

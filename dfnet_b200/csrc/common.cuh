@@ -14,6 +14,9 @@ namespace dfb {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+// Device-side "mbarrier wait timed out" flag of the CURRENT device (one int per device, allocated on first use;
+// the kernels only ever write it on a protocol failure, so sharing it between launches is benign).
+int device_error_flag(int** out);
 
 #define DFB_CHECK_CUDA(expr)                                                              \
   do {                                                                                    \
@@ -103,6 +106,9 @@ struct DfbNerf {
   int num_sms = 0;
   float* lin_dev = nullptr;  // [Nc | Nf] linspace grids of the last render config
   int lin_nc = -1, lin_nf = -1;
+  // per-handle (= per-device) launch scratch: the handle's launches are ordered on one stream at a time
+  mutable uint32_t* bwd_scratch = nullptr;  // tcgen05 backward: L2-resident per-CTA scratch (mlp_tc_bwd.cu)
+  mutable int bwd_scratch_ctas = 0;
 };
 
 namespace dfb {
@@ -168,6 +174,8 @@ struct CompositeArgs {
   int typ_fine, test_time;
   float beta_min;
   float *rgb, *disp, *acc, *weights, *depth, *tsig, *beta;  // any may be null
+  const float* noise;  // [N,S] standard-normal draws (coarse pass only, rendering.py:173-174) or null
+  float noise_std;
 };
 
 struct SampleArgs {

@@ -268,8 +268,6 @@ __global__ void __launch_bounds__(128, 1) k_umma_selftest_mn(const float* A, con
 using namespace dfb;
 
 
-static int* g_wg_error_flag = nullptr;
-
 // dW [Cout,Cin,KH,KW] (+ optional dB [Cout]) from gO NHWC [B,H,W,Cout] and X NHWC [B,H,W,Cin_pad] (16-bit, fmt 0 f16 / 1 bf16).
 // Both outputs are overwritten.
 extern "C" int dfb_conv_wgrad(const void* gO, const void* X, int B, int H, int W, int Cin, int Cin_pad, int Cout, int KH, int fmt,
@@ -278,9 +276,10 @@ extern "C" int dfb_conv_wgrad(const void* gO, const void* X, int B, int H, int W
   DFB_REQUIRE(B >= 1 && H >= 1 && W >= 1 && Cin >= 1 && Cin_pad % 8 == 0 && Cin_pad >= Cin && Cout % 64 == 0 && Cout >= 64,
               DFB_ERR_INVALID, "dfb_conv_wgrad: bad shape");
   DFB_REQUIRE(KH == 1 || KH == 3 || KH == 5, DFB_ERR_UNSUPPORTED, "kernel size must be 1, 3 or 5");
-  if (!g_wg_error_flag) {
-    DFB_CHECK_CUDA(cudaMalloc(&g_wg_error_flag, 4));
-    DFB_CHECK_CUDA(cudaMemset(g_wg_error_flag, 0, 4));
+  int* error_flag = nullptr;
+  {
+    const int rc = device_error_flag(&error_flag);
+    if (rc) return rc;
   }
   int dev = 0, sms = 0;
   DFB_CHECK_CUDA(cudaGetDevice(&dev));
@@ -299,7 +298,7 @@ extern "C" int dfb_conv_wgrad(const void* gO, const void* X, int B, int H, int W
   a.n_split = std::max(1, std::min(a.n_tiles, sms / units));
   a.PW = wg::kTW + 2 * a.pad;
   a.x_bytes = (uint32_t)(a.NB / 8) * wg::kTH * a.PW * 16u;
-  a.fmt = fmt, a.error_flag = g_wg_error_flag;
+  a.fmt = fmt, a.error_flag = error_flag;
   const size_t smem = (size_t)wg::kStages * (wg::kGBytes + a.x_bytes) + 256;
   DFB_REQUIRE(smem <= 232448, DFB_ERR_UNSUPPORTED, "shared memory budget exceeded");
   DFB_CHECK_CUDA(cudaMemsetAsync(dW, 0, (size_t)Cout * Cin * KH * KH * 4, st));

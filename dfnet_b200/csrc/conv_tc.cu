@@ -477,8 +477,6 @@ extern "C" void dfb_conv_destroy(DfbConv* c) {
   delete c;
 }
 
-static int* g_conv_error_flag = nullptr;
-
 int dfb_conv_run(DfbConv* c, const void* in_nhwc16, int B, int H, int W, int relu, void* out_nhwc16, void* tap_nhwc16,
                  float* out_nchw32, const void* mask_nhwc16, const void* addend_nhwc16, void* stream);
 
@@ -491,9 +489,10 @@ int dfb_conv_run(DfbConv* c, const void* in_nhwc16, int B, int H, int W, int rel
                  float* out_nchw32, const void* mask_nhwc16, const void* addend_nhwc16, void* stream) {
   DFB_REQUIRE(c && in_nhwc16 && (out_nhwc16 || tap_nhwc16 || out_nchw32), DFB_ERR_INVALID, "dfb_conv_fwd: null argument");
   DFB_REQUIRE(B >= 1 && H >= 1 && W >= 1, DFB_ERR_INVALID, "bad image size");
-  if (!g_conv_error_flag) {
-    DFB_CHECK_CUDA(cudaMalloc(&g_conv_error_flag, 4));
-    DFB_CHECK_CUDA(cudaMemset(g_conv_error_flag, 0, 4));
+  int* error_flag = nullptr;
+  {
+    const int rc = device_error_flag(&error_flag);
+    if (rc) return rc;
   }
   conv::ConvArgs a = {};
   a.in = (const __half*)in_nhwc16, a.wimg = c->wimg, a.bias = c->bias;
@@ -506,7 +505,7 @@ int dfb_conv_run(DfbConv* c, const void* in_nhwc16, int B, int H, int W, int rel
   a.a_bytes = (uint32_t)a.PH * a.PW * 16u * 8u;
   a.b_bytes = (uint32_t)c->nt * 16u * 8u * (uint32_t)c->tps;
   a.tps = c->tps, a.n_wst = c->n_wst;
-  a.error_flag = g_conv_error_flag;
+  a.error_flag = error_flag;
   const int64_t n_tiles = (int64_t)a.tiles_x * a.tiles_y * B * a.n_ntiles;
   DFB_REQUIRE(n_tiles < (1ll << 30), DFB_ERR_INVALID, "image too large");
   const int grid = (int)std::min<int64_t>(n_tiles, c->num_sms);

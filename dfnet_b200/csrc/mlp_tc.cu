@@ -926,8 +926,6 @@ int pack_tc_weights(DfbNerf* n, int which, const std::vector<std::vector<float>>
   return DFB_OK;
 }
 
-static int* g_error_flag = nullptr;
-
 // 3-D tensor map over a packed weight image: [n_img][64][128 x u16], one box = one 16 KB image.
 static int make_weight_tmap(void* base, size_t bytes, CUtensorMap* out) {
   static PFN_cuTensorMapEncodeTiled encode = nullptr;
@@ -964,9 +962,10 @@ int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const
   DFB_REQUIRE(kind == DFB_MMA_F16 || kind == DFB_MMA_BF16, DFB_ERR_INVALID, "bad mma kind");
   const bool full = mode == MLP_FULL;
   DFB_REQUIRE(!full || raybias, DFB_ERR_INVALID, "ray-constant inputs missing");
-  if (!g_error_flag) {
-    DFB_CHECK_CUDA(cudaMalloc(&g_error_flag, sizeof(int)));
-    DFB_CHECK_CUDA(cudaMemset(g_error_flag, 0, sizeof(int)));
+  int* error_flag = nullptr;
+  {
+    const int rc = device_error_flag(&error_flag);
+    if (rc) return rc;
   }
   const int cg = tc_cta_group();
   tc::TcArgs a = {};
@@ -1000,7 +999,7 @@ int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const
   a.rayrec = rayrec, a.z = z, a.raybias = raybias, a.S = S, a.P = n_rays * S, a.raw = raw;
   DFB_REQUIRE(!masks || full, DFB_ERR_INVALID, "ReLU masks are an output of the fine network only");
   a.masks = masks;
-  a.error_flag = g_error_flag;
+  a.error_flag = error_flag;
 #ifdef DFB_TC_PROF
   if (!g_prof) {
     DFB_CHECK_CUDA(cudaMalloc(&g_prof, 512 * 16 * sizeof(unsigned long long)));

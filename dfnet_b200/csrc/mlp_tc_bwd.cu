@@ -609,11 +609,8 @@ bool tc_bwd_supported(const DfbNerf* n) {
   return np.loaded && np.fine && np.blob16b[0] != nullptr && !np.tcb_tbl.empty();
 }
 
-static int* g_bwd_error_flag = nullptr;
 const uint32_t* g_dbg_tc_mask_in = nullptr;
 uint32_t* g_dbg_tc_mask_out = nullptr;
-static uint32_t* g_bwd_scratch = nullptr;
-static int g_bwd_scratch_ctas = 0;
 
 // Fine-network backward for P = n_rays*S samples: g_samp[P,32] from raw / g_raw (see the header comment).
 int launch_mlp_tc_bwd(const DfbNerf* nerf, int kind, const float* rayrec, const float* z, const float* raybias,
@@ -622,9 +619,10 @@ int launch_mlp_tc_bwd(const DfbNerf* nerf, int kind, const float* rayrec, const 
   const NetPack& np = nerf->net[1];
   DFB_REQUIRE(tc_bwd_supported(nerf), DFB_ERR_UNSUPPORTED, "network shape not supported by the tcgen05 backward kernel");
   DFB_REQUIRE(kind == DFB_MMA_F16 || kind == DFB_MMA_BF16, DFB_ERR_INVALID, "bad mma kind");
-  if (!g_bwd_error_flag) {
-    DFB_CHECK_CUDA(cudaMalloc(&g_bwd_error_flag, sizeof(int)));
-    DFB_CHECK_CUDA(cudaMemset(g_bwd_error_flag, 0, sizeof(int)));
+  int* error_flag = nullptr;
+  {
+    const int rc = device_error_flag(&error_flag);
+    if (rc) return rc;
   }
   tcb::BtArgs a;
   memset(&a, 0, sizeof(a));
@@ -657,19 +655,19 @@ int launch_mlp_tc_bwd(const DfbNerf* nerf, int kind, const float* rayrec, const 
   memcpy(a.tsig_w, q, sizeof(a.tsig_w)), q += 128;
   memcpy(a.tbeta_w, q, sizeof(a.tbeta_w));
   a.rayrec = rayrec, a.z = z, a.raybias = raybias, a.raw = raw, a.g_raw = g_raw, a.g_samp = g_samp;
-  a.S = S, a.P = n_rays * S, a.error_flag = g_bwd_error_flag;
+  a.S = S, a.P = n_rays * S, a.error_flag = error_flag;
   a.mask_in = g_dbg_tc_mask_in, a.mask_out = g_dbg_tc_mask_out;
   if (a.P == 0) return DFB_OK;
   const int64_t tiles = (a.P + tcb::kTileM - 1) / tcb::kTileM;
   a.n_pass = (tiles + 1) / 2;
   const int grid = (int)std::min<int64_t>(a.n_pass, nerf->num_sms);
-  if (g_bwd_scratch_ctas < grid) {
-    if (g_bwd_scratch) cudaFree(g_bwd_scratch);
-    g_bwd_scratch = nullptr, g_bwd_scratch_ctas = 0;
-    DFB_CHECK_CUDA(cudaMalloc(&g_bwd_scratch, (size_t)nerf->num_sms * tcb::kScrWords * 4));
-    g_bwd_scratch_ctas = nerf->num_sms;
+  if (nerf->bwd_scratch_ctas < grid) {  // per handle (= per device), see DfbNerf
+    if (nerf->bwd_scratch) cudaFree(nerf->bwd_scratch);
+    nerf->bwd_scratch = nullptr, nerf->bwd_scratch_ctas = 0;
+    DFB_CHECK_CUDA(cudaMalloc(&nerf->bwd_scratch, (size_t)nerf->num_sms * tcb::kScrWords * 4));
+    nerf->bwd_scratch_ctas = nerf->num_sms;
   }
-  a.scratch = g_bwd_scratch;
+  a.scratch = nerf->bwd_scratch;
   auto launch = [&](auto kern) -> int {
     DFB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tcb::kSmemTotal));
     kern<<<grid, tcb::kThreads, tcb::kSmemTotal, st>>>(a);

@@ -21,6 +21,19 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches += n; }
 
+int device_error_flag(int** out) {
+  static int* flags[64] = {nullptr};
+  int dev = 0;
+  DFB_CHECK_CUDA(cudaGetDevice(&dev));
+  DFB_REQUIRE(dev >= 0 && dev < 64, DFB_ERR_UNSUPPORTED, "device index %d out of range", dev);
+  if (!flags[dev]) {
+    DFB_CHECK_CUDA(cudaMalloc(&flags[dev], sizeof(int)));
+    DFB_CHECK_CUDA(cudaMemset(flags[dev], 0, sizeof(int)));
+  }
+  *out = flags[dev];
+  return DFB_OK;
+}
+
 }  // namespace dfb
 
 using namespace dfb;
@@ -88,6 +101,7 @@ extern "C" void dfb_nerf_destroy(DfbNerf* n) {
   if (n->emb_a) cudaFree(n->emb_a);
   if (n->emb_t) cudaFree(n->emb_t);
   if (n->lin_dev) cudaFree(n->lin_dev);
+  if (n->bwd_scratch) cudaFree(n->bwd_scratch);
   delete n;
 }
 

@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_composite(CompositeArgs
       oma[i] = __fsub_rn(1.f, __fsub_rn(1.f, expf(__fmul_rn(nd, __fadd_rn(ss, st)))));
       omas[i] = __fsub_rn(1.f, __fsub_rn(1.f, expf(__fmul_rn(nd, ss))));
     } else {
-      const float ss = fmaxf(raw[i * C + (C - 1)], 0.f);  // relu(sigma + 0*noise)
+      // relu(sigma + noise * raw_noise_std)
+      const float ss = fmaxf(a.noise ? __fadd_rn(raw[i * C + (C - 1)], __fmul_rn(a.noise[ray * S + i], a.noise_std)) : raw[i * C + (C - 1)], 0.f);
       oma[i] = __fsub_rn(1.f, __fsub_rn(1.f, expf(__fmul_rn(nd, ss))));
     }
   }
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_composite(CompositeArgs
       s_beta += __fmul_rn(tw, raw[i * 9 + 8]);
       s_depth += static_depth ? __fmul_rn(__fmul_rn(als, Ts[i]), zi) : __fmul_rn(w, zi);
     } else {
-      const float ss = fmaxf(raw[i * C + (C - 1)], 0.f);
+      const float ss = fmaxf(a.noise ? __fadd_rn(raw[i * C + (C - 1)], __fmul_rn(a.noise[ray * S + i], a.noise_std)) : raw[i * C + (C - 1)], 0.f);
       const float al = __fsub_rn(1.f, expf(__fmul_rn(nd, ss)));
       const float w = __fmul_rn(al, Ti);
       if (a.weights) a.weights[ray * S + i] = w;

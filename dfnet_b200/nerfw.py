@@ -10,6 +10,10 @@ import os
 import torch
 import torch.nn as nn
 
+img2mse = lambda x, y: torch.mean((x - y) ** 2)  # noqa: E731  (reference models/nerfw.py:11; plain tensors, host side)
+mse2psnr = lambda x: -10. * torch.log(x) / torch.log(torch.tensor([10.], device=x.device))  # noqa: E731  (:12)
+to8b = lambda x: (255 * __import__("numpy").clip(x, 0, 1)).astype("uint8")  # noqa: E731  (:13)
+
 
 class NeRFW(nn.Module):
     """NeRF-W / NeRF-Hist MLP container (reference models/nerfw.py:220-295).
@@ -87,3 +91,102 @@ def make_synthetic_nerf(D=8, W=256, in_channels_a=50, in_channels_t=20, n_vocab=
             NeRFW("fine", D=D, W=W, encode_appearance=True, encode_transient=True,
                   in_channels_a=in_channels_a, in_channels_t=in_channels_t), gain, sigma_bias)
     return coarse, net_fine, emb_a, emb_t
+
+
+def _arg(args, name, default):
+    return getattr(args, name, default)
+
+
+def create_nerf(args):
+    """Instantiate the NeRF-Hist networks, optimizer and render kwargs and reload the newest checkpoint (reference
+    models/nerfw.py:356-502) -> (render_kwargs_train, render_kwargs_test, start, grad_vars, optimizer).
+
+    Same `args` attribute names as models/options.py.  Checkpoint format (run_nerf.py:150-167): a torch-saved dict
+    with global_step, network_fn_state_dict, network_fine_state_dict, embedding_a_state_dict, embedding_t_state_dict
+    (+ optimizer_state_dict, which the reference does not reload either); the newest `*tar*` file of
+    basedir/expname is taken unless args.ft_path names one.  The kwargs carry the modules; the arithmetic of
+    `network_query_fn` (positional encoding + MLP, nerfw.py:15-95) lives inside the fused kernels, so the entry is kept
+    only for signature compatibility and render() ignores it."""
+    if not _arg(args, "NeRFH", True):
+        raise NotImplementedError("only the NeRF-Hist / NeRF-W networks (--NeRFH) are on the B200 path")
+    if _arg(args, "multi_gpu", False):
+        raise NotImplementedError("--multi_gpu (nn.DataParallel) is replaced by one process per GPU (bench.py --gpus N)")
+    if _arg(args, "reduce_embedding", -1) not in (-1, None) or _arg(args, "i_embed", 0) != 0:
+        raise NotImplementedError("only the paper-default positional encoding (reduce_embedding=-1, i_embed=0) is on the B200 path")
+    if not _arg(args, "use_viewdirs", True):
+        raise NotImplementedError("NeRF-Hist always renders with use_viewdirs=True")
+    if not _arg(args, "encode_hist", True):
+        raise NotImplementedError("NeRF-Hist needs --encode_hist (the reference leaves embedding_a undefined without it, nerfw.py:384-390)")
+    multires, multires_views = _arg(args, "multires", 10), _arg(args, "multires_views", 4)
+    input_ch, input_ch_views = 3 + 6 * multires, 3 + 6 * multires_views
+    if not torch.cuda.is_available():
+        raise RuntimeError("create_nerf needs a CUDA device (the reference hard-codes torch.device('cuda'), nerfw.py:380)")
+    device = torch.device("cuda", torch.cuda.current_device())
+    embedding_a = nn.Embedding(args.N_vocab, 5).to(device)
+    embedding_t = nn.Embedding(args.N_vocab, 2).to(device)
+    model = NeRFW("coarse", D=args.netdepth, W=args.netwidth, skips=[4], in_channels_xyz=input_ch,
+                  in_channels_dir=input_ch_views).to(device)
+    grad_vars = list(model.parameters())
+    model_fine = None
+    if args.N_importance > 0:
+        model_fine = NeRFW("fine", D=args.netdepth, W=args.netwidth, skips=[4], in_channels_xyz=input_ch,
+                           in_channels_dir=input_ch_views, encode_appearance=True, encode_transient=True,
+                           in_channels_a=args.in_channels_a, in_channels_t=args.in_channels_t).to(device)
+        grad_vars += list(model_fine.parameters())
+        grad_vars += list(embedding_a.parameters())
+        grad_vars += list(embedding_t.parameters())
+    if _arg(args, "no_grad_update", False):
+        grad_vars, optimizer = None, None
+    else:
+        optimizer = torch.optim.Adam(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999))
+
+    start = 0
+    ft_path = _arg(args, "ft_path", None)
+    if ft_path is not None and ft_path != "None":
+        ckpts = [ft_path]
+    else:
+        d = os.path.join(args.basedir, args.expname)
+        ckpts = [os.path.join(d, f) for f in sorted(os.listdir(d)) if "tar" in f]
+    print("Found ckpts", ckpts)
+    if len(ckpts) > 0 and not _arg(args, "no_reload", False):
+        print("Reloading from", ckpts[-1])
+        ckpt = torch.load(ckpts[-1], map_location=device, weights_only=False)
+        start = ckpt["global_step"]
+        model.load_state_dict(ckpt["network_fn_state_dict"])
+        if model_fine is not None:
+            model_fine.load_state_dict(ckpt["network_fine_state_dict"])
+            embedding_a.load_state_dict(ckpt["embedding_a_state_dict"])
+            embedding_t.load_state_dict(ckpt["embedding_t_state_dict"])
+
+    def network_query_fn(*a, **k):  # noqa: ARG001
+        raise RuntimeError("network_query_fn is fused into the render kernels; call dfnet_b200.rendering.render "
+                           "(or NeRFW.forward on embedded points)")
+
+    render_kwargs_train = {
+        "network_query_fn": network_query_fn, "perturb": args.perturb, "N_importance": args.N_importance,
+        "network_fine": model_fine, "N_samples": args.N_samples, "network_fn": model,
+        "use_viewdirs": _arg(args, "use_viewdirs", True), "white_bkgd": _arg(args, "white_bkgd", False),
+        "raw_noise_std": _arg(args, "raw_noise_std", 0.), "embedding_a": embedding_a, "embedding_t": embedding_t,
+        "test_time": False}
+    if _arg(args, "dataset_type", "7Scenes") != "llff" or _arg(args, "no_ndc", False):
+        render_kwargs_train["ndc"] = False
+        render_kwargs_train["lindisp"] = _arg(args, "lindisp", False)
+    render_kwargs_test = dict(render_kwargs_train)
+    render_kwargs_test["perturb"] = False
+    render_kwargs_test["raw_noise_std"] = 0.
+    render_kwargs_test["test_time"] = True
+    return render_kwargs_train, render_kwargs_test, start, grad_vars, optimizer
+
+
+def save_checkpoint(path, global_step, render_kwargs, optimizer=None):
+    """The checkpoint dict run_nerf.py:150-167 writes (same keys; create_nerf above and the reference's create_nerf
+    both load it)."""
+    d = {"global_step": global_step, "network_fn_state_dict": render_kwargs["network_fn"].state_dict()}
+    if render_kwargs.get("network_fine") is not None:
+        d["network_fine_state_dict"] = render_kwargs["network_fine"].state_dict()
+        d["embedding_a_state_dict"] = render_kwargs["embedding_a"].state_dict()
+        d["embedding_t_state_dict"] = render_kwargs["embedding_t"].state_dict()
+    if optimizer is not None:
+        d["optimizer_state_dict"] = optimizer.state_dict()
+    torch.save(d, path)
+    return path

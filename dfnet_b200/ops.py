@@ -63,6 +63,17 @@ class NerfHandle:
         self._ws = None
         self.refresh(force=True)
 
+    def __reduce__(self):
+        # handles are caches of device state: pickling / deep-copying a module that carries one (torch.save(model),
+        # copy.deepcopy) drops it, and the copy builds its own on first use
+        return (_no_handle, ())
+
+    def invalidate(self):
+        """Force a re-upload on the next render.  Change detection compares (data_ptr, _version) of every tensor;
+        writes through `.data` (p.data.copy_(...), common in older training code) do not bump `_version`, so call this
+        (or refresh(force=True)) after such writes."""
+        self._versions = None
+
     def _param_versions(self):
         # polled on every render: iterate the tensors directly (state_dict() renames and detaches every one of them)
         v = []
@@ -101,20 +112,29 @@ class NerfHandle:
     # ------------------------------------------------------------------------------
     def render(self, N_samples, N_importance, test_time, rays=None, c2w=None, H=0, W=0, focal=1.0, near=0.0,
                far=1.0, hist=None, perturb=False, t_rand=None, u=None, mma="f16", lindisp=False, raw_noise_std=0.0,
-               want=()):
+               noise=None, ert_eps=0.0, want=()):
         """dfb_render_fwd.  Returns dict(rgb, disp, acc, + requested extras)."""
         cfg = _lib.RenderCfg(N_samples=N_samples, N_importance=N_importance, test_time=int(bool(test_time)),
                              perturb=int(bool(perturb)), mma_kind=_lib.MMA_KINDS[mma], lindisp=int(bool(lindisp)),
-                             raw_noise_std=float(raw_noise_std))
+                             raw_noise_std=float(raw_noise_std), ert_eps=float(ert_eps))
+        hb = self.desc.hist_bin
         if rays is not None:
             _require_cuda(rays, "rays")
+            if rays.dim() != 2 or rays.shape[1] != 11 + hb:
+                raise _lib.DfbError(f"ray records must be [N, 11 + hist_bin = {11 + hb}] ([o3,d3,near,far,viewdir3,hist], reference "
+                                    f"rendering.py:382-389), got {tuple(rays.shape)}")
             rays = _f32c(rays)
             N, dev = rays.shape[0], rays.device
+            cfg.ray_stride = rays.shape[1]
         else:
             _require_cuda(c2w, "c2w")
             c2w = _f32c(c2w[:3, :4])
+            if hist is None or hist.numel() != hb:
+                raise _lib.DfbError(f"img_idx / hist must hold hist_bin = {hb} values, got "
+                                    f"{0 if hist is None else hist.numel()}")
             hist = _f32c(hist.reshape(-1)).to(c2w.device)
             N, dev = H * W, c2w.device
+            cfg.hist_len = hist.numel()
         S = N_samples + N_importance
         out = {"rgb": torch.empty(N, 3, device=dev), "disp": torch.empty(N, device=dev),
                "acc": torch.empty(N, device=dev)}
@@ -131,8 +151,10 @@ class NerfHandle:
             t_rand = _f32c(t_rand).to(dev)
         if u is not None:
             u = _f32c(u).to(dev)
+        if noise is not None:
+            noise = _f32c(noise).to(dev)
         check(lib.dfb_render_fwd(self._h, C.byref(cfg), _ptr(rays), _ptr(c2w), H, W, focal, near, far, _ptr(hist), N,
-                                 _ptr(t_rand), _ptr(u), _ptr(out["rgb"]), _ptr(out["disp"]), _ptr(out["acc"]),
+                                 _ptr(t_rand), _ptr(u), _ptr(noise), _ptr(out["rgb"]), _ptr(out["disp"]), _ptr(out["acc"]),
                                  C.byref(ex), _ptr(ws), ws_bytes, _stream()))
         return out
 
@@ -140,6 +162,9 @@ class NerfHandle:
                           device):
         """dfb_render_image_host: pinned host pose/hist in, pinned host image out, all on the current stream."""
         stage = 256 * 2 + (H * W * 5 * 4 + 255) // 256 * 256
+        if hist_host.numel() != self.desc.hist_bin:
+            raise _lib.DfbError(f"hist must hold hist_bin = {self.desc.hist_bin} values, got {hist_host.numel()}")
+        cfg.hist_len = hist_host.numel()
         ws, ws_bytes = self.workspace(cfg, H * W, device, extra_bytes=stage)
         check(lib.dfb_render_image_host(self._h, C.byref(cfg), _ptr(c2w_host), H, W, focal, near, far, _ptr(hist_host),
                                         _ptr(rgb_host), _ptr(disp_host), _ptr(acc_host), _ptr(ws), ws.numel(),
@@ -149,6 +174,8 @@ class NerfHandle:
         """dfb_render_bwd_mma: gradients of a test-time render w.r.t. rays_o, rays_d and viewdirs, each [N,3].
         mma = the kind the forward ran with; "f16"/"bf16" run the 8x256 fine network's backward on tcgen05."""
         _require_cuda(rays, "rays")
+        if rays.dim() != 2 or rays.shape[1] != 11 + self.desc.hist_bin:
+            raise _lib.DfbError(f"ray records must be [N, 11 + hist_bin = {11 + self.desc.hist_bin}], got {tuple(rays.shape)}")
         rays, z_vals, raw, g_rgb = _f32c(rays), _f32c(z_vals), _f32c(raw), _f32c(g_rgb)
         N, S = z_vals.shape
         dev = rays.device
@@ -157,7 +184,7 @@ class NerfHandle:
         ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
         g_o, g_d, g_vd = (torch.empty(N, 3, device=dev) for _ in range(3))
         # relu_masks: the forward's saved ReLU masks (render(want=("relu_masks",)), tcgen05 path) -> no forward recompute
-        check(lib.dfb_render_bwd_saved(self._h, _lib.MMA_KINDS[mma], _ptr(rays), N, S, _ptr(z_vals), _ptr(raw), _ptr(relu_masks),
+        check(lib.dfb_render_bwd_saved(self._h, _lib.MMA_KINDS[mma], _ptr(rays), rays.shape[1], N, S, _ptr(z_vals), _ptr(raw), _ptr(relu_masks),
                                        _ptr(g_rgb), _ptr(g_o), _ptr(g_d), _ptr(g_vd), _ptr(ws), need.value, _stream()))
         return g_o, g_d, g_vd
 
@@ -170,16 +197,20 @@ class NerfHandle:
         return out
 
 
-_HANDLES = {}
+def _no_handle():
+    return None
 
 
 def handle_for(network_fn, network_fine=None, embedding_a=None, embedding_t=None):
-    """One handle per (coarse, fine, emb_a, emb_t) module set; weights re-uploaded when they change."""
-    key = tuple(id(m) for m in (network_fn, network_fine, embedding_a, embedding_t))
-    h = _HANDLES.get(key)
-    if h is None or h._mods[0] is not network_fn:
+    """One handle per (coarse, fine, emb_a, emb_t) module set; weights re-uploaded when they change.
+    The handle is cached ON the coarse module (a module -> handle -> module cycle the garbage collector can free), so
+    it lives exactly as long as the networks do and its device memory is released with them."""
+    cache = network_fn.__dict__.setdefault("_dfb_handles", {})
+    key = tuple(id(m) for m in (network_fine, embedding_a, embedding_t))
+    h = cache.get(key)
+    if h is None or h._mods[1:] != (network_fine, embedding_a, embedding_t):
         h = NerfHandle(network_fn, network_fine, embedding_a, embedding_t)
-        _HANDLES[key] = h
+        cache[key] = h
     else:
         h.refresh()
     return h
@@ -188,16 +219,17 @@ def handle_for(network_fn, network_fine=None, embedding_a=None, embedding_t=None
 def nerfw_forward(module, x, sigma_only=False, output_transient=True):
     """NeRFW.forward seam (reference nerfw.py:297-354) through dfb_nerfw_forward."""
     fine = module.typ == "fine"
-    h = _HANDLES.get(("single", id(module)))
+    h = module.__dict__.get("_dfb_single_handle")
     if h is None:
         if fine:
-            proxy = module  # a fine net needs a coarse slot; reuse the same trunk sizes
+            # a fine net needs a coarse slot: a proxy with the same trunk sizes (never evaluated)
             from .nerfw import NeRFW
-            coarse = NeRFW("coarse", D=module.D, W=module.W, skips=module.skips)
-            h = NerfHandle(coarse, proxy, None, None)
+            with torch.random.fork_rng(devices=[]):   # NeRFW.__init__ reseeds the global RNG (nerfw.py:245): keep that
+                coarse = NeRFW("coarse", D=module.D, W=module.W, skips=module.skips)  # side effect out of a forward call
+            h = NerfHandle(coarse, module, None, None)
         else:
             h = NerfHandle(module, None, None, None)
-        _HANDLES[("single", id(module))] = h
+        module.__dict__["_dfb_single_handle"] = h
     else:
         h.refresh()
     mode = 0 if sigma_only else (2 if (output_transient and fine) else 1)
@@ -220,7 +252,7 @@ def sample_pdf(bins, weights, N_samples, det=False, u=None):
     return samples, inds
 
 
-def raw2outputs(raw, z_vals, typ, test_time, beta_min=0.1):
+def raw2outputs(raw, z_vals, typ, test_time, beta_min=0.1, noise=None, raw_noise_std=0.0):
     """raw2outputs_NeRFW seam (reference rendering.py:132-243)."""
     _require_cuda(raw, "raw")
     raw, z = _f32c(raw), _f32c(z_vals)
@@ -232,7 +264,8 @@ def raw2outputs(raw, z_vals, typ, test_time, beta_min=0.1):
     o["transient_sigmas"] = torch.empty(N, S, device=dev) if Cc == 9 else None
     check(lib.dfb_raw2outputs(_ptr(raw), _ptr(z), N, S, Cc, 1 if typ == "fine" else 0, int(bool(test_time)),
                               beta_min, _ptr(o["rgb"]), _ptr(o["disp"]), _ptr(o["acc"]), _ptr(o["weights"]),
-                              _ptr(o["depth"]), _ptr(o["transient_sigmas"]), _ptr(o["beta"]), _stream()))
+                              _ptr(o["depth"]), _ptr(o["transient_sigmas"]), _ptr(o["beta"]),
+                              _ptr(_f32c(noise) if noise is not None else None), float(raw_noise_std), _stream()))
     return o
 
 

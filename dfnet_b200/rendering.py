@@ -2,12 +2,20 @@
 
 Same names, arguments and return structure as the reference (render, batchify_rays,
 render_rays, raw2outputs_NeRFW, sample_pdf); the arithmetic runs in libdfnet_b200 through
-dfnet_b200.ops.  Options no shipped config reaches (ndc, c2w_staticcam, white_bkgd,
-raw_noise_std > 0) raise instead of silently diverging.
+dfnet_b200.ops.  Options no shipped config reaches (ndc, c2w_staticcam, white_bkgd)
+raise instead of silently diverging.
 """
+import os
+import struct
+import time
+import zlib
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
 import torch
 
-from . import ops
+from . import _lib, ops
+from .nerfw import to8b
 from .ray_utils import get_rays  # noqa: F401  (re-exported like `from models.ray_utils import *`)
 
 DEFAULT_MMA = "f16"
@@ -28,13 +36,18 @@ def raw2outputs_NeRFW(raw, z_vals, rays_d=None, raw_noise_std=0, output_transien
                       white_bkgd=False, test_time=False, static_only=True, typ="coarse"):
     """Volumetric compositing (reference rendering.py:132-243) ->
     (rgb_map, disp_map, acc_map, weights, depth_map, transient_sigmas, beta)."""
-    if raw_noise_std != 0 or white_bkgd:
-        raise NotImplementedError("raw_noise_std / white_bkgd are not on the B200 hot path")
+    if white_bkgd:
+        raise NotImplementedError("white_bkgd is not on the B200 hot path")
     if not static_only:
         raise NotImplementedError("static_only=False is never used by the reference")
     if typ == "coarse" and test_time and raw.shape[-1] != 1:
         raw = raw[..., :1]
-    o = ops.raw2outputs(raw, z_vals, typ, test_time, beta_min)
+    noise = None
+    if not output_transient:
+        # the reference draws randn_like(static_sigmas) on this branch even when raw_noise_std == 0 (:173)
+        noise = torch.randn(raw.shape[:-1], device=raw.device)
+    o = ops.raw2outputs(raw, z_vals, typ, test_time, beta_min, noise=noise if raw_noise_std else None,
+                        raw_noise_std=raw_noise_std if not output_transient else 0.0)
     if typ == "coarse" and test_time:
         return None, None, o["acc"], o["weights"], None, None, None
     return o["rgb"], o["disp"], o["acc"], o["weights"], o["depth"], o["transient_sigmas"], o["beta"]
@@ -85,8 +98,6 @@ def _handle(kw):
 def _check_kwargs(kw):
     if kw.get("white_bkgd"):
         raise NotImplementedError("white_bkgd is dropped by the reference itself (rendering.py:295) and unsupported here")
-    if kw.get("raw_noise_std", 0.0):
-        raise NotImplementedError("raw_noise_std > 0 (NeRF training noise) is not on the B200 hot path yet")
 
 
 def render_rays(ray_batch, network_fn, network_query_fn=None, N_samples=64, retraw=False, lindisp=False, perturb=0.,
@@ -98,11 +109,14 @@ def render_rays(ray_batch, network_fn, network_query_fn=None, N_samples=64, retr
     _check_kwargs(kw)
     h = _handle(kw)
     N = ray_batch.shape[0]
-    t_rand = u = None
-    if perturb > 0.:
-        # same draws, shapes and order as the reference (:282 then sample_pdf :36)
-        t_rand = torch.rand(N, N_samples, device=ray_batch.device)
-        if N_importance > 0:
+    t_rand = u = noise = None
+    if perturb > 0. or raw_noise_std > 0.:
+        # same draws, shapes and order as the reference: t_rand (:282), then the coarse pass' randn_like(static_sigmas)
+        # (:173 - drawn even when raw_noise_std == 0, it advances the generator between t_rand and u), then u (:36)
+        if perturb > 0.:
+            t_rand = torch.rand(N, N_samples, device=ray_batch.device)
+        noise = torch.randn(N, N_samples, device=ray_batch.device)
+        if N_importance > 0 and perturb > 0.:
             if pytest:
                 import numpy as np
                 np.random.seed(0)
@@ -115,7 +129,8 @@ def render_rays(ray_batch, network_fn, network_query_fn=None, N_samples=64, retr
     if retraw:
         want.append("raw")
     o = h.render(N_samples, N_importance, test_time, rays=ray_batch, perturb=perturb > 0., t_rand=t_rand, u=u,
-                 mma=mma or DEFAULT_MMA, lindisp=lindisp, want=want)
+                 mma=mma or DEFAULT_MMA, lindisp=lindisp, raw_noise_std=raw_noise_std,
+                 noise=noise if raw_noise_std > 0. else None, want=want)
     ret = {"rgb_map": o["rgb"], "disp_map": o["disp"], "acc_map": o["acc"]}
     for k in want:
         ret[k] = o[k]
@@ -125,7 +140,7 @@ def render_rays(ray_batch, network_fn, network_query_fn=None, N_samples=64, retr
 def batchify_rays(rays_flat, chunk=1024 * 32, **kwargs):
     """Reference rendering.py:339-351.  The kernels bound their own workspace, so `chunk`
     only controls how the torch.rand draws are grouped when perturb > 0."""
-    if kwargs.get("perturb", 0.) > 0.:
+    if kwargs.get("perturb", 0.) > 0. or kwargs.get("raw_noise_std", 0.) > 0.:
         outs = {}
         for i in range(0, rays_flat.shape[0], chunk):
             r = render_rays(rays_flat[i:i + chunk], **kwargs)
@@ -168,7 +183,7 @@ def render(H, W, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0.,
                          torch.full((n, 1), float(far), device=rays_d.device), hist], -1)
         rgb, disp, acc = _RenderRaysFn.apply(rays_o, rays_d, viewdirs, nfh, h, Nc, Nf, mma)
         return [rgb.reshape(sh + [3]), disp.reshape(sh), acc.reshape(sh), {}]
-    if c2w is not None and not perturb:
+    if c2w is not None and not perturb and not kwargs.get("raw_noise_std", 0.):
         # whole image from one pose: rays are generated in-kernel
         h = _handle(kwargs)
         want = []
@@ -202,3 +217,138 @@ def render(H, W, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0.,
         all_ret[k] = torch.reshape(all_ret[k], sh + list(all_ret[k].shape[1:]))
     k_extract = ["rgb_map", "disp_map", "acc_map"]
     return [all_ret[k] for k in k_extract] + [{k: v for k, v in all_ret.items() if k not in k_extract}]
+
+
+def write_png(path, img8):
+    """8-bit RGB / greyscale PNG with the standard library only (the reference calls imageio.imwrite,
+    rendering.py:441-452; imageio is used instead when it is installed)."""
+    try:
+        import imageio
+        imageio.imwrite(path, img8)
+        return
+    except ImportError:
+        pass
+    a = np.ascontiguousarray(img8, dtype=np.uint8)
+    if a.ndim == 2:
+        a = a[..., None]
+    h, w, c = a.shape
+    ctype = {1: 0, 3: 2, 4: 6}[c]
+    rows = np.concatenate([np.zeros((h, 1), np.uint8), a.reshape(h, w * c)], 1).tobytes()  # filter type 0 per scanline
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xffffffff)
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, ctype, 0, 0, 0)) +
+                chunk(b"IDAT", zlib.compress(rows, 3)) + chunk(b"IEND", b""))
+
+
+def render_path(args, render_poses, hwf, chunk, render_kwargs, gt_imgs=None, savedir=None, render_factor=0,
+                single_gt_img=False, img_ids=torch.Tensor(0), mma=None):
+    """Validation render loop (reference rendering.py:403-458) -> (rgbs [n,H,W,3], disps [n,H,W]) numpy.
+
+    Per image the reference runs render(...) and `.cpu().numpy()`; here one dfb_render_image_host call uploads the pose
+    and histogram, renders and downloads rgb / disp into pinned host memory on the current stream.  Two sets of pinned
+    buffers alternate, so image i+1 renders while image i is turned into PSNR and PNG files; the PNG encoder runs on a
+    worker thread (off the stream's critical path).  Files and printed PSNR are the reference's: {i:03d}.png,
+    {i:03d}_GT.png, {i:03d}_disp.png."""
+    H, W, focal = hwf
+    if render_factor != 0:
+        H, W, focal = int(H // render_factor), int(W // render_factor), focal / render_factor
+    H, W = int(H), int(W)
+    kw = dict(render_kwargs)
+    kw.pop("network_query_fn", None)
+    mma = mma or kw.pop("mma", None) or DEFAULT_MMA
+    near, far = float(kw.get("near", 0.)), float(kw.get("far", 1.))
+    n = len(render_poses)
+    fast = bool(kw.get("test_time")) and kw.get("N_importance", 0) > 0 and not kw.get("perturb") and not kw.get("raw_noise_std")
+    rgbs, disps, psnr = [], [], []
+    pool = ThreadPoolExecutor(max_workers=2) if savedir is not None else None
+    jobs = []
+    t0 = time.time()
+
+    def consume(i, rgb_np, disp_np):
+        rgbs.append(rgb_np), disps.append(disp_np)
+        if i == 0:
+            print(rgb_np.shape, disp_np.shape)
+        if gt_imgs is not None:
+            gt = gt_imgs if single_gt_img else gt_imgs[i]
+            psnr.append(-10. * np.log10(np.mean(np.square(rgb_np - np.asarray(gt)))))
+        if savedir is not None:
+            jobs.append(pool.submit(write_png, os.path.join(savedir, "{:03d}.png".format(i)), to8b(rgb_np)))
+            if gt_imgs is not None:
+                jobs.append(pool.submit(write_png, os.path.join(savedir, "{:03d}_GT.png".format(i)), to8b(np.asarray(gt_imgs[i]))))
+            jobs.append(pool.submit(write_png, os.path.join(savedir, "{:03d}_disp.png".format(i)), to8b(disp_np / np.max(disp_np))))
+
+    if fast and n > 0:
+        h = _handle(kw)
+        dev = next(kw["network_fn"].parameters()).device
+        cfg = _lib.RenderCfg(N_samples=kw["N_samples"], N_importance=kw["N_importance"], test_time=1, perturb=0,
+                             mma_kind=_lib.MMA_KINDS[mma], lindisp=int(bool(kw.get("lindisp", False))), raw_noise_std=0.0)
+        poses_h = torch.stack([torch.as_tensor(p)[:3, :4] for p in render_poses]).float().cpu().contiguous().pin_memory()
+        hists_h = torch.stack([torch.as_tensor(img_ids[i]).reshape(-1) for i in range(n)]).float().cpu().contiguous().pin_memory()
+        bufs = [(torch.empty(H * W, 3).pin_memory(), torch.empty(H * W).pin_memory(), torch.empty(H * W).pin_memory(),
+                 torch.cuda.Event()) for _ in range(2)]
+        stream = torch.cuda.current_stream(dev)
+
+        def launch(i):
+            rgb_h, disp_h, acc_h, ev = bufs[i & 1]
+            h.render_image_host(cfg, poses_h[i], H, W, float(focal), near, far, hists_h[i], rgb_h, disp_h, acc_h, dev)
+            ev.record(stream)
+        launch(0)
+        for i in range(n):
+            rgb_h, disp_h, _, ev = bufs[i & 1]
+            ev.synchronize()
+            rgb_np, disp_np = rgb_h.numpy().reshape(H, W, 3).copy(), disp_h.numpy().reshape(H, W).copy()
+            if i + 1 < n:
+                launch(i + 1)   # the next image renders while this one is scored and encoded
+            consume(i, rgb_np, disp_np)
+    else:
+        for i, c2w in enumerate(render_poses):
+            rgb, disp, acc, _ = render(H, W, focal, chunk=chunk, c2w=c2w[:3, :4], img_idx=img_ids[i], mma=mma, **kw)
+            consume(i, rgb.cpu().numpy(), disp.cpu().numpy())
+    for j in jobs:
+        j.result()
+    if pool is not None:
+        pool.shutdown()
+    rgbs = np.stack(rgbs, 0) if rgbs else np.zeros((0, H, W, 3), np.float32)
+    disps = np.stack(disps, 0) if disps else np.zeros((0, H, W), np.float32)
+    print("Mean PSNR of this run is:", np.mean(psnr, 0) if psnr else float("nan"), "(%.2f s)" % (time.time() - t0))
+    return rgbs, disps
+
+
+def render_test(args, train_dl, val_dl, hwf, start, render_kwargs_test, decoder_coarse=None, decoder_fine=None):
+    """Reference rendering.py:460-530: renders the training and validation views of the two loaders into
+    basedir/expname/evaluate_{train,val}_{test|path}_{start:06d}/ with render_path.  Loader batches are the reference's
+    (img [1,3,H,W], pose [1,12], hist [1,hist_bin]).  Videos (--render_video_*) need imageio and are written when it is
+    installed."""
+    dev = next(render_kwargs_test["network_fn"].parameters()).device
+    for tag, dl, video, vname in (("train", train_dl, getattr(args, "render_video_train", False), "trainset"),
+                                  ("val", val_dl, getattr(args, "render_video_test", False), "test")):
+        savedir = os.path.join(args.basedir, args.expname,
+                               "evaluate_{}_{}_{:06d}".format(tag, "test" if getattr(args, "render_test", False) else "path", start))
+        os.makedirs(savedir, exist_ok=True)
+        images, poses, index = [], [], []
+        for img, pose, img_idx in dl:
+            images.append(img.permute(0, 2, 3, 1))
+            p = torch.zeros(1, 4, 4)
+            p[0, :3, :4] = pose.reshape(3, 4)[:3, :4]
+            p[0, 3, 3] = 1.
+            poses.append(p), index.append(img_idx)
+        images = torch.cat(images, 0).numpy()
+        poses = torch.cat(poses, 0).to(dev)
+        index = torch.cat(index, 0).to(dev)
+        print(("train" if tag == "train" else "test") + " poses shape", poses.shape)
+        with torch.no_grad():
+            rgbs, disps = render_path(args, poses, hwf, args.chunk, render_kwargs_test, gt_imgs=images, savedir=savedir,
+                                      img_ids=index)
+        print("Saved {} set".format("train" if tag == "train" else "test"))
+        if video:
+            try:
+                import imageio
+            except ImportError:
+                print("imageio is not installed: skipping the mp4 of the", tag, "set")
+                continue
+            base = os.path.join(args.basedir, args.expname, "{}_{}_{:06d}_".format(args.expname, vname, start))
+            imageio.mimwrite(base + ("train" if tag == "train" else "test") + "_rgb.mp4", to8b(rgbs), fps=15, quality=8)
+            imageio.mimwrite(base + ("train" if tag == "train" else "test") + "_disp.mp4", to8b(disps / np.max(disps)), fps=15, quality=8)
+    return

@@ -95,8 +95,12 @@ typedef struct DfbRenderCfg {
   int32_t perturb;      /* 1: stratified jitter; t_rand and u must be supplied         */
   int32_t mma_kind;     /* DFB_MMA_*                                                   */
   int32_t lindisp;      /* sample linearly in disparity (rendering.py:272-273)         */
-  float raw_noise_std;  /* must be 0: the reference's noise is randn()*std             */
-  int32_t reserved;
+  float raw_noise_std;  /* std of the density noise (rendering.py:173-174); != 0 needs the `noise` draws  */
+  int32_t ray_stride;   /* rays mode: floats per ray record as laid out by the caller; must be
+                           11 + hist_bin (the [o3,d3,near,far,viewdir3,hist] row of rendering.py:382-389)  */
+  int32_t hist_len;     /* c2w mode: number of floats behind `hist`; must be hist_bin            */
+  float ert_eps;        /* opt-in early ray termination (0 = off, the parity path): fine samples behind the
+                           depth where the COARSE transmittance falls below ert_eps are not evaluated   */
 } DfbRenderCfg;
 
 /* Optional outputs (NULL = not wanted).  Train-mode extras follow rendering.py:318-331. */
@@ -128,11 +132,13 @@ int dfb_render_workspace_bytes(const DfbNerf* nerf, const DfbRenderCfg* cfg, int
  *                   for an H x W image with N == H*W; near/far scalars; hist device [hist_bin].
  * t_rand [N,Nc] / u [N,Nf]: uniform draws the reference takes from torch.rand when
  * perturb > 0 (:282, :36); NULL when perturb == 0.
+ * noise [N,Nc]: the standard-normal draws of the coarse compositing (torch.randn_like(static_sigmas), :173);
+ * required when cfg->raw_noise_std != 0, else NULL (the reference multiplies them by 0).
  * Outputs rgb [N,3], disp [N], acc [N] (device). */
 int dfb_render_fwd(DfbNerf* nerf, const DfbRenderCfg* cfg, const float* rays, const float* c2w, int H, int W,
                    float focal, float near, float far, const float* hist, int64_t N, const float* t_rand,
-                   const float* u, float* rgb, float* disp, float* acc, const DfbRenderExtras* extras, void* ws,
-                   size_t ws_bytes, void* stream);
+                   const float* u, const float* noise, float* rgb, float* disp, float* acc,
+                   const DfbRenderExtras* extras, void* ws, size_t ws_bytes, void* stream);
 
 /* Same as dfb_render_fwd with c2w/hist and the three outputs in HOST memory (pinned for
  * true asynchrony): the pose/histogram upload and the image download are enqueued on
@@ -145,18 +151,18 @@ int dfb_render_image_host(DfbNerf* nerf, const DfbRenderCfg* cfg, const float* c
 /* Backward of the test-time render w.r.t. the rays — what train.py needs from the renderer
  * (feature/direct_feature_matching.py:342-378: the NeRF weights are frozen and z_samples detached,
  * models/rendering.py:302, so only the fine network's inputs carry gradient).
- * rays [N,11+hist_bin] as in the forward; z_vals [N,S] and raw [N,S,9] are the forward's extras
+ * rays [N,ray_stride] as in the forward (ray_stride must be 11+hist_bin); z_vals [N,S] and raw [N,S,9] are the forward's extras
  * (S = N_samples + N_importance); g_rgb [N,3] is dLoss/d rgb_map.  Outputs: gradients w.r.t. rays_o,
  * rays_d (through pts = o + d*z) and the view directions (through the direction encoding), each [N,3].
  * fp32 kernels (forward recompute + input-gradient chain); all device pointers. */
 int dfb_render_bwd_workspace_bytes(const DfbNerf* nerf, int64_t n_rays, int S, size_t* out);
-int dfb_render_bwd(DfbNerf* nerf, const float* rays, int64_t N, int S, const float* z_vals, const float* raw,
+int dfb_render_bwd(DfbNerf* nerf, const float* rays, int ray_stride, int64_t N, int S, const float* z_vals, const float* raw,
                    const float* g_rgb, float* g_rays_o, float* g_rays_d, float* g_viewdirs, void* ws, size_t ws_bytes,
                    void* stream);
 /* Same with the fine network's forward recompute and input-gradient chain on the tensor cores (tcgen05, 8x256
  * networks; mma_kind as in DfbRenderCfg: the kind the forward ran with).  DFB_MMA_FP32_SIMT = dfb_render_bwd;
  * other network shapes fall back to the fp32 kernels. */
-int dfb_render_bwd_mma(DfbNerf* nerf, int mma_kind, const float* rays, int64_t N, int S, const float* z_vals,
+int dfb_render_bwd_mma(DfbNerf* nerf, int mma_kind, const float* rays, int ray_stride, int64_t N, int S, const float* z_vals,
                        const float* raw, const float* g_rgb, float* g_rays_o, float* g_rays_d, float* g_viewdirs, void* ws,
                        size_t ws_bytes, void* stream);
 
@@ -164,7 +170,7 @@ int dfb_render_bwd_mma(DfbNerf* nerf, int mma_kind, const float* rays, int64_t N
  * mma_kind): the backward kernel skips the forward recompute (15 instead of 26 MMA steps per tile).  relu_masks == NULL
  * recomputes.  N*S must keep every internal 16384-ray chunk aligned to 128 samples (any S that is a multiple of 1/128
  * of the chunk, e.g. every S when N <= 16384). */
-int dfb_render_bwd_saved(DfbNerf* nerf, int mma_kind, const float* rays, int64_t N, int S, const float* z_vals,
+int dfb_render_bwd_saved(DfbNerf* nerf, int mma_kind, const float* rays, int ray_stride, int64_t N, int S, const float* z_vals,
                          const float* raw, const uint32_t* relu_masks, const float* g_rgb, float* g_rays_o, float* g_rays_d,
                          float* g_viewdirs, void* ws, size_t ws_bytes, void* stream);
 
@@ -173,10 +179,11 @@ int dfb_render_bwd_saved(DfbNerf* nerf, int mma_kind, const float* rays, int64_t
 int dfb_sample_pdf(const float* bins, const float* weights, const float* u, int64_t N, int n_bins, int Nf,
                    float* samples, int32_t* inds, void* stream);
 /* raw2outputs_NeRFW (rendering.py:132-243).  typ: 0 coarse, 1 fine.  raw [N,S,C] with
- * C = 1 (coarse+test), 4 (coarse train) or 9 (fine).  Any output may be NULL. */
+ * C = 1 (coarse+test), 4 (coarse train) or 9 (fine).  Any output may be NULL.
+ * noise [N,S] (nullable) with raw_noise_std: the coarse pass' density noise (:173-174; the fine pass has none). */
 int dfb_raw2outputs(const float* raw, const float* z_vals, int64_t N, int S, int C, int typ, int test_time,
                     float beta_min, float* rgb, float* disp, float* acc, float* weights, float* depth,
-                    float* transient_sigmas, float* beta, void* stream);
+                    float* transient_sigmas, float* beta, const float* noise, float raw_noise_std, void* stream);
 /* get_rays (ray_utils.py:5-15): c2w device [3,4] -> rays_o, rays_d device [H*W,3]. */
 int dfb_get_rays(const float* c2w, int row_stride, int H, int W, float focal, float* rays_o, float* rays_d,
                  void* stream);

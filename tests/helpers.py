@@ -133,3 +133,91 @@ def pad_nerfw_state_dict(P, W, W2=256, in_xyz=63):
         for nm, r in (("transient_sigma", 1), ("transient_rgb", 3), ("transient_beta", 1)):
             Q[f"{nm}.0.weight"], Q[f"{nm}.0.bias"] = pad(P[f"{nm}.0.weight"], r, H2), P[f"{nm}.0.bias"]
     return Q
+
+
+def torch_nerfw_forward(m, x, mode):
+    """Plain torch restatement of NeRFW.forward (reference models/nerfw.py:297-354) on the module's own layers; test
+    infrastructure for fitting a field (dfnet_b200's NeRFW.forward itself runs on the CUDA kernels and is not
+    differentiable w.r.t. the weights).  mode: "sigma" | "static" | "full"."""
+    ixyz = x[:, :m.in_channels_xyz]
+    h = ixyz
+    for i in range(m.D):
+        if i in m.skips:
+            h = torch.cat([ixyz, h], 1)
+        h = getattr(m, f"xyz_encoding_{i + 1}")(h)
+    sigma = m.static_sigma(h)
+    if mode == "sigma":
+        return sigma
+    final = m.xyz_encoding_final(h)
+    nd = m.in_channels_dir + m.in_channels_a
+    de = m.dir_encoding(torch.cat([final, x[:, m.in_channels_xyz:m.in_channels_xyz + nd]], 1))
+    static = torch.cat([m.static_rgb(de), sigma], 1)
+    if mode == "static":
+        return static
+    t = m.transient_encoding(torch.cat([final, x[:, m.in_channels_xyz + nd:]], 1))
+    return torch.cat([static, m.transient_rgb(t), m.transient_sigma(t), m.transient_beta(t)], 1)
+
+
+def _embed_t(x, L):
+    out = [x]
+    for l in range(L):
+        out += [torch.sin(x * 2.0 ** l), torch.cos(x * 2.0 ** l)]
+    return torch.cat(out, -1)
+
+
+def fit_synthetic_scene(D=8, W=256, steps=400, batch=8192, device="cpu", seed=0):
+    """A "trained-like" NeRF-Hist field: the seeded default-initialised networks regressed (Adam, fp32, plain torch) onto
+    an analytic scene in front of the benchmark camera - three solid objects with sharp density steps (sigma 0 / 40) and a
+    position-dependent colour with high-frequency stripes, a faint transient fog.  Returns (coarse, fine, emb_a, emb_t)
+    like make_synthetic_nerf.  Used by the sharper-field parity tests: the oracle is evaluated on the SAME weights, so
+    the fit does not need to be reproducible across machines."""
+    state = torch.get_rng_state()
+    c, f, ea, et = my_nerfw.make_synthetic_nerf(D=D, W=W, gain=1.0, sigma_bias=0.0)
+    c, f, ea, et = c.to(device), f.to(device), ea.to(device), et.to(device)
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    opt = torch.optim.Adam(list(c.parameters()) + list(f.parameters()), lr=1e-3)
+    hist = torch.tensor([5, 10, 20, 30, 15, 10, 5, 3, 1, 1], device=device)
+
+    def scene(p):
+        s1 = ((p - torch.tensor([0.15, 0.1, -0.4], device=device)).norm(dim=-1) < 0.35)
+        s2 = ((p - torch.tensor([-0.35, -0.15, -0.9], device=device)).abs().amax(-1) < 0.25)
+        wall = p[:, 2] < -1.2
+        inside = (s1 | s2 | wall).float()
+        sigma = 40.0 * inside
+        stripes = 0.5 + 0.5 * torch.sin(18.0 * p[:, :1] + 11.0 * p[:, 1:2])
+        rgb = torch.cat([stripes, 0.5 + 0.4 * torch.sin(7.0 * p[:, 1:2]), 0.3 + 0.6 * s1.float()[:, None]], 1)
+        return sigma, rgb
+
+    with torch.enable_grad():
+        for it in range(steps):
+            p = (torch.rand(batch, 3, generator=g) * torch.tensor([1.6, 1.2, 2.5]) + torch.tensor([-0.8, -0.6, -1.5])).to(device)
+            d = torch.nn.functional.normalize(torch.randn(batch, 3, generator=g), dim=-1).to(device)
+            sig, rgb = scene(p)
+            a = ea(hist).reshape(1, -1).expand(batch, -1)
+            t = et(hist).reshape(1, -1).expand(batch, -1)
+            x = torch.cat([_embed_t(p, 10), _embed_t(d, 4), a, t], -1)
+            out_f = torch_nerfw_forward(f, x, "full")
+            out_c = torch_nerfw_forward(c, x[:, :63], "sigma")
+            w = 1.0 / 40.0
+            loss = (((out_f[:, 3] - sig) * w) ** 2).mean() + (((out_c[:, 0] - sig) * w) ** 2).mean() + \
+                ((out_f[:, :3] - rgb) ** 2 * (0.05 + (sig > 0).float()[:, None])).mean() + \
+                (out_f[:, 7] ** 2).mean() * 0.1 + ((out_f[:, 8] - 0.05) ** 2).mean() * 0.1
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+    for m in (c, f, ea, et):
+        for q in m.parameters():
+            q.requires_grad_(False)
+    torch.set_rng_state(state)
+    return c, f, ea, et
+
+
+def full_size_pair(H=480, W=640, seed=6):
+    """The 640x480 target / render pair of BASELINE config[2] (tests/golden/make_golden_dfnet_full.py): a smooth
+    low-frequency image plus noise, and a slightly shifted / re-lit copy of it (a render resembles its target)."""
+    rng = np.random.RandomState(seed)
+    yy, xx = np.meshgrid(np.linspace(0, 1, H, dtype=np.float32), np.linspace(0, 1, W, dtype=np.float32), indexing="ij")
+    base = np.stack([0.5 + 0.4 * np.sin(9 * xx + 3 * yy), 0.5 + 0.4 * np.cos(7 * yy - 2 * xx), 0.3 + 0.5 * xx * yy]).astype(np.float32)
+    a = np.clip(base + 0.08 * rng.randn(3, H, W).astype(np.float32), 0, 1)
+    b = np.clip(0.95 * np.roll(base, (3, -2), (1, 2)) + 0.02 + 0.08 * rng.randn(3, H, W).astype(np.float32), 0, 1)
+    return np.stack([a, b]).astype(np.float32)

@@ -1,7 +1,7 @@
 """GPU parity tests of the DFNet feature path (tcgen05 implicit-GEMM convolutions, fused losses)
 through the C ABI.  Floating-point kernels: compared with a plain PyTorch fp32 reference of the same
 op and with the reference-generated golden vectors; tolerance 1e-3 of the tensor's magnitude for a
-single layer and for losses, 5e-3 of the feature magnitude through the 13+2-layer fp16 network."""
+single layer, for losses and for the feature stacks through the 13+2-layer network."""
 import ctypes as C
 import os
 
@@ -10,7 +10,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from helpers import synthetic_dfnet
+from helpers import full_size_pair, sd_checksum, synthetic_dfnet
 
 pytestmark = pytest.mark.gpu
 
@@ -248,3 +248,37 @@ def test_dfnet_cambridge_shape_ragged_pooling():
     for s in range(2):
         for l in range(3):
             assert relmax(feats[s][l].cpu().numpy(), want[s][l]) < 5e-3, (s, l)
+
+
+def test_dfnet_full_size_pair_vs_reference_golden():
+    """BASELINE config[2] numerically: the 640x480 target / render pair through DFNet against the UNMODIFIED reference
+    (tests/golden/make_golden_dfnet_full.py; a [.., ::16, ::24, ::32] subsample of both feature stacks, per-level
+    statistics, pose, and the cosine losses).  Feature gate: 1e-3 of the level's magnitude (north star)."""
+    from dfnet_b200.dfnet import feature_loss, preprocess_features_for_loss
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "dfnet_full_golden.npz"))
+    net = synthetic_dfnet("DFNet")
+    assert sd_checksum(net.state_dict()) == bytes(g["sha"]).decode()
+    net = net.to(dev())
+    x = torch.tensor(full_size_pair(), device=dev())
+    with torch.no_grad():
+        feats, pose = net(x, return_feature=True, isSingleStream=False, return_pose=True, upsampleH=480, upsampleW=640)
+    torch.cuda.synchronize()
+    assert feats[0].shape == (3, 1, 128, 480, 640)
+    e_pose = relmax(pose.cpu().numpy(), g["pose"])
+    errs = {}
+    for nm, f in (("t", feats[0]), ("r", feats[1])):
+        got, want = f[:, :, ::16, ::24, ::32].cpu().numpy(), g[f"feat_{nm}_sub"]
+        for l in range(3):
+            errs[(nm, l)] = relmax(got[l], want[l])
+            st = g[f"feat_{nm}_stats"][l]
+            assert abs(float(f[l].abs().sum().double()) - st[0]) / st[0] < 1e-3, (nm, l)
+            assert abs(float((f[l].double() ** 2).sum()) - st[2]) / st[2] < 2e-3, (nm, l)
+    print("DFNet 640x480 vs reference: pose", e_pose, "features (max err / max |x| per stream, level):", errs)
+    assert e_pose < 1e-3
+    assert max(errs.values()) < 1e-3, errs
+    ft = preprocess_features_for_loss(feats[0])[0]
+    fr = preprocess_features_for_loss(feats[1])[0]
+    for key, a, b in (("loss_lvl0", fr[:128].contiguous(), ft[:128].contiguous()), ("loss_lvl012", fr, ft)):
+        got, want = float(feature_loss(a, b)), float(g[key])
+        print(key, got, want)
+        assert abs(got - want) < 1e-3 * abs(want), (key, got, want)

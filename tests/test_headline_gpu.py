@@ -1,0 +1,232 @@
+"""Parity of the paths the headline numbers rest on (VERDICT r01 "weak" 1-2): the end-to-end host call
+`dfb_render_image_host` that bench.py's `e2e` leg times, the full-size fp16 tensor-core render against the ORACLE (not
+against the repo's own fp32 kernels), BASELINE config[4]'s shape, a trained-like (sharp) field, and the §8b shims
+`render_path` / `create_nerf` with their file formats."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import fit_synthetic_scene, np_params, rel_err, synthetic_nets
+from oracle import nerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+HIST = np.array([5, 10, 20, 30, 15, 10, 5, 3, 1, 1], np.float32)
+C2W = np.array([[0.9962, -0.0872, 0.0, 0.0], [0.0872, 0.9962, 0.0, 0.0], [0.0, 0.0, 1.0, 1.0]], np.float32)
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from dfnet_b200 import ops
+    mods, nets = synthetic_nets(8, 256)
+    h = ops.NerfHandle(*[m.to(dev()) for m in mods])
+    return ops, h, nets
+
+
+def _oracle_subset(nets, H, W, focal, near, far, Nc, Nf, sel):
+    o, d = O.get_rays(H, W, focal, C2W)
+    rec = O.make_ray_records(o.reshape(-1, 3)[sel], d.reshape(-1, 3)[sel], near, far, HIST[None])
+    O.set_linear_backend("torch")   # same arithmetic, threaded GEMMs: keeps 2 000 rays x 192 samples within seconds
+    try:
+        return O.render_rays(rec, nets, Nc, Nf, test_time=True)
+    finally:
+        O.set_linear_backend("numpy")
+
+
+def test_render_image_host_is_the_device_path_and_matches_the_oracle(ctx):
+    """a10: the render_path step (host pose in, host image out) at BASELINE config[1] size.  Its three host outputs must
+    be bit-identical to dfb_render_fwd's device outputs (checks the staging offsets and the D2H copies) and a 2 000-ray
+    subset must match the oracle at the north star's 1e-3."""
+    from dfnet_b200 import _lib
+    ops, h, nets = ctx
+    H, W, focal, near, far, Nc, Nf = 480, 640, 585.0, 0.0, 2.5, 64, 128
+    cfg = _lib.RenderCfg(N_samples=Nc, N_importance=Nf, test_time=1, perturb=0, mma_kind=_lib.MMA_KINDS["f16"],
+                         lindisp=0, raw_noise_std=0.0)
+    c2w_h, hist_h = torch.tensor(C2W).pin_memory(), torch.tensor(HIST).pin_memory()
+    rgb_h, disp_h, acc_h = torch.empty(H * W, 3).pin_memory(), torch.empty(H * W).pin_memory(), torch.empty(H * W).pin_memory()
+    rgb_h.fill_(-7.0), disp_h.fill_(-7.0), acc_h.fill_(-7.0)
+    h.render_image_host(cfg, c2w_h, H, W, focal, near, far, hist_h, rgb_h, disp_h, acc_h, dev())
+    torch.cuda.synchronize()
+    o = h.render(Nc, Nf, True, c2w=torch.tensor(C2W, device=dev()), H=H, W=W, focal=focal, near=near, far=far,
+                 hist=torch.tensor(HIST, device=dev()), mma="f16")
+    torch.cuda.synchronize()
+    assert torch.equal(rgb_h, o["rgb"].cpu()) and torch.equal(disp_h, o["disp"].cpu()) and torch.equal(acc_h, o["acc"].cpu())
+    sel = np.arange(0, H * W, 153)[:2000]
+    want = _oracle_subset(nets, H, W, focal, near, far, Nc, Nf, sel)
+    e_rgb = rel_err(rgb_h.numpy()[sel], want["rgb_map"])
+    e_acc = rel_err(acc_h.numpy()[sel], want["acc_map"])
+    print("render_image_host vs oracle (2000 rays, f16): rgb", e_rgb, "acc", e_acc)
+    assert e_rgb < 1e-3 and e_acc < 1e-3
+    ok = want["disp_map"] < 1e3       # disp = 1/depth is ill-conditioned where depth -> 0
+    assert ok.mean() > 0.9 and rel_err(disp_h.numpy()[sel][ok], want["disp_map"][ok]) < 2e-3
+    # a histogram of the wrong length is refused before anything is read
+    with pytest.raises(_lib.DfbError):
+        h.render_image_host(cfg, c2w_h, H, W, focal, near, far, torch.zeros(3).pin_memory(), rgb_h, disp_h, acc_h, dev())
+
+
+@pytest.mark.parametrize("name,H,W,focal,near,far,Nc,Nf,n", [
+    ("cfg2", 480, 640, 585.0, 0.0, 2.5, 64, 128, 2000),
+    ("cfg5", 1080, 1920, 1674.0, 0.0, 20.0, 64, 192, 800)])
+def test_full_size_tensor_core_render_vs_oracle(ctx, name, H, W, focal, near, far, Nc, Nf, n):
+    """The fp16 tcgen05 render of a whole image (BASELINE config[1] and config[4] shapes) against the oracle on a ray
+    subset spread over the image, both cta_group variants."""
+    ops, h, nets = ctx
+    sel = np.linspace(0, H * W - 1, n).astype(np.int64)
+    want = _oracle_subset(nets, H, W, focal, near, far, Nc, Nf, sel)
+    for cg in ("2", "1"):
+        os.environ["DFB_TC_CTA_GROUP"] = cg
+        try:
+            o = h.render(Nc, Nf, True, c2w=torch.tensor(C2W, device=dev()), H=H, W=W, focal=focal, near=near, far=far,
+                         hist=torch.tensor(HIST, device=dev()), mma="f16")
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("DFB_TC_CTA_GROUP", None)
+        e_rgb = rel_err(o["rgb"].cpu().numpy()[sel], want["rgb_map"])
+        e_acc = rel_err(o["acc"].cpu().numpy()[sel], want["acc_map"])
+        print(name, "cta_group", cg, "f16 vs oracle: rgb", e_rgb, "acc", e_acc)
+        assert e_rgb < 1e-3 and e_acc < 1e-3, (name, cg)
+
+
+def test_ray_record_width_is_checked(ctx):
+    """a record that is not [.., 11 + hist_bin] wide (e.g. a stray img_idx column, or the reference's default
+    empty img_idx) must raise, not be read misaligned."""
+    from dfnet_b200._lib import DfbError
+    ops, h, _ = ctx
+    bad = torch.zeros(16, 22, device=dev())
+    with pytest.raises(DfbError):
+        h.render(64, 128, True, rays=bad, mma="f16")
+    with pytest.raises(DfbError):
+        h.render(64, 128, True, c2w=torch.tensor(C2W, device=dev()), H=2, W=2, focal=1.0, hist=torch.zeros(0), mma="f16")
+    with pytest.raises(DfbError):
+        h.render_backward(bad, torch.zeros(16, 192, device=dev()), torch.zeros(16, 192, 9, device=dev()),
+                          torch.zeros(16, 3, device=dev()), mma="f16")
+
+
+@pytest.fixture(scope="module")
+def fitted():
+    """Trained-like field: sharp density steps (sigma 0 / 40), striped colours; fitted on the GPU with plain torch."""
+    c, f, ea, et = fit_synthetic_scene(steps=400, batch=16384, device=dev())
+    nets = dict(coarse=np_params(c), fine=np_params(f), emb_a=ea.weight.detach().cpu().numpy(),
+                emb_t=et.weight.detach().cpu().numpy(), D=8, skips=(4,), beta_min=0.1)
+    return (c, f, ea, et), nets
+
+
+def test_trained_like_field_precision_ladder(fitted):
+    """VERDICT r01 weak #2c.  A field with structure (the seeded gain-1.6 field renders rgb in [0.51, 0.55]): rendered
+    rgb spans ~[0.1, 0.95].  Gates:
+      * hidden activations stay far inside fp16's range (max |pre-activation| recorded from the oracle);
+      * fp32 kernels: <= 1e-4 of the oracle on every ray;
+      * fp16 tensor-core kernels: operand rounding (2^-11) is amplified by a sharp field - the per-ray error is
+        gated in distribution (mean <= 1e-3, 99th percentile <= 1e-2) and the measured numbers are printed; the 1e-3
+        MAX bar of the smooth field does not hold here (measured ~5 % of rays above it), which is what the fp32 path
+        is for."""
+    from dfnet_b200 import ops
+    mods, nets = fitted
+    H, W, focal, near, far, Nc, Nf = 480, 640, 585.0, 0.0, 2.5, 64, 128
+    sel = np.linspace(0, H * W - 1, 1500).astype(np.int64)
+    amax = [0.0]
+    lin0 = O._linear
+
+    def lin_track(x, w, b):
+        y = lin0(x, w, b)
+        amax[0] = max(amax[0], float(np.abs(y).max()))
+        return y
+    O._linear = lin_track
+    try:
+        want = _oracle_subset(nets, H, W, focal, near, far, Nc, Nf, sel)
+    finally:
+        O._linear = lin0
+    print("trained-like field: max |pre-activation| =", amax[0], " rgb range", want["rgb_map"].min(), want["rgb_map"].max())
+    assert amax[0] < 65504 / 16
+    assert want["rgb_map"].max() - want["rgb_map"].min() > 0.5      # the field has structure
+    h = ops.NerfHandle(*mods)
+    o, d = O.get_rays(H, W, focal, C2W)
+    rec = torch.tensor(O.make_ray_records(o.reshape(-1, 3)[sel], d.reshape(-1, 3)[sel], near, far, HIST[None]), device=dev())
+    got32 = h.render(Nc, Nf, True, rays=rec, mma="fp32")
+    e32 = rel_err(got32["rgb"].cpu().numpy(), want["rgb_map"])
+    print("fp32 kernels vs oracle: max rel rgb err", e32)
+    assert e32 < 1e-4
+    for mma in ("f16", "bf16"):
+        got = h.render(Nc, Nf, True, rays=rec, mma=mma)
+        r = np.abs(got["rgb"].cpu().numpy() - want["rgb_map"]) / np.maximum(np.abs(want["rgb_map"]), 1e-3)
+        per_ray = r.max(1)
+        print(f"{mma} tensor-core kernels vs oracle on the trained-like field: mean {per_ray.mean():.2e} p99 "
+              f"{np.percentile(per_ray, 99):.2e} max {per_ray.max():.2e} frac>1e-3 {(per_ray > 1e-3).mean():.3f}")
+        assert np.isfinite(r).all()
+        if mma == "f16":
+            assert per_ray.mean() < 1e-3 and np.percentile(per_ray, 99) < 1e-2
+
+
+def test_render_path_shim_writes_the_reference_files(ctx, tmp_path):
+    """§8b: render_path on top of dfb_render_image_host - same return values as per-image render() calls, the
+    reference's file names, 8-bit PNGs that decode to to8b(rgb)."""
+    import cv2
+    from dfnet_b200 import rendering
+    from dfnet_b200.nerfw import to8b
+    mods, _ = synthetic_nets(8, 256)
+    c, f, ea, et = [m.to(dev()) for m in mods]
+    kw = dict(network_query_fn=None, perturb=False, N_importance=32, network_fine=f, N_samples=16, network_fn=c,
+              use_viewdirs=True, white_bkgd=False, raw_noise_std=0.0, embedding_a=ea, embedding_t=et, test_time=True,
+              ndc=False, lindisp=False, near=0.0, far=2.5)
+    H, W, focal = 24, 32, 30.0
+    poses = torch.tensor(np.stack([np.concatenate([C2W, [[0, 0, 0, 1]]], 0)] * 3).astype(np.float32), device=dev())
+    poses[1, 0, 3] = 0.1
+    poses[2, 1, 3] = -0.1
+    hists = torch.tensor(np.stack([HIST, HIST[::-1].copy(), HIST]), device=dev())
+    gt = np.random.RandomState(0).rand(3, H, W, 3).astype(np.float32)
+    args = types.SimpleNamespace()
+    rgbs, disps = rendering.render_path(args, poses, (H, W, focal), 32768, kw, gt_imgs=gt, savedir=str(tmp_path), img_ids=hists)
+    assert rgbs.shape == (3, H, W, 3) and disps.shape == (3, H, W)
+    for i in range(3):
+        rgb, disp, acc, _ = rendering.render(H, W, focal, c2w=poses[i, :3, :4], img_idx=hists[i], **kw)
+        assert np.array_equal(rgbs[i], rgb.cpu().numpy()) and np.array_equal(disps[i], disp.cpu().numpy())
+        png = cv2.imread(str(tmp_path / f"{i:03d}.png"))[..., ::-1]
+        assert np.array_equal(png, to8b(rgbs[i]))
+        assert np.array_equal(cv2.imread(str(tmp_path / f"{i:03d}_GT.png"))[..., ::-1], to8b(gt[i]))
+        assert np.array_equal(cv2.imread(str(tmp_path / f"{i:03d}_disp.png"), cv2.IMREAD_UNCHANGED),
+                              to8b(disps[i] / np.max(disps[i])))
+    # render_factor and the general (non test-time) branch
+    kw_train = dict(kw, test_time=False)
+    r2, d2 = rendering.render_path(args, poses[:1], (H, W, focal), 32768, kw_train, render_factor=2, img_ids=hists, mma="fp32")
+    assert r2.shape == (1, H // 2, W // 2, 3) and np.isfinite(r2).all()
+
+
+def test_create_nerf_and_tar_checkpoint_roundtrip(tmp_path):
+    """§8b: create_nerf(args) -> kwargs / optimizer; the .tar checkpoint dict of run_nerf.py:150-167 written by
+    save_checkpoint is found (newest *tar* file of basedir/expname) and reloaded bit for bit."""
+    from dfnet_b200 import nerfw, rendering
+    exp = tmp_path / "exp"
+    exp.mkdir()
+    args = types.SimpleNamespace(NeRFH=True, encode_hist=True, multires=10, multires_views=4, use_viewdirs=True, i_embed=0,
+                                 reduce_embedding=-1, N_vocab=1000, netdepth=8, netwidth=128, N_importance=64, N_samples=64,
+                                 in_channels_a=50, in_channels_t=20, no_grad_update=False, lrate=5e-4, basedir=str(tmp_path),
+                                 expname="exp", ft_path=None, no_reload=False, perturb=1.0, white_bkgd=False,
+                                 raw_noise_std=0.0, dataset_type="7Scenes", no_ndc=True, lindisp=False, multi_gpu=False)
+    ktr, kte, start, grad_vars, opt = nerfw.create_nerf(args)
+    assert start == 0 and isinstance(opt, torch.optim.Adam) and len(grad_vars) == 24 + 38 + 2
+    assert ktr["test_time"] is False and kte["test_time"] is True and kte["perturb"] is False and ktr["perturb"] == 1.0
+    assert ktr["ndc"] is False and next(ktr["network_fn"].parameters()).is_cuda
+    with torch.no_grad():   # make the four modules distinguishable from a fresh construction
+        for k in ("network_fn", "network_fine", "embedding_a", "embedding_t"):
+            for p in ktr[k].parameters():
+                p.add_(torch.randn_like(p) * 0.01)
+    nerfw.save_checkpoint(str(exp / "000100.tar"), 1234, ktr, opt)
+    nerfw.save_checkpoint(str(exp / "000050.tar"), 50, {"network_fn": nerfw.NeRFW("coarse", W=128),
+                                                        "network_fine": None}, None)   # older: must not be picked
+    ktr2, kte2, start2, _, _ = nerfw.create_nerf(args)
+    assert start2 == 1234
+    for k in ("network_fn", "network_fine", "embedding_a", "embedding_t"):
+        a, b = ktr[k].state_dict(), ktr2[k].state_dict()
+        assert list(a) == list(b) and all(torch.equal(a[n], b[n]) for n in a)
+    # the reloaded networks render the same image
+    img = [rendering.render(12, 16, 15.0, c2w=torch.tensor(C2W, device=dev()), img_idx=torch.tensor(HIST, device=dev()),
+                            near=0.0, far=2.5, **kk)[0] for kk in (kte, kte2)]
+    assert torch.equal(img[0], img[1])
+    args.no_grad_update = True
+    assert nerfw.create_nerf(args)[3:] == (None, None)
