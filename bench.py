@@ -128,59 +128,258 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_oracle_rays_per_s(n_rays, repeats=1):
-    """Reference arithmetic on the host (numpy oracle port, all BLAS threads) on a bounded
-    ray sample of the same image."""
+def _cpu_inputs(n_rays):
     from dfnet_b200 import nerfw
-    import torch
     from oracle import nerf_oracle as O
-    torch.set_num_threads(os.cpu_count())
-    O.set_linear_backend("torch")  # Linear layers through torch-CPU addmm, like the reference
     mods = nerfw.make_synthetic_nerf(D=8, W=NETW)
-    nets = dict(coarse={k: v.numpy() for k, v in mods[0].state_dict().items()},
-                fine={k: v.numpy() for k, v in mods[1].state_dict().items()},
-                emb_a=mods[2].weight.detach().numpy(), emb_t=mods[3].weight.detach().numpy(), D=8, skips=(4,))
     o, d = O.get_rays(H, W, FOCAL, pose(0))
     sel = np.linspace(0, H * W - 1, n_rays).astype(np.int64)
-    rec = O.make_ray_records(o.reshape(-1, 3)[sel], d.reshape(-1, 3)[sel], NEAR, FAR, HIST[None])
-    best = None
-    for _ in range(repeats):
+    return mods, o.reshape(-1, 3)[sel], d.reshape(-1, 3)[sel]
+
+
+class CpuReference:
+    """The reference's own CPU implementation of the path on a bounded ray sample of the same image, all host threads.
+    kind "reference": the UNMODIFIED reference (models.rendering.render from baseline/_ref, see baseline/make_ref.py);
+    kind "port": the numpy oracle port with its Linear layers on torch-CPU addmm, when baseline/_ref is absent."""
+
+    def __init__(self, n_rays):
+        import torch
+        torch.set_num_threads(os.cpu_count())
+        self.n_rays = n_rays
+        self.mods, self.o, self.d = _cpu_inputs(n_rays)
+        sys.path.insert(0, ROOT)
+        from baseline import ref_shims
+        self.kind = "reference" if ref_shims.available() else "port"
+        if self.kind == "reference":
+            from baseline import ref_runner
+            self.kw = ref_runner.reference_render_kwargs(self.mods, test_time=True, N_samples=NC, N_importance=NF)
+            self.run = lambda n: ref_runner.reference_render_rays(
+                self.kw, torch.from_numpy(self.o[:n]), torch.from_numpy(self.d[:n]), NEAR, FAR, torch.from_numpy(HIST[None]))
+            self.what = ("unmodified reference models.rendering.render (baseline/_ref), torch-CPU fp32, chunk 32768, "
+                         "netchunk 65536")
+        else:
+            from oracle import nerf_oracle as O
+            O.set_linear_backend("torch")  # Linear layers through torch-CPU addmm, like the reference
+            m = self.mods
+            self.nets = dict(coarse={k: v.numpy() for k, v in m[0].state_dict().items()},
+                             fine={k: v.numpy() for k, v in m[1].state_dict().items()},
+                             emb_a=m[2].weight.detach().numpy(), emb_t=m[3].weight.detach().numpy(), D=8, skips=(4,))
+            self.run = lambda n: O.render_rays(O.make_ray_records(self.o[:n], self.d[:n], NEAR, FAR, HIST[None]), self.nets,
+                                               NC, NF, test_time=True)
+            self.what = "oracle port of render_rays, Linear layers via torch-CPU addmm"
+
+    def time(self, n=None):
+        n = n or self.n_rays
         t0 = time.perf_counter()
-        O.render_rays(rec, nets, NC, NF, test_time=True)
+        self.run(n)
         dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return n_rays / best, best
+        return n / dt, dt
+
+    def sample(self, dt=None):
+        return (f"{self.n_rays} rays spread over the same {W}x{H} image" + (f", {dt:.1f} s" if dt else " per step") +
+                f" ({self.what}; {NC}+{NF} samples, 8x{NETW} NeRF-W, {os.cpu_count()} threads)")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_rays = args.cpu_rays
+    ref = CpuReference(args.cpu_rays)
     for _ in range(args.warmup):
-        cpu_oracle_rays_per_s(min(n_rays, 512))
+        ref.time(min(args.cpu_rays, 512))
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_oracle_rays_per_s(n_rays)
+        ref.time()
     dt = time.perf_counter() - t0
-    v = n_rays * args.steps / dt
-    cores = os.cpu_count()
+    v = args.cpu_rays * args.steps / dt
     line = {"impl": "reference", "metric": "rays/sec", "value": v, "unit": "rays/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_cfg(args), "gpu_launches": 0,
-            "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
-                             "sample": f"{n_rays} rays of the {W}x{H} image per step (oracle port of render_rays, Linear layers via "
-                                       f"torch-CPU addmm on all cores, {NC}+{NF} samples, 8x{NETW} NeRF-W)"},
+            "cpu_baseline": {"value": v, "unit": "rays/s", "cores": os.cpu_count(), "kind": ref.kind, "sample": ref.sample()},
             "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 def workload_cfg(args):
+    # identical for both arms (the driver compares the dicts): what the workload IS, not how an arm computes it
     return {"workload": f"{LABEL}, 8x{NETW} NeRF-W coarse+fine, test-time render_path step (1 image = {H * W} rays per step)",
             "H": H, "W": W, "N_samples": NC, "N_importance": NF, "netdepth": 8, "netwidth": NETW,
-            "mma": args.mma, "parallelism": f"images sharded over {args.gpus} rank(s), no collective",
+            "parallelism": f"images sharded over {args.gpus} rank(s), no collective",
             "l2": "per-chunk working set (~0.65 GB of intermediates per 65 536 rays) exceeds the 126 MB L2; no extra flush"}
+
+
+def _event_timed(fn, steps, warmup, stream, barrier):
+    """(total ms, per-step ms list) of `steps` calls after `warmup`, CUDA events on `stream`."""
+    import torch
+    for i in range(warmup):
+        fn(i)
+    barrier()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    evs[0].record(stream)
+    for i in range(steps):
+        fn(warmup + i)
+        evs[i + 1].record(stream)
+    barrier()
+    per = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
+    return evs[0].elapsed_time(evs[steps]), per
+
+
+def bench_extras(args, dev, rank, world, mma):
+    """BASELINE configs [2], [3], [4] next to the headline, each through the repo's public Python API:
+      dfnet : DFNet siamese forward on a 640x480 target/render pair + level-0 cosine feature loss (1 GPU per rank)
+      train : train_on_batch (SURVEY cfg4: 480x640 image, 120x160 render, 8x256 NeRF-W 64+128, DFNet F+G, Adam), one
+              image per rank and ONE all-reduce of the pose regressor's gradients when WORLD_SIZE > 1
+      cfg5  : one 1920x1080 image, 64+192 samples, per rank.
+    Every number is max-over-ranks device time; values are whole-job aggregates."""
+    import types
+    import torch
+    import torch.distributed as dist
+    from dfnet_b200 import _lib, nerfw, ops, parallel
+    from dfnet_b200 import direct_feature_matching as dfm
+    from dfnet_b200.dfnet import DFNet, feature_loss
+    lib = _lib.lib
+    stream = torch.cuda.current_stream()
+    pk, pk_kind = peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    out = {}
+    # ---- config[2]: DFNet pair + feature-matching loss ------------------------------------------------------------
+    torch.manual_seed(1234)
+    net = DFNet().to(dev).eval()
+    x_h = torch.rand(2, 3, 480, 640).pin_memory()
+    x = x_h.to(dev)
+
+    @torch.no_grad()
+    def dfnet_step(i):
+        feats, _ = net(x, return_feature=True, isSingleStream=False, return_pose=False, upsampleH=480, upsampleW=640)
+        return feature_loss(feats[1][0, 0], feats[0][0, 0])
+
+    @torch.no_grad()
+    def dfnet_step_e2e(i):
+        xd = x_h.to(dev, non_blocking=True)
+        feats, _ = net(xd, return_feature=True, isSingleStream=False, return_pose=False, upsampleH=480, upsampleW=640)
+        return float(feature_loss(feats[1][0, 0], feats[0][0, 0]))   # host read of the loss every step
+
+    l0 = lib.dfb_launch_count()
+    ms, _ = _event_timed(dfnet_step, 10, 3, stream, barrier)
+    launches = (lib.dfb_launch_count() - l0) / 13
+    ms = max_ranks(ms) / 10
+    ms_e2e, _ = _event_timed(dfnet_step_e2e, 10, 3, stream, barrier)
+    ms_e2e = max_ranks(ms_e2e) / 10
+    fa = torch.randn(128, 480 * 640, device=dev)
+    fb = torch.randn(128, 480 * 640, device=dev)
+    lms, _ = _event_timed(lambda i: feature_loss(fa, fb), 20, 3, stream, barrier)
+    lms /= 20
+    del fa, fb
+    conv_flop = 2 * 325.3e9          # SURVEY 8a: 325.3 GFLOP per 480x640 image, two images
+    loss_bytes = 2 * 128 * 480 * 640 * 4
+    peak_t = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
+    out["dfnet"] = {
+        "metric": "DFNet 640x480 pairs/sec (siamese forward, 3 levels upsampled + level-0 cosine loss)",
+        "value": world * 1e3 / ms, "unit": "pairs/s", "ms_per_pair": ms, "gpu_launches_per_pair": launches,
+        "e2e": {"value": world * 1e3 / ms_e2e, "unit": "pairs/s", "h2d_bytes_per_step": 2 * 3 * 480 * 640 * 4, "d2h_bytes_per_step": 4},
+        "roofline": {"bound": "tensor", "kernel": "k_conv_tc (whole forward: 13 encoder + 6 head convolutions)",
+                     "achieved": conv_flop / (ms * 1e-3) / 1e12, "peak": peak_t, "unit": "TFLOP/s",
+                     "frac": conv_flop / (ms * 1e-3) / 1e12 / peak_t, "traffic": None,
+                     "note": "algorithmic 325.3 GFLOP per image (SURVEY 8a) x 2 images / time of the whole pair step"},
+        "loss_roofline": {"bound": "hbm", "kernel": "k_cosine (dfb_cosine_loss, level 0: 2 x [128, 307200] fp32 read once)",
+                          "achieved": loss_bytes / (lms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                          "frac": loss_bytes / (lms * 1e-3) / 1e9 / pk["hbm_gbs"], "ms": lms, "traffic": None},
+        "dtype": "f16 operands / fp32 accumulate"}
+    del net, x
+    # ---- config[3]: train_on_batch, data-parallel over ranks -------------------------------------------------------
+    torch.manual_seed(0)
+    Fnet, Gnet = DFNet().to(dev), DFNet().to(dev).eval()
+    with torch.no_grad():
+        Fnet.fc_pose.weight.mul_(1e-2)
+        Fnet.fc_pose.bias.copy_(torch.tensor([1., 0, 0, 0.1, 0, 1, 0, -0.05, 0, 0, 1, 2.0]))
+    for p in Gnet.parameters():
+        p.requires_grad_(False)
+    Fnet.train()
+    for m in Fnet.modules():   # freeze_bn_layer_train (reference feature/direct_feature_matching.py:52-61, train.py:111-112)
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.eval()
+            m.weight.requires_grad_(False), m.bias.requires_grad_(False)
+    c, f, ea, et = [m.to(dev) for m in nerfw.make_synthetic_nerf(D=8, W=256, fine=True)]
+    for m in (c, f, ea, et):
+        for p in m.parameters():
+            p.requires_grad_(False)
+    kw = dict(network_query_fn=None, perturb=0.0, N_importance=128, network_fine=f, N_samples=64, network_fn=c,
+              use_viewdirs=True, white_bkgd=False, raw_noise_std=0.0, embedding_a=ea, embedding_t=et, test_time=True,
+              ndc=False, lindisp=False, near=0.0, far=2.5, mma=mma)
+    targs = types.SimpleNamespace(DFNet=True, preprocess_ImgNet=False, svd_reg=True, combine_loss=True, per_channel=False,
+                                  chunk=32768, batch_size=1, combine_loss_w=[0.0, 0.0, 1.0], feature_matching_lvl=[0])
+    opt = torch.optim.Adam([p for p in Fnet.parameters() if p.requires_grad], lr=1e-5)
+    rng = np.random.RandomState(rank)
+    data = torch.from_numpy(rng.rand(1, 3, 480, 640).astype(np.float32)).pin_memory()
+    tpose = torch.tensor([[1., 0, 0, 0.1, 0, 1, 0, -0.05, 0, 0, 1, 2.0]])
+    thist = torch.tensor(HIST[None])
+    world_setup = dict(pose_scale=0.5, pose_scale2=1.0, move_all_cam_vec=[0.0, 0.0, 0.05])
+
+    def train_step(i):
+        # host image in (pinned), host loss / PSNR out every step: this IS the end-to-end call (train.py's inner loop)
+        return dfm.train_on_batch(targs, data, Fnet, Gnet, tpose, thist, (480, 640, 585.0), opt, True, dev, world_setup, **kw)
+
+    parallel.allreduce_stats(reset=True)
+    l0 = lib.dfb_launch_count()
+    n_tr = 10
+    tot, per = _event_timed(train_step, n_tr, 4, stream, barrier)
+    launches = (lib.dfb_launch_count() - l0) / (n_tr + 4)
+    ar = parallel.allreduce_stats(reset=True)
+    ms_mean = max_ranks(tot) / n_tr
+    ms_med = max_ranks(float(np.median(per)))
+    out["train"] = {
+        "metric": "train_on_batch steps/sec (BASELINE config[3] / SURVEY cfg4: 480x640 image, 120x160 render, 8x256 NeRF-W 64+128, "
+                  "DFNet F+G, feature_matching_lvl=[0], Adam), one image per rank",
+        "value": world * 1e3 / ms_mean, "unit": "steps/s", "ms_per_step": ms_mean, "ms_median": ms_med, "steps": n_tr, "warmup": 4,
+        "gpu_launches_per_step": launches, "n_gpus": world, "scaling": "weak",
+        "allreduce": {"calls_per_step": ar["calls"] / max(n_tr + 4, 1), "bytes_per_call": ar["bytes_per_call"],
+                      "ms_per_call": ar["ms"] / max(ar["timed_calls"], 1) if ar["timed_calls"] else 0.0,
+                      "exposed_ms_per_step": ar["exposed_ms"] / max(ar["timed_calls"], 1) if ar["timed_calls"] else 0.0,
+                      "note": "ONE NCCL all-reduce of the pose regressor's flat fp32 gradient bucket per step, issued on a side "
+                              "stream as soon as the bucket is complete; ms_per_call = device time of the collective, "
+                              "exposed = time the main stream waited for it"},
+        "e2e": {"value": world * 1e3 / ms_mean, "unit": "steps/s", "h2d_bytes_per_step": 3 * 480 * 640 * 4 + 12 * 4 + 10 * 4,
+                "d2h_bytes_per_step": 8},
+        "dtype": f"render {mma} operands / fp32 accumulate; DFNet fp16 forward, bf16 gradients, fp32 weight gradients"}
+    del Fnet, Gnet, opt
+    # ---- config[4]: the 1920x1080, 64+192 image -------------------------------------------------------------------
+    Hc, Wc, fc, nearc, farc, Ncc, Nfc = WORKLOADS["cfg5"][:7]
+    h = ops.NerfHandle(c, f, ea, et)
+    c2w = torch.tensor(pose(rank * 1000), device=dev)
+    hist_d = torch.tensor(HIST, device=dev)
+
+    def cfg5_step(i):
+        return h.render(Ncc, Nfc, True, c2w=c2w, H=Hc, W=Wc, focal=fc, near=nearc, far=farc, hist=hist_d, mma=mma)
+
+    lib.dfb_profile_enable(1)
+    ms5, _ = _event_timed(cfg5_step, 3, 3, stream, barrier)
+    lib.dfb_profile_enable(0)
+    cm, fm, cl, fl = C.c_double(), C.c_double(), C.c_int64(), C.c_int64()
+    lib.dfb_profile_read(C.byref(cm), C.byref(fm), C.byref(cl), C.byref(fl))
+    ms5 = max_ranks(ms5) / 3
+    f_c, f_f = mlp_flops(256)
+    fine_tf = (Hc * Wc * 6 * (Ncc + Nfc) * f_f) / (fm.value * 1e-3) / 1e12 if fm.value > 0 else 0.0
+    out["cfg5"] = {
+        "metric": "rays/sec, BASELINE config[4] shape (1920x1080 image, 64+192 samples, 8x256 NeRF-W), one image per rank",
+        "value": world * Hc * Wc / (ms5 * 1e-3), "unit": "rays/s", "ms_per_image": ms5, "n_gpus": world, "scaling": "weak",
+        "images_per_sec": world * 1e3 / ms5,
+        "roofline": {"bound": "tensor", "kernel": "fine NeRF-W MLP", "achieved": fine_tf, "peak": peak_t, "unit": "TFLOP/s",
+                     "frac": fine_tf / peak_t, "traffic": None,
+                     "whole_step_tflops": Hc * Wc * (Ncc * f_c + (Ncc + Nfc) * f_f) / (ms5 * 1e-3) / 1e12}}
+    return out
 
 
 def main():
@@ -192,6 +391,8 @@ def main():
     ap.add_argument("--mma", default=os.environ.get("DFB_MMA", "auto"), choices=["auto", "f16", "bf16", "fp32"])
     ap.add_argument("--cpu-rays", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the BASELINE config[2]/[3]/[4] measurements (keys dfnet, train, cfg5 of the JSON line)")
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS),
                     help="cfg2 = BASELINE config[1] (the headline, default); cfg5 = BASELINE config[4] (1920x1080, 64+192); "
                          "shipped = the reference's own defaults (netwidth 128, 64+64)")
@@ -340,11 +541,17 @@ def main():
                 "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 12 * 4 + 10 * 4,
                         "d2h_bytes_per_step": N * 5 * 4, "images_per_sec": world * args.steps / (ms_e2e * 1e-3)},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
+        line["mma"] = mma
         if world == 1 and not args.no_cpu_baseline:
-            v, dt = cpu_oracle_rays_per_s(args.cpu_rays)
-            line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
-                                    "sample": f"{args.cpu_rays} rays of the same {W}x{H} image, {dt:.1f} s "
-                                              "(oracle port of render_rays; Linear layers via torch-CPU addmm, all cores)"}
+            ref = CpuReference(args.cpu_rays)
+            ref.time(256)
+            v, dt = ref.time()
+            line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": os.cpu_count(), "kind": ref.kind, "sample": ref.sample(dt)}
+    extras = {}
+    if not args.no_extras and args.workload == "cfg2":
+        extras = bench_extras(args, dev, rank, world, mma)
+    if rank == 0:
+        line.update(extras)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

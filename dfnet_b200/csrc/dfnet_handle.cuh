@@ -42,6 +42,11 @@ struct DfbDfnet {
   float* fc_w = nullptr;
   float* fc_b = nullptr;
   bool loaded = false;
+  // data-parallel training: cudaEvent_t recorded by dfb_dfnet_bwd on its stream as soon as the parameter
+  // gradients of fc_pose and of the encoder layers >= bucket_first_layer are complete (the deep, parameter-heavy
+  // layers are differentiated FIRST), so that the caller can all-reduce that bucket while the backward continues
+  void* bucket_event = nullptr;
+  int bucket_first_layer = 0;
 };
 
 static const int kEncCin[13] = {3, 64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512};

@@ -319,6 +319,8 @@ extern "C" int dfb_dfnet_bwd(DfbDfnet* d, int B, int H, int W, uint32_t flags, i
                               g_params[2 * i + 1], stream);
       if (rc) return rc;
     }
+    if (g_params && d->bucket_event && i == d->bucket_first_layer)
+      DFB_CHECK_CUDA(cudaEventRecord((cudaEvent_t)d->bucket_event, st));
     if (i == 0) {
       if (g_x) {
         int rc = dfb_conv_run(d->enc_dg[0], cur, nb, h, w, 0, nullptr, nullptr, g_x, nullptr, nullptr, stream);
@@ -353,6 +355,13 @@ extern "C" int dfb_dfnet_bwd(DfbDfnet* d, int B, int H, int W, uint32_t flags, i
       cur = out, flip ^= 1;
     }
   }
+  return DFB_OK;
+}
+
+// See DfbDfnet::bucket_event.  event = NULL switches the notification off.
+extern "C" int dfb_dfnet_bwd_bucket_event(DfbDfnet* d, int first_layer, void* event) {
+  DFB_REQUIRE(d && first_layer >= 0 && first_layer <= 12, DFB_ERR_INVALID, "dfb_dfnet_bwd_bucket_event: bad arguments");
+  d->bucket_event = event, d->bucket_first_layer = first_layer;
   return DFB_OK;
 }
 

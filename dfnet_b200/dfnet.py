@@ -52,6 +52,9 @@ class _DfnetHandle:
         self._ws = None
         self._bwd_ws = None
         self.n_levels = len(module.hypercolumn_layers)
+        self.grad_sync = None      # parallel.GradSync: set by a data-parallel training step (train_on_batch)
+        self._bucket_ev = None
+        self.last_flat_grad = self.last_grad_views = None
 
     def refresh(self, module, train=False, bn_train=False):
         # state_dict() walks and renames every tensor (~ms): cache the tensors themselves, keyed on their identity,
@@ -85,6 +88,11 @@ class _DfnetHandle:
         self._bn_loaded = bool(bn_train)
         self._versions = v
         self.n_params = len(ts)
+
+    def invalidate(self):
+        """Force a re-upload on the next forward.  Change detection compares (data_ptr, _version) of every tensor; writes
+        through `.data` do not bump `_version`, so call this after such writes."""
+        self._versions = None
 
     def forward(self, x, return_feature, single, return_pose, upH, upW, tape=False, bf16=False, bn_train=False):
         """tape=True keeps every activation in a fresh buffer (returned as 4th value) for `backward`.
@@ -177,10 +185,20 @@ class _DfnetHandle:
                 off += n
             head = range(26, 26 + 8 * self.n_levels)
             ptrs = (C.c_void_p * len(grads))(*[None if i in head else g.data_ptr() for i, g in enumerate(grads)])
-            self.last_flat_grad = flat
+            self.last_flat_grad, self.last_grad_views = flat, grads
+        sync = self.grad_sync if grads is not None and self.grad_sync is not None and self.grad_sync.world() > 1 else None
+        if sync is not None:
+            # conv4_1 (encoder layer 7) and everything deeper + fc_pose: 88 % of the bucket, complete early
+            if self._bucket_ev is None:
+                self._bucket_ev = torch.cuda.Event()
+                self._bucket_ev.record()      # creates the cudaEvent_t the library re-records
+            check(lib.dfb_dfnet_bwd_bucket_event(self._h, 7, C.c_void_p(self._bucket_ev.cuda_event)))
         check(lib.dfb_dfnet_bwd(self._h, B, H, W, flags, upH, upW, p(g_ft), p(g_fr), level_mask, p(g_pose), p(ws), p(gx_sub),
                                 ptrs, 0 if grads is None else len(grads), p(self._bwd_ws), self._bwd_ws.numel(),
                                 C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        if sync is not None:
+            check(lib.dfb_dfnet_bwd_bucket_event(self._h, 0, None))
+            sync.launch(flat, sum(sizes[:14]), self._bucket_ev)
         return g_x, grads
 
 

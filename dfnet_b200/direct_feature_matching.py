@@ -65,61 +65,77 @@ def rgb_loss(rgb, target, extras=None):
     return img2mse(rgb, target)
 
 
-def train_on_batch(args, data, model, feat_model, pose, img_idx, hwf, optimizer, half_res, device, world_setup_dict,
-                   **render_kwargs_test):
-    """One optimisation step (reference feature/direct_feature_matching.py:322-390), same arguments and return value
-    (iter_loss [1] numpy, iter_psnr numpy).  When torch.distributed is initialised with more than one rank the pose
-    regressor's gradients are averaged with a single all-reduce before the optimizer step."""
+def predict_pose(args, data, model, world_setup_dict, device):
+    """Stage 1: pose regression -> (pose_ [B,3,4] in the regressor's frame, pose_nerf in NeRF world scale).
+    Reference feature/direct_feature_matching.py:329-335."""
+    _, pose_ = inference_pose_regression(args, data, device, model, retFeature=False)
+    return pose_, fix_coord_supp(args, pose_.clone(), world_setup_dict, device=device)
+
+
+def render_prediction(args, c2w, img_idx, hwf, half_res, render_kwargs):
+    """Stage 2: the NeRF-Hist view at the predicted pose as a [1,3,H,W] image; at quarter resolution followed by the
+    x4 bicubic upsampling when half_res (reference :341-352).  Differentiable w.r.t. c2w."""
     H, W, focal = hwf
     H, W = int(H), int(W)
-    data = data.to(device)
+    s = 4 if half_res else 1
+    rgb, _, _, extras = render(H // s, W // s, focal / s, chunk=args.chunk, c2w=c2w, img_idx=img_idx, **render_kwargs)
+    rgb = rgb[None, ...].permute(0, 3, 1, 2)
+    return (upsample_bicubic(rgb, (H, W)) if half_res else rgb), extras
 
-    # pose regression module
-    _, pose_ = inference_pose_regression(args, data, device, model, retFeature=False)
-    pose_nerf = pose_.clone()
-    # rescale the predicted pose to nerf scales
-    pose_nerf = fix_coord_supp(args, pose_nerf, world_setup_dict, device=device)
-    pose = pose.to(device)
-    img_idx = img_idx.to(device)
 
-    # direct matching module
-    if half_res:
-        rgb, disp, acc, extras = render(H // 4, W // 4, focal / 4, chunk=args.chunk, c2w=pose_nerf[0, :3, :4], img_idx=img_idx,
-                                        **render_kwargs_test)
-        rgb = rgb[None, ...].permute(0, 3, 1, 2)
-        rgb = upsample_bicubic(rgb, (H, W))
-    else:
-        rgb, disp, acc, extras = render(H, W, focal, chunk=args.chunk, c2w=pose_nerf[0, :3, :4], img_idx=img_idx,
-                                        **render_kwargs_test)
-        rgb = rgb[None, ...].permute(0, 3, 1, 2)
-
-    # feature metric module
+def matching_terms(args, data, rgb, feat_model, device):
+    """Stage 3: photometric MSE and the cosine feature-metric loss between the target image and the rendered view
+    through the frozen feature net (reference :354-370).  Only the rendered stream carries gradient."""
     feat_model.grad_levels = list(args.feature_matching_lvl)  # levels whose gradient is non-zero after index_select
-    feature_list, _ = inference_pose_regression(args, torch.cat([data, rgb]), device, feat_model, retFeature=True,
-                                                isSingleStream=False, return_pose=False)
-    feature_target, feature_rgb = feature_list[0], feature_list[1]
+    (feature_target, feature_rgb), _ = inference_pose_regression(args, torch.cat([data, rgb]), device, feat_model, retFeature=True,
+                                                                 isSingleStream=False, return_pose=False)
+    lv = torch.tensor(args.feature_matching_lvl, device=feature_rgb.device)
+    f_rgb = preprocess_features_for_loss(torch.index_select(feature_rgb, 0, lv))
+    f_tgt = preprocess_features_for_loss(torch.index_select(feature_target, 0, lv))
+    return rgb_loss(rgb, data), feature_loss(f_rgb[0], f_tgt[0], per_channel=args.per_channel)
 
-    photo_loss = rgb_loss(rgb, data, extras)
-    indices = torch.tensor(args.feature_matching_lvl, device=feature_rgb.device)
-    feature_rgb = torch.index_select(feature_rgb, 0, indices)
-    feature_target = torch.index_select(feature_target, 0, indices)
-    feature_rgb = preprocess_features_for_loss(feature_rgb)
-    feature_target = preprocess_features_for_loss(feature_target)
-    feat_loss = feature_loss(feature_rgb[0], feature_target[0], per_channel=args.per_channel)
 
+def apply_gradients(model, optimizer):
+    """Stage 4: optimizer step on the pose regressor.  Data parallel (torch.distributed initialised, world > 1): the
+    gradients were averaged by the GradSync attached to the regressor's handle WHILE its backward ran (dfnet.py); here
+    the compute stream only waits for the collective and the parameters' .grad are pointed at the averaged flat bucket.
+    Modules without such a handle fall back to parallel.allreduce_gradients_."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        h = getattr(model, "_handle", None)
+        sync = getattr(h, "grad_sync", None)
+        if sync is not None and h.last_grad_views is not None:
+            sync.finish()
+            for p, g in zip(model._load_order_params(), h.last_grad_views):
+                if p.grad is not None:
+                    p.grad = g
+            h.last_grad_views = None
+        else:
+            parallel.allreduce_gradients_(model.parameters())
+    optimizer.step()
+    optimizer.zero_grad()
+
+
+def train_on_batch(args, data, model, feat_model, pose, img_idx, hwf, optimizer, half_res, device, world_setup_dict,
+                   **render_kwargs_test):
+    """One optimisation step with the reference's signature and return value (feature/direct_feature_matching.py:322-390:
+    iter_loss [1] numpy, iter_psnr numpy), composed of the four stages above.  Differences in mechanism, not in
+    arithmetic: every stage runs on the sm_100a kernels with hand-written backward passes; under torch.distributed the
+    pose regressor's gradients are averaged with ONE bucketed all-reduce overlapped with its backward; loss
+    and PSNR come back in a single device-to-host copy."""
     if not args.combine_loss:
         raise ValueError("train_on_batch needs --combine_loss (the reference leaves `loss` undefined without it, "
                          "feature/direct_feature_matching.py:373-378)")
-    pose_loss = PoseLoss(args, pose_, pose, device)
-    loss = args.combine_loss_w[0] * pose_loss + args.combine_loss_w[1] * photo_loss + args.combine_loss_w[2] * feat_loss
-
+    data, pose, img_idx = data.to(device), pose.to(device), img_idx.to(device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and getattr(model, "_handle", None) is not None \
+            and model._handle.grad_sync is None:
+        model._handle.grad_sync = parallel.GradSync()
+    pose_, pose_nerf = predict_pose(args, data, model, world_setup_dict, device)
+    rgb, _ = render_prediction(args, pose_nerf[0, :3, :4], img_idx, hwf, half_res, render_kwargs_test)
+    photo_loss, feat_loss = matching_terms(args, data, rgb, feat_model, device)
+    w = args.combine_loss_w
+    loss = w[0] * PoseLoss(args, pose_, pose, device) + w[1] * photo_loss + w[2] * feat_loss
     loss.backward()
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        parallel.allreduce_gradients_(model.parameters())
-    optimizer.step()
-    optimizer.zero_grad()
-    psnr = mse2psnr(img2mse(rgb.detach(), data))
-
-    iter_loss = np.array([loss.detach().cpu().numpy()])
-    iter_psnr = psnr.detach().cpu().numpy()
-    return iter_loss, iter_psnr
+    apply_gradients(model, optimizer)
+    with torch.no_grad():
+        host = torch.stack([loss.detach().reshape(()), mse2psnr(img2mse(rgb.detach(), data)).reshape(())]).cpu().numpy()
+    return np.array([host[0]]), host[1]

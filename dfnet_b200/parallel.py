@@ -66,3 +66,89 @@ def allreduce_gradients_(params, group=None):
         g.copy_(flat[off:off + n].view_as(g))
         off += n
     return flat.numel()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Gradient all-reduce as the tail of the pose regressor's backward
+# ---------------------------------------------------------------------------------------------------------------------
+_STATS = {"calls": 0, "bytes": 0, "ms": 0.0, "exposed_ms": 0.0, "timed_calls": 0, "pending": []}
+
+
+def allreduce_stats(reset=False):
+    """Accumulated all-reduce measurements of GradSync (bench.py): device time of the collectives and the time the
+    compute stream actually waited for them, from CUDA events (resolved lazily here, never inside a step)."""
+    for ev in _STATS["pending"]:
+        a0, a1, w0, w1 = ev
+        a1.synchronize(), w1.synchronize()
+        _STATS["ms"] += a0.elapsed_time(a1)
+        _STATS["exposed_ms"] += w0.elapsed_time(w1)
+        _STATS["timed_calls"] += 1
+    _STATS["pending"] = []
+    out = {k: v for k, v in _STATS.items() if k != "pending"}
+    out["bytes_per_call"] = _STATS["bytes"] / max(_STATS["calls"], 1)
+    if reset:
+        _STATS.update(calls=0, bytes=0, ms=0.0, exposed_ms=0.0, timed_calls=0)
+    return out
+
+
+class GradSync:
+    """Averages ONE flat fp32 gradient bucket over the ranks while the backward that fills it is still running.
+
+    dfb_dfnet_bwd writes every parameter gradient of the pose regressor into one flat buffer and records an event when
+    the tail of that buffer (fc_pose and the deep, parameter-heavy encoder layers, differentiated first) is complete.
+    `launch` enqueues the collective for that tail on a side stream behind the event and the collective for the head
+    behind the end of the backward; `finish` makes the compute stream wait for both.  The result is the average in
+    place, so the optimizer reads it without another copy.  Counted as one logical all-reduce of the bucket per step
+    (two NCCL launches).  CPU tensors (gloo tests) take the same path without streams."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.side = None
+        self._pending = None
+
+    def world(self):
+        return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+
+    def launch(self, flat, split, tail_ready=None):
+        """flat: the bucket; flat[split:] is complete when `tail_ready` (torch.cuda.Event) fires, flat[:split] when the
+        work enqueued so far on the current stream is done."""
+        w = self.world()
+        if w == 1:
+            return
+        _STATS["calls"] += 1
+        _STATS["bytes"] += flat.numel() * 4
+        if not flat.is_cuda:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            flat /= w
+            return
+        main = torch.cuda.current_stream(flat.device)
+        if self.side is None:
+            self.side = torch.cuda.Stream(flat.device)
+        done_all = torch.cuda.Event()
+        done_all.record(main)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(tail_ready if tail_ready is not None else done_all)
+            a0.record(self.side)
+            if split < flat.numel():
+                dist.all_reduce(flat[split:], op=dist.ReduceOp.AVG, group=self.group)
+            self.side.wait_event(done_all)
+            if split > 0:
+                dist.all_reduce(flat[:split], op=dist.ReduceOp.AVG, group=self.group)
+            a1.record(self.side)
+        self._pending = (a0, a1, flat)
+
+    def finish(self):
+        """The current stream waits for the collectives launched by `launch`."""
+        if self._pending is None:
+            return
+        a0, a1, flat = self._pending
+        self._pending = None
+        main = torch.cuda.current_stream(flat.device)
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record(main)
+        main.wait_stream(self.side)
+        w1.record(main)
+        flat.record_stream(self.side)
+        if len(_STATS["pending"]) < 64:
+            _STATS["pending"].append((a0, a1, w0, w1))

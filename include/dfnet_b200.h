@@ -323,6 +323,13 @@ int dfb_dfnet_bwd(DfbDfnet* d, int B, int H, int W, uint32_t flags, int upH, int
                   const float* g_feats_r, uint32_t level_mask, const float* g_pose, const void* tape, float* g_x,
                   float* const* g_params, int n_params, void* scratch, size_t scratch_bytes, void* stream);
 
+/* Data-parallel training ("one NCCL allreduce ... overlapped as the tail of F's backward"): from now on
+ * dfb_dfnet_bwd records `event` (a cudaEvent_t) on its stream as soon as the gradients of fc_pose and of the encoder
+ * layers >= first_layer (0..12, VGG order) are complete.  The backward walks the encoder from conv5_3 down to conv1_1,
+ * so with first_layer = 7 (conv4_1) 88 % of the gradient bytes are ready while 90 % of the backward's work is still to
+ * run; the caller all-reduces g_params[2*first_layer ..] on another stream behind this event.  NULL switches it off. */
+int dfb_dfnet_bwd_bucket_event(DfbDfnet* d, int first_layer, void* event);
+
 /* Backward of dfb_cosine_loss w.r.t. fr (g_loss: device scalar), of dfb_mse w.r.t. a, and the adjoints of the two
  * resampling operators (outputs overwritten). */
 int dfb_cosine_loss_bwd(const float* fr, const float* ft, int C, int64_t HW, int per_channel, float eps, const float* g_loss,

@@ -101,3 +101,38 @@ def test_gradient_allreduce_gloo_world2():
         assert grads[3] is None
         for i, g in enumerate(grads[:3]):
             assert torch.allclose(g, torch.full_like(g, 1.5 * (i + 1)))  # mean of (1, 2) * (i + 1)
+
+
+def _sync_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dfnet_b200 import parallel
+    parallel.allreduce_stats(reset=True)
+    sync = parallel.GradSync()
+    flat = torch.arange(10, dtype=torch.float32) * (rank + 1)
+    views = [flat[:4].view(2, 2), flat[4:]]
+    sync.launch(flat, 4)     # two buckets: head [0,4), tail [4,10)
+    sync.finish()
+    st = parallel.allreduce_stats()
+    q.put((rank, flat.clone(), views[0].clone(), st["calls"], st["bytes_per_call"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_grad_sync_flat_bucket_gloo_world2():
+    """GradSync (the bucketed all-reduce train_on_batch overlaps with the pose regressor's backward) averages the flat
+    bucket in place on every rank, so parameter views into it see the averaged values."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_sync_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=120) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+    assert all(p.exitcode == 0 for p in ps)
+    want = torch.arange(10, dtype=torch.float32) * 1.5
+    for rank, flat, v0, calls, nbytes in res:
+        assert torch.equal(flat, want) and torch.equal(v0, want[:4].view(2, 2))
+        assert calls == 1 and nbytes == 40

@@ -275,8 +275,8 @@ class _Recorder:
         self.model.zero_grad()
 
 
-@pytest.mark.parametrize("case", ["lvl0", "lvl012"])
-def test_train_on_batch_vs_reference_golden(case):
+@pytest.mark.parametrize("case,mma", [("lvl0", "fp32"), ("lvl012", "fp32"), ("lvl0", "f16"), ("lvl012", "f16")])
+def test_train_on_batch_vs_reference_golden(case, mma):
     """One full step (pose regressor -> SVD -> render at H//4 -> bicubic x4 -> feature net -> losses -> backward) against
     the gradients the reference's own train_on_batch produced on the CPU in fp32 (tests/golden/make_golden_train.py).
     Loss / PSNR: 1e-3.  Gradients: the GPU step evaluates the networks with fp16 storage, so ReLU masks and max-pool
@@ -307,8 +307,8 @@ def test_train_on_batch_vs_reference_golden(case):
             p.requires_grad_(False)
     kw = dict(network_query_fn=None, perturb=0.0, N_importance=cfg["Nf"], network_fine=f, N_samples=cfg["Nc"], network_fn=c,
               use_viewdirs=True, white_bkgd=False, raw_noise_std=0.0, embedding_a=ea, embedding_t=et, test_time=True,
-              ndc=False, lindisp=False, near=cfg["near"], far=cfg["far"], mma="fp32")
-    rec = _Recorder(Fnet)
+              ndc=False, lindisp=False, near=cfg["near"], far=cfg["far"], mma=mma)   # f16: the product default (tcgen05
+    rec = _Recorder(Fnet)                                                              # forward with saved masks + dfb_render_bwd_saved)
     loss, psnr = dfm.train_on_batch(cfg["args"], cfg["data"], Fnet, Gnet, cfg["pose"], cfg["hist"], cfg["hwf"], rec, True, dev(),
                                     cfg["world"], **kw)
     want_loss, want_psnr = float(g[f"{case}_loss"].reshape(-1)[0]), float(g[f"{case}_psnr"].reshape(-1)[0])
@@ -325,5 +325,5 @@ def test_train_on_batch_vs_reference_golden(case):
         nr = abs(float(gg.norm()) / float(g[f"{case}_g_{n}_stats"][0]) - 1.0)
         worst_cos = min(worst_cos, (cos, n))
         worst_norm = max(worst_norm, (nr, n))
-    print(case, "loss", float(loss.reshape(-1)[0]), want_loss, "worst cos", worst_cos, "worst norm dev", worst_norm)
+    print(case, mma, "loss", float(loss.reshape(-1)[0]), want_loss, "worst cos", worst_cos, "worst norm dev", worst_norm)
     assert worst_cos[0] > 0.95 and worst_norm[0] < 0.10, (worst_cos, worst_norm)
