@@ -388,7 +388,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mma", default=os.environ.get("DFB_MMA", "auto"), choices=["auto", "f16", "bf16", "fp32"])
+    ap.add_argument("--mma", default=os.environ.get("DFB_MMA", "auto"), choices=["auto", "f16", "f16s", "bf16", "fp32"])
     ap.add_argument("--cpu-rays", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true",
@@ -536,7 +536,7 @@ def main():
                         "MLP launches; fine_executed_tflops counts the layers actually issued"}
         line = {"metric": "rays/sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": {"f16": "f16", "bf16": "bf16", "fp32": "f32"}[mma], "data": "synthetic",
+                "vs_baseline": None, "dtype": {"f16": "f16", "f16s": "f16", "bf16": "bf16", "fp32": "f32"}[mma], "data": "synthetic",
                 "config": workload_cfg(args), "images_per_sec": world * args.steps / (ms * 1e-3),
                 "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 12 * 4 + 10 * 4,
                         "d2h_bytes_per_step": N * 5 * 4, "images_per_sec": world * args.steps / (ms_e2e * 1e-3)},

@@ -22,8 +22,9 @@ SYMBOLS = [
     "dfb_resize_bilinear_ac_bwd", "dfb_dfnet_bwd_bucket_event",
 ]
 
-MMA_FP32_SIMT, MMA_F16, MMA_BF16 = 0, 1, 2
-MMA_KINDS = {"fp32": MMA_FP32_SIMT, "f16": MMA_F16, "bf16": MMA_BF16}
+MMA_FP32_SIMT, MMA_F16, MMA_BF16, MMA_F16_SPLIT_COARSE = 0, 1, 2, 3
+# "f16s": fp16 tensor-core path with the split-precision (hi + lo operands) coarse pass, see include/dfnet_b200.h
+MMA_KINDS = {"fp32": MMA_FP32_SIMT, "f16": MMA_F16, "bf16": MMA_BF16, "f16s": MMA_F16_SPLIT_COARSE}
 
 
 class NerfDesc(C.Structure):

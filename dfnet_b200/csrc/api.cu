@@ -11,6 +11,9 @@ namespace {
 
 constexpr int64_t kChunkRays = 1 << 16;  // internal batchify (bounds the workspace, not a tuning knob of the ABI)
 
+// operand kind of everything but the coarse sigma-only pass
+int eff_kind(int k) { return k == DFB_MMA_F16_SPLIT_COARSE ? DFB_MMA_F16 : k; }
+
 struct WsLayout {
   size_t rayrec, extra, z_c, raw_c, rb_c, w_c, z_s, z_all, raw_f, rb_f, lin, total;
 };
@@ -49,7 +52,7 @@ int check_cfg(const DfbNerf* n, const DfbRenderCfg* c) {
   DFB_REQUIRE(c->N_importance == 0 || n->desc.has_fine, DFB_ERR_INVALID, "N_importance > 0 needs network_fine");
   DFB_REQUIRE(n->net[0].loaded && (c->N_importance == 0 || n->net[1].loaded), DFB_ERR_INVALID, "parameters not loaded");
   DFB_REQUIRE(c->N_importance == 0 || n->has_emb, DFB_ERR_INVALID, "embedding_a / embedding_t not set");
-  DFB_REQUIRE(c->mma_kind >= 0 && c->mma_kind <= 2, DFB_ERR_INVALID, "unknown mma_kind %d", c->mma_kind);
+  DFB_REQUIRE(c->mma_kind >= 0 && c->mma_kind <= 3, DFB_ERR_INVALID, "unknown mma_kind %d", c->mma_kind);
   return DFB_OK;
 }
 
@@ -63,7 +66,8 @@ int run_mlp_inner(const DfbNerf* n, const DfbRenderCfg* c, int which, int mode, 
   // The tcgen05 kernel covers the 8x256 networks (sigma-only coarse pass and full fine pass); every
   // other shape or mode (other widths, the train-mode coarse pass) runs on the fp32 CUDA kernel.
   if (c->mma_kind != DFB_MMA_FP32_SIMT && tc_supported(n, which, mode))
-    return launch_mlp_tc_rays(n, which, mode, c->mma_kind, rayrec, z, rb, rays, S, raw, st, masks);
+    return launch_mlp_tc_rays(n, which, mode, eff_kind(c->mma_kind), rayrec, z, rb, rays, S, raw, st, masks,
+                              c->mma_kind == DFB_MMA_F16_SPLIT_COARSE && which == 0 && mode == MLP_SIGMA);
   DFB_REQUIRE(!masks, DFB_ERR_UNSUPPORTED, "relu_masks are an output of the tcgen05 path (8x256 fine network, mma f16 / bf16)");
   return launch_mlp_simt_rays(n, which, mode, rayrec, z, rb, rays, S, raw, st);
 }
@@ -212,7 +216,7 @@ extern "C" int dfb_render_fwd(DfbNerf* n, const DfbRenderCfg* c, const float* ra
     // tcgen05 path: the per-ray bias carries the step's constant bias and is stored as packed 16-bit pairs
     const bool tc_f = c->mma_kind != DFB_MMA_FP32_SIMT && tc_supported(n, 1, MLP_FULL);
     rc = launch_raybias(pa.extra, pa.n_extra, nr, n->net[1], true, rb_f, tc_f ? 256 : n->net[1].n_dt, st,
-                        tc_f ? n->net[1].tc_dtbias_dev : nullptr, tc_f ? (c->mma_kind == DFB_MMA_F16 ? 1 : 2) : 0,
+                        tc_f ? n->net[1].tc_dtbias_dev : nullptr, tc_f ? (eff_kind(c->mma_kind) == DFB_MMA_F16 ? 1 : 2) : 0,
                         tc_f ? 128 : 0);
     if (rc) return rc;
     float* raw_f = ex && ex->raw ? ex->raw + r0 * S * 9 : P(L.raw_f);
@@ -437,6 +441,7 @@ extern "C" int dfb_render_bwd_saved(DfbNerf* n, int mma_kind, const float* rays,
                                     float* g_rays_d, float* g_viewdirs, void* ws, size_t ws_bytes, void* stream) {
   DFB_REQUIRE(!relu_masks || (mma_kind != DFB_MMA_FP32_SIMT && n && tc_bwd_supported(n)), DFB_ERR_UNSUPPORTED,
               "saved ReLU masks need the tcgen05 backward (8x256 fine network, mma f16 / bf16)");
+  mma_kind = eff_kind(mma_kind);
   DFB_REQUIRE(mma_kind == DFB_MMA_FP32_SIMT || mma_kind == DFB_MMA_F16 || mma_kind == DFB_MMA_BF16, DFB_ERR_INVALID, "bad mma kind");
   DFB_REQUIRE(n && rays && z_vals && raw && g_rgb && g_rays_o && g_rays_d && g_viewdirs, DFB_ERR_INVALID, "null argument");
   DFB_REQUIRE(n->desc.has_fine && n->net[1].loaded && n->has_emb, DFB_ERR_INVALID, "fine network / embeddings not loaded");

@@ -87,6 +87,11 @@ struct NetPack {
   size_t blob16_bytes = 0;
   std::vector<float> tc_tbl;  // host copy of the bias / head-weight table passed as kernel parameter
   float* tc_dtbias_dev = nullptr;  // [W] constant bias of the dir|transient.0 step (W_dt b_final when folded), added by k_raybias
+  // split-precision coarse pass (DFB_MMA_F16_SPLIT_COARSE): [hi image | lo image] of the sigma-only program in the
+  // cta_group::2 chunking (lo = rn16(w - rn16(w))), and the fp32 biases [step][256] in global memory
+  void* blob16x3 = nullptr;
+  size_t blob16x3_bytes = 0;
+  float* tc_bias32_dev = nullptr;
 
   // ---- tcgen05 backward layout (fine 8x256 network): the 26-step image of mlp_tc_bwd.cu ------
   void* blob16b[2] = {nullptr, nullptr};  // [fp16|bf16]
@@ -124,9 +129,10 @@ int launch_mlp_simt_embedded(const DfbNerf* nerf, int which, int mode, const flo
                              cudaStream_t st);
 // tcgen05 MLP (W == 256).  kind: DFB_MMA_F16 / DFB_MMA_BF16.
 // masks (nullable, fine network only): ReLU masks for the tcgen05 backward, see TcArgs::masks in mlp_tc.cu
+// split3: the split-precision variant of the sigma-only pass (three MMA sub-steps per layer on hi/lo fp16 operands)
 int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const float* rayrec, const float* z,
                        const float* raybias, int64_t n_rays, int S, float* raw, cudaStream_t st,
-                       uint32_t* masks = nullptr);
+                       uint32_t* masks = nullptr, bool split3 = false);
 bool tc_supported(const DfbNerf* nerf, int which, int mode);
 // Networks narrower than 256 run on the 256-wide tcgen05 kernels EXACTLY, embedded with zero weights / zero biases
 // (a ReLU unit with zero input weights and bias stays at 0 and feeds nothing): tc_pad_params returns the state dict

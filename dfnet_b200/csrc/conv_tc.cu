@@ -396,15 +396,27 @@ int dfb_conv_update_impl(DfbConv* c, const float* weight, const float* bias, con
   DFB_REQUIRE(c && weight, DFB_ERR_INVALID, "dfb_conv_update: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t wn = (size_t)c->Cout0 * c->Cin0 * c->KH * c->KW;
-  // stage host tensors on the device (cudaMemcpyDefault accepts either side)
+  // Device-resident sources (a training loop re-loads the parameters after every optimizer step) are packed in place;
+  // only host tensors are staged.  (Staging everything through cudaMallocAsync cost ~60 pool allocations per step, and
+  // the pool hands its memory back to the driver at synchronisation points: sporadic 30-500 ms stalls.)
+  auto on_device = [](const void* p) {
+    if (!p) return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+  };
   float* stage = nullptr;
-  const size_t need = (wn + 3 * (size_t)c->Cout0) * 4;
-  DFB_CHECK_CUDA(cudaMallocAsync((void**)&stage, need, st));
-  float* dw = stage, *db = stage + wn, *dsc = db + c->Cout0, *dsh = dsc + c->Cout0;
-  DFB_CHECK_CUDA(cudaMemcpyAsync(dw, weight, wn * 4, cudaMemcpyDefault, st));
-  if (bias) DFB_CHECK_CUDA(cudaMemcpyAsync(db, bias, c->Cout0 * 4, cudaMemcpyDefault, st));
-  if (bn_scale) DFB_CHECK_CUDA(cudaMemcpyAsync(dsc, bn_scale, c->Cout0 * 4, cudaMemcpyDefault, st));
-  if (bn_shift) DFB_CHECK_CUDA(cudaMemcpyAsync(dsh, bn_shift, c->Cout0 * 4, cudaMemcpyDefault, st));
+  const float *dw = weight, *db = bias, *dsc = bn_scale, *dsh = bn_shift;
+  if (!(on_device(weight) && on_device(bias) && on_device(bn_scale) && on_device(bn_shift))) {
+    const size_t need = (wn + 3 * (size_t)c->Cout0) * 4;
+    DFB_CHECK_CUDA(cudaMallocAsync((void**)&stage, need, st));
+    float* sb = stage + wn, *ssc = sb + c->Cout0, *ssh = ssc + c->Cout0;
+    DFB_CHECK_CUDA(cudaMemcpyAsync(stage, weight, wn * 4, cudaMemcpyDefault, st));
+    if (bias) DFB_CHECK_CUDA(cudaMemcpyAsync(sb, bias, c->Cout0 * 4, cudaMemcpyDefault, st));
+    if (bn_scale) DFB_CHECK_CUDA(cudaMemcpyAsync(ssc, bn_scale, c->Cout0 * 4, cudaMemcpyDefault, st));
+    if (bn_shift) DFB_CHECK_CUDA(cudaMemcpyAsync(ssh, bn_shift, c->Cout0 * 4, cudaMemcpyDefault, st));
+    dw = stage, db = sb, dsc = ssc, dsh = ssh;
+  }
   conv::PackArgs a = {};
   a.w = dw, a.b = bias ? db : nullptr, a.sc = bn_scale ? dsc : nullptr, a.sh = bn_shift ? dsh : nullptr;
   a.img = (uint16_t*)c->wimg, a.bias = c->bias;
@@ -413,7 +425,7 @@ int dfb_conv_update_impl(DfbConv* c, const float* weight, const float* bias, con
   a.total = (int64_t)c->wimg_bytes / 2;
   conv::k_pack_conv_weights<<<(unsigned)((a.total + 255) / 256), 256, 0, st>>>(a);
   DFB_LAUNCH_CHECK();
-  DFB_CHECK_CUDA(cudaFreeAsync(stage, st));
+  if (stage) DFB_CHECK_CUDA(cudaFreeAsync(stage, st));
   return DFB_OK;
 }
 

@@ -31,6 +31,7 @@ struct DfbDfnet {
   DfbConv* enc_dg[13] = {};
   DfbConv* head1_dg[3] = {};
   DfbConv* head5_dg[3] = {};
+  float* bn_stage = nullptr;  // [3][4][128] staging of the BatchNorm vectors handed to dfb_dfnet_load
   float* bn_sc = nullptr;  // [3][128] eval-mode BatchNorm scale / shift of the heads (device)
   float* bn_sh = nullptr;
   // train-mode BatchNorm of the heads (run_feature.py without freezeBN: batch statistics over the whole call's batch)

@@ -248,6 +248,7 @@ extern "C" void dfb_dfnet_destroy(DfbDfnet* d) {
   if (d->bn_part) cudaFree(d->bn_part);
   if (d->bn_sc) cudaFree(d->bn_sc);
   if (d->bn_sh) cudaFree(d->bn_sh);
+  if (d->bn_stage) cudaFree(d->bn_stage);
   if (d->fc_w) cudaFree(d->fc_w);
   if (d->fc_b) cudaFree(d->fc_b);
   delete d;
@@ -344,13 +345,13 @@ extern "C" int dfb_dfnet_load_ex(DfbDfnet* d, const float* const* params, const 
     DFB_REQUIRE(ne[0] == 64 * kTapCh[l] && ne[1] == 64 && ne[2] == 128 * 64 * 25 && ne[3] == 128 && ne[4] == 128 &&
                     ne[5] == 128 && ne[6] == 128 && ne[7] == 128,
                 DFB_ERR_INVALID, "adaptation layer %d has the wrong size", l);
-    float* bn = nullptr;  // the four BatchNorm vectors may live on the host: stage them
-    DFB_CHECK_CUDA(cudaMallocAsync((void**)&bn, 4 * 128 * 4, nullptr));
+    // the four BatchNorm vectors may live on the host: stage them (persistent staging buffer, see dfb_conv_update_impl)
+    if (!d->bn_stage) DFB_CHECK_CUDA(cudaMalloc(&d->bn_stage, 3 * 4 * 128 * 4));
+    float* bn = d->bn_stage + (size_t)l * 4 * 128;
     for (int k = 0; k < 4; ++k) DFB_CHECK_CUDA(cudaMemcpyAsync(bn + 128 * k, p[4 + k], 512, cudaMemcpyDefault, nullptr));
     float* sc = d->bn_sc + 128 * l, *sh = d->bn_sh + 128 * l;
     k_bn_fold<<<1, 128>>>(bn, bn + 128, bn + 256, bn + 384, bn_eps, sc, sh);
     DFB_LAUNCH_CHECK();
-    DFB_CHECK_CUDA(cudaFreeAsync(bn, nullptr));
     int rc = conv_set(&d->head1[l], kTapCh[l], 64, 1, p[0], p[1], nullptr, nullptr, 0, 0);
     if (rc) return rc;
     rc = conv_set(&d->head5[l], 64, 128, 5, p[2], p[3], sc, sh, 0, 0);

@@ -51,7 +51,8 @@ constexpr int kSmemW = kStages * kChunkBytes;
 constexpr int kSmemBar = 256;
 constexpr int kSmemTotal = kSmemA + kSmemW + kSmemBar;  // 229632 B
 constexpr int kThreads = 448;
-constexpr int kMaxSteps = 16;
+constexpr int kMaxSteps = 16;   // epilogue steps (layers) of a program
+constexpr int kMaxSub = 32;     // MMA sub-steps: the split-precision coarse pass runs three per layer
 constexpr int kTblScal = kMaxSteps * 256;
 constexpr int kTblFloats = kTblScal + 16;
 
@@ -76,11 +77,17 @@ struct TcArgs {
   // cta_group::2 only: 3-D tensor map over the weight image ([images][64 rows][256 B]); 2-SM TMA loads let
   // BOTH CTAs' halves of a stage complete on the LEADER's mbarrier (no relay hop)
   alignas(64) CUtensorMap tmap;
-  Step steps[kMaxSteps];
+  // MMA program: n_steps sub-steps.  A layer is one sub-step (first = last = 1) or, in the split-precision coarse
+  // pass (X3), three that accumulate into the same TMEM columns: A_hi W_hi (first), A_lo W_hi, A_hi W_lo (last).
+  // `first`: wait for the layer's A operand, start a fresh accumulator; `last`: publish the accumulator (D_FULL).
+  Step steps[kMaxSub];
+  uint8_t first[kMaxSub], last[kMaxSub];
   int n_steps;
-  int kind[kMaxSteps];    // EpiKind of every step (EPI_DT = head + store halves)
-  int last_pe_step;       // last step that reads the PE panels (skip layer)
+  int n_epi;              // epilogue steps (= layers)
+  int kind[kMaxSteps];    // EpiKind of every epilogue step (EPI_DT = head + store halves)
+  int last_pe_step;       // last SUB-step that reads the PE panels (skip layer)
   const void* wimg;       // packed 16-bit weight image, chunk i at wimg + i*16 KB
+  const float* bias32;    // X3 only: fp32 biases in global memory, [epilogue step][256]
   const float* rayrec;    // [n_rays,12]
   const float* z;         // [n_rays,S]
   const float* raybias;   // [n_rays,256] (fine) or null
@@ -215,6 +222,50 @@ __device__ __forceinline__ void epi_blocks(uint32_t t_row, uint32_t h_row, const
   }
 }
 
+// Split-precision (X3) hidden layer: bias + ReLU in fp32, then the activation is stored as TWO fp16 operands,
+// hi = rn16(x) in the slot's panels and lo = rn16(x - hi) in the same panel of the "lo" region (kSlotBytes further):
+// hi + lo carries 22 mantissa bits, and the next layer accumulates A_hi W_hi + A_lo W_hi + A_hi W_lo in fp32.
+__device__ __forceinline__ void epi_block_x3(const uint32_t (&v)[32], const float* __restrict__ bias, int cb, uint32_t h_row) {
+  uint32_t hi[16], lo[16];
+  const float4* b4 = reinterpret_cast<const float4*>(bias + cb * 32);
+#pragma unroll
+  for (int q4 = 0; q4 < 8; ++q4) {
+    const float4 bb = __ldg(b4 + q4);
+    const float bw[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int q = 2 * q4 + e;
+      const float x0 = fmaxf(__uint_as_float(v[2 * q]) + bw[2 * e], 0.f);
+      const float x1 = fmaxf(__uint_as_float(v[2 * q + 1]) + bw[2 * e + 1], 0.f);
+      const __half2 h = __floats2half2_rn(x0, x1);
+      const float2 hf = __half22float2(h);
+      const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+      hi[q] = *reinterpret_cast<const uint32_t*>(&h);
+      lo[q] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+  }
+  const uint32_t dst = h_row + (uint32_t)(cb * 4) * kPanelBytes;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    st_shared_v4(dst + q * kPanelBytes, hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+    st_shared_v4(dst + kSlotBytes + q * kPanelBytes, lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+  }
+}
+
+__device__ __forceinline__ void epi_blocks_x3(uint32_t t_row, uint32_t h_row, const float* bias, int cb0, int cb1) {
+  uint32_t v0[32], v1[32];
+  tmem_ld32(t_row + cb0 * 32, v0);
+#pragma unroll 1
+  for (int cb = cb0; cb < cb1; cb += 2) {
+    tmem_ld_wait(v0);
+    tmem_ld32(t_row + (cb + 1) * 32, v1);
+    epi_block_x3(v0, bias, cb, h_row);
+    tmem_ld_wait(v1);
+    if (cb + 2 < cb1) tmem_ld32(t_row + (cb + 2) * 32, v0);
+    epi_block_x3(v1, bias, cb + 1, h_row);
+  }
+}
+
 // MMA issue for one (step, slot): KS K=16 MMAs per weight stage.  Kept as lean as possible:
 // this single warp paces the tensor pipe.
 // 2-SM TMA load of one 16 KB weight image (box [1][64][128 x 16-bit]) into this CTA's shared memory;
@@ -229,10 +280,10 @@ __device__ __forceinline__ void tma_load_img_2sm(uint32_t dst, const CUtensorMap
 template <int CG, int KS>
 __device__ __forceinline__ void issue_step(uint32_t& stage, uint32_t& phase, int nch, uint32_t a_lo, uint32_t b_rows,
                                            uint32_t d_tmem, uint32_t idesc, uint32_t sW, uint32_t sBar, int* err,
-                                           unsigned long long* prof_acc) {
+                                           unsigned long long* prof_acc, uint32_t acc = 0) {
+  // acc = 1: the sub-step continues the accumulator of the previous one (split-precision coarse pass)
   const uint32_t desc_hi = (128u >> 4) | (1u << 14);  // SBO 128 B, descriptor version 1, no swizzle
   const uint32_t b_step = 2u * b_rows;                // (2 panels * b_rows * 16 B) >> 4
-  uint32_t acc = 0;
   if (CG == 1) {
     // Stages are filled and waited for in PAIRS (one "full" barrier per two 16 KB stages, see the
     // producer) but released one by one: half the mbarrier waits / elect blocks per MMA.
@@ -288,8 +339,15 @@ __device__ __forceinline__ void issue_step(uint32_t& stage, uint32_t& phase, int
 // both CTAs; epilogue / encoder threads of the peer arrive remotely on the leader's barriers
 // (mapa + mbarrier.arrive.release.cluster); weight stages are filled by 2-SM TMA loads
 // (cp.async.bulk.tensor...cta_group::2) that credit both CTAs' bytes to the leader's "full" barrier.
-template <typename T, int FULL, int CG>
+//
+// X3 (coarse sigma-only pass, fp16): split-precision operands.  ONE 128-row slot per CTA whose activations are kept
+// as hi + lo fp16 pairs (the "lo" copy lives where slot 1 would be), three MMA sub-steps per layer (see TcArgs) and an
+// fp32 bias/ReLU epilogue: the products carry ~22 mantissa bits, i.e. the pass that decides WHERE the fine samples go
+// is as exact as the fp32 kernels at 3x the tensor work of the fp16 pass (mlp kind DFB_MMA_F16_SPLIT_COARSE).
+template <typename T, int FULL, int CG, bool X3 = false>
 __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
+  static_assert(!X3 || (FULL == 0 && std::is_same<T, __half>::value), "split precision: fp16 coarse pass only");
+  constexpr int NSLOT = X3 ? 1 : 2;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sA = smem_u32(smem);
   const uint32_t sW = sA + kSmemA;
@@ -331,7 +389,7 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
         const int nch = a.steps[s].n_chunks;
         const uint8_t* src0 = wimg + (size_t)a.steps[s].chunk_base * (kChunkBytes * CG);
         const int img0 = a.steps[s].chunk_base * CG + (int)rank;  // image index of chunk 0 for this CTA (CG 2)
-        for (int slot = 0; slot < 2; ++slot) {
+        for (int slot = 0; slot < NSLOT; ++slot) {
           const uint8_t* src = src0;
           for (int c = 0; c < nch; ++c, src += kChunkBytes * CG) {
             PROF_WAIT(0, mbar_wait(bar(W_EMPTY + stage), phase ^ 1, a.error_flag));
@@ -361,32 +419,40 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
     PROF_DECL
     uint32_t stage = 0, phase = 0;
     int lp = 0;
-    for (int64_t p = unit0; p < a.n_pass; p += n_units, ++lp)
+    const int n_epi = a.n_epi;
+    for (int64_t p = unit0; p < a.n_pass; p += n_units, ++lp) {
+      int e = 0;  // epilogue step (layer) the sub-step belongs to
       for (int s = 0; s < n_steps; ++s) {
         const int nch = a.steps[s].n_chunks, nn = a.steps[s].n;
         const uint32_t idesc = make_idesc(fmt, nn, kTileM * CG);
         const uint32_t b_rows = nn / CG;  // B rows held by each CTA; LBO = b_rows * 16 B
-        for (int slot = 0; slot < 2; ++slot) {
-          if (s == 0) {
-            if (lp > 0) PROF_WAIT(2, mbar_wait_cluster<CG>(bar(PASS_DONE + slot), (lp - 1) & 1, a.error_flag));
-            PROF_WAIT(2, mbar_wait_cluster<CG>(bar(PE_READY + slot), lp & 1, a.error_flag));
-          } else {
-            PROF_STEP(s, mbar_wait_cluster<CG>(bar(A_READY + slot), (lp * (n_steps - 1) + s - 1) & 1, a.error_flag));
+        const bool first = a.first[s] != 0, last = a.last[s] != 0;
+        for (int slot = 0; slot < NSLOT; ++slot) {
+          if (first) {
+            if (e == 0) {
+              if (lp > 0) PROF_WAIT(2, mbar_wait_cluster<CG>(bar(PASS_DONE + slot), (lp - 1) & 1, a.error_flag));
+              PROF_WAIT(2, mbar_wait_cluster<CG>(bar(PE_READY + slot), lp & 1, a.error_flag));
+            } else {
+              PROF_STEP(e, mbar_wait_cluster<CG>(bar(A_READY + slot), (lp * (n_epi - 1) + e - 1) & 1, a.error_flag));
+            }
+            tc_fence_after();
           }
-          tc_fence_after();
           const uint32_t d_tmem = tmem_base + slot * 256;
           // low word: start address >> 4 | LBO (2048 B >> 4) << 16; one K=16 step advances by 2 panels
           const uint32_t a_lo = ((sA + slot * kSlotBytes + a.steps[s].a_panel0 * kPanelBytes) >> 4) | ((kPanelBytes >> 4) << 16);
-          if (nn == 256) issue_step<CG, 2 * CG>(stage, phase, nch, a_lo, b_rows, d_tmem, idesc, sW, sBar, a.error_flag, PROF_PTR);
-          else if (nn == 128) issue_step<CG, 4 * CG>(stage, phase, nch, a_lo, b_rows, d_tmem, idesc, sW, sBar, a.error_flag, PROF_PTR);
-          else issue_step<CG, 8 * CG>(stage, phase, nch, a_lo, b_rows, d_tmem, idesc, sW, sBar, a.error_flag, PROF_PTR);
+          const uint32_t acc0 = first ? 0u : 1u;
+          if (nn == 256) issue_step<CG, 2 * CG>(stage, phase, nch, a_lo, b_rows, d_tmem, idesc, sW, sBar, a.error_flag, PROF_PTR, acc0);
+          else if (nn == 128) issue_step<CG, 4 * CG>(stage, phase, nch, a_lo, b_rows, d_tmem, idesc, sW, sBar, a.error_flag, PROF_PTR, acc0);
+          else issue_step<CG, 8 * CG>(stage, phase, nch, a_lo, b_rows, d_tmem, idesc, sW, sBar, a.error_flag, PROF_PTR, acc0);
           if (elect_one()) {
-            umma_commit<CG>(bar(D_FULL + slot));
+            if (last) umma_commit<CG>(bar(D_FULL + slot));
             if (s == a.last_pe_step) umma_commit<CG>(bar(PE_FREE + slot));
           }
           __syncwarp();
         }
+        if (last) ++e;
       }
+    }
     PROF_FLUSH(4)
     PROF_FLUSH_STEPS
   } else if (warp >= 8 && warp < 12) {
@@ -394,9 +460,9 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
     const int r = tid - 256;
     int lp = 0;
     for (int64_t p = unit0; p < a.n_pass; p += n_units, ++lp)
-      for (int slot = 0; slot < 2; ++slot) {
+      for (int slot = 0; slot < NSLOT; ++slot) {
         if (lp > 0) mbar_wait_relaxed(bar(PE_FREE + slot), (lp - 1) & 1, a.error_flag);
-        int64_t g = ((2 * p + slot) * CG + rank) * kTileM + r;
+        int64_t g = ((NSLOT * p + slot) * CG + rank) * kTileM + r;
         g = g < a.P ? g : a.P - 1;
         const int64_t ray = g / a.S;
         const float* rr = a.rayrec + ray * kRayRec;
@@ -408,7 +474,12 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
         const uint32_t dst = sA + slot * kSlotBytes + kHPanels * kPanelBytes + r * 16;
         auto put = [&](int col, float v) {
           T h = (T)v;
-          st_shared_b16(dst + (uint32_t)(col >> 3) * kPanelBytes + (col & 7) * 2, *reinterpret_cast<uint16_t*>(&h));
+          const uint32_t at = dst + (uint32_t)(col >> 3) * kPanelBytes + (col & 7) * 2;
+          st_shared_b16(at, *reinterpret_cast<uint16_t*>(&h));
+          if (X3) {  // lo part of the split operand, in the "lo" region of the slot
+            T l = (T)(v - (float)h);
+            st_shared_b16(at + kSlotBytes, *reinterpret_cast<uint16_t*>(&l));
+          }
         };
         put(0, pt[0]), put(1, pt[1]), put(2, pt[2]), put(63, 0.f);
 #pragma unroll 1
@@ -440,10 +511,10 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
     uint32_t nd = 0;
     for (int64_t p = unit0; p < a.n_pass; p += n_units) {
       // row of slot `sl` in the flattened [ray][sample] array (recomputed where needed: registers are scarce here)
-      auto row_of = [&](int sl) { return ((2 * p + sl) * CG + rank) * kTileM + r; };
+      auto row_of = [&](int sl) { return ((NSLOT * p + sl) * CG + rank) * kTileM + r; };
       int rayi[2];
 #pragma unroll
-      for (int slot = 0; slot < 2; ++slot) {
+      for (int slot = 0; slot < NSLOT; ++slot) {
         const int64_t gg = row_of(slot);
         rayi[slot] = (int)((gg < a.P ? gg : a.P - 1) / a.S);
         // the per-ray bias row (1 KB) is read by the dir/transient layer much later in the pass: pull it
@@ -451,11 +522,12 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
         if (FULL) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.raybias + (size_t)rayi[slot] * 256 + (tid & 7) * 32));
         cx[slot].sig = 0.f;
       }
-      for (int s = 0; s < n_steps; ++s, ++nd) {
+      const int n_epi = a.n_epi;
+      for (int s = 0; s < n_epi; ++s, ++nd) {
         const int boff = s * 256;
         const int kd = a.kind[s];
 #pragma unroll
-        for (int slot = 0; slot < 2; ++slot) {
+        for (int slot = 0; slot < NSLOT; ++slot) {
           const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + slot * 256;
           const uint32_t h_row = sA + slot * kSlotBytes + r * 16;
           const float* rbs = FULL ? a.raybias + (size_t)rayi[slot] * 256 : nullptr;
@@ -468,7 +540,8 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
           // pass: they are computed on clamped rows but must not write masks — the buffer has ceil(P/128) tiles)
           if (MK && ((2 * p + slot) * CG + rank) * kTileM < a.P)
             mrow = a.masks + ((((2 * p + slot) * CG + rank) * 12 + a.mlayer[s]) * 8) * 128 + r;
-          if (kd == EPI_HIDDEN) epi_blocks<T, EPI_HIDDEN, MK>(t_row, h_row, a, boff, w0, w0 + 4, rbs, mrow);
+          if (X3 && kd == EPI_HIDDEN) epi_blocks_x3(t_row, h_row, a.bias32 + boff, w0, w0 + 4);
+          else if (kd == EPI_HIDDEN) epi_blocks<T, EPI_HIDDEN, MK>(t_row, h_row, a, boff, w0, w0 + 4, rbs, mrow);
           else if (kd == EPI_T) epi_blocks<T, EPI_T, MK>(t_row, h_row, a, boff, n0, n0 + 2, rbs, mrow);
           else if (kd == EPI_DT) epi_blocks<T, EPI_DT, MK>(t_row, h_row, a, boff, w0, w0 + 4, rbs, mrow);
           else if (kd == EPI_FINAL) epi_blocks<T, EPI_FINAL, false>(t_row, h_row, a, boff, w0, w0 + 4, rbs, mrow);
@@ -497,7 +570,7 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
           }
           tc_fence_before();
           fence_proxy_async();
-          arrive_leader<CG>(bar((s + 1 < n_steps ? A_READY : PASS_DONE) + slot));
+          arrive_leader<CG>(bar((s + 1 < n_epi ? A_READY : PASS_DONE) + slot));
         }
       }
     }
@@ -520,6 +593,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_tc(const __grid_constant__ 
 template <typename T, int FULL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_mlp_tc2(const __grid_constant__ TcArgs a) {
   mlp_tc_body<T, FULL, 2>(a);
+}
+
+// split-precision coarse pass (see mlp_tc_body, X3)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_mlp_tc2_x3(const __grid_constant__ TcArgs a) {
+  mlp_tc_body<__half, 0, 2, true>(a);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -898,6 +976,35 @@ int pack_tc_weights(DfbNerf* n, int which, const std::vector<std::vector<float>>
       DFB_CHECK_CUDA(cudaMemcpy(np.blob16[k][cg - 1], img16[k].data(), np.blob16_bytes, cudaMemcpyHostToDevice));
     }
   }
+  // split-precision image of the sigma-only program (the first 9 steps: trunk + sigma), cta_group::2 chunking:
+  // all hi chunks, then all lo chunks
+  {
+    if (np.blob16x3) { cudaFree(np.blob16x3); np.blob16x3 = nullptr; }
+    const std::vector<LStep> cprog = build_program(false);
+    size_t imgs = 0;
+    for (const LStep& st : cprog) imgs += (size_t)st.K * st.N * 2 / tc::kChunkBytes;
+    std::vector<uint16_t> img(2 * imgs * tc::kChunkBytes / 2, 0);
+    size_t ii = 0;
+    for (const LStep& st : cprog) {
+      const int rows = st.N / 2;
+      const int kc = tc::kChunkBytes / (rows * 2);
+      for (int k0 = 0; k0 < st.K; k0 += kc)
+        for (int h = 0; h < 2; ++h, ++ii) {
+          const size_t base = ii * (tc::kChunkBytes / 2);
+          for (int kk = 0; kk < kc; ++kk)
+            for (int r = 0; r < rows; ++r) {
+              const float v = wval(st.logical, h * rows + r, k0 + kk);
+              const size_t idx = base + (size_t)(kk / 8) * rows * 8 + (size_t)r * 8 + kk % 8;
+              const __half hh = __float2half_rn(v);
+              img[idx] = f2h(v);
+              img[imgs * (tc::kChunkBytes / 2) + idx] = f2h(v - __half2float(hh));
+            }
+        }
+    }
+    np.blob16x3_bytes = 2 * imgs * tc::kChunkBytes;
+    DFB_CHECK_CUDA(cudaMalloc(&np.blob16x3, np.blob16x3_bytes));
+    DFB_CHECK_CUDA(cudaMemcpy(np.blob16x3, img.data(), np.blob16x3_bytes, cudaMemcpyHostToDevice));
+  }
   // fp32 table read through the constant bank by the epilogue (see TcArgs::tbl); biases by program step
   np.tc_tbl.assign(tc::kTblFloats, 0.f);
   float* tb = np.tc_tbl.data();
@@ -911,6 +1018,10 @@ int pack_tc_weights(DfbNerf* n, int which, const std::vector<std::vector<float>>
     // lg == 9: the bias of dir_encoding / transient_encoding.0 is part of the per-ray bias
   }
   tb[tc::kTblScal] = P[21][0];
+  if (np.tc_bias32_dev) cudaFree(np.tc_bias32_dev);
+  np.tc_bias32_dev = nullptr;
+  DFB_CHECK_CUDA(cudaMalloc(&np.tc_bias32_dev, tc::kTblScal * sizeof(float)));
+  DFB_CHECK_CUDA(cudaMemcpy(np.tc_bias32_dev, tb, tc::kTblScal * sizeof(float), cudaMemcpyHostToDevice));
   if (fine) {
     std::vector<float> dtb(W, 0.f);
     if (fold_final()) dtb = folded_b;
@@ -956,39 +1067,53 @@ static int tc_cta_group() {  // read per launch so that tests can exercise both 
 }
 
 int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const float* rayrec, const float* z,
-                       const float* raybias, int64_t n_rays, int S, float* raw, cudaStream_t st, uint32_t* masks) {
+                       const float* raybias, int64_t n_rays, int S, float* raw, cudaStream_t st, uint32_t* masks, bool split3) {
   const NetPack& np = nerf->net[which];
   DFB_REQUIRE(tc_supported(nerf, which, mode), DFB_ERR_UNSUPPORTED, "network shape not supported by the tcgen05 kernel");
   DFB_REQUIRE(kind == DFB_MMA_F16 || kind == DFB_MMA_BF16, DFB_ERR_INVALID, "bad mma kind");
   const bool full = mode == MLP_FULL;
   DFB_REQUIRE(!full || raybias, DFB_ERR_INVALID, "ray-constant inputs missing");
+  DFB_REQUIRE(!split3 || (mode == MLP_SIGMA && kind == DFB_MMA_F16 && np.blob16x3), DFB_ERR_UNSUPPORTED,
+              "the split-precision pass covers the sigma-only coarse network with fp16 operands");
   int* error_flag = nullptr;
   {
     const int rc = device_error_flag(&error_flag);
     if (rc) return rc;
   }
-  const int cg = tc_cta_group();
+  const int cg = split3 ? 2 : tc_cta_group();
   tc::TcArgs a = {};
   const std::vector<LStep> prog = build_program(full);
-  a.n_steps = (int)prog.size();
-  a.last_pe_step = 4;
-  int cb = 0;
-  for (int s = 0; s < a.n_steps; ++s) {
-    const LStep& ls = prog[s];
+  a.n_epi = (int)prog.size();
+  int total_chunks = 0;
+  for (const LStep& ls : prog) total_chunks += ls.K / (tc::kChunkBytes / ((ls.N / cg) * 2));
+  int cb = 0, ns = 0;
+  for (int e = 0; e < a.n_epi; ++e) {
+    const LStep& ls = prog[e];
     const int kc = tc::kChunkBytes / ((ls.N / cg) * 2);
-    a.steps[s].n_chunks = ls.K / kc;
-    a.steps[s].ksteps = kc / 16;
-    a.steps[s].n = ls.N;
-    a.steps[s].a_panel0 = ls.a_panel0;
-    a.steps[s].chunk_base = cb;
-    a.kind[s] = ls.kind;
+    tc::Step stp;
+    stp.n_chunks = ls.K / kc, stp.ksteps = kc / 16, stp.n = ls.N, stp.a_panel0 = ls.a_panel0, stp.chunk_base = cb;
+    if (!split3) {
+      a.steps[ns] = stp, a.first[ns] = 1, a.last[ns] = 1;
+      if (e == 4) a.last_pe_step = ns;
+      ++ns;
+    } else {
+      // A_hi W_hi, A_lo W_hi (lo operand: 40 panels further), A_hi W_lo (lo image: total_chunks further)
+      a.steps[ns] = stp, a.first[ns] = 1, a.last[ns] = 0, ++ns;
+      a.steps[ns] = stp, a.steps[ns].a_panel0 = ls.a_panel0 + tc::kHPanels + tc::kPePanels, a.first[ns] = 0, a.last[ns] = 0, ++ns;
+      a.steps[ns] = stp, a.steps[ns].chunk_base = total_chunks + cb, a.first[ns] = 0, a.last[ns] = 1;
+      if (e == 4) a.last_pe_step = ns;
+      ++ns;
+    }
+    a.kind[e] = ls.kind;
     // mask layers (see TcArgs::masks): trunk 0..7, dir|transient.0 = 8, transient_encoding.{2,4,6} = 9..11
-    a.mlayer[s] = ls.logical < 8 ? ls.logical : (ls.logical == 9 || ls.logical == 19) ? 8 : (ls.logical >= 10 && ls.logical <= 12) ? ls.logical - 1 : -1;
+    a.mlayer[e] = ls.logical < 8 ? ls.logical : (ls.logical == 9 || ls.logical == 19) ? 8 : (ls.logical >= 10 && ls.logical <= 12) ? ls.logical - 1 : -1;
     cb += ls.K / kc;
   }
-  a.wimg = np.blob16[kind == DFB_MMA_F16 ? 0 : 1][cg - 1];
+  a.n_steps = ns;
+  a.bias32 = np.tc_bias32_dev;
+  a.wimg = split3 ? np.blob16x3 : np.blob16[kind == DFB_MMA_F16 ? 0 : 1][cg - 1];
   if (cg == 2) {
-    int rc = make_weight_tmap(const_cast<void*>(a.wimg), np.blob16_bytes, &a.tmap);
+    int rc = make_weight_tmap(const_cast<void*>(a.wimg), split3 ? np.blob16x3_bytes : np.blob16_bytes, &a.tmap);
     if (rc) return rc;
   }
   memcpy(a.tbl, np.tc_tbl.data(), sizeof(a.tbl));
@@ -1014,7 +1139,8 @@ int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const
 #endif
   if (a.P == 0) return DFB_OK;
   const int64_t tiles = (a.P + tc::kTileM - 1) / tc::kTileM;
-  a.n_pass = (tiles + 2 * cg - 1) / (2 * cg);
+  const int nslot = split3 ? 1 : 2;
+  a.n_pass = (tiles + nslot * cg - 1) / (nslot * cg);
   const int grid = cg * (int)std::min<int64_t>(a.n_pass, nerf->num_sms / cg);
   auto launch = [&](auto kern) -> int {
     DFB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal));
@@ -1023,6 +1149,7 @@ int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const
     return DFB_OK;
   };
   const bool f16 = kind == DFB_MMA_F16;
+  if (split3) return launch(tc::k_mlp_tc2_x3);
   if (cg == 2) {
     if (masks) return f16 ? launch(tc::k_mlp_tc2<__half, 2>) : launch(tc::k_mlp_tc2<__nv_bfloat16, 2>);
     if (f16) return full ? launch(tc::k_mlp_tc2<__half, 1>) : launch(tc::k_mlp_tc2<__half, 0>);

@@ -27,6 +27,14 @@ int device_error_flag(int** out) {
   DFB_CHECK_CUDA(cudaGetDevice(&dev));
   DFB_REQUIRE(dev >= 0 && dev < 64, DFB_ERR_UNSUPPORTED, "device index %d out of range", dev);
   if (!flags[dev]) {
+    // first use of this device by the library: keep the stream-ordered allocator's pool resident (the default release
+    // threshold of 0 returns the memory to the driver at every synchronisation point, and re-acquiring it costs ms)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
     DFB_CHECK_CUDA(cudaMalloc(&flags[dev], sizeof(int)));
     DFB_CHECK_CUDA(cudaMemset(flags[dev], 0, sizeof(int)));
   }

@@ -63,7 +63,7 @@ class _RenderRaysFn(torch.autograd.Function):
         rec = torch.cat([rays_o, rays_d, near_far_hist[:, :2], viewdirs, near_far_hist[:, 2:]], -1)
         # tcgen05 path: the forward also saves the ReLU masks of the fine network (one bit per activation), so that
         # the backward kernel does not have to recompute the forward
-        saved = mma in ("f16", "bf16") and handle.tc_train
+        saved = mma in ("f16", "bf16", "f16s") and handle.tc_train
         o = handle.render(N_samples, N_importance, True, rays=rec, mma=mma,
                           want=("z_vals", "raw", "relu_masks") if saved else ("z_vals", "raw"))
         ctx.handle, ctx.mma, ctx.saved = handle, mma, saved

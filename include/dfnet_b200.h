@@ -37,6 +37,12 @@ extern "C" {
 #define DFB_MMA_FP32_SIMT 0 /* fp32 FFMA, any width (exact-order fallback for odd sizes)   */
 #define DFB_MMA_F16 1       /* tcgen05.mma kind::f16, fp16 operands, fp32 accumulate in TMEM */
 #define DFB_MMA_BF16 2      /* tcgen05.mma kind::f16, bf16 operands, fp32 accumulate in TMEM */
+/* DFB_MMA_F16 with a SPLIT-PRECISION coarse pass: the sigma-only coarse network - the pass that decides where the fine
+ * samples are placed - runs on hi + lo fp16 operand pairs (A_hi W_hi + A_lo W_hi + A_hi W_lo, fp32 accumulate; ~22
+ * mantissa bits, 3x the coarse tensor work); the fine network runs as DFB_MMA_F16.  On fields with sharp density steps
+ * the fp16 rounding of the coarse pass moves fine samples across surfaces and dominates the image error;
+ * this kind removes that term.  (kind::tf32 would not: it has fp16's 10-bit mantissa.) */
+#define DFB_MMA_F16_SPLIT_COARSE 3
 
 const char* dfb_last_error(void);
 int dfb_version(void);
