@@ -1,6 +1,8 @@
 // C ABI entry points for rendering (see include/dfnet_b200.h).  Orchestrates the kernels of
 // render_kernels.cu / mlp_simt.cu / mlp_tc.cu the way models/rendering.py:245-400 chains
 // render -> batchify_rays -> render_rays -> {network_query_fn, raw2outputs_NeRFW, sample_pdf}.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -10,6 +12,11 @@ using namespace dfb;
 namespace {
 
 constexpr int64_t kChunkRays = 1 << 16;  // internal batchify (bounds the workspace, not a tuning knob of the ABI)
+
+bool fuse_composite() {  // read per call so that tests can compare both paths in one process
+  const char* e = getenv("DFB_TC_FUSE_COMPOSITE");
+  return !(e && e[0] == '0');
+}
 
 // operand kind of everything but the coarse sigma-only pass
 int eff_kind(int k) { return k == DFB_MMA_F16_SPLIT_COARSE ? DFB_MMA_F16 : k; }
@@ -62,25 +69,28 @@ bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
 
 int run_mlp_inner(const DfbNerf* n, const DfbRenderCfg* c, int which, int mode, const float* rayrec, const float* z,
-                  const float* rb, int64_t rays, int S, float* raw, cudaStream_t st, uint32_t* masks) {
+                  const float* rb, int64_t rays, int S, float* raw, cudaStream_t st, uint32_t* masks, float* part) {
   // The tcgen05 kernel covers the 8x256 networks (sigma-only coarse pass and full fine pass); every
   // other shape or mode (other widths, the train-mode coarse pass) runs on the fp32 CUDA kernel.
   if (c->mma_kind != DFB_MMA_FP32_SIMT && tc_supported(n, which, mode))
     return launch_mlp_tc_rays(n, which, mode, eff_kind(c->mma_kind), rayrec, z, rb, rays, S, raw, st, masks,
-                              c->mma_kind == DFB_MMA_F16_SPLIT_COARSE && which == 0 && mode == MLP_SIGMA);
+                              c->mma_kind == DFB_MMA_F16_SPLIT_COARSE && which == 0 && mode == MLP_SIGMA, part,
+                              part ? composite_part_k(S) : 0);
+  DFB_REQUIRE(!part, DFB_ERR_UNSUPPORTED, "fused compositing is a mode of the tcgen05 fine pass");
   DFB_REQUIRE(!masks, DFB_ERR_UNSUPPORTED, "relu_masks are an output of the tcgen05 path (8x256 fine network, mma f16 / bf16)");
   return launch_mlp_simt_rays(n, which, mode, rayrec, z, rb, rays, S, raw, st);
 }
 
 int run_mlp(const DfbNerf* n, const DfbRenderCfg* c, int which, int mode, const float* rayrec, const float* z,
-            const float* rb, int64_t rays, int S, float* raw, cudaStream_t st, uint32_t* masks = nullptr) {
-  if (!g_prof_on) return run_mlp_inner(n, c, which, mode, rayrec, z, rb, rays, S, raw, st, masks);
+            const float* rb, int64_t rays, int S, float* raw, cudaStream_t st, uint32_t* masks = nullptr,
+            float* part = nullptr) {
+  if (!g_prof_on) return run_mlp_inner(n, c, which, mode, rayrec, z, rb, rays, S, raw, st, masks, part);
   ProfRec r;
   r.which = which;
   DFB_CHECK_CUDA(cudaEventCreate(&r.a));
   DFB_CHECK_CUDA(cudaEventCreate(&r.b));
   DFB_CHECK_CUDA(cudaEventRecord(r.a, st));
-  int rc = run_mlp_inner(n, c, which, mode, rayrec, z, rb, rays, S, raw, st, masks);
+  int rc = run_mlp_inner(n, c, which, mode, rayrec, z, rb, rays, S, raw, st, masks, part);
   DFB_CHECK_CUDA(cudaEventRecord(r.b, st));
   g_prof.push_back(r);
   return rc;
@@ -224,6 +234,19 @@ extern "C" int dfb_render_fwd(DfbNerf* n, const DfbRenderCfg* c, const float* ra
     if (ex && ex->relu_masks) {
       DFB_REQUIRE((r0 * S) % 128 == 0, DFB_ERR_INVALID, "relu_masks: chunk start not aligned to a 128-sample tile");
       masks = ex->relu_masks + (size_t)(r0 * S / 128) * kReluMaskWordsPerTile;
+    }
+    // Test-time render_path step on the tcgen05 path with nothing but rgb / disp / acc wanted: compositing is fused
+    // into the heads epilogue of the fine kernel (no [P,9] raw tensor; one 32-byte record per 32 samples instead) and
+    // k_composite_partials chains the records.  DFB_TC_FUSE_COMPOSITE=0 keeps the raw round trip (A/B measurement).
+    const bool fuse = tc_f && c->test_time && fuse_composite() &&
+                      !(ex && (ex->raw || ex->depth || ex->beta || ex->transient_sigmas || ex->relu_masks));
+    if (fuse) {
+      float* part = P(L.raw_f);  // the raw buffer's space: rays * part_k * 32 B << rays * S * 36 B
+      rc = run_mlp(n, c, 1, MLP_FULL, rayrec, z_all, rb_f, nr, S, nullptr, st, nullptr, part);
+      if (rc) return rc;
+      rc = launch_composite_partials(part, composite_part_k(S), nr, S, rgb + r0 * 3, disp + r0, acc + r0, st);
+      if (rc) return rc;
+      continue;
     }
     rc = run_mlp(n, c, 1, MLP_FULL, rayrec, z_all, rb_f, nr, S, raw_f, st, masks);
     if (rc) return rc;

@@ -132,7 +132,12 @@ int launch_mlp_simt_embedded(const DfbNerf* nerf, int which, int mode, const flo
 // split3: the split-precision variant of the sigma-only pass (three MMA sub-steps per layer on hi/lo fp16 operands)
 int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const float* rayrec, const float* z,
                        const float* raybias, int64_t n_rays, int S, float* raw, cudaStream_t st,
-                       uint32_t* masks = nullptr, bool split3 = false);
+                       uint32_t* masks = nullptr, bool split3 = false, float* part = nullptr, int part_k = 0);
+// fused compositing (fine pass at test time): records per ray of launch_mlp_tc_rays(part = ...) and the kernel that
+// chains them into rgb / disp / acc
+inline int composite_part_k(int S) { return (S + 30) / 32 + 1; }
+int launch_composite_partials(const float* part, int part_k, int64_t n_rays, int S, float* rgb, float* disp, float* acc,
+                              cudaStream_t st);
 bool tc_supported(const DfbNerf* nerf, int which, int mode);
 // Networks narrower than 256 run on the 256-wide tcgen05 kernels EXACTLY, embedded with zero weights / zero biases
 // (a ReLU unit with zero input weights and bias stays at 0 and feeds nothing): tc_pad_params returns the state dict

@@ -95,6 +95,11 @@ struct TcArgs {
   int64_t P;              // n_rays * S
   int64_t n_pass;         // ceil(tiles / 2)
   float* raw;             // [P,1] or [P,9]
+  // FULL == 3 (test-time fine pass, fused compositing): instead of raw, every warp of the heads epilogue composites
+  // the ray segments inside its 32 rows and writes one record per segment, part[(ray * part_k + k) * 8] =
+  // {prod(1-alpha), prod(1-alpha_static), rgb[3], acc, static depth, 0}, k = index of the warp within the ray
+  float* part;
+  int part_k;
   int* error_flag;
   unsigned long long* prof;  // optional [gridDim.x][16] cycle counters (DFB_TC_PROF builds)
   // FULL == 2 (training forward): ReLU masks of the 12 hidden layers, one bit per activation, for the tcgen05
@@ -219,6 +224,67 @@ __device__ __forceinline__ void epi_blocks(uint32_t t_row, uint32_t h_row, const
     tmem_ld_wait(v1);
     if (cb + 2 < cb1) tmem_ld32(t_row + (cb + 2) * 32, v0);
     epi_block<T, KIND, MK>(v1, a, bias_off, cb + 1, rb, h_row, mrow);
+  }
+}
+
+// Fused test-time compositing of the fine pass (models/rendering.py:132-243 with test_time and static_only, i.e.
+// what k_composite_fine_tt computes from the raw tensor): called by the 32 lanes of a heads-epilogue warp, lane = row g
+// of the flattened [ray][sample] array.  Ray segments inside the warp are composited with segmented warp scans
+// (transmittance = running product of 1 - alpha inside the segment) and the last lane of every segment writes the
+// segment's record; k_composite_partials chains the <= ceil(S/32) + 1 records of a ray.  fp32 throughout: nothing
+// downstream decides a sample index, and the tensor-core path is gated at 1e-3.
+__device__ __forceinline__ void fused_composite(const TcArgs& a, int64_t g, int ray, float ss, float st,
+                                                const float (&cs)[3], const float (&ct)[3]) {
+  const int lane = threadIdx.x & 31;
+  const bool valid = g < a.P;
+  const int i = (int)(g - (int64_t)ray * a.S);
+  const float zi = valid ? __ldg(a.z + g) : 0.f;
+  float zn = __shfl_down_sync(0xffffffffu, zi, 1);
+  if (lane == 31 && valid && i + 1 < a.S) zn = __ldg(a.z + g + 1);
+  const float delta = (i + 1 < a.S) ? __fsub_rn(zn, zi) : 1e2f;
+  float al = 0.f, als = 0.f, alt = 0.f, oma = 1.f, omas = 1.f;
+  if (valid) {
+    al = __fsub_rn(1.f, expf(__fmul_rn(-delta, __fadd_rn(ss, st))));
+    als = __fsub_rn(1.f, expf(__fmul_rn(-delta, ss)));
+    alt = __fsub_rn(1.f, expf(__fmul_rn(-delta, st)));
+    oma = __fsub_rn(1.f, al), omas = __fsub_rn(1.f, als);
+  }
+  // inclusive segmented products
+  float pa = oma, ps = omas;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const float ta = __shfl_up_sync(0xffffffffu, pa, off), ts = __shfl_up_sync(0xffffffffu, ps, off);
+    const int rr = __shfl_up_sync(0xffffffffu, ray, off);
+    if (lane >= off && rr == ray) pa *= ta, ps *= ts;
+  }
+  const int rprev = __shfl_up_sync(0xffffffffu, ray, 1);
+  const float ta1 = __shfl_up_sync(0xffffffffu, pa, 1), ts1 = __shfl_up_sync(0xffffffffu, ps, 1);
+  const bool cont = lane >= 1 && rprev == ray;
+  const float Te = cont ? ta1 : 1.f, Tse = cont ? ts1 : 1.f;   // exclusive: transmittance in front of this sample
+  const float sw = __fmul_rn(als, Te), tw = __fmul_rn(alt, Te);
+  float acc[5];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) acc[c] = __fadd_rn(__fmul_rn(sw, cs[c]), __fmul_rn(tw, ct[c]));
+  acc[3] = __fmul_rn(al, Te);
+  acc[4] = __fmul_rn(__fmul_rn(als, Tse), zi);
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int rr = __shfl_up_sync(0xffffffffu, ray, off);
+    const bool take = lane >= off && rr == ray;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+      const float t = __shfl_up_sync(0xffffffffu, acc[c], off);
+      if (take) acc[c] += t;
+    }
+  }
+  const int rnext = __shfl_down_sync(0xffffffffu, ray, 1);
+  const int64_t ray0 = (int64_t)ray * a.S;
+  const int64_t seg_first = ray0 > (g & ~(int64_t)31) ? ray0 : (g & ~(int64_t)31);
+  if ((lane == 31 || rnext != ray) && seg_first < a.P) {
+    const int k = (int)((g >> 5) - (ray0 >> 5));
+    float4* o = reinterpret_cast<float4*>(a.part + ((size_t)ray * a.part_k + k) * 8);
+    o[0] = make_float4(pa, ps, acc[0], acc[1]);
+    o[1] = make_float4(acc[2], acc[3], acc[4], 0.f);
   }
 }
 
@@ -552,10 +618,25 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
             tmem_ld32(t_row, v);
             tmem_ld_wait(v);
             const int64_t gg = row_of(slot);
+            if (FULL == 3 && kd == EPI_HEADS) {
+              // fused compositing: the accumulator has been read, so the slot is handed back to the tensor pipe
+              // first and the activation / compositing arithmetic overlaps the next pass' first layers
+              tc_fence_before();
+              arrive_leader<CG>(bar(PASS_DONE + slot));
+              const float cs[3] = {sigmoid_f(__uint_as_float(v[8]) + a.tbl[kTblScal + 1]),
+                                   sigmoid_f(__uint_as_float(v[9]) + a.tbl[kTblScal + 2]),
+                                   sigmoid_f(__uint_as_float(v[10]) + a.tbl[kTblScal + 3])};
+              const float ct[3] = {sigmoid_f(__uint_as_float(v[0]) + a.tbl[kTblScal + 4]),
+                                   sigmoid_f(__uint_as_float(v[1]) + a.tbl[kTblScal + 5]),
+                                   sigmoid_f(__uint_as_float(v[2]) + a.tbl[kTblScal + 6])};
+              const float st = softplus_f(__uint_as_float(v[3]) + a.tbl[kTblScal + 7]);
+              fused_composite(a, gg, rayi[slot], cx[slot].sig, st, cs, ct);
+              continue;
+            }
             if (kd == EPI_SIGMA) {
               cx[slot].sig = softplus_f(__uint_as_float(v[0]) + a.tbl[kTblScal]);
               if (!FULL && gg < a.P) a.raw[gg] = cx[slot].sig;
-            } else if (gg < a.P) {
+            } else if (FULL != 3 && gg < a.P) {
               float* o = a.raw + gg * 9;
               o[0] = sigmoid_f(__uint_as_float(v[8]) + a.tbl[kTblScal + 1]);
               o[1] = sigmoid_f(__uint_as_float(v[9]) + a.tbl[kTblScal + 2]);
@@ -1067,7 +1148,8 @@ static int tc_cta_group() {  // read per launch so that tests can exercise both 
 }
 
 int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const float* rayrec, const float* z,
-                       const float* raybias, int64_t n_rays, int S, float* raw, cudaStream_t st, uint32_t* masks, bool split3) {
+                       const float* raybias, int64_t n_rays, int S, float* raw, cudaStream_t st, uint32_t* masks, bool split3,
+                       float* part, int part_k) {
   const NetPack& np = nerf->net[which];
   DFB_REQUIRE(tc_supported(nerf, which, mode), DFB_ERR_UNSUPPORTED, "network shape not supported by the tcgen05 kernel");
   DFB_REQUIRE(kind == DFB_MMA_F16 || kind == DFB_MMA_BF16, DFB_ERR_INVALID, "bad mma kind");
@@ -1123,7 +1205,9 @@ int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const
   }
   a.rayrec = rayrec, a.z = z, a.raybias = raybias, a.S = S, a.P = n_rays * S, a.raw = raw;
   DFB_REQUIRE(!masks || full, DFB_ERR_INVALID, "ReLU masks are an output of the fine network only");
+  DFB_REQUIRE(!part || (full && !masks && part_k >= 1), DFB_ERR_INVALID, "fused compositing is a mode of the fine pass without masks");
   a.masks = masks;
+  a.part = part, a.part_k = part_k;
   a.error_flag = error_flag;
 #ifdef DFB_TC_PROF
   if (!g_prof) {
@@ -1150,6 +1234,10 @@ int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const
   };
   const bool f16 = kind == DFB_MMA_F16;
   if (split3) return launch(tc::k_mlp_tc2_x3);
+  if (part) {
+    if (cg == 2) return f16 ? launch(tc::k_mlp_tc2<__half, 3>) : launch(tc::k_mlp_tc2<__nv_bfloat16, 3>);
+    return f16 ? launch(tc::k_mlp_tc<__half, 3>) : launch(tc::k_mlp_tc<__nv_bfloat16, 3>);
+  }
   if (cg == 2) {
     if (masks) return f16 ? launch(tc::k_mlp_tc2<__half, 2>) : launch(tc::k_mlp_tc2<__nv_bfloat16, 2>);
     if (f16) return full ? launch(tc::k_mlp_tc2<__half, 1>) : launch(tc::k_mlp_tc2<__half, 0>);

@@ -516,6 +516,36 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_composite_fine_tt(Compo
   }
 }
 
+// Chains the per-warp segment records of the fused fine pass (mlp_tc.cu, fused_composite) front to back:
+// rgb += T * C_k, acc += T * A_k, depth += T_static * D_k, T *= prod_k (rendering.py:196-242, test_time).
+__global__ void __launch_bounds__(128) k_composite_partials(const float* __restrict__ part, int part_k, int64_t N, int S,
+                                                             float* __restrict__ rgb, float* __restrict__ disp,
+                                                             float* __restrict__ acc) {
+  const int64_t ray = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (ray >= N) return;
+  const int64_t g0 = ray * S;
+  const int K = (int)(((g0 + S - 1) >> 5) - (g0 >> 5)) + 1;
+  const float4* p = reinterpret_cast<const float4*>(part + (size_t)ray * part_k * 8);
+  float T = 1.f, Ts = 1.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, ac = 0.f, dep = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float4 u = __ldcs(p + 2 * k), v = __ldcs(p + 2 * k + 1);
+    r0 = fmaf(T, u.z, r0), r1 = fmaf(T, u.w, r1), r2 = fmaf(T, v.x, r2);
+    ac = fmaf(T, v.y, ac);
+    dep = fmaf(Ts, v.z, dep);
+    T *= u.x, Ts *= u.y;
+  }
+  rgb[ray * 3 + 0] = r0, rgb[ray * 3 + 1] = r1, rgb[ray * 3 + 2] = r2;
+  acc[ray] = ac;
+  disp[ray] = __fdiv_rn(1.f, fmaxf(1e-10f, __fdiv_rn(dep, ac)));
+}
+
+int launch_composite_partials(const float* part, int part_k, int64_t n_rays, int S, float* rgb, float* disp, float* acc,
+                              cudaStream_t st) {
+  k_composite_partials<<<(unsigned)((n_rays + 127) / 128), 128, 0, st>>>(part, part_k, n_rays, S, rgb, disp, acc);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
 int launch_composite(const CompositeArgs& a, cudaStream_t st) {
   // render_path step: fine pass at test time with only rgb / disp / acc wanted
   if (a.C == 9 && a.typ_fine && a.test_time && !a.weights && !a.tsig && !a.beta && !a.depth) {
