@@ -1,0 +1,240 @@
+// Data-side and evaluation kernels around the hot path.
+//
+// Reference arithmetic (paths relative to /root/reference):
+//   k_luma_hist       dataset_loaders/seven_scenes.py:346-352 (histogram of the Y channel, as percentages, rounded)
+//                     with dataset_loaders/utils/color.py:29-35 (rgb_to_yuv, Y = 0.299 r + 0.587 g + 0.114 b)
+//   k_resize_area     dataset_loaders/seven_scenes.py:328-332 (cv2.resize(..., interpolation=cv2.INTER_AREA) of the
+//                     float image when df != 1); also feature/direct_feature_matching.py:149
+//   k_pose_error      script/feature/misc.py:49-107 (compute_error_in_q: SVD-orthogonalised rotation, quaternions,
+//                     angular error in degrees, translation error)
+#include "common.cuh"
+
+namespace dfb {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// luma histogram: one block row per image, shared-memory integer bins (exact, order independent)
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kMaxBins = 256;
+
+__global__ void __launch_bounds__(256) k_luma_hist_count(const float* __restrict__ img, int64_t plane, int bins,
+                                                         unsigned int* __restrict__ counts) {
+  __shared__ unsigned int sh[kMaxBins];
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < bins; i += 256) sh[i] = 0;
+  __syncthreads();
+  const float* r = img + (size_t)b * 3 * plane;
+  const float* g = r + plane;
+  const float* bl = g + plane;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < plane; i += (int64_t)gridDim.x * 256) {
+    // 0.299 * r + 0.587 * g + 0.114 * b, every product and sum rounded to fp32 like the tensor expression
+    const float y = __fadd_rn(__fadd_rn(__fmul_rn(0.299f, r[i]), __fmul_rn(0.587f, g[i])), __fmul_rn(0.114f, bl[i]));
+    if (y >= 0.f && y <= 1.f) {   // torch.histc ignores values outside [min, max]
+      // ATen histc (CPU): pos = (int64)((x - min) / (max - min) * bins), the maximum goes to the last bin
+      int pos = (int)__fmul_rn(__fdiv_rn(__fsub_rn(y, 0.f), 1.f), (float)bins);
+      pos = pos < bins - 1 ? pos : bins - 1;
+      atomicAdd(&sh[pos], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < bins; i += 256)
+    if (sh[i]) atomicAdd(&counts[(size_t)b * bins + i], sh[i]);
+}
+
+// hist / hist.sum() * 100, torch.round (half to even); the float32 sum of integer counts is exact below 2^24 pixels
+__global__ void k_luma_hist_final(const unsigned int* __restrict__ counts, int bins, float* __restrict__ out) {
+  const int b = blockIdx.x;
+  __shared__ float tot;
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < bins; ++i) s = __fadd_rn(s, (float)counts[(size_t)b * bins + i]);
+    tot = s;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < bins; i += blockDim.x)
+    out[(size_t)b * bins + i] = rintf(__fmul_rn(__fdiv_rn((float)counts[(size_t)b * bins + i], tot), 100.f));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// INTER_AREA downscale of an HWC float image (cv2's area tables: fractional coverage at both ends of a cell)
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void area_span(int d, double scale, int ssize, int& s0, int& s1, float& w_first, float& w_full,
+                                          float& w_last) {
+  // cv2 computeResizeAreaTab: destination cell [d*scale, (d+1)*scale) over the source axis
+  const double fsx1 = d * scale, fsx2 = fsx1 + scale;
+  const double cell = fmin(scale, (double)ssize - fsx1);
+  int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
+  sx2 = sx2 < ssize - 1 ? sx2 : ssize - 1;
+  sx1 = sx1 < sx2 ? sx1 : sx2;
+  w_first = (sx1 - fsx1 > 1e-3) ? (float)((sx1 - fsx1) / cell) : 0.f;
+  w_full = (float)(1.0 / cell);
+  w_last = (fsx2 - sx2 > 1e-3) ? (float)(fmin(fmin(fsx2 - sx2, 1.0), cell) / cell) : 0.f;
+  s0 = sx1, s1 = sx2;
+}
+
+__global__ void __launch_bounds__(256) k_resize_area(const float* __restrict__ src, int H, int W, int C, int h, int w,
+                                                     float* __restrict__ dst) {
+  const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t total = (int64_t)h * w * C;
+  if (idx >= total) return;
+  const int c = (int)(idx % C);
+  const int dx = (int)((idx / C) % w), dy = (int)(idx / ((int64_t)C * w));
+  const double sx = (double)W / w, sy = (double)H / h;
+  int x0, x1, y0, y1;
+  float wxf, wx, wxl, wyf, wy, wyl;
+  area_span(dx, sx, W, x0, x1, wxf, wx, wxl);
+  area_span(dy, sy, H, y0, y1, wyf, wy, wyl);
+  auto row = [&](int y) {
+    const float* p = src + ((int64_t)y * W) * C + c;
+    float s = 0.f;
+    if (wxf > 0.f) s = fmaf(p[(int64_t)(x0 - 1) * C], wxf, s);
+    for (int x = x0; x < x1; ++x) s = fmaf(p[(int64_t)x * C], wx, s);
+    if (wxl > 0.f) s = fmaf(p[(int64_t)x1 * C], wxl, s);
+    return s;
+  };
+  float acc = 0.f;
+  if (wyf > 0.f) acc = fmaf(row(y0 - 1), wyf, acc);
+  for (int y = y0; y < y1; ++y) acc = fmaf(row(y), wy, acc);
+  if (wyl > 0.f) acc = fmaf(row(y1), wyl, acc);
+  dst[idx] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// pose error: one thread per pose pair, double precision inside (a 3x3 problem)
+// ---------------------------------------------------------------------------------------------------------------------
+// R -> U V^T (the orthogonal polar factor, what torch.svd + matmul(u, v^T) produces) by Jacobi eigen-decomposition of
+// R^T R = V diag(s^2) V^T and U V^T = R V diag(1/s) V^T.
+__device__ void polar_orthogonal(const double R[9], double Q[9]) {
+  double A[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += R[k * 3 + i] * R[k * 3 + j];
+      A[i * 3 + j] = s;
+    }
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    const double off = fabs(A[1]) + fabs(A[2]) + fabs(A[5]);
+    if (off < 1e-300) break;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        const double apq = A[p * 3 + q];
+        if (fabs(apq) < 1e-300) continue;
+        const double theta = (A[q * 3 + q] - A[p * 3 + p]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < 3; ++k) {  // A <- A J
+          const double akp = A[k * 3 + p], akq = A[k * 3 + q];
+          A[k * 3 + p] = c * akp - s * akq, A[k * 3 + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < 3; ++k) {  // A <- J^T A
+          const double apk = A[p * 3 + k], aqk = A[q * 3 + k];
+          A[p * 3 + k] = c * apk - s * aqk, A[q * 3 + k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < 3; ++k) {
+          const double vkp = V[k * 3 + p], vkq = V[k * 3 + q];
+          V[k * 3 + p] = c * vkp - s * vkq, V[k * 3 + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  double M[9];  // V diag(1/s) V^T
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += V[i * 3 + k] * V[j * 3 + k] / sqrt(fmax(A[k * 3 + k], 1e-300));
+      M[i * 3 + j] = s;
+    }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += R[i * 3 + k] * M[k * 3 + j];
+      Q[i * 3 + j] = s;
+    }
+}
+
+// pytorch3d 0.3.0 transforms.matrix_to_quaternion (requirements.txt:76; not vendored): w = sqrt(max(0, 1 + m00 + m11 +
+// m22)) / 2 and x, y, z alike with copysign from the antisymmetric part; float32 like torch.Tensor(...)
+__device__ void mat_to_quat(const float m[9], float q[4]) {
+  const float m00 = m[0], m11 = m[4], m22 = m[8];
+  const float o0 = 0.5f * sqrtf(fmaxf(0.f, 1.f + m00 + m11 + m22));
+  const float x = 0.5f * sqrtf(fmaxf(0.f, 1.f + m00 - m11 - m22));
+  const float y = 0.5f * sqrtf(fmaxf(0.f, 1.f - m00 + m11 - m22));
+  const float z = 0.5f * sqrtf(fmaxf(0.f, 1.f - m00 - m11 + m22));
+  q[0] = o0;
+  q[1] = copysignf(x, m[7] - m[5]);
+  q[2] = copysignf(y, m[2] - m[6]);
+  q[3] = copysignf(z, m[3] - m[1]);
+}
+
+__global__ void k_pose_error(const float* __restrict__ pred, const float* __restrict__ gt, int n, int use_svd,
+                             float* __restrict__ out, float* __restrict__ pred_fixed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = pred + (size_t)i * 12;
+  const float* g = gt + (size_t)i * 12;
+  float Rp[9], Rg[9];
+  double Rd[9], Qd[9];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) Rd[r * 3 + c] = p[r * 4 + c], Rg[r * 3 + c] = g[r * 4 + c];
+  if (use_svd) {
+    polar_orthogonal(Rd, Qd);
+    for (int k = 0; k < 9; ++k) Rp[k] = (float)Qd[k];
+  } else {
+    for (int k = 0; k < 9; ++k) Rp[k] = (float)Rd[k];
+  }
+  if (pred_fixed)
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c) pred_fixed[(size_t)i * 12 + r * 4 + c] = Rp[r * 3 + c];
+      pred_fixed[(size_t)i * 12 + r * 4 + 3] = p[r * 4 + 3];
+    }
+  float q1[4], q2[4];
+  mat_to_quat(Rg, q1), mat_to_quat(Rp, q2);
+  const float n1 = sqrtf(q1[0] * q1[0] + q1[1] * q1[1] + q1[2] * q1[2] + q1[3] * q1[3]);
+  const float n2 = sqrtf(q2[0] * q2[0] + q2[1] * q2[1] + q2[2] * q2[2] + q2[3] * q2[3]);
+  float d = 0.f;
+  for (int k = 0; k < 4; ++k) d += (q1[k] / n1) * (q2[k] / n2);
+  d = fminf(fmaxf(fabsf(d), -1.f), 1.f);
+  const float theta = 2.f * acosf(d) * 180.f / 3.14159265358979323846f;
+  const float dx = g[3] - p[3], dy = g[7] - p[7], dz = g[11] - p[11];
+  out[(size_t)i * 2 + 0] = sqrtf(dx * dx + dy * dy + dz * dz);
+  out[(size_t)i * 2 + 1] = theta;
+}
+
+}  // namespace dfb
+
+using namespace dfb;
+
+extern "C" int dfb_luma_hist(const float* img, int B, int H, int W, int bins, float* hist, void* ws, size_t ws_bytes,
+                             void* stream) {
+  DFB_REQUIRE(img && hist && ws && B >= 1 && H >= 1 && W >= 1, DFB_ERR_INVALID, "dfb_luma_hist: bad arguments");
+  DFB_REQUIRE(bins >= 1 && bins <= kMaxBins, DFB_ERR_INVALID, "dfb_luma_hist: 1 <= bins <= %d", kMaxBins);
+  DFB_REQUIRE((int64_t)H * W < (1 << 24), DFB_ERR_UNSUPPORTED, "dfb_luma_hist: images of 2^24 pixels or more");
+  DFB_REQUIRE(ws_bytes >= (size_t)B * bins * 4, DFB_ERR_WORKSPACE, "dfb_luma_hist: workspace needs B*bins*4 bytes");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned int* counts = (unsigned int*)ws;
+  DFB_CHECK_CUDA(cudaMemsetAsync(counts, 0, (size_t)B * bins * 4, st));
+  const int64_t plane = (int64_t)H * W;
+  const int gx = (int)std::min<int64_t>((plane + 255) / 256, 296);
+  k_luma_hist_count<<<dim3(gx, B), 256, 0, st>>>(img, plane, bins, counts);
+  DFB_LAUNCH_CHECK();
+  k_luma_hist_final<<<B, 64, 0, st>>>(counts, bins, hist);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+extern "C" int dfb_resize_area(const float* src, int H, int W, int C, int h, int w, float* dst, void* stream) {
+  DFB_REQUIRE(src && dst && H >= 1 && W >= 1 && C >= 1 && h >= 1 && w >= 1, DFB_ERR_INVALID, "dfb_resize_area: bad arguments");
+  DFB_REQUIRE(h <= H && w <= W, DFB_ERR_UNSUPPORTED, "dfb_resize_area: INTER_AREA is implemented for downscaling (cv2 switches to "
+                                                     "bilinear interpolation when enlarging)");
+  const int64_t total = (int64_t)h * w * C;
+  k_resize_area<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, H, W, C, h, w, dst);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+extern "C" int dfb_pose_error(const float* pred, const float* gt, int n, int use_svd, float* out, float* pred_fixed,
+                              void* stream) {
+  DFB_REQUIRE(pred && gt && out && n >= 0, DFB_ERR_INVALID, "dfb_pose_error: bad arguments");
+  if (n == 0) return DFB_OK;
+  k_pose_error<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(pred, gt, n, use_svd, out, pred_fixed);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}

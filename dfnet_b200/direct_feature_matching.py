@@ -139,3 +139,44 @@ def train_on_batch(args, data, model, feat_model, pose, img_idx, hwf, optimizer,
     with torch.no_grad():
         host = torch.stack([loss.detach().reshape(()), mse2psnr(img2mse(rgb.detach(), data)).reshape(())]).cpu().numpy()
     return np.array([host[0]]), host[1]
+
+
+def prepare_batch_render(args, pose, batch_size, target_, H, W, focal, half_res=True, rand=True):
+    """Reference feature/direct_feature_matching.py:144-176: a random batch of rays and their target colours from a batch
+    of images -> (batch_rays [2,N,3], target_s [N,3]).  Rays come from dfb_get_rays, the half-resolution targets from
+    dfb_resize_area (the reference round-trips through cv2.resize on the host), the selection is a gather on the device;
+    the permutation is drawn with torch.randperm on the CPU generator, as in the reference."""
+    from . import data as _data
+    from . import ops
+    dev = pose.device if pose.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    tgt = target_.to(dev).permute(0, 2, 3, 1).contiguous()   # [B,H,W,3]
+    if half_res:
+        N_rand = batch_size * (H // 2) * (W // 2)
+        # the reference passes dims=(H//2, W//2) to cv2.resize, i.e. (width, height) = (H//2, W//2) (:149)
+        tgt = torch.stack([_data.resize_area(tgt[i], (H // 2, W // 2)) for i in range(batch_size)], 0)
+        rh, rw, rf = H // 2, W // 2, focal / 2
+    else:
+        N_rand = args.N_rand
+        rh, rw, rf = H, W, focal
+    rays = torch.stack([torch.stack(ops.get_rays(rh, rw, rf, pose[i].to(dev)), 0) for i in range(batch_size)], 0)  # [B,2,h,w,3]
+    rays_rgb = torch.cat((rays, tgt[:, None, ...]), 1).permute(0, 2, 3, 1, 4).reshape(-1, 3, 3)
+    sel = torch.randperm(rays_rgb.shape[0])[:N_rand].to(dev)
+    batch = rays_rgb[sel].permute(1, 0, 2)
+    return batch[:2], batch[2]
+
+
+def eval_on_batch(args, data, model, feat_model, pose, img_idx, hwf, half_res, device, world_setup_dict, **render_kwargs_test):
+    """One evaluation step (reference feature/direct_feature_matching.py:178-213): pose loss of the regressor and the PSNR
+    of N_rand random rays rendered at the predicted pose -> (iter_loss [1], iter_psnr) numpy."""
+    with torch.no_grad():
+        H, W, focal = hwf
+        H, W = int(H), int(W)
+        data = data.to(device)
+        _, pose_ = inference_pose_regression(args, data, device, model)
+        pose_nerf = fix_coord_supp(args, pose_.clone(), world_setup_dict, device=device) if getattr(args, "NeRFH", True) else pose_.clone()
+        batch_rays, target = prepare_batch_render(args, pose_nerf, args.batch_size, data, H, W, focal, False)
+        rgb, _, _, _ = render(H, W, focal, chunk=args.chunk, rays=batch_rays, img_idx=img_idx.to(device), **render_kwargs_test)
+        loss = PoseLoss(args, pose_, pose.to(device), device)
+        psnr = mse2psnr(img2mse(rgb, target))
+        host = torch.stack([loss.reshape(()), psnr.reshape(())]).cpu().numpy()
+    return np.array([host[0]]), host[1]

@@ -154,3 +154,56 @@ def upsample_bilinear_ac(x, size):
     out = torch.empty(B, Cc, size[0], size[1], device=a.device)
     check(lib.dfb_resize_bilinear_ac(_p(a), B * Cc, h, w, size[0], size[1], _p(out), _stream()))
     return out
+
+
+def pose_errors(pred, gt, use_svd=True, return_fixed=False):
+    """dfb_pose_error: pred, gt [n,12] (or [n,3,4]) CUDA tensors -> [n,2] = (translation error, rotation error in
+    degrees); with return_fixed also the predicted poses with U V^T rotations."""
+    if not pred.is_cuda:
+        raise _lib.DfbError("pose_errors inputs must be CUDA tensors")
+    p = pred.detach().float().reshape(-1, 12).contiguous()
+    g = gt.detach().float().reshape(-1, 12).contiguous().to(p.device)
+    n = p.shape[0]
+    out = torch.empty(n, 2, device=p.device)
+    fixed = torch.empty(n, 12, device=p.device) if return_fixed else None
+    check(lib.dfb_pose_error(_p(p), _p(g), n, int(bool(use_svd)), _p(out), _p(fixed) if fixed is not None else None, _stream()))
+    return (out, fixed) if return_fixed else out
+
+
+def compute_error_in_q(args, dl, model, device, results, batch_size=1):
+    """Reference feature/misc.py:49-107 with the same arguments and return value (results [n,2] filled with
+    (metres, degrees); vis_info dict).  The reference pulls every prediction to the host, runs torch.svd and the
+    quaternion conversion per image; here the predictions stay on the device and ONE dfb_pose_error launch scores the
+    whole loader, followed by a single device-to-host copy."""
+    import numpy as np
+    preds, gts = [], []
+    with torch.no_grad():
+        for batch in dl:
+            data, pose = batch[0], batch[1]
+            _, predict_pose = model(data.to(device))
+            preds.append(predict_pose.reshape(-1, 12))
+            gts.append(pose.reshape(-1, 12))
+    if not preds:
+        return results, {"pose": np.zeros((0, 3)), "pose_gt": np.zeros((0, 3)), "theta": np.zeros((0,))}
+    pred, gt = torch.cat(preds, 0), torch.cat(gts, 0).to(device)
+    err, fixed = pose_errors(pred, gt, use_svd=True, return_fixed=True)
+    err_h = err.cpu().numpy()
+    n = err_h.shape[0]
+    results[:n, :] = err_h
+    vis_info_ret = {"pose": fixed.reshape(n, 3, 4)[:, :, 3].cpu().numpy(), "pose_gt": gt.reshape(n, 3, 4)[:, :, 3].cpu().numpy(),
+                    "theta": err_h[:, 1].copy()}
+    return results, vis_info_ret
+
+
+def get_error_in_q(args, dl, model, sample_size, device, batch_size=1):
+    """Reference feature/misc.py:110-124: median / mean translation and rotation error over the loader (printed in the
+    reference's format; also returned)."""
+    import numpy as np
+    model.eval()
+    results = np.zeros((sample_size, 2))
+    results, vis_info = compute_error_in_q(args, dl, model, device, results, batch_size)
+    median_result = np.median(results, axis=0)
+    mean_result = np.mean(results, axis=0)
+    print('Median error {}m and {} degrees.'.format(median_result[0], median_result[1]))
+    print('Mean error {}m and {} degrees.'.format(mean_result[0], mean_result[1]))
+    return median_result, mean_result

@@ -350,6 +350,22 @@ int dfb_resize_bilinear_ac_bwd(const float* g_dst, int64_t planes, int h, int w,
 int dfb_debug_umma_gemm_mn(const float* A, const float* B, int N, int K, int fmt_a, int fmt_b, int variant, float* D,
                            void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Data side and evaluation around the hot path
+ * ---------------------------------------------------------------------------------------------- */
+/* Luma histogram of the loaders (dataset_loaders/seven_scenes.py:346-352 with utils/color.py:29-35): img [B,3,H,W] fp32
+ * in [0,1] -> hist [B,bins] = round(histc(0.299 r + 0.587 g + 0.114 b, bins, 0, 1) / count * 100), the integer-valued
+ * percentages that index embedding_a / embedding_t.  ws: B*bins*4 bytes. */
+int dfb_luma_hist(const float* img, int B, int H, int W, int bins, float* hist, void* ws, size_t ws_bytes, void* stream);
+/* cv2.resize(img, (w, h), interpolation=cv2.INTER_AREA) of an HWC fp32 image, downscaling only
+ * (dataset_loaders/seven_scenes.py:328-332, feature/direct_feature_matching.py:149). */
+int dfb_resize_area(const float* src, int H, int W, int C, int h, int w, float* dst, void* stream);
+/* compute_error_in_q (feature/misc.py:49-107) for n pose pairs at once: pred, gt [n,12] row-major 3x4; use_svd: the
+ * predicted rotation is replaced by U V^T first (:70-77).  out [n,2] = {|t_gt - t_pred|, angle between the rotations
+ * in degrees via quaternions (pytorch3d 0.3.0 matrix_to_quaternion)}; pred_fixed [n,12] (nullable): the predicted
+ * pose with the orthogonalised rotation. */
+int dfb_pose_error(const float* pred, const float* gt, int n, int use_svd, float* out, float* pred_fixed, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
