@@ -19,7 +19,7 @@ SYMBOLS = [
     "dfb_cosine_loss", "dfb_triplet_loss", "dfb_triplet_loss_bwd", "dfb_mse", "dfb_resize_bicubic", "dfb_resize_bilinear_ac",
     "dfb_conv_create_ex", "dfb_conv_fwd_ex", "dfb_conv_wgrad", "dfb_dfnet_load_ex", "dfb_dfnet_bn_batch_stats", "dfb_dfnet_tape_bytes", "dfb_debug_dfnet_tape_layout",
     "dfb_dfnet_bwd_workspace_bytes", "dfb_dfnet_bwd", "dfb_cosine_loss_bwd", "dfb_mse_bwd", "dfb_resize_bicubic_bwd",
-    "dfb_resize_bilinear_ac_bwd", "dfb_dfnet_bwd_bucket_event", "dfb_luma_hist", "dfb_resize_area", "dfb_pose_error",
+    "dfb_resize_bilinear_ac_bwd", "dfb_dfnet_bwd_bucket_event", "dfb_luma_hist", "dfb_resize_area", "dfb_pose_error", "dfb_debug_conv_prof",
 ]
 
 MMA_FP32_SIMT, MMA_F16, MMA_BF16, MMA_F16_SPLIT_COARSE = 0, 1, 2, 3
@@ -103,6 +103,7 @@ def _load():
     lib.dfb_dfnet_bwd.argtypes = [vp, i32, i32, i32, C.c_uint32, i32, i32, vp, vp, C.c_uint32, vp, vp, vp, C.POINTER(vp), i32,
                                   vp, C.c_size_t, vp]
     lib.dfb_dfnet_bwd_bucket_event.argtypes = [vp, i32, vp]
+    lib.dfb_debug_conv_prof.argtypes = [i32, vp, i32, C.POINTER(i32)]
     lib.dfb_luma_hist.argtypes = [vp, i32, i32, i32, i32, vp, vp, C.c_size_t, vp]
     lib.dfb_resize_area.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
     lib.dfb_pose_error.argtypes = [vp, vp, i32, i32, vp, vp, vp]

@@ -1,5 +1,6 @@
 // Internal shared declarations for libdfnet_b200 (not part of the public ABI).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
@@ -139,6 +140,8 @@ inline int composite_part_k(int S) { return (S + 30) / 32 + 1; }
 int launch_composite_partials(const float* part, int part_k, int64_t n_rays, int S, float* rgb, float* disp, float* acc,
                               cudaStream_t st);
 bool tc_supported(const DfbNerf* nerf, int which, int mode);
+// 3-D tensor map over a packed image of 16 KB chunks: [n][64][128 x u16], one box = one chunk (2-SM TMA weight loads)
+int make_weight_tmap(void* base, size_t bytes, CUtensorMap* out);
 // Networks narrower than 256 run on the 256-wide tcgen05 kernels EXACTLY, embedded with zero weights / zero biases
 // (a ReLU unit with zero input weights and bias stays at 0 and feeds nothing): tc_pad_params returns the state dict
 // of the equivalent 8x256 network (state-dict order, hidden units 0..W-1 / 0..W/2-1 live).

@@ -21,6 +21,9 @@
 #include <algorithm>
 #include <vector>
 
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -30,13 +33,20 @@ namespace conv {
 using namespace dfb::tc;
 
 constexpr int kTH = 16, kTW = 8;  // pixel patch of one M tile (128 pixels)
-constexpr int kBStages = 4;       // weight ring
-constexpr int kAStages = 2;       // patch ring
+constexpr int kBStages = 4;       // weight ring (1-CTA kernel: 32 KB stages)
+constexpr int kBStages2 = 8;      // weight ring of the cta_group::2 kernel (16 KB half-stages per CTA)
+constexpr int kAStages = 3;       // patch ring
 constexpr int kThreads = 320;
 
-enum Bar { A_FULL = 0, A_EMPTY = 2, B_FULL = 4, B_EMPTY = 8, D_FULL = 12, D_EMPTY = 14, N_BARS = 16 };
+enum Bar { A_FULL = 0, A_EMPTY = 4, B_FULL2 = 8, B_EMPTY2 = 16, D_FULL2 = 24, D_EMPTY2 = 26, N_BARS2 = 28 };
 
 struct ConvArgs {
+  // cta_group::2 only: 3-D tensor map over the pair-layout weight image ([half-stages][64 rows][256 B] = 16 KB boxes)
+  alignas(64) CUtensorMap tmap;
+  // input patches: 5-D tensor map over the NHWC input seen as [B][C/8 panels][H][W][8 channels] (dims innermost first:
+  // 8 ch, W, H, panel, B), box = [1][8 panels][PH][PW][8 ch] = exactly the shared-memory patch image
+  // [panel][patch row][patch col][16 B]; the halo outside the image is zero-filled by the TMA unit
+  alignas(64) CUtensorMap tmap_in;
   const __half* in;   // NHWC [B,H,W,Cin]
   const uint8_t* wimg;
   const float* bias;  // [Cout]
@@ -58,7 +68,11 @@ struct ConvArgs {
   int tps;            // filter taps per weight stage (256 / nt): narrow layers get more MMA work per stage
   int n_wst;          // weight stages per channel slice = ceil(KH*KW / tps)
   int* error_flag;
+  unsigned long long* prof;  // optional [gridDim.x][8] cycle counters (dfb_debug_conv_prof): issuer waits D_EMPTY / A_FULL /
+                             // B_FULL / total, epilogue wait D_FULL / total, loader wait A_EMPTY, producer wait B_EMPTY
 };
+
+#define CPROF(slot, stmt) { const long long _t = clock64(); stmt; if (a.prof) pacc[slot] += clock64() - _t; }
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -142,134 +156,147 @@ __device__ __forceinline__ void epi_store(const ConvArgs& a, const uint32_t (&v)
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__ ConvArgs a) {
+// CG = 2 (cta_group::2): the two CTAs of a cluster work on two neighbouring 128-pixel M tiles with ONE weight stream:
+// each CTA holds half of every weight stage (its nt/2 rows of B, a 16 KB image loaded by a 2-SM TMA that credits the
+// leader's barrier), the leader issues tcgen05.mma.cta_group::2 (M = 256) for the pair and tcgen05.commit multicasts
+// the stage / accumulator hand-offs to both CTAs.  Per SM the L2 -> shared-memory weight traffic halves (the 1-CTA
+// kernel streams 295 KB of filter per 4608 tensor cycles at 256 channels: 64 B/clk/SM, which is what bounds it) and
+// the ring holds twice as many stages in the same shared memory.
+template <typename T, int CG>
+__device__ __forceinline__ void conv_tc_body(const ConvArgs& a) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int NB = CG == 2 ? kBStages2 : kBStages;
   const int nt = a.nt;
+  const uint32_t b_stage = a.b_bytes / CG;   // bytes of a weight stage held by this CTA
   const uint32_t sA = smem_u32(smem);
   const uint32_t sB = sA + kAStages * a.a_bytes;
-  const uint32_t sBar = sB + kBStages * a.b_bytes;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kAStages * a.a_bytes + kBStages * a.b_bytes + N_BARS * 8);
+  const uint32_t sBar = sB + NB * b_stage;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kAStages * a.a_bytes + NB * b_stage + N_BARS2 * 8);
   const int tid = threadIdx.x, warp = tid >> 5;
   auto bar = [&](int i) { return sBar + 8u * i; };
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
 
   if (tid == 0) {
-    for (int i = 0; i < kAStages; ++i) mbar_init(bar(A_FULL + i), 128), mbar_init(bar(A_EMPTY + i), 1);
-    for (int i = 0; i < kBStages; ++i) mbar_init(bar(B_FULL + i), 1), mbar_init(bar(B_EMPTY + i), 1);
-    for (int i = 0; i < 2; ++i) mbar_init(bar(D_FULL + i), 1), mbar_init(bar(D_EMPTY + i), 128);
+    for (int i = 0; i < kAStages; ++i) mbar_init(bar(A_FULL + i), 1), mbar_init(bar(A_EMPTY + i), 1);
+    for (int i = 0; i < NB; ++i) mbar_init(bar(B_FULL2 + i), 1), mbar_init(bar(B_EMPTY2 + i), 1);
+    for (int i = 0; i < 2; ++i) mbar_init(bar(D_FULL2 + i), 1), mbar_init(bar(D_EMPTY2 + i), 128 * CG);
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc<1>(smem_u32(tmem_slot), 512);
+  if (warp == 9) tmem_alloc<CG>(smem_u32(tmem_slot), 512);
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int tiles_img = a.tiles_x * a.tiles_y;
   const int n_mtiles = tiles_img * a.B;
-  const int n_tiles = n_mtiles * a.n_ntiles;
+  // a "tile" of the schedule = CG neighbouring M tiles x one N tile; this CTA's M tile is CG * (t / n_ntiles) + rank
+  const int n_tiles = ((n_mtiles + CG - 1) / CG) * a.n_ntiles;
   const int n_taps = a.KH * a.KW;
   const uint32_t panel_stride = (uint32_t)a.PH * a.PW * 16u;
+  const int unit0 = blockIdx.x / CG, n_units = gridDim.x / CG;
 
-  if (warp >= 4 && warp < 8) {
-    // ===== patch loader: [panel][patch row][patch col][16 B] for every 64-channel slice =========
-    const int lt = tid - 128;
-    const int c8l = lt & 7;          // panel within the slice: 8 consecutive threads = 128 contiguous bytes
-    const int e0 = lt >> 3;          // first patch entry of this thread (16 entries per pass)
-    const int n_ent = a.PH * a.PW;
-    // flat sequence over (tile, channel slice) so that the next patch (also the next tile's) loads
-    // while the tensor pipe works on the current one
+  if (warp == 4) {
+    // ===== patch loader: ONE TMA box per 64-channel slice (patch + halo, zero-filled outside the image) ============
+    // (the first version gathered the patch with 16-byte cp.async from 128 threads: ~600 address-arithmetic instructions
+    // per thread and slice, and the MMA issuer waited 28-48 % of its time for patches, 70 % on the 1x1 layers)
+    long long pacc[4] = {0, 0, 0, 0};
     uint32_t seq = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-      const int mt = t / a.n_ntiles;
-      const int b = mt / tiles_img, ti = mt % tiles_img;
+    for (int t = unit0; t < n_tiles; t += n_units) {
+      const int mt = CG * (t / a.n_ntiles) + (int)rank;
+      const bool mt_ok = mt < n_mtiles;   // the last pair of an odd tile count: this CTA's half is empty
+      const int b = mt_ok ? mt / tiles_img : a.B, ti = mt_ok ? mt % tiles_img : 0;   // b == B: wholly out of bounds -> zeros
       const int y0 = (ti / a.tiles_x) * kTH - a.pad, x0 = (ti % a.tiles_x) * kTW - a.pad;
-      const __half* base = a.in + ((int64_t)b * a.H * a.W) * a.Cin;
       for (int cc = 0; cc < a.n_cc; ++cc, ++seq) {
         const uint32_t st = seq % kAStages, ph = (seq / kAStages) & 1;
-        mbar_wait(bar(A_EMPTY + st), ph ^ 1, a.error_flag);
-        const int c8 = cc * 8 + c8l;
-        const bool cok = c8 < a.cpp;
-        const uint32_t dst0 = sA + st * a.a_bytes + c8l * panel_stride;
-        for (int e = e0; e < n_ent; e += 16) {
-          const int pr = e / a.PW, pc = e - pr * a.PW;
-          const int yy = y0 + pr, xx = x0 + pc;
-          const bool ok = cok && yy >= 0 && yy < a.H && xx >= 0 && xx < a.W;
-          const __half* src = ok ? base + ((int64_t)yy * a.W + xx) * a.Cin + c8 * 8 : a.in;
-          cp_async16(dst0 + e * 16, src, ok ? 16u : 0u);
-        }
-        cp_async_commit();
-        if (seq >= 1) {
-          cp_async_wait<1>();
-          fence_proxy_async();
-          mbar_arrive(bar(A_FULL + (seq - 1) % kAStages));
-        }
-      }
-    }
-    if (seq >= 1) {
-      cp_async_wait<0>();
-      fence_proxy_async();
-      mbar_arrive(bar(A_FULL + (seq - 1) % kAStages));
-    }
-  } else if (warp == 8) {
-    // ===== weight producer: one stage = one tap of one channel slice ============================
-    uint32_t it = 0;
-    const int per_tile = a.n_cc * a.n_wst;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-      const int ntile = t % a.n_ntiles;
-      const uint8_t* src = a.wimg + (size_t)ntile * per_tile * a.b_bytes;
-      for (int c = 0; c < per_tile; ++c, ++it) {
-        const uint32_t stage = it % kBStages, ph = (it / kBStages) & 1;
-        mbar_wait(bar(B_EMPTY + stage), ph ^ 1, a.error_flag);
+        CPROF(0, mbar_wait(bar(A_EMPTY + st), ph ^ 1, a.error_flag));
         if (elect_one()) {
-          mbar_expect_tx(bar(B_FULL + stage), a.b_bytes);
-          bulk_g2s(sB + stage * a.b_bytes, src + (size_t)c * a.b_bytes, a.b_bytes, bar(B_FULL + stage));
+          if (CG == 1) {
+            mbar_expect_tx(bar(A_FULL + st), a.a_bytes);
+            tma_load_5d<1>(sA + st * a.a_bytes, &a.tmap_in, 0, x0, y0, cc * 8, b, bar(A_FULL + st));
+          } else {
+            const uint32_t bar_leader = bar(A_FULL + st) & 0xFEFFFFFFu;
+            if (rank == 0) mbar_expect_tx(bar(A_FULL + st), 2 * a.a_bytes);
+            tma_load_5d<2>(sA + st * a.a_bytes, &a.tmap_in, 0, x0, y0, cc * 8, b, bar_leader);
+          }
         }
         __syncwarp();
       }
     }
+    if (a.prof && (tid & 31) == 0) a.prof[blockIdx.x * 8 + 6] = pacc[0];
+  } else if (warp == 8) {
+    // ===== weight producer: one stage = tps taps of one channel slice ==============================
+    uint32_t it = 0;
+    long long pacc[4] = {0, 0, 0, 0};
+    const int per_tile = a.n_cc * a.n_wst;
+    for (int t = unit0; t < n_tiles; t += n_units) {
+      const int ntile = t % a.n_ntiles;
+      const uint8_t* src = a.wimg + (size_t)ntile * per_tile * a.b_bytes;
+      for (int c = 0; c < per_tile; ++c, ++it) {
+        const uint32_t stage = it % NB, ph = (it / NB) & 1;
+        CPROF(0, mbar_wait(bar(B_EMPTY2 + stage), ph ^ 1, a.error_flag));
+        if (elect_one()) {
+          if (CG == 1) {
+            mbar_expect_tx(bar(B_FULL2 + stage), a.b_bytes);
+            bulk_g2s(sB + stage * b_stage, src + (size_t)c * a.b_bytes, a.b_bytes, bar(B_FULL2 + stage));
+          } else {
+            // the leader arms ITS barrier with both halves' bytes; every CTA loads its own 16 KB half with a 2-SM TMA
+            // whose completion is credited to the leader's barrier
+            const uint32_t bar_leader = bar(B_FULL2 + stage) & 0xFEFFFFFFu;
+            if (rank == 0) mbar_expect_tx(bar(B_FULL2 + stage), a.b_bytes);
+            tma_load_img_2sm(sB + stage * b_stage, &a.tmap, (ntile * per_tile + c) * 2 + (int)rank, bar_leader);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (a.prof && (tid & 31) == 0) a.prof[blockIdx.x * 8 + 7] = pacc[0];
   } else if (warp == 9) {
-    // ===== MMA issuer =============================================================================
-    const uint32_t idesc = make_idesc(std::is_same<T, __nv_bfloat16>::value ? 1 : 0, nt, 128);
-    // A: SBO = patch row pitch, LBO = panel stride.  B: SBO = 128 B, LBO = nt*16 B.
+    // ===== MMA issuer (the leader CTA issues for the pair) ===========================================
+    if (rank == 0) {
+    const uint32_t idesc = make_idesc(std::is_same<T, __nv_bfloat16>::value ? 1 : 0, nt, 128 * CG);
+    // A: SBO = patch row pitch, LBO = panel stride.  B: SBO = 128 B, LBO = rows held by a CTA * 16 B.
+    const uint32_t b_rows = (uint32_t)nt / CG;
     const uint32_t a_hi = ((uint32_t)(a.PW * 16) >> 4) | (1u << 14);
     const uint32_t b_hi = (128u >> 4) | (1u << 14);
-    const uint32_t a_lbo = (panel_stride >> 4) << 16, b_lbo = (uint32_t)nt << 16;
-    const uint32_t b_step = 2u * nt;                  // two weight panels per K=16 step
+    const uint32_t a_lbo = (panel_stride >> 4) << 16, b_lbo = b_rows << 16;
+    const uint32_t b_step = 2u * b_rows;               // two weight panels per K=16 step
     const uint32_t a_step = 2u * (panel_stride >> 4);  // two patch panels per K=16 step
     uint32_t ita = 0, itb = 0, tl = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tl) {
+    long long pacc[4] = {0, 0, 0, 0};
+    const long long t_start = clock64();
+    for (int t = unit0; t < n_tiles; t += n_units, ++tl) {
       const uint32_t buf = tl & 1;
-      mbar_wait(bar(D_EMPTY + buf), ((tl >> 1) & 1) ^ 1, a.error_flag);
+      CPROF(0, mbar_wait_cluster<CG>(bar(D_EMPTY2 + buf), ((tl >> 1) & 1) ^ 1, a.error_flag));
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + buf * 256;
       uint32_t acc = 0;
       for (int cc = 0; cc < a.n_cc; ++cc, ++ita) {
         const uint32_t ast = ita % kAStages, aph = (ita / kAStages) & 1;
-        mbar_wait(bar(A_FULL + ast), aph, a.error_flag);
+        CPROF(1, mbar_wait_cluster<CG>(bar(A_FULL + ast), aph, a.error_flag));
         const int np = min(8, a.cpp - cc * 8);
         const int ks_n = (np + 1) >> 1;
         const uint32_t patch = (sA + ast * a.a_bytes) >> 4;
         for (int ws = 0; ws < a.n_wst; ++ws, ++itb) {
-          const uint32_t stage = itb % kBStages, ph = (itb / kBStages) & 1;
-          mbar_wait(bar(B_FULL + stage), ph, a.error_flag);
+          const uint32_t stage = itb % NB, ph = (itb / NB) & 1;
+          CPROF(2, mbar_wait_cluster<CG>(bar(B_FULL2 + stage), ph, a.error_flag));
           tc_fence_after();
           const int tp0 = ws * a.tps, tpn = min(a.tps, n_taps - tp0);
-          const uint32_t b_lo0 = ((sB + stage * a.b_bytes) >> 4) | b_lbo;
+          const uint32_t b_lo0 = ((sB + stage * b_stage) >> 4) | b_lbo;
           if (elect_one()) {
             for (int tt = 0; tt < tpn; ++tt) {
               const int tp = tp0 + tt, ky = tp / a.KW, kx = tp - ky * a.KW;
               const uint32_t a_lo = (patch + (uint32_t)(ky * a.PW + kx)) | a_lbo;
-              const uint32_t b_lo = b_lo0 + (uint32_t)tt * 8u * nt;  // 8 panels * nt*16 B per tap, in 16 B units
+              const uint32_t b_lo = b_lo0 + (uint32_t)tt * 8u * b_rows;  // 8 panels * b_rows*16 B per tap, in 16 B units
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
                 if (ks < ks_n)
-                  umma_f16<1>(d_tmem, mk64(a_lo + ks * a_step, a_hi), mk64(b_lo + ks * b_step, b_hi), idesc, acc | (uint32_t)(tt | ks));
+                  umma_f16<CG>(d_tmem, mk64(a_lo + ks * a_step, a_hi), mk64(b_lo + ks * b_step, b_hi), idesc, acc | (uint32_t)(tt | ks));
               acc = 1;
             }
-            umma_commit<1>(bar(B_EMPTY + stage));
+            umma_commit<CG>(bar(B_EMPTY2 + stage));
             if (ws == a.n_wst - 1) {
-              umma_commit<1>(bar(A_EMPTY + ast));
-              if (cc == a.n_cc - 1) umma_commit<1>(bar(D_FULL + buf));
+              umma_commit<CG>(bar(A_EMPTY + ast));
+              if (cc == a.n_cc - 1) umma_commit<CG>(bar(D_FULL2 + buf));
             }
           }
           __syncwarp();
@@ -277,18 +304,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
         }
       }
     }
+    if (a.prof && (tid & 31) == 0) {
+      for (int i = 0; i < 3; ++i) a.prof[blockIdx.x * 8 + i] = pacc[i];
+      a.prof[blockIdx.x * 8 + 3] = clock64() - t_start;
+    }
+    }
   } else if (warp < 4) {
     // ===== epilogue (thread = pixel of the 16x8 patch) ===============================================
     const int r = tid;
     uint32_t tl = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tl) {
+    long long pacc[4] = {0, 0, 0, 0};
+    const long long t_start = clock64();
+    for (int t = unit0; t < n_tiles; t += n_units, ++tl) {
       const uint32_t buf = tl & 1;
-      const int mt = t / a.n_ntiles, n0 = (t % a.n_ntiles) * nt;
-      const int b = mt / tiles_img, ti = mt % tiles_img;
+      const int mt = CG * (t / a.n_ntiles) + (int)rank, n0 = (t % a.n_ntiles) * nt;
+      const bool mt_ok = mt < n_mtiles;
+      const int b = mt_ok ? mt / tiles_img : 0, ti = mt_ok ? mt % tiles_img : 0;
       const int y = (ti / a.tiles_x) * kTH + (r >> 3), x = (ti % a.tiles_x) * kTW + (r & 7);
-      const bool valid = y < a.H && x < a.W;
+      const bool valid = mt_ok && y < a.H && x < a.W;
       const int64_t m = ((int64_t)b * a.H + y) * a.W + x;
-      mbar_wait(bar(D_FULL + buf), (tl >> 1) & 1, a.error_flag);
+      CPROF(0, mbar_wait(bar(D_FULL2 + buf), (tl >> 1) & 1, a.error_flag));
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 256;
       const int64_t plane = (int64_t)a.H * a.W;
@@ -305,15 +340,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
         epi_store<T>(a, v1, m, valid, n0 + (cb + 1) * 32, nchw_base, plane);
       }
       tc_fence_before();
-      mbar_arrive(bar(D_EMPTY + buf));
+      arrive_leader<CG>(bar(D_EMPTY2 + buf));
     }
+    if (a.prof && tid == 0) a.prof[blockIdx.x * 8 + 4] = pacc[0], a.prof[blockIdx.x * 8 + 5] = clock64() - t_start;
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync(); else __syncthreads();
   if (warp == 9) {
     tc_fence_after();
-    tmem_dealloc<1>(tmem_base, 512);
+    tmem_dealloc<CG>(tmem_base, 512);
   }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__ ConvArgs a) {
+  conv_tc_body<T, 1>(a);
+}
+
+template <typename T>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant__ ConvArgs a) {
+  conv_tc_body<T, 2>(a);
 }
 
 }  // namespace conv
@@ -330,6 +376,7 @@ struct DfbConv {
   int nchw_C = 0;  // channels of the fp32 NCHW output (real output channels)
   size_t wimg_bytes = 0;
   uint8_t* wimg = nullptr;
+  uint8_t* wimg2 = nullptr;  // the same filter in the cta_group::2 layout: every stage split into the two CTAs' row halves
   float* bias = nullptr;
   int num_sms = 0;
 };
@@ -349,6 +396,7 @@ struct PackArgs {
   uint16_t* img;
   float* bias;      // [Cout] folded bias of this launch
   int Cin0, Cout0, KH, KW, Cin, Cout, nt, n_ntiles, n_cc, tps, n_wst, fmt, dgrad;
+  int cg;           // 1: [..][tap in stage][8 panels][nt rows][8]; 2: [..][row half][tap in stage][8 panels][nt/2 rows][8]
   int64_t total;    // elements of the image
 };
 
@@ -366,9 +414,11 @@ __global__ void k_pack_conv_weights(const PackArgs a) {
   if (i >= a.total) return;
   int64_t r = i;
   const int e = (int)(r % 8); r /= 8;
-  const int rr = (int)(r % a.nt); r /= a.nt;
+  const int rows = a.nt / a.cg;
+  int rr = (int)(r % rows); r /= rows;
   const int pp = (int)(r % 8); r /= 8;
   const int tis = (int)(r % a.tps); r /= a.tps;
+  if (a.cg == 2) { rr += (int)(r % 2) * rows; r /= 2; }
   const int ws = (int)(r % a.n_wst); r /= a.n_wst;
   const int cc = (int)(r % a.n_cc); r /= a.n_cc;
   const int t = (int)r;
@@ -423,8 +473,14 @@ int dfb_conv_update_impl(DfbConv* c, const float* weight, const float* bias, con
   a.Cin0 = c->Cin0, a.Cout0 = c->Cout0, a.KH = c->KH, a.KW = c->KW, a.Cin = c->Cin, a.Cout = c->Cout, a.nt = c->nt;
   a.n_ntiles = c->n_ntiles, a.n_cc = c->n_cc, a.tps = c->tps, a.n_wst = c->n_wst, a.fmt = c->fmt, a.dgrad = c->dgrad;
   a.total = (int64_t)c->wimg_bytes / 2;
+  a.cg = 1;
   conv::k_pack_conv_weights<<<(unsigned)((a.total + 255) / 256), 256, 0, st>>>(a);
   DFB_LAUNCH_CHECK();
+  if (c->wimg2) {
+    a.img = (uint16_t*)c->wimg2, a.cg = 2;
+    conv::k_pack_conv_weights<<<(unsigned)((a.total + 255) / 256), 256, 0, st>>>(a);
+    DFB_LAUNCH_CHECK();
+  }
   if (stage) DFB_CHECK_CUDA(cudaFreeAsync(stage, st));
   return DFB_OK;
 }
@@ -466,7 +522,8 @@ int dfb_conv_create_impl(int Cin0, int Cout0, int KH, int KW, const float* weigh
   c->n_wst = (KH * KW + c->tps - 1) / c->tps;
   c->num_sms = sms;
   c->wimg_bytes = (size_t)c->n_ntiles * c->n_cc * c->n_wst * c->tps * c->nt * 16 * 8;
-  if (cudaMalloc(&c->wimg, c->wimg_bytes) != cudaSuccess || cudaMalloc(&c->bias, Cout * 4) != cudaSuccess) {
+  if (cudaMalloc(&c->wimg, c->wimg_bytes) != cudaSuccess || cudaMalloc(&c->wimg2, c->wimg_bytes) != cudaSuccess ||
+      cudaMalloc(&c->bias, Cout * 4) != cudaSuccess) {
     dfb_conv_destroy(c);
     DFB_REQUIRE(false, DFB_ERR_CUDA, "dfb_conv_create: out of device memory");
   }
@@ -485,6 +542,7 @@ extern "C" int dfb_conv_create(int Cin, int Cout, int KH, int KW, const float* w
 extern "C" void dfb_conv_destroy(DfbConv* c) {
   if (!c) return;
   if (c->wimg) cudaFree(c->wimg);
+  if (c->wimg2) cudaFree(c->wimg2);
   if (c->bias) cudaFree(c->bias);
   delete c;
 }
@@ -495,6 +553,46 @@ int dfb_conv_run(DfbConv* c, const void* in_nhwc16, int B, int H, int W, int rel
 extern "C" int dfb_conv_fwd(DfbConv* c, const void* in_nhwc16, int B, int H, int W, int relu, void* out_nhwc16,
                             void* tap_nhwc16, float* out_nchw32, void* stream) {
   return dfb_conv_run(c, in_nhwc16, B, H, W, relu, out_nhwc16, tap_nhwc16, out_nchw32, nullptr, nullptr, stream);
+}
+
+// 5-D tensor map over the NHWC 16-bit input for the patch loads of k_conv_tc (see ConvArgs::tmap_in).
+static int make_patch_tmap(const void* in, int B, int H, int W, int Cpad, int PH, int PW, CUtensorMap* out) {
+  static PFN_cuTensorMapEncodeTiled encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    DFB_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    DFB_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, DFB_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    encode = (PFN_cuTensorMapEncodeTiled)fn;
+  }
+  DFB_REQUIRE(((uintptr_t)in & 15) == 0 && Cpad % 8 == 0, DFB_ERR_INVALID, "conv input must be 16-byte aligned NHWC with C % 8 == 0");
+  const cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cpad / 8), (cuuint64_t)B};
+  const cuuint64_t strides[4] = {(cuuint64_t)Cpad * 2, (cuuint64_t)W * Cpad * 2, 16, (cuuint64_t)H * W * Cpad * 2};
+  const cuuint32_t box[5] = {8, (cuuint32_t)PW, (cuuint32_t)PH, 8, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, const_cast<void*>(in), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DFB_REQUIRE(r == CUDA_SUCCESS, DFB_ERR_CUDA, "cuTensorMapEncodeTiled (conv input, %dx%dx%dx%d) failed (%d)", B, H, W, Cpad, (int)r);
+  return DFB_OK;
+}
+
+static unsigned long long* g_conv_prof = nullptr;  // dfb_debug_conv_prof: counters of the LAST conv launch
+static int g_conv_prof_grid = 0;
+
+// Debug seam (tools/conv_prof.py): on != 0 makes every following conv launch record per-CTA cycle counters
+// ([cta][8]: issuer waits D_EMPTY, A_FULL, B_FULL, issuer total, epilogue wait D_FULL, epilogue total, loader wait
+// A_EMPTY, producer wait B_EMPTY); out_host (nullable) receives the counters of the last launch, *grid its CTA count.
+extern "C" int dfb_debug_conv_prof(int on, unsigned long long* out_host, int max_cta, int* grid) {
+  if (on && !g_conv_prof) DFB_CHECK_CUDA(cudaMalloc(&g_conv_prof, 512 * 8 * sizeof(unsigned long long)));
+  if (!on && g_conv_prof && !out_host) { cudaFree(g_conv_prof); g_conv_prof = nullptr; }
+  if (out_host && g_conv_prof) {
+    DFB_CHECK_CUDA(cudaDeviceSynchronize());
+    const int n = std::min(max_cta, g_conv_prof_grid);
+    DFB_CHECK_CUDA(cudaMemcpy(out_host, g_conv_prof, (size_t)n * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (grid) *grid = n;
+  }
+  return DFB_OK;
 }
 
 int dfb_conv_run(DfbConv* c, const void* in_nhwc16, int B, int H, int W, int relu, void* out_nhwc16, void* tap_nhwc16,
@@ -518,20 +616,39 @@ int dfb_conv_run(DfbConv* c, const void* in_nhwc16, int B, int H, int W, int rel
   a.b_bytes = (uint32_t)c->nt * 16u * 8u * (uint32_t)c->tps;
   a.tps = c->tps, a.n_wst = c->n_wst;
   a.error_flag = error_flag;
-  const int64_t n_tiles = (int64_t)a.tiles_x * a.tiles_y * B * a.n_ntiles;
-  DFB_REQUIRE(n_tiles < (1ll << 30), DFB_ERR_INVALID, "image too large");
-  const int grid = (int)std::min<int64_t>(n_tiles, c->num_sms);
-  const size_t smem = (size_t)conv::kAStages * a.a_bytes + (size_t)conv::kBStages * a.b_bytes + 256;
+  const int64_t n_mtiles = (int64_t)a.tiles_x * a.tiles_y * B;
+  DFB_REQUIRE(n_mtiles * a.n_ntiles < (1ll << 30), DFB_ERR_INVALID, "image too large");
+  // DFB_CONV_CTA_GROUP=2 selects the cta_group::2 kernel (CTA pairs share every weight stage).  Measured (r02, tools/
+  // conv_prof.py): with TMA patch loads both kernels wait < 15 % for operands and run the 3x3 / 5x5 layers at the same
+  // speed; the pair kernel is slower on the epilogue-bound layers (conv1_1, 1x1), so the 1-CTA kernel is the default.
+  static const int cg_env = [] { const char* e = getenv("DFB_CONV_CTA_GROUP"); return (e && e[0] == '2') ? 2 : 1; }();
+  const int cg = (c->wimg2 && n_mtiles >= 2) ? cg_env : 1;
+  const int64_t n_tiles = ((n_mtiles + cg - 1) / cg) * a.n_ntiles;
+  const int grid = cg * (int)std::min<int64_t>(n_tiles, c->num_sms / cg);
+  const int nb = cg == 2 ? conv::kBStages2 : conv::kBStages;
+  const size_t smem = (size_t)conv::kAStages * a.a_bytes + (size_t)nb * (a.b_bytes / cg) + 256;
   DFB_REQUIRE(smem <= 232448, DFB_ERR_UNSUPPORTED, "shared memory budget exceeded");
-  if (c->fmt) {
-    DFB_CHECK_CUDA(cudaFuncSetAttribute(conv::k_conv_tc<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv::k_conv_tc<__nv_bfloat16><<<grid, conv::kThreads, smem, (cudaStream_t)stream>>>(a);
-  } else {
-    DFB_CHECK_CUDA(cudaFuncSetAttribute(conv::k_conv_tc<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv::k_conv_tc<__half><<<grid, conv::kThreads, smem, (cudaStream_t)stream>>>(a);
+  if (cg == 2) {
+    a.wimg = c->wimg2;
+    const int rc = make_weight_tmap(c->wimg2, c->wimg_bytes, &a.tmap);
+    if (rc) return rc;
   }
-  DFB_LAUNCH_CHECK();
-  return DFB_OK;
+  {
+    const int rc = make_patch_tmap(in_nhwc16, B, H, W, c->Cin_pad, a.PH, a.PW, &a.tmap_in);
+    if (rc) return rc;
+  }
+  if (g_conv_prof) {
+    DFB_CHECK_CUDA(cudaMemsetAsync(g_conv_prof, 0, 512 * 8 * sizeof(unsigned long long), (cudaStream_t)stream));
+    a.prof = g_conv_prof, g_conv_prof_grid = grid;
+  }
+  auto launch = [&](auto kern) -> int {
+    DFB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, conv::kThreads, smem, (cudaStream_t)stream>>>(a);
+    DFB_LAUNCH_CHECK();
+    return DFB_OK;
+  };
+  if (cg == 2) return c->fmt ? launch(conv::k_conv_tc2<__nv_bfloat16>) : launch(conv::k_conv_tc2<__half>);
+  return c->fmt ? launch(conv::k_conv_tc<__nv_bfloat16>) : launch(conv::k_conv_tc<__half>);
 }
 
 extern "C" int dfb_conv_create_ex(int Cin, int Cout, int KH, int KW, const float* weight, const float* bias, const float* bn_scale,

@@ -334,15 +334,6 @@ __device__ __forceinline__ void epi_blocks_x3(uint32_t t_row, uint32_t h_row, co
 
 // MMA issue for one (step, slot): KS K=16 MMAs per weight stage.  Kept as lean as possible:
 // this single warp paces the tensor pipe.
-// 2-SM TMA load of one 16 KB weight image (box [1][64][128 x 16-bit]) into this CTA's shared memory;
-// the transaction bytes are credited to the barrier at `bar_leader` in the LEADER CTA's shared memory.
-__device__ __forceinline__ void tma_load_img_2sm(uint32_t dst, const CUtensorMap* tmap, int img, uint32_t bar_leader) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_leader), "r"(0), "r"(0), "r"(img)
-      : "memory");
-}
-
 template <int CG, int KS>
 __device__ __forceinline__ void issue_step(uint32_t& stage, uint32_t& phase, int nch, uint32_t a_lo, uint32_t b_rows,
                                            uint32_t d_tmem, uint32_t idesc, uint32_t sW, uint32_t sBar, int* err,
@@ -1119,7 +1110,7 @@ int pack_tc_weights(DfbNerf* n, int which, const std::vector<std::vector<float>>
 }
 
 // 3-D tensor map over a packed weight image: [n_img][64][128 x u16], one box = one 16 KB image.
-static int make_weight_tmap(void* base, size_t bytes, CUtensorMap* out) {
+int make_weight_tmap(void* base, size_t bytes, CUtensorMap* out) {
   static PFN_cuTensorMapEncodeTiled encode = nullptr;
   if (!encode) {
     void* fn = nullptr;

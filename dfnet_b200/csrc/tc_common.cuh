@@ -1,5 +1,6 @@
 // Shared PTX wrappers for the tcgen05 / TMEM / mbarrier / bulk-copy kernels (mlp_tc.cu, conv_tc.cu).
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
@@ -97,6 +98,34 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+
+// 2-SM TMA load of one 16 KB weight image (box [1][64][128 x 16-bit]) into this CTA's shared memory;
+// the transaction bytes are credited to the barrier at `bar_leader` in the LEADER CTA's shared memory.
+__device__ __forceinline__ void tma_load_img_2sm(uint32_t dst, const CUtensorMap* tmap, int img, uint32_t bar_leader) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_leader), "r"(0), "r"(0), "r"(img)
+      : "memory");
+}
+
+// 5-D tiled TMA load (box given by the tensor map) into this CTA's shared memory, completion on `bar`.  Out-of-bounds
+// coordinates (negative or past the extent) are zero-filled, which is what a convolution's halo needs.
+// CG 2: 2-SM form, `bar` is the barrier address inside the LEADER CTA (see tma_load_img_2sm).
+template <int CG = 1>
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tmap, int c0, int c1, int c2, int c3, int c4,
+                                            uint32_t bar) {
+  if (CG == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+  }
 }
 
 template <int CG = 1>

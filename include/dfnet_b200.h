@@ -344,6 +344,9 @@ int dfb_mse_bwd(const float* a, const float* b, int64_t n, const float* g_loss, 
 int dfb_resize_bicubic_bwd(const float* g_dst, int64_t planes, int h, int w, int Ho, int Wo, float* g_src, void* stream);
 int dfb_resize_bilinear_ac_bwd(const float* g_dst, int64_t planes, int h, int w, int Ho, int Wo, float* g_src, void* stream);
 
+/* Debug seam (tools/conv_prof.py): per-CTA cycle counters of the convolution kernel's roles, see csrc/conv_tc.cu. */
+int dfb_debug_conv_prof(int on, unsigned long long* out_host, int max_cta, int* grid);
+
 /* Debug seam: one tcgen05 tile with MN-major operands, D[128,N] = sum_k A[k][m] * B[k][n] (A [K,128], B [K,N] fp32 on
  * the device, rounded to fmt_a / fmt_b: 0 = f16, 1 = bf16).  Pins the descriptor convention the weight-gradient
  * kernel relies on. */
