@@ -48,6 +48,9 @@ struct DfbDfnet {
   // layers are differentiated FIRST), so that the caller can all-reduce that bucket while the backward continues
   void* bucket_event = nullptr;
   int bucket_first_layer = 0;
+  // forward: side streams for the adaptation heads (fork / join around the caller's stream, see dfnet_fwd_impl)
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t ev[5] = {};
 };
 
 static const int kEncCin[13] = {3, 64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512};

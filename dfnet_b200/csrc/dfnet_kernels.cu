@@ -12,6 +12,8 @@
 
 #include "common.cuh"
 
+#include <stdlib.h>
+
 #include "dfnet_handle.cuh"
 #include "tc_common.cuh"
 
@@ -97,6 +99,71 @@ __global__ void __launch_bounds__(128) k_resize_bilinear_ac(const float* __restr
     else
       for (int k = 0; k < 4 && xq + k < Wo; ++k) d[k] = o[k];
   }
+}
+
+// Upsampling variant: one block = one plane x kRsRows output rows.  The <= kRsRows*sy + 2 source rows the block needs
+// are staged in shared memory once (the first version gathered 16 scalars from L2 per 16-byte store and ran at 2.6
+// TB/s); afterwards every thread produces float4 stores from shared memory, so the kernel is bound by its HBM writes.
+// Same arithmetic as k_resize_bilinear_ac (bit-identical results).
+constexpr int kRsRows = 16;
+__global__ void __launch_bounds__(256) k_resize_bilinear_ac_up(const float* __restrict__ src, float* __restrict__ dst, int h, int w,
+                                                               int Ho, int Wo, int nrows_max) {
+  extern __shared__ float srows[];  // [nrows][w]
+  const int pl = blockIdx.y, yo0 = blockIdx.x * kRsRows, yo1 = min(Ho, yo0 + kRsRows);
+  const float sy = Ho > 1 ? (float)(h - 1) / (float)(Ho - 1) : 0.f, sx = Wo > 1 ? (float)(w - 1) / (float)(Wo - 1) : 0.f;
+  const int ys0 = (int)(sy * yo0);
+  const int ylast = (int)(sy * (yo1 - 1));
+  const int ys1 = min(h - 1, ylast + 1);
+  const int nrows = ys1 - ys0 + 1;
+  const float* sp = src + ((int64_t)pl * h + ys0) * w;
+  for (int i = threadIdx.x; i < nrows * w; i += 256) srows[i] = __ldg(sp + i);
+  __syncthreads();
+  const int nq = (Wo + 3) >> 2;
+  for (int q = threadIdx.x; q < nq; q += 256) {
+    const int xq = q * 4;
+    int x0[4], x1[4];
+    float lx[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int xo = min(xq + k, Wo - 1);
+      const float fx = sx * xo;
+      x0[k] = (int)fx, x1[k] = x0[k] + (x0[k] < w - 1), lx[k] = fx - x0[k];
+    }
+    const bool vec = xq + 3 < Wo && (Wo & 3) == 0;
+    for (int yo = yo0; yo < yo1; ++yo) {
+      const float fy = sy * yo;
+      const int y0 = (int)fy, y1 = y0 + (y0 < h - 1);
+      const float ly = fy - y0;
+      const float* r0 = srows + (y0 - ys0) * w;
+      const float* r1 = srows + (y1 - ys0) * w;
+      float o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        o[k] = (1.f - ly) * ((1.f - lx[k]) * r0[x0[k]] + lx[k] * r0[x1[k]]) + ly * ((1.f - lx[k]) * r1[x0[k]] + lx[k] * r1[x1[k]]);
+      float* d = dst + ((int64_t)pl * Ho + yo) * Wo + xq;
+      if (vec) __stcs(reinterpret_cast<float4*>(d), make_float4(o[0], o[1], o[2], o[3]));
+      else
+        for (int k = 0; k < 4 && xq + k < Wo; ++k) d[k] = o[k];
+    }
+  }
+}
+
+// picks the staged kernel for upsampling (source rows of a block fit shared memory), the gather kernel otherwise
+static int launch_resize_bilinear_ac(const float* src, float* dst, int64_t planes, int h, int w, int Ho, int Wo, cudaStream_t st) {
+  const double sy = Ho > 1 ? (double)(h - 1) / (double)(Ho - 1) : 0.0;
+  const int nrows_max = (int)(sy * (kRsRows - 1)) + 3;
+  const size_t smem = (size_t)nrows_max * w * sizeof(float);
+  if (Ho >= h && Wo >= w && smem <= 48 * 1024 && planes <= 65535) {
+    const dim3 g((Ho + kRsRows - 1) / kRsRows, (unsigned)planes);
+    k_resize_bilinear_ac_up<<<g, 256, smem, st>>>(src, dst, h, w, Ho, Wo, nrows_max);
+    DFB_LAUNCH_CHECK();
+    return DFB_OK;
+  }
+  const dim3 rg((Wo + 511) / 512, Ho, (unsigned)((planes + kResizePlanes - 1) / kResizePlanes));
+  DFB_REQUIRE(rg.z <= 65535, DFB_ERR_INVALID, "too many planes");
+  k_resize_bilinear_ac<<<rg, 128, 0, st>>>(src, dst, (int)planes, h, w, Ho, Wo);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
 }
 
 // adaptive average pool to 1x1 over NHWC fp16 -> fp32 [B,C]; one block per (b, 64 channels)
@@ -249,6 +316,10 @@ extern "C" void dfb_dfnet_destroy(DfbDfnet* d) {
   if (d->bn_sc) cudaFree(d->bn_sc);
   if (d->bn_sh) cudaFree(d->bn_sh);
   if (d->bn_stage) cudaFree(d->bn_stage);
+  for (int i = 0; i < 2; ++i)
+    if (d->side[i]) cudaStreamDestroy(d->side[i]);
+  for (int i = 0; i < 5; ++i)
+    if (d->ev[i]) cudaEventDestroy(d->ev[i]);
   if (d->fc_w) cudaFree(d->fc_w);
   if (d->fc_b) cudaFree(d->fc_b);
   delete d;
@@ -483,40 +554,14 @@ static int dfnet_fwd_impl(DfbDfnet* d, const float* x, int B, int H, int W, uint
   cudaStream_t st = (cudaStream_t)stream;
   char* base = (char*)ws;
   const int64_t plane = (int64_t)H * W, npix = (int64_t)B * plane;
+  // (a direct fp32 kernel for conv1_1 fused with this normalisation was measured at the tensor-core kernel's speed once
+  // that kernel loaded its patches by TMA - 110 vs 107 us under ncu - and was dropped)
   k_input_norm_nhwc8<T><<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(x, (T*)(base + L.in8), npix, plane);
   DFB_LAUNCH_CHECK();
-  const void* cur = base + L.in8;
-  int h = H, w = W, lv = 0;
-  const int last_conv = d->n_levels == 1 && !ret_pose ? 1 : 12;  // DFNet_s stops after conv1_2 when no pose is needed
-  for (int i = 0; i <= last_conv; ++i) {
-    void* tap = nullptr;
-    if (ret_feat && lv < d->n_levels && kTapConv[lv] == i) { tap = base + L.tap[lv]; ++lv; }
-    const bool need_out = i < last_conv || ret_pose || tape;
-    void* o = need_out ? base + L.act[i] : nullptr;
-    DfbConv* cv = bf ? d->enc_bf[i] : d->enc[i];
-    DFB_REQUIRE(cv, DFB_ERR_INVALID, "training variants not loaded (dfb_dfnet_load_ex flags bit0)");
-    if (!bf && !tape && d->enc_n128[i] && 2 * dfb_conv_tiles(cv, B, h, w) <= dfb_conv_num_sms(cv)) cv = d->enc_n128[i];
-    int rc = dfb_conv_fwd(cv, cur, B, h, w, 1, o, tap, nullptr, stream);
-    if (rc) return rc;
-    if (i == last_conv && !ret_pose) break;
-    cur = o;
-    if (kPoolAfter[i]) {
-      const int64_t n = (int64_t)B * (h / 2) * (w / 2) * (kEncCout[i] / 8);
-      k_maxpool2x2_nhwc<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const T*)cur, (T*)(base + L.pool[i]), B, h, w, kEncCout[i]);
-      DFB_LAUNCH_CHECK();
-      cur = base + L.pool[i], h /= 2, w /= 2;
-    }
-  }
-  if (ret_pose) {  // cur = pool5 output [B,h,w,512]
-    float* pooled = (float*)(base + L.pooled);
-    k_avgpool_nhwc<T><<<dim3(512 / 64, B), 256, 0, st>>>((const T*)cur, pooled, h * w, 512);
-    DFB_LAUNCH_CHECK();
-    k_fc_small<<<B, 12 * 32, 0, st>>>(pooled, d->fc_w, d->fc_b, pose, 512, 12);
-    DFB_LAUNCH_CHECK();
-  }
-  if (ret_feat) {
-    const int Bs = single ? B : B / 2;
-    for (int l = 0; l < d->n_levels; ++l) {
+  // One adaptation head (1x1 conv + ReLU, 5x5 conv + BatchNorm, resampling into the stacks) on stream `st`.
+  const int Bs = single ? B : B / 2;
+  auto run_head = [&](int l, cudaStream_t st) -> int {
+    void* stream = (void*)st;
       const int fh = L.h[kTapConv[l]], fw = L.w[kTapConv[l]];
       int rc = dfb_conv_fwd(d->head1[l], base + L.tap[l], B, fh, fw, 1, base + L.mid[l], nullptr, nullptr, stream);
       if (rc) return rc;
@@ -540,20 +585,18 @@ static int dfnet_fwd_impl(DfbDfnet* d, const float* x, int B, int H, int W, uint
           dfb::k_bn_apply<<<ag, 256, 0, st>>>(featbuf, B, Bs, fplane, stat, feats_t + l * lvl_stride,
                                               single ? nullptr : feats_r + l * lvl_stride);
           DFB_LAUNCH_CHECK();
-          continue;
+          return DFB_OK;
         }
         dfb::k_bn_apply<<<ag, 256, 0, st>>>(featbuf, B, B, fplane, stat, featbuf, nullptr);  // in place, then resample
         DFB_LAUNCH_CHECK();
         const int planes_s = Bs * 128;
-        const dim3 rg((upW + 511) / 512, upH, (planes_s + kResizePlanes - 1) / kResizePlanes);
-        k_resize_bilinear_ac<<<rg, 128, 0, st>>>(featbuf, feats_t + l * lvl_stride, planes_s, fh, fw, upH, upW);
-        DFB_LAUNCH_CHECK();
+        rc = launch_resize_bilinear_ac(featbuf, feats_t + l * lvl_stride, planes_s, fh, fw, upH, upW, st);
+        if (rc) return rc;
         if (!single) {
-          k_resize_bilinear_ac<<<rg, 128, 0, st>>>(featbuf + (size_t)planes_s * fh * fw, feats_r + l * lvl_stride, planes_s, fh, fw,
-                                                   upH, upW);
-          DFB_LAUNCH_CHECK();
+          rc = launch_resize_bilinear_ac(featbuf + (size_t)planes_s * fh * fw, feats_r + l * lvl_stride, planes_s, fh, fw, upH, upW, st);
+          if (rc) return rc;
         }
-        continue;
+        return DFB_OK;
       }
       if (fh == upH && fw == upW) {
         // align_corners resampling to the same size is the identity (level 0 at full resolution):
@@ -565,22 +608,78 @@ static int dfnet_fwd_impl(DfbDfnet* d, const float* x, int B, int H, int W, uint
                             feats_r + l * lvl_stride, stream);
           if (rc) return rc;
         }
-        continue;
+        return DFB_OK;
       }
       float* featbuf = (float*)(base + L.feat);
       rc = dfb_conv_fwd(d->head5[l], mid, B, fh, fw, 0, nullptr, nullptr, featbuf, stream);
       if (rc) return rc;
       const int planes_s = Bs * 128;
-      const dim3 rg((upW + 511) / 512, upH, (planes_s + kResizePlanes - 1) / kResizePlanes);
-      k_resize_bilinear_ac<<<rg, 128, 0, st>>>(featbuf, feats_t + l * lvl_stride, planes_s, fh, fw, upH, upW);
-      DFB_LAUNCH_CHECK();
+      rc = launch_resize_bilinear_ac(featbuf, feats_t + l * lvl_stride, planes_s, fh, fw, upH, upW, st);
+      if (rc) return rc;
       if (!single) {
-        k_resize_bilinear_ac<<<rg, 128, 0, st>>>(featbuf + (size_t)planes_s * fh * fw, feats_r + l * lvl_stride, planes_s, fh, fw,
-                                                 upH, upW);
-        DFB_LAUNCH_CHECK();
+        rc = launch_resize_bilinear_ac(featbuf + (size_t)planes_s * fh * fw, feats_r + l * lvl_stride, planes_s, fh, fw, upH, upW, st);
+        if (rc) return rc;
       }
+    return DFB_OK;
+  };
+  // The heads only depend on their tap, so they run on side streams NEXT TO the rest of the encoder: every kernel
+  // here is a persistent grid of <= 148 CTAs whose tile counts rarely divide by 148 (conv3: 300 tiles, conv4: 160,
+  // conv5: 40-80), and the CTAs of a concurrent kernel fill the SMs that finish early.  Level 0 (the 5x5 conv at full
+  // resolution, 40 % of the forward's FLOPs) gets its own stream; levels 1 and 2 share one (and the fp32 staging buffer).
+  // DFB_DFNET_STREAMS=0 serialises everything on the caller's stream.
+  static const bool use_streams = [] { const char* e = getenv("DFB_DFNET_STREAMS"); return !(e && e[0] == '0'); }();
+  const bool fork = ret_feat && use_streams && !(flags & 32);
+  if (fork && !d->side[0]) {
+    for (int i = 0; i < 2; ++i) DFB_CHECK_CUDA(cudaStreamCreateWithFlags(&d->side[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 5; ++i) DFB_CHECK_CUDA(cudaEventCreateWithFlags(&d->ev[i], cudaEventDisableTiming));
+  }
+  const void* cur = base + L.in8;
+  int h = H, w = W, lv = 0;
+  const int last_conv = d->n_levels == 1 && !ret_pose ? 1 : 12;  // DFNet_s stops after conv1_2 when no pose is needed
+  for (int i = 0; i <= last_conv; ++i) {
+    void* tap = nullptr;
+    if (ret_feat && lv < d->n_levels && kTapConv[lv] == i) { tap = base + L.tap[lv]; ++lv; }
+    const bool need_out = i < last_conv || ret_pose || tape;
+    void* o = need_out ? base + L.act[i] : nullptr;
+    DfbConv* cv = bf ? d->enc_bf[i] : d->enc[i];
+    DFB_REQUIRE(cv, DFB_ERR_INVALID, "training variants not loaded (dfb_dfnet_load_ex flags bit0)");
+    if (!bf && !tape && d->enc_n128[i] && 2 * dfb_conv_tiles(cv, B, h, w) <= dfb_conv_num_sms(cv)) cv = d->enc_n128[i];
+    int rc = dfb_conv_fwd(cv, cur, B, h, w, 1, o, tap, nullptr, stream);
+    if (rc) return rc;
+    if (tap && fork) {  // level lv-1 is ready: its head starts on a side stream while the encoder continues
+      const int l = lv - 1;
+      cudaStream_t hs = d->side[l == 0 ? 0 : 1];
+      DFB_CHECK_CUDA(cudaEventRecord(d->ev[l], st));
+      DFB_CHECK_CUDA(cudaStreamWaitEvent(hs, d->ev[l], 0));
+      rc = run_head(l, hs);
+      if (rc) return rc;
+    }
+    if (i == last_conv && !ret_pose) break;
+    cur = o;
+    if (kPoolAfter[i]) {
+      const int64_t n = (int64_t)B * (h / 2) * (w / 2) * (kEncCout[i] / 8);
+      k_maxpool2x2_nhwc<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const T*)cur, (T*)(base + L.pool[i]), B, h, w, kEncCout[i]);
+      DFB_LAUNCH_CHECK();
+      cur = base + L.pool[i], h /= 2, w /= 2;
     }
   }
+  if (ret_pose) {  // cur = pool5 output [B,h,w,512]
+    float* pooled = (float*)(base + L.pooled);
+    k_avgpool_nhwc<T><<<dim3(512 / 64, B), 256, 0, st>>>((const T*)cur, pooled, h * w, 512);
+    DFB_LAUNCH_CHECK();
+    k_fc_small<<<B, 12 * 32, 0, st>>>(pooled, d->fc_w, d->fc_b, pose, 512, 12);
+    DFB_LAUNCH_CHECK();
+  }
+  if (ret_feat && !fork)
+    for (int l = 0; l < d->n_levels; ++l) {
+      const int rc = run_head(l, st);
+      if (rc) return rc;
+    }
+  if (fork)  // join: the caller's stream continues when both side streams are done
+    for (int i = 0; i < 2; ++i) {
+      DFB_CHECK_CUDA(cudaEventRecord(d->ev[3 + i], d->side[i]));
+      DFB_CHECK_CUDA(cudaStreamWaitEvent(st, d->ev[3 + i], 0));
+    }
   return DFB_OK;
 }
 
@@ -883,11 +982,7 @@ extern "C" int dfb_resize_bicubic(const float* src, int64_t planes, int h, int w
 // torch.nn.UpsamplingBilinear2d(size=(Ho,Wo)) (align_corners=True) on fp32 [P,h,w] planes.
 extern "C" int dfb_resize_bilinear_ac(const float* src, int64_t planes, int h, int w, int Ho, int Wo, float* dst, void* stream) {
   DFB_REQUIRE(src && dst && planes >= 1 && h >= 1 && w >= 1 && Ho >= 1 && Wo >= 1, DFB_ERR_INVALID, "bad arguments");
-  const dim3 rg((Wo + 511) / 512, Ho, (unsigned)((planes + kResizePlanes - 1) / kResizePlanes));
-  DFB_REQUIRE(rg.z <= 65535, DFB_ERR_INVALID, "too many planes");
-  k_resize_bilinear_ac<<<rg, 128, 0, (cudaStream_t)stream>>>(src, dst, (int)planes, h, w, Ho, Wo);
-  DFB_LAUNCH_CHECK();
-  return DFB_OK;
+  return launch_resize_bilinear_ac(src, dst, planes, h, w, Ho, Wo, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------
