@@ -42,7 +42,7 @@ class RenderCfg(C.Structure):
 class RenderExtras(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in
                 ("rgb0", "disp0", "acc0", "z_std", "beta", "transient_sigmas", "raw", "weights_coarse", "z_vals",
-                 "z_samples", "inds", "depth", "relu_masks")]
+                 "z_samples", "inds", "depth", "relu_masks", "n_live")]
 
 
 class DfbError(RuntimeError):

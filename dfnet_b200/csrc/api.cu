@@ -69,13 +69,14 @@ bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
 
 int run_mlp_inner(const DfbNerf* n, const DfbRenderCfg* c, int which, int mode, const float* rayrec, const float* z,
-                  const float* rb, int64_t rays, int S, float* raw, cudaStream_t st, uint32_t* masks, float* part) {
+                  const float* rb, int64_t rays, int S, float* raw, cudaStream_t st, uint32_t* masks, float* part,
+                  const int* ert_rowmap = nullptr, const int* ert_offsets = nullptr) {
   // The tcgen05 kernel covers the 8x256 networks (sigma-only coarse pass and full fine pass); every
   // other shape or mode (other widths, the train-mode coarse pass) runs on the fp32 CUDA kernel.
   if (c->mma_kind != DFB_MMA_FP32_SIMT && tc_supported(n, which, mode))
     return launch_mlp_tc_rays(n, which, mode, eff_kind(c->mma_kind), rayrec, z, rb, rays, S, raw, st, masks,
                               c->mma_kind == DFB_MMA_F16_SPLIT_COARSE && which == 0 && mode == MLP_SIGMA, part,
-                              part ? composite_part_k(S) : 0);
+                              part ? composite_part_k(S) : 0, ert_rowmap, ert_offsets);
   DFB_REQUIRE(!part, DFB_ERR_UNSUPPORTED, "fused compositing is a mode of the tcgen05 fine pass");
   DFB_REQUIRE(!masks, DFB_ERR_UNSUPPORTED, "relu_masks are an output of the tcgen05 path (8x256 fine network, mma f16 / bf16)");
   return launch_mlp_simt_rays(n, which, mode, rayrec, z, rb, rays, S, raw, st);
@@ -83,14 +84,14 @@ int run_mlp_inner(const DfbNerf* n, const DfbRenderCfg* c, int which, int mode, 
 
 int run_mlp(const DfbNerf* n, const DfbRenderCfg* c, int which, int mode, const float* rayrec, const float* z,
             const float* rb, int64_t rays, int S, float* raw, cudaStream_t st, uint32_t* masks = nullptr,
-            float* part = nullptr) {
-  if (!g_prof_on) return run_mlp_inner(n, c, which, mode, rayrec, z, rb, rays, S, raw, st, masks, part);
+            float* part = nullptr, const int* ert_rowmap = nullptr, const int* ert_offsets = nullptr) {
+  if (!g_prof_on) return run_mlp_inner(n, c, which, mode, rayrec, z, rb, rays, S, raw, st, masks, part, ert_rowmap, ert_offsets);
   ProfRec r;
   r.which = which;
   DFB_CHECK_CUDA(cudaEventCreate(&r.a));
   DFB_CHECK_CUDA(cudaEventCreate(&r.b));
   DFB_CHECK_CUDA(cudaEventRecord(r.a, st));
-  int rc = run_mlp_inner(n, c, which, mode, rayrec, z, rb, rays, S, raw, st, masks, part);
+  int rc = run_mlp_inner(n, c, which, mode, rayrec, z, rb, rays, S, raw, st, masks, part, ert_rowmap, ert_offsets);
   DFB_CHECK_CUDA(cudaEventRecord(r.b, st));
   g_prof.push_back(r);
   return rc;
@@ -218,8 +219,26 @@ extern "C" int dfb_render_fwd(DfbNerf* n, const DfbRenderCfg* c, const float* ra
     sa.inds = ex && ex->inds ? ex->inds + r0 * Nf : nullptr;
     sa.z_vals = ex && ex->z_vals ? ex->z_vals + r0 * S : P(L.z_all);
     sa.z_std = train && ex && ex->z_std ? ex->z_std + r0 : nullptr;
+    // opt-in early ray termination (test-time fused path only): workspace carved from the unused raw buffer, behind the
+    // segment records: n_live [nr], offsets [nr+1], rowmap [nr*S]
+    const bool tc_fine = c->mma_kind != DFB_MMA_FP32_SIMT && tc_supported(n, 1, MLP_FULL);
+    const bool fuse_ok = tc_fine && c->test_time && fuse_composite() &&
+                         !(ex && (ex->raw || ex->depth || ex->beta || ex->transient_sigmas || ex->relu_masks));
+    DFB_REQUIRE(c->ert_eps == 0.f || (fuse_ok && c->ert_eps > 0.f && c->ert_eps < 1.f), DFB_ERR_INVALID,
+                "ert_eps (early ray termination) needs the fused test-time tensor-core path (test_time, mma f16 / bf16, no raw / "
+                "depth / beta extras) and 0 < ert_eps < 1");
+    int *ert_nlive = nullptr, *ert_off = nullptr, *ert_map = nullptr;
+    if (c->ert_eps > 0.f) {
+      char* eb = base + L.raw_f + align256((size_t)nr * composite_part_k(S) * 32);
+      ert_nlive = (int*)eb, ert_off = (int*)(eb + align256((size_t)nr * 4)), ert_map = (int*)(eb + 2 * align256((size_t)(nr + 1) * 4));
+      sa.ert_eps = c->ert_eps, sa.n_live = ert_nlive;
+    }
     rc = launch_sample(sa, st);
     if (rc) return rc;
+    if (ert_nlive) {
+      rc = launch_ert_compact(ert_nlive, nr, S, ert_off, ert_map, st);
+      if (rc) return rc;
+    }
     const float* z_all = sa.z_vals;
     // ---- fine network (rendering.py:307-316) -------------------------------------------------
     float* rb_f = P(L.rb_f);
@@ -242,9 +261,11 @@ extern "C" int dfb_render_fwd(DfbNerf* n, const DfbRenderCfg* c, const float* ra
                       !(ex && (ex->raw || ex->depth || ex->beta || ex->transient_sigmas || ex->relu_masks));
     if (fuse) {
       float* part = P(L.raw_f);  // the raw buffer's space: rays * part_k * 32 B << rays * S * 36 B
-      rc = run_mlp(n, c, 1, MLP_FULL, rayrec, z_all, rb_f, nr, S, nullptr, st, nullptr, part);
+      rc = run_mlp(n, c, 1, MLP_FULL, rayrec, z_all, rb_f, nr, S, nullptr, st, nullptr, part, ert_map, ert_off);
       if (rc) return rc;
-      rc = launch_composite_partials(part, composite_part_k(S), nr, S, rgb + r0 * 3, disp + r0, acc + r0, st);
+      if (ex && ex->n_live && ert_nlive)
+        DFB_CHECK_CUDA(cudaMemcpyAsync(ex->n_live + r0, ert_nlive, (size_t)nr * 4, cudaMemcpyDeviceToDevice, st));
+      rc = launch_composite_partials(part, composite_part_k(S), nr, S, rgb + r0 * 3, disp + r0, acc + r0, st, ert_off);
       if (rc) return rc;
       continue;
     }

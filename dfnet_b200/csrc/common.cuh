@@ -133,12 +133,15 @@ int launch_mlp_simt_embedded(const DfbNerf* nerf, int which, int mode, const flo
 // split3: the split-precision variant of the sigma-only pass (three MMA sub-steps per layer on hi/lo fp16 operands)
 int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const float* rayrec, const float* z,
                        const float* raybias, int64_t n_rays, int S, float* raw, cudaStream_t st,
-                       uint32_t* masks = nullptr, bool split3 = false, float* part = nullptr, int part_k = 0);
+                       uint32_t* masks = nullptr, bool split3 = false, float* part = nullptr, int part_k = 0,
+                       const int* ert_rowmap = nullptr, const int* ert_offsets = nullptr);
+// early ray termination: offsets [N+1] = exclusive scan of n_live (offsets[N] = live rows), rowmap[row] = ray*S + i
+int launch_ert_compact(const int* n_live, int64_t n_rays, int S, int* offsets, int* rowmap, cudaStream_t st);
 // fused compositing (fine pass at test time): records per ray of launch_mlp_tc_rays(part = ...) and the kernel that
 // chains them into rgb / disp / acc
 inline int composite_part_k(int S) { return (S + 30) / 32 + 1; }
 int launch_composite_partials(const float* part, int part_k, int64_t n_rays, int S, float* rgb, float* disp, float* acc,
-                              cudaStream_t st);
+                              cudaStream_t st, const int* ert_offsets = nullptr);
 bool tc_supported(const DfbNerf* nerf, int which, int mode);
 // 3-D tensor map over a packed image of 16 KB chunks: [n][64][128 x u16], one box = one chunk (2-SM TMA weight loads)
 int make_weight_tmap(void* base, size_t bytes, CUtensorMap* out);
@@ -209,6 +212,10 @@ struct SampleArgs {
   int32_t* inds;       // [N,Nf] or null
   float* z_vals;       // [N,Nc+Nf] sorted union, or null (mode A only)
   float* z_std;        // [N] or null
+  // opt-in early ray termination (mode A): n_live[ray] = number of sorted depths up to the coarse sample behind which
+  // the COARSE transmittance 1 - cumsum(w_c) has fallen below ert_eps (>= 1); null = off
+  float ert_eps;
+  int* n_live;
 };
 
 int launch_prep(const PrepArgs& a, cudaStream_t st);

@@ -100,6 +100,12 @@ struct TcArgs {
   // {prod(1-alpha), prod(1-alpha_static), rgb[3], acc, static depth, 0}, k = index of the warp within the ray
   float* part;
   int part_k;
+  // FULL == 4: FULL == 3 on a COMPACTED sample list (opt-in early ray termination, DfbRenderCfg::ert_eps): row g of the
+  // tiles is sample rowmap[g] of the flattened [ray][sample] array, ray r owns rows [offsets[r], offsets[r+1]) (its first
+  // n_live samples), *P_dev = offsets[n_rays] is the number of live rows (known on the device only: no host round trip)
+  const int* rowmap;
+  const int* offsets;
+  const int* P_dev;
   int* error_flag;
   unsigned long long* prof;  // optional [gridDim.x][16] cycle counters (DFB_TC_PROF builds)
   // FULL == 2 (training forward): ReLU masks of the 12 hidden layers, one bit per activation, for the tcgen05
@@ -233,14 +239,20 @@ __device__ __forceinline__ void epi_blocks(uint32_t t_row, uint32_t h_row, const
 // (transmittance = running product of 1 - alpha inside the segment) and the last lane of every segment writes the
 // segment's record; k_composite_partials chains the <= ceil(S/32) + 1 records of a ray.  fp32 throughout: nothing
 // downstream decides a sample index, and the tensor-core path is gated at 1e-3.
-__device__ __forceinline__ void fused_composite(const TcArgs& a, int64_t g, int ray, float ss, float st,
+template <bool ERT>
+__device__ __forceinline__ void fused_composite(const TcArgs& a, int64_t g, int64_t gfull, int ray, int64_t P, float ss, float st,
                                                 const float (&cs)[3], const float (&ct)[3]) {
+  // g: row of the tile grid (compacted when ERT), gfull: index of the sample in [ray][sample] order
   const int lane = threadIdx.x & 31;
-  const bool valid = g < a.P;
-  const int i = (int)(g - (int64_t)ray * a.S);
-  const float zi = valid ? __ldg(a.z + g) : 0.f;
+  const bool valid = g < P;
+  const int i = (int)(gfull - (int64_t)ray * a.S);
+  const float zi = valid ? __ldg(a.z + gfull) : 0.f;
+  const int rnext = __shfl_down_sync(0xffffffffu, ray, 1);
   float zn = __shfl_down_sync(0xffffffffu, zi, 1);
-  if (lane == 31 && valid && i + 1 < a.S) zn = __ldg(a.z + g + 1);
+  // the next lane holds the next sample of the same ray, except at the end of the warp and (ERT) at a ray's last live
+  // sample, whose successor was not evaluated but still has a depth
+  // (rows past the end of the list are clamped onto the last ray: g + 1 >= P marks the last real row)
+  if ((lane == 31 || rnext != ray || g + 1 >= P) && valid && i + 1 < a.S) zn = __ldg(a.z + gfull + 1);
   const float delta = (i + 1 < a.S) ? __fsub_rn(zn, zi) : 1e2f;
   float al = 0.f, als = 0.f, alt = 0.f, oma = 1.f, omas = 1.f;
   if (valid) {
@@ -277,10 +289,9 @@ __device__ __forceinline__ void fused_composite(const TcArgs& a, int64_t g, int 
       if (take) acc[c] += t;
     }
   }
-  const int rnext = __shfl_down_sync(0xffffffffu, ray, 1);
-  const int64_t ray0 = (int64_t)ray * a.S;
+  const int64_t ray0 = ERT ? (int64_t)__ldg(a.offsets + ray) : (int64_t)ray * a.S;   // first row of the ray
   const int64_t seg_first = ray0 > (g & ~(int64_t)31) ? ray0 : (g & ~(int64_t)31);
-  if ((lane == 31 || rnext != ray) && seg_first < a.P) {
+  if ((lane == 31 || rnext != ray) && seg_first < P) {
     const int k = (int)((g >> 5) - (ray0 >> 5));
     float4* o = reinterpret_cast<float4*>(a.part + ((size_t)ray * a.part_k + k) * 8);
     o[0] = make_float4(pa, ps, acc[0], acc[1]);
@@ -435,13 +446,16 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int n_steps = a.n_steps;
+  constexpr bool ERT = FULL == 4;
+  const int64_t P = ERT ? (int64_t)__ldg(a.P_dev) : a.P;
+  const int64_t n_pass = ERT ? ((P + kTileM - 1) / kTileM + NSLOT * CG - 1) / (NSLOT * CG) : a.n_pass;
 
   if (warp == 12) {
     // ===== weight producer (warp-uniform control flow, one elected lane issues) ============
     PROF_DECL
     uint32_t stage = 0, phase = 0;
     const uint8_t* wimg = reinterpret_cast<const uint8_t*>(a.wimg) + (size_t)rank * kChunkBytes;
-    for (int64_t p = unit0; p < a.n_pass; p += n_units)
+    for (int64_t p = unit0; p < n_pass; p += n_units)
       for (int s = 0; s < n_steps; ++s) {
         const int nch = a.steps[s].n_chunks;
         const uint8_t* src0 = wimg + (size_t)a.steps[s].chunk_base * (kChunkBytes * CG);
@@ -477,7 +491,7 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
     uint32_t stage = 0, phase = 0;
     int lp = 0;
     const int n_epi = a.n_epi;
-    for (int64_t p = unit0; p < a.n_pass; p += n_units, ++lp) {
+    for (int64_t p = unit0; p < n_pass; p += n_units, ++lp) {
       int e = 0;  // epilogue step (layer) the sub-step belongs to
       for (int s = 0; s < n_steps; ++s) {
         const int nch = a.steps[s].n_chunks, nn = a.steps[s].n;
@@ -516,11 +530,12 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
     // ===== encoder: positional encoding of the next pass (nerfw.py:128-133) =================
     const int r = tid - 256;
     int lp = 0;
-    for (int64_t p = unit0; p < a.n_pass; p += n_units, ++lp)
+    for (int64_t p = unit0; p < n_pass; p += n_units, ++lp)
       for (int slot = 0; slot < NSLOT; ++slot) {
         if (lp > 0) mbar_wait_relaxed(bar(PE_FREE + slot), (lp - 1) & 1, a.error_flag);
         int64_t g = ((NSLOT * p + slot) * CG + rank) * kTileM + r;
-        g = g < a.P ? g : a.P - 1;
+        g = g < P ? g : P - 1;
+        if (ERT) g = __ldg(a.rowmap + g);
         const int64_t ray = g / a.S;
         const float* rr = a.rayrec + ray * kRayRec;
         const float zz = __ldg(a.z + g);
@@ -566,14 +581,16 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
     EpiCtx cx[2];
     PROF_DECL
     uint32_t nd = 0;
-    for (int64_t p = unit0; p < a.n_pass; p += n_units) {
+    for (int64_t p = unit0; p < n_pass; p += n_units) {
       // row of slot `sl` in the flattened [ray][sample] array (recomputed where needed: registers are scarce here)
       auto row_of = [&](int sl) { return ((NSLOT * p + sl) * CG + rank) * kTileM + r; };
-      int rayi[2];
+      int rayi[2], gfi[2];
 #pragma unroll
       for (int slot = 0; slot < NSLOT; ++slot) {
         const int64_t gg = row_of(slot);
-        rayi[slot] = (int)((gg < a.P ? gg : a.P - 1) / a.S);
+        const int64_t gc = gg < P ? gg : P - 1;
+        gfi[slot] = ERT ? __ldg(a.rowmap + gc) : (int)gc;   // sample index in [ray][sample] order (< 2^31: the chunk bound)
+        rayi[slot] = gfi[slot] / a.S;
         // the per-ray bias row (1 KB) is read by the dir/transient layer much later in the pass: pull it
         // into L1 now so that those loads do not pay eight serial L2 round trips
         if (FULL) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.raybias + (size_t)rayi[slot] * 256 + (tid & 7) * 32));
@@ -595,7 +612,7 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
           uint32_t* mrow = nullptr;
           // (tiles past the end of the sample array exist when the tile count is not a multiple of the tiles per
           // pass: they are computed on clamped rows but must not write masks — the buffer has ceil(P/128) tiles)
-          if (MK && ((2 * p + slot) * CG + rank) * kTileM < a.P)
+          if (MK && ((2 * p + slot) * CG + rank) * kTileM < P)
             mrow = a.masks + ((((2 * p + slot) * CG + rank) * 12 + a.mlayer[s]) * 8) * 128 + r;
           if (X3 && kd == EPI_HIDDEN) epi_blocks_x3(t_row, h_row, a.bias32 + boff, w0, w0 + 4);
           else if (kd == EPI_HIDDEN) epi_blocks<T, EPI_HIDDEN, MK>(t_row, h_row, a, boff, w0, w0 + 4, rbs, mrow);
@@ -609,7 +626,7 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
             tmem_ld32(t_row, v);
             tmem_ld_wait(v);
             const int64_t gg = row_of(slot);
-            if (FULL == 3 && kd == EPI_HEADS) {
+            if (FULL >= 3 && kd == EPI_HEADS) {
               // fused compositing: the accumulator has been read, so the slot is handed back to the tensor pipe
               // first and the activation / compositing arithmetic overlaps the next pass' first layers
               tc_fence_before();
@@ -621,13 +638,13 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
                                    sigmoid_f(__uint_as_float(v[1]) + a.tbl[kTblScal + 5]),
                                    sigmoid_f(__uint_as_float(v[2]) + a.tbl[kTblScal + 6])};
               const float st = softplus_f(__uint_as_float(v[3]) + a.tbl[kTblScal + 7]);
-              fused_composite(a, gg, rayi[slot], cx[slot].sig, st, cs, ct);
+              fused_composite<ERT>(a, gg, ERT ? (int64_t)gfi[slot] : gg, rayi[slot], P, cx[slot].sig, st, cs, ct);
               continue;
             }
             if (kd == EPI_SIGMA) {
               cx[slot].sig = softplus_f(__uint_as_float(v[0]) + a.tbl[kTblScal]);
-              if (!FULL && gg < a.P) a.raw[gg] = cx[slot].sig;
-            } else if (FULL != 3 && gg < a.P) {
+              if (!FULL && gg < P) a.raw[gg] = cx[slot].sig;
+            } else if (FULL < 3 && gg < P) {
               float* o = a.raw + gg * 9;
               o[0] = sigmoid_f(__uint_as_float(v[8]) + a.tbl[kTblScal + 1]);
               o[1] = sigmoid_f(__uint_as_float(v[9]) + a.tbl[kTblScal + 2]);
@@ -1140,7 +1157,7 @@ static int tc_cta_group() {  // read per launch so that tests can exercise both 
 
 int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const float* rayrec, const float* z,
                        const float* raybias, int64_t n_rays, int S, float* raw, cudaStream_t st, uint32_t* masks, bool split3,
-                       float* part, int part_k) {
+                       float* part, int part_k, const int* ert_rowmap, const int* ert_offsets) {
   const NetPack& np = nerf->net[which];
   DFB_REQUIRE(tc_supported(nerf, which, mode), DFB_ERR_UNSUPPORTED, "network shape not supported by the tcgen05 kernel");
   DFB_REQUIRE(kind == DFB_MMA_F16 || kind == DFB_MMA_BF16, DFB_ERR_INVALID, "bad mma kind");
@@ -1153,7 +1170,7 @@ int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const
     const int rc = device_error_flag(&error_flag);
     if (rc) return rc;
   }
-  const int cg = split3 ? 2 : tc_cta_group();
+  const int cg = (split3 || ert_rowmap) ? 2 : tc_cta_group();
   tc::TcArgs a = {};
   const std::vector<LStep> prog = build_program(full);
   a.n_epi = (int)prog.size();
@@ -1197,8 +1214,10 @@ int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const
   a.rayrec = rayrec, a.z = z, a.raybias = raybias, a.S = S, a.P = n_rays * S, a.raw = raw;
   DFB_REQUIRE(!masks || full, DFB_ERR_INVALID, "ReLU masks are an output of the fine network only");
   DFB_REQUIRE(!part || (full && !masks && part_k >= 1), DFB_ERR_INVALID, "fused compositing is a mode of the fine pass without masks");
+  DFB_REQUIRE(!ert_rowmap || (part && ert_offsets), DFB_ERR_INVALID, "early ray termination is a mode of the fused fine pass");
   a.masks = masks;
   a.part = part, a.part_k = part_k;
+  a.rowmap = ert_rowmap, a.offsets = ert_offsets, a.P_dev = ert_offsets ? ert_offsets + n_rays : nullptr;
   a.error_flag = error_flag;
 #ifdef DFB_TC_PROF
   if (!g_prof) {
@@ -1225,6 +1244,7 @@ int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const
   };
   const bool f16 = kind == DFB_MMA_F16;
   if (split3) return launch(tc::k_mlp_tc2_x3);
+  if (ert_rowmap) return f16 ? launch(tc::k_mlp_tc2<__half, 4>) : launch(tc::k_mlp_tc2<__nv_bfloat16, 4>);
   if (part) {
     if (cg == 2) return f16 ? launch(tc::k_mlp_tc2<__half, 3>) : launch(tc::k_mlp_tc2<__nv_bfloat16, 3>);
     return f16 ? launch(tc::k_mlp_tc<__half, 3>) : launch(tc::k_mlp_tc<__nv_bfloat16, 3>);

@@ -376,6 +376,24 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_sample_pdf(SampleArgs a
     s2 = warp_sum(s2);
     if (lane == 0) a.z_std[ray] = sqrtf(s2 / (float)Nf);
   }
+  if (modeA && a.n_live) {
+    // early ray termination: the coarse transmittance after sample j is 1 - sum_{i<=j} w_i; everything behind the coarse
+    // sample that follows the first j with T < eps is dropped from the fine pass (one coarse interval of margin)
+    float zt = 0.f;
+    if (lane == 0) {
+      const float* w = a.w_c + ray * a.Nc;
+      float cum = 0.f;
+      int j = 0;
+      for (; j < a.Nc; ++j) { cum += w[j]; if (1.f - cum < a.ert_eps) break; }
+      zt = zall[min(j + 1, a.Nc - 1)];
+    }
+    zt = __shfl_sync(0xffffffffu, zt, 0);
+    int cnt = 0;
+    for (int i = lane; i < a.Nc; i += 32) cnt += zall[i] <= zt;
+    for (int k = lane; k < Nf; k += 32) cnt += smp[k] <= zt;
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) a.n_live[ray] = max(cnt, 1);
+  }
   if (modeA && a.z_vals) {  // torch.sort(torch.cat([z_vals, z_samples], -1), -1) values
     // Both lists are normally already sorted (coarse depths always; samples when u is the
     // deterministic grid): then the union is a merge, each element's rank is its own index plus a
@@ -516,15 +534,53 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_composite_fine_tt(Compo
   }
 }
 
+// Early ray termination, compaction: exclusive scan of n_live over the rays of a chunk (<= 65 536, one block) and the
+// row map of the compacted sample list.
+__global__ void __launch_bounds__(1024) k_ert_scan(const int* __restrict__ n_live, int n, int* __restrict__ offsets) {
+  __shared__ int part[1024];
+  const int per = (n + 1023) / 1024, i0 = min(threadIdx.x * per, n), i1 = min(i0 + per, n);
+  int s = 0;
+  for (int i = i0; i < i1; ++i) s += n_live[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  int run = threadIdx.x ? part[threadIdx.x - 1] : 0;
+  for (int i = i0; i < i1; ++i) { offsets[i] = run; run += n_live[i]; }
+  if (threadIdx.x == 1023) offsets[n] = part[1023];
+}
+
+__global__ void __launch_bounds__(128) k_ert_rowmap(const int* __restrict__ offsets, int64_t N, int S, int* __restrict__ rowmap) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * 4 + warp;
+  if (ray >= N) return;
+  const int o0 = offsets[ray], n = offsets[ray + 1] - o0;
+  for (int i = lane; i < n; i += 32) rowmap[o0 + i] = (int)(ray * S + i);
+}
+
+int launch_ert_compact(const int* n_live, int64_t n_rays, int S, int* offsets, int* rowmap, cudaStream_t st) {
+  DFB_REQUIRE(n_rays <= (1 << 20), DFB_ERR_INVALID, "ERT scan: too many rays in one chunk");
+  k_ert_scan<<<1, 1024, 0, st>>>(n_live, (int)n_rays, offsets);
+  DFB_LAUNCH_CHECK();
+  k_ert_rowmap<<<(unsigned)((n_rays + 3) / 4), 128, 0, st>>>(offsets, n_rays, S, rowmap);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
 // Chains the per-warp segment records of the fused fine pass (mlp_tc.cu, fused_composite) front to back:
 // rgb += T * C_k, acc += T * A_k, depth += T_static * D_k, T *= prod_k (rendering.py:196-242, test_time).
 __global__ void __launch_bounds__(128) k_composite_partials(const float* __restrict__ part, int part_k, int64_t N, int S,
                                                              float* __restrict__ rgb, float* __restrict__ disp,
-                                                             float* __restrict__ acc) {
+                                                             float* __restrict__ acc, const int* __restrict__ offsets) {
   const int64_t ray = (int64_t)blockIdx.x * 128 + threadIdx.x;
   if (ray >= N) return;
-  const int64_t g0 = ray * S;
-  const int K = (int)(((g0 + S - 1) >> 5) - (g0 >> 5)) + 1;
+  // rows of the ray in the tile grid: [ray*S, ray*S + S), or its live rows in the compacted list (ERT)
+  const int64_t g0 = offsets ? offsets[ray] : ray * S, g1 = offsets ? offsets[ray + 1] : g0 + S;
+  const int K = (int)(((g1 - 1) >> 5) - (g0 >> 5)) + 1;
   const float4* p = reinterpret_cast<const float4*>(part + (size_t)ray * part_k * 8);
   float T = 1.f, Ts = 1.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, ac = 0.f, dep = 0.f;
   for (int k = 0; k < K; ++k) {
@@ -540,8 +596,8 @@ __global__ void __launch_bounds__(128) k_composite_partials(const float* __restr
 }
 
 int launch_composite_partials(const float* part, int part_k, int64_t n_rays, int S, float* rgb, float* disp, float* acc,
-                              cudaStream_t st) {
-  k_composite_partials<<<(unsigned)((n_rays + 127) / 128), 128, 0, st>>>(part, part_k, n_rays, S, rgb, disp, acc);
+                              cudaStream_t st, const int* ert_offsets) {
+  k_composite_partials<<<(unsigned)((n_rays + 127) / 128), 128, 0, st>>>(part, part_k, n_rays, S, rgb, disp, acc, ert_offsets);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }

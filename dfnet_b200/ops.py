@@ -141,10 +141,11 @@ class NerfHandle:
         shapes = {"rgb0": (N, 3), "disp0": (N,), "acc0": (N,), "z_std": (N,), "beta": (N,),
                   "transient_sigmas": (N, S), "raw": (N, S, 9) if N_importance > 0 else (N, N_samples, 4),
                   "weights_coarse": (N, N_samples), "z_vals": (N, S), "z_samples": (N, max(N_importance, 1)),
-                  "inds": (N, max(N_importance, 1)), "depth": (N,), "relu_masks": ((N * S + 127) // 128, 12, 8, 128)}
+                  "inds": (N, max(N_importance, 1)), "depth": (N,), "relu_masks": ((N * S + 127) // 128, 12, 8, 128),
+                  "n_live": (N,)}
         ex = _lib.RenderExtras()
         for k in want:
-            out[k] = torch.empty(shapes[k], device=dev, dtype=torch.int32 if k in ("inds", "relu_masks") else torch.float32)
+            out[k] = torch.empty(shapes[k], device=dev, dtype=torch.int32 if k in ("inds", "relu_masks", "n_live") else torch.float32)
             setattr(ex, k, out[k].data_ptr())
         ws, ws_bytes = self.workspace(cfg, N, dev)
         if t_rand is not None:

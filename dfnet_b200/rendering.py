@@ -102,7 +102,7 @@ def _check_kwargs(kw):
 
 def render_rays(ray_batch, network_fn, network_query_fn=None, N_samples=64, retraw=False, lindisp=False, perturb=0.,
                 N_importance=0, network_fine=None, white_bkgd=False, raw_noise_std=0., verbose=False, pytest=False,
-                i_epoch=-1, embedding_a=None, embedding_t=None, test_time=False, mma=None):
+                i_epoch=-1, embedding_a=None, embedding_t=None, test_time=False, mma=None, ert_eps=0.0):
     """Render a batch of ray records [N, 11+hist_bin] (reference rendering.py:245-337)."""
     kw = dict(network_fn=network_fn, network_fine=network_fine, embedding_a=embedding_a, embedding_t=embedding_t,
               white_bkgd=white_bkgd, raw_noise_std=raw_noise_std)
@@ -130,7 +130,7 @@ def render_rays(ray_batch, network_fn, network_query_fn=None, N_samples=64, retr
         want.append("raw")
     o = h.render(N_samples, N_importance, test_time, rays=ray_batch, perturb=perturb > 0., t_rand=t_rand, u=u,
                  mma=mma or DEFAULT_MMA, lindisp=lindisp, raw_noise_std=raw_noise_std,
-                 noise=noise if raw_noise_std > 0. else None, want=want)
+                 noise=noise if raw_noise_std > 0. else None, ert_eps=ert_eps, want=want)
     ret = {"rgb_map": o["rgb"], "disp_map": o["disp"], "acc_map": o["acc"]}
     for k in want:
         ret[k] = o[k]
@@ -160,6 +160,7 @@ def render(H, W, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0.,
     kwargs.pop("network_query_fn", None)
     _check_kwargs(kwargs)
     mma = kwargs.pop("mma", None) or DEFAULT_MMA
+    ert_eps = float(kwargs.pop("ert_eps", 0.0) or 0.0)   # opt-in early ray termination (not a reference option)
     test_time = kwargs.get("test_time", False)
     Nc, Nf = kwargs["N_samples"], kwargs.get("N_importance", 0)
     perturb = kwargs.get("perturb", 0.)
@@ -193,7 +194,7 @@ def render(H, W, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0.,
             want.append("raw")
         o = h.render(Nc, Nf, test_time, c2w=c2w, H=int(H), W=int(W), focal=float(focal), near=float(near),
                      far=float(far), hist=img_idx.to(c2w.device), mma=mma, lindisp=kwargs.get("lindisp", False),
-                     want=want)
+                     ert_eps=ert_eps, want=want)
         sh = [int(H), int(W)]
         all_ret = {"rgb_map": o["rgb"], "disp_map": o["disp"], "acc_map": o["acc"], **{k: o[k] for k in want}}
     else:
@@ -212,7 +213,7 @@ def render(H, W, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0.,
             img_idx = img_idx.reshape(1, -1).repeat(rays_d.shape[0], 1)
         rec = torch.cat([rays_o, rays_d, near * nf, far * nf, viewdirs, img_idx], -1)
         kwargs.pop("use_viewdirs", None), kwargs.pop("ndc", None)
-        all_ret = batchify_rays(rec, chunk, mma=mma, **{k: v for k, v in kwargs.items() if k not in ("ndc",)})
+        all_ret = batchify_rays(rec, chunk, mma=mma, ert_eps=ert_eps, **{k: v for k, v in kwargs.items() if k not in ("ndc",)})
     for k in all_ret:
         all_ret[k] = torch.reshape(all_ret[k], sh + list(all_ret[k].shape[1:]))
     k_extract = ["rgb_map", "disp_map", "acc_map"]

@@ -125,6 +125,7 @@ typedef struct DfbRenderExtras {
   float* depth;            /* [N]                                                       */
   uint32_t* relu_masks;    /* [ceil(N*S/128), 12, 8, 128] ReLU masks of the fine network's 12 hidden layers, one bit per
                               activation (tcgen05 path only): input of dfb_render_bwd_saved               */
+  int32_t* n_live;         /* [N]   early ray termination (cfg->ert_eps > 0): fine samples evaluated per ray */
 } DfbRenderExtras;
 #define DFB_RELU_MASK_WORDS_PER_TILE (12 * 8 * 128)
 

@@ -294,3 +294,46 @@ def test_fused_compositing_matches_the_raw_round_trip(ctx, n_rays, Nc, Nf, cg):
     ok = out["0"]["disp"] < 1e3
     assert rel_err(out["1"]["disp"][ok], out["0"]["disp"][ok]) < 1e-4
     assert np.isfinite(out["1"]["disp"]).all()
+
+
+def test_early_ray_termination_opt_in(ctx, fitted):
+    """N1: opt-in early ray termination (ert_eps): fine samples behind the depth where the COARSE transmittance falls
+    below ert_eps are not evaluated (compacted sample list, rays keep a prefix of their sorted samples).
+      * ert_eps -> tiny (nothing terminates): n_live == S everywhere and the image equals the parity path's to fp32 noise;
+      * on a field with surfaces a large share of the samples is skipped and the image moves by at most ~ert_eps;
+      * the option is refused where it cannot apply (train mode, fp32 kernels)."""
+    from dfnet_b200 import ops
+    from dfnet_b200._lib import DfbError
+    _, h_smooth, _ = ctx
+    mods, _ = fitted
+    h_sharp = ops.NerfHandle(*mods)
+    H, W, focal, near, far, Nc, Nf = 120, 160, 146.0, 0.0, 2.5, 64, 128
+    c2w, hist = torch.tensor(C2W, device=dev()), torch.tensor(HIST, device=dev())
+    for name, h in (("smooth", h_smooth), ("sharp", h_sharp)):
+        base = h.render(Nc, Nf, True, c2w=c2w, H=H, W=W, focal=focal, near=near, far=far, hist=hist, mma="f16")
+        rgb0, acc0, disp0 = base["rgb"].clone(), base["acc"].clone(), base["disp"].clone()
+        off = h.render(Nc, Nf, True, c2w=c2w, H=H, W=W, focal=focal, near=near, far=far, hist=hist, mma="f16", ert_eps=1e-30,
+                       want=("n_live",))
+        if name == "smooth":      # (on the sharp field the coarse transmittance reaches exactly 0 in fp32 behind a surface)
+            assert int(off["n_live"].min()) == Nc + Nf
+        assert rel_err(off["rgb"].cpu().numpy(), rgb0.cpu().numpy()) < 2e-5
+        for eps in (1e-2, 1e-3):
+            o = h.render(Nc, Nf, True, c2w=c2w, H=H, W=W, focal=focal, near=near, far=far, hist=hist, mma="f16", ert_eps=eps,
+                         want=("n_live",))
+            frac = float(o["n_live"].float().mean()) / (Nc + Nf)
+            d_rgb = float((o["rgb"] - rgb0).abs().max())
+            m_rgb = float((o["rgb"] - rgb0).abs().mean())
+            d_acc = float((o["acc"] - acc0).abs().max())
+            print(f"ERT {name} eps={eps:g}: evaluated {100 * frac:.1f} % of the fine samples, |d rgb| mean {m_rgb:.2e} max {d_rgb:.2e}, "
+                  f"max |d acc| {d_acc:.2e}")
+            assert int(o["n_live"].min()) >= 1 and int(o["n_live"].max()) <= Nc + Nf
+            # the criterion is the COARSE network's transmittance: where the two networks disagree about a surface the
+            # dropped tail still carries fine-network weight, so the bound is statistical (mean <= eps), not per ray
+            assert m_rgb < eps and d_rgb < 0.1 and d_acc < 0.25
+            assert torch.isfinite(o["disp"]).all()
+            if name == "sharp":       # hierarchical sampling already puts 2/3 of the samples at the surface: the dead tail is
+                assert frac < 0.99    # only the coarse-grid samples behind it (measured 93.7 % / 94.7 % evaluated)
+    with pytest.raises(DfbError):
+        h_smooth.render(Nc, Nf, False, c2w=c2w, H=8, W=8, focal=8.0, near=near, far=far, hist=hist, mma="f16", ert_eps=1e-3)
+    with pytest.raises(DfbError):
+        h_smooth.render(Nc, Nf, True, c2w=c2w, H=8, W=8, focal=8.0, near=near, far=far, hist=hist, mma="fp32", ert_eps=1e-3)
