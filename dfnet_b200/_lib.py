@@ -20,6 +20,8 @@ SYMBOLS = [
     "dfb_conv_create_ex", "dfb_conv_fwd_ex", "dfb_conv_wgrad", "dfb_dfnet_load_ex", "dfb_dfnet_bn_batch_stats", "dfb_dfnet_tape_bytes", "dfb_debug_dfnet_tape_layout",
     "dfb_dfnet_bwd_workspace_bytes", "dfb_dfnet_bwd", "dfb_cosine_loss_bwd", "dfb_mse_bwd", "dfb_resize_bicubic_bwd",
     "dfb_resize_bilinear_ac_bwd", "dfb_dfnet_bwd_bucket_event", "dfb_luma_hist", "dfb_resize_area", "dfb_pose_error", "dfb_debug_conv_prof",
+    "dfb_conv_update", "dfb_embed_xyz16", "dfb_rows_expand16", "dfb_rows_reduce_bf16", "dfb_nerf_heads_fwd", "dfb_nerf_heads_bwd",
+    "dfb_raw2outputs_bwd", "dfb_cast_f16_bf16",
 ]
 
 MMA_FP32_SIMT, MMA_F16, MMA_BF16, MMA_F16_SPLIT_COARSE = 0, 1, 2, 3
@@ -103,6 +105,14 @@ def _load():
     lib.dfb_dfnet_bwd.argtypes = [vp, i32, i32, i32, C.c_uint32, i32, i32, vp, vp, C.c_uint32, vp, vp, vp, C.POINTER(vp), i32,
                                   vp, C.c_size_t, vp]
     lib.dfb_dfnet_bwd_bucket_event.argtypes = [vp, i32, vp]
+    lib.dfb_conv_update.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.dfb_embed_xyz16.argtypes = [vp, i32, vp, i64, i32, i32, i32, vp, vp]
+    lib.dfb_rows_expand16.argtypes = [vp, i64, i32, i32, vp, vp]
+    lib.dfb_rows_reduce_bf16.argtypes = [vp, i64, i32, i32, vp, vp]
+    lib.dfb_nerf_heads_fwd.argtypes = [vp, vp, vp, i64, i64, i32, vp, vp]
+    lib.dfb_nerf_heads_bwd.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp]
+    lib.dfb_raw2outputs_bwd.argtypes = [vp, vp, i64, i32, i32, vp, f32, vp, vp, vp, vp, vp]
+    lib.dfb_cast_f16_bf16.argtypes = [vp, vp, i64, vp]
     lib.dfb_debug_conv_prof.argtypes = [i32, vp, i32, C.POINTER(i32)]
     lib.dfb_luma_hist.argtypes = [vp, i32, i32, i32, i32, vp, vp, C.c_size_t, vp]
     lib.dfb_resize_area.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]

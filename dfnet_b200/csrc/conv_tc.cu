@@ -539,6 +539,11 @@ extern "C" int dfb_conv_create(int Cin, int Cout, int KH, int KW, const float* w
   return dfb_conv_create_impl(Cin, Cout, KH, KW, weight, bias, bn_scale, bn_shift, 0, 0, out, 0);
 }
 
+extern "C" int dfb_conv_update(DfbConv* c, const float* weight, const float* bias, const float* bn_scale, const float* bn_shift,
+                               void* stream) {
+  return dfb_conv_update_impl(c, weight, bias, bn_scale, bn_shift, stream);
+}
+
 extern "C" void dfb_conv_destroy(DfbConv* c) {
   if (!c) return;
   if (c->wimg) cudaFree(c->wimg);

@@ -1,0 +1,255 @@
+// Kernels of the NeRF-Hist TRAINING step (reference script/run_nerf.py:32-80, models/losses.py:19-57).
+//
+// The training forward / backward of the NeRF-W MLPs runs layer by layer on the tcgen05 convolution machinery of the
+// DFNet path: a Linear layer over P samples is a 1x1 convolution over a P-pixel image, so k_conv_tc (forward and
+// data-gradient with the ReLU-mask epilogue) and k_conv_wgrad (weight gradient, MN-major operands) apply unchanged; the
+// orchestration lives in dfnet_b200/nerf_train.py.  This file holds what is specific to NeRF around those layers:
+//
+//   k_embed_xyz16          pts = o + d*z and the positional encoding (models/nerfw.py:105-133) as the first layer's
+//                          NHWC 16-bit operand [P, 64]
+//   k_rows_expand16        per-ray pre-activation contribution (view direction / appearance / transient codes through
+//                          their slice of dir_encoding.0 / transient_encoding.0) broadcast to the ray's samples
+//   k_rows_reduce          its adjoint: sum of a [P, C] gradient over the samples of each ray
+//   k_heads_fwd / _bwd     Softplus / Sigmoid heads (models/nerfw.py:275-295): fp32 pre-activations -> raw, and
+//                          d raw -> d pre-activation from the stored outputs (sigmoid' = o (1 - o), softplus' = 1 - e^-o)
+//   k_raw2outputs_bwd      adjoint of raw2outputs_NeRFW (models/rendering.py:132-243) in train mode w.r.t. raw, for the
+//                          outputs the NeRF-W loss reads: rgb (coarse / fine), beta, transient_sigmas
+//   k_cast_f16_bf16        forward activations (fp16) as bf16 operands of the weight-gradient kernel
+#include "common.cuh"
+
+namespace dfb {
+
+__global__ void __launch_bounds__(128) k_embed_xyz16(const float* __restrict__ rays, int ray_stride, const float* __restrict__ z,
+                                                     int64_t P, int S, int L, int ld, __half* __restrict__ out) {
+  const int64_t g = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (g >= P) return;
+  const float* r = rays + (g / S) * ray_stride;
+  const float zz = z[g];
+  float pt[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) pt[c] = __fadd_rn(r[c], __fmul_rn(r[3 + c], zz));
+  __half* o = out + g * ld;
+  for (int c = 0; c < 3; ++c) o[c] = __float2half_rn(pt[c]);
+  for (int l = 0; l < L; ++l) {
+    const float fr = (float)(1 << l);
+    for (int c = 0; c < 3; ++c) {
+      float sn, cs;
+      sincosf(__fmul_rn(pt[c], fr), &sn, &cs);
+      o[3 + 6 * l + c] = __float2half_rn(sn);
+      o[3 + 6 * l + 3 + c] = __float2half_rn(cs);
+    }
+  }
+  for (int c = 3 + 6 * L; c < ld; ++c) o[c] = __float2half_rn(0.f);
+}
+
+// out[p, c] = fp16(rb[ray(p), c])
+__global__ void __launch_bounds__(256) k_rows_expand16(const float* __restrict__ rb, int64_t P, int S, int C, __half* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;   // one thread per 8 channels
+  const int c8 = C / 8;
+  if (i >= P * c8) return;
+  const int64_t p = i / c8;
+  const int c = (int)(i % c8) * 8;
+  const float* s = rb + (p / S) * C + c;
+  __half2 h[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) h[k] = __floats2half2_rn(s[2 * k], s[2 * k + 1]);
+  *reinterpret_cast<uint4*>(out + p * C + c) = *reinterpret_cast<uint4*>(h);
+}
+
+// out[r, c] = sum_{s < S} g[(r*S + s), c]  (g bf16, accumulation fp32); one block per ray, one thread per channel
+__global__ void k_rows_reduce(const __nv_bfloat16* __restrict__ g, int S, int C, float* __restrict__ out) {
+  const int64_t r = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f;
+    const __nv_bfloat16* p = g + (r * S) * C + c;
+    for (int s = 0; s < S; ++s) acc += __bfloat162float(p[(int64_t)s * C]);
+    out[r * C + c] = acc;
+  }
+}
+
+__device__ __forceinline__ float nt_softplus(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float nt_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+
+// pre-activations are fp32 planes [channel][P] (the NCHW output of the head convolutions, plane stride `ps`)
+__global__ void __launch_bounds__(256) k_heads_fwd(const float* __restrict__ sig, const float* __restrict__ rgb,
+                                                   const float* __restrict__ tr, int64_t P, int64_t ps, int C,
+                                                   float* __restrict__ raw) {
+  const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (p >= P) return;
+  float* o = raw + p * C;
+  for (int c = 0; c < 3; ++c) o[c] = nt_sigmoid(rgb[c * ps + p]);
+  o[3] = nt_softplus(sig[p]);
+  if (C == 9) {   // transient head planes: rgb(3), sigma, beta
+    for (int c = 0; c < 3; ++c) o[4 + c] = nt_sigmoid(tr[c * ps + p]);
+    o[7] = nt_softplus(tr[3 * ps + p]);
+    o[8] = nt_softplus(tr[4 * ps + p]);
+  }
+}
+
+// d raw -> d pre-activation as bf16 NHWC [P, 64] operands (columns past the head's width are zero):
+// g_sig[:,0]; g_rgb[:,0:3]; g_tr[:,0:5] = transient rgb(3), sigma, beta
+__global__ void __launch_bounds__(256) k_heads_bwd(const float* __restrict__ raw, const float* __restrict__ g_raw, int64_t P, int C,
+                                                   __nv_bfloat16* __restrict__ g_sig, __nv_bfloat16* __restrict__ g_rgb,
+                                                   __nv_bfloat16* __restrict__ g_tr) {
+  const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (p >= P) return;
+  const float* o = raw + p * C;
+  const float* g = g_raw + p * C;
+  float v[9];
+  for (int c = 0; c < 3; ++c) v[c] = g[c] * o[c] * (1.f - o[c]);
+  v[3] = g[3] * (1.f - expf(-o[3]));
+  if (C == 9) {
+    for (int c = 4; c < 7; ++c) v[c] = g[c] * o[c] * (1.f - o[c]);
+    v[7] = g[7] * (1.f - expf(-o[7]));
+    v[8] = g[8] * (1.f - expf(-o[8]));
+  }
+  const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
+  __nv_bfloat16* a = g_sig + p * 64;
+  __nv_bfloat16* b = g_rgb + p * 64;
+  for (int c = 0; c < 64; ++c) a[c] = zero, b[c] = zero;
+  a[0] = __float2bfloat16_rn(v[3]);
+  for (int c = 0; c < 3; ++c) b[c] = __float2bfloat16_rn(v[c]);
+  if (C == 9) {
+    __nv_bfloat16* t = g_tr + p * 64;
+    for (int c = 0; c < 64; ++c) t[c] = zero;
+    for (int c = 0; c < 5; ++c) t[c] = __float2bfloat16_rn(v[4 + c]);
+  }
+}
+
+// One thread per ray.  C == 9 (fine, train mode): loss inputs rgb = sum T (a_s c_s + a_t c_t), beta = sum T a_t b + beta_min,
+// transient_sigmas = sigma_t.  C == 4 (coarse, train mode): rgb = sum T a c, a = 1 - exp(-delta relu(sigma + noise std)).
+// With E_i the upstream-weighted emission of sample i, d/d a_j of sum_{i>j} T_i E_i is -T_j R_j with the backward
+// recurrence R_j = E_{j+1} + (1 - a_{j+1}) R_{j+1} (no division by 1 - a).
+__global__ void __launch_bounds__(128) k_raw2outputs_bwd(const float* __restrict__ raw, const float* __restrict__ z, int64_t N, int S,
+                                                         int C, const float* __restrict__ noise, float noise_std,
+                                                         const float* __restrict__ g_rgb, const float* __restrict__ g_beta,
+                                                         const float* __restrict__ g_tsig, float* __restrict__ g_raw) {
+  const int64_t ray = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (ray >= N) return;
+  const float* rw = raw + ray * S * C;
+  const float* zz = z + ray * S;
+  float* go = g_raw + ray * S * C;
+  const float g0 = g_rgb ? g_rgb[ray * 3] : 0.f, g1 = g_rgb ? g_rgb[ray * 3 + 1] : 0.f, g2 = g_rgb ? g_rgb[ray * 3 + 2] : 0.f;
+  const float gb = g_beta ? g_beta[ray] : 0.f;
+  auto delta_at = [&](int i) { return (i + 1 < S) ? __fsub_rn(zz[i + 1], zz[i]) : 1e2f; };
+  // pass 1 (front to back): transmittance in front of every sample, parked in g_raw's sigma slot
+  double T = 1.0;
+  for (int i = 0; i < S; ++i) {
+    const float d = delta_at(i);
+    float a;
+    if (C == 9) a = 1.f - expf(-d * (rw[i * 9 + 3] + rw[i * 9 + 7]));
+    else a = 1.f - expf(-d * fmaxf(rw[i * C + 3] + (noise ? noise[ray * S + i] * noise_std : 0.f), 0.f));
+    go[i * C + 3] = (float)T;
+    T *= (double)(1.f - a);
+  }
+  // pass 2 (back to front)
+  double R = 0.0;
+  for (int i = S - 1; i >= 0; --i) {
+    const float d = delta_at(i), Ti = go[i * C + 3];
+    if (C == 9) {
+      const float ss = rw[i * 9 + 3], st = rw[i * 9 + 7];
+      const float es = expf(-d * ss), et = expf(-d * st), ea = expf(-d * (ss + st));
+      const float as = 1.f - es, at = 1.f - et;
+      const float gcs = g0 * rw[i * 9] + g1 * rw[i * 9 + 1] + g2 * rw[i * 9 + 2];
+      const float gct = g0 * rw[i * 9 + 4] + g1 * rw[i * 9 + 5] + g2 * rw[i * 9 + 6] + gb * rw[i * 9 + 8];
+      const float E = as * gcs + at * gct;
+      const float dA = -Ti * (float)R;             // through the transmittance of the samples behind
+      go[i * 9 + 0] = g0 * as * Ti, go[i * 9 + 1] = g1 * as * Ti, go[i * 9 + 2] = g2 * as * Ti;
+      go[i * 9 + 4] = g0 * at * Ti, go[i * 9 + 5] = g1 * at * Ti, go[i * 9 + 6] = g2 * at * Ti;
+      go[i * 9 + 8] = gb * at * Ti;
+      go[i * 9 + 3] = d * (es * Ti * gcs + ea * dA);
+      go[i * 9 + 7] = d * (et * Ti * gct + ea * dA) + (g_tsig ? g_tsig[ray * S + i] : 0.f);
+      R = (double)E + (double)ea * R;
+    } else {
+      const float pre = rw[i * C + 3] + (noise ? noise[ray * S + i] * noise_std : 0.f);
+      const float sg = fmaxf(pre, 0.f);
+      const float ea = expf(-d * sg), a = 1.f - ea;
+      const float gc = g0 * rw[i * C] + g1 * rw[i * C + 1] + g2 * rw[i * C + 2];
+      const float E = a * gc;
+      go[i * C + 0] = g0 * a * Ti, go[i * C + 1] = g1 * a * Ti, go[i * C + 2] = g2 * a * Ti;
+      go[i * C + 3] = pre > 0.f ? d * ea * (Ti * gc - Ti * (float)R) : 0.f;
+      R = (double)E + (double)ea * R;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_cast_f16_bf16(const __half* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 2;
+  if (i + 1 < n) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(src + i));
+    *reinterpret_cast<__nv_bfloat162*>(dst + i) = __floats2bfloat162_rn(f.x, f.y);
+  } else if (i < n) {
+    dst[i] = __float2bfloat16_rn(__half2float(src[i]));
+  }
+}
+
+}  // namespace dfb
+
+using namespace dfb;
+
+extern "C" int dfb_embed_xyz16(const float* rays, int ray_stride, const float* z, int64_t N, int S, int L, int ld, void* out,
+                               void* stream) {
+  DFB_REQUIRE(rays && z && out && N >= 0 && S >= 1 && L >= 0 && ray_stride >= 6, DFB_ERR_INVALID, "dfb_embed_xyz16: bad arguments");
+  DFB_REQUIRE(ld >= 3 + 6 * L && ld % 8 == 0, DFB_ERR_INVALID, "dfb_embed_xyz16: ld must be a multiple of 8 and >= 3 + 6 L");
+  const int64_t P = N * S;
+  if (P == 0) return DFB_OK;
+  k_embed_xyz16<<<(unsigned)((P + 127) / 128), 128, 0, (cudaStream_t)stream>>>(rays, ray_stride, z, P, S, L, ld, (__half*)out);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+extern "C" int dfb_rows_expand16(const float* rb, int64_t N, int S, int C, void* out, void* stream) {
+  DFB_REQUIRE(rb && out && N >= 0 && S >= 1 && C >= 8 && C % 8 == 0, DFB_ERR_INVALID, "dfb_rows_expand16: bad arguments");
+  const int64_t n = N * S * (C / 8);
+  if (n == 0) return DFB_OK;
+  k_rows_expand16<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rb, N * S, S, C, (__half*)out);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+extern "C" int dfb_rows_reduce_bf16(const void* g, int64_t N, int S, int C, float* out, void* stream) {
+  DFB_REQUIRE(g && out && N >= 0 && S >= 1 && C >= 1, DFB_ERR_INVALID, "dfb_rows_reduce_bf16: bad arguments");
+  if (N == 0) return DFB_OK;
+  k_rows_reduce<<<(unsigned)N, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)g, S, C, out);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+extern "C" int dfb_nerf_heads_fwd(const float* sig_pre, const float* rgb_pre, const float* tr_pre, int64_t P, int64_t plane_stride,
+                                  int C, float* raw, void* stream) {
+  DFB_REQUIRE(sig_pre && rgb_pre && raw && (C == 4 || (C == 9 && tr_pre)), DFB_ERR_INVALID, "dfb_nerf_heads_fwd: bad arguments");
+  if (P == 0) return DFB_OK;
+  k_heads_fwd<<<(unsigned)((P + 255) / 256), 256, 0, (cudaStream_t)stream>>>(sig_pre, rgb_pre, tr_pre, P, plane_stride, C, raw);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+extern "C" int dfb_nerf_heads_bwd(const float* raw, const float* g_raw, int64_t P, int C, void* g_sig16, void* g_rgb16, void* g_tr16,
+                                  void* stream) {
+  DFB_REQUIRE(raw && g_raw && g_sig16 && g_rgb16 && (C == 4 || (C == 9 && g_tr16)), DFB_ERR_INVALID, "dfb_nerf_heads_bwd: bad arguments");
+  if (P == 0) return DFB_OK;
+  k_heads_bwd<<<(unsigned)((P + 255) / 256), 256, 0, (cudaStream_t)stream>>>(raw, g_raw, P, C, (__nv_bfloat16*)g_sig16,
+                                                                            (__nv_bfloat16*)g_rgb16, (__nv_bfloat16*)g_tr16);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+extern "C" int dfb_raw2outputs_bwd(const float* raw, const float* z_vals, int64_t N, int S, int C, const float* noise,
+                                   float raw_noise_std, const float* g_rgb, const float* g_beta, const float* g_tsig, float* g_raw,
+                                   void* stream) {
+  DFB_REQUIRE(raw && z_vals && g_raw && (C == 4 || C == 9), DFB_ERR_INVALID, "dfb_raw2outputs_bwd: raw must be [N,S,4] or [N,S,9]");
+  DFB_REQUIRE(raw_noise_std == 0.f || (noise && C == 4), DFB_ERR_INVALID, "dfb_raw2outputs_bwd: noise applies to the coarse pass");
+  if (N == 0) return DFB_OK;
+  k_raw2outputs_bwd<<<(unsigned)((N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(raw, z_vals, N, S, C, raw_noise_std != 0.f ? noise : nullptr,
+                                                                                  raw_noise_std, g_rgb, g_beta, g_tsig, g_raw);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+extern "C" int dfb_cast_f16_bf16(const void* src, void* dst, int64_t n, void* stream) {
+  DFB_REQUIRE(src && dst && n >= 0, DFB_ERR_INVALID, "dfb_cast_f16_bf16: bad arguments");
+  if (n == 0) return DFB_OK;
+  k_cast_f16_bf16<<<(unsigned)((n / 2 + 256) / 256), 256, 0, (cudaStream_t)stream>>>((const __half*)src, (__nv_bfloat16*)dst, n);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}

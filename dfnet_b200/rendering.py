@@ -107,6 +107,12 @@ def render_rays(ray_batch, network_fn, network_query_fn=None, N_samples=64, retr
     kw = dict(network_fn=network_fn, network_fine=network_fine, embedding_a=embedding_a, embedding_t=embedding_t,
               white_bkgd=white_bkgd, raw_noise_std=raw_noise_std)
     _check_kwargs(kw)
+    if not test_time and torch.is_grad_enabled() and any(
+            p.requires_grad for m in (network_fn, network_fine, embedding_a, embedding_t) if m is not None for p in m.parameters()):
+        # NeRF-Hist training (run_nerf.py:51): differentiable w.r.t. the networks and the histogram embeddings
+        from . import nerf_train
+        return nerf_train.render_rays_train(ray_batch, network_fn, network_fine, embedding_a, embedding_t, N_samples, N_importance,
+                                            perturb=perturb, raw_noise_std=raw_noise_std, lindisp=lindisp, retraw=retraw, pytest=pytest)
     h = _handle(kw)
     N = ray_batch.shape[0]
     t_rand = u = noise = None
@@ -140,7 +146,8 @@ def render_rays(ray_batch, network_fn, network_query_fn=None, N_samples=64, retr
 def batchify_rays(rays_flat, chunk=1024 * 32, **kwargs):
     """Reference rendering.py:339-351.  The kernels bound their own workspace, so `chunk`
     only controls how the torch.rand draws are grouped when perturb > 0."""
-    if kwargs.get("perturb", 0.) > 0. or kwargs.get("raw_noise_std", 0.) > 0.:
+    if kwargs.get("perturb", 0.) > 0. or kwargs.get("raw_noise_std", 0.) > 0. or (
+            torch.is_grad_enabled() and not kwargs.get("test_time", False)):
         outs = {}
         for i in range(0, rays_flat.shape[0], chunk):
             r = render_rays(rays_flat[i:i + chunk], **kwargs)

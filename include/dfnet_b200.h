@@ -355,6 +355,32 @@ int dfb_debug_umma_gemm_mn(const float* A, const float* B, int N, int K, int fmt
                            void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * NeRF-Hist training step (run_nerf.py:32-80, models/losses.py:19-57).  The MLP layers run as 1x1
+ * convolutions over the P = N*S samples on the dfb_conv_* kernels (forward, data gradient with ReLU mask, weight
+ * gradient); these are the NeRF-specific pieces around them (all device pointers, see csrc/nerf_train.cu).
+ * ---------------------------------------------------------------------------------------------- */
+/* Re-pack an existing convolution handle from new fp32 parameters (after an optimizer step). */
+int dfb_conv_update(DfbConv* conv, const float* weight, const float* bias, const float* bn_scale, const float* bn_shift, void* stream);
+/* pts = o + d*z, positional encoding with L bands (nerfw.py:105-133) -> fp16 [N*S, ld], columns >= 3+6L zero.
+ * rays: [N, ray_stride] with o at 0..2 and d at 3..5. */
+int dfb_embed_xyz16(const float* rays, int ray_stride, const float* z, int64_t N, int S, int L, int ld, void* out, void* stream);
+/* out[p, :] = fp16(rb[p / S, :]) for p < N*S (C % 8 == 0), and its adjoint out[r, :] = sum_s g[r*S + s, :] (g bf16). */
+int dfb_rows_expand16(const float* rb, int64_t N, int S, int C, void* out, void* stream);
+int dfb_rows_reduce_bf16(const void* g, int64_t N, int S, int C, float* out, void* stream);
+/* Heads (nerfw.py:275-295): fp32 pre-activation planes [channel][P] (plane stride given) -> raw [P,C], C = 4 (static rgb,
+ * sigma) or 9 (+ transient rgb, sigma, beta; tr_pre planes in that order).  Backward: d raw -> d pre-activation as bf16
+ * [P,64] operands (zero padded) for the head layers' data / weight gradient convolutions. */
+int dfb_nerf_heads_fwd(const float* sig_pre, const float* rgb_pre, const float* tr_pre, int64_t P, int64_t plane_stride, int C,
+                       float* raw, void* stream);
+int dfb_nerf_heads_bwd(const float* raw, const float* g_raw, int64_t P, int C, void* g_sig16, void* g_rgb16, void* g_tr16,
+                       void* stream);
+/* Adjoint of raw2outputs_NeRFW (rendering.py:132-243) in train mode w.r.t. raw [N,S,C] for the outputs NerfWLoss reads:
+ * C = 9: g_rgb [N,3], g_beta [N], g_tsig [N,S] (any may be NULL); C = 4: g_rgb (+ the coarse pass' noise draws). */
+int dfb_raw2outputs_bwd(const float* raw, const float* z_vals, int64_t N, int S, int C, const float* noise, float raw_noise_std,
+                        const float* g_rgb, const float* g_beta, const float* g_tsig, float* g_raw, void* stream);
+int dfb_cast_f16_bf16(const void* src, void* dst, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Data side and evaluation around the hot path
  * ---------------------------------------------------------------------------------------------- */
 /* Luma histogram of the loaders (dataset_loaders/seven_scenes.py:346-352 with utils/color.py:29-35): img [B,3,H,W] fp32

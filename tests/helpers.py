@@ -221,3 +221,19 @@ def full_size_pair(H=480, W=640, seed=6):
     a = np.clip(base + 0.08 * rng.randn(3, H, W).astype(np.float32), 0, 1)
     b = np.clip(0.95 * np.roll(base, (3, -2), (1, 2)) + 0.02 + 0.08 * rng.randn(3, H, W).astype(np.float32), 0, 1)
     return np.stack([a, b]).astype(np.float32)
+
+
+def nerf_train_case(case):
+    """Inputs of the NeRF-Hist training-step golden (tests/golden/make_golden_nerf_train.py and the GPU test): seeded
+    networks of the reference's default width (128) and of the benchmark width (256), a bundle of rays looking at the
+    synthetic field, random target colours."""
+    W = 128 if case == "w128" else 256
+    state = torch.get_rng_state()
+    mods = my_nerfw.make_synthetic_nerf(D=8, W=W)
+    torch.set_rng_state(state)
+    rng = np.random.RandomState(31 + W)
+    n = 96
+    o = np.tile(np.array([[0.0, 0.0, 1.0]], np.float32), (n, 1)) + 0.05 * rng.randn(n, 3).astype(np.float32)
+    d = (rng.randn(n, 3) * 0.25 + np.array([0, 0, -1.0])).astype(np.float32)
+    return dict(mods=mods, rays=np.stack([o, d]).astype(np.float32), target=rng.rand(n, 3).astype(np.float32),
+                hist=np.array([[5, 10, 20, 30, 15, 10, 5, 3, 1, 1]], np.float32), Nc=16, Nf=24, near=0.0, far=2.5)

@@ -1,0 +1,184 @@
+"""NeRF-Hist training step: `render` in train mode differentiable w.r.t. the NeRF-W networks and the
+histogram embeddings, against the UNMODIFIED reference's step (tests/golden/make_golden_nerf_train.py: render(...,
+retraw=True, **render_kwargs_train) -> NerfWLoss -> backward, CPU fp32), plus kernel-level checks of the pieces."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import nerf_train_case
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def _kwargs(mods, Nc, Nf):
+    c, f, ea, et = mods
+    return dict(network_query_fn=None, perturb=0.0, N_importance=Nf, network_fine=f, N_samples=Nc, network_fn=c, use_viewdirs=True,
+                white_bkgd=False, raw_noise_std=0.0, embedding_a=ea, embedding_t=et, test_time=False, ndc=False, lindisp=False)
+
+
+@pytest.mark.parametrize("case", ["w128", "w256"])
+def test_nerf_training_step_vs_reference_golden(case):
+    from dfnet_b200 import rendering
+    from dfnet_b200.losses import loss_dict
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "nerf_train_golden.npz"))
+    cfg = nerf_train_case(case)
+    mods = [m.to(dev()) for m in cfg["mods"]]
+    for m in mods:
+        for p in m.parameters():
+            p.requires_grad_(True)
+    kw = _kwargs(mods, cfg["Nc"], cfg["Nf"])
+    rays = torch.tensor(cfg["rays"], device=dev())
+    target = torch.tensor(cfg["target"], device=dev())
+    rgb, disp, acc, extras = rendering.render(1, 1, 1.0, chunk=32768, rays=(rays[0], rays[1]), retraw=True, near=cfg["near"],
+                                              far=cfg["far"], img_idx=torch.tensor(cfg["hist"], device=dev()), **kw)
+    assert extras["raw"].shape == (rays.shape[1], cfg["Nc"] + cfg["Nf"], 9)
+    results = {"rgb_fine": rgb, "rgb_coarse": extras["rgb0"], "beta": extras["beta"], "transient_sigmas": extras["transient_sigmas"]}
+    loss_d = loss_dict["nerfw"](coef=1)(results, target)
+    loss = sum(l for l in loss_d.values())
+    loss.backward()
+    # forward: fp16 operands against the fp32 reference
+    for k, want in (("rgb", rgb), ("rgb0", extras["rgb0"]), ("beta", extras["beta"])):
+        e = float(np.abs(want.detach().cpu().numpy() - g[f"{case}_{k}"]).max() / np.abs(g[f"{case}_{k}"]).max())
+        print(case, k, "max err / max", e)
+        assert e < 2e-3, (k, e)
+    for k in ("c_l", "f_l", "b_l", "s_l"):
+        assert abs(float(loss_d[k]) - float(g[f"{case}_{k}"])) < 2e-3 * max(abs(float(g[f"{case}_{k}"])), 1e-2), k
+    assert abs(float(loss) - float(g[f"{case}_loss"])) < 1e-3 * abs(float(g[f"{case}_loss"]))
+    names = bytes(g[f"{case}_names"]).decode().split("\n")
+    got = {}
+    for tag, m in zip(("coarse", "fine", "emb_a", "emb_t"), mods):
+        for n, p in m.named_parameters():
+            got[f"{tag}.{n}"] = p.grad if p.grad is not None else torch.zeros_like(p)
+    assert sorted(got) == sorted(names)
+    worst_cos, worst_norm = (1.0, ""), (0.0, "")
+    for n in names:
+        gg = got[n].flatten()
+        want_norm = float(g[f"{case}_g_{n}_stats"][0])
+        sub = gg[:: max(1, gg.numel() // 2048)][:2048].double().cpu()
+        want = torch.from_numpy(g[f"{case}_g_{n}_sub"]).double()
+        if want_norm < 1e-12:
+            assert float(gg.norm()) < 1e-6, n
+            continue
+        cos = float(F.cosine_similarity(sub, want, dim=0)) if float(want.norm()) > 0 else 1.0
+        nr = abs(float(gg.norm()) / want_norm - 1.0)
+        worst_cos = min(worst_cos, (cos, n))
+        worst_norm = max(worst_norm, (nr, n))
+    print(case, "loss", float(loss), float(g[f"{case}_loss"]), "worst cos", worst_cos, "worst norm dev", worst_norm)
+    # bf16 gradients through fp16 activations (ReLU masks of a few units flip against the fp32 run)
+    assert worst_cos[0] > 0.995 and worst_norm[0] < 0.03, (worst_cos, worst_norm)    # measured 0.9990 / 0.8 %
+
+
+def test_raw2outputs_backward_vs_float64_autograd():
+    """dfb_raw2outputs_bwd (fine with rgb / beta / transient_sigmas upstream, coarse with noise) against float64 autograd
+    of a torch restatement of raw2outputs_NeRFW (rendering.py:132-243, train mode)."""
+    from dfnet_b200.nerf_train import _CompositeFn
+    torch.manual_seed(4)
+    N, S = 37, 40
+    z, _ = torch.sort(torch.rand(N, S, device=dev()) * 2.5, -1)
+    for typ, Cc in (("fine", 9), ("coarse", 4)):
+        raw = torch.rand(N, S, Cc, device=dev())
+        raw[..., 3] = raw[..., 3] * 6 - (1.0 if typ == "coarse" else 0.0)
+        if Cc == 9:
+            raw[..., 7] *= 3
+        noise = torch.randn(N, S, device=dev()) if typ == "coarse" else None
+        std = 0.7 if typ == "coarse" else 0.0
+        x = raw.clone().requires_grad_(True)
+        rgb, disp, acc, w, beta, tsig = _CompositeFn.apply(x, z, typ, 0.1, noise, std)
+        gr, gb, gt = torch.randn_like(rgb), torch.randn_like(beta), torch.randn(N, S, device=dev())
+        L = (rgb * gr).sum() + ((beta * gb).sum() + (tsig * gt).sum() if typ == "fine" else 0.0)
+        L.backward()
+        xd = raw.double().requires_grad_(True)
+        zd = z.double()
+        delta = torch.cat([zd[:, 1:] - zd[:, :-1], 1e2 * torch.ones_like(zd[:, :1])], -1)
+        if typ == "fine":
+            a_s, a_t = 1 - torch.exp(-delta * xd[..., 3]), 1 - torch.exp(-delta * xd[..., 7])
+            a = 1 - torch.exp(-delta * (xd[..., 3] + xd[..., 7]))
+        else:
+            a = 1 - torch.exp(-delta * torch.relu(xd[..., 3] + noise.double() * std))
+        T = torch.cumprod(torch.cat([torch.ones_like(a[:, :1]), 1 - a], -1)[:, :-1], -1)
+        if typ == "fine":
+            rgb_r = ((a_s * T)[..., None] * xd[..., :3]).sum(1) + ((a_t * T)[..., None] * xd[..., 4:7]).sum(1)
+            beta_r = (a_t * T * xd[..., 8]).sum(1) + 0.1
+            Lr = (rgb_r * gr.double()).sum() + (beta_r * gb.double()).sum() + (xd[..., 7] * gt.double()).sum()
+        else:
+            rgb_r = ((a * T)[..., None] * xd[..., :3]).sum(1)
+            Lr = (rgb_r * gr.double()).sum()
+        Lr.backward()
+        assert float((rgb.double() - rgb_r).abs().max()) < 1e-5
+        err = float((x.grad.double() - xd.grad).abs().max() / xd.grad.abs().max())
+        print(typ, "raw2outputs backward max err / max", err)
+        assert err < 2e-5
+
+
+def test_nerf_training_reduces_the_loss():
+    """A few Adam steps of the reference's loop body on one ray bundle: the loss goes down, with perturb and noise on."""
+    from dfnet_b200 import rendering
+    from dfnet_b200.losses import loss_dict
+    cfg = nerf_train_case("w128")
+    mods = [m.to(dev()) for m in cfg["mods"]]
+    params = [p for m in mods for p in m.parameters()]
+    for p in params:
+        p.requires_grad_(True)
+    opt = torch.optim.Adam(params, lr=5e-4)
+    kw = _kwargs(mods, cfg["Nc"], cfg["Nf"])
+    kw["perturb"], kw["raw_noise_std"] = 1.0, 1.0
+    rays = torch.tensor(cfg["rays"], device=dev())
+    target = torch.tensor(cfg["target"], device=dev()) * 0.2 + 0.4
+    torch.manual_seed(0)
+    hist = []
+    for it in range(40):
+        rgb, _, _, ex = rendering.render(1, 1, 1.0, chunk=32768, rays=(rays[0], rays[1]), retraw=True, near=cfg["near"], far=cfg["far"],
+                                         img_idx=torch.tensor(cfg["hist"], device=dev()), **kw)
+        opt.zero_grad()
+        ld = loss_dict["nerfw"](coef=1)({"rgb_fine": rgb, "rgb_coarse": ex["rgb0"], "beta": ex["beta"],
+                                         "transient_sigmas": ex["transient_sigmas"]}, target)
+        loss = sum(ld.values())
+        loss.backward()
+        opt.step()
+        hist.append((float(loss.detach()), float(ld["c_l"].detach())))
+    print("total loss", hist[0][0], "->", hist[-1][0], " coarse colour loss", hist[0][1], "->", hist[-1][1])
+    assert np.isfinite(np.array(hist)).all()
+    assert hist[-1][0] < hist[0][0] - 0.2 and hist[-1][1] < hist[0][1]    # NeRF-W's loss trades beta against the fine residual;
+                                                                          # the total and the (unweighted) coarse term must fall
+    # the inference path sees the updated weights (handles re-upload on version change)
+    with torch.no_grad():
+        kt = dict(kw, perturb=False, raw_noise_std=0.0, test_time=True)
+        out = rendering.render(1, 1, 1.0, rays=(rays[0], rays[1]), near=cfg["near"], far=cfg["far"],
+                               img_idx=torch.tensor(cfg["hist"], device=dev()), **kt)[0]
+    assert torch.isfinite(out).all()
+
+
+def test_train_on_batch_nerfw_loop_body():
+    """The reference's loop body as one call (run_nerf.py:33-77): random pixels of an image, loss, Adam step, lr decay."""
+    import types
+    from dfnet_b200 import nerf_train
+    from dfnet_b200.losses import loss_dict
+    cfg = nerf_train_case("w128")
+    mods = [m.to(dev()) for m in cfg["mods"]]
+    params = [p for m in mods for p in m.parameters()]
+    for p in params:
+        p.requires_grad_(True)
+    args = types.SimpleNamespace(chunk=32768, lrate=5e-4, lrate_decay=5)
+    opt = torch.optim.Adam(params, lr=args.lrate)
+    kw = _kwargs(mods, 32, 32)
+    kw["perturb"] = 1.0
+    H, W, focal = 60, 80, 73.0
+    torch.manual_seed(1)
+    np.random.seed(1)
+    target = torch.rand(3, H, W) * 0.3 + 0.3
+    pose = torch.tensor([[1., 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 1]])
+    hist = torch.tensor(cfg["hist"])
+    losses = []
+    for step in range(12):
+        loss, psnr = nerf_train.train_on_batch_nerfw(args, target, pose, hist, H, W, focal, 512, opt, loss_dict["nerfw"](coef=1), step, kw,
+                                                     near=0.0, far=2.5)
+        losses.append(float(loss))
+    assert np.isfinite(losses).all() and losses[-1] < losses[0] and torch.isfinite(psnr)
+    assert abs(opt.param_groups[0]["lr"] - args.lrate * 0.1 ** (11 / 5000)) < 1e-12
