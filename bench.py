@@ -355,6 +355,51 @@ def bench_extras(args, dev, rank, world, mma):
                 "d2h_bytes_per_step": 8},
         "dtype": f"render {mma} operands / fp32 accumulate; DFNet fp16 forward, bf16 gradients, fp32 weight gradients"}
     del Fnet, Gnet, opt
+    # ---- NeRF-Hist training step: the reference's defaults (N_rand 1536, 64+64 samples, netwidth 128) ------
+    from dfnet_b200 import nerf_train
+    from dfnet_b200.losses import loss_dict
+    tmods = [m.to(dev) for m in nerfw.make_synthetic_nerf(D=8, W=128, fine=True)]
+    tparams = [p for m in tmods for p in m.parameters()]
+    for p in tparams:
+        p.requires_grad_(True)
+    nargs = types.SimpleNamespace(chunk=32768, lrate=5e-4, lrate_decay=250)
+    nopt = torch.optim.Adam(tparams, lr=nargs.lrate, betas=(0.9, 0.999))
+    nkw = dict(network_query_fn=None, perturb=1.0, N_importance=64, network_fine=tmods[1], N_samples=64, network_fn=tmods[0],
+               use_viewdirs=True, white_bkgd=False, raw_noise_std=0.0, embedding_a=tmods[2], embedding_t=tmods[3], test_time=False,
+               ndc=False, lindisp=False)
+    nimg = torch.rand(3, 120, 160).pin_memory()
+    nloss = loss_dict["nerfw"](coef=1)
+    np.random.seed(rank)
+
+    def nerf_step(i):
+        # host image / pose in, host loss out: the loop body of train_on_epoch_nerfw (run_nerf.py:33-77)
+        loss, psnr = nerf_train.train_on_batch_nerfw(nargs, nimg, tpose[0], thist, 120, 160, 146.0, 1536, nopt, nloss, i, nkw,
+                                                     near=0.0, far=2.5)
+        return float(loss)
+
+    l0 = lib.dfb_launch_count()
+    totn, pern = _event_timed(nerf_step, 10, 4, stream, barrier)
+    out["nerf_train"] = {
+        "metric": "NeRF-Hist training steps/sec (reference defaults: N_rand 1536 rays, 64+64 samples, 8x128 NeRF-W coarse+fine, "
+                  "NerfWLoss, Adam), one image per rank, no collective (the reference trains on one GPU)",
+        "value": world * 1e3 / (max_ranks(totn) / 10), "unit": "steps/s", "ms_per_step": max_ranks(totn) / 10,
+        "ms_median": float(np.median(pern)), "gpu_launches_per_step": (lib.dfb_launch_count() - l0) / 14,
+        "rays_per_sec": world * 1536 * 1e3 / (max_ranks(totn) / 10),
+        "dtype": "fp16 activations, bf16 gradients, fp32 accumulation and weight gradients"}
+    del tmods, tparams, nopt
+    # ---- the other operand kinds / options on the headline workload ---------------------------------------------------
+    hq = ops.NerfHandle(c, f, ea, et)
+    c2w0 = torch.tensor(pose(rank * 1000), device=dev)
+    hist0 = torch.tensor(HIST, device=dev)
+    base_rgb = hq.render(NC, NF, True, c2w=c2w0, H=H, W=W, focal=FOCAL, near=NEAR, far=FAR, hist=hist0, mma=mma)["rgb"].clone()
+    for key, kwv, what in (("split_coarse", dict(mma="f16s"), "mma f16s: split-precision (hi+lo fp16, 3 MMA sub-steps) coarse pass + fp16 fine pass"),
+                           ("ert", dict(mma=mma, ert_eps=1e-3), "opt-in early ray termination, ert_eps 1e-3")):
+        msq, _ = _event_timed(lambda i: hq.render(NC, NF, True, c2w=c2w0, H=H, W=W, focal=FOCAL, near=NEAR, far=FAR, hist=hist0, **kwv),
+                              4, 3, stream, barrier)
+        oq = hq.render(NC, NF, True, c2w=c2w0, H=H, W=W, focal=FOCAL, near=NEAR, far=FAR, hist=hist0, **kwv)
+        out[key] = {"what": what, "value": world * H * W / (max_ranks(msq) / 4 * 1e-3), "unit": "rays/s", "ms_per_image": max_ranks(msq) / 4,
+                    "max_abs_rgb_diff_vs_headline": float((oq["rgb"] - base_rgb).abs().max())}
+    del hq
     # ---- config[4]: the 1920x1080, 64+192 image -------------------------------------------------------------------
     Hc, Wc, fc, nearc, farc, Ncc, Nfc = WORKLOADS["cfg5"][:7]
     h = ops.NerfHandle(c, f, ea, et)

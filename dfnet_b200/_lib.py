@@ -21,7 +21,7 @@ SYMBOLS = [
     "dfb_dfnet_bwd_workspace_bytes", "dfb_dfnet_bwd", "dfb_cosine_loss_bwd", "dfb_mse_bwd", "dfb_resize_bicubic_bwd",
     "dfb_resize_bilinear_ac_bwd", "dfb_dfnet_bwd_bucket_event", "dfb_luma_hist", "dfb_resize_area", "dfb_pose_error", "dfb_debug_conv_prof",
     "dfb_conv_update", "dfb_embed_xyz16", "dfb_rows_expand16", "dfb_rows_reduce_bf16", "dfb_nerf_heads_fwd", "dfb_nerf_heads_bwd",
-    "dfb_raw2outputs_bwd", "dfb_cast_f16_bf16",
+    "dfb_raw2outputs_bwd", "dfb_cast_f16_bf16", "dfb_render_poses_fwd",
 ]
 
 MMA_FP32_SIMT, MMA_F16, MMA_BF16, MMA_F16_SPLIT_COARSE = 0, 1, 2, 3
@@ -74,6 +74,7 @@ def _load():
     lib.dfb_render_workspace_bytes.argtypes = [vp, C.POINTER(RenderCfg), i64, C.POINTER(C.c_size_t)]
     lib.dfb_render_fwd.argtypes = [vp, C.POINTER(RenderCfg), vp, vp, i32, i32, f32, f32, f32, vp, i64, vp, vp, vp, vp, vp,
                                    vp, C.POINTER(RenderExtras), vp, C.c_size_t, vp]
+    lib.dfb_render_poses_fwd.argtypes = [vp, C.POINTER(RenderCfg), vp, i32, i32, i32, f32, f32, f32, vp, vp, vp, vp, vp, C.c_size_t, vp]
     lib.dfb_render_image_host.argtypes = [vp, C.POINTER(RenderCfg), vp, i32, i32, f32, f32, f32, vp, vp, vp, vp, vp,
                                           C.c_size_t, vp]
     lib.dfb_render_bwd_workspace_bytes.argtypes = [vp, i64, i32, C.POINTER(C.c_size_t)]

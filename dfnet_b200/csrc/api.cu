@@ -107,15 +107,37 @@ extern "C" int dfb_render_workspace_bytes(const DfbNerf* n, const DfbRenderCfg* 
   return DFB_OK;
 }
 
+static int render_fwd_impl(DfbNerf* n, const DfbRenderCfg* c, const float* rays, const float* c2w, int n_pose, int H, int W,
+                           float focal, float near, float far, const float* hist, int64_t N, const float* t_rand,
+                           const float* u, const float* noise, float* rgb, float* disp, float* acc,
+                           const DfbRenderExtras* ex, void* ws, size_t ws_bytes, void* stream);
+
 extern "C" int dfb_render_fwd(DfbNerf* n, const DfbRenderCfg* c, const float* rays, const float* c2w, int H, int W,
                               float focal, float near, float far, const float* hist, int64_t N, const float* t_rand,
                               const float* u, const float* noise, float* rgb, float* disp, float* acc,
                               const DfbRenderExtras* ex, void* ws, size_t ws_bytes, void* stream) {
+  return render_fwd_impl(n, c, rays, c2w, 1, H, W, focal, near, far, hist, N, t_rand, u, noise, rgb, disp, acc, ex, ws, ws_bytes, stream);
+}
+
+// Batched multi-pose render (random view synthesis, feature/misc.py:249-289 renders hundreds of small views one by one):
+// n_pose poses [n_pose,3,4] with their histograms [n_pose,hist_bin], one H x W image each, rays image-major.
+extern "C" int dfb_render_poses_fwd(DfbNerf* n, const DfbRenderCfg* c, const float* c2w, int n_pose, int H, int W, float focal,
+                                    float near, float far, const float* hist, float* rgb, float* disp, float* acc, void* ws,
+                                    size_t ws_bytes, void* stream) {
+  DFB_REQUIRE(c2w && hist && n_pose >= 1, DFB_ERR_INVALID, "dfb_render_poses_fwd: bad arguments");
+  return render_fwd_impl(n, c, nullptr, c2w, n_pose, H, W, focal, near, far, hist, (int64_t)n_pose * H * W, nullptr, nullptr, nullptr,
+                         rgb, disp, acc, nullptr, ws, ws_bytes, stream);
+}
+
+static int render_fwd_impl(DfbNerf* n, const DfbRenderCfg* c, const float* rays, const float* c2w, int n_pose, int H, int W,
+                           float focal, float near, float far, const float* hist, int64_t N, const float* t_rand,
+                           const float* u, const float* noise, float* rgb, float* disp, float* acc,
+                           const DfbRenderExtras* ex, void* ws, size_t ws_bytes, void* stream) {
   int rc = check_cfg(n, c);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   DFB_REQUIRE((rays != nullptr) != (c2w != nullptr), DFB_ERR_INVALID, "pass exactly one of rays / c2w");
-  DFB_REQUIRE(!c2w || ((int64_t)H * W == N && hist), DFB_ERR_INVALID, "c2w mode needs N == H*W and a histogram");
+  DFB_REQUIRE(!c2w || ((int64_t)H * W * n_pose == N && hist), DFB_ERR_INVALID, "c2w mode needs N == n_pose*H*W and a histogram");
   DFB_REQUIRE(rgb && disp && acc, DFB_ERR_INVALID, "rgb/disp/acc outputs are required");
   const DfbNerfDesc& d = n->desc;
   // the kernels index rays as r*(11+hist_bin) and hist[0..hist_bin): a record of any other width would be read
@@ -160,7 +182,7 @@ extern "C" int dfb_render_fwd(DfbNerf* n, const DfbRenderCfg* c, const float* ra
     const int64_t nr = std::min<int64_t>(chunk, N - r0);
     PrepArgs pa = {};
     pa.rays = rays ? rays + r0 * (11 + hb) : nullptr;
-    pa.c2w = c2w, pa.c2w_ld = 4, pa.H = H, pa.W = W, pa.focal = focal, pa.near = near, pa.far = far, pa.hist = hist;
+    pa.c2w = c2w, pa.c2w_ld = 4, pa.n_pose = n_pose, pa.H = H, pa.W = W, pa.focal = focal, pa.near = near, pa.far = far, pa.hist = hist;
     pa.hb = hb, pa.n_vocab = d.n_vocab, pa.emb_a = n->emb_a, pa.emb_t = n->emb_t;
     pa.N = nr, pa.Nc = Nc, pa.t_vals = d_lin, pa.t_rand = c->perturb ? t_rand + r0 * Nc : nullptr;
     pa.lindisp = c->lindisp, pa.rayrec = P(L.rayrec), pa.z = P(L.z_c);

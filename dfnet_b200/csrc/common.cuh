@@ -163,8 +163,9 @@ int launch_mlp_tc_bwd(const DfbNerf* nerf, int kind, const float* rayrec, const 
 // ---- argument blocks of the non-MLP render kernels (render_kernels.cu) ----------------
 struct PrepArgs {
   const float* rays;    // [N, 11+hb] or null
-  const float* c2w;     // [3,4] (row stride c2w_ld) or null
+  const float* c2w;     // [3,4] (row stride c2w_ld) or null; n_pose > 1: [n_pose][3][c2w_ld] back to back, image-major rays
   int c2w_ld;
+  int n_pose;           // c2w mode: number of poses (images of H x W rays each); hist is [n_pose][hb] then
   int H, W;
   float focal, near, far;
   const float* hist;    // [hb] (c2w mode)

@@ -36,6 +36,7 @@ struct DfbDfnet {
   float* bn_sh = nullptr;
   // train-mode BatchNorm of the heads (run_feature.py without freezeBN: batch statistics over the whole call's batch)
   DfbConv* head5_raw[3] = {};   // the 5x5 convs without the BatchNorm folded in
+  DfbConv* head5_raw_dg[3] = {};  // their data-gradient convolutions (training of the heads: BatchNorm differentiated separately)
   float* bn_gb = nullptr;       // [3][2][128] gamma, beta (device)
   float* bn_stat = nullptr;     // [3][4][128] batch mean, biased variance, scale, shift of the last train-mode forward
   double* bn_part = nullptr;    // [128][64][2] partial sums
@@ -60,7 +61,7 @@ static const int kTapConv[3] = {1, 6, 12};   // conv1_2, conv3_3, conv5_3
 static const int kTapCh[3] = {64, 256, 512};
 
 struct DfWs {
-  size_t in8, act[13], pool[13], tap[3], mid[3], feat, pooled, total;
+  size_t in8, act[13], pool[13], tap[3], mid[3], zbn[3], feat, pooled, total;   // zbn: pre-BatchNorm head outputs (tape only)
   int h[13], w[13];  // input resolution of every encoder conv
 };
 DfWs dfnet_ws(int B, int H, int W, int n_levels, int upH, int upW, bool tape);

@@ -310,6 +310,7 @@ extern "C" void dfb_dfnet_destroy(DfbDfnet* d) {
   for (auto c : d->head1_dg) dfb_conv_destroy(c);
   for (auto c : d->head5_dg) dfb_conv_destroy(c);
   for (auto c : d->head5_raw) dfb_conv_destroy(c);
+  for (auto c : d->head5_raw_dg) dfb_conv_destroy(c);
   if (d->bn_gb) cudaFree(d->bn_gb);
   if (d->bn_stat) cudaFree(d->bn_stat);
   if (d->bn_part) cudaFree(d->bn_part);
@@ -364,6 +365,12 @@ __global__ void k_bn_finalize(const double* __restrict__ part, double n, const f
   const double mean = s / n, var = fmax(q / n - mean * mean, 0.0);
   const float sc = gamma[c] / sqrtf((float)var + eps);
   stat[c] = (float)mean, stat[128 + c] = (float)var, stat[256 + c] = sc, stat[384 + c] = beta[c] - (float)mean * sc;
+}
+// eval-mode BatchNorm as "statistics": stat = {running_mean, running_var, scale, shift} (bn = gamma, beta, mean, var)
+__global__ void k_bn_stat_from_running(const float* __restrict__ bn, float eps, float* __restrict__ stat) {
+  const int c = threadIdx.x;
+  const float sc = bn[c] / sqrtf(bn[384 + c] + eps);
+  stat[c] = bn[256 + c], stat[128 + c] = bn[384 + c], stat[256 + c] = sc, stat[384 + c] = bn[128 + c] - bn[256 + c] * sc;
 }
 // y = x * scale[c] + shift[c]; images [0,Bs) go to out_t, [Bs,B) to out_r (siamese split; out_r unused when Bs == B)
 __global__ void __launch_bounds__(256) k_bn_apply(const float* x, int B, int Bs, int64_t plane,
@@ -432,10 +439,14 @@ extern "C" int dfb_dfnet_load_ex(DfbDfnet* d, const float* const* params, const 
       if (rc) return rc;
       if (!d->bn_gb) DFB_CHECK_CUDA(cudaMalloc(&d->bn_gb, 3 * 2 * 128 * 4));
       if (!d->bn_stat) DFB_CHECK_CUDA(cudaMalloc(&d->bn_stat, 3 * 4 * 128 * 4));
-      if (!d->bn_part) DFB_CHECK_CUDA(cudaMalloc(&d->bn_part, (size_t)128 * dfb::kBnSplits * 2 * sizeof(double)));
+      if (!d->bn_part) DFB_CHECK_CUDA(cudaMalloc(&d->bn_part, (size_t)3 * 128 * dfb::kBnSplits * 2 * sizeof(double)));
       DFB_CHECK_CUDA(cudaMemcpyAsync(d->bn_gb + (l * 2 + 0) * 128, p[4], 512, cudaMemcpyDefault, nullptr));
       DFB_CHECK_CUDA(cudaMemcpyAsync(d->bn_gb + (l * 2 + 1) * 128, p[5], 512, cudaMemcpyDefault, nullptr));
       d->bn_eps = bn_eps;
+    }
+    if (flags & 8) {  // training of the heads themselves: data gradient of the un-folded 5x5 conv
+      rc = conv_set(&d->head5_raw_dg[l], 64, 128, 5, p[2], nullptr, nullptr, nullptr, 1, 1);
+      if (rc) return rc;
     }
     if (train) {
       rc = conv_set(&d->head1_dg[l], kTapCh[l], 64, 1, p[0], nullptr, nullptr, nullptr, 1, 1);
@@ -500,6 +511,7 @@ DfWs dfnet_ws(int B, int H, int W, int n_levels, int upH, int upW, bool tape) {
       // fp32 NCHW staging: levels that need resampling, and every level under train-mode BatchNorm (the batch
       // statistics need the whole pre-BatchNorm output before anything can be written to the stacks)
       if (lv < n_levels) stage = std::max(stage, (size_t)B * h * wd * 128 * 4);
+      if (tape && lv < n_levels) w.zbn[lv] = take((size_t)B * h * wd * 128 * 4);
       ++lv;
     }
     if (kPoolAfter[i]) {
@@ -567,19 +579,32 @@ static int dfnet_fwd_impl(DfbDfnet* d, const float* x, int B, int H, int W, uint
       if (rc) return rc;
       const size_t lvl_stride = (size_t)Bs * 128 * upH * upW;
       const __half* mid = (const __half*)(base + L.mid[l]);
-      if (flags & 32) {
-        // train-mode BatchNorm: conv without the fold over the WHOLE batch -> batch statistics -> normalise
+      if (flags & (32 | 64)) {
+        // bit5, train-mode BatchNorm: conv without the fold over the WHOLE batch -> batch statistics -> normalise.
+        // bit6, heads being trained (tape): the same un-folded sequence with the pre-BatchNorm output z kept on the tape
+        // (the BatchNorm backward needs it); in eval mode the "statistics" are the running ones.
         DFB_REQUIRE(d->head5_raw[l] && d->bn_stat, DFB_ERR_INVALID, "train-mode BatchNorm variants not loaded (dfb_dfnet_load_ex flags bit2)");
-        float* featbuf = (float*)(base + L.feat);
+        const bool keep_z = (flags & 64) != 0;
+        DFB_REQUIRE(!keep_z || tape, DFB_ERR_INVALID, "flags bit6 (head tape) needs bit3 (tape)");
+        float* stagebuf = (float*)(base + L.feat);
+        float* featbuf = keep_z ? (float*)(base + L.zbn[l]) : stagebuf;
         rc = dfb_conv_fwd(d->head5_raw[l], mid, B, fh, fw, 0, nullptr, nullptr, featbuf, stream);
         if (rc) return rc;
         const int64_t fplane = (int64_t)fh * fw;
         float* stat = d->bn_stat + l * 4 * 128;
-        dfb::k_bn_partial<<<dim3(dfb::kBnSplits, 128), 256, 0, st>>>(featbuf, B, fplane, d->bn_part);
-        DFB_LAUNCH_CHECK();
-        dfb::k_bn_finalize<<<1, 128, 0, st>>>(d->bn_part, (double)B * (double)fplane, d->bn_gb + (l * 2) * 128,
-                                              d->bn_gb + (l * 2 + 1) * 128, d->bn_eps, stat);
-        DFB_LAUNCH_CHECK();
+        if (flags & 32) {
+          // (one partial-sum buffer for all levels: the levels' heads run on different streams, so each level gets its
+          // own third of it)
+          double* part = d->bn_part + (size_t)l * 128 * dfb::kBnSplits * 2;
+          dfb::k_bn_partial<<<dim3(dfb::kBnSplits, 128), 256, 0, st>>>(featbuf, B, fplane, part);
+          DFB_LAUNCH_CHECK();
+          dfb::k_bn_finalize<<<1, 128, 0, st>>>(part, (double)B * (double)fplane, d->bn_gb + (l * 2) * 128,
+                                                d->bn_gb + (l * 2 + 1) * 128, d->bn_eps, stat);
+          DFB_LAUNCH_CHECK();
+        } else {
+          dfb::k_bn_stat_from_running<<<1, 128, 0, st>>>(d->bn_stage + (size_t)l * 512, d->bn_eps, stat);
+          DFB_LAUNCH_CHECK();
+        }
         const dim3 ag((unsigned)std::min<int64_t>((fplane + 255) / 256, 64), B * 128);
         if (fh == upH && fw == upW) {
           dfb::k_bn_apply<<<ag, 256, 0, st>>>(featbuf, B, Bs, fplane, stat, feats_t + l * lvl_stride,
@@ -587,8 +612,9 @@ static int dfnet_fwd_impl(DfbDfnet* d, const float* x, int B, int H, int W, uint
           DFB_LAUNCH_CHECK();
           return DFB_OK;
         }
-        dfb::k_bn_apply<<<ag, 256, 0, st>>>(featbuf, B, B, fplane, stat, featbuf, nullptr);  // in place, then resample
+        dfb::k_bn_apply<<<ag, 256, 0, st>>>(featbuf, B, B, fplane, stat, stagebuf, nullptr);  // (in place unless z is kept), then resample
         DFB_LAUNCH_CHECK();
+        featbuf = stagebuf;
         const int planes_s = Bs * 128;
         rc = launch_resize_bilinear_ac(featbuf, feats_t + l * lvl_stride, planes_s, fh, fw, upH, upW, st);
         if (rc) return rc;
@@ -628,7 +654,7 @@ static int dfnet_fwd_impl(DfbDfnet* d, const float* x, int B, int H, int W, uint
   // resolution, 40 % of the forward's FLOPs) gets its own stream; levels 1 and 2 share one (and the fp32 staging buffer).
   // DFB_DFNET_STREAMS=0 serialises everything on the caller's stream.
   static const bool use_streams = [] { const char* e = getenv("DFB_DFNET_STREAMS"); return !(e && e[0] == '0'); }();
-  const bool fork = ret_feat && use_streams && !(flags & 32);
+  const bool fork = ret_feat && use_streams;
   if (fork && !d->side[0]) {
     for (int i = 0; i < 2; ++i) DFB_CHECK_CUDA(cudaStreamCreateWithFlags(&d->side[i], cudaStreamNonBlocking));
     for (int i = 0; i < 5; ++i) DFB_CHECK_CUDA(cudaEventCreateWithFlags(&d->ev[i], cudaEventDisableTiming));
@@ -648,7 +674,9 @@ static int dfnet_fwd_impl(DfbDfnet* d, const float* x, int B, int H, int W, uint
     if (rc) return rc;
     if (tap && fork) {  // level lv-1 is ready: its head starts on a side stream while the encoder continues
       const int l = lv - 1;
-      cudaStream_t hs = d->side[l == 0 ? 0 : 1];
+      // level 0 has its own stream when it writes straight into the stacks (no resampling: the usual case); a level that
+      // is resampled goes through the shared fp32 staging buffer and therefore shares the levels-1/2 stream
+      cudaStream_t hs = d->side[(l == 0 && L.h[kTapConv[0]] == upH && L.w[kTapConv[0]] == upW) ? 0 : 1];
       DFB_CHECK_CUDA(cudaEventRecord(d->ev[l], st));
       DFB_CHECK_CUDA(cudaStreamWaitEvent(hs, d->ev[l], 0));
       rc = run_head(l, hs);

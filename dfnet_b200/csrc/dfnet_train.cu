@@ -159,6 +159,69 @@ __global__ void k_fc_bwd(const float* __restrict__ g_pose, const float* __restri
   }
 }
 
+// BatchNorm backward of the adaptation heads (y = gamma * zhat + beta, zhat = (z - mean) * rstd), fp32 NCHW [B,128,plane].
+// Pass 1: per channel S1 = sum g_y, S2 = sum g_y * zhat (double partial sums, [128][kBnBwdSplits][2]).
+constexpr int kBnBwdSplits = 32;
+__global__ void __launch_bounds__(256) k_bn_bwd_partial(const float* __restrict__ gy, const float* __restrict__ z, int B, int64_t plane,
+                                                        const float* __restrict__ stat, float eps, double* __restrict__ part) {
+  __shared__ double sh[2][8];
+  const int c = blockIdx.y, sp = blockIdx.x;
+  const float mean = stat[c], rstd = rsqrtf(stat[128 + c] + eps);
+  const int64_t n = (int64_t)B * plane;
+  double s1 = 0.0, s2 = 0.0;
+  for (int64_t i = (int64_t)sp * 256 + threadIdx.x; i < n; i += (int64_t)kBnBwdSplits * 256) {
+    const int64_t b = i / plane, p = i - b * plane;
+    const int64_t at = (b * 128 + c) * plane + p;
+    const float g = gy[at];
+    s1 += (double)g, s2 += (double)(g * ((z[at] - mean) * rstd));
+  }
+  for (int o = 16; o > 0; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o), s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  if ((threadIdx.x & 31) == 0) sh[0][threadIdx.x >> 5] = s1, sh[1][threadIdx.x >> 5] = s2;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b2 = 0.0;
+    for (int w = 0; w < 8; ++w) a += sh[0][w], b2 += sh[1][w];
+    part[((size_t)c * kBnBwdSplits + sp) * 2] = a, part[((size_t)c * kBnBwdSplits + sp) * 2 + 1] = b2;
+  }
+}
+// sums[c] = {S1, S2}; g_gamma = S2, g_beta = S1 (nullable outputs)
+__global__ void k_bn_bwd_finalize(const double* __restrict__ part, float* __restrict__ sums, float* __restrict__ g_gamma,
+                                  float* __restrict__ g_beta) {
+  const int c = threadIdx.x;
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = 0; i < kBnBwdSplits; ++i) s1 += part[((size_t)c * kBnBwdSplits + i) * 2], s2 += part[((size_t)c * kBnBwdSplits + i) * 2 + 1];
+  sums[c] = (float)s1, sums[128 + c] = (float)s2;
+  if (g_gamma) g_gamma[c] = (float)s2;
+  if (g_beta) g_beta[c] = (float)s1;
+}
+// Pass 2: g_z = gamma * rstd * (g_y - [batch statistics] (S1 + zhat * S2) / M) -> bf16 NHWC [B,plane,128].
+// gamma * rstd = scale (stat[256 + c]).  thread = (pixel, 8-channel group), pixels fastest.
+__global__ void k_bn_bwd_apply(const float* __restrict__ gy, const float* __restrict__ z, int64_t npix, int64_t plane,
+                               const float* __restrict__ stat, const float* __restrict__ sums, float eps, int batch_stats, float inv_m,
+                               uint16_t* __restrict__ gz) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix * 16) return;
+  const int64_t pix = i % npix;
+  const int c8 = (int)(i / npix);
+  const int64_t b = pix / plane, p = pix % plane;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c8 * 8 + j;
+    const int64_t at = (b * 128 + c) * plane + p;
+    float g = __ldg(gy + at);
+    if (batch_stats) {
+      const float zh = (__ldg(z + at) - stat[c]) * rsqrtf(stat[128 + c] + eps);
+      g -= (sums[c] + zh * sums[128 + c]) * inv_m;
+    }
+    v[j] = g * stat[256 + c];
+  }
+  uint4 o;
+  o.x = tc::pack2<__nv_bfloat16>(v[0], v[1]), o.y = tc::pack2<__nv_bfloat16>(v[2], v[3]);
+  o.z = tc::pack2<__nv_bfloat16>(v[4], v[5]), o.w = tc::pack2<__nv_bfloat16>(v[6], v[7]);
+  *reinterpret_cast<uint4*>(gz + pix * 128 + c8 * 8) = o;
+}
+
 // input normalisation backward: g_x[b,c] = g_norm[b,c] / std[c]
 __global__ void k_unnorm_grad(float* __restrict__ g, int64_t plane, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -172,7 +235,7 @@ __global__ void k_unnorm_grad(float* __restrict__ g, int64_t plane, int64_t n) {
 using namespace dfb;
 
 namespace {
-struct BwdWs { size_t gA, gB, gC, gtap[3], gmid, g16, fstage, gpooled, xcvt, total; };
+struct BwdWs { size_t gA, gB, gC, gtap[3], gmid, g16, fstage, gpooled, xcvt, bnpart, bnsums, total; };
 
 BwdWs bwd_ws(int nb, int H, int W) {
   BwdWs w = {};
@@ -188,6 +251,8 @@ BwdWs bwd_ws(int nb, int H, int W) {
   w.fstage = take(px * 128 * 4);  // level 0 is resampled too when upsampleH/W differ from the input size
   w.gpooled = take((size_t)nb * 512 * 4 + 256);
   w.xcvt = take(px * 64 * 2);
+  w.bnpart = take((size_t)128 * kBnBwdSplits * 2 * sizeof(double));
+  w.bnsums = take(256 * sizeof(float));
   w.total = off;
   return w;
 }
@@ -213,9 +278,18 @@ extern "C" int dfb_dfnet_bwd(DfbDfnet* d, int B, int H, int W, uint32_t flags, i
   const bool feat_grad = ret_feat && (g_feats_t || g_feats_r) && level_mask;
   const bool pose_grad = ret_pose && g_pose;
   DFB_REQUIRE(feat_grad || pose_grad, DFB_ERR_INVALID, "no gradient given");
-  DFB_REQUIRE(!(feat_grad && pose_grad), DFB_ERR_UNSUPPORTED, "feature and pose gradients in one call are not supported");
+  // flags bit6: the forward ran the heads un-folded and kept their pre-BatchNorm outputs: the heads (1x1, 5x5, BatchNorm
+  // affine) are differentiated too (run_feature.py training); bit5 additionally means batch statistics
+  const bool head_tape = (flags & 64) != 0, bn_batch = (flags & 32) != 0;
   DFB_REQUIRE(d->enc_dg[0], DFB_ERR_INVALID, "training variants not loaded (dfb_dfnet_load_ex flags bit0)");
-  DFB_REQUIRE(!g_params || pose_grad, DFB_ERR_UNSUPPORTED, "weight gradients are implemented for the pose path");
+  DFB_REQUIRE(!g_params || pose_grad || (feat_grad && head_tape), DFB_ERR_UNSUPPORTED,
+              "parameter gradients of the feature path need a forward with the head tape (flags bit6)");
+  DFB_REQUIRE(!(feat_grad && bn_batch) || head_tape, DFB_ERR_UNSUPPORTED,
+              "the backward through train-mode BatchNorm needs a forward with the head tape (flags bit6)");
+  DFB_REQUIRE(!head_tape || !feat_grad || single || (g_feats_t && g_feats_r), DFB_ERR_UNSUPPORTED,
+              "training the heads differentiates both streams of a siamese forward");
+  DFB_REQUIRE(!head_tape || !feat_grad || d->head5_raw_dg[0], DFB_ERR_INVALID,
+              "head training variants not loaded (dfb_dfnet_load_ex flags bit3)");
   DFB_REQUIRE(!g_params || n_params == 26 + 8 * d->n_levels + 2, DFB_ERR_INVALID, "g_params has the wrong length");
   cudaStream_t st = (cudaStream_t)stream;
   const DfWs L = dfnet_ws(B, H, W, d->n_levels, upH, upW, true);
@@ -223,6 +297,8 @@ extern "C" int dfb_dfnet_bwd(DfbDfnet* d, int B, int H, int W, uint32_t flags, i
   int b0 = 0, nb = B;
   if (feat_grad && !single) {
     DFB_REQUIRE(B % 2 == 0, DFB_ERR_INVALID, "siamese mode needs an even batch");
+    DFB_REQUIRE(!pose_grad || (g_feats_t && g_feats_r), DFB_ERR_UNSUPPORTED,
+                "pose and feature gradients in one call differentiate the whole batch (both streams)");
     if (!g_feats_t) b0 = B / 2, nb = B / 2;
     else if (!g_feats_r) nb = B / 2;
   }
@@ -251,6 +327,62 @@ extern "C" int dfb_dfnet_bwd(DfbDfnet* d, int B, int H, int W, uint32_t flags, i
         if (g_feats_r) pieces[np++] = {g_feats_r, g_feats_t ? Bs : 0, Bs};
       }
       uint16_t* g16 = (uint16_t*)(sc + S.g16);
+      if (head_tape) {
+        // ---- heads being trained: BatchNorm backward on the kept pre-BatchNorm output, then weight + data gradients ----
+        const int64_t fplane = (int64_t)fh * fw, npix_all = (int64_t)nb * fplane;
+        float* gy = (float*)(sc + S.fstage);   // d loss / d y for ALL images of the call, fp32 NCHW [nb,128,fh,fw]
+        for (int p = 0; p < np; ++p) {
+          const float* src = pieces[p].g + l * lvl_stride;
+          float* dstp = gy + (size_t)pieces[p].at * 128 * fplane;
+          const int n = pieces[p].n;
+          if (fh != upH || fw != upW) {
+            DFB_CHECK_CUDA(cudaMemsetAsync(dstp, 0, (size_t)n * 128 * fplane * 4, st));
+            const int64_t tot = (int64_t)n * 128 * upH * upW;
+            k_resize_bilinear_ac_bwd<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(src, dstp, n * 128, fh, fw, upH, upW);
+            DFB_LAUNCH_CHECK();
+          } else {
+            DFB_CHECK_CUDA(cudaMemcpyAsync(dstp, src, (size_t)n * 128 * fplane * 4, cudaMemcpyDeviceToDevice, st));
+          }
+        }
+        const float* z = (const float*)(tp + L.zbn[l]);
+        const float* stat = d->bn_stat + l * 4 * 128;
+        double* part = (double*)(sc + S.bnpart);
+        float* sums = (float*)(sc + S.bnsums);
+        float* const* hp = g_params ? g_params + 26 + 8 * l : nullptr;
+        k_bn_bwd_partial<<<dim3(kBnBwdSplits, 128), 256, 0, st>>>(gy, z, nb, fplane, stat, d->bn_eps, part);
+        DFB_LAUNCH_CHECK();
+        k_bn_bwd_finalize<<<1, 128, 0, st>>>(part, sums, hp ? hp[4] : nullptr, hp ? hp[5] : nullptr);
+        DFB_LAUNCH_CHECK();
+        k_bn_bwd_apply<<<(unsigned)((npix_all * 16 + 255) / 256), 256, 0, st>>>(gy, z, npix_all, fplane, stat, sums, d->bn_eps,
+                                                                              bn_batch ? 1 : 0, 1.f / (float)npix_all, g16);
+        DFB_LAUNCH_CHECK();
+        const char* mid = tp + L.mid[l];
+        if (hp && hp[2]) {   // 5x5 conv: weight / bias gradient (input = the ReLU output of the 1x1 conv)
+          const int64_t n16 = npix_all * 64 / 8;
+          k_f16_to_bf16<<<(unsigned)((n16 + 255) / 256), 256, 0, st>>>((const uint4*)mid, (uint4*)(sc + S.xcvt), n16);
+          DFB_LAUNCH_CHECK();
+          int rc = dfb_conv_wgrad(g16, sc + S.xcvt, nb, fh, fw, 64, 64, 128, 5, 1, hp[2], hp[3], stream);
+          if (rc) return rc;
+          // batch statistics remove the per-channel mean, so d loss / d (5x5 bias) = sum g_z is exactly 0; the sum of the
+          // bf16-rounded g_z is only rounding residue
+          if (bn_batch && hp[3]) DFB_CHECK_CUDA(cudaMemsetAsync(hp[3], 0, 128 * sizeof(float), st));
+        }
+        int rc = dfb_conv_run(d->head5_raw_dg[l], g16, nb, fh, fw, 0, sc + S.gmid, nullptr, nullptr, mid, nullptr, stream);
+        if (rc) return rc;
+        if (hp && hp[0]) {   // 1x1 conv: weight / bias gradient (input = the pre-ReLU tap of the encoder)
+          const int C = kTapCh[l];
+          const int64_t n16 = npix_all * C / 8;
+          k_f16_to_bf16<<<(unsigned)((n16 + 255) / 256), 256, 0, st>>>((const uint4*)(tp + L.tap[l]), (uint4*)(sc + S.xcvt), n16);
+          DFB_LAUNCH_CHECK();
+          rc = dfb_conv_wgrad(sc + S.gmid, sc + S.xcvt, nb, fh, fw, C, C, 64, 1, 1, hp[0], hp[1], stream);
+          if (rc) return rc;
+        }
+        rc = dfb_conv_run(d->head1_dg[l], sc + S.gmid, nb, fh, fw, 0, sc + S.gtap[l], nullptr, nullptr, nullptr, nullptr, stream);
+        if (rc) return rc;
+        gtap[l] = (const uint16_t*)(sc + S.gtap[l]);
+        i_start = ci;
+        continue;
+      }
       for (int p = 0; p < np; ++p) {
         const float* src = pieces[p].g + l * lvl_stride;
         const int n = pieces[p].n;
@@ -292,13 +424,14 @@ extern "C" int dfb_dfnet_bwd(DfbDfnet* d, int B, int H, int W, uint32_t flags, i
     k_avgpool_bwd<<<(unsigned)((n5 + 255) / 256), 256, 0, st>>>(gpooled, (uint16_t*)(sc + S.gC), h5 * w5, 512, n5);
     DFB_LAUNCH_CHECK();
     uint16_t* g12 = (uint16_t*)bufs[flip];
+    const uint16_t* add12 = gtap[2];   // feature gradient of conv5_3's pre-activation tap (combined feature + pose backward)
     if ((L.h[12] | L.w[12]) & 1) {
       const int64_t n16 = (int64_t)B * L.h[12] * L.w[12] * 512 / 8;
-      k_fill16<<<(unsigned)((n16 + 255) / 256), 256, 0, st>>>((uint4*)g12, nullptr, n16);
+      k_fill16<<<(unsigned)((n16 + 255) / 256), 256, 0, st>>>((uint4*)g12, (const uint4*)add12, n16);
       DFB_LAUNCH_CHECK();
     }
     const int64_t nw = (int64_t)B * h5 * w5 * (512 / 8);
-    k_maxpool2x2_bwd<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>((const uint16_t*)act_ptr(12), (const uint16_t*)(sc + S.gC), nullptr, g12,
+    k_maxpool2x2_bwd<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>((const uint16_t*)act_ptr(12), (const uint16_t*)(sc + S.gC), add12, g12,
                                                                   B, L.h[12], L.w[12], 512);
     DFB_LAUNCH_CHECK();
     cur = g12, flip ^= 1, i_start = 12;

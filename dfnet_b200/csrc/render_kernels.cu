@@ -37,13 +37,18 @@ __global__ void __launch_bounds__(kPrepThreads) k_prep_rays(PrepArgs a) {
   if (r < a.N) {
     float o[3], d[3], vd[3], nr, fr;
     if (a.c2w) {
-      const int64_t rg = a.pix0 + r;
+      const int64_t rg0 = a.pix0 + r;
+      const int64_t hw = (int64_t)a.H * a.W;
+      const int img = a.n_pose > 1 ? (int)(rg0 / hw) : 0;       // batched multi-pose render: image-major rays
+      const int64_t rg = a.n_pose > 1 ? rg0 - (int64_t)img * hw : rg0;
+      const float* c2w = a.c2w + (size_t)img * 3 * a.c2w_ld;
+      const float* hist = a.hist + (size_t)img * a.hb;
       const int pj = (int)(rg / a.W), pi = (int)(rg % a.W);
       const float dx = __fdiv_rn(__fsub_rn((float)pi, (float)(a.W * 0.5)), a.focal);
       const float dy = -__fdiv_rn(__fsub_rn((float)pj, (float)(a.H * 0.5)), a.focal);
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        const float* R = a.c2w + k * a.c2w_ld;
+        const float* R = c2w + k * a.c2w_ld;
         d[k] = __fadd_rn(__fadd_rn(__fmul_rn(dx, R[0]), __fmul_rn(dy, R[1])), __fmul_rn(-1.0f, R[2]));
         o[k] = R[3];
       }
@@ -51,7 +56,7 @@ __global__ void __launch_bounds__(kPrepThreads) k_prep_rays(PrepArgs a) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) vd[k] = __fdiv_rn(d[k], nrm);
       nr = a.near, fr = a.far;
-      for (int b = 0; b < a.hb; ++b) hidx[tid * a.hb + b] = min(max((int)a.hist[b], 0), a.n_vocab - 1);
+      for (int b = 0; b < a.hb; ++b) hidx[tid * a.hb + b] = min(max((int)hist[b], 0), a.n_vocab - 1);
     } else {
       const float* p = a.rays + r * (11 + a.hb);
 #pragma unroll

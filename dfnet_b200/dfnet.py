@@ -56,7 +56,7 @@ class _DfnetHandle:
         self._bucket_ev = None
         self.last_flat_grad = self.last_grad_views = None
 
-    def refresh(self, module, train=False, bn_train=False):
+    def refresh(self, module, train=False, bn_train=False, head_train=False):
         # state_dict() walks and renames every tensor (~ms): cache the tensors themselves, keyed on their identity,
         # and poll their versions
         key = (id(module), tuple(id(t) for t in module.parameters()), tuple(id(t) for t in module.buffers()))
@@ -65,8 +65,10 @@ class _DfnetHandle:
         sd = self._sd
         # (the BatchNorm running statistics are buffers: a train-mode forward updates them, which bumps their versions)
         v = [(t.data_ptr(), t._version) for t in sd.values()] + [bool(train)]
-        have_bn = getattr(self, "_bn_loaded", False)
-        if v[:-1] == (self._versions or [None])[:-1] and (self._versions[-1] or not train) and (have_bn or not bn_train):
+        bn_train = bn_train or head_train      # both need the un-folded 5x5 convs and the BatchNorm vectors on the device
+        have_bn, have_ht = getattr(self, "_bn_loaded", False), getattr(self, "_ht_loaded", False)
+        if v[:-1] == (self._versions or [None])[:-1] and (self._versions[-1] or not train) and (have_bn or not bn_train) and \
+                (have_ht or not head_train):
             return
         names = [f"encoder.{i}" for i, m in enumerate(module.encoder) if isinstance(m, nn.Conv2d)]
         ts = []
@@ -84,8 +86,8 @@ class _DfnetHandle:
         # bit 1: everything is ordered on the legacy default stream -> the library skips its host synchronisation
         on_default = all(t.is_cuda for t in ts) and torch.cuda.current_stream(ts[0].device).cuda_stream == 0
         check(lib.dfb_dfnet_load_ex(self._h, ptrs, numel, len(ts), eps,
-                                    (1 if train else 0) | (2 if on_default else 0) | (4 if bn_train else 0)))
-        self._bn_loaded = bool(bn_train)
+                                    (1 if train else 0) | (2 if on_default else 0) | (4 if bn_train else 0) | (8 if head_train else 0)))
+        self._bn_loaded, self._ht_loaded = bool(bn_train), bool(head_train)
         self._versions = v
         self.n_params = len(ts)
 
@@ -94,7 +96,7 @@ class _DfnetHandle:
         through `.data` do not bump `_version`, so call this after such writes."""
         self._versions = None
 
-    def forward(self, x, return_feature, single, return_pose, upH, upW, tape=False, bf16=False, bn_train=False):
+    def forward(self, x, return_feature, single, return_pose, upH, upW, tape=False, bf16=False, bn_train=False, head_train=False):
         """tape=True keeps every activation in a fresh buffer (returned as 4th value) for `backward`.
         bn_train=True: train-mode BatchNorm in the heads (batch statistics, see `bn_batch_stats`)."""
         if not x.is_cuda:
@@ -107,7 +109,7 @@ class _DfnetHandle:
         if tape:
             check(lib.dfb_dfnet_tape_bytes(self._h, B, H, W, upH, upW, C.byref(need)))
             ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
-            flags |= 8 | (16 if bf16 else 0)
+            flags |= 8 | (16 if bf16 else 0) | (64 if head_train and return_feature else 0)
         else:
             check(lib.dfb_dfnet_workspace_bytes(self._h, B, H, W, upH, upW, C.byref(need)))
             if self._ws is None or self._ws.numel() < need.value or self._ws.device != dev:
@@ -183,8 +185,9 @@ class _DfnetHandle:
             for sh, n in zip(param_shapes, sizes):
                 grads.append(flat[off:off + n].view(sh))
                 off += n
-            head = range(26, 26 + 8 * self.n_levels)
-            ptrs = (C.c_void_p * len(grads))(*[None if i in head else g.data_ptr() for i, g in enumerate(grads)])
+            # BatchNorm running statistics (entries 6, 7 of every head) are buffers, not parameters
+            skip = {26 + 8 * l + k for l in range(self.n_levels) for k in ((6, 7) if flags & 64 else range(8))}
+            ptrs = (C.c_void_p * len(grads))(*[None if i in skip else g.data_ptr() for i, g in enumerate(grads)])
             self.last_flat_grad, self.last_grad_views = flat, grads
         sync = self.grad_sync if grads is not None and self.grad_sync is not None and self.grad_sync.world() > 1 else None
         if sync is not None:
@@ -209,10 +212,10 @@ class _DfnetFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, handle, cfg, *params):
-        return_feature, single, return_pose, upH, upW, level_mask, _bf16, bn_train = cfg
+        return_feature, single, return_pose, upH, upW, level_mask, _bf16, bn_train, head_train = cfg
         need_p = any(t.requires_grad for t in params)
         ft, fr, pose, tape = handle.forward(x, return_feature, single, return_pose, upH, upW, tape=True, bf16=bool(cfg[6]),
-                                            bn_train=bn_train)
+                                            bn_train=bn_train, head_train=head_train)
         ctx.handle, ctx.tape, ctx.cfg, ctx.need_p = handle, tape, cfg, need_p
         ctx.xshape = (x.shape[0], x.shape[2], x.shape[3])
         ctx.pshapes = [t.shape for t in params]
@@ -226,24 +229,29 @@ class _DfnetFn(torch.autograd.Function):
     def backward(ctx, *gs):
         g = dict(zip(ctx.slots, gs))
         g_ft, g_fr, g_pose = (None if g.get(k) is None else g[k].float().contiguous() for k in ("ft", "fr", "pose"))
-        return_feature, single, return_pose, upH, upW, level_mask, _bf16, bn_train = ctx.cfg
+        return_feature, single, return_pose, upH, upW, level_mask, _bf16, bn_train, head_train = ctx.cfg
         n_out = 3 + len(ctx.pshapes)
-        if bn_train and (g.get("ft") is not None or g.get("fr") is not None):
-            raise NotImplementedError("the backward through train-mode BatchNorm (run_feature.py training) is not on the B200 path yet")
+        feat_g = g_ft is not None or g_fr is not None
         if g_ft is None and g_fr is None and g_pose is None:
             return (None,) * n_out
-        if (g_ft is not None or g_fr is not None) and ctx.need_p:
-            raise NotImplementedError("parameter gradients cover the pose path (train.py); training the adaptation heads "
-                                      "(run_feature.py) is not on the B200 path yet")
-        if (g_ft is not None or g_fr is not None) and g_pose is not None:
-            raise NotImplementedError("feature and pose gradients through one DFNet forward are not on the B200 path yet")
+        if feat_g and (bn_train or ctx.need_p) and not head_train:
+            raise NotImplementedError("feature-path gradients through train-mode BatchNorm / w.r.t. parameters need the head tape "
+                                      "(a forward with trainable adaptation heads)")
+        if feat_g and head_train and not single and (g_ft is None or g_fr is None):
+            # a siamese forward whose loss reads one stream only: the other stream's gradient is zero
+            z = torch.zeros_like(g_ft if g_ft is not None else g_fr)
+            g_ft, g_fr = (g_ft if g_ft is not None else z), (g_fr if g_fr is not None else z)
+        if feat_g and g_pose is not None and not single and (g_ft is None or g_fr is None):
+            z = torch.zeros_like(g_ft if g_ft is not None else g_fr)
+            g_ft, g_fr = (g_ft if g_ft is not None else z), (g_fr if g_fr is not None else z)
         g_x, grads = ctx.handle.backward(ctx.tape, ctx.xshape, upH, upW, g_ft, g_fr, level_mask, g_pose, ctx.want_gx,
                                          ctx.pshapes if ctx.need_p else None)
         ctx.tape = None
         pg = [None] * len(ctx.pshapes)
         if grads is not None:
-            head = range(26, len(grads) - 2)
-            pg = [None if i in head else t for i, t in enumerate(grads)]
+            n_lv = (len(grads) - 28) // 8
+            skip = {26 + 8 * l + k for l in range(n_lv) for k in ((6, 7) if head_train and feat_g else range(8))}
+            pg = [None if i in skip else t for i, t in enumerate(grads)]
         return (g_x, None, None, *pg)
 
 
@@ -278,14 +286,18 @@ class DFNet(nn.Module):
             self._handle = _DfnetHandle(self)
         params = self._load_order_params()
         train = torch.is_grad_enabled() and (x.requires_grad or any(t.requires_grad for t in params))
-        self._handle.refresh(self, train=train, bn_train=bn_train)
+        # the adaptation heads themselves are trained (run_feature.py): their parameters require grad and features are returned
+        head_params = [t for l in range(len(self.hypercolumn_layers)) for t in params[26 + 8 * l:26 + 8 * l + 6]]
+        head_train = bool(train and return_feature and any(t.requires_grad for t in head_params))
+        self._handle.refresh(self, train=train, bn_train=bn_train, head_train=head_train)
         if train:
             levels = getattr(self, "grad_levels", None)
             mask = sum(1 << l for l in (range(len(self.hypercolumn_layers)) if levels is None else levels))
             # train_dtype: "f16" (default: the inference kernels' fp16 forward, bf16 gradients) or "bf16" (BASELINE config[3]:
             # bf16 storage in the pose regressor's forward as well)
             bf16 = getattr(self, "train_dtype", "f16") == "bf16" and not return_feature
-            cfg = (bool(return_feature), bool(isSingleStream), bool(return_pose), int(upsampleH), int(upsampleW), mask, bf16, bn_train)
+            cfg = (bool(return_feature), bool(isSingleStream), bool(return_pose), int(upsampleH), int(upsampleW), mask, bf16, bn_train,
+                   head_train)
             outs = list(_DfnetFn.apply(x, self._handle, cfg, *params))
             ft = outs.pop(0) if return_feature else None
             fr = outs.pop(0) if return_feature and not isSingleStream else None

@@ -207,3 +207,63 @@ def get_error_in_q(args, dl, model, sample_size, device, batch_size=1):
     print('Median error {}m and {} degrees.'.format(median_result[0], median_result[1]))
     print('Mean error {}m and {} degrees.'.format(mean_result[0], mean_result[1]))
     return median_result, mean_result
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Random view synthesis for DFNet training (reference feature/misc.py:203-289): NeRF renders of the training poses and of
+# perturbed ("virtual") poses.  The reference renders one view per render() call and pulls every image to the host; here a
+# whole batch of poses is rendered by ONE dfb_render_poses_fwd call and upsampled in one batched bicubic launch.
+# ---------------------------------------------------------------------------------------------------------------------
+def _render_pose_batch(args, poses_nerf, img_idxs, hwf, render_kwargs_test, poses_per_call=64):
+    from . import ops
+    from .rendering import DEFAULT_MMA
+    H, W, focal = hwf
+    H, W = int(H), int(W)
+    kw = render_kwargs_test
+    h = ops.handle_for(kw["network_fn"], kw.get("network_fine"), kw.get("embedding_a"), kw.get("embedding_t"))
+    tiny = bool(getattr(args, "tinyimg", False))
+    s = float(args.tinyscale) if tiny else 1.0
+    rh, rw, rf = int(H // s), int(W // s), focal / s
+    outs = []
+    for i in range(0, poses_nerf.shape[0], poses_per_call):
+        o = h.render_poses(kw["N_samples"], kw["N_importance"], poses_nerf[i:i + poses_per_call], img_idxs[i:i + poses_per_call], rh, rw,
+                           rf, kw.get("near", 0.), kw.get("far", 1.), mma=kw.get("mma") or DEFAULT_MMA, lindisp=kw.get("lindisp", False))
+        rgb = o["rgb"]
+        if tiny:
+            rgb = upsample_bicubic(rgb.permute(0, 3, 1, 2), (H, W)).permute(0, 2, 3, 1)
+        outs.append(rgb)
+    return torch.cat(outs, 0)
+
+
+def _fix_coord_supp(args, pose, world_setup_dict):
+    import numpy as np
+    pose = pose.clone()
+    pose[:, :3, 3] *= world_setup_dict["pose_scale"]
+    pose[:, :3, 3] += torch.as_tensor(np.asarray(world_setup_dict["move_all_cam_vec"], np.float32), device=pose.device)
+    pose[:, :3, 3] *= world_setup_dict["pose_scale2"]
+    return pose
+
+
+def render_virtual_imgs(args, pose_perturb, img_idxs, hwf, device, render_kwargs_test, world_setup_dict):
+    """Reference feature/misc.py:249-289 -> rgbs [n,H,W,3] (host tensor, like the reference).  pose_perturb [n,3,4] in the
+    dataset frame (rescaled to the NeRF frame like fix_coord_supp), img_idxs [n,1,hist_bin] / [n,hist_bin]."""
+    poses = _fix_coord_supp(args, torch.as_tensor(pose_perturb, dtype=torch.float32).reshape(-1, 3, 4).to(device), world_setup_dict)
+    hists = torch.as_tensor(img_idxs, dtype=torch.float32).reshape(poses.shape[0], -1).to(device)
+    with torch.no_grad():
+        return _render_pose_batch(args, poses, hists, hwf, render_kwargs_test).cpu()
+
+
+def render_nerfw_imgs(args, dl, hwf, device, render_kwargs_test, world_setup_dict):
+    """Reference feature/misc.py:203-247 -> (targets [n,H,W,3], rgbs [n,H,W,3], poses [n,3,4], img_idxs [n,1,hist_bin])
+    host tensors: the NeRF render of every training view next to its photograph."""
+    targets, poses, idxs = [], [], []
+    for target, pose, img_idx in dl:
+        targets.append(target[0].permute(1, 2, 0))
+        poses.append(pose.reshape(3, 4))
+        idxs.append(img_idx)
+    poses_t = torch.stack(poses)
+    idx_t = torch.stack(idxs)
+    with torch.no_grad():
+        rgbs = _render_pose_batch(args, _fix_coord_supp(args, poses_t.to(device).float(), world_setup_dict),
+                                  idx_t.reshape(len(poses), -1).to(device).float(), hwf, render_kwargs_test).cpu()
+    return torch.stack(targets).detach().cpu(), rgbs, poses_t.cpu(), idx_t.cpu()

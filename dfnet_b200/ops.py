@@ -159,6 +159,24 @@ class NerfHandle:
                                  C.byref(ex), _ptr(ws), ws_bytes, _stream()))
         return out
 
+    def render_poses(self, N_samples, N_importance, c2w, hist, H, W, focal, near, far, mma="f16", lindisp=False):
+        """dfb_render_poses_fwd: test-time render of n poses [n,3,4] (histograms [n,hist_bin]) in one call
+        -> dict(rgb [n,H,W,3], disp [n,H,W], acc [n,H,W])."""
+        _require_cuda(c2w, "c2w")
+        c2w = _f32c(c2w[:, :3, :4])
+        n, dev = c2w.shape[0], c2w.device
+        hist = _f32c(hist.reshape(n, -1)).to(dev)
+        if hist.shape[1] != self.desc.hist_bin:
+            raise _lib.DfbError(f"hist must be [n, hist_bin = {self.desc.hist_bin}], got {tuple(hist.shape)}")
+        cfg = _lib.RenderCfg(N_samples=N_samples, N_importance=N_importance, test_time=1, perturb=0, mma_kind=_lib.MMA_KINDS[mma],
+                             lindisp=int(bool(lindisp)), raw_noise_std=0.0, hist_len=hist.shape[1])
+        N = n * H * W
+        out = {"rgb": torch.empty(n, H, W, 3, device=dev), "disp": torch.empty(n, H, W, device=dev), "acc": torch.empty(n, H, W, device=dev)}
+        ws, ws_bytes = self.workspace(cfg, N, dev)
+        check(lib.dfb_render_poses_fwd(self._h, C.byref(cfg), _ptr(c2w), n, H, W, float(focal), float(near), float(far), _ptr(hist),
+                                       _ptr(out["rgb"]), _ptr(out["disp"]), _ptr(out["acc"]), _ptr(ws), ws_bytes, _stream()))
+        return out
+
     def render_image_host(self, cfg, c2w_host, H, W, focal, near, far, hist_host, rgb_host, disp_host, acc_host,
                           device):
         """dfb_render_image_host: pinned host pose/hist in, pinned host image out, all on the current stream."""

@@ -147,6 +147,14 @@ int dfb_render_fwd(DfbNerf* nerf, const DfbRenderCfg* cfg, const float* rays, co
                    const float* u, const float* noise, float* rgb, float* disp, float* acc,
                    const DfbRenderExtras* extras, void* ws, size_t ws_bytes, void* stream);
 
+/* Batched multi-pose render: n_pose poses c2w [n_pose,3,4] with histograms hist [n_pose,hist_bin] (device), one H x W
+ * image each in ONE call; outputs [n_pose*H*W, ...] image-major.  Random view synthesis renders hundreds of small virtual
+ * views per refresh (feature/misc.py:249-289 `render_virtual_imgs`, one render() call per view in the reference).
+ * cfg->hist_len = hist_bin.  Workspace as dfb_render_workspace_bytes for n_pose*H*W rays. */
+int dfb_render_poses_fwd(DfbNerf* nerf, const DfbRenderCfg* cfg, const float* c2w, int n_pose, int H, int W, float focal,
+                         float near, float far, const float* hist, float* rgb, float* disp, float* acc, void* ws, size_t ws_bytes,
+                         void* stream);
+
 /* Same as dfb_render_fwd with c2w/hist and the three outputs in HOST memory (pinned for
  * true asynchrony): the pose/histogram upload and the image download are enqueued on
  * `stream` around the kernels.  This is the call render_path() makes per image

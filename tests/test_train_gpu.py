@@ -327,3 +327,109 @@ def test_train_on_batch_vs_reference_golden(case, mma):
         worst_norm = max(worst_norm, (nr, n))
     print(case, mma, "loss", float(loss.reshape(-1)[0]), want_loss, "worst cos", worst_cos, "worst norm dev", worst_norm)
     assert worst_cos[0] > 0.95 and worst_norm[0] < 0.10, (worst_cos, worst_norm)
+
+
+@pytest.mark.parametrize("bn_mode", ["train", "eval"])
+def test_dfnet_head_and_encoder_training_gradients(bn_mode):
+    """run_feature.py training: ONE siamese forward returns features and pose, the loss reads both, every
+    parameter is trained - encoder, adaptation heads (1x1, 5x5, BatchNorm affine), fc_pose.  dfb_dfnet_bwd with the head
+    tape (BatchNorm backward with batch statistics or running statistics, head weight gradients, combined feature + pose
+    gradient through the encoder) against torch autograd pinned to the kernels' forward state, and against plain fp32."""
+    from dfnet_b200 import misc
+    net = synthetic_dfnet("DFNet", seed=5).to(dev())
+    with torch.no_grad():
+        _randomise_bn(net, 9)
+    net.train()
+    if bn_mode == "eval":
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.eval()
+    B, H, W = 2, 48, 64
+    torch.manual_seed(12)
+    x = torch.rand(2 * B, 3, H, W, device=dev())
+    wt = torch.randn(3, B, 128, H, W, device=dev()) / (3 * B * 128 * H * W) ** 0.5
+    wr = torch.randn(3, B, 128, H, W, device=dev()) / (3 * B * 128 * H * W) ** 0.5
+    target = torch.randn(2 * B, 12, device=dev())
+
+    def loss_of(feats, pose, mse):
+        return (feats[0] * wt).sum() + (feats[1] * wr).sum() + 0.5 * mse(pose, target)
+    feats, pose = net(x, return_feature=True, isSingleStream=False, return_pose=True, upsampleH=H, upsampleW=W)
+    loss_of(feats, pose, misc.mse).backward()
+    got = {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
+    assert len(got) == len(list(net.parameters()))
+    acts = net._handle.tape_activations()
+    for quant, pin, tol, cos_min in ((torch.float16, acts, 5e-2, 0.999), (None, None, 1.0, 0.97)):
+        net.zero_grad()
+        f_t, pose_t = torch_dfnet_forward(net, x, True, False, True, H, W, quant, pin)
+        loss_of(f_t, pose_t, F.mse_loss).backward()
+        worst = (0.0, 1.0, "")
+        for n, p in net.named_parameters():
+            if bn_mode == "train" and "adapt_layer" in n and n.endswith(".2.bias"):
+                # batch statistics remove the mean: d loss / d (5x5 bias) is exactly 0 (torch: ~1e-9 of rounding); the
+                # kernels' bf16 gradient operands leave a residue that must be negligible against the layer's weight gradient
+                assert float(got[n].abs().max()) < 2e-3 * float(got[n.replace(".bias", ".weight")].abs().max()), n
+                continue
+            err, cos = close_grad(got[n], p.grad, tol=tol, cos_min=cos_min)
+            if 1 - cos > 1 - worst[1]:
+                worst = (err, cos, n)
+        print(bn_mode, "head + encoder parameter gradients vs", quant, "worst (err, cos, name):", worst)
+
+
+def test_batched_pose_render_and_virtual_views():
+    """8f-2: dfb_render_poses_fwd renders a batch of poses in one call, bit-identical to per-pose renders;
+    render_virtual_imgs (feature/misc.py:249-289) on top of it with the tiny-image + bicubic path."""
+    import types
+    from helpers import synthetic_nets
+    from dfnet_b200 import misc, ops, rendering
+    mods, _ = synthetic_nets(8, 256)
+    c, f, ea, et = [m.to(dev()) for m in mods]
+    h = ops.NerfHandle(c, f, ea, et)
+    rng = np.random.RandomState(5)
+    n, H, W, focal = 5, 24, 40, 35.0
+    poses = np.tile(np.eye(4, dtype=np.float32)[None, :3], (n, 1, 1))
+    poses[:, :, 3] = rng.randn(n, 3) * 0.1 + np.array([0, 0, 1.0])
+    hists = np.stack([np.roll(np.array([5., 10, 20, 30, 15, 10, 5, 3, 1, 1], np.float32), i) for i in range(n)])
+    o = h.render_poses(16, 32, torch.tensor(poses, device=dev()), torch.tensor(hists, device=dev()), H, W, focal, 0.0, 2.5, mma="f16")
+    for i in range(n):
+        one = h.render(16, 32, True, c2w=torch.tensor(poses[i], device=dev()), H=H, W=W, focal=focal, near=0.0, far=2.5,
+                       hist=torch.tensor(hists[i], device=dev()), mma="f16")
+        assert torch.equal(o["rgb"][i].reshape(-1, 3), one["rgb"]) and torch.equal(o["disp"][i].reshape(-1), one["disp"])
+    kw = dict(network_query_fn=None, perturb=False, N_importance=32, network_fine=f, N_samples=16, network_fn=c, use_viewdirs=True,
+              white_bkgd=False, raw_noise_std=0.0, embedding_a=ea, embedding_t=et, test_time=True, ndc=False, lindisp=False,
+              near=0.0, far=2.5)
+    args = types.SimpleNamespace(tinyimg=True, tinyscale=4.0, chunk=32768)
+    world = dict(pose_scale=1.0, pose_scale2=1.0, move_all_cam_vec=[0.0, 0.0, 0.0])
+    Hf, Wf = 96, 160
+    rgbs = misc.render_virtual_imgs(args, torch.tensor(poses), torch.tensor(hists)[:, None], (Hf, Wf, focal * 4), dev(), kw, world)
+    assert rgbs.shape == (n, Hf, Wf, 3) and not rgbs.is_cuda
+    ref, _, _, _ = rendering.render(Hf // 4, Wf // 4, focal, c2w=torch.tensor(poses[2], device=dev()),
+                                    img_idx=torch.tensor(hists[2], device=dev()), **kw)
+    want = torch.nn.Upsample(size=(Hf, Wf), mode="bicubic")(ref[None].permute(0, 3, 1, 2))[0].permute(1, 2, 0).cpu()
+    assert float((rgbs[2] - want).abs().max()) < 2e-5
+
+
+def test_dfnet_feature_training_step_reduces_the_loss():
+    """run_feature.py's step (pose loss + triplet loss on a siamese forward, RVS pose loss), a few Adam steps."""
+    import types
+    from dfnet_b200 import feature_train
+    net = synthetic_dfnet("DFNet", seed=2).to(dev())
+    net.train()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+    args = types.SimpleNamespace(tripletloss=True, triplet_margin=1.0, combine_loss_w=[1.0, 1.0, 1.0], featurenet_batch_size=2,
+                                 freezeBN=False)
+    torch.manual_seed(3)
+    n, H, W = 6, 48, 64
+    targets, rgbs, virt = torch.rand(n, H, W, 3), torch.rand(n, H, W, 3), torch.rand(n, H, W, 3)
+    rgbs = 0.7 * targets + 0.3 * rgbs
+    poses = torch.randn(n, 3, 4) * 0.3
+    poses_p = poses + 0.05 * torch.randn(n, 3, 4)
+    np.random.seed(0)
+    hist = [feature_train.train_on_batch_with_random_view_synthesis(args, targets, rgbs, poses, virt, poses_p, net, n, None, opt, (H, W, 60.0))
+            for _ in range(6)]
+    print("DFNet training epoch losses", hist)
+    assert np.isfinite(hist).all() and hist[-1] < hist[0]
+    plain = feature_train.train_on_batch(args, targets, rgbs, poses, net, n, None, opt, (H, W, 60.0))
+    assert np.isfinite(plain)
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            assert int(m.num_batches_tracked) > 0          # train-mode BatchNorm kept its running statistics
