@@ -587,15 +587,17 @@ def main():
                         "d2h_bytes_per_step": N * 5 * 4, "images_per_sec": world * args.steps / (ms_e2e * 1e-3)},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
         line["mma"] = mma
+    extras = {}
+    if not args.no_extras and args.workload == "cfg2":
+        extras = bench_extras(args, dev, rank, world, mma)
+    if rank == 0:
+        # the CPU baseline runs LAST: torch's intra-op thread pool keeps spinning after the reference's CPU matmuls and
+        # slowed every host-bound step measured after it (train_on_batch: 30 ms instead of 20 ms per step)
         if world == 1 and not args.no_cpu_baseline:
             ref = CpuReference(args.cpu_rays)
             ref.time(256)
             v, dt = ref.time()
             line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": os.cpu_count(), "kind": ref.kind, "sample": ref.sample(dt)}
-    extras = {}
-    if not args.no_extras and args.workload == "cfg2":
-        extras = bench_extras(args, dev, rank, world, mma)
-    if rank == 0:
         line.update(extras)
         print(json.dumps(line))
     if world > 1:

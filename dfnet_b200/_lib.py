@@ -14,7 +14,7 @@ SYMBOLS = [
     "dfb_last_error", "dfb_version", "dfb_device_ok", "dfb_linspace_f32", "dfb_nerf_create", "dfb_nerf_destroy",
     "dfb_nerf_load", "dfb_nerf_set_embeddings", "dfb_nerfw_forward", "dfb_render_workspace_bytes",
     "dfb_render_fwd", "dfb_render_image_host", "dfb_render_bwd", "dfb_render_bwd_mma", "dfb_render_bwd_saved", "dfb_render_bwd_workspace_bytes", "dfb_sample_pdf", "dfb_raw2outputs", "dfb_get_rays",
-    "dfb_launch_count", "dfb_profile_enable", "dfb_profile_read", "dfb_debug_umma_gemm", "dfb_debug_umma_gemm_mn", "dfb_debug_tc_prof", "dfb_debug_bwd_masks", "dfb_debug_umma_rate", "dfb_debug_tmem_rate", "dfb_debug_tmem_rate_mma", "dfb_conv_create", "dfb_conv_destroy", "dfb_conv_fwd",
+    "dfb_launch_count", "dfb_profile_enable", "dfb_profile_read", "dfb_debug_umma_gemm", "dfb_debug_umma_gemm_mn", "dfb_debug_tc_prof", "dfb_debug_tcb_prof", "dfb_debug_bwd_masks", "dfb_debug_umma_rate", "dfb_debug_tmem_rate", "dfb_debug_tmem_rate_mma", "dfb_conv_create", "dfb_conv_destroy", "dfb_conv_fwd",
     "dfb_dfnet_create", "dfb_dfnet_destroy", "dfb_dfnet_load", "dfb_dfnet_workspace_bytes", "dfb_dfnet_fwd",
     "dfb_cosine_loss", "dfb_triplet_loss", "dfb_triplet_loss_bwd", "dfb_mse", "dfb_resize_bicubic", "dfb_resize_bilinear_ac",
     "dfb_conv_create_ex", "dfb_conv_fwd_ex", "dfb_conv_wgrad", "dfb_dfnet_load_ex", "dfb_dfnet_bn_batch_stats", "dfb_dfnet_tape_bytes", "dfb_debug_dfnet_tape_layout",
@@ -88,6 +88,7 @@ def _load():
     lib.dfb_debug_umma_gemm.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
     lib.dfb_debug_umma_gemm_mn.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp]
     lib.dfb_debug_tc_prof.argtypes = [vp, i32]
+    lib.dfb_debug_tcb_prof.argtypes = [vp, i32]
     lib.dfb_debug_umma_rate.argtypes = [i32, i32, i32, C.POINTER(C.c_double)]
     lib.dfb_debug_tmem_rate.argtypes = [i32, i32, i32, C.POINTER(C.c_double)]
     lib.dfb_debug_tmem_rate_mma.argtypes = [i32, i32, i32, i32, C.POINTER(C.c_double)]

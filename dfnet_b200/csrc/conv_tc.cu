@@ -400,9 +400,24 @@ struct PackArgs {
   int64_t total;    // elements of the image
 };
 
-// weight image: [n tile][channel slice][weight stage][tap in stage][8 panels][nt rows][8 elements]; one thread = one element
-__global__ void k_pack_conv_weights(const PackArgs a) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// weight image: [n tile][channel slice][weight stage][tap in stage][8 panels][nt rows][8 elements]; one thread = the 8
+// elements (input channels) of one row = one 16-byte store.  Batched: a training loop re-packs every convolution of the
+// pose regressor after each optimizer step (51 images), which as one launch per image cost ~1 ms of the 20 ms step.
+constexpr int kMaxPack = 64;
+struct PackBatchArgs {
+  int n;
+  int blk0[kMaxPack + 1];   // first block of every entry
+  PackArgs e[kMaxPack];
+};
+
+__global__ void __launch_bounds__(256) k_pack_conv_weights(const __grid_constant__ PackBatchArgs b) {
+  int lo = 0, hi = b.n;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if ((int)blockIdx.x >= b.blk0[mid]) lo = mid; else hi = mid;
+  }
+  const PackArgs& a = b.e[lo];
+  const int64_t i = (int64_t)((int)blockIdx.x - b.blk0[lo]) * blockDim.x + threadIdx.x;   // 8-element group
   if (i < a.Cout) {
     float bf = 0.f;
     if (!a.dgrad) {  // y = scale * (conv + bias) + shift
@@ -411,9 +426,8 @@ __global__ void k_pack_conv_weights(const PackArgs a) {
     }
     a.bias[i] = bf;
   }
-  if (i >= a.total) return;
+  if (i * 8 >= a.total) return;
   int64_t r = i;
-  const int e = (int)(r % 8); r /= 8;
   const int rows = a.nt / a.cg;
   int rr = (int)(r % rows); r /= rows;
   const int pp = (int)(r % 8); r /= 8;
@@ -423,18 +437,61 @@ __global__ void k_pack_conv_weights(const PackArgs a) {
   const int cc = (int)(r % a.n_cc); r /= a.n_cc;
   const int t = (int)r;
   const int tp = ws * a.tps + tis;
-  float v = 0.f;
+  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (tp < a.KH * a.KW) {
     const int ky = tp / a.KW, kx = tp % a.KW;
-    const int ci = (cc * 8 + pp) * 8 + e, n = t * a.nt + rr;
+    const int ci0 = (cc * 8 + pp) * 8, n = t * a.nt + rr;
+    const int64_t kk = (int64_t)a.KH * a.KW;
     if (!a.dgrad) {
-      if (ci < a.Cin0) v = (a.sc ? a.sc[n] : 1.f) * a.w[(((int64_t)n * a.Cin0 + ci) * a.KH + ky) * a.KW + kx];
-    } else if (n < a.Cin0 && ci < a.Cout0) {
+      const float scn = a.sc ? a.sc[n] : 1.f;
+      const float* src = a.w + ((int64_t)n * a.Cin0 + ci0) * kk + ky * a.KW + kx;
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (ci0 + e < a.Cin0) v[e] = scn * src[e * kk];
+    } else if (n < a.Cin0) {
       // data gradient: n = input channel of the layer, ci = its output channel, filter flipped
-      v = (a.sc ? a.sc[ci] : 1.f) * a.w[(((int64_t)ci * a.Cin0 + n) * a.KH + (a.KH - 1 - ky)) * a.KW + (a.KW - 1 - kx)];
+      const float* src = a.w + ((int64_t)ci0 * a.Cin0 + n) * kk + (a.KH - 1 - ky) * a.KW + (a.KW - 1 - kx);
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (ci0 + e < a.Cout0) v[e] = (a.sc ? a.sc[ci0 + e] : 1.f) * src[(int64_t)e * a.Cin0 * kk];
     }
   }
-  a.img[i] = a.fmt ? __bfloat16_as_ushort(__float2bfloat16_rn(v)) : __half_as_ushort(__float2half_rn(v));
+  uint32_t pk[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t lo16 = a.fmt ? __bfloat16_as_ushort(__float2bfloat16_rn(v[2 * q])) : __half_as_ushort(__float2half_rn(v[2 * q]));
+    const uint32_t hi16 = a.fmt ? __bfloat16_as_ushort(__float2bfloat16_rn(v[2 * q + 1])) : __half_as_ushort(__float2half_rn(v[2 * q + 1]));
+    pk[q] = lo16 | (hi16 << 16);
+  }
+  reinterpret_cast<uint4*>(a.img)[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+}
+
+// Packing requests collected between pack_batch_begin() and pack_batch_flush() (dfb_dfnet_load_ex) go out as ONE launch
+// on the legacy default stream; outside such a bracket every request is launched at once.
+struct PackBatch {
+  PackBatchArgs args;
+  bool open = false;
+};
+static thread_local PackBatch g_pack;
+
+static int pack_launch(cudaStream_t st) {
+  if (g_pack.args.n == 0) return DFB_OK;
+  k_pack_conv_weights<<<(unsigned)g_pack.args.blk0[g_pack.args.n], 256, 0, st>>>(g_pack.args);
+  g_pack.args.n = 0;
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+static int pack_push(const PackArgs& a, cudaStream_t st) {
+  if (g_pack.args.n == kMaxPack) {
+    const int rc = pack_launch(st);
+    if (rc) return rc;
+  }
+  const int64_t groups = std::max<int64_t>(a.total / 8, a.Cout);
+  const int k = g_pack.args.n++;
+  if (k == 0) g_pack.args.blk0[0] = 0;
+  g_pack.args.e[k] = a;
+  g_pack.args.blk0[k + 1] = g_pack.args.blk0[k] + (int)((groups + 255) / 256);
+  return g_pack.open ? DFB_OK : pack_launch(st);
 }
 
 }  // namespace conv
@@ -474,15 +531,34 @@ int dfb_conv_update_impl(DfbConv* c, const float* weight, const float* bias, con
   a.n_ntiles = c->n_ntiles, a.n_cc = c->n_cc, a.tps = c->tps, a.n_wst = c->n_wst, a.fmt = c->fmt, a.dgrad = c->dgrad;
   a.total = (int64_t)c->wimg_bytes / 2;
   a.cg = 1;
-  conv::k_pack_conv_weights<<<(unsigned)((a.total + 255) / 256), 256, 0, st>>>(a);
-  DFB_LAUNCH_CHECK();
-  if (c->wimg2) {
-    a.img = (uint16_t*)c->wimg2, a.cg = 2;
-    conv::k_pack_conv_weights<<<(unsigned)((a.total + 255) / 256), 256, 0, st>>>(a);
-    DFB_LAUNCH_CHECK();
+  // staged (host) sources are released right below, so their request cannot wait for a batched launch
+  const bool was_open = conv::g_pack.open;
+  if (stage) {
+    const int rc0 = conv::pack_launch(st);
+    if (rc0) return rc0;
+    conv::g_pack.open = false;
   }
+  int rc = conv::pack_push(a, st);
+  if (!rc && c->wimg2) {
+    a.img = (uint16_t*)c->wimg2, a.cg = 2;
+    rc = conv::pack_push(a, st);
+  }
+  conv::g_pack.open = was_open;
   if (stage) DFB_CHECK_CUDA(cudaFreeAsync(stage, st));
-  return DFB_OK;
+  return rc;
+}
+
+// Bracket for callers that (re)pack many convolutions in a row on the legacy default stream (dfb_dfnet_load_ex).
+void dfb_conv_pack_batch_begin() { conv::g_pack.open = true; }
+int dfb_conv_pack_batch_flush(bool discard) {
+  conv::g_pack.open = false;
+  if (discard) conv::g_pack.args.n = 0;   // a failed load may have destroyed handles the pending requests point to
+  return conv::pack_launch(nullptr);
+}
+// DFB_CONV_CTA_GROUP=2 selects the cta_group::2 kernel and its second weight image (see dfb_conv_run)
+static int conv_cg_env() {
+  static const int cg_env = [] { const char* e = getenv("DFB_CONV_CTA_GROUP"); return (e && e[0] == '2') ? 2 : 1; }();
+  return cg_env;
 }
 
 // fmt: 0 fp16 / 1 bf16 operands.  dgrad != 0 builds the DATA-GRADIENT convolution of the layer described by
@@ -522,8 +598,8 @@ int dfb_conv_create_impl(int Cin0, int Cout0, int KH, int KW, const float* weigh
   c->n_wst = (KH * KW + c->tps - 1) / c->tps;
   c->num_sms = sms;
   c->wimg_bytes = (size_t)c->n_ntiles * c->n_cc * c->n_wst * c->tps * c->nt * 16 * 8;
-  if (cudaMalloc(&c->wimg, c->wimg_bytes) != cudaSuccess || cudaMalloc(&c->wimg2, c->wimg_bytes) != cudaSuccess ||
-      cudaMalloc(&c->bias, Cout * 4) != cudaSuccess) {
+  if (cudaMalloc(&c->wimg, c->wimg_bytes) != cudaSuccess ||
+      (conv_cg_env() == 2 && cudaMalloc(&c->wimg2, c->wimg_bytes) != cudaSuccess) || cudaMalloc(&c->bias, Cout * 4) != cudaSuccess) {
     dfb_conv_destroy(c);
     DFB_REQUIRE(false, DFB_ERR_CUDA, "dfb_conv_create: out of device memory");
   }
@@ -626,8 +702,7 @@ int dfb_conv_run(DfbConv* c, const void* in_nhwc16, int B, int H, int W, int rel
   // DFB_CONV_CTA_GROUP=2 selects the cta_group::2 kernel (CTA pairs share every weight stage).  Measured (r02, tools/
   // conv_prof.py): with TMA patch loads both kernels wait < 15 % for operands and run the 3x3 / 5x5 layers at the same
   // speed; the pair kernel is slower on the epilogue-bound layers (conv1_1, 1x1), so the 1-CTA kernel is the default.
-  static const int cg_env = [] { const char* e = getenv("DFB_CONV_CTA_GROUP"); return (e && e[0] == '2') ? 2 : 1; }();
-  const int cg = (c->wimg2 && n_mtiles >= 2) ? cg_env : 1;
+  const int cg = (c->wimg2 && n_mtiles >= 2) ? conv_cg_env() : 1;
   const int64_t n_tiles = ((n_mtiles + cg - 1) / cg) * a.n_ntiles;
   const int grid = cg * (int)std::min<int64_t>(n_tiles, c->num_sms / cg);
   const int nb = cg == 2 ? conv::kBStages2 : conv::kBStages;

@@ -393,8 +393,20 @@ static int conv_set(DfbConv** slot, int Cin, int Cout, int K, const float* w, co
 // params: 13 x (conv weight, bias), then per level (w1x1, b1x1, w5x5, b5x5, bn_weight, bn_bias,
 // bn_running_mean, bn_running_var), then fc_pose weight, bias — fp32, host or device memory.
 // flags bit0: also (re)build the training variants (bf16 forward and data-gradient convolutions).
+static int dfnet_load_impl(DfbDfnet* d, const float* const* params, const int64_t* numel, int n_params, float bn_eps, uint32_t flags);
+
 extern "C" int dfb_dfnet_load_ex(DfbDfnet* d, const float* const* params, const int64_t* numel, int n_params, float bn_eps,
                                  uint32_t flags) {
+  // every (re)packing request of the call goes out as one launch (conv_tc.cu, k_pack_conv_weights); the flush precedes
+  // the copies / synchronisation at the end of dfnet_load_impl only in stream order, which is all they need
+  dfb_conv_pack_batch_begin();
+  const int rc = dfnet_load_impl(d, params, numel, n_params, bn_eps, flags);
+  const int rc2 = dfb_conv_pack_batch_flush(rc != 0);
+  if (!rc && !rc2 && !(flags & 2)) DFB_CHECK_CUDA(cudaStreamSynchronize(nullptr));
+  return rc ? rc : rc2;
+}
+
+static int dfnet_load_impl(DfbDfnet* d, const float* const* params, const int64_t* numel, int n_params, float bn_eps, uint32_t flags) {
   DFB_REQUIRE(d && params && numel, DFB_ERR_INVALID, "null argument");
   const int expect = 26 + 8 * d->n_levels + 2;
   DFB_REQUIRE(n_params == expect, DFB_ERR_INVALID, "expected %d tensors, got %d", expect, n_params);

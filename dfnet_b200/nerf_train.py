@@ -66,13 +66,18 @@ def _conv(handle, x, Hh, relu, out=None, tap=None, nchw=None, mask=None, addend=
     check(lib.dfb_conv_fwd_ex(handle, _p(x), 1, Hh, 8, int(relu), _p(out), _p(tap), _p(nchw), _p(mask), _p(addend), _st()))
 
 
+def trainable_shape(net):
+    """True for the network shapes the training executor covers (8 layers, netwidth 128 / 256, skip at 4, 10 xyz bands)."""
+    return net.D == 8 and list(net.skips) == [4] and net.W % 128 == 0 and net.in_channels_xyz == 63
+
+
 class NetTrainer:
     """Layer-wise training executor of one NeRFW module (coarse: static branch; fine: static + transient)."""
 
     def __init__(self, net):
         dev = next(net.parameters()).device
         W, H2 = net.W, net.W // 2
-        if net.D != 8 or list(net.skips) != [4] or W % 128 != 0 or net.in_channels_xyz != 63:
+        if not trainable_shape(net):
             raise NotImplementedError("NeRF training on the B200 path covers the 8-layer networks with netwidth 128 or 256 "
                                       "(the reference default and the benchmark shape), skip at layer 4, 10 xyz bands")
         self.net, self.dev, self.W, self.H2, self.fine = net, dev, W, H2, net.typ == "fine"

@@ -109,10 +109,14 @@ def render_rays(ray_batch, network_fn, network_query_fn=None, N_samples=64, retr
     _check_kwargs(kw)
     if not test_time and torch.is_grad_enabled() and any(
             p.requires_grad for m in (network_fn, network_fine, embedding_a, embedding_t) if m is not None for p in m.parameters()):
-        # NeRF-Hist training (run_nerf.py:51): differentiable w.r.t. the networks and the histogram embeddings
+        # NeRF-Hist training (run_nerf.py:51): differentiable w.r.t. the networks and the histogram embeddings.  Other
+        # network shapes render through the forward kernels below; their outputs carry no gradient to the parameters
+        # (freshly constructed modules require grad by default, so this is also the path of a plain train-mode render).
         from . import nerf_train
-        return nerf_train.render_rays_train(ray_batch, network_fn, network_fine, embedding_a, embedding_t, N_samples, N_importance,
-                                            perturb=perturb, raw_noise_std=raw_noise_std, lindisp=lindisp, retraw=retraw, pytest=pytest)
+        if all(nerf_train.trainable_shape(m) for m in (network_fn, network_fine) if m is not None):
+            return nerf_train.render_rays_train(ray_batch, network_fn, network_fine, embedding_a, embedding_t, N_samples, N_importance,
+                                                perturb=perturb, raw_noise_std=raw_noise_std, lindisp=lindisp, retraw=retraw,
+                                                pytest=pytest)
     h = _handle(kw)
     N = ray_batch.shape[0]
     t_rand = u = noise = None

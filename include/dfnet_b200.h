@@ -280,6 +280,10 @@ int dfb_profile_read(double* coarse_ms, double* fine_ms, int64_t* coarse_launche
 /* Debug seam: per-CTA cycle counters of the last tcgen05 MLP launch; only libraries built with
  * -DDFB_TC_PROF record them (returns DFB_ERR_UNSUPPORTED otherwise). out_host: [n_cta][16] u64. */
 int dfb_debug_tc_prof(unsigned long long* out_host, int n_cta);
+/* Same for the tcgen05 render backward (k_mlp_tc_bwd): out_host [n_cta][64] u64 = producer {wait W_EMPTY,-,-,total},
+ * issuer {wait W_FULL, wait A_READY / PASS_DONE, wait PE_READY, total}, epilogue slot 0 / slot 1 {wait D_FULL,-,-,total},
+ * then the busy cycles of slot 0's epilogue per program step (tools/tcb_prof.py). */
+int dfb_debug_tcb_prof(unsigned long long* out_host, int n_cta);
 /* Debug seam (tests only): ReLU masks of the render backward's forward recompute, device buffers [P][12][8] uint32
  * (fine 8x256 network, N <= 16384 rays).  simt_dump <- fp32 kernels (word j bit l = column 32j+l); tc_out <- tcgen05
  * kernel (bit 16*(c&1) + (c>>1)%16 of word c/32 = column c); tc_in replaces the tcgen05 kernel's own masks so that its
