@@ -266,9 +266,11 @@ static int render_fwd_impl(DfbNerf* n, const DfbRenderCfg* c, const float* rays,
     float* rb_f = P(L.rb_f);
     // tcgen05 path: the per-ray bias carries the step's constant bias and is stored as packed 16-bit pairs
     const bool tc_f = c->mma_kind != DFB_MMA_FP32_SIMT && tc_supported(n, 1, MLP_FULL);
+    // (the native 128-wide program reads the two halves contiguously, the padded embedding at columns 0 / 128)
+    const bool nat_f = tc_f && tc_native128(n, 1, ex && ex->relu_masks, false);
     rc = launch_raybias(pa.extra, pa.n_extra, nr, n->net[1], true, rb_f, tc_f ? 256 : n->net[1].n_dt, st,
-                        tc_f ? n->net[1].tc_dtbias_dev : nullptr, tc_f ? (eff_kind(c->mma_kind) == DFB_MMA_F16 ? 1 : 2) : 0,
-                        tc_f ? 128 : 0);
+                        tc_f ? (nat_f ? n->net[1].tc_dtbias_n_dev : n->net[1].tc_dtbias_dev) : nullptr,
+                        tc_f ? (eff_kind(c->mma_kind) == DFB_MMA_F16 ? 1 : 2) : 0, tc_f && !nat_f ? 128 : 0);
     if (rc) return rc;
     float* raw_f = ex && ex->raw ? ex->raw + r0 * S * 9 : P(L.raw_f);
     uint32_t* masks = nullptr;

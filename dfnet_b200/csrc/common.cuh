@@ -93,6 +93,11 @@ struct NetPack {
   void* blob16x3 = nullptr;
   size_t blob16x3_bytes = 0;
   float* tc_bias32_dev = nullptr;
+  // native 128-wide program (W == 128, the reference's default netwidth; mlp_tc.cu build_program): cta_group::2 images
+  void* blob16n[2] = {nullptr, nullptr};  // [fp16|bf16]
+  size_t blob16n_bytes = 0;
+  std::vector<float> tc_tbl_n;
+  float* tc_dtbias_n_dev = nullptr;       // [128] contiguous [dir 64 | transient 64]
 
   // ---- tcgen05 backward layout (fine 8x256 network): the 26-step image of mlp_tc_bwd.cu ------
   void* blob16b[2] = {nullptr, nullptr};  // [fp16|bf16]
@@ -149,6 +154,8 @@ int make_weight_tmap(void* base, size_t bytes, CUtensorMap* out);
 // (a ReLU unit with zero input weights and bias stays at 0 and feeds nothing): tc_pad_params returns the state dict
 // of the equivalent 8x256 network (state-dict order, hidden units 0..W-1 / 0..W/2-1 live).
 bool tc_padded_shape(const dfb::NetPack& np);
+int tc_cta_group_env();
+bool tc_native128(const DfbNerf* nerf, int which, bool masks, bool split3);
 std::vector<std::vector<float>> tc_pad_params(const dfb::NetPack& np, const std::vector<std::vector<float>>& P);
 int pack_tc_weights(DfbNerf* nerf, int which, const std::vector<std::vector<float>>& P);
 // tcgen05 backward of the fine network w.r.t. its inputs (mlp_tc_bwd.cu)

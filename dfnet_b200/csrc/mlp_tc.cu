@@ -67,7 +67,7 @@ enum Bar { W_FULL = 0, W_EMPTY = 4, D_FULL = 8, A_READY = 10, PASS_DONE = 12, PE
 
 struct Step {
   int n_chunks;    // 16 KB weight chunks streamed for this step
-  int ksteps;      // K=16 MMA steps per chunk
+  int ksteps;      // K=16 MMA steps issued per chunk (the native 128-wide program leaves the tail of some chunks unused)
   int n;           // MMA N (256 or 128)
   int a_panel0;    // first A-operand panel of the step
   int chunk_base;  // index of the step's first chunk in the packed weight image
@@ -86,6 +86,11 @@ struct TcArgs {
   int n_epi;              // epilogue steps (= layers)
   int kind[kMaxSteps];    // EpiKind of every epilogue step (EPI_DT = head + store halves)
   int last_pe_step;       // last SUB-step that reads the PE panels (skip layer)
+  // network width in 64-column units: 4 = the 8x256 program (also every narrower network embedded in it), 2 = the native
+  // 8x128 program (the reference's default netwidth, models/options.py:31): 128-column trunk steps, 64-column transient
+  // steps, positional encoding in panels 16..23 so that [h | PE] stays one contiguous K range, panels 24..31 zero
+  int hb;
+  int pe_panel0;          // first A panel of the positional encoding (32, or 16 in the native 128-wide program)
   const void* wimg;       // packed 16-bit weight image, chunk i at wimg + i*16 KB
   const float* bias32;    // X3 only: fp32 biases in global memory, [epilogue step][256]
   const float* rayrec;    // [n_rays,12]
@@ -209,7 +214,7 @@ __device__ __forceinline__ void epi_block(const uint32_t (&v)[32], const TcArgs&
     for (int q = 0; q < 16; ++q) m |= gt0_mask2<T>(pk[q]) & (0x00010001u << q);
     mrow[cb * 128] = m;
   }
-  const uint32_t dst = h_row + (uint32_t)(((cb + 4) & 7) * 4) * kPanelBytes;
+  const uint32_t dst = h_row + (uint32_t)(((cb + a.hb) & (2 * a.hb - 1)) * 4) * kPanelBytes;
 #pragma unroll
   for (int q = 0; q < 4; ++q) st_shared_v4(dst + q * kPanelBytes, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
 }
@@ -220,6 +225,7 @@ __device__ __forceinline__ void epi_block(const uint32_t (&v)[32], const TcArgs&
 template <typename T, int KIND, bool MK>
 __device__ __forceinline__ void epi_blocks(uint32_t t_row, uint32_t h_row, const TcArgs& a, int bias_off, int cb0, int cb1,
                                            const float* rb, uint32_t* mrow) {
+  if (cb0 >= cb1) return;
   uint32_t v0[32], v1[32];
   tmem_ld32(t_row + cb0 * 32, v0);
 #pragma unroll 1
@@ -348,8 +354,9 @@ __device__ __forceinline__ void epi_blocks_x3(uint32_t t_row, uint32_t h_row, co
 template <int CG, int KS>
 __device__ __forceinline__ void issue_step(uint32_t& stage, uint32_t& phase, int nch, uint32_t a_lo, uint32_t b_rows,
                                            uint32_t d_tmem, uint32_t idesc, uint32_t sW, uint32_t sBar, int* err,
-                                           unsigned long long* prof_acc, uint32_t acc = 0) {
+                                           unsigned long long* prof_acc, uint32_t acc = 0, int kcap = KS) {
   // acc = 1: the sub-step continues the accumulator of the previous one (split-precision coarse pass)
+  // kcap (CG = 2 only): K=16 steps issued per chunk
   const uint32_t desc_hi = (128u >> 4) | (1u << 14);  // SBO 128 B, descriptor version 1, no swizzle
   const uint32_t b_step = 2u * b_rows;                // (2 panels * b_rows * 16 B) >> 4
   if (CG == 1) {
@@ -387,7 +394,7 @@ __device__ __forceinline__ void issue_step(uint32_t& stage, uint32_t& phase, int
     if (elect_one()) {
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks)
-        umma_f16<CG>(d_tmem, mk64(a_lo + ks * 256, desc_hi), mk64(b_lo + ks * b_step, desc_hi), idesc, acc | ks);
+        if (ks < kcap) umma_f16<CG>(d_tmem, mk64(a_lo + ks * 256, desc_hi), mk64(b_lo + ks * b_step, desc_hi), idesc, acc | ks);
       umma_commit<CG>(sBar + 8u * (W_EMPTY + stage));
     }
     __syncwarp();
@@ -433,14 +440,25 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar(D_FULL + s), 1);
-      mbar_init(bar(A_READY + s), 256 * CG);   // both epilogue warpgroups arrive for every slot
-      mbar_init(bar(PASS_DONE + s), 256 * CG);
-      mbar_init(bar(PE_READY + s), 128 * CG);
+      // ONE arrival per warp (lane 0, after __syncwarp): with one arrival per thread the 512 remote release-arrivals per
+      // (layer, slot) were 38-46 % of the epilogue warps' time (tools/tc_prof.py)
+      mbar_init(bar(A_READY + s), 8 * CG);     // both epilogue warpgroups arrive for every slot
+      mbar_init(bar(PASS_DONE + s), 8 * CG);
+      mbar_init(bar(PE_READY + s), 4 * CG);
       mbar_init(bar(PE_FREE + s), 1);
     }
     fence_barrier_init();
   }
   if (warp == 13) tmem_alloc<CG>(smem_u32(tmem_slot), 512);
+  if (a.hb == 2) {
+    // native 128-wide program: panels 24..31 of both slots are read by the K = 128 / 256 ranges of layer 0, the skip layer
+    // and the sigma step against zero weights; they must hold finite values (0 x NaN is NaN)
+    for (int i = tid; i < 2 * 8 * (kPanelBytes / 16); i += kThreads) {
+      const int sl = i / (8 * (kPanelBytes / 16)), o = i % (8 * (kPanelBytes / 16));
+      st_shared_v4(sA + sl * kSlotBytes + 24 * kPanelBytes + o * 16, 0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async();
+  }
   tc_fence_before();
   if (CG == 2) cluster_sync(); else __syncthreads();
   tc_fence_after();
@@ -512,9 +530,10 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
           // low word: start address >> 4 | LBO (2048 B >> 4) << 16; one K=16 step advances by 2 panels
           const uint32_t a_lo = ((sA + slot * kSlotBytes + a.steps[s].a_panel0 * kPanelBytes) >> 4) | ((kPanelBytes >> 4) << 16);
           const uint32_t acc0 = first ? 0u : 1u;
-          if (nn == 256) issue_step<CG, 2 * CG>(stage, phase, nch, a_lo, b_rows, d_tmem, idesc, sW, sBar, a.error_flag, PROF_PTR, acc0);
-          else if (nn == 128) issue_step<CG, 4 * CG>(stage, phase, nch, a_lo, b_rows, d_tmem, idesc, sW, sBar, a.error_flag, PROF_PTR, acc0);
-          else issue_step<CG, 8 * CG>(stage, phase, nch, a_lo, b_rows, d_tmem, idesc, sW, sBar, a.error_flag, PROF_PTR, acc0);
+          const int kcap = a.steps[s].ksteps;
+          if (nn == 256) issue_step<CG, 2 * CG>(stage, phase, nch, a_lo, b_rows, d_tmem, idesc, sW, sBar, a.error_flag, PROF_PTR, acc0, kcap);
+          else if (nn == 128) issue_step<CG, 4 * CG>(stage, phase, nch, a_lo, b_rows, d_tmem, idesc, sW, sBar, a.error_flag, PROF_PTR, acc0, kcap);
+          else issue_step<CG, 8 * CG>(stage, phase, nch, a_lo, b_rows, d_tmem, idesc, sW, sBar, a.error_flag, PROF_PTR, acc0, kcap);
           if (elect_one()) {
             if (last) umma_commit<CG>(bar(D_FULL + slot));
             if (s == a.last_pe_step) umma_commit<CG>(bar(PE_FREE + slot));
@@ -543,7 +562,7 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) pt[c] = __fadd_rn(__ldg(rr + c), __fmul_rn(__ldg(rr + 3 + c), zz));
         // column c of the encoding lives at panel c/8, byte (c%8)*2 of this row's 16-byte slot
-        const uint32_t dst = sA + slot * kSlotBytes + kHPanels * kPanelBytes + r * 16;
+        const uint32_t dst = sA + slot * kSlotBytes + a.pe_panel0 * kPanelBytes + r * 16;
         auto put = [&](int col, float v) {
           T h = (T)v;
           const uint32_t at = dst + (uint32_t)(col >> 3) * kPanelBytes + (col & 7) * 2;
@@ -566,7 +585,8 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
           }
         }
         fence_proxy_async();
-        arrive_leader<CG>(bar(PE_READY + slot));
+        __syncwarp();
+        if ((tid & 31) == 0) arrive_leader<CG>(bar(PE_READY + slot));
       }
   } else if (warp < 8) {
     // ===== epilogue: BOTH warpgroups work on every (slot, step) ===================================
@@ -607,7 +627,9 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
           const float* rbs = FULL ? a.raybias + (size_t)rayi[slot] * 256 : nullptr;
           PROF_WAIT(0, mbar_wait(bar(D_FULL + slot), nd & 1, a.error_flag));
           tc_fence_after();
-          const int w0 = 4 * wg, n0 = 2 * wg;  // first 32-column block of this warpgroup (256- / 128-wide steps)
+          // first 32-column block of this warpgroup: full-width steps (hb blocks each) and half-width steps (hb / 2 each;
+          // in the native 128-wide program a half-width step is two blocks, both done by warpgroup 0)
+          const int hb = a.hb, w0 = hb * wg, n0 = hb == 4 ? 2 * wg : 0, n1 = hb == 4 ? n0 + 2 : (wg == 0 ? 2 : 0);
           constexpr bool MK = FULL == 2;
           uint32_t* mrow = nullptr;
           // (tiles past the end of the sample array exist when the tile count is not a multiple of the tiles per
@@ -615,10 +637,10 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
           if (MK && ((2 * p + slot) * CG + rank) * kTileM < P)
             mrow = a.masks + ((((2 * p + slot) * CG + rank) * 12 + a.mlayer[s]) * 8) * 128 + r;
           if (X3 && kd == EPI_HIDDEN) epi_blocks_x3(t_row, h_row, a.bias32 + boff, w0, w0 + 4);
-          else if (kd == EPI_HIDDEN) epi_blocks<T, EPI_HIDDEN, MK>(t_row, h_row, a, boff, w0, w0 + 4, rbs, mrow);
-          else if (kd == EPI_T) epi_blocks<T, EPI_T, MK>(t_row, h_row, a, boff, n0, n0 + 2, rbs, mrow);
-          else if (kd == EPI_DT) epi_blocks<T, EPI_DT, MK>(t_row, h_row, a, boff, w0, w0 + 4, rbs, mrow);
-          else if (kd == EPI_FINAL) epi_blocks<T, EPI_FINAL, false>(t_row, h_row, a, boff, w0, w0 + 4, rbs, mrow);
+          else if (kd == EPI_HIDDEN) epi_blocks<T, EPI_HIDDEN, MK>(t_row, h_row, a, boff, w0, w0 + hb, rbs, mrow);
+          else if (kd == EPI_T) epi_blocks<T, EPI_T, MK>(t_row, h_row, a, boff, n0, n1, rbs, mrow);
+          else if (kd == EPI_DT) epi_blocks<T, EPI_DT, MK>(t_row, h_row, a, boff, w0, w0 + hb, rbs, mrow);
+          else if (kd == EPI_FINAL) epi_blocks<T, EPI_FINAL, false>(t_row, h_row, a, boff, w0, w0 + hb, rbs, mrow);
           else if (wg == 0) {
             // head steps: column 0 = sigma (EPI_SIGMA); columns 0..4 = transient rgb(3), sigma, beta and
             // columns 8..10 = static rgb (EPI_HEADS)
@@ -630,7 +652,8 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
               // fused compositing: the accumulator has been read, so the slot is handed back to the tensor pipe
               // first and the activation / compositing arithmetic overlaps the next pass' first layers
               tc_fence_before();
-              arrive_leader<CG>(bar(PASS_DONE + slot));
+              __syncwarp();
+              if ((tid & 31) == 0) arrive_leader<CG>(bar(PASS_DONE + slot));
               const float cs[3] = {sigmoid_f(__uint_as_float(v[8]) + a.tbl[kTblScal + 1]),
                                    sigmoid_f(__uint_as_float(v[9]) + a.tbl[kTblScal + 2]),
                                    sigmoid_f(__uint_as_float(v[10]) + a.tbl[kTblScal + 3])};
@@ -657,9 +680,9 @@ __device__ __forceinline__ void mlp_tc_body(const TcArgs& a) {
               o[8] = softplus_f(__uint_as_float(v[4]) + a.tbl[kTblScal + 8]);
             }
           }
-          tc_fence_before();
-          fence_proxy_async();
-          arrive_leader<CG>(bar((s + 1 < n_epi ? A_READY : PASS_DONE) + slot));
+          // every lane orders its own TMEM reads and shared-memory writes, the warp synchronises, lane 0 releases
+          PROF_WAIT(1, tc_fence_before(); fence_proxy_async(); __syncwarp());
+          PROF_WAIT(2, if ((tid & 31) == 0) arrive_leader<CG>(bar((s + 1 < n_epi ? A_READY : PASS_DONE) + slot)));
         }
       }
     }
@@ -885,6 +908,11 @@ uint16_t f2b(float f) { __nv_bfloat16 h = __float2bfloat16_rn(f); uint16_t u; me
 
 }  // namespace
 
+int tc_cta_group_env() {  // read per launch so that tests can exercise both variants in one process
+  const char* e = getenv("DFB_TC_CTA_GROUP");
+  return (e && e[0] == '1') ? 1 : 2;
+}
+
 bool tc_padded_shape(const NetPack& np) {
   return np.D == 8 && np.skip == 4 && np.pek == 64 && np.W >= 32 && np.W <= 256 && np.W % 16 == 0;
 }
@@ -949,7 +977,8 @@ namespace {
 // 20 static_sigma as an N=64 step (row 0) on the trunk output, 21 the remaining heads as ONE block-structured
 // K=256, N=64 step: rows 0..4 = transient_rgb(3), transient_sigma, transient_beta on k < 128
 // (transient_encoding.6 output, panels 0..15), rows 8..10 = static_rgb on k >= 128 (dir_encoding, panels 16..31).
-struct LStep { int logical, K, N, a_panel0, kind; };
+// kcap: K=16 MMA steps issued per chunk (0 = the whole chunk); K is the range the chunks cover.
+struct LStep { int logical, K, N, a_panel0, kind, kcap; };
 
 // xyz_encoding_final has no activation, so W_dir*(W_f h + b_f) = (W_dir W_f) h + W_dir b_f: folding it
 // removes one 256x256 layer per fine sample (DFB_TC_FOLD_FINAL=0 keeps the literal layer sequence).
@@ -961,37 +990,53 @@ bool fold_final() {
   return f != 0;
 }
 
-std::vector<LStep> build_program(bool fine) {
+// native128: the 8x128 network (the reference's default netwidth) as its own program instead of the zero-padded 8x256
+// embedding: 128-column trunk steps, 64-column transient steps, a quarter of the MMA work and half of the epilogue work.
+// cta_group::2 chunking only (a 16 KB image per CTA holds 128 K columns of an N = 128 step, 256 of an N = 64 step).  The
+// positional encoding sits in panels 16..23 and panels 24..31 hold zeros, so that layer 0 (A = panels 16..31), the skip
+// layer ([h | PE | 0] = panels 0..31) and the sigma step read whole chunks; steps with a shorter K stop early (kcap).
+std::vector<LStep> build_program(bool fine, bool native128 = false) {
   std::vector<LStep> pr;
-  for (int i = 0; i < 8; ++i) pr.push_back({i, i == 0 ? 64 : (i == 4 ? 320 : 256), 256, i == 0 ? 32 : 0, tc::EPI_HIDDEN});
-  pr.push_back({20, 256, 64, 0, tc::EPI_SIGMA});
+  if (native128) {
+    for (int i = 0; i < 8; ++i) pr.push_back({i, i == 4 ? 256 : 128, 128, i == 0 ? 16 : 0, tc::EPI_HIDDEN, 0});
+    pr.push_back({20, 256, 64, 0, tc::EPI_SIGMA, 8});
+    if (!fine) return pr;
+    pr.push_back({19, 128, 128, 0, tc::EPI_DT, 0});
+    for (int i = 0; i < 3; ++i) pr.push_back({10 + i, 256, 64, 0, tc::EPI_T, 4});
+    pr.push_back({21, 256, 64, 0, tc::EPI_HEADS, 8});
+    return pr;
+  }
+  for (int i = 0; i < 8; ++i) pr.push_back({i, i == 0 ? 64 : (i == 4 ? 320 : 256), 256, i == 0 ? 32 : 0, tc::EPI_HIDDEN, 0});
+  pr.push_back({20, 256, 64, 0, tc::EPI_SIGMA, 0});
   if (!fine) return pr;
   if (fold_final()) {
-    pr.push_back({19, 256, 256, 0, tc::EPI_DT});
+    pr.push_back({19, 256, 256, 0, tc::EPI_DT, 0});
   } else {
-    pr.push_back({8, 256, 256, 0, tc::EPI_FINAL});
-    pr.push_back({9, 256, 256, 0, tc::EPI_DT});
+    pr.push_back({8, 256, 256, 0, tc::EPI_FINAL, 0});
+    pr.push_back({9, 256, 256, 0, tc::EPI_DT, 0});
   }
-  for (int i = 0; i < 3; ++i) pr.push_back({10 + i, 128, 128, 0, tc::EPI_T});
-  pr.push_back({21, 256, 64, 0, tc::EPI_HEADS});
+  for (int i = 0; i < 3; ++i) pr.push_back({10 + i, 128, 128, 0, tc::EPI_T, 0});
+  pr.push_back({21, 256, 64, 0, tc::EPI_HEADS, 0});
   return pr;
+}
+
+// DFB_TC_NATIVE128=0 keeps 128-wide networks on the zero-padded 8x256 embedding (A/B measurements and tests); read per
+// call, the native image is always packed
+bool native128_enabled() {
+  const char* e = getenv("DFB_TC_NATIVE128");
+  return !(e && e[0] == '0') && fold_final();
 }
 }  // namespace
 
 // Pack the network into the streaming order of the kernel.  For every step, K is cut into
 // chunks; a chunk is stored as `cg` consecutive 16 KB images, image h holding rows
 // [h*N/cg, (h+1)*N/cg) of B as [K/8 panels][N/cg rows][8 elements] (see the layout note above).
-int pack_tc_weights(DfbNerf* n, int which, const std::vector<std::vector<float>>& P_in) {
-  NetPack& np = n->net[which];
-  for (int k = 0; k < 2; ++k)
-    for (int g = 0; g < 2; ++g)
-      if (np.blob16[k][g]) { cudaFree(np.blob16[k][g]); np.blob16[k][g] = nullptr; }
-  np.tc_tbl.clear();
-  if (!tc_padded_shape(np)) return DFB_OK;  // SIMT only
-  const std::vector<std::vector<float>> P = tc_pad_params(np, P_in);  // narrower networks: embedded in 8x256 with zeros
-  const int W = 256, H = 128, in_xyz = np.in_xyz;
+// native = false: the 8x256 program (P already zero-padded to 256); native = true: the 8x128 program on the unpadded
+// parameters (cta_group::2 images only, no split-precision image).
+static int pack_tc_variant(NetPack& np, const std::vector<std::vector<float>>& P, int W, bool native) {
+  const int H = W / 2, in_xyz = np.in_xyz;
   const bool fine = np.fine;
-  const std::vector<LStep> prog = build_program(fine);
+  const std::vector<LStep> prog = build_program(fine, native);
   // dir_encoding[:, :W] stacked on transient_encoding.0[:, :W] (row nn, column k)
   auto wdt = [&](int nn, int k) -> double {
     if (nn < H) return P[18][(size_t)nn * (W + np.in_dir + np.a_dim) + k];
@@ -1011,21 +1056,21 @@ int pack_tc_weights(DfbNerf* n, int which, const std::vector<std::vector<float>>
       }
     }
   }
-  // value of the logical weight matrix at (n, k)
+  // value of the logical weight matrix at (n, k); zero beyond the layer's true K (chunks cover whole K ranges)
   auto wval = [&](int lg, int nn, int k) -> float {
     if (lg == 0) return k < in_xyz ? P[0][(size_t)nn * in_xyz + k] : 0.f;
     if (lg < 8) {
-      if (lg == 4) {  // K order [h(256) | pe(64)]; torch order is cat([input_xyz, h])
+      if (lg == 4) {  // K order [h(W) | pe(64)]; torch order is cat([input_xyz, h])
         if (k < W) return P[8][(size_t)nn * (W + in_xyz) + in_xyz + k];
         const int c = k - W;
         return c < in_xyz ? P[8][(size_t)nn * (W + in_xyz) + c] : 0.f;
       }
-      return P[2 * lg][(size_t)nn * W + k];
+      return k < W ? P[2 * lg][(size_t)nn * W + k] : 0.f;
     }
-    if (lg == 8) return P[16][(size_t)nn * W + k];  // xyz_encoding_final
-    if (lg == 9) return (float)wdt(nn, k);
-    if (lg == 19) return folded_w[(size_t)nn * W + k];
-    if (lg == 20) return nn == 0 ? P[20][k] : 0.f;  // static_sigma
+    if (lg == 8) return k < W ? P[16][(size_t)nn * W + k] : 0.f;  // xyz_encoding_final
+    if (lg == 9) return k < W ? (float)wdt(nn, k) : 0.f;
+    if (lg == 19) return k < W ? folded_w[(size_t)nn * W + k] : 0.f;
+    if (lg == 20) return nn == 0 && k < W ? P[20][k] : 0.f;  // static_sigma
     if (lg == 21) {
       if (k < H) {
         if (nn < 3) return P[34][(size_t)nn * H + k];  // transient_rgb
@@ -1033,11 +1078,11 @@ int pack_tc_weights(DfbNerf* n, int which, const std::vector<std::vector<float>>
         if (nn == 4) return P[36][k];                  // transient_beta
         return 0.f;
       }
-      return (nn >= 8 && nn < 11) ? P[22][(size_t)(nn - 8) * H + (k - H)] : 0.f;  // static_rgb
+      return (nn >= 8 && nn < 11 && k < 2 * H) ? P[22][(size_t)(nn - 8) * H + (k - H)] : 0.f;  // static_rgb
     }
-    return P[26 + 2 * (lg - 10)][(size_t)nn * H + k];  // transient_encoding.{2,4,6}
+    return k < H ? P[26 + 2 * (lg - 10)][(size_t)nn * H + k] : 0.f;  // transient_encoding.{2,4,6}
   };
-  for (int cg = 1; cg <= 2; ++cg) {
+  for (int cg = native ? 2 : 1; cg <= 2; ++cg) {
     size_t total_imgs = 0;
     for (const LStep& st : prog) total_imgs += (size_t)st.K * st.N * 2 / tc::kChunkBytes;
     std::vector<uint16_t> img16[2];
@@ -1047,6 +1092,7 @@ int pack_tc_weights(DfbNerf* n, int which, const std::vector<std::vector<float>>
     for (const LStep& st : prog) {
       const int rows = st.N / cg;
       const int kc = tc::kChunkBytes / (rows * 2);  // K columns per chunk
+      DFB_REQUIRE(st.K % kc == 0, DFB_ERR_INVALID, "tcgen05 program: K = %d is not a whole number of %d-column chunks", st.K, kc);
       for (int k0 = 0; k0 < st.K; k0 += kc)
         for (int h = 0; h < cg; ++h, ++img) {
           const size_t base = img * (tc::kChunkBytes / 2);
@@ -1059,15 +1105,17 @@ int pack_tc_weights(DfbNerf* n, int which, const std::vector<std::vector<float>>
             }
         }
     }
-    np.blob16_bytes = total_imgs * tc::kChunkBytes;
+    DFB_REQUIRE(img == total_imgs, DFB_ERR_INVALID, "tcgen05 program: image count mismatch");
+    (native ? np.blob16n_bytes : np.blob16_bytes) = total_imgs * tc::kChunkBytes;
     for (int k = 0; k < 2; ++k) {
-      DFB_CHECK_CUDA(cudaMalloc(&np.blob16[k][cg - 1], np.blob16_bytes));
-      DFB_CHECK_CUDA(cudaMemcpy(np.blob16[k][cg - 1], img16[k].data(), np.blob16_bytes, cudaMemcpyHostToDevice));
+      void** dst = native ? &np.blob16n[k] : &np.blob16[k][cg - 1];
+      DFB_CHECK_CUDA(cudaMalloc(dst, total_imgs * tc::kChunkBytes));
+      DFB_CHECK_CUDA(cudaMemcpy(*dst, img16[k].data(), total_imgs * tc::kChunkBytes, cudaMemcpyHostToDevice));
     }
   }
   // split-precision image of the sigma-only program (the first 9 steps: trunk + sigma), cta_group::2 chunking:
   // all hi chunks, then all lo chunks
-  {
+  if (!native) {
     if (np.blob16x3) { cudaFree(np.blob16x3); np.blob16x3 = nullptr; }
     const std::vector<LStep> cprog = build_program(false);
     size_t imgs = 0;
@@ -1095,35 +1143,64 @@ int pack_tc_weights(DfbNerf* n, int which, const std::vector<std::vector<float>>
     DFB_CHECK_CUDA(cudaMemcpy(np.blob16x3, img.data(), np.blob16x3_bytes, cudaMemcpyHostToDevice));
   }
   // fp32 table read through the constant bank by the epilogue (see TcArgs::tbl); biases by program step
-  np.tc_tbl.assign(tc::kTblFloats, 0.f);
-  float* tb = np.tc_tbl.data();
+  std::vector<float>& tbl = native ? np.tc_tbl_n : np.tc_tbl;
+  tbl.assign(tc::kTblFloats, 0.f);
+  float* tb = tbl.data();
   for (size_t s = 0; s < prog.size(); ++s) {
     const int lg = prog[s].logical;
     float* dst = tb + s * 256;
-    if (lg < 8) memcpy(dst, P[2 * lg + 1].data(), 256 * sizeof(float));
-    else if (lg == 8) memcpy(dst, P[17].data(), 256 * sizeof(float));
-    else if (lg == 19) memcpy(dst, folded_b.data(), 256 * sizeof(float));
+    if (lg < 8) memcpy(dst, P[2 * lg + 1].data(), W * sizeof(float));
+    else if (lg == 8) memcpy(dst, P[17].data(), W * sizeof(float));
+    else if (lg == 19) memcpy(dst, folded_b.data(), W * sizeof(float));
     else if (lg >= 10 && lg <= 12) memcpy(dst, P[27 + 2 * (lg - 10)].data(), H * sizeof(float));
     // lg == 9: the bias of dir_encoding / transient_encoding.0 is part of the per-ray bias
   }
   tb[tc::kTblScal] = P[21][0];
-  if (np.tc_bias32_dev) cudaFree(np.tc_bias32_dev);
-  np.tc_bias32_dev = nullptr;
-  DFB_CHECK_CUDA(cudaMalloc(&np.tc_bias32_dev, tc::kTblScal * sizeof(float)));
-  DFB_CHECK_CUDA(cudaMemcpy(np.tc_bias32_dev, tb, tc::kTblScal * sizeof(float), cudaMemcpyHostToDevice));
+  if (!native) {
+    if (np.tc_bias32_dev) cudaFree(np.tc_bias32_dev);
+    np.tc_bias32_dev = nullptr;
+    DFB_CHECK_CUDA(cudaMalloc(&np.tc_bias32_dev, tc::kTblScal * sizeof(float)));
+    DFB_CHECK_CUDA(cudaMemcpy(np.tc_bias32_dev, tb, tc::kTblScal * sizeof(float), cudaMemcpyHostToDevice));
+  }
   if (fine) {
     std::vector<float> dtb(W, 0.f);
     if (fold_final()) dtb = folded_b;
-    if (np.tc_dtbias_dev) cudaFree(np.tc_dtbias_dev);
-    np.tc_dtbias_dev = nullptr;
-    DFB_CHECK_CUDA(cudaMalloc(&np.tc_dtbias_dev, W * sizeof(float)));
-    DFB_CHECK_CUDA(cudaMemcpy(np.tc_dtbias_dev, dtb.data(), W * sizeof(float), cudaMemcpyHostToDevice));
+    float** dd = native ? &np.tc_dtbias_n_dev : &np.tc_dtbias_dev;
+    if (*dd) cudaFree(*dd);
+    *dd = nullptr;
+    DFB_CHECK_CUDA(cudaMalloc(dd, W * sizeof(float)));
+    DFB_CHECK_CUDA(cudaMemcpy(*dd, dtb.data(), W * sizeof(float), cudaMemcpyHostToDevice));
   }
   if (fine) {
     for (int c = 0; c < 3; ++c) tb[tc::kTblScal + 1 + c] = P[23][c], tb[tc::kTblScal + 4 + c] = P[35][c];
     tb[tc::kTblScal + 7] = P[33][0], tb[tc::kTblScal + 8] = P[37][0];
   }
   return DFB_OK;
+}
+
+int pack_tc_weights(DfbNerf* n, int which, const std::vector<std::vector<float>>& P_in) {
+  NetPack& np = n->net[which];
+  for (int k = 0; k < 2; ++k) {
+    for (int g = 0; g < 2; ++g)
+      if (np.blob16[k][g]) { cudaFree(np.blob16[k][g]); np.blob16[k][g] = nullptr; }
+    if (np.blob16n[k]) { cudaFree(np.blob16n[k]); np.blob16n[k] = nullptr; }
+  }
+  np.tc_tbl.clear(), np.tc_tbl_n.clear();
+  if (!tc_padded_shape(np)) return DFB_OK;  // SIMT only
+  // narrower networks: embedded in 8x256 with zeros (every mode of the kernel) ...
+  const int rc = pack_tc_variant(np, tc_pad_params(np, P_in), 256, false);
+  if (rc) return rc;
+  // ... and, for the reference's default netwidth, additionally as the native 128-wide program (inference passes)
+  if (np.W == 128 && fold_final()) return pack_tc_variant(np, P_in, 128, true);
+  return DFB_OK;
+}
+
+// true when launch_mlp_tc_rays will run the native 128-wide program for this network (decides the layout of the per-ray
+// bias: contiguous [dir 64 | transient 64] instead of the padded embedding's [dir | 0 | transient | 0])
+bool tc_native128(const DfbNerf* n, int which, bool masks, bool split3) {
+  const NetPack& np = n->net[which];
+  return np.W == 128 && np.blob16n[0] != nullptr && !np.tc_tbl_n.empty() && !masks && !split3 && tc_cta_group_env() == 2 &&
+         native128_enabled();
 }
 
 // 3-D tensor map over a packed weight image: [n_img][64][128 x u16], one box = one 16 KB image.
@@ -1150,10 +1227,7 @@ static unsigned long long* g_prof = nullptr;
 // cta_group used by the tcgen05 kernel.  2 (default): CTA pairs share every weight chunk, which halves the
 // L2 -> shared-memory weight stream per SM (the 1-CTA kernel waits ~25 % of its time for weight stages);
 // measured 3.46 vs 3.39 M rays/s.  DFB_TC_CTA_GROUP=1 selects the 1-CTA kernel.
-static int tc_cta_group() {  // read per launch so that tests can exercise both variants in one process
-  const char* e = getenv("DFB_TC_CTA_GROUP");
-  return (e && e[0] == '1') ? 1 : 2;
-}
+static int tc_cta_group() { return tc_cta_group_env(); }
 
 int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const float* rayrec, const float* z,
                        const float* raybias, int64_t n_rays, int S, float* raw, cudaStream_t st, uint32_t* masks, bool split3,
@@ -1171,8 +1245,10 @@ int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const
     if (rc) return rc;
   }
   const int cg = (split3 || ert_rowmap) ? 2 : tc_cta_group();
+  const bool native = cg == 2 && tc_native128(nerf, which, masks != nullptr, split3);
   tc::TcArgs a = {};
-  const std::vector<LStep> prog = build_program(full);
+  const std::vector<LStep> prog = build_program(full, native);
+  a.hb = native ? 2 : 4, a.pe_panel0 = native ? 16 : tc::kHPanels;
   a.n_epi = (int)prog.size();
   int total_chunks = 0;
   for (const LStep& ls : prog) total_chunks += ls.K / (tc::kChunkBytes / ((ls.N / cg) * 2));
@@ -1181,7 +1257,7 @@ int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const
     const LStep& ls = prog[e];
     const int kc = tc::kChunkBytes / ((ls.N / cg) * 2);
     tc::Step stp;
-    stp.n_chunks = ls.K / kc, stp.ksteps = kc / 16, stp.n = ls.N, stp.a_panel0 = ls.a_panel0, stp.chunk_base = cb;
+    stp.n_chunks = ls.K / kc, stp.ksteps = ls.kcap ? ls.kcap : kc / 16, stp.n = ls.N, stp.a_panel0 = ls.a_panel0, stp.chunk_base = cb;
     if (!split3) {
       a.steps[ns] = stp, a.first[ns] = 1, a.last[ns] = 1;
       if (e == 4) a.last_pe_step = ns;
@@ -1201,12 +1277,12 @@ int launch_mlp_tc_rays(const DfbNerf* nerf, int which, int mode, int kind, const
   }
   a.n_steps = ns;
   a.bias32 = np.tc_bias32_dev;
-  a.wimg = split3 ? np.blob16x3 : np.blob16[kind == DFB_MMA_F16 ? 0 : 1][cg - 1];
+  a.wimg = split3 ? np.blob16x3 : native ? np.blob16n[kind == DFB_MMA_F16 ? 0 : 1] : np.blob16[kind == DFB_MMA_F16 ? 0 : 1][cg - 1];
   if (cg == 2) {
-    int rc = make_weight_tmap(const_cast<void*>(a.wimg), split3 ? np.blob16x3_bytes : np.blob16_bytes, &a.tmap);
+    int rc = make_weight_tmap(const_cast<void*>(a.wimg), split3 ? np.blob16x3_bytes : native ? np.blob16n_bytes : np.blob16_bytes, &a.tmap);
     if (rc) return rc;
   }
-  memcpy(a.tbl, np.tc_tbl.data(), sizeof(a.tbl));
+  memcpy(a.tbl, (native ? np.tc_tbl_n : np.tc_tbl).data(), sizeof(a.tbl));
   for (int i = 0; i < tc::kMaxSteps * 128; ++i) {
     const float lo = a.tbl[2 * i], hi = a.tbl[2 * i + 1];
     a.btbl[i] = kind == DFB_MMA_F16 ? ((uint32_t)f2h(hi) << 16 | f2h(lo)) : ((uint32_t)f2b(hi) << 16 | f2b(lo));

@@ -259,9 +259,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_tc_bwd(const __grid_constan
     for (int i = 0; i < kMaxStages; ++i) mbar_init(bar(W_FULL + i), 1), mbar_init(bar(W_EMPTY + i), 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar(D_FULL + s), 1);
-      mbar_init(bar(A_READY + s), 128);
-      mbar_init(bar(PASS_DONE + s), 128);
-      mbar_init(bar(PE_READY + s), 128);
+      mbar_init(bar(A_READY + s), 4);     // one arrival per warp (lane 0, after __syncwarp), see mlp_tc.cu
+      mbar_init(bar(PASS_DONE + s), 4);
+      mbar_init(bar(PE_READY + s), 4);
       mbar_init(bar(PE_FREE + s), 1);
     }
     fence_barrier_init();
@@ -368,7 +368,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_tc_bwd(const __grid_constan
         }
         __threadfence_block();
         fence_proxy_async();
-        mbar_arrive(bar(PE_READY + slot));
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(bar(PE_READY + slot));
       }
   } else if (warp < 8) {
     // ===== epilogue warpgroups (thread = accumulator row = sample) ================================
@@ -542,7 +543,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_tc_bwd(const __grid_constan
         }
         tc_fence_before();
         fence_proxy_async();
-        mbar_arrive(bar((s + 1 < a.n_steps ? A_READY : PASS_DONE) + slot));
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(bar((s + 1 < a.n_steps ? A_READY : PASS_DONE) + slot));
 #ifdef DFB_TC_PROF
         pstep[s] += clock64() - _ts;
 #endif

@@ -105,6 +105,9 @@ extern "C" void dfb_nerf_destroy(DfbNerf* n) {
     for (int k = 0; k < 2; ++k)
       if (n->net[i].blob16b[k]) cudaFree(n->net[i].blob16b[k]);
     if (n->net[i].tc_dtbias_dev) cudaFree(n->net[i].tc_dtbias_dev);
+    if (n->net[i].tc_dtbias_n_dev) cudaFree(n->net[i].tc_dtbias_n_dev);
+    for (int k = 0; k < 2; ++k)
+      if (n->net[i].blob16n[k]) cudaFree(n->net[i].blob16n[k]);
   }
   if (n->emb_a) cudaFree(n->emb_a);
   if (n->emb_t) cudaFree(n->emb_t);

@@ -187,11 +187,16 @@ __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // arrive on the barrier at local address `bar` of CTA `cta` of the cluster
+// Arrive on the barrier at the same offset in CTA `cta` of the cluster.  Default semantics (release at CTA scope), as
+// CUTLASS' ClusterBarrier::arrive(cta_id) does: what the arrival publishes are this thread's (warp's) shared-memory
+// writes, already made visible to the async proxy by fence.proxy.async, and completed TMEM reads - both local to this
+// SM, whose own tensor core is the consumer.  With .release.cluster ptxas emits MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in
+// front of every arrival: ~1 000 cycles each, 38-46 % of the epilogue warps' time in the MLP kernels (tools/tc_prof.py).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
       "r"(cta)
       : "memory");
 }

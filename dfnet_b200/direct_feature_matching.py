@@ -89,10 +89,42 @@ def matching_terms(args, data, rgb, feat_model, device):
     feat_model.grad_levels = list(args.feature_matching_lvl)  # levels whose gradient is non-zero after index_select
     (feature_target, feature_rgb), _ = inference_pose_regression(args, torch.cat([data, rgb]), device, feat_model, retFeature=True,
                                                                  isSingleStream=False, return_pose=False)
-    lv = torch.tensor(args.feature_matching_lvl, device=feature_rgb.device)
-    f_rgb = preprocess_features_for_loss(torch.index_select(feature_rgb, 0, lv))
-    f_tgt = preprocess_features_for_loss(torch.index_select(feature_target, 0, lv))
+    f_rgb = preprocess_features_for_loss(_take_levels(feature_rgb, args.feature_matching_lvl, feat_model))
+    # the target stream is a constant of the step (frozen feature net, image without gradient)
+    f_tgt = preprocess_features_for_loss(_take_levels(feature_target.detach(), args.feature_matching_lvl, feat_model))
     return rgb_loss(rgb, data), feature_loss(f_rgb[0], f_tgt[0], per_channel=args.per_channel)
+
+
+class _TakeLevels(torch.autograd.Function):
+    """stack[lv0:lv0+n] as a view.  The reference's torch.index_select (:365-366) copies the selected levels (157 MB per
+    level at 480x640) and its backward fills a zero stack and index_adds into it; here the forward is a view and the backward
+    hands the feature net a stack in which ONLY the selected levels are written - the consumer was told through
+    `grad_levels` (set by matching_terms) to read nothing else."""
+
+    @staticmethod
+    def forward(ctx, stack, lv0, n):
+        ctx.shape, ctx.lv0, ctx.n = stack.shape, lv0, n
+        ctx.set_materialize_grads(False)
+        return stack.narrow(0, lv0, n)
+
+    @staticmethod
+    def backward(ctx, g):
+        if g is None:
+            return None, None, None
+        full = torch.empty(ctx.shape, device=g.device, dtype=g.dtype)
+        full.narrow(0, ctx.lv0, ctx.n).copy_(g)
+        return full, None, None
+
+
+def _take_levels(stack, levels, feat_model):
+    lv = [int(l) for l in levels]
+    from .dfnet import DFNet
+    contiguous = lv == list(range(lv[0], lv[0] + len(lv)))
+    if contiguous and not (torch.is_grad_enabled() and stack.requires_grad):
+        return stack.narrow(0, lv[0], len(lv))
+    if contiguous and isinstance(feat_model, DFNet) and list(getattr(feat_model, "grad_levels", None) or []) == lv:
+        return _TakeLevels.apply(stack, lv[0], len(lv))
+    return torch.index_select(stack, 0, torch.tensor(lv, device=stack.device))
 
 
 def apply_gradients(model, optimizer):

@@ -93,6 +93,46 @@ def test_full_size_tensor_core_render_vs_oracle(ctx, name, H, W, focal, near, fa
         assert e_rgb < 1e-3 and e_acc < 1e-3, (name, cg)
 
 
+def test_native_128_wide_program_vs_oracle_and_embedding(monkeypatch):
+    """The reference's default networks (netwidth 128, 64+64 samples, models/options.py:31-33,56-57) at 640x480: the native
+    128-wide tcgen05 program against the ORACLE at the north star's 1e-3 on a 2 000-ray subset, against the same network
+    zero-padded into the 8x256 program (DFB_TC_NATIVE128=0: same function, different MMA shapes), with early ray
+    termination, and on a ragged ray count."""
+    from dfnet_b200 import ops
+    mods, nets = synthetic_nets(8, 128)
+    h = ops.NerfHandle(*[m.to(dev()) for m in mods])
+    H, W, focal, near, far, Nc, Nf = 480, 640, 585.0, 0.0, 2.5, 64, 64
+    kw = dict(c2w=torch.tensor(C2W, device=dev()), H=H, W=W, focal=focal, near=near, far=far, hist=torch.tensor(HIST, device=dev()))
+    l0 = ops.lib.dfb_launch_count()
+    nat = {k: v.clone() for k, v in h.render(Nc, Nf, True, mma="f16", **kw).items()}
+    torch.cuda.synchronize()
+    assert ops.lib.dfb_launch_count() > l0
+    monkeypatch.setenv("DFB_TC_NATIVE128", "0")
+    emb = {k: v.clone() for k, v in h.render(Nc, Nf, True, mma="f16", **kw).items()}
+    torch.cuda.synchronize()
+    monkeypatch.delenv("DFB_TC_NATIVE128")
+    sel = np.linspace(0, H * W - 1, 2000).astype(np.int64)
+    want = _oracle_subset(nets, H, W, focal, near, far, Nc, Nf, sel)
+    for name, o in (("native", nat), ("embedded", emb)):
+        e_rgb = rel_err(o["rgb"].cpu().numpy()[sel], want["rgb_map"])
+        e_acc = rel_err(o["acc"].cpu().numpy()[sel], want["acc_map"])
+        print(name, "128-wide f16 vs oracle: rgb", e_rgb, "acc", e_acc)
+        assert e_rgb < 1e-3 and e_acc < 1e-3, name
+    assert rel_err(nat["rgb"].cpu().numpy(), emb["rgb"].cpu().numpy()) < 1e-3
+    # bf16 operands and the extras path (raw, depth: unfused compositing) on a ragged ray count
+    o, d = O.get_rays(H, W, focal, C2W)
+    idx = np.arange(0, H * W, 307)[:997]
+    rec = torch.tensor(O.make_ray_records(o.reshape(-1, 3)[idx], d.reshape(-1, 3)[idx], near, far, HIST[None]), device=dev())
+    ref = h.render(Nc, Nf, True, rays=rec, mma="fp32", want=("raw", "depth"))
+    for mma, tol in (("f16", 1e-3), ("bf16", 1e-2)):
+        got = h.render(Nc, Nf, True, rays=rec, mma=mma, want=("raw", "depth"))
+        for k in ("rgb", "acc", "depth"):
+            assert rel_err(got[k].cpu().numpy(), ref[k].cpu().numpy()) < tol, (mma, k)
+    # opt-in early ray termination runs on the same program
+    ert = h.render(Nc, Nf, True, mma="f16", ert_eps=1e-3, **kw)
+    assert float((ert["rgb"] - nat["rgb"]).abs().max()) < 5e-3
+
+
 def test_split_precision_coarse_pass_vs_oracle(ctx):
     """mma="f16s" on the benchmark field: the coarse weights (which decide the sample indices) match the oracle like the
     fp32 kernels do, indices almost never flip, the image stays inside 1e-3."""

@@ -96,14 +96,19 @@ for name, se in sorted(seen.items()):
             cur_e = max(cur_e, e)
         else:
             busy += cur_e - cur_s
-            gaps.append((s - cur_e, k["name"][:60]))
+            gaps.append((s - cur_e, k["name"][:60], cur_e, s))
             cur_s, cur_e = s, e
     busy += cur_e - cur_s
     span = ks[-1]["ts"] + ks[-1]["dur"] - ks[0]["ts"]
     print(f"{name}: host span {se['dur'] / 1e3:.2f} ms, first->last kernel {span / 1e3:.2f} ms, GPU busy {busy / 1e3:.2f} ms, "
           f"idle {(span - busy) / 1e3:.2f} ms in {len(gaps)} gaps, {len(ks)} device ops, lead-in {(ks[0]['ts'] - t0) / 1e3:.2f} ms")
     if name == sorted(seen)[-1]:
-        print("  largest gaps (us, before kernel):", [(round(g, 1), n) for g, n in sorted(gaps, reverse=True)[:12]])
+        cpu = [e for e in tr if e.get("cat") in ("cpu_op", "cuda_runtime", "cuda_driver", "user_annotation") and "dur" in e]
+        print("  largest gaps (us, kernel after the gap | host activity overlapping the gap, longest first):")
+        for gdur, nm, g0, g1 in sorted(gaps, reverse=True)[:14]:
+            ov = sorted([(min(e["ts"] + e["dur"], g1) - max(e["ts"], g0), e["name"][:48]) for e in cpu
+                         if e["ts"] < g1 and e["ts"] + e["dur"] > g0 and not e["name"].startswith("STEP")], reverse=True)[:5]
+            print(f"    {gdur:7.1f}  {nm:60s} | " + ", ".join(f"{n} {d:.0f}" for d, n in ov))
         agg = collections.defaultdict(lambda: [0, 0.0])
         for k in ks:
             nm = k["name"].split("(")[0][:70] if "dfb::" in k["name"] else k["name"][:160]

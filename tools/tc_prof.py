@@ -11,14 +11,16 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dfnet_b200 import nerfw, ops  # noqa: E402
 
 dev = torch.device("cuda:0")
-mods = nerfw.make_synthetic_nerf(D=8, W=256)
+WIDTH = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+NF = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+mods = nerfw.make_synthetic_nerf(D=8, W=WIDTH)
 h = ops.NerfHandle(*[m.to(dev) for m in mods])
 c2w = torch.tensor([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 1.0]], device=dev)
 hist = torch.tensor([5, 10, 20, 30, 15, 10, 5, 3, 1, 1.0], device=dev)
 for which in (0, 1):
     os.environ["DFB_TC_PROF_WHICH"] = str(which)
     for _ in range(2):
-        h.render(64, 128, True, c2w=c2w, H=256, W=256, focal=300.0, near=0.0, far=2.5, hist=hist, mma="f16")
+        h.render(64, NF, True, c2w=c2w, H=256, W=256, focal=300.0, near=0.0, far=2.5, hist=hist, mma="f16")
     torch.cuda.synchronize()
     big = np.zeros((512, 16), np.uint64)
     rc = ops.lib.dfb_debug_tc_prof(big.ctypes.data_as(C.c_void_p), 512)
@@ -26,7 +28,7 @@ for which in (0, 1):
     assert rc == 0, rc
     b = buf.astype(np.float64)
     names = {0: ("producer", ["wait W_EMPTY"]), 4: ("mma", ["wait W_FULL", "wait W_FULLP", "wait A_READY/PE"]),
-             8: ("epi slot0", ["wait D_FULL"]), 12: ("epi slot1", ["wait D_FULL"])}
+             8: ("epi wg0", ["wait D_FULL", "fences", "arrive"]), 12: ("epi wg1", ["wait D_FULL", "fences", "arrive"])}
     print(f"--- network {which} ({'coarse' if which == 0 else 'fine'}) : mean over CTAs, cycles")
     for base, (nm, labels) in names.items():
         tot = b[:, base + 3]
