@@ -65,11 +65,15 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity,
     }
   }
 }
+// Default (CTA-scope acquire) semantics, like CUTLASS' ClusterBarrier::wait: the waiter (the MMA issuer) reads no data
+// through generic loads afterwards - it issues tcgen05 instructions behind tcgen05.fence::after_thread_sync.  With
+// .acquire.cluster every poll was followed by CCTL.IVALL, an SM-wide L1 invalidation (14 sites in the fine kernel) that
+// threw away the per-ray bias rows the epilogue warps had prefetched.
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(bar), "r"(parity)
