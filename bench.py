@@ -73,13 +73,13 @@ def pose(i):
 
 def ncu_traffic_per_launch(avg_rays_per_launch):
     """dram__bytes_read.sum + dram__bytes_write.sum of the fine tcgen05 MLP kernel (compositing fused into its heads
-    epilogue) from the committed `ncu --set full` capture (profiles/r02_ncu_mlp_tc_summary.csv: the 45 056-ray last chunk
-    of a 640x480 image), scaled to this run's average launch."""
+    epilogue) from the committed `ncu --set full` capture (profiles/r02_ncu_mlp_tc_summary.csv: one 65 536-ray chunk of a
+    640x480 image), scaled to this run's average launch."""
     p = os.path.join(ROOT, "profiles", "r02_ncu_mlp_tc_summary.csv")
     try:
         rows = {r.split(",")[0]: r.strip().split(",") for r in open(p)}
         mb = sum(float(rows[k][3].strip('"')) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-        return mb * 1e6 * avg_rays_per_launch / 45056.0
+        return mb * 1e6 * avg_rays_per_launch / 65536.0
     except Exception:  # noqa: BLE001
         return None
 
@@ -571,7 +571,7 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": f"{pk_kind} bf16_tflops_sustained (kernel timed inside a long step)",
                 "traffic": ncu_traffic_per_launch(N * args.steps / max(fl, 1)) if mma != "fp32" and args.workload == "cfg2" else None,
-                "traffic_note": "DRAM bytes per launch from profiles/r02_ncu_mlp_tc_summary.csv (ncu --set full, 45 056-ray "
+                "traffic_note": "DRAM bytes per launch from profiles/r02_ncu_mlp_tc_summary.csv (ncu --set full, 65 536-ray "
                                 "launch) scaled to this run's average launch: depths, per-ray bias and ray records in, 32-byte "
                                 "partial records out (compositing is fused; the [P,9] raw tensor is no longer written)",
                 "kernel_share_of_step": (fine_ms + coarse_ms) / ms,

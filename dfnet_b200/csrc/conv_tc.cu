@@ -156,6 +156,26 @@ __device__ __forceinline__ void epi_store(const ConvArgs& a, const uint32_t (&v)
   }
 }
 
+// MMAs of up to `tpn` consecutive filter taps of one channel slice (KSN K=16 steps each), issued by ONE thread.  The tap's
+// A operand is the patch window shifted by (ky, kx); the position advances incrementally.  (The first version recomputed
+// ky = tap / KW per tap and predicated every K step inside one unrolled body: ~200 instructions per tap on the single
+// issuing thread, more than the 128-512 tensor cycles a tap is worth - the issuer, not the tensor pipe, bounded every layer.)
+template <int CG, int KSN>
+__device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t a_step, uint32_t b_lo, uint32_t b_hi,
+                                           uint32_t b_step, uint32_t b_tap, uint32_t idesc, int tpn, uint32_t kx, uint32_t kw,
+                                           uint32_t wrap, uint32_t acc) {
+#pragma unroll 1
+  for (int tt = 0; tt < tpn; ++tt) {
+    umma_f16<CG>(d_tmem, mk64(a_lo, a_hi), mk64(b_lo, b_hi), idesc, acc);
+#pragma unroll
+    for (int ks = 1; ks < KSN; ++ks) umma_f16<CG>(d_tmem, mk64(a_lo + ks * a_step, a_hi), mk64(b_lo + ks * b_step, b_hi), idesc, 1u);
+    acc = 1u;
+    b_lo += b_tap;
+    ++a_lo;
+    if (++kx == kw) kx = 0, a_lo += wrap;
+  }
+}
+
 // CG = 2 (cta_group::2): the two CTAs of a cluster work on two neighbouring 128-pixel M tiles with ONE weight stream:
 // each CTA holds half of every weight stage (its nt/2 rows of B, a 16 KB image loaded by a 2-SM TMA that credits the
 // leader's barrier), the leader issues tcgen05.mma.cta_group::2 (M = 256) for the pair and tcgen05.commit multicasts
@@ -261,6 +281,8 @@ __device__ __forceinline__ void conv_tc_body(const ConvArgs& a) {
     const uint32_t a_lbo = (panel_stride >> 4) << 16, b_lbo = b_rows << 16;
     const uint32_t b_step = 2u * b_rows;               // two weight panels per K=16 step
     const uint32_t a_step = 2u * (panel_stride >> 4);  // two patch panels per K=16 step
+    const uint32_t b_tap = 8u * b_rows;                // 8 panels * b_rows * 16 B per tap, in 16-byte units
+    const uint32_t kw = (uint32_t)a.KW, wrap = (uint32_t)(a.PW - a.KW);   // next filter row: + PW - KW patch columns
     uint32_t ita = 0, itb = 0, tl = 0;
     long long pacc[4] = {0, 0, 0, 0};
     const long long t_start = clock64();
@@ -276,23 +298,21 @@ __device__ __forceinline__ void conv_tc_body(const ConvArgs& a) {
         const int np = min(8, a.cpp - cc * 8);
         const int ks_n = (np + 1) >> 1;
         const uint32_t patch = (sA + ast * a.a_bytes) >> 4;
+        // running tap position inside the filter: a_off = ky * PW + kx in 16-byte units (no division per tap)
+        uint32_t kx = 0, a_off = 0;
+        int taps_left = n_taps;
         for (int ws = 0; ws < a.n_wst; ++ws, ++itb) {
           const uint32_t stage = itb % NB, ph = (itb / NB) & 1;
           CPROF(2, mbar_wait_cluster<CG>(bar(B_FULL2 + stage), ph, a.error_flag));
           tc_fence_after();
-          const int tp0 = ws * a.tps, tpn = min(a.tps, n_taps - tp0);
+          const int tpn = min(a.tps, taps_left);
           const uint32_t b_lo0 = ((sB + stage * b_stage) >> 4) | b_lbo;
           if (elect_one()) {
-            for (int tt = 0; tt < tpn; ++tt) {
-              const int tp = tp0 + tt, ky = tp / a.KW, kx = tp - ky * a.KW;
-              const uint32_t a_lo = (patch + (uint32_t)(ky * a.PW + kx)) | a_lbo;
-              const uint32_t b_lo = b_lo0 + (uint32_t)tt * 8u * b_rows;  // 8 panels * b_rows*16 B per tap, in 16 B units
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                if (ks < ks_n)
-                  umma_f16<CG>(d_tmem, mk64(a_lo + ks * a_step, a_hi), mk64(b_lo + ks * b_step, b_hi), idesc, acc | (uint32_t)(tt | ks));
-              acc = 1;
-            }
+            const uint32_t a0 = (patch + a_off) | a_lbo;
+            if (ks_n == 4) issue_taps<CG, 4>(d_tmem, a0, a_hi, a_step, b_lo0, b_hi, b_step, b_tap, idesc, tpn, kx, kw, wrap, acc);
+            else if (ks_n == 1) issue_taps<CG, 1>(d_tmem, a0, a_hi, a_step, b_lo0, b_hi, b_step, b_tap, idesc, tpn, kx, kw, wrap, acc);
+            else if (ks_n == 2) issue_taps<CG, 2>(d_tmem, a0, a_hi, a_step, b_lo0, b_hi, b_step, b_tap, idesc, tpn, kx, kw, wrap, acc);
+            else issue_taps<CG, 3>(d_tmem, a0, a_hi, a_step, b_lo0, b_hi, b_step, b_tap, idesc, tpn, kx, kw, wrap, acc);
             umma_commit<CG>(bar(B_EMPTY2 + stage));
             if (ws == a.n_wst - 1) {
               umma_commit<CG>(bar(A_EMPTY + ast));
@@ -300,6 +320,12 @@ __device__ __forceinline__ void conv_tc_body(const ConvArgs& a) {
             }
           }
           __syncwarp();
+          // every lane advances the tap position (the elected lane may change between stages)
+          for (int tt = 0; tt < tpn; ++tt) {
+            ++a_off;
+            if (++kx == kw) kx = 0, a_off += wrap;
+          }
+          taps_left -= tpn;
           acc = 1;
         }
       }

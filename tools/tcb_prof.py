@@ -29,7 +29,9 @@ for _ in range(2):
 torch.cuda.synchronize()
 big = np.zeros((256, 64), np.uint64)
 rc = ops.lib.dfb_debug_tcb_prof(big.ctypes.data_as(C.c_void_p), 256)
-assert rc == 0, rc
+if rc != 0:
+    print("no cycle counters in this build (make -C dfnet_b200/csrc prof); ran one forward + backward of", H * W, "rays")
+    sys.exit(0)
 b = big[:148].astype(np.float64)
 names = {0: ("producer", ["wait W_EMPTY"]), 4: ("issuer", ["wait W_FULL", "wait A_READY/PASS_DONE", "wait PE_READY"]),
          8: ("epi slot0", ["wait D_FULL"]), 12: ("epi slot1", ["wait D_FULL"])}
