@@ -581,10 +581,20 @@ int dfb_conv_pack_batch_flush(bool discard) {
   if (discard) conv::g_pack.args.n = 0;   // a failed load may have destroyed handles the pending requests point to
   return conv::pack_launch(nullptr);
 }
-// DFB_CONV_CTA_GROUP=2 selects the cta_group::2 kernel and its second weight image (see dfb_conv_run)
+// cta_group used by the convolution kernel.  2 (default): CTA pairs work on two neighbouring M tiles with one weight stream
+// and one MMA instruction for both SMs; DFB_CONV_CTA_GROUP=1 selects the 1-CTA kernel (also used for single-tile launches).
+// Read per call so that tests can exercise both variants in one process; both weight images are always packed.
 static int conv_cg_env() {
-  static const int cg_env = [] { const char* e = getenv("DFB_CONV_CTA_GROUP"); return (e && e[0] == '2') ? 2 : 1; }();
-  return cg_env;
+  const char* e = getenv("DFB_CONV_CTA_GROUP");
+  return (e && e[0] == '1') ? 1 : 2;
+}
+// rounds of the persistent grid for a B x H x W launch: ceil(schedule units / resident units), a unit being one CTA
+// (1-CTA kernel) or a CTA pair working on two M tiles (cta_group::2)
+int64_t dfb_conv_rounds(const DfbConv* c, int B, int H, int W) {
+  const int64_t n_mtiles = (int64_t)((W + conv::kTW - 1) / conv::kTW) * ((H + conv::kTH - 1) / conv::kTH) * B;
+  const int cg = (c->wimg2 && n_mtiles >= 2) ? conv_cg_env() : 1;
+  const int64_t n_tiles = ((n_mtiles + cg - 1) / cg) * c->n_ntiles, units = c->num_sms / cg;
+  return (n_tiles + units - 1) / units;
 }
 
 // fmt: 0 fp16 / 1 bf16 operands.  dgrad != 0 builds the DATA-GRADIENT convolution of the layer described by
@@ -624,8 +634,8 @@ int dfb_conv_create_impl(int Cin0, int Cout0, int KH, int KW, const float* weigh
   c->n_wst = (KH * KW + c->tps - 1) / c->tps;
   c->num_sms = sms;
   c->wimg_bytes = (size_t)c->n_ntiles * c->n_cc * c->n_wst * c->tps * c->nt * 16 * 8;
-  if (cudaMalloc(&c->wimg, c->wimg_bytes) != cudaSuccess ||
-      (conv_cg_env() == 2 && cudaMalloc(&c->wimg2, c->wimg_bytes) != cudaSuccess) || cudaMalloc(&c->bias, Cout * 4) != cudaSuccess) {
+  if (cudaMalloc(&c->wimg, c->wimg_bytes) != cudaSuccess || cudaMalloc(&c->wimg2, c->wimg_bytes) != cudaSuccess ||
+      cudaMalloc(&c->bias, Cout * 4) != cudaSuccess) {
     dfb_conv_destroy(c);
     DFB_REQUIRE(false, DFB_ERR_CUDA, "dfb_conv_create: out of device memory");
   }
@@ -725,9 +735,9 @@ int dfb_conv_run(DfbConv* c, const void* in_nhwc16, int B, int H, int W, int rel
   a.error_flag = error_flag;
   const int64_t n_mtiles = (int64_t)a.tiles_x * a.tiles_y * B;
   DFB_REQUIRE(n_mtiles * a.n_ntiles < (1ll << 30), DFB_ERR_INVALID, "image too large");
-  // DFB_CONV_CTA_GROUP=2 selects the cta_group::2 kernel (CTA pairs share every weight stage).  Measured (r02, tools/
-  // conv_prof.py): with TMA patch loads both kernels wait < 15 % for operands and run the 3x3 / 5x5 layers at the same
-  // speed; the pair kernel is slower on the epilogue-bound layers (conv1_1, 1x1), so the 1-CTA kernel is the default.
+  // cta_group::2 (CTA pairs share every weight stage, one MMA instruction feeds both SMs) is the default: with the lean
+  // issue loop and CTA-scope barrier arrivals it is faster on every layer class (r02: conv1_2 79 -> 70 us, 5x5 level-0
+  // head 252 -> 210 us, conv3_2 56 -> 54 us at 480x640, batch 2); earlier in the round the two kernels had measured equal.
   const int cg = (c->wimg2 && n_mtiles >= 2) ? conv_cg_env() : 1;
   const int64_t n_tiles = ((n_mtiles + cg - 1) / cg) * a.n_ntiles;
   const int grid = cg * (int)std::min<int64_t>(n_tiles, c->num_sms / cg);

@@ -14,6 +14,7 @@ int dfb_conv_create_impl(int Cin0, int Cout0, int KH, int KW, const float* weigh
                          const float* bn_shift, int fmt, int dgrad, DfbConv** out, int nt_force = 0);
 int64_t dfb_conv_tiles(const DfbConv* c, int B, int H, int W);
 int dfb_conv_num_sms(const DfbConv* c);
+int64_t dfb_conv_rounds(const DfbConv* c, int B, int H, int W);
 int dfb_conv_update_impl(DfbConv* c, const float* weight, const float* bias, const float* bn_scale, const float* bn_shift,
                          void* stream);
 void dfb_conv_pack_batch_begin();

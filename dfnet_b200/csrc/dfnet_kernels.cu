@@ -416,7 +416,7 @@ static int dfnet_load_impl(DfbDfnet* d, const float* const* params, const int64_
                 "encoder conv %d has the wrong size", i);
     int rc = conv_set(&d->enc[i], kEncCin[i], kEncCout[i], 3, params[2 * i], params[2 * i + 1], nullptr, nullptr, 0, 0);
     if (rc) return rc;
-    if (kEncCout[i] % 256 == 0 && (!train || d->enc_n128[i])) {  // inference handles: second packing with 128-wide tiles (kept current once it exists)
+    if (kEncCout[i] % 256 == 0) {  // second packing with 128-wide output-channel tiles (see the tile choice in dfnet_fwd_impl)
       rc = conv_set(&d->enc_n128[i], kEncCin[i], kEncCout[i], 3, params[2 * i], params[2 * i + 1], nullptr, nullptr, 0, 0, 128);
       if (rc) return rc;
     }
@@ -681,7 +681,14 @@ static int dfnet_fwd_impl(DfbDfnet* d, const float* x, int B, int H, int W, uint
     void* o = need_out ? base + L.act[i] : nullptr;
     DfbConv* cv = bf ? d->enc_bf[i] : d->enc[i];
     DFB_REQUIRE(cv, DFB_ERR_INVALID, "training variants not loaded (dfb_dfnet_load_ex flags bit0)");
-    if (!bf && !tape && d->enc_n128[i] && 2 * dfb_conv_tiles(cv, B, h, w) <= dfb_conv_num_sms(cv)) cv = d->enc_n128[i];
+    // Tile choice by wave count: the persistent grid runs ceil(tiles / SMs) rounds.  A 128-wide tile is half the MMA work
+    // of a 256-wide one plus a second load of the input patch (~0.6 of its time, measured); it wins where the 256-wide
+    // tiling lands just above a multiple of the SM count (480x640 pair: conv3_x 300 tiles = 3 rounds -> 600 = 5 half
+    // rounds; conv4_x 160 = 2 rounds -> 320 = 3 half rounds; conv5_x 40 -> 80 tiles in one round).
+    if (!bf && d->enc_n128[i]) {
+      const double c256 = (double)dfb_conv_rounds(cv, B, h, w), c128 = 0.62 * (double)dfb_conv_rounds(d->enc_n128[i], B, h, w);
+      if (c128 < c256) cv = d->enc_n128[i];
+    }
     int rc = dfb_conv_fwd(cv, cur, B, h, w, 1, o, tap, nullptr, stream);
     if (rc) return rc;
     if (tap && fork) {  // level lv-1 is ready: its head starts on a side stream while the encoder continues

@@ -118,3 +118,8 @@ for name, se in sorted(seen.items()):
         for nm, (n, d) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
             print(f"    {d / 1e3:8.3f} ms  x{n:<4d} {nm}")
         print("  total kernel time %.3f ms" % (sum(k["dur"] for k in ks) / 1e3))
+        if os.environ.get("LIST"):
+            print("  every device op of the step (start us, duration us, grid, name):")
+            for k in ks:
+                g = k.get("args", {}).get("grid", "")
+                print(f"    {k['ts'] - ks[0]['ts']:9.1f} {k['dur']:8.1f} {str(g):>14s}  {k['name'][:70]}")
