@@ -102,6 +102,8 @@ struct NetPack {
   // ---- tcgen05 backward layout (fine 8x256 network): the 26-step image of mlp_tc_bwd.cu ------
   void* blob16b[2] = {nullptr, nullptr};  // [fp16|bf16]
   size_t blob16b_bytes = 0;
+  void* blob16b2[2] = {nullptr, nullptr}; // the same program in the cta_group::2 chunking (16 KB half-chunk images)
+  size_t blob16b2_bytes = 0;
   std::vector<float> tcb_tbl;
 };
 

@@ -34,6 +34,9 @@
 #include <algorithm>
 #include <type_traits>
 
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -74,7 +77,8 @@ enum Kind { F_HID, F_DT, F_T3, B_MASK, B_DIRPE, B_PESKIP, B_PE0, HEADS, SUB };
 
 struct Step {
   int n_chunks;    // weight chunks
-  int cbytes;      // bytes per chunk: 16 KB, or the two 8-column panels of a short (K = 16) step
+  int cbytes;      // bytes per chunk (1-CTA kernel): 16 KB, or the two 8-column panels of a short (K = 16) step
+  int img_base;    // cta_group::2 kernel: index of the step's first 16 KB image (chunk c = images img_base + 2c, + 2c + 1)
   int n;           // MMA N
   int a_panel0;    // first A panel
   uint32_t w_off;  // byte offset of the first chunk in the packed image
@@ -89,6 +93,8 @@ struct Step {
 };
 
 struct BtArgs {
+  // cta_group::2 only: 3-D tensor map over the pair-layout weight image ([images][64 rows][256 B] = 16 KB boxes), see mlp_tc.cu
+  alignas(64) CUtensorMap tmap;
   Step steps[kSteps];
   const void* wimg;
   const float* rayrec;   // [n_rays,12]
@@ -213,7 +219,7 @@ __device__ __forceinline__ void store_block(uint32_t dst, const uint32_t (&pk)[1
 // One weight chunk = KS K-steps.  Every ring stage has its own full / empty barrier pair: the refill of a stage starts as
 // soon as ITS MMAs have completed and the stage is waited for on its own, so n_stages - 1 chunks of MMA work cover the
 // refill latency (with stages armed in pairs only one pair did, and the issuer waited 21 % of the kernel for weights).
-template <int KS>
+template <int CG, int KS>
 __device__ __forceinline__ void issue_step(uint32_t& stage, uint32_t& phase, uint32_t n_stages, int nch, uint32_t a_lo,
                                            uint32_t b_rows, uint32_t d_tmem, uint32_t idesc, uint32_t sW, uint32_t sBar, int* err,
                                            unsigned long long* pacc, uint32_t acc) {
@@ -233,8 +239,8 @@ __device__ __forceinline__ void issue_step(uint32_t& stage, uint32_t& phase, uin
     if (elect_one()) {
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks)
-        umma_f16<1>(d_tmem, mk64(a_lo + ks * 256, desc_hi), mk64(b_lo + ks * b_step, desc_hi), idesc, acc | ks);
-      umma_commit<1>(sBar + 8u * (W_EMPTY + stage));
+        umma_f16<CG>(d_tmem, mk64(a_lo + ks * 256, desc_hi), mk64(b_lo + ks * b_step, desc_hi), idesc, acc | ks);
+      umma_commit<CG>(sBar + 8u * (W_EMPTY + stage));
     }
     __syncwarp();
     a_lo += 256u * KS;
@@ -243,8 +249,14 @@ __device__ __forceinline__ void issue_step(uint32_t& stage, uint32_t& phase, uin
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kThreads, 1) k_mlp_tc_bwd(const __grid_constant__ BtArgs a) {
+// CG = 2 (cta_group::2): the two CTAs of a cluster work on one 256-row tile per slot with ONE weight stream and one MMA
+// instruction for both SMs, exactly like the forward kernel (mlp_tc.cu, mlp_tc_body): each CTA keeps its own 128 rows
+// (A operand, TMEM accumulators, masks, epilogue) and half of every weight chunk (2-SM TMA crediting the leader's barrier);
+// tcgen05.commit multicasts the stage / accumulator hand-offs, one lane per warp arrives on the leader's barriers.
+// The 1-CTA kernel reads the whole B operand per SM and writes the whole weight stream into its shared memory: 187 B/clk
+// of shared-memory traffic against 128 B/clk available, which is what bounded it.
+template <typename T, int CG>
+__device__ __forceinline__ void mlp_tc_bwd_body(const BtArgs& a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sA = smem_u32(smem);
   const uint32_t sW = sA + 2u * (uint32_t)a.slot_bytes;
@@ -254,21 +266,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_tc_bwd(const __grid_constan
   auto bar = [&](int i) { return sBar + 8u * i; };
   const int fmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
   uint32_t* scr = a.scratch + (size_t)blockIdx.x * kScrWords;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  const int64_t unit0 = blockIdx.x / CG, n_units = gridDim.x / CG;   // a unit = CTA (CG 1) or CTA pair (CG 2)
 
   if (tid == 0) {
     for (int i = 0; i < kMaxStages; ++i) mbar_init(bar(W_FULL + i), 1), mbar_init(bar(W_EMPTY + i), 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar(D_FULL + s), 1);
-      mbar_init(bar(A_READY + s), 4);     // one arrival per warp (lane 0, after __syncwarp), see mlp_tc.cu
-      mbar_init(bar(PASS_DONE + s), 4);
-      mbar_init(bar(PE_READY + s), 4);
+      mbar_init(bar(A_READY + s), 4 * CG);     // one arrival per warp (lane 0, after __syncwarp), see mlp_tc.cu
+      mbar_init(bar(PASS_DONE + s), 4 * CG);
+      mbar_init(bar(PE_READY + s), 4 * CG);
       mbar_init(bar(PE_FREE + s), 1);
     }
     fence_barrier_init();
   }
-  if (warp == 13) tmem_alloc<1>(smem_u32(tmem_slot), 512);
+  if (warp == 13) tmem_alloc<CG>(smem_u32(tmem_slot), 512);
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -277,17 +291,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_tc_bwd(const __grid_constan
     uint32_t stage = 0, phase = 0;
     TCB_PROF_DECL
     const uint8_t* wimg = reinterpret_cast<const uint8_t*>(a.wimg);
-    for (int64_t p = blockIdx.x; p < a.n_pass; p += gridDim.x)
+    for (int64_t p = unit0; p < a.n_pass; p += n_units)
       for (int s = 0; s < a.n_steps; ++s) {
         const int nch = a.steps[s].n_chunks, cbytes = a.steps[s].cbytes;
         const uint8_t* src0 = wimg + a.steps[s].w_off;
+        const int img0 = a.steps[s].img_base + (int)rank;
         for (int slot = 0; slot < 2; ++slot) {
           const uint8_t* src = src0;
           for (int c = 0; c < nch; ++c, src += cbytes) {
             TCB_PROF_WAIT(0, mbar_wait(bar(W_EMPTY + stage), phase ^ 1, a.error_flag));
             if (elect_one()) {
-              mbar_expect_tx(bar(W_FULL + stage), cbytes);
-              bulk_g2s(sW + stage * kChunkBytes, src, cbytes, bar(W_FULL + stage));
+              if (CG == 1) {
+                mbar_expect_tx(bar(W_FULL + stage), cbytes);
+                bulk_g2s(sW + stage * kChunkBytes, src, cbytes, bar(W_FULL + stage));
+              } else {
+                // the leader arms ITS barrier with both halves' bytes; every CTA loads its own 16 KB image with a 2-SM
+                // TMA whose completion is credited to the leader's barrier
+                const uint32_t bar_leader = bar(W_FULL + stage) & 0xFEFFFFFFu;
+                if (rank == 0) mbar_expect_tx(bar(W_FULL + stage), 2 * kChunkBytes);
+                tma_load_img_2sm(sW + stage * kChunkBytes, &a.tmap, img0 + 2 * c, bar_leader);
+              }
             }
             __syncwarp();
             if (++stage == (uint32_t)a.n_stages) stage = 0, phase ^= 1;
@@ -295,15 +318,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_tc_bwd(const __grid_constan
         }
       }
     TCB_PROF_FLUSH(0)
+  } else if (warp == 13 && rank != 0) {
+    // peer CTA of a pair: the leader issues every MMA
   } else if (warp == 13) {
     // ===== MMA issuer ==========================================================================
     uint32_t stage = 0, phase = 0, na = 0;   // na: A_READY phases consumed (the same for both slots)
     int lp = 0;
     TCB_PROF_DECL
-    for (int64_t p = blockIdx.x; p < a.n_pass; p += gridDim.x, ++lp)
+    for (int64_t p = unit0; p < a.n_pass; p += n_units, ++lp)
       for (int s = 0; s < a.n_steps; ++s) {
         const int nch = a.steps[s].n_chunks, nn = a.steps[s].n;
-        const uint32_t idesc = make_idesc(fmt, nn, kTileM);
+        const uint32_t idesc = make_idesc(fmt, nn, kTileM * CG);
+        const uint32_t b_rows = (uint32_t)nn / CG;   // B rows held by each CTA
         const bool first = s == 0 || !a.steps[s - 1].chain;   // first MMA group of its accumulator
         const uint32_t acc0 = (uint32_t)a.steps[s].acc;
         for (int slot = 0; slot < 2; ++slot) {
@@ -317,14 +343,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_tc_bwd(const __grid_constan
           const uint32_t d_tmem = tmem_base + slot * 256 + a.steps[s].d_col;
           const uint32_t a_lo = ((sA + slot * a.slot_bytes + a.steps[s].a_panel0 * kPanelBytes) >> 4) | ((kPanelBytes >> 4) << 16);
           const uint32_t nst = (uint32_t)a.n_stages;
-          if (a.steps[s].kshort) issue_step<1>(stage, phase, nst, nch, a_lo, nn, d_tmem, idesc, sW, sBar, a.error_flag, TCB_PROF_PTR, acc0);
-          else if (nn == 256) issue_step<2>(stage, phase, nst, nch, a_lo, nn, d_tmem, idesc, sW, sBar, a.error_flag, TCB_PROF_PTR, acc0);
-          else if (nn == 128) issue_step<4>(stage, phase, nst, nch, a_lo, nn, d_tmem, idesc, sW, sBar, a.error_flag, TCB_PROF_PTR, acc0);
-          else issue_step<8>(stage, phase, nst, nch, a_lo, nn, d_tmem, idesc, sW, sBar, a.error_flag, TCB_PROF_PTR, acc0);
+          if (a.steps[s].kshort) issue_step<CG, 1>(stage, phase, nst, nch, a_lo, b_rows, d_tmem, idesc, sW, sBar, a.error_flag, TCB_PROF_PTR, acc0);
+          else if (nn == 256) issue_step<CG, 2 * CG>(stage, phase, nst, nch, a_lo, b_rows, d_tmem, idesc, sW, sBar, a.error_flag, TCB_PROF_PTR, acc0);
+          else if (nn == 128) issue_step<CG, 4 * CG>(stage, phase, nst, nch, a_lo, b_rows, d_tmem, idesc, sW, sBar, a.error_flag, TCB_PROF_PTR, acc0);
+          else issue_step<CG, 8 * CG>(stage, phase, nst, nch, a_lo, b_rows, d_tmem, idesc, sW, sBar, a.error_flag, TCB_PROF_PTR, acc0);
           if (elect_one()) {
-            if (!a.steps[s].chain) umma_commit<1>(bar(D_FULL + slot));
+            if (!a.steps[s].chain) umma_commit<CG>(bar(D_FULL + slot));
             // last reader of the positional-encoding panels (the skip layer, then ghA in the same panels)
-            if (s == a.pe_free_step) umma_commit<1>(bar(PE_FREE + slot));
+            if (s == a.pe_free_step) umma_commit<CG>(bar(PE_FREE + slot));
           }
           __syncwarp();
         }
@@ -335,10 +361,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_tc_bwd(const __grid_constan
     // ===== encoder: positional encoding of the next pass + its Jacobian for step 25 ================
     const int r = tid - 256;
     int lp = 0;
-    for (int64_t p = blockIdx.x; p < a.n_pass; p += gridDim.x, ++lp)
+    for (int64_t p = unit0; p < a.n_pass; p += n_units, ++lp)
       for (int slot = 0; slot < 2; ++slot) {
         if (lp > 0) mbar_wait_relaxed(bar(PE_FREE + slot), (lp - 1) & 1, a.error_flag);
-        int64_t g = (2 * p + slot) * kTileM + r;
+        int64_t g = ((2 * p + slot) * CG + rank) * kTileM + r;
         g = g < a.P ? g : a.P - 1;
         const int64_t ray = g / a.S;
         const float* rr = a.rayrec + ray * kRayRec;
@@ -369,7 +395,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_tc_bwd(const __grid_constan
         __threadfence_block();
         fence_proxy_async();
         __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(bar(PE_READY + slot));
+        if ((tid & 31) == 0) arrive_leader<CG>(bar(PE_READY + slot));
       }
   } else if (warp < 8) {
     // ===== epilogue warpgroups (thread = accumulator row = sample) ================================
@@ -385,16 +411,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_tc_bwd(const __grid_constan
 #ifdef DFB_TC_PROF
     unsigned long long pstep[kSteps] = {0};
 #endif
-    for (int64_t p = blockIdx.x; p < a.n_pass; p += gridDim.x, ++lp) {
-      const int64_t g = (2 * p + slot) * kTileM + r;
+    for (int64_t p = unit0; p < a.n_pass; p += n_units, ++lp) {
+      const int64_t tile = (2 * p + slot) * CG + rank;   // 128-row tile of the flattened [ray][sample] array
+      const int64_t g = tile * kTileM + r;
       const bool valid = g < a.P;
       const int64_t gc = valid ? g : a.P - 1;
       const float* rb = a.raybias + (gc / a.S) * 256;
       asm volatile("prefetch.global.L1 [%0];" ::"l"(rb + (tid & 7) * 32));
       float isc = 1.f;
       // saved masks cover ceil(P/128) tiles; a tile past the end (odd tile count) has no rows and reads the scratch
-      const uint32_t* mpass = a.saved_masks && (2 * p + slot) * kTileM < a.P
-                                  ? a.saved_masks + (size_t)(2 * p + slot) * (kMaskLayers * 8 * 128) + r : mbase;
+      const uint32_t* mpass = a.saved_masks && tile * kTileM < a.P
+                                  ? a.saved_masks + (size_t)tile * (kMaskLayers * 8 * 128) + r : mbase;
       for (int s = 0; s < a.n_steps; ++s) {
         const int kd = a.steps[s].kind, ncb = a.steps[s].ncb;
         if (kd == SUB) continue;   // first MMA group of a compound step: nothing to read yet
@@ -544,7 +571,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_tc_bwd(const __grid_constan
         tc_fence_before();
         fence_proxy_async();
         __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(bar((s + 1 < a.n_steps ? A_READY : PASS_DONE) + slot));
+        if ((tid & 31) == 0) arrive_leader<CG>(bar((s + 1 < a.n_steps ? A_READY : PASS_DONE) + slot));
 #ifdef DFB_TC_PROF
         pstep[s] += clock64() - _ts;
 #endif
@@ -559,11 +586,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_tc_bwd(const __grid_constan
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync(); else __syncthreads();
   if (warp == 13) {
     tc_fence_after();
-    tmem_dealloc<1>(tmem_base, 512);
+    tmem_dealloc<CG>(tmem_base, 512);
   }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1) k_mlp_tc_bwd(const __grid_constant__ BtArgs a) {
+  mlp_tc_bwd_body<T, 1>(a);
+}
+
+template <typename T>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_mlp_tc_bwd2(const __grid_constant__ BtArgs a) {
+  mlp_tc_bwd_body<T, 2>(a);
 }
 
 }  // namespace tcb
@@ -617,8 +654,10 @@ constexpr int kPeFreeStep = 19;     // the sigma short step: last reader of ghA 
 
 int pack_tc_bwd_weights(DfbNerf* n, int which, const std::vector<std::vector<float>>& P_in) {
   NetPack& np = n->net[which];
-  for (int k = 0; k < 2; ++k)
+  for (int k = 0; k < 2; ++k) {
     if (np.blob16b[k]) { cudaFree(np.blob16b[k]); np.blob16b[k] = nullptr; }
+    if (np.blob16b2[k]) { cudaFree(np.blob16b2[k]); np.blob16b2[k] = nullptr; }
+  }
   np.tcb_tbl.clear();
   if (!np.fine || !tc_padded_shape(np)) return DFB_OK;
   const std::vector<std::vector<float>> P = tc_pad_params(np, P_in);  // narrower networks: embedded in 8x256 with zeros
@@ -686,6 +725,39 @@ int pack_tc_bwd_weights(DfbNerf* n, int which, const std::vector<std::vector<flo
     DFB_CHECK_CUDA(cudaMalloc(&np.blob16b[k], np.blob16b_bytes));
     DFB_CHECK_CUDA(cudaMemcpy(np.blob16b[k], img16[k].data(), np.blob16b_bytes, cudaMemcpyHostToDevice));
   }
+  // cta_group::2 layout: every chunk is two 16 KB images, image h = rows [h N/2, (h+1) N/2) of B over the chunk's K
+  // columns (64 / 128 / 256 for N = 256 / 128 / 64; a short step fills the first N/2 x 32 bytes of its images)
+  {
+    size_t n_img = 0;
+    for (const BStep& st : prog) {
+      const int rows = st.N / 2, kc = st.kshort ? 16 : tcb::kChunkBytes / (rows * 2);
+      DFB_REQUIRE(st.K % kc == 0, DFB_ERR_INVALID, "backward program: K = %d is not a whole number of %d-column chunks", st.K, kc);
+      n_img += 2 * (size_t)(st.K / kc);
+    }
+    std::vector<uint16_t> im2[2];
+    im2[0].assign(n_img * (tcb::kChunkBytes / 2), 0);
+    im2[1].assign(n_img * (tcb::kChunkBytes / 2), 0);
+    size_t img = 0;
+    for (const BStep& st : prog) {
+      const int rows = st.N / 2, kc = st.kshort ? 16 : tcb::kChunkBytes / (rows * 2);
+      for (int k0 = 0; k0 < st.K; k0 += kc)
+        for (int h = 0; h < 2; ++h, ++img) {
+          const size_t b0 = img * (tcb::kChunkBytes / 2);
+          for (int kk = 0; kk < kc; ++kk)
+            for (int r = 0; r < rows; ++r) {
+              const float v = wval(st.logical, h * rows + r, k0 + kk);
+              const size_t idx = b0 + (size_t)(kk / 8) * rows * 8 + (size_t)r * 8 + kk % 8;
+              im2[0][idx] = f2h(v);
+              im2[1][idx] = f2b(v);
+            }
+        }
+    }
+    np.blob16b2_bytes = n_img * tcb::kChunkBytes;
+    for (int k = 0; k < 2; ++k) {
+      DFB_CHECK_CUDA(cudaMalloc(&np.blob16b2[k], np.blob16b2_bytes));
+      DFB_CHECK_CUDA(cudaMemcpy(np.blob16b2[k], im2[k].data(), np.blob16b2_bytes, cudaMemcpyHostToDevice));
+    }
+  }
   // fp32 table: [10][256] biases of the packed rows | dt_bias 256 | t3_bias 128
   np.tcb_tbl.assign(10 * 256 + 256 + 128, 0.f);
   float* tb = np.tcb_tbl.data();
@@ -700,7 +772,7 @@ int pack_tc_bwd_weights(DfbNerf* n, int which, const std::vector<std::vector<flo
 
 bool tc_bwd_supported(const DfbNerf* n) {
   const NetPack& np = n->net[1];
-  return np.loaded && np.fine && np.blob16b[0] != nullptr && !np.tcb_tbl.empty();
+  return np.loaded && np.fine && np.blob16b[0] != nullptr && np.blob16b2[0] != nullptr && !np.tcb_tbl.empty();
 }
 
 static unsigned long long* g_tcb_prof = nullptr;
@@ -723,17 +795,26 @@ int launch_mlp_tc_bwd(const DfbNerf* nerf, int kind, const float* rayrec, const 
   memset(&a, 0, sizeof(a));
   const std::vector<BStep> prog = bwd_program();
   DFB_REQUIRE((int)prog.size() == tcb::kSteps, DFB_ERR_INVALID, "backward program / kSteps mismatch");
-  int ns = 0;
+  // DFB_TC_CTA_GROUP=1 selects the 1-CTA kernel (as for the forward kernel); the default is the cta_group::2 pair kernel
+  const int cg = tc_cta_group_env();
+  int ns = 0, img = 0;
   size_t woff = 0;
   for (int s = 0; s < tcb::kSteps; ++s) {
     const BStep& ls = prog[s];
-    const int cbytes = ls.kshort ? ls.N * 32 : tcb::kChunkBytes;
-    const int nch = (int)((size_t)ls.K * ls.N * 2 / cbytes);
-    const tcb::Step st_full = {nch, cbytes, ls.N, ls.a_panel0, (uint32_t)woff, ls.kind, ls.ml, ls.brow,
+    int cbytes, nch;
+    if (cg == 1) {
+      cbytes = ls.kshort ? ls.N * 32 : tcb::kChunkBytes;
+      nch = (int)((size_t)ls.K * ls.N * 2 / cbytes);
+    } else {
+      cbytes = tcb::kChunkBytes;
+      nch = ls.kshort ? 1 : ls.K / (tcb::kChunkBytes / ((ls.N / 2) * 2));
+    }
+    const tcb::Step st_full = {nch, cbytes, img, ls.N, ls.a_panel0, (uint32_t)woff, ls.kind, ls.ml, ls.brow,
                                ls.ncb, ls.d_col, ls.kshort, ls.acc, ls.chain};
     woff += (size_t)ls.K * ls.N * 2;
+    img += 2 * (ls.kshort ? 1 : ls.K / (tcb::kChunkBytes / ((ls.N / 2) * 2)));
     if (!saved_masks) a.steps[ns++] = st_full;
-    else if (s == kFirstBwdStep - 1) a.steps[ns++] = {0, tcb::kChunkBytes, 128, 0, 0u, tcb::HEADS, 11, 0, 0, 0, 0, 0, 0};  // head derivatives only, no MMA
+    else if (s == kFirstBwdStep - 1) a.steps[ns++] = {0, tcb::kChunkBytes, 0, 128, 0, 0u, tcb::HEADS, 11, 0, 0, 0, 0, 0, 0};  // head derivatives only, no MMA
     else if (s >= kFirstBwdStep) a.steps[ns++] = st_full;
   }
   a.n_steps = ns;
@@ -744,7 +825,11 @@ int launch_mlp_tc_bwd(const DfbNerf* nerf, int kind, const float* rayrec, const 
   const int smem_bytes = tcb::smem_total(pe_panels, a.n_stages);
   a.pe_free_step = saved_masks ? kPeFreeStep - (kFirstBwdStep - 1) : kPeFreeStep;
   a.saved_masks = saved_masks;
-  a.wimg = np.blob16b[kind == DFB_MMA_F16 ? 0 : 1];
+  a.wimg = cg == 2 ? np.blob16b2[kind == DFB_MMA_F16 ? 0 : 1] : np.blob16b[kind == DFB_MMA_F16 ? 0 : 1];
+  if (cg == 2) {
+    const int rc = make_weight_tmap(const_cast<void*>(a.wimg), np.blob16b2_bytes, &a.tmap);
+    if (rc) return rc;
+  }
   const float* tb = np.tcb_tbl.data();
   for (int i = 0; i < 10 * 128; ++i) {
     const float lo = tb[2 * i], hi = tb[2 * i + 1];
@@ -763,8 +848,8 @@ int launch_mlp_tc_bwd(const DfbNerf* nerf, int kind, const float* rayrec, const 
   a.prof = g_tcb_prof;
 #endif
   const int64_t tiles = (a.P + tcb::kTileM - 1) / tcb::kTileM;
-  a.n_pass = (tiles + 1) / 2;
-  const int grid = (int)std::min<int64_t>(a.n_pass, nerf->num_sms);
+  a.n_pass = (tiles + 2 * cg - 1) / (2 * cg);
+  const int grid = cg * (int)std::min<int64_t>(a.n_pass, nerf->num_sms / cg);
   if (nerf->bwd_scratch_ctas < grid) {  // per handle (= per device), see DfbNerf
     if (nerf->bwd_scratch) cudaFree(nerf->bwd_scratch);
     nerf->bwd_scratch = nullptr, nerf->bwd_scratch_ctas = 0;
@@ -778,6 +863,7 @@ int launch_mlp_tc_bwd(const DfbNerf* nerf, int kind, const float* rayrec, const 
     DFB_LAUNCH_CHECK();
     return DFB_OK;
   };
+  if (cg == 2) return kind == DFB_MMA_F16 ? launch(tcb::k_mlp_tc_bwd2<__half>) : launch(tcb::k_mlp_tc_bwd2<__nv_bfloat16>);
   if (kind == DFB_MMA_F16) return launch(tcb::k_mlp_tc_bwd<__half>);
   return launch(tcb::k_mlp_tc_bwd<__nv_bfloat16>);
 }

@@ -102,8 +102,10 @@ extern "C" void dfb_nerf_destroy(DfbNerf* n) {
     for (int k = 0; k < 2; ++k)
       for (int g = 0; g < 2; ++g)
         if (n->net[i].blob16[k][g]) cudaFree(n->net[i].blob16[k][g]);
-    for (int k = 0; k < 2; ++k)
+    for (int k = 0; k < 2; ++k) {
       if (n->net[i].blob16b[k]) cudaFree(n->net[i].blob16b[k]);
+      if (n->net[i].blob16b2[k]) cudaFree(n->net[i].blob16b2[k]);
+    }
     if (n->net[i].tc_dtbias_dev) cudaFree(n->net[i].tc_dtbias_dev);
     if (n->net[i].tc_dtbias_n_dev) cudaFree(n->net[i].tc_dtbias_n_dev);
     for (int k = 0; k < 2; ++k)
