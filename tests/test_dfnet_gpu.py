@@ -54,8 +54,12 @@ def check_feats(tag, got, want, L, FEAT_L2=FEAT_L2, FEAT_MAX=FEAT_MAX):
 @pytest.mark.parametrize("cin,cout,k,B,H,W,relu", [
     (3, 64, 3, 2, 48, 64, 1), (64, 128, 3, 1, 37, 53, 1), (256, 64, 1, 2, 12, 16, 1), (64, 128, 5, 1, 48, 64, 0),
     (512, 512, 3, 1, 30, 40, 1), (128, 256, 3, 3, 9, 7, 0)])
-def test_conv_layer_vs_torch_fp32(cin, cout, k, B, H, W, relu):
+@pytest.mark.parametrize("cg", ["2", "1"])
+def test_conv_layer_vs_torch_fp32(cin, cout, k, B, H, W, relu, cg, monkeypatch):
+    """Both variants of the convolution kernel: cta_group::2 CTA pairs (the default) and the 1-CTA kernel
+    (DFB_CONV_CTA_GROUP=1, also what a single-tile launch uses)."""
     from dfnet_b200._lib import lib, check
+    monkeypatch.setenv("DFB_CONV_CTA_GROUP", cg)
     torch.manual_seed(cin * 7 + cout + k)
     w = torch.randn(cout, cin, k, k, device=dev()) * (2.0 / (cin * k * k)) ** 0.5
     b = torch.randn(cout, device=dev()) * 0.1
