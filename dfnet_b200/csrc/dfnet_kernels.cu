@@ -584,7 +584,10 @@ static int dfnet_fwd_impl(DfbDfnet* d, const float* x, int B, int H, int W, uint
   DFB_LAUNCH_CHECK();
   // One adaptation head (1x1 conv + ReLU, 5x5 conv + BatchNorm, resampling into the stacks) on stream `st`.
   const int Bs = single ? B : B / 2;
+  // flags bits 8..10: level l is not wanted (its head is not evaluated, its slice of the stacks is left untouched)
+  const uint32_t skip = (flags >> 8) & 7u;
   auto run_head = [&](int l, cudaStream_t st) -> int {
+    if (skip & (1u << l)) return DFB_OK;
     void* stream = (void*)st;
       const int fh = L.h[kTapConv[l]], fw = L.w[kTapConv[l]];
       int rc = dfb_conv_fwd(d->head1[l], base + L.tap[l], B, fh, fw, 1, base + L.mid[l], nullptr, nullptr, stream);
@@ -673,10 +676,17 @@ static int dfnet_fwd_impl(DfbDfnet* d, const float* x, int B, int H, int W, uint
   }
   const void* cur = base + L.in8;
   int h = H, w = W, lv = 0;
-  const int last_conv = d->n_levels == 1 && !ret_pose ? 1 : 12;  // DFNet_s stops after conv1_2 when no pose is needed
+  // without a pose the encoder stops after the deepest hyper-column that is wanted (DFNet_s: conv1_2; DFNet with only
+  // level 0 wanted, e.g. the feature net of train_on_batch with feature_matching_lvl = [0]: conv1_2 as well)
+  int last_conv = 12;
+  if (!ret_pose && ret_feat) {
+    last_conv = 0;
+    for (int l = 0; l < d->n_levels; ++l)
+      if (!(skip & (1u << l))) last_conv = std::max(last_conv, kTapConv[l]);
+  }
   for (int i = 0; i <= last_conv; ++i) {
     void* tap = nullptr;
-    if (ret_feat && lv < d->n_levels && kTapConv[lv] == i) { tap = base + L.tap[lv]; ++lv; }
+    if (ret_feat && lv < d->n_levels && kTapConv[lv] == i) { tap = (skip & (1u << lv)) ? nullptr : base + L.tap[lv]; ++lv; }
     const bool need_out = i < last_conv || ret_pose || tape;
     void* o = need_out ? base + L.act[i] : nullptr;
     DfbConv* cv = bf ? d->enc_bf[i] : d->enc[i];

@@ -96,16 +96,19 @@ class _DfnetHandle:
         through `.data` do not bump `_version`, so call this after such writes."""
         self._versions = None
 
-    def forward(self, x, return_feature, single, return_pose, upH, upW, tape=False, bf16=False, bn_train=False, head_train=False):
+    def forward(self, x, return_feature, single, return_pose, upH, upW, tape=False, bf16=False, bn_train=False, head_train=False,
+                skip_levels=0):
         """tape=True keeps every activation in a fresh buffer (returned as 4th value) for `backward`.
-        bn_train=True: train-mode BatchNorm in the heads (batch statistics, see `bn_batch_stats`)."""
+        bn_train=True: train-mode BatchNorm in the heads (batch statistics, see `bn_batch_stats`).
+        skip_levels: bit l set = feature level l is not wanted (not computed; its slice of the stacks is uninitialised)."""
         if not x.is_cuda:
             raise _lib.DfbError("DFNet input must be a CUDA tensor: the dfnet_b200 hot path has no CPU fallback")
         x = x.detach().float().contiguous()
         B, _, H, W = x.shape
         dev = x.device
         need = C.c_size_t()
-        flags = (1 if return_feature else 0) | (2 if single else 0) | (4 if return_pose else 0) | (32 if bn_train else 0)
+        flags = (1 if return_feature else 0) | (2 if single else 0) | (4 if return_pose else 0) | (32 if bn_train else 0) \
+            | ((int(skip_levels) & 7) << 8)
         if tape:
             check(lib.dfb_dfnet_tape_bytes(self._h, B, H, W, upH, upW, C.byref(need)))
             ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
@@ -212,10 +215,10 @@ class _DfnetFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, handle, cfg, *params):
-        return_feature, single, return_pose, upH, upW, level_mask, _bf16, bn_train, head_train = cfg
+        return_feature, single, return_pose, upH, upW, level_mask, _bf16, bn_train, head_train, skip = cfg
         need_p = any(t.requires_grad for t in params)
         ft, fr, pose, tape = handle.forward(x, return_feature, single, return_pose, upH, upW, tape=True, bf16=bool(cfg[6]),
-                                            bn_train=bn_train, head_train=head_train)
+                                            bn_train=bn_train, head_train=head_train, skip_levels=skip)
         ctx.handle, ctx.tape, ctx.cfg, ctx.need_p = handle, tape, cfg, need_p
         ctx.xshape = (x.shape[0], x.shape[2], x.shape[3])
         ctx.pshapes = [t.shape for t in params]
@@ -229,7 +232,7 @@ class _DfnetFn(torch.autograd.Function):
     def backward(ctx, *gs):
         g = dict(zip(ctx.slots, gs))
         g_ft, g_fr, g_pose = (None if g.get(k) is None else g[k].float().contiguous() for k in ("ft", "fr", "pose"))
-        return_feature, single, return_pose, upH, upW, level_mask, _bf16, bn_train, head_train = ctx.cfg
+        return_feature, single, return_pose, upH, upW, level_mask, _bf16, bn_train, head_train, _skip = ctx.cfg
         n_out = 3 + len(ctx.pshapes)
         feat_g = g_ft is not None or g_fr is not None
         if g_ft is None and g_fr is None and g_pose is None:
@@ -290,21 +293,31 @@ class DFNet(nn.Module):
         head_params = [t for l in range(len(self.hypercolumn_layers)) for t in params[26 + 8 * l:26 + 8 * l + 6]]
         head_train = bool(train and return_feature and any(t.requires_grad for t in head_params))
         self._handle.refresh(self, train=train, bn_train=bn_train, head_train=head_train)
+        # want_levels (optional attribute, None = all): hyper-column levels the caller is going to read.  The others are not
+        # computed - their slices of the returned stacks are uninitialised - and without a pose the encoder stops after the
+        # deepest wanted level.  The reference always evaluates all three; train_on_batch reads feature_matching_lvl only.
+        n_lv = len(self.hypercolumn_layers)
+        want = getattr(self, "want_levels", None)
+        skip = 0 if (want is None or bn_train or not return_feature) else sum(1 << l for l in range(n_lv) if l not in set(want))
         if train:
             levels = getattr(self, "grad_levels", None)
+            if skip and levels is None:
+                levels = [l for l in range(n_lv) if not (skip >> l) & 1]
+            if skip and any((skip >> l) & 1 for l in levels):
+                raise ValueError("grad_levels must be a subset of want_levels")
             mask = sum(1 << l for l in (range(len(self.hypercolumn_layers)) if levels is None else levels))
             # train_dtype: "f16" (default: the inference kernels' fp16 forward, bf16 gradients) or "bf16" (BASELINE config[3]:
             # bf16 storage in the pose regressor's forward as well)
             bf16 = getattr(self, "train_dtype", "f16") == "bf16" and not return_feature
             cfg = (bool(return_feature), bool(isSingleStream), bool(return_pose), int(upsampleH), int(upsampleW), mask, bf16, bn_train,
-                   head_train)
+                   head_train, skip)
             outs = list(_DfnetFn.apply(x, self._handle, cfg, *params))
             ft = outs.pop(0) if return_feature else None
             fr = outs.pop(0) if return_feature and not isSingleStream else None
             pose = outs.pop(0) if return_pose else None
         else:
             ft, fr, pose = self._handle.forward(x, return_feature, isSingleStream, return_pose, int(upsampleH), int(upsampleW),
-                                                bn_train=bn_train)
+                                                bn_train=bn_train, skip_levels=skip)
         if bn_train:
             # torch.nn.BatchNorm2d bookkeeping: running = (1 - m) running + m stat, with the UNBIASED batch variance
             stats = self._handle.bn_batch_stats(x.device)

@@ -86,9 +86,15 @@ def render_prediction(args, c2w, img_idx, hwf, half_res, render_kwargs):
 def matching_terms(args, data, rgb, feat_model, device):
     """Stage 3: photometric MSE and the cosine feature-metric loss between the target image and the rendered view
     through the frozen feature net (reference :354-370).  Only the rendered stream carries gradient."""
-    feat_model.grad_levels = list(args.feature_matching_lvl)  # levels whose gradient is non-zero after index_select
-    (feature_target, feature_rgb), _ = inference_pose_regression(args, torch.cat([data, rgb]), device, feat_model, retFeature=True,
-                                                                 isSingleStream=False, return_pose=False)
+    # hints for the feature net, scoped to this call: only feature_matching_lvl is read afterwards, so the other levels are
+    # neither computed (want_levels; with level 0 alone the encoder stops after conv1_2) nor differentiated (grad_levels)
+    prev = (getattr(feat_model, "grad_levels", None), getattr(feat_model, "want_levels", None))
+    feat_model.grad_levels = feat_model.want_levels = list(args.feature_matching_lvl)
+    try:
+        (feature_target, feature_rgb), _ = inference_pose_regression(args, torch.cat([data, rgb]), device, feat_model, retFeature=True,
+                                                                     isSingleStream=False, return_pose=False)
+    finally:
+        feat_model.grad_levels, feat_model.want_levels = prev
     f_rgb = preprocess_features_for_loss(_take_levels(feature_rgb, args.feature_matching_lvl, feat_model))
     # the target stream is a constant of the step (frozen feature net, image without gradient)
     f_tgt = preprocess_features_for_loss(_take_levels(feature_target.detach(), args.feature_matching_lvl, feat_model))
@@ -122,7 +128,7 @@ def _take_levels(stack, levels, feat_model):
     contiguous = lv == list(range(lv[0], lv[0] + len(lv)))
     if contiguous and not (torch.is_grad_enabled() and stack.requires_grad):
         return stack.narrow(0, lv[0], len(lv))
-    if contiguous and isinstance(feat_model, DFNet) and list(getattr(feat_model, "grad_levels", None) or []) == lv:
+    if contiguous and isinstance(feat_model, DFNet):   # matching_terms told it to differentiate exactly these levels
         return _TakeLevels.apply(stack, lv[0], len(lv))
     return torch.index_select(stack, 0, torch.tensor(lv, device=stack.device))
 

@@ -232,7 +232,8 @@ int dfb_dfnet_workspace_bytes(const DfbDfnet* net, int B, int H, int W, int upH,
  * flags: bit0 return_feature, bit1 isSingleStream, bit2 return_pose, bit3 keep the tape (training), bit4 bf16
  * encoder (pose-only training), bit5 train-mode BatchNorm in the heads: batch statistics over the whole batch of this
  * call (run_feature.py:133,204 without freezeBN; needs dfb_dfnet_load_ex flags bit2; the statistics are read back with
- * dfb_dfnet_bn_batch_stats for the caller's running-statistics update).
+ * dfb_dfnet_bn_batch_stats for the caller's running-statistics update), bits 8..10 level 0 / 1 / 2 not wanted (its head is
+ * skipped and its slice of the stacks left untouched; without a pose the encoder stops after the deepest wanted level).
  * feats_t / feats_r: [L, Bs, 128, upH, upW] fp32, Bs = B (single stream; feats_r unused) or B/2
  * (siamese: first half of the batch -> feats_t, second half -> feats_r).  pose: [B,12]. */
 int dfb_dfnet_fwd(DfbDfnet* net, const float* x, int B, int H, int W, uint32_t flags, int upH, int upW, float* feats_t,

@@ -178,6 +178,40 @@ def test_feature_loss_vs_reference_golden(g):
     assert abs(float(feature_loss(a, b, img_in=False)) - 1.0) < 1e-6
 
 
+@pytest.mark.parametrize("want", [[0], [1], [0, 2]])
+def test_dfnet_want_levels_skips_the_other_levels(want):
+    """The `want_levels` hint (set by train_on_batch's matching_terms around the feature net's call): the wanted levels are
+    bit-identical to a full forward, with and without a pose; the gradient w.r.t. the image through a wanted level equals
+    the full forward's."""
+    net = synthetic_dfnet("DFNet").to(dev()).eval()
+    for p in net.parameters():
+        p.requires_grad_(False)
+    torch.manual_seed(5)
+    x = torch.rand(2, 3, 72, 104, device=dev())
+    with torch.no_grad():
+        full, pose_full = net(x, return_feature=True, isSingleStream=False, return_pose=True, upsampleH=72, upsampleW=104)
+        net.want_levels = want
+        for rp in (False, True):
+            part, pose = net(x, return_feature=True, isSingleStream=False, return_pose=rp, upsampleH=72, upsampleW=104)
+            torch.cuda.synchronize()
+            for l in want:
+                assert torch.equal(part[0][l], full[0][l]) and torch.equal(part[1][l], full[1][l]), (want, l, rp)
+            if rp:
+                assert torch.equal(pose, pose_full)
+    grads = []
+    for w in (None, want):
+        net.want_levels = net.grad_levels = w
+        xi = x.clone().requires_grad_(True)
+        f, _ = net(xi, return_feature=True, isSingleStream=False, return_pose=False, upsampleH=72, upsampleW=104)
+        f[1][want[0]].square().mean().backward()
+        grads.append(xi.grad.clone())
+    net.want_levels = net.grad_levels = None
+    # (the full backward adds the other levels' zero gradients in bf16 at the taps: equal up to that rounding)
+    diff = float((grads[0] - grads[1]).abs().max()) / float(grads[0].abs().max())
+    print("want", want, "image-gradient difference vs the full forward / backward:", diff)
+    assert torch.isfinite(grads[1]).all() and diff < 1e-2
+
+
 def test_dfnet_full_size_pair_properties():
     """BASELINE config[2] shape: a 640x480 target/render pair, level-0 cosine loss."""
     from dfnet_b200.dfnet import feature_loss
