@@ -420,16 +420,20 @@ static int dfnet_load_impl(DfbDfnet* d, const float* const* params, const int64_
       rc = conv_set(&d->enc_n128[i], kEncCin[i], kEncCout[i], 3, params[2 * i], params[2 * i + 1], nullptr, nullptr, 0, 0, 128);
       if (rc) return rc;
     }
-    if (train) {
+    if (train && !(flags & 32)) {   // bit5: the bf16 encoder forward is not going to run with these weights
       rc = conv_set(&d->enc_bf[i], kEncCin[i], kEncCout[i], 3, params[2 * i], params[2 * i + 1], nullptr, nullptr, 1, 0);
       if (rc) return rc;
+    }
+    if (train) {
       rc = conv_set(&d->enc_dg[i], kEncCin[i], kEncCout[i], 3, params[2 * i], nullptr, nullptr, nullptr, 1, 1);
       if (rc) return rc;
     }
   }
   if (!d->bn_sc) DFB_CHECK_CUDA(cudaMalloc(&d->bn_sc, 3 * 128 * 4));
   if (!d->bn_sh) DFB_CHECK_CUDA(cudaMalloc(&d->bn_sh, 3 * 128 * 4));
-  for (int l = 0; l < d->n_levels; ++l) {
+  // bit4: the adaptation heads are not going to be evaluated with these weights (a pose regressor re-loaded after every
+  // optimizer step): their images are left as they are
+  for (int l = 0; l < ((flags & 16) ? 0 : d->n_levels); ++l) {
     const float* const* p = params + 26 + 8 * l;
     const int64_t* ne = numel + 26 + 8 * l;
     DFB_REQUIRE(ne[0] == 64 * kTapCh[l] && ne[1] == 64 && ne[2] == 128 * 64 * 25 && ne[3] == 128 && ne[4] == 128 &&

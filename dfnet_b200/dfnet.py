@@ -56,7 +56,10 @@ class _DfnetHandle:
         self._bucket_ev = None
         self.last_flat_grad = self.last_grad_views = None
 
-    def refresh(self, module, train=False, bn_train=False, head_train=False):
+    def refresh(self, module, train=False, bn_train=False, head_train=False, need_feats=True, need_bf16=True):
+        """need_feats / need_bf16 = False: the adaptation heads / the bf16 encoder variant are not (re)packed by this load
+        (a pose regressor that is re-loaded after every optimizer step never evaluates its heads, and only
+        train_dtype="bf16" runs the bf16 encoder); they are brought up to date by the first call that needs them."""
         # state_dict() walks and renames every tensor (~ms): cache the tensors themselves, keyed on their identity,
         # and poll their versions
         key = (id(module), tuple(id(t) for t in module.parameters()), tuple(id(t) for t in module.buffers()))
@@ -67,9 +70,14 @@ class _DfnetHandle:
         v = [(t.data_ptr(), t._version) for t in sd.values()] + [bool(train)]
         bn_train = bn_train or head_train      # both need the un-folded 5x5 convs and the BatchNorm vectors on the device
         have_bn, have_ht = getattr(self, "_bn_loaded", False), getattr(self, "_ht_loaded", False)
+        heads_ok, bf_ok = getattr(self, "_heads_current", False), getattr(self, "_bf_current", False)
         if v[:-1] == (self._versions or [None])[:-1] and (self._versions[-1] or not train) and (have_bn or not bn_train) and \
-                (have_ht or not head_train):
+                (have_ht or not head_train) and (heads_ok or not need_feats) and (bf_ok or not (need_bf16 and train)):
             return
+        same = v[:-1] == (self._versions or [None])[:-1]
+        # variants that are current stay current only if the weights did not change; what this load packs becomes current
+        need_feats = need_feats or bn_train or head_train or (same and heads_ok)
+        need_bf16 = need_bf16 or (same and bf_ok)
         names = [f"encoder.{i}" for i, m in enumerate(module.encoder) if isinstance(m, nn.Conv2d)]
         ts = []
         for n in names:
@@ -86,8 +94,10 @@ class _DfnetHandle:
         # bit 1: everything is ordered on the legacy default stream -> the library skips its host synchronisation
         on_default = all(t.is_cuda for t in ts) and torch.cuda.current_stream(ts[0].device).cuda_stream == 0
         check(lib.dfb_dfnet_load_ex(self._h, ptrs, numel, len(ts), eps,
-                                    (1 if train else 0) | (2 if on_default else 0) | (4 if bn_train else 0) | (8 if head_train else 0)))
+                                    (1 if train else 0) | (2 if on_default else 0) | (4 if bn_train else 0) | (8 if head_train else 0)
+                                    | (0 if need_feats else 16) | (0 if need_bf16 else 32)))
         self._bn_loaded, self._ht_loaded = bool(bn_train), bool(head_train)
+        self._heads_current, self._bf_current = bool(need_feats), bool(need_bf16 and train)
         self._versions = v
         self.n_params = len(ts)
 
@@ -292,7 +302,8 @@ class DFNet(nn.Module):
         # the adaptation heads themselves are trained (run_feature.py): their parameters require grad and features are returned
         head_params = [t for l in range(len(self.hypercolumn_layers)) for t in params[26 + 8 * l:26 + 8 * l + 6]]
         head_train = bool(train and return_feature and any(t.requires_grad for t in head_params))
-        self._handle.refresh(self, train=train, bn_train=bn_train, head_train=head_train)
+        self._handle.refresh(self, train=train, bn_train=bn_train, head_train=head_train, need_feats=bool(return_feature),
+                             need_bf16=getattr(self, "train_dtype", "f16") == "bf16" and not return_feature)
         # want_levels (optional attribute, None = all): hyper-column levels the caller is going to read.  The others are not
         # computed - their slices of the returned stacks are uninitialised - and without a pose the encoder stops after the
         # deepest wanted level.  The reference always evaluates all three; train_on_batch reads feature_matching_lvl only.

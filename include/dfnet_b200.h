@@ -323,7 +323,9 @@ int dfb_conv_wgrad(const void* gO, const void* X, int B, int H, int W, int Cin, 
 
 /* dfb_dfnet_load, flags bit0: also build the training variants (bf16 encoder, data-gradient convolutions); bit1: the
  * caller's work is ordered on the legacy default stream and the sources stay alive in stream order (no host
- * synchronisation); bit2: also build the train-mode BatchNorm variants of the heads (5x5 convs without the fold). */
+ * synchronisation); bit2: also build the train-mode BatchNorm variants of the heads (5x5 convs without the fold); bit3: the
+ * heads' own training variants; bit4: leave the adaptation heads' images as they are (they are not going to be evaluated
+ * with these weights: a pose regressor re-loaded after every optimizer step); bit5: likewise the bf16 encoder variant. */
 int dfb_dfnet_load_ex(DfbDfnet* d, const float* const* params, const int64_t* numel, int n_params, float bn_eps,
                       uint32_t flags);
 /* Batch statistics of the last forward with flags bit5: out [n_levels][2][128] = mean, biased variance per channel. */
