@@ -103,7 +103,8 @@ __global__ void __launch_bounds__(256) k_resize_area(const float* __restrict__ s
 // ---------------------------------------------------------------------------------------------------------------------
 // R -> U V^T (the orthogonal polar factor, what torch.svd + matmul(u, v^T) produces) by Jacobi eigen-decomposition of
 // R^T R = V diag(s^2) V^T and U V^T = R V diag(1/s) V^T.
-__device__ void polar_orthogonal(const double R[9], double Q[9]) {
+// Vout / s2out (nullable): the eigenvectors and eigenvalues of R^T R, i.e. V and the squared singular values of R.
+__device__ void polar_orthogonal(const double R[9], double Q[9], double* Vout = nullptr, double* s2out = nullptr) {
   double A[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j) {
@@ -148,6 +149,55 @@ __device__ void polar_orthogonal(const double R[9], double Q[9]) {
       for (int k = 0; k < 3; ++k) s += R[i * 3 + k] * M[k * 3 + j];
       Q[i * 3 + j] = s;
     }
+  if (Vout)
+    for (int k = 0; k < 9; ++k) Vout[k] = V[k];
+  if (s2out)
+    for (int k = 0; k < 3; ++k) s2out[k] = fmax(A[k * 3 + k], 1e-300);
+}
+
+// svd_reg of the pose regressor (feature/direct_feature_matching.py:81-86: u, s, v = torch.svd(R); R <- u v^T) as one
+// kernel without the host synchronisation torch.svd's error check costs a training step.  One thread per 3x3 matrix,
+// double precision.  aux [n][21] = U (9) | V (9) | s (3) for the backward.
+__global__ void k_polar3x3_fwd(const float* __restrict__ A, int n, float* __restrict__ Q, double* __restrict__ aux) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double R[9], Qd[9], V[9], s2[3];
+  for (int k = 0; k < 9; ++k) R[k] = A[(size_t)i * 9 + k];
+  polar_orthogonal(R, Qd, V, s2);
+  for (int k = 0; k < 9; ++k) Q[(size_t)i * 9 + k] = (float)Qd[k];
+  if (aux) {
+    double* a = aux + (size_t)i * 21;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {   // U = R V diag(1/s)
+        double u = 0;
+        for (int k = 0; k < 3; ++k) u += R[r * 3 + k] * V[k * 3 + c];
+        a[r * 3 + c] = u / sqrt(s2[c]);
+      }
+    for (int k = 0; k < 9; ++k) a[9 + k] = V[k];
+    for (int k = 0; k < 3; ++k) a[18 + k] = sqrt(s2[k]);
+  }
+}
+
+// Adjoint of R -> U V^T: with M = U^T G V, dR = U [ (M - M^T)_ij / (s_i + s_j) ] V^T  (the differential of the orthogonal
+// polar factor is dQ = U [ (X - X^T)_ij / (s_i + s_j) ] V^T, X = U^T dR V).
+__global__ void k_polar3x3_bwd(const double* __restrict__ aux, const float* __restrict__ G, int n, float* __restrict__ dA) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* a = aux + (size_t)i * 21;
+  const double *U = a, *V = a + 9, *s = a + 18;
+  double g[9], T[9], M[9], N[9];
+  for (int k = 0; k < 9; ++k) g[k] = G[(size_t)i * 9 + k];
+  for (int r = 0; r < 3; ++r)       // T = U^T G
+    for (int c = 0; c < 3; ++c) T[r * 3 + c] = U[0 * 3 + r] * g[0 * 3 + c] + U[1 * 3 + r] * g[1 * 3 + c] + U[2 * 3 + r] * g[2 * 3 + c];
+  for (int r = 0; r < 3; ++r)       // M = T V
+    for (int c = 0; c < 3; ++c) M[r * 3 + c] = T[r * 3 + 0] * V[0 * 3 + c] + T[r * 3 + 1] * V[1 * 3 + c] + T[r * 3 + 2] * V[2 * 3 + c];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) N[r * 3 + c] = (M[r * 3 + c] - M[c * 3 + r]) / (s[r] + s[c]);
+  for (int r = 0; r < 3; ++r)       // T = U N
+    for (int c = 0; c < 3; ++c) T[r * 3 + c] = U[r * 3 + 0] * N[0 * 3 + c] + U[r * 3 + 1] * N[1 * 3 + c] + U[r * 3 + 2] * N[2 * 3 + c];
+  for (int r = 0; r < 3; ++r)       // dA = T V^T
+    for (int c = 0; c < 3; ++c)
+      dA[(size_t)i * 9 + r * 3 + c] = (float)(T[r * 3 + 0] * V[c * 3 + 0] + T[r * 3 + 1] * V[c * 3 + 1] + T[r * 3 + 2] * V[c * 3 + 2]);
 }
 
 // pytorch3d 0.3.0 transforms.matrix_to_quaternion (requirements.txt:76; not vendored): w = sqrt(max(0, 1 + m00 + m11 +
@@ -235,6 +285,22 @@ extern "C" int dfb_pose_error(const float* pred, const float* gt, int n, int use
   DFB_REQUIRE(pred && gt && out && n >= 0, DFB_ERR_INVALID, "dfb_pose_error: bad arguments");
   if (n == 0) return DFB_OK;
   k_pose_error<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(pred, gt, n, use_svd, out, pred_fixed);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+extern "C" int dfb_polar3x3_fwd(const float* A, int n, float* Q, double* aux, void* stream) {
+  DFB_REQUIRE(A && Q && n >= 0, DFB_ERR_INVALID, "dfb_polar3x3_fwd: bad arguments");
+  if (n == 0) return DFB_OK;
+  k_polar3x3_fwd<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(A, n, Q, aux);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+extern "C" int dfb_polar3x3_bwd(const double* aux, const float* G, int n, float* dA, void* stream) {
+  DFB_REQUIRE(aux && G && dA && n >= 0, DFB_ERR_INVALID, "dfb_polar3x3_bwd: bad arguments");
+  if (n == 0) return DFB_OK;
+  k_polar3x3_bwd<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(aux, G, n, dA);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }

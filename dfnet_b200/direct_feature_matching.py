@@ -14,7 +14,7 @@ import torch.distributed as dist
 
 from . import parallel
 from .dfnet import feature_loss, preprocess_features_for_loss  # noqa: F401  (same import surface as the reference)
-from .misc import PoseLoss, img2mse, mse2psnr, upsample_bicubic
+from .misc import PoseLoss, img2mse, mse2psnr, polar_orthogonalize, upsample_bicubic
 from .rendering import render
 
 _MEAN = (0.485, 0.456, 0.406)
@@ -42,10 +42,7 @@ def inference_pose_regression(args, data, device, model, retFeature=False, isSin
         return features, predict_pose
     pose = predict_pose.reshape(inputs.shape[0], 3, 4)
     if getattr(args, "svd_reg", False):
-        R_torch = pose[:, :3, :3].clone()
-        u, s, v = torch.svd(R_torch)
-        Rs = torch.matmul(u, v.transpose(-2, -1))
-        pose[:, :3, :3] = Rs
+        pose[:, :3, :3] = polar_orthogonalize(pose[:, :3, :3].clone())   # u v^T of torch.svd, without its host sync
     return features, pose
 
 

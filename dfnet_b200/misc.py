@@ -156,6 +156,37 @@ def upsample_bilinear_ac(x, size):
     return out
 
 
+class _PolarFn(torch.autograd.Function):
+    """R [B,3,3] -> U V^T of its SVD (what `u, s, v = torch.svd(R); u @ v.transpose(-2, -1)` computes, reference
+    feature/direct_feature_matching.py:81-86) with the adjoint, both as one tiny kernel and without torch.svd's host-side
+    status check, which drains the GPU in the middle of every training step."""
+
+    @staticmethod
+    def forward(ctx, R):
+        A = R.detach().float().contiguous()
+        n = A.shape[0]
+        Q = torch.empty_like(A)
+        aux = torch.empty(n, 21, dtype=torch.float64, device=A.device)
+        check(lib.dfb_polar3x3_fwd(_p(A), n, _p(Q), _p(aux), _stream()))
+        ctx.save_for_backward(aux)
+        return Q
+
+    @staticmethod
+    def backward(ctx, g):
+        aux, = ctx.saved_tensors
+        G = g.float().contiguous()
+        dA = torch.empty_like(G)
+        check(lib.dfb_polar3x3_bwd(_p(aux), _p(G), G.shape[0], _p(dA), _stream()))
+        return dA
+
+
+def polar_orthogonalize(R):
+    """Nearest rotation-like matrix U V^T of every 3x3 matrix of R [B,3,3] (CUDA), differentiable."""
+    if not R.is_cuda:
+        raise _lib.DfbError("polar_orthogonalize input must be a CUDA tensor: the dfnet_b200 path has no CPU fallback")
+    return _PolarFn.apply(R)
+
+
 def pose_errors(pred, gt, use_svd=True, return_fixed=False):
     """dfb_pose_error: pred, gt [n,12] (or [n,3,4]) CUDA tensors -> [n,2] = (translation error, rotation error in
     degrees); with return_fixed also the predicted poses with U V^T rotations."""

@@ -410,6 +410,11 @@ int dfb_resize_area(const float* src, int H, int W, int C, int h, int w, float* 
  * in degrees via quaternions (pytorch3d 0.3.0 matrix_to_quaternion)}; pred_fixed [n,12] (nullable): the predicted
  * pose with the orthogonalised rotation. */
 int dfb_pose_error(const float* pred, const float* gt, int n, int use_svd, float* out, float* pred_fixed, void* stream);
+/* svd_reg of the pose regressor (feature/direct_feature_matching.py:81-86: u, s, v = torch.svd(R); R <- u v^T): the
+ * orthogonal polar factor of n 3x3 matrices A [n,9] -> Q [n,9] on the device (no host synchronisation; torch.svd checks
+ * its status on the host), and its adjoint G [n,9] -> dA [n,9].  aux [n,21] doubles = U | V | s, written by the forward. */
+int dfb_polar3x3_fwd(const float* A, int n, float* Q, double* aux, void* stream);
+int dfb_polar3x3_bwd(const double* aux, const float* G, int n, float* dA, void* stream);
 
 #ifdef __cplusplus
 }

@@ -433,3 +433,31 @@ def test_dfnet_feature_training_step_reduces_the_loss():
     for m in net.modules():
         if isinstance(m, torch.nn.BatchNorm2d):
             assert int(m.num_batches_tracked) > 0          # train-mode BatchNorm kept its running statistics
+
+
+def test_polar_orthogonalize_vs_torch_svd():
+    """svd_reg of the pose regressor (reference feature/direct_feature_matching.py:81-86): the device kernel against
+    u @ v^T of torch.svd, forward and the gradient through it (float64 autograd), on near-rotations (what the regressor
+    predicts), scaled / sheared matrices and a reflection."""
+    from dfnet_b200.misc import polar_orthogonalize
+    torch.manual_seed(0)
+    n = 64
+    q, _ = torch.linalg.qr(torch.randn(n, 3, 3, dtype=torch.float64))
+    A = q + 0.2 * torch.randn(n, 3, 3, dtype=torch.float64)
+    A[:8] *= torch.linspace(0.05, 20.0, 8, dtype=torch.float64)[:, None, None]
+    A[8] = torch.diag(torch.tensor([1.0, 1.0, -1.0], dtype=torch.float64)) + 0.05 * torch.randn(3, 3, dtype=torch.float64)
+    G = torch.randn(n, 3, 3, dtype=torch.float64)
+    a64 = A.clone().requires_grad_(True)
+    u, s, v = torch.svd(a64)
+    want = u @ v.transpose(-2, -1)
+    (want * G).sum().backward()
+    a32 = A.float().to(dev()).requires_grad_(True)
+    got = polar_orthogonalize(a32)
+    (got * G.float().to(dev())).sum().backward()
+    torch.cuda.synchronize()
+    assert float((got.detach().cpu().double() - want.detach()).abs().max()) < 2e-6
+    eye = got.detach().cpu().double() @ got.detach().cpu().double().transpose(-2, -1)
+    assert float((eye - torch.eye(3, dtype=torch.float64)).abs().max()) < 2e-6
+    gw = a64.grad
+    err = float((a32.grad.cpu().double() - gw).abs().max()) / float(gw.abs().max())
+    assert err < 1e-5, err
