@@ -20,7 +20,7 @@ SYMBOLS = [
     "dfb_conv_create_ex", "dfb_conv_fwd_ex", "dfb_conv_wgrad", "dfb_dfnet_load_ex", "dfb_dfnet_bn_batch_stats", "dfb_dfnet_tape_bytes", "dfb_debug_dfnet_tape_layout",
     "dfb_dfnet_bwd_workspace_bytes", "dfb_dfnet_bwd", "dfb_cosine_loss_bwd", "dfb_mse_bwd", "dfb_resize_bicubic_bwd",
     "dfb_resize_bilinear_ac_bwd", "dfb_dfnet_bwd_bucket_event", "dfb_luma_hist", "dfb_resize_area", "dfb_pose_error", "dfb_polar3x3_fwd", "dfb_polar3x3_bwd", "dfb_debug_conv_prof",
-    "dfb_conv_update", "dfb_embed_xyz16", "dfb_rows_expand16", "dfb_rows_reduce_bf16", "dfb_nerf_heads_fwd", "dfb_nerf_heads_bwd",
+    "dfb_conv_update", "dfb_conv_pack_begin", "dfb_conv_pack_end", "dfb_embed_xyz16", "dfb_rows_expand16", "dfb_rows_reduce_bf16", "dfb_nerf_heads_fwd", "dfb_nerf_heads_bwd",
     "dfb_raw2outputs_bwd", "dfb_cast_f16_bf16", "dfb_render_poses_fwd",
 ]
 
@@ -119,6 +119,8 @@ def _load():
     lib.dfb_luma_hist.argtypes = [vp, i32, i32, i32, i32, vp, vp, C.c_size_t, vp]
     lib.dfb_resize_area.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
     lib.dfb_pose_error.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+    lib.dfb_conv_pack_begin.argtypes = []
+    lib.dfb_conv_pack_end.argtypes = [vp]
     lib.dfb_polar3x3_fwd.argtypes = [vp, i32, vp, vp, vp]
     lib.dfb_polar3x3_bwd.argtypes = [vp, vp, i32, vp, vp]
     lib.dfb_cosine_loss_bwd.argtypes = [vp, vp, i32, i64, i32, f32, vp, vp, vp, C.c_size_t, vp]

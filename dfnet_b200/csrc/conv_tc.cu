@@ -576,11 +576,19 @@ int dfb_conv_update_impl(DfbConv* c, const float* weight, const float* bias, con
 
 // Bracket for callers that (re)pack many convolutions in a row on the legacy default stream (dfb_dfnet_load_ex).
 void dfb_conv_pack_batch_begin() { conv::g_pack.open = true; }
-int dfb_conv_pack_batch_flush(bool discard) {
+int dfb_conv_pack_batch_flush(bool discard, void* stream) {
   conv::g_pack.open = false;
   if (discard) conv::g_pack.args.n = 0;   // a failed load may have destroyed handles the pending requests point to
-  return conv::pack_launch(nullptr);
+  return conv::pack_launch((cudaStream_t)stream);
 }
+// ABI form of the bracket (nerf_train.py re-loads ~60 one-by-one convolutions after every optimizer step): between
+// dfb_conv_pack_begin and dfb_conv_pack_end every dfb_conv_update of device-resident tensors is queued and goes out as one
+// launch on `stream`; the sources must stay unchanged until then.
+extern "C" int dfb_conv_pack_begin() {
+  dfb_conv_pack_batch_begin();
+  return DFB_OK;
+}
+extern "C" int dfb_conv_pack_end(void* stream) { return dfb_conv_pack_batch_flush(false, stream); }
 // cta_group used by the convolution kernel.  2 (default): CTA pairs work on two neighbouring M tiles with one weight stream
 // and one MMA instruction for both SMs; DFB_CONV_CTA_GROUP=1 selects the 1-CTA kernel (also used for single-tile launches).
 // Read per call so that tests can exercise both variants in one process; both weight images are always packed.

@@ -18,7 +18,7 @@ int64_t dfb_conv_rounds(const DfbConv* c, int B, int H, int W);
 int dfb_conv_update_impl(DfbConv* c, const float* weight, const float* bias, const float* bn_scale, const float* bn_shift,
                          void* stream);
 void dfb_conv_pack_batch_begin();
-int dfb_conv_pack_batch_flush(bool discard);
+int dfb_conv_pack_batch_flush(bool discard, void* stream = nullptr);
 int dfb_conv_run(DfbConv* c, const void* in_nhwc16, int B, int H, int W, int relu, void* out_nhwc16, void* tap_nhwc16,
                  float* out_nchw32, const void* mask_nhwc16, const void* addend_nhwc16, void* stream);
 

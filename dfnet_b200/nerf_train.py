@@ -107,6 +107,16 @@ class NetTrainer:
         v = [(p.data_ptr(), p._version) for p in n.parameters()]
         if v == self._versions:
             return
+        # every layer's (re)packing request of this load goes out as ONE launch (the staging tensors stay untouched until
+        # dfb_conv_pack_end); launched one by one they were 116 launches per training step
+        check(lib.dfb_conv_pack_begin())
+        try:
+            self._load_layers(n)
+        finally:
+            check(lib.dfb_conv_pack_end(_st()))
+        self._versions = v
+
+    def _load_layers(self, n):
         W = self.W
         for i in range(8):
             lin = getattr(n, f"xyz_encoding_{i + 1}")[0]
@@ -129,7 +139,6 @@ class NetTrainer:
                 self.L[f"t{k}"].load(te[idx].weight, te[idx].bias)
             self.L["th"].load(torch.cat([n.transient_rgb[0].weight, n.transient_sigma[0].weight, n.transient_beta[0].weight], 0),
                               torch.cat([n.transient_rgb[0].bias, n.transient_sigma[0].bias, n.transient_beta[0].bias], 0))
-        self._versions = v
 
     # ---- buffers ----------------------------------------------------------------------------------------------------
     def begin(self):

@@ -376,6 +376,10 @@ int dfb_debug_umma_gemm_mn(const float* A, const float* B, int N, int K, int fmt
  * ---------------------------------------------------------------------------------------------- */
 /* Re-pack an existing convolution handle from new fp32 parameters (after an optimizer step). */
 int dfb_conv_update(DfbConv* conv, const float* weight, const float* bias, const float* bn_scale, const float* bn_shift, void* stream);
+/* Bracket for re-loading many convolutions in a row: between _begin and _end every dfb_conv_update of device-resident
+ * tensors is queued and all of them go out as ONE packing launch on `stream` (the sources must stay unchanged until then). */
+int dfb_conv_pack_begin(void);
+int dfb_conv_pack_end(void* stream);
 /* pts = o + d*z, positional encoding with L bands (nerfw.py:105-133) -> fp16 [N*S, ld], columns >= 3+6L zero.
  * rays: [N, ray_stride] with o at 0..2 and d at 3..5. */
 int dfb_embed_xyz16(const float* rays, int ray_stride, const float* z, int64_t N, int S, int L, int ld, void* out, void* stream);

@@ -59,6 +59,27 @@ elif what == "dfnet":
     def step(i):
         feats, _ = net(x, return_feature=True, isSingleStream=False, return_pose=False, upsampleH=480, upsampleW=640)
         return feature_loss(feats[1][0, 0], feats[0][0, 0])
+elif what == "nerf":
+    from dfnet_b200 import nerf_train
+    from dfnet_b200.losses import loss_dict
+    tm = [m.to(dev) for m in nerfw.make_synthetic_nerf(D=8, W=128, fine=True)]
+    tp = [p for m in tm for p in m.parameters()]
+    for p in tp:
+        p.requires_grad_(True)
+    nargs = types.SimpleNamespace(chunk=32768, lrate=5e-4, lrate_decay=250)
+    nopt = torch.optim.Adam(tp, lr=nargs.lrate, betas=(0.9, 0.999))
+    nkw = dict(network_query_fn=None, perturb=1.0, N_importance=64, network_fine=tm[1], N_samples=64, network_fn=tm[0],
+               use_viewdirs=True, white_bkgd=False, raw_noise_std=0.0, embedding_a=tm[2], embedding_t=tm[3], test_time=False,
+               ndc=False, lindisp=False)
+    nimg = torch.rand(3, 120, 160).pin_memory()
+    nloss = loss_dict["nerfw"](coef=1)
+    npose = torch.tensor([1., 0, 0, 0.1, 0, 1, 0, -0.05, 0, 0, 1, 2.0])
+    nhist = torch.tensor([[5., 10, 20, 30, 15, 10, 5, 3, 1, 1]])
+
+    def step(i):
+        loss, psnr = nerf_train.train_on_batch_nerfw(nargs, nimg, npose, nhist, 120, 160, 146.0, 1536, nopt, nloss, i, nkw,
+                                                     near=0.0, far=2.5)
+        return float(loss)
 else:
     raise SystemExit("unknown workload")
 
