@@ -152,6 +152,9 @@ int launch_composite_partials(const float* part, int part_k, int64_t n_rays, int
 bool tc_supported(const DfbNerf* nerf, int which, int mode);
 // 3-D tensor map over a packed image of 16 KB chunks: [n][64][128 x u16], one box = one chunk (2-SM TMA weight loads)
 int make_weight_tmap(void* base, size_t bytes, CUtensorMap* out);
+// 5-D tensor map over an NHWC 16-bit tensor seen as [B][C/8 panels][H][W][8 channels]; one box = npanels x PH x PW pixels
+// x 8 channels = the shared-memory image [panel][row][col][16 B] (conv_tc.cu); out-of-bounds coordinates are zero-filled
+int make_patch_tmap(const void* in, int B, int H, int W, int Cpad, int PH, int PW, CUtensorMap* out, int npanels = 8);
 // Networks narrower than 256 run on the 256-wide tcgen05 kernels EXACTLY, embedded with zero weights / zero biases
 // (a ReLU unit with zero input weights and bias stays at 0 and feeds nothing): tc_pad_params returns the state dict
 // of the equivalent 8x256 network (state-dict order, hidden units 0..W-1 / 0..W/2-1 live).

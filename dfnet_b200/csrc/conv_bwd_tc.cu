@@ -38,13 +38,17 @@ __device__ __forceinline__ uint16_t cvt16(float v, int fmt) {
 // weight-gradient kernel
 // ------------------------------------------------------------------------------------------
 constexpr int kTH = 16, kTW = 8;   // pixel tile = 128 contraction steps
-constexpr int kStages = 2;
-constexpr int kThreads = 160;      // warps 0-3: tile loaders, then epilogue; warp 4: MMA issuer
+constexpr int kMaxStages = 3;
+constexpr int kThreads = 160;      // warps 0-3: epilogue (warp 0 first produces the tiles by TMA); warp 4: MMA issuer
 constexpr uint32_t kGBytes = 16u * kTH * kTW * 16u;  // gO tile: 16 channel panels x 128 pixels x 16 B
 
-enum Bar { FULL = 0, EMPTY = 2, DONE = 4, N_BARS = 5 };
+enum Bar { FULL = 0, EMPTY = 3, DONE = 6, N_BARS = 7 };
 
 struct WgArgs {
+  // 5-D tensor maps over gO and X (NHWC seen as [B][C/8][H][W][8]): one box = the tile's shared-memory image
+  alignas(64) CUtensorMap tmap_g;
+  alignas(64) CUtensorMap tmap_x;
+  int n_stages;        // tile ring depth (3 where shared memory allows, else 2)
   const uint16_t* gO;  // NHWC [B,H,W,Cout]
   const uint16_t* X;   // NHWC [B,H,W,Cin_pad]
   float* dW;           // [Cout][Cin][KH][KW], accumulated with atomics (zeroed by the caller)
@@ -69,6 +73,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // D[co][kx*NB + ci] accumulates in TMEM over all the CTA's tiles; A = gO tile, B = X patch shifted by kx.
 __global__ void __launch_bounds__(kThreads, 1) k_conv_wgrad(const __grid_constant__ WgArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  const int kStages = a.n_stages;
   const uint32_t sG = smem_u32(smem);
   const uint32_t sX = sG + kStages * kGBytes;
   const uint32_t sBar = sX + kStages * a.x_bytes;
@@ -85,7 +90,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_wgrad(const __grid_constan
   if (t0 >= t1) return;  // uniform per CTA
 
   if (tid == 0) {
-    for (int i = 0; i < kStages; ++i) mbar_init(bar(FULL + i), 128), mbar_init(bar(EMPTY + i), 1);
+    for (int i = 0; i < kMaxStages; ++i) mbar_init(bar(FULL + i), 1), mbar_init(bar(EMPTY + i), 1);
     mbar_init(bar(DONE), 1);
     fence_barrier_init();
   }
@@ -99,50 +104,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_wgrad(const __grid_constan
   const uint32_t xpanel = (uint32_t)kTH * a.PW * 16u;
 
   if (warp < 4) {
-    const int cpo = a.Cout / 8, cpp = a.Cin_pad / 8;
-    uint32_t seq = 0;
-    for (int t = t0; t < t1; ++t, ++seq) {
-      const uint32_t st = seq % kStages, ph = (seq / kStages) & 1;
-      mbar_wait(bar(EMPTY + st), ph ^ 1, a.error_flag);
-      const int b = t / tiles_img, ti = t % tiles_img;
-      const int y0 = (ti / a.tiles_x) * kTH, x0 = (ti % a.tiles_x) * kTW;
-      // gO tile: 16 consecutive threads read the 256 contiguous bytes of one pixel's 128 channels
-      {
-        const uint16_t* base = a.gO + (int64_t)b * a.H * a.W * a.Cout;
-        const uint32_t dst0 = sG + st * kGBytes;
-        const int panel = tid & 15, c8 = cob * 16 + panel;
-        for (int pix = tid >> 4; pix < kTH * kTW; pix += 8) {
-          const int y = y0 + (pix >> 3), x = x0 + (pix & 7);
-          const bool ok = c8 < cpo && y < a.H && x < a.W;
-          const uint16_t* src = ok ? base + ((int64_t)y * a.W + x) * a.Cout + c8 * 8 : a.gO;
-          cp_async16(dst0 + panel * 2048u + pix * 16u, src, ok ? 16u : 0u);
+    if (warp == 0) {
+      // ===== tile producer: two TMA boxes per tile (gO tile, X patch of filter row ky incl. halo; out-of-image pixels and
+      // channels past the tensor are zero-filled by the TMA unit).  The first version gathered both with 16-byte cp.async
+      // from 128 threads (~1 000 address-arithmetic instructions per thread and tile, two stages): the weight-gradient
+      // kernels ran at ~200 TFLOP/s, loader-bound.
+      uint32_t seq = 0;
+      for (int t = t0; t < t1; ++t, ++seq) {
+        const uint32_t st = seq % kStages, ph = (seq / kStages) & 1;
+        mbar_wait(bar(EMPTY + st), ph ^ 1, a.error_flag);
+        if (elect_one()) {
+          const int b = t / tiles_img, ti = t % tiles_img;
+          const int y0 = (ti / a.tiles_x) * kTH, x0 = (ti % a.tiles_x) * kTW;
+          mbar_expect_tx(bar(FULL + st), kGBytes + a.x_bytes);
+          tma_load_5d<1>(sG + st * kGBytes, &a.tmap_g, 0, x0, y0, cob * 16, b, bar(FULL + st));
+          tma_load_5d<1>(sX + st * a.x_bytes, &a.tmap_x, 0, x0 - a.pad, y0 + ky - a.pad, cib * npan, b, bar(FULL + st));
         }
-      }
-      // X patch for filter row ky: rows y0+ky-pad .. +15, cols x0-pad .. x0+7+pad
-      {
-        const uint16_t* base = a.X + (int64_t)b * a.H * a.W * a.Cin_pad;
-        const uint32_t dst0 = sX + st * a.x_bytes;
-        const int n_ent = kTH * a.PW;
-        for (int q = tid; q < n_ent * npan; q += 128) {
-          const int panel = q % npan, e = q / npan;
-          const int pr = e / a.PW, pc = e - pr * a.PW;
-          const int yy = y0 + pr + ky - a.pad, xx = x0 + pc - a.pad;
-          const int c8 = cib * npan + panel;
-          const bool ok = c8 < cpp && yy >= 0 && yy < a.H && xx >= 0 && xx < a.W;
-          const uint16_t* src = ok ? base + ((int64_t)yy * a.W + xx) * a.Cin_pad + c8 * 8 : a.X;
-          cp_async16(dst0 + panel * xpanel + e * 16u, src, ok ? 16u : 0u);
-        }
-      }
-      cp_async_commit();
-      if (seq >= 1) {
-        cp_async_wait<1>();
-        fence_proxy_async();
-        mbar_arrive(bar(FULL + (seq - 1) % kStages));
+        __syncwarp();
       }
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    mbar_arrive(bar(FULL + (seq - 1) % kStages));
 
     // ===== epilogue: thread = output channel; columns = (kx, ci) ==================================
     mbar_wait(bar(DONE), 0, a.error_flag);
@@ -331,8 +311,16 @@ extern "C" int dfb_conv_wgrad(const void* gO, const void* X, int B, int H, int W
   a.PW = wg::kTW + 2 * a.pad;
   a.x_bytes = (uint32_t)(a.NB / 8) * wg::kTH * a.PW * 16u;
   a.fmt = fmt, a.error_flag = error_flag;
-  const size_t smem = (size_t)wg::kStages * (wg::kGBytes + a.x_bytes) + 256;
+  a.n_stages = (size_t)wg::kMaxStages * (wg::kGBytes + a.x_bytes) + 256 <= 232448 ? wg::kMaxStages : 2;
+  const size_t smem = (size_t)a.n_stages * (wg::kGBytes + a.x_bytes) + 256;
   DFB_REQUIRE(smem <= 232448, DFB_ERR_UNSUPPORTED, "shared memory budget exceeded");
+  DFB_REQUIRE(Cout % 8 == 0, DFB_ERR_INVALID, "dfb_conv_wgrad: Cout must be a multiple of 8");
+  {
+    int rc = make_patch_tmap(gO, B, H, W, Cout, wg::kTH, wg::kTW, &a.tmap_g, 16);
+    if (rc) return rc;
+    rc = make_patch_tmap(X, B, H, W, Cin_pad, wg::kTH, a.PW, &a.tmap_x, a.NB / 8);
+    if (rc) return rc;
+  }
   DFB_CHECK_CUDA(cudaMemsetAsync(dW, 0, (size_t)Cout * Cin * KH * KH * 4, st));
   DFB_CHECK_CUDA(cudaFuncSetAttribute(wg::k_conv_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   wg::k_conv_wgrad<<<units * a.n_split, wg::kThreads, smem, st>>>(a);

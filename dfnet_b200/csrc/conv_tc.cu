@@ -681,7 +681,7 @@ extern "C" int dfb_conv_fwd(DfbConv* c, const void* in_nhwc16, int B, int H, int
 }
 
 // 5-D tensor map over the NHWC 16-bit input for the patch loads of k_conv_tc (see ConvArgs::tmap_in).
-static int make_patch_tmap(const void* in, int B, int H, int W, int Cpad, int PH, int PW, CUtensorMap* out) {
+int dfb::make_patch_tmap(const void* in, int B, int H, int W, int Cpad, int PH, int PW, CUtensorMap* out, int npanels) {
   static PFN_cuTensorMapEncodeTiled encode = nullptr;
   if (!encode) {
     void* fn = nullptr;
@@ -693,7 +693,7 @@ static int make_patch_tmap(const void* in, int B, int H, int W, int Cpad, int PH
   DFB_REQUIRE(((uintptr_t)in & 15) == 0 && Cpad % 8 == 0, DFB_ERR_INVALID, "conv input must be 16-byte aligned NHWC with C % 8 == 0");
   const cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cpad / 8), (cuuint64_t)B};
   const cuuint64_t strides[4] = {(cuuint64_t)Cpad * 2, (cuuint64_t)W * Cpad * 2, 16, (cuuint64_t)H * W * Cpad * 2};
-  const cuuint32_t box[5] = {8, (cuuint32_t)PW, (cuuint32_t)PH, 8, 1};
+  const cuuint32_t box[5] = {8, (cuuint32_t)PW, (cuuint32_t)PH, (cuuint32_t)npanels, 1};
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, const_cast<void*>(in), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
