@@ -138,8 +138,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_wgrad(const __grid_constan
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int ci = cib * a.NB + c0 + j;
-            if (c0 + j < a.NB && ci < a.Cin)
-              atomicAdd(a.dW + (((int64_t)co * a.Cin + ci) * a.KH + ky) * a.KW + kx, __uint_as_float(v[j]));
+            if (c0 + j < a.NB && ci < a.Cin) {
+              float* o = a.dW + (((int64_t)co * a.Cin + ci) * a.KH + ky) * a.KW + kx;
+              if (a.n_split > 1) atomicAdd(o, __uint_as_float(v[j]));
+              else *o = __uint_as_float(v[j]);   // this CTA covered every pixel tile: a plain store, no zero-fill needed
+            }
           }
         }
       }
@@ -307,6 +310,10 @@ extern "C" int dfb_conv_wgrad(const void* gO, const void* X, int B, int H, int W
   a.tiles_x = (W + wg::kTW - 1) / wg::kTW, a.tiles_y = (H + wg::kTH - 1) / wg::kTH;
   a.n_tiles = a.tiles_x * a.tiles_y * B;
   const int units = a.n_cib * a.n_cob * KH;
+  // Pixel tiles are split over as many CTAs as the GPU has SMs (fp32 atomics at the end; a CTA that covers every tile
+  // stores directly).  Measured and dropped: running the deep layers unsplit (conv4_x / conv5_x of a 480x640 image have 40 /
+  // 10 tiles) - the MN-major MMAs of a tile take ~6 000 cycles, not the nominal 1 536 (the 2 KB panel stride of the
+  // no-swizzle MN-major operands maps all 16 panels onto the same banks), so fewer CTAs lose more than the atomics cost.
   a.n_split = std::max(1, std::min(a.n_tiles, sms / units));
   a.PW = wg::kTW + 2 * a.pad;
   a.x_bytes = (uint32_t)(a.NB / 8) * wg::kTH * a.PW * 16u;
@@ -321,7 +328,7 @@ extern "C" int dfb_conv_wgrad(const void* gO, const void* X, int B, int H, int W
     rc = make_patch_tmap(X, B, H, W, Cin_pad, wg::kTH, a.PW, &a.tmap_x, a.NB / 8);
     if (rc) return rc;
   }
-  DFB_CHECK_CUDA(cudaMemsetAsync(dW, 0, (size_t)Cout * Cin * KH * KH * 4, st));
+  if (a.n_split > 1) DFB_CHECK_CUDA(cudaMemsetAsync(dW, 0, (size_t)Cout * Cin * KH * KH * 4, st));
   DFB_CHECK_CUDA(cudaFuncSetAttribute(wg::k_conv_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   wg::k_conv_wgrad<<<units * a.n_split, wg::kThreads, smem, st>>>(a);
   DFB_LAUNCH_CHECK();
