@@ -17,7 +17,7 @@ SYMBOLS = [
     "dfb_launch_count", "dfb_profile_enable", "dfb_profile_read", "dfb_debug_umma_gemm", "dfb_debug_umma_gemm_mn", "dfb_debug_tc_prof", "dfb_debug_tcb_prof", "dfb_debug_bwd_masks", "dfb_debug_umma_rate", "dfb_debug_tmem_rate", "dfb_debug_tmem_rate_mma", "dfb_conv_create", "dfb_conv_destroy", "dfb_conv_fwd",
     "dfb_dfnet_create", "dfb_dfnet_destroy", "dfb_dfnet_load", "dfb_dfnet_workspace_bytes", "dfb_dfnet_fwd",
     "dfb_cosine_loss", "dfb_triplet_loss", "dfb_triplet_loss_bwd", "dfb_mse", "dfb_resize_bicubic", "dfb_resize_bilinear_ac",
-    "dfb_conv_create_ex", "dfb_conv_fwd_ex", "dfb_conv_wgrad", "dfb_dfnet_load_ex", "dfb_dfnet_bn_batch_stats", "dfb_dfnet_tape_bytes", "dfb_debug_dfnet_tape_layout",
+    "dfb_conv_create_ex", "dfb_conv_fwd_ex", "dfb_conv_fwd_ex2", "dfb_conv_wgrad", "dfb_conv_wgrad_acc", "dfb_dfnet_load_ex", "dfb_dfnet_bn_batch_stats", "dfb_dfnet_tape_bytes", "dfb_debug_dfnet_tape_layout",
     "dfb_dfnet_bwd_workspace_bytes", "dfb_dfnet_bwd", "dfb_cosine_loss_bwd", "dfb_mse_bwd", "dfb_resize_bicubic_bwd",
     "dfb_resize_bilinear_ac_bwd", "dfb_dfnet_bwd_bucket_event", "dfb_luma_hist", "dfb_resize_area", "dfb_pose_error", "dfb_polar3x3_fwd", "dfb_polar3x3_bwd", "dfb_debug_conv_prof",
     "dfb_conv_update", "dfb_conv_pack_begin", "dfb_conv_pack_end", "dfb_embed_xyz16", "dfb_rows_expand16", "dfb_rows_reduce_bf16", "dfb_nerf_heads_fwd", "dfb_nerf_heads_bwd",
@@ -99,6 +99,8 @@ def _load():
     lib.dfb_conv_create_ex.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, i32, i32, C.POINTER(vp)]
     lib.dfb_conv_fwd_ex.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.dfb_conv_wgrad.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp]
+    lib.dfb_conv_wgrad_acc.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp]
+    lib.dfb_conv_fwd_ex2.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.dfb_dfnet_load_ex.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i32, f32, C.c_uint32]
     lib.dfb_dfnet_bn_batch_stats.argtypes = [vp, vp, vp]
     lib.dfb_dfnet_tape_bytes.argtypes = [vp, i32, i32, i32, i32, i32, C.POINTER(C.c_size_t)]

@@ -49,6 +49,7 @@ struct WgArgs {
   alignas(64) CUtensorMap tmap_g;
   alignas(64) CUtensorMap tmap_x;
   int n_stages;        // tile ring depth (3 where shared memory allows, else 2)
+  int atomic;          // 1: the epilogue adds to dW (pixel tiles split over CTAs, or the caller accumulates); 0: it stores
   const uint16_t* gO;  // NHWC [B,H,W,Cout]
   const uint16_t* X;   // NHWC [B,H,W,Cin_pad]
   float* dW;           // [Cout][Cin][KH][KW], accumulated with atomics (zeroed by the caller)
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_wgrad(const __grid_constan
             const int ci = cib * a.NB + c0 + j;
             if (c0 + j < a.NB && ci < a.Cin) {
               float* o = a.dW + (((int64_t)co * a.Cin + ci) * a.KH + ky) * a.KW + kx;
-              if (a.n_split > 1) atomicAdd(o, __uint_as_float(v[j]));
+              if (a.atomic) atomicAdd(o, __uint_as_float(v[j]));
               else *o = __uint_as_float(v[j]);   // this CTA covered every pixel tile: a plain store, no zero-fill needed
             }
           }
@@ -284,9 +285,23 @@ using namespace dfb;
 
 
 // dW [Cout,Cin,KH,KW] (+ optional dB [Cout]) from gO NHWC [B,H,W,Cout] and X NHWC [B,H,W,Cin_pad] (16-bit, fmt 0 f16 / 1 bf16).
-// Both outputs are overwritten.
+// Both outputs are overwritten (accumulate != 0: added to, the caller zeroed them - one memset for a whole flat gradient
+// buffer instead of two per layer).
+static int conv_wgrad_impl(const void* gO, const void* X, int B, int H, int W, int Cin, int Cin_pad, int Cout, int KH, int fmt,
+                           float* dW, float* dB, void* stream, int accumulate);
+
 extern "C" int dfb_conv_wgrad(const void* gO, const void* X, int B, int H, int W, int Cin, int Cin_pad, int Cout, int KH, int fmt,
                               float* dW, float* dB, void* stream) {
+  return conv_wgrad_impl(gO, X, B, H, W, Cin, Cin_pad, Cout, KH, fmt, dW, dB, stream, 0);
+}
+
+extern "C" int dfb_conv_wgrad_acc(const void* gO, const void* X, int B, int H, int W, int Cin, int Cin_pad, int Cout, int KH, int fmt,
+                                  float* dW, float* dB, void* stream) {
+  return conv_wgrad_impl(gO, X, B, H, W, Cin, Cin_pad, Cout, KH, fmt, dW, dB, stream, 1);
+}
+
+static int conv_wgrad_impl(const void* gO, const void* X, int B, int H, int W, int Cin, int Cin_pad, int Cout, int KH, int fmt,
+                           float* dW, float* dB, void* stream, int accumulate) {
   DFB_REQUIRE(gO && X && dW, DFB_ERR_INVALID, "dfb_conv_wgrad: null argument");
   DFB_REQUIRE(B >= 1 && H >= 1 && W >= 1 && Cin >= 1 && Cin_pad % 8 == 0 && Cin_pad >= Cin && Cout % 64 == 0 && Cout >= 64,
               DFB_ERR_INVALID, "dfb_conv_wgrad: bad shape");
@@ -328,12 +343,13 @@ extern "C" int dfb_conv_wgrad(const void* gO, const void* X, int B, int H, int W
     rc = make_patch_tmap(X, B, H, W, Cin_pad, wg::kTH, a.PW, &a.tmap_x, a.NB / 8);
     if (rc) return rc;
   }
-  if (a.n_split > 1) DFB_CHECK_CUDA(cudaMemsetAsync(dW, 0, (size_t)Cout * Cin * KH * KH * 4, st));
+  a.atomic = (a.n_split > 1 || accumulate) ? 1 : 0;
+  if (a.n_split > 1 && !accumulate) DFB_CHECK_CUDA(cudaMemsetAsync(dW, 0, (size_t)Cout * Cin * KH * KH * 4, st));
   DFB_CHECK_CUDA(cudaFuncSetAttribute(wg::k_conv_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   wg::k_conv_wgrad<<<units * a.n_split, wg::kThreads, smem, st>>>(a);
   DFB_LAUNCH_CHECK();
   if (dB) {
-    DFB_CHECK_CUDA(cudaMemsetAsync(dB, 0, (size_t)Cout * 4, st));
+    if (!accumulate) DFB_CHECK_CUDA(cudaMemsetAsync(dB, 0, (size_t)Cout * 4, st));
     const int64_t npix = (int64_t)B * H * W;
     if (Cout == 64 || Cout == 128 || Cout == 256 || Cout == 512) {
       const int nl = 256 / (Cout / 8);

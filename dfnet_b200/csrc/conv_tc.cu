@@ -53,6 +53,8 @@ struct ConvArgs {
   __half* out;        // NHWC [B,H,W,Cout], after activation (nullable)
   __half* tap;        // NHWC [B,H,W,Cout], before activation (nullable)
   float* out_nchw;    // fp32 [B,nchw_C,H,W], before activation (nullable)
+  uint16_t* out_bf16; // NHWC [B,H,W,Cout] bf16 copy of `out` (after activation; nullable): the weight-gradient kernel's
+                      // operand type, written here instead of by a separate conversion kernel (NeRF-Hist training)
   const uint16_t* mask;    // NHWC 16-bit [B,H,W,Cout]: result zeroed where mask <= 0 (ReLU backward; nullable)
   const uint16_t* addend;  // NHWC 16-bit [B,H,W,Cout] added after masking (gradient of a second consumer; nullable)
   int B, H, W, Cin, Cout, KH, KW, pad, relu;
@@ -153,6 +155,13 @@ __device__ __forceinline__ void epi_store(const ConvArgs& a, const uint32_t (&v)
     for (int q = 0; q < 4; ++q)
       d[q] = make_uint4(pack2<T>(xv[8 * q], xv[8 * q + 1]), pack2<T>(xv[8 * q + 2], xv[8 * q + 3]),
                         pack2<T>(xv[8 * q + 4], xv[8 * q + 5]), pack2<T>(xv[8 * q + 6], xv[8 * q + 7]));
+    if (a.out_bf16) {
+      uint4* d2 = reinterpret_cast<uint4*>(a.out_bf16 + o);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        d2[q] = make_uint4(pack2<__nv_bfloat16>(xv[8 * q], xv[8 * q + 1]), pack2<__nv_bfloat16>(xv[8 * q + 2], xv[8 * q + 3]),
+                           pack2<__nv_bfloat16>(xv[8 * q + 4], xv[8 * q + 5]), pack2<__nv_bfloat16>(xv[8 * q + 6], xv[8 * q + 7]));
+    }
   }
 }
 
@@ -673,11 +682,11 @@ extern "C" void dfb_conv_destroy(DfbConv* c) {
 }
 
 int dfb_conv_run(DfbConv* c, const void* in_nhwc16, int B, int H, int W, int relu, void* out_nhwc16, void* tap_nhwc16,
-                 float* out_nchw32, const void* mask_nhwc16, const void* addend_nhwc16, void* stream);
+                 float* out_nchw32, const void* mask_nhwc16, const void* addend_nhwc16, void* stream, void* out_bf16);
 
 extern "C" int dfb_conv_fwd(DfbConv* c, const void* in_nhwc16, int B, int H, int W, int relu, void* out_nhwc16,
                             void* tap_nhwc16, float* out_nchw32, void* stream) {
-  return dfb_conv_run(c, in_nhwc16, B, H, W, relu, out_nhwc16, tap_nhwc16, out_nchw32, nullptr, nullptr, stream);
+  return dfb_conv_run(c, in_nhwc16, B, H, W, relu, out_nhwc16, tap_nhwc16, out_nchw32, nullptr, nullptr, stream, nullptr);
 }
 
 // 5-D tensor map over the NHWC 16-bit input for the patch loads of k_conv_tc (see ConvArgs::tmap_in).
@@ -721,8 +730,9 @@ extern "C" int dfb_debug_conv_prof(int on, unsigned long long* out_host, int max
 }
 
 int dfb_conv_run(DfbConv* c, const void* in_nhwc16, int B, int H, int W, int relu, void* out_nhwc16, void* tap_nhwc16,
-                 float* out_nchw32, const void* mask_nhwc16, const void* addend_nhwc16, void* stream) {
+                 float* out_nchw32, const void* mask_nhwc16, const void* addend_nhwc16, void* stream, void* out_bf16) {
   DFB_REQUIRE(c && in_nhwc16 && (out_nhwc16 || tap_nhwc16 || out_nchw32), DFB_ERR_INVALID, "dfb_conv_fwd: null argument");
+  DFB_REQUIRE(!out_bf16 || out_nhwc16, DFB_ERR_INVALID, "dfb_conv_fwd: the bf16 copy accompanies the 16-bit output");
   DFB_REQUIRE(B >= 1 && H >= 1 && W >= 1, DFB_ERR_INVALID, "bad image size");
   int* error_flag = nullptr;
   {
@@ -731,7 +741,7 @@ int dfb_conv_run(DfbConv* c, const void* in_nhwc16, int B, int H, int W, int rel
   }
   conv::ConvArgs a = {};
   a.in = (const __half*)in_nhwc16, a.wimg = c->wimg, a.bias = c->bias;
-  a.out = (__half*)out_nhwc16, a.tap = (__half*)tap_nhwc16, a.out_nchw = out_nchw32;
+  a.out = (__half*)out_nhwc16, a.tap = (__half*)tap_nhwc16, a.out_nchw = out_nchw32, a.out_bf16 = (uint16_t*)out_bf16;
   a.mask = (const uint16_t*)mask_nhwc16, a.addend = (const uint16_t*)addend_nhwc16, a.nchw_C = c->nchw_C;
   a.B = B, a.H = H, a.W = W, a.Cin = c->Cin_pad, a.Cout = c->Cout, a.KH = c->KH, a.KW = c->KW, a.pad = c->pad, a.relu = relu;
   a.nt = c->nt, a.n_ntiles = c->n_ntiles, a.n_cc = c->n_cc, a.cpp = c->cpp;
@@ -784,5 +794,12 @@ extern "C" int dfb_conv_create_ex(int Cin, int Cout, int KH, int KW, const float
 extern "C" int dfb_conv_fwd_ex(DfbConv* c, const void* in_nhwc16, int B, int H, int W, int relu, void* out_nhwc16,
                                void* tap_nhwc16, float* out_nchw32, const void* mask_nhwc16, const void* addend_nhwc16,
                                void* stream) {
-  return dfb_conv_run(c, in_nhwc16, B, H, W, relu, out_nhwc16, tap_nhwc16, out_nchw32, mask_nhwc16, addend_nhwc16, stream);
+  return dfb_conv_run(c, in_nhwc16, B, H, W, relu, out_nhwc16, tap_nhwc16, out_nchw32, mask_nhwc16, addend_nhwc16, stream, nullptr);
+}
+
+// dfb_conv_fwd_ex with a bf16 copy of the 16-bit output (the operand type of dfb_conv_wgrad), written by the same epilogue
+extern "C" int dfb_conv_fwd_ex2(DfbConv* c, const void* in_nhwc16, int B, int H, int W, int relu, void* out_nhwc16,
+                                void* tap_nhwc16, float* out_nchw32, const void* mask_nhwc16, const void* addend_nhwc16,
+                                void* out_bf16, void* stream) {
+  return dfb_conv_run(c, in_nhwc16, B, H, W, relu, out_nhwc16, tap_nhwc16, out_nchw32, mask_nhwc16, addend_nhwc16, stream, out_bf16);
 }

@@ -20,7 +20,7 @@ int dfb_conv_update_impl(DfbConv* c, const float* weight, const float* bias, con
 void dfb_conv_pack_batch_begin();
 int dfb_conv_pack_batch_flush(bool discard, void* stream = nullptr);
 int dfb_conv_run(DfbConv* c, const void* in_nhwc16, int B, int H, int W, int relu, void* out_nhwc16, void* tap_nhwc16,
-                 float* out_nchw32, const void* mask_nhwc16, const void* addend_nhwc16, void* stream);
+                 float* out_nchw32, const void* mask_nhwc16, const void* addend_nhwc16, void* stream, void* out_bf16 = nullptr);
 
 struct DfbDfnet {
   int n_levels = 3;

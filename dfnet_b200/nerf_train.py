@@ -62,8 +62,12 @@ class _Layer:
             pass
 
 
-def _conv(handle, x, Hh, relu, out=None, tap=None, nchw=None, mask=None, addend=None):
-    check(lib.dfb_conv_fwd_ex(handle, _p(x), 1, Hh, 8, int(relu), _p(out), _p(tap), _p(nchw), _p(mask), _p(addend), _st()))
+def _conv(handle, x, Hh, relu, out=None, tap=None, nchw=None, mask=None, addend=None, out_bf=None):
+    """out_bf: bf16 copy of `out`, written by the same epilogue (the weight-gradient kernel's operand type)."""
+    if out_bf is not None:
+        check(lib.dfb_conv_fwd_ex2(handle, _p(x), 1, Hh, 8, int(relu), _p(out), _p(tap), _p(nchw), _p(mask), _p(addend), _p(out_bf), _st()))
+    else:
+        check(lib.dfb_conv_fwd_ex(handle, _p(x), 1, Hh, 8, int(relu), _p(out), _p(tap), _p(nchw), _p(mask), _p(addend), _st()))
 
 
 def trainable_shape(net):
@@ -165,6 +169,17 @@ class NetTrainer:
         Hh = Pp // 8
         f16 = torch.float16
         N = rb_dir.shape[0]
+        # with gradients wanted every activation that is a weight-gradient operand gets a bf16 twin from the same epilogue
+        # (26 separate conversion launches per step otherwise)
+        twin = torch.is_grad_enabled()
+        bfd = torch.bfloat16
+        tw = {}
+
+        def bf(name, cols):
+            if not twin:
+                return None
+            tw[name] = self.buf("bf_" + name, Pp, cols, bfd)
+            return tw[name]
         h = []
         x = pe16
         skip = self.buf("skip", Pp, W, f16)
@@ -172,19 +187,19 @@ class NetTrainer:
             o = self.buf(f"h{i}", Pp, W, f16)
             if i == 4:
                 _conv(self.L["xpe"].fwd, pe16, Hh, 0, tap=skip)                       # W_pe . pe (pre-activation part)
-                _conv(self.L["x4"].fwd, x, Hh, 1, out=o, addend=skip)
+                _conv(self.L["x4"].fwd, x, Hh, 1, out=o, addend=skip, out_bf=bf(f"h{i}", W))
             else:
-                _conv(self.L[f"x{i}"].fwd, x, Hh, 1, out=o)
+                _conv(self.L[f"x{i}"].fwd, x, Hh, 1, out=o, out_bf=bf(f"h{i}", W))
             h.append(o)
             x = o
         planes = self.buf("planes", 3 * 64, Pp, torch.float32)                        # fp32 head pre-activations [ch][P]
         _conv(self.L["sigma"].fwd, x, Hh, 0, nchw=planes[0:64])
         final = self.buf("final", Pp, W, f16)
-        _conv(self.L["final"].fwd, x, Hh, 0, out=final)
+        _conv(self.L["final"].fwd, x, Hh, 0, out=final, out_bf=bf("final", W))
         add_d = self.buf("add_d", Pp, H2, f16)
         check(lib.dfb_rows_expand16(_p(rb_dir.contiguous()), N, S, H2, _p(add_d), _st()))
         dirh = self.buf("dirh", Pp, H2, f16)
-        _conv(self.L["dir"].fwd, final, Hh, 1, out=dirh, addend=add_d)
+        _conv(self.L["dir"].fwd, final, Hh, 1, out=dirh, addend=add_d, out_bf=bf("dirh", H2))
         _conv(self.L["rgb"].fwd, dirh, Hh, 0, nchw=planes[64:128])
         t = []
         Cc = 4
@@ -193,17 +208,17 @@ class NetTrainer:
             add_t = self.buf("add_t", Pp, H2, f16)
             check(lib.dfb_rows_expand16(_p(rb_t.contiguous()), N, S, H2, _p(add_t), _st()))
             o = self.buf("t0", Pp, H2, f16)
-            _conv(self.L["t0"].fwd, final, Hh, 1, out=o, addend=add_t)
+            _conv(self.L["t0"].fwd, final, Hh, 1, out=o, addend=add_t, out_bf=bf("t0", H2))
             t.append(o)
             for k in (1, 2, 3):
                 o2 = self.buf(f"t{k}", Pp, H2, f16)
-                _conv(self.L[f"t{k}"].fwd, t[-1], Hh, 1, out=o2)
+                _conv(self.L[f"t{k}"].fwd, t[-1], Hh, 1, out=o2, out_bf=bf(f"t{k}", H2))
                 t.append(o2)
             _conv(self.L["th"].fwd, t[-1], Hh, 0, nchw=planes[128:192])
         raw = torch.empty(P, Cc, device=self.dev)
         check(lib.dfb_nerf_heads_fwd(_p(planes[0:64]), _p(planes[64:128]), _p(planes[128:192]) if self.fine else None, P, Pp, Cc,
                                      _p(raw), _st()))
-        return raw, dict(pe=pe16, h=h, final=final, dirh=dirh, t=t, P=P, Pp=Pp, S=S, N=N)
+        return raw, dict(pe=pe16, h=h, final=final, dirh=dirh, t=t, P=P, Pp=Pp, S=S, N=N, bf=tw)
 
     # ---- backward ---------------------------------------------------------------------------------------------------
     def backward(self, tape, raw, g_raw):
@@ -215,15 +230,27 @@ class NetTrainer:
         Cc = 9 if self.fine else 4
         st = _st()
 
+        twins = tape.get("bf", {})
+
         def cast(x, name):
+            if name in twins:        # written by the forward's epilogue
+                return twins[name]
             o = self.buf("bf_" + name, x.shape[0], x.shape[1], bf)
             check(lib.dfb_cast_f16_bf16(_p(x), _p(o), x.numel(), st))
             return o
 
+        # all weight / bias gradients of this backward live in ONE zeroed buffer (one memset instead of two per layer)
+        need = sum(l.cout_pad * l.cin + l.cout_pad + 4 for l in self.L.values())
+        flat = torch.zeros(need, device=self.dev)
+        cursor = [0]
+
         def wgrad(gO, X, cin, cout_pad):
-            dW = torch.empty(cout_pad, cin, device=self.dev)
-            dB = torch.empty(cout_pad, device=self.dev)
-            check(lib.dfb_conv_wgrad(_p(gO), _p(X), 1, Hh, 8, cin, X.shape[1], cout_pad, 1, 1, _p(dW), _p(dB), st))
+            o0 = cursor[0]
+            dW = flat[o0:o0 + cout_pad * cin].view(cout_pad, cin)
+            dB = flat[o0 + cout_pad * cin:o0 + cout_pad * cin + cout_pad]
+            cursor[0] = o0 + (cout_pad * cin + cout_pad + 3) // 4 * 4
+            assert cursor[0] <= need
+            check(lib.dfb_conv_wgrad_acc(_p(gO), _p(X), 1, Hh, 8, cin, X.shape[1], cout_pad, 1, 1, _p(dW), _p(dB), st))
             return dW, dB
 
         gs = self.buf("g_sig", Pp, 64, bf)

@@ -316,9 +316,16 @@ int dfb_conv_create_ex(int Cin, int Cout, int KH, int KW, const float* weight, c
 /* dfb_conv_fwd plus the backward epilogue: result zeroed where mask_nhwc16 <= 0 (ReLU'), then addend_nhwc16 added. */
 int dfb_conv_fwd_ex(DfbConv* c, const void* in_nhwc16, int B, int H, int W, int relu, void* out_nhwc16, void* tap_nhwc16,
                     float* out_nchw32, const void* mask_nhwc16, const void* addend_nhwc16, void* stream);
+/* dfb_conv_fwd_ex with a bf16 copy of the 16-bit output (out_bf16, NHWC like out_nhwc16; the operand type of
+ * dfb_conv_wgrad), written by the same epilogue instead of a separate conversion kernel. */
+int dfb_conv_fwd_ex2(DfbConv* conv, const void* in_nhwc16, int B, int H, int W, int relu, void* out_nhwc16, void* tap_nhwc16,
+                     float* out_nchw32, const void* mask_nhwc16, const void* addend_nhwc16, void* out_bf16, void* stream);
 /* Weight (and optional bias) gradient of a KHxKH convolution, stride 1, pad KH/2 (torch autograd conv backward w.r.t.
  * weight): gO NHWC [B,H,W,Cout], X NHWC [B,H,W,Cin_pad] 16-bit (fmt 0 f16 / 1 bf16) -> dW fp32 [Cout,Cin,KH,KH], dB [Cout]. */
 int dfb_conv_wgrad(const void* gO, const void* X, int B, int H, int W, int Cin, int Cin_pad, int Cout, int KH, int fmt,
+                   float* dW, float* dB, void* stream);
+/* Same, ADDING to dW / dB (the caller zeroed them: one memset for a flat gradient buffer instead of two per layer). */
+int dfb_conv_wgrad_acc(const void* gO, const void* X, int B, int H, int W, int Cin, int Cin_pad, int Cout, int KH, int fmt,
                    float* dW, float* dB, void* stream);
 
 /* dfb_dfnet_load, flags bit0: also build the training variants (bf16 encoder, data-gradient convolutions); bit1: the
