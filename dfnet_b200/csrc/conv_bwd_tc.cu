@@ -8,6 +8,7 @@
 // [8-channel panel][patch row][patch col][16 B], eight consecutive pixels of a patch row form one
 // 8(K) x 16 B(MN) core matrix, the next channel panel is SBO away and the next patch row (the next
 // 8 pixels of the K dimension) LBO away, so again every filter tap is only a shifted start address.
+// Tiles (gO tile, X patch of one filter row incl. halo) arrive as two TMA boxes each through a 3-stage ring.
 #include <stdlib.h>
 #include <string.h>
 

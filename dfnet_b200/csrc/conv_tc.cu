@@ -5,7 +5,7 @@
 //
 // im2col-free: an M tile is a 16 x 8 pixel patch.  For every 64-channel slice the patch PLUS ITS
 // HALO is loaded once into shared memory as [8-channel panel][patch row][patch col][16 B]
-// (16-byte cp.async from NHWC, coalesced 128 B per pixel, zero fill outside the image).  The A
+// (ONE 5-D TMA box over the NHWC tensor, zero fill outside the image by the TMA unit).  The A
 // operand of filter tap (ky,kx) is then just a shifted window of that patch: 8 consecutive pixels
 // of a row are one 8x16B core matrix, the next row is SBO = patch_width*16 B away and the next
 // 8-channel panel LBO = patch_rows*patch_width*16 B away, so tcgen05.mma reads all KH*KW taps
@@ -14,7 +14,9 @@
 // are double-buffered in TMEM; the epilogue applies bias / ReLU and writes NHWC 16-bit (next
 // layer), an optional pre-activation tap, or fp32 NCHW (the layout the reference returns).
 //
-// Warps: 0-3 epilogue (thread = pixel), 4-7 patch loader, 8 weight producer, 9 MMA issuer.
+// Warps: 0-3 epilogue (thread = pixel), 4 patch producer (TMA), 8 weight producer, 9 MMA issuer (warps 5-7 idle).
+// Default variant k_conv_tc2 (cta_group::2): CTA pairs work on two neighbouring M tiles with one weight stream and one
+// MMA instruction for both SMs; k_conv_tc (DFB_CONV_CTA_GROUP=1, single-tile launches) is the 1-CTA variant.
 #include <stdlib.h>
 #include <string.h>
 

@@ -1,16 +1,22 @@
-// tcgen05 NeRF-W MLP for the 8x256 networks (BASELINE config[1]/[4]): a persistent,
-// warp-specialised kernel.  Each CTA owns all 512 TMEM columns and works on two 128-sample
-// tiles ("slots") that alternate between the tensor pipe and the epilogue warps:
+// tcgen05 NeRF-W MLP (8x256 of BASELINE config[1]/[4], 8x128 of the reference's shipped configs as its own program,
+// other widths zero-padded into 8x256): a persistent, warp-specialised kernel.  Each CTA owns all 512 TMEM columns and
+// works on two 128-sample tiles ("slots") that alternate between the tensor pipe and the epilogue warps.  Default
+// variant k_mlp_tc2: CTA PAIRS (cta_group::2) share every weight chunk and one MMA instruction feeds both SMs;
+// k_mlp_tc (DFB_TC_CTA_GROUP=1) is the 1-CTA variant.
 //
-//   warp 12      weight producer : cp.async.bulk (TMA) of pre-packed 16 KB weight chunks from
-//                                  L2 into a 4-stage shared-memory ring, mbarrier complete_tx
-//   warp 13      MMA issuer      : one thread issues tcgen05.mma.cta_group::1.kind::f16
-//                                  (M=128, N=256|128, K=16) with A = activations in shared memory,
-//                                  B = weight chunk, D = fp32 accumulators in TMEM; tcgen05.commit
-//                                  releases ring stages and publishes finished layers
-//   warps 0-3    epilogue slot 0 : tcgen05.ld 32x32b (thread = sample row), bias/ReLU in fp32,
-//   warps 4-7    epilogue slot 1   pack to fp16/bf16 and store the next layer's A operand in place;
-//                                  sigma / rgb / transient heads are fp32 dot products in registers
+//   warp 12      weight producer : pre-packed 16 KB weight chunks from L2 into a 4-stage shared-memory ring
+//                                  (2-SM TMA of this CTA's half of a chunk, credited to the leader's mbarrier;
+//                                  1-CTA variant: cp.async.bulk)
+//   warp 13      MMA issuer      : one elected thread of the pair's leader issues tcgen05.mma.cta_group::2.kind::f16
+//                                  (M = 256 over the pair, N = 256|128|64, K = 16) with A = activations in shared
+//                                  memory, B = weight chunk, D = fp32 accumulators in TMEM; multicast tcgen05.commit
+//                                  releases ring stages and publishes finished layers in both CTAs
+//   warps 0-7    epilogue        : thread = accumulator row (sample) of BOTH slots, the two warpgroups split every
+//                                  step's columns; tcgen05.ld 32x32b, bias + ReLU as packed HFMA2.RELU, 16-bit store of
+//                                  the next layer's A operand in place; the output heads are MMA steps of their own
+//                                  (N = 64) whose epilogue applies softplus / sigmoid and, on the render_path step,
+//                                  composites the ray segments in registers (fused_composite); ONE barrier arrival per
+//                                  warp with CTA-scope release (see mbar_arrive_cluster in tc_common.cuh)
 //   warps 8-11   encoder         : pts = o + d*z and the 63-wide positional encoding of the NEXT
 //                                  pass's tiles, written straight into the A-operand layout
 //
