@@ -133,6 +133,34 @@ def test_native_128_wide_program_vs_oracle_and_embedding(monkeypatch):
     assert float((ert["rgb"] - nat["rgb"]).abs().max()) < 5e-3
 
 
+def test_pair_kernels_are_deterministic_over_repeats(ctx):
+    """The cta_group::2 kernels hand tiles between the two CTAs of a pair through barriers with CTA-scope release / acquire
+    (tc_common.cuh, mbar_arrive_cluster): a missing ordering would show up as run-to-run differences.  30 renders of the
+    640x480 image (fused compositing), 10 training forwards with masks + saved-mask backwards: bit-identical every time."""
+    ops, h, nets = ctx
+    H, W, focal, near, far, Nc, Nf = 480, 640, 585.0, 0.0, 2.5, 64, 128
+    kw = dict(c2w=torch.tensor(C2W, device=dev()), H=H, W=W, focal=focal, near=near, far=far, hist=torch.tensor(HIST, device=dev()))
+    first = {k: v.clone() for k, v in h.render(Nc, Nf, True, mma="f16", **kw).items()}
+    for _ in range(30):
+        o = h.render(Nc, Nf, True, mma="f16", **kw)
+        for k in ("rgb", "disp", "acc"):
+            assert torch.equal(o[k], first[k]), k
+    oo, dd = O.get_rays(H, W, focal, C2W)
+    idx = np.arange(0, H * W, 41)[:4099]      # ragged: not a multiple of the 128-sample tile
+    rec = torch.tensor(O.make_ray_records(oo.reshape(-1, 3)[idx], dd.reshape(-1, 3)[idx], near, far, HIST[None]), device=dev())
+    g = torch.randn(rec.shape[0], 3, device=dev()) * 1e-6
+    ref = None
+    for _ in range(10):
+        t = h.render(Nc, Nf, True, rays=rec, mma="f16", want=("z_vals", "raw", "relu_masks"))
+        grads = h.render_backward(rec, t["z_vals"], t["raw"], g, mma="f16", relu_masks=t["relu_masks"])
+        m = t["relu_masks"].view(-1, 12, 8, 128)       # the 128-wide transient layers (9..11) write 4 of their 8 words
+        cur = [t["raw"].clone(), torch.cat([m[:, :9].reshape(-1), m[:, 9:, :4].reshape(-1)])] + [x.clone() for x in grads]
+        if ref is None:
+            ref = cur
+        for name, a, b in zip(("raw", "relu_masks", "g_rays_o", "g_rays_d", "g_viewdirs"), cur, ref):
+            assert torch.equal(a, b), (name, int((a != b).sum()), a.numel())
+
+
 def test_split_precision_coarse_pass_vs_oracle(ctx):
     """mma="f16s" on the benchmark field: the coarse weights (which decide the sample indices) match the oracle like the
     fp32 kernels do, indices almost never flip, the image stays inside 1e-3."""
