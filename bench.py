@@ -343,10 +343,20 @@ def bench_extras(args, dev, rank, world, mma):
     ar = parallel.allreduce_stats(reset=True)
     ms_mean = max_ranks(tot) / n_tr
     ms_med = max_ranks(float(np.median(per)))
+    # the same step with the feature net evaluating ALL three hyper-column levels, as the reference does before it
+    # index_selects feature_matching_lvl (the default step skips the levels nothing reads: identical loss and gradients)
+    os.environ["DFB_ALL_LEVELS"] = "1"
+    tot_all, _ = _event_timed(train_step, 5, 2, stream, barrier)
+    del os.environ["DFB_ALL_LEVELS"]
+    ms_all = max_ranks(tot_all) / 5
     out["train"] = {
         "metric": "train_on_batch steps/sec (BASELINE config[3] / SURVEY cfg4: 480x640 image, 120x160 render, 8x256 NeRF-W 64+128, "
                   "DFNet F+G, feature_matching_lvl=[0], Adam), one image per rank",
         "value": world * 1e3 / ms_mean, "unit": "steps/s", "ms_per_step": ms_mean, "ms_median": ms_med, "steps": n_tr, "warmup": 4,
+        "ms_per_step_all_levels": ms_all,
+        "note": "the frozen feature net evaluates only feature_matching_lvl (with [0] its encoder stops after conv1_2); loss, PSNR "
+                "and every gradient are identical to evaluating all three levels and selecting afterwards, which is what the "
+                "reference does and what ms_per_step_all_levels times",
         "gpu_launches_per_step": launches, "n_gpus": world, "scaling": "weak",
         "allreduce": {"calls_per_step": ar["calls"] / max(n_tr, 1), "bytes_per_call": ar["bytes_per_call"],
                       "ms_per_call": ar["ms"] / max(ar["timed_calls"], 1) if ar["timed_calls"] else 0.0,

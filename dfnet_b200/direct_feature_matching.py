@@ -8,6 +8,8 @@ dfb_render_bwd), the bicubic x4 upsampling and its adjoint, the frozen feature n
 cosine / MSE losses.  torch is the host runtime: autograd graph edges, the 3x3 SVD, the [1,3,4] pose arithmetic and
 the optimizer.
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -87,6 +89,8 @@ def matching_terms(args, data, rgb, feat_model, device):
     # neither computed (want_levels; with level 0 alone the encoder stops after conv1_2) nor differentiated (grad_levels)
     prev = (getattr(feat_model, "grad_levels", None), getattr(feat_model, "want_levels", None))
     feat_model.grad_levels = feat_model.want_levels = list(args.feature_matching_lvl)
+    if os.environ.get("DFB_ALL_LEVELS") == "1":   # A/B: evaluate every level like the reference does (and discards)
+        feat_model.want_levels = None
     try:
         (feature_target, feature_rgb), _ = inference_pose_regression(args, torch.cat([data, rgb]), device, feat_model, retFeature=True,
                                                                      isSingleStream=False, return_pose=False)
