@@ -328,8 +328,8 @@ static int conv_wgrad_impl(const void* gO, const void* X, int B, int H, int W, i
   const int units = a.n_cib * a.n_cob * KH;
   // Pixel tiles are split over as many CTAs as the GPU has SMs (fp32 atomics at the end; a CTA that covers every tile
   // stores directly).  Measured and dropped: running the deep layers unsplit (conv4_x / conv5_x of a 480x640 image have 40 /
-  // 10 tiles) - the MN-major MMAs of a tile take ~6 000 cycles, not the nominal 1 536 (the 2 KB panel stride of the
-  // no-swizzle MN-major operands maps all 16 panels onto the same banks), so fewer CTAs lose more than the atomics cost.
+  // 10 tiles) - a tile costs ~5 000 cycles (its two TMA boxes are 4 600 separate 16-byte rows; the MMAs are 1 536), so
+  // fewer CTAs lose more than the atomics cost.
   a.n_split = std::max(1, std::min(a.n_tiles, sms / units));
   a.PW = wg::kTW + 2 * a.pad;
   a.x_bytes = (uint32_t)(a.NB / 8) * wg::kTH * a.PW * 16u;
