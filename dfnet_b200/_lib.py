@@ -6,6 +6,10 @@ compute entry point refuses to run without a CUDA device.
 import ctypes as C
 import os
 
+import torch
+
+_raw_stream = torch._C._cuda_getCurrentRawStream
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DFB_LIB_PATH", os.path.join(_HERE, "libdfnet_b200.so"))  # override: profiling builds only
 
@@ -21,12 +25,17 @@ SYMBOLS = [
     "dfb_dfnet_bwd_workspace_bytes", "dfb_dfnet_bwd", "dfb_cosine_loss_bwd", "dfb_mse_bwd", "dfb_resize_bicubic_bwd",
     "dfb_resize_bilinear_ac_bwd", "dfb_dfnet_bwd_bucket_event", "dfb_luma_hist", "dfb_resize_area", "dfb_pose_error", "dfb_polar3x3_fwd", "dfb_polar3x3_bwd", "dfb_debug_conv_prof",
     "dfb_conv_update", "dfb_conv_pack_begin", "dfb_conv_pack_end", "dfb_embed_xyz16", "dfb_rows_expand16", "dfb_rows_reduce_bf16", "dfb_nerf_heads_fwd", "dfb_nerf_heads_bwd",
-    "dfb_raw2outputs_bwd", "dfb_cast_f16_bf16", "dfb_render_poses_fwd",
+    "dfb_raw2outputs_bwd", "dfb_cast_f16_bf16", "dfb_render_poses_fwd", "dfb_copy2d_batch",
 ]
 
 MMA_FP32_SIMT, MMA_F16, MMA_BF16, MMA_F16_SPLIT_COARSE = 0, 1, 2, 3
 # "f16s": fp16 tensor-core path with the split-precision (hi + lo operands) coarse pass, see include/dfnet_b200.h
 MMA_KINDS = {"fp32": MMA_FP32_SIMT, "f16": MMA_F16, "bf16": MMA_BF16, "f16s": MMA_F16_SPLIT_COARSE}
+
+
+class Copy2d(C.Structure):
+    """DfbCopy2d (include/dfnet_b200.h): one strided fp32 copy of dfb_copy2d_batch."""
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("rows", C.c_int), ("cols", C.c_int), ("src_ld", C.c_int), ("dst_ld", C.c_int)]
 
 
 class NerfDesc(C.Structure):
@@ -125,6 +134,7 @@ def _load():
     lib.dfb_conv_pack_end.argtypes = [vp]
     lib.dfb_polar3x3_fwd.argtypes = [vp, i32, vp, vp, vp]
     lib.dfb_polar3x3_bwd.argtypes = [vp, vp, i32, vp, vp]
+    lib.dfb_copy2d_batch.argtypes = [vp, i32, vp]
     lib.dfb_cosine_loss_bwd.argtypes = [vp, vp, i32, i64, i32, f32, vp, vp, vp, C.c_size_t, vp]
     lib.dfb_mse_bwd.argtypes = [vp, vp, i64, vp, vp, vp]
     lib.dfb_resize_bicubic_bwd.argtypes = [vp, i64, i32, i32, i32, i32, vp, vp]
@@ -147,6 +157,13 @@ def _load():
 
 
 lib = _load()
+
+
+def raw_stream():
+    """The current torch CUDA stream of the current device as a stream argument of the C ABI (a `void*`). The raw accessor
+    costs ~0.2 us against ~1.5 us for `torch.cuda.current_stream().cuda_stream`, which adds up over the ~500 launches of a
+    training step."""
+    return C.c_void_p(_raw_stream(-1))
 
 
 def check(rc):

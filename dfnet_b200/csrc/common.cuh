@@ -46,6 +46,24 @@ int device_error_flag(int** out);
     }                                                                           \
   } while (0)
 
+
+// Launch with programmatic stream serialization when `pdl` (the kernel calls pdl_wait() before it touches global memory,
+// see tc_common.cuh); an ordinary launch otherwise.  DFB_PDL=0 in the environment turns it off everywhere.
+inline bool dfb_pdl_env() {
+  const char* e = getenv("DFB_PDL");
+  return !(e && e[0] == '0');
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t dfb_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = (pdl && dfb_pdl_env()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 constexpr int kRayRec = 12;  // o3 d3 near far vd3 pad
 constexpr size_t kReluMaskWordsPerTile = DFB_RELU_MASK_WORDS_PER_TILE;
 

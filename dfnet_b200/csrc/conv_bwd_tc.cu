@@ -100,6 +100,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_wgrad(const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();               // global memory is read and written only from here on
+  pdl_launch_dependents();
   const uint32_t tmem_base = *tmem_slot;
   const int tiles_img = a.tiles_x * a.tiles_y;
   const int npan = a.NB / 8;
@@ -187,6 +189,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_wgrad(const __grid_constan
 template <typename T>
 __global__ void k_bias_grad_generic(const uint16_t* __restrict__ gO, int64_t npix, int C, float* __restrict__ gB) {
   const int c = blockIdx.x * 64 + (threadIdx.x & 63), part = threadIdx.x >> 6;
+  pdl_wait();
+  pdl_launch_dependents();
   float s = 0.f;
   for (int64_t p = (int64_t)blockIdx.y * 4 + part; p < npix; p += (int64_t)gridDim.y * 4)
     s += std::is_same<T, __nv_bfloat16>::value ? __uint_as_float((uint32_t)gO[p * C + c] << 16)
@@ -204,6 +208,8 @@ __global__ void k_bias_grad_generic(const uint16_t* __restrict__ gO, int64_t npi
 template <typename T>
 __global__ void __launch_bounds__(256) k_bias_grad(const uint16_t* __restrict__ gO, int64_t npix, int C, float* __restrict__ gB) {
   const int cgs = C >> 3, g = threadIdx.x % cgs, lane = threadIdx.x / cgs, nl = 256 / cgs;
+  pdl_wait();
+  pdl_launch_dependents();
   float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int64_t p = (int64_t)blockIdx.x * nl + lane; p < npix; p += (int64_t)gridDim.x * nl) {
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(gO + p * C) + g);
@@ -346,8 +352,16 @@ static int conv_wgrad_impl(const void* gO, const void* X, int B, int H, int W, i
   }
   a.atomic = (a.n_split > 1 || accumulate) ? 1 : 0;
   if (a.n_split > 1 && !accumulate) DFB_CHECK_CUDA(cudaMemsetAsync(dW, 0, (size_t)Cout * Cin * KH * KH * 4, st));
-  DFB_CHECK_CUDA(cudaFuncSetAttribute(wg::k_conv_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  wg::k_conv_wgrad<<<units * a.n_split, wg::kThreads, smem, st>>>(a);
+  {
+    static thread_local uint64_t attr_set = 0;   // bit d: set on device d
+    int cur = 0;
+    DFB_CHECK_CUDA(cudaGetDevice(&cur));
+    if (!((attr_set >> (cur & 63)) & 1)) {
+      DFB_CHECK_CUDA(cudaFuncSetAttribute(wg::k_conv_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+      attr_set |= 1ull << (cur & 63);
+    }
+  }
+  DFB_CHECK_CUDA(dfb_launch_pdl(wg::k_conv_wgrad, dim3(units * a.n_split), dim3(wg::kThreads), smem, st, true, a));
   DFB_LAUNCH_CHECK();
   if (dB) {
     if (!accumulate) DFB_CHECK_CUDA(cudaMemsetAsync(dB, 0, (size_t)Cout * 4, st));
@@ -355,12 +369,12 @@ static int conv_wgrad_impl(const void* gO, const void* X, int B, int H, int W, i
     if (Cout == 64 || Cout == 128 || Cout == 256 || Cout == 512) {
       const int nl = 256 / (Cout / 8);
       const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((npix + nl - 1) / nl, 148 * 4));
-      if (fmt) wg::k_bias_grad<__nv_bfloat16><<<blocks, 256, 0, st>>>((const uint16_t*)gO, npix, Cout, dB);
-      else wg::k_bias_grad<__half><<<blocks, 256, 0, st>>>((const uint16_t*)gO, npix, Cout, dB);
+      auto kern = fmt ? wg::k_bias_grad<__nv_bfloat16> : wg::k_bias_grad<__half>;
+      DFB_CHECK_CUDA(dfb_launch_pdl(kern, dim3(blocks), dim3(256), 0, st, true, (const uint16_t*)gO, npix, Cout, dB));
     } else {
       const int splits = (int)std::max<int64_t>(1, std::min<int64_t>(64, npix / 256));
-      if (fmt) wg::k_bias_grad_generic<__nv_bfloat16><<<dim3(Cout / 64, splits), 256, 0, st>>>((const uint16_t*)gO, npix, Cout, dB);
-      else wg::k_bias_grad_generic<__half><<<dim3(Cout / 64, splits), 256, 0, st>>>((const uint16_t*)gO, npix, Cout, dB);
+      auto kern = fmt ? wg::k_bias_grad_generic<__nv_bfloat16> : wg::k_bias_grad_generic<__half>;
+      DFB_CHECK_CUDA(dfb_launch_pdl(kern, dim3(Cout / 64, splits), dim3(256), 0, st, true, (const uint16_t*)gO, npix, Cout, dB));
     }
     DFB_LAUNCH_CHECK();
   }

@@ -217,6 +217,10 @@ __device__ __forceinline__ void conv_tc_body(const ConvArgs& a) {
   tc_fence_before();
   if (CG == 2) cluster_sync(); else __syncthreads();
   tc_fence_after();
+  // everything above touched only this CTA's shared memory / TMEM and ran next to the previous kernel's tail; from here on
+  // global memory is read and written.  The successor may start its own set-up now: every CTA of this grid is resident.
+  pdl_wait();
+  pdl_launch_dependents();
   const uint32_t tmem_base = *tmem_slot;
   const int tiles_img = a.tiles_x * a.tiles_y;
   const int n_mtiles = tiles_img * a.B;
@@ -414,6 +418,8 @@ struct DfbConv {
   size_t wimg_bytes = 0;
   uint8_t* wimg = nullptr;
   uint8_t* wimg2 = nullptr;  // the same filter in the cta_group::2 layout: every stage split into the two CTAs' row halves
+  CUtensorMap tmap2;         // tensor map over wimg2 (encoded on first use; the image is re-packed in place, never moved)
+  bool tmap2_valid = false;
   float* bias = nullptr;
   int num_sms = 0;
 };
@@ -692,7 +698,33 @@ extern "C" int dfb_conv_fwd(DfbConv* c, const void* in_nhwc16, int B, int H, int
 }
 
 // 5-D tensor map over the NHWC 16-bit input for the patch loads of k_conv_tc (see ConvArgs::tmap_in).
+// Encoding a tensor map costs 2-3 us on the host - a third of an asynchronous launch through this ABI - and a training
+// step launches the same convolutions on the same (persistent) buffers every time: the maps are kept in a small
+// direct-mapped cache keyed by everything that determines them (a map depends on nothing else, so entries never go stale).
+namespace {
+struct TmapKey { const void* in; int B, H, W, Cpad, PH, PW, np; };
+struct TmapEntry { TmapKey k; CUtensorMap m; bool valid; };
+thread_local TmapEntry g_tmap_cache[64];
+}  // namespace
+
+static int make_patch_tmap_uncached(const void* in, int B, int H, int W, int Cpad, int PH, int PW, CUtensorMap* out, int npanels);
+
 int dfb::make_patch_tmap(const void* in, int B, int H, int W, int Cpad, int PH, int PW, CUtensorMap* out, int npanels) {
+  const TmapKey k = {in, B, H, W, Cpad, PH, PW, npanels};
+  uint64_t hsh = (uint64_t)(uintptr_t)in * 0x9E3779B97F4A7C15ull;
+  hsh ^= ((uint64_t)B << 40) ^ ((uint64_t)H << 28) ^ ((uint64_t)W << 16) ^ ((uint64_t)Cpad << 6) ^ ((uint64_t)PH << 3) ^ (uint64_t)PW ^ ((uint64_t)npanels << 50);
+  TmapEntry& e = g_tmap_cache[(hsh >> 20) & 63];
+  if (e.valid && memcmp(&e.k, &k, sizeof(k)) == 0) {
+    *out = e.m;
+    return DFB_OK;
+  }
+  const int rc = make_patch_tmap_uncached(in, B, H, W, Cpad, PH, PW, out, npanels);
+  if (rc) return rc;
+  e.k = k, e.m = *out, e.valid = true;
+  return DFB_OK;
+}
+
+static int make_patch_tmap_uncached(const void* in, int B, int H, int W, int Cpad, int PH, int PW, CUtensorMap* out, int npanels) {
   static PFN_cuTensorMapEncodeTiled encode = nullptr;
   if (!encode) {
     void* fn = nullptr;
@@ -766,8 +798,12 @@ int dfb_conv_run(DfbConv* c, const void* in_nhwc16, int B, int H, int W, int rel
   DFB_REQUIRE(smem <= 232448, DFB_ERR_UNSUPPORTED, "shared memory budget exceeded");
   if (cg == 2) {
     a.wimg = c->wimg2;
-    const int rc = make_weight_tmap(c->wimg2, c->wimg_bytes, &a.tmap);
-    if (rc) return rc;
+    if (!c->tmap2_valid) {
+      const int rc = make_weight_tmap(c->wimg2, c->wimg_bytes, &c->tmap2);
+      if (rc) return rc;
+      c->tmap2_valid = true;
+    }
+    a.tmap = c->tmap2;
   }
   {
     const int rc = make_patch_tmap(in_nhwc16, B, H, W, c->Cin_pad, a.PH, a.PW, &a.tmap_in);
@@ -777,14 +813,21 @@ int dfb_conv_run(DfbConv* c, const void* in_nhwc16, int B, int H, int W, int rel
     DFB_CHECK_CUDA(cudaMemsetAsync(g_conv_prof, 0, 512 * 8 * sizeof(unsigned long long), (cudaStream_t)stream));
     a.prof = g_conv_prof, g_conv_prof_grid = grid;
   }
-  auto launch = [&](auto kern) -> int {
-    DFB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, conv::kThreads, smem, (cudaStream_t)stream>>>(a);
+  // the four variants share one function-pointer type, so the "attribute already set" flag is per variant, not per lambda
+  auto launch = [&](auto kern, int variant) -> int {
+    static thread_local uint64_t attr_set[4] = {0, 0, 0, 0};   // bit d: set on device d (the attribute is per device)
+    int dev = 0;
+    DFB_CHECK_CUDA(cudaGetDevice(&dev));
+    if (!((attr_set[variant] >> (dev & 63)) & 1)) {
+      DFB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+      attr_set[variant] |= 1ull << (dev & 63);
+    }
+    DFB_CHECK_CUDA(dfb_launch_pdl(kern, dim3(grid), dim3(conv::kThreads), smem, (cudaStream_t)stream, true, a));
     DFB_LAUNCH_CHECK();
     return DFB_OK;
   };
-  if (cg == 2) return c->fmt ? launch(conv::k_conv_tc2<__nv_bfloat16>) : launch(conv::k_conv_tc2<__half>);
-  return c->fmt ? launch(conv::k_conv_tc<__nv_bfloat16>) : launch(conv::k_conv_tc<__half>);
+  if (cg == 2) return c->fmt ? launch(conv::k_conv_tc2<__nv_bfloat16>, 3) : launch(conv::k_conv_tc2<__half>, 2);
+  return c->fmt ? launch(conv::k_conv_tc<__nv_bfloat16>, 1) : launch(conv::k_conv_tc<__half>, 0);
 }
 
 extern "C" int dfb_conv_create_ex(int Cin, int Cout, int KH, int KW, const float* weight, const float* bias, const float* bn_scale,

@@ -7,6 +7,8 @@
 //                     float image when df != 1); also feature/direct_feature_matching.py:149
 //   k_pose_error      script/feature/misc.py:49-107 (compute_error_in_q: SVD-orthogonalised rotation, quaternions,
 //                     angular error in degrees, translation error)
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace dfb {
@@ -304,3 +306,44 @@ extern "C" int dfb_polar3x3_bwd(const double* aux, const float* G, int n, float*
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }
+
+// ---- batched strided copy ------------------------------------------------------------------------------------------------
+// Every parameter of a network goes into its padded fp32 staging tensor before the weight images are re-packed (the NeRF-W
+// trainer re-loads 13 / 18 layers per optimizer step).  Done with one tensor.copy_ per weight and bias that was 60+ launches
+// of 1-2 us with ~8 us of host time each; here the whole list is one launch: block = (item, row range), thread = column.
+namespace {
+constexpr int kMaxCopy = 96;
+struct CopyBatchArgs {
+  DfbCopy2d it[kMaxCopy];
+  int n;
+};
+__global__ void __launch_bounds__(256) k_copy2d_batch(const __grid_constant__ CopyBatchArgs b) {
+  const DfbCopy2d& c = b.it[blockIdx.x];
+  const int64_t total = (int64_t)c.rows * c.cols;
+  for (int64_t i = (int64_t)blockIdx.y * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.y * 256) {
+    const int r = (int)(i / c.cols), col = (int)(i - (int64_t)r * c.cols);
+    c.dst[(int64_t)r * c.dst_ld + col] = c.src[(int64_t)r * c.src_ld + col];
+  }
+}
+}  // namespace
+
+extern "C" int dfb_copy2d_batch(const DfbCopy2d* items, int n, void* stream) {
+  DFB_REQUIRE(n >= 0 && (items || n == 0), DFB_ERR_INVALID, "dfb_copy2d_batch: bad arguments");
+  for (int i0 = 0; i0 < n; i0 += kMaxCopy) {
+    CopyBatchArgs b;
+    b.n = std::min(kMaxCopy, n - i0);
+    int64_t big = 1;
+    for (int i = 0; i < b.n; ++i) {
+      const DfbCopy2d& c = items[i0 + i];
+      DFB_REQUIRE(c.src && c.dst && c.rows >= 0 && c.cols >= 0 && c.src_ld >= c.cols && c.dst_ld >= c.cols, DFB_ERR_INVALID,
+                  "dfb_copy2d_batch: item %d is malformed", i0 + i);
+      b.it[i] = c;
+      big = std::max<int64_t>(big, (int64_t)c.rows * c.cols);
+    }
+    const int gy = (int)std::min<int64_t>(32, (big + 2047) / 2048);
+    k_copy2d_batch<<<dim3(b.n, gy), 256, 0, (cudaStream_t)stream>>>(b);
+    DFB_LAUNCH_CHECK();
+  }
+  return DFB_OK;
+}
+

@@ -186,6 +186,14 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while
+// its predecessor in the stream is still running; it must not touch global memory before pdl_wait(), which returns once
+// the predecessor has completed and its writes are visible.  pdl_launch_dependents() lets the SUCCESSOR start early.  Both
+// are no-ops in a kernel launched the ordinary way.  The layer kernels of the training executors are 8-10 us long with a
+// fixed 3-4 us of launch latency + barrier / TMEM set-up that this overlaps with the predecessor's tail.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");

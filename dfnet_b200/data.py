@@ -7,7 +7,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import check, lib
+from ._lib import check, lib, raw_stream
 
 
 def _p(t):
@@ -15,7 +15,7 @@ def _p(t):
 
 
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return raw_stream()
 
 
 def image_histogram(img, hist_bin=10):

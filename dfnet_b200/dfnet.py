@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import check, lib
+from ._lib import check, lib, raw_stream
 
 _VGG16_CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512, "M"]
 _TAP_CHANNELS = {"conv1_2": 64, "conv3_3": 256, "conv5_3": 512}
@@ -139,7 +139,7 @@ class _DfnetHandle:
         def p(t):
             return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
         check(lib.dfb_dfnet_fwd(self._h, p(x), B, H, W, flags, upH, upW, p(ft), p(fr), p(pose), p(ws),
-                                ws.numel(), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+                                ws.numel(), raw_stream()))
         if tape:
             self.last_tape = (ws, flags, (B, H, W, upH, upW))  # debug: tests read the stored activations back
             return ft, fr, pose, (ws, flags)
@@ -148,7 +148,7 @@ class _DfnetHandle:
     def bn_batch_stats(self, device):
         """[L,2,128]: batch mean and biased variance of every head's BatchNorm input in the last bn_train forward."""
         out = torch.empty(self.n_levels, 2, 128, device=device)
-        check(lib.dfb_dfnet_bn_batch_stats(self._h, C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        check(lib.dfb_dfnet_bn_batch_stats(self._h, C.c_void_p(out.data_ptr()), raw_stream()))
         return out
 
     def tape_activations(self):
@@ -211,7 +211,7 @@ class _DfnetHandle:
             check(lib.dfb_dfnet_bwd_bucket_event(self._h, 7, C.c_void_p(self._bucket_ev.cuda_event)))
         check(lib.dfb_dfnet_bwd(self._h, B, H, W, flags, upH, upW, p(g_ft), p(g_fr), level_mask, p(g_pose), p(ws), p(gx_sub),
                                 ptrs, 0 if grads is None else len(grads), p(self._bwd_ws), self._bwd_ws.numel(),
-                                C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+                                raw_stream()))
         if sync is not None:
             check(lib.dfb_dfnet_bwd_bucket_event(self._h, 0, None))
             sync.launch(flat, sum(sizes[:14]), self._bucket_ev)
@@ -381,7 +381,7 @@ class _CosineLossFn(torch.autograd.Function):
         ws = torch.empty(max(Cc * 64 * 3, (HW + 255) // 256), device=a.device)
         check(lib.dfb_cosine_loss(C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), Cc, HW, int(bool(per_channel)), 1e-6,
                                   C.c_void_p(loss.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel() * 4,
-                                  C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+                                  raw_stream()))
         ctx.save_for_backward(a, b)
         ctx.per_channel = bool(per_channel)
         return loss
@@ -396,7 +396,7 @@ class _CosineLossFn(torch.autograd.Function):
         ws = torch.empty(Cc * 64 * 3, device=a.device)
         check(lib.dfb_cosine_loss_bwd(C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), Cc, HW, int(ctx.per_channel), 1e-6,
                                       C.c_void_p(g.data_ptr()), C.c_void_p(ga.data_ptr()), C.c_void_p(ws.data_ptr()),
-                                      ws.numel() * 4, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+                                      ws.numel() * 4, raw_stream()))
         return ga, None, None  # the target stream is a constant of the step (its inputs carry no gradient)
 
 
@@ -416,7 +416,7 @@ def feature_loss(feature_rgb, feature_target, img_in=True, per_channel=False):
     ws = torch.empty(max(Cc * 64 * 3, (HW + 255) // 256), device=fr.device)
     check(lib.dfb_cosine_loss(C.c_void_p(fr.data_ptr()), C.c_void_p(ft.data_ptr()), Cc, HW, int(bool(per_channel)), 1e-6,
                               C.c_void_p(loss.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel() * 4,
-                              C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+                              raw_stream()))
     return loss
 
 

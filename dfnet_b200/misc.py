@@ -6,7 +6,7 @@ import math
 import torch
 
 from . import _lib
-from ._lib import check, lib
+from ._lib import check, lib, raw_stream
 
 
 def _p(t):
@@ -14,7 +14,7 @@ def _p(t):
 
 
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return raw_stream()
 
 
 def _triplet_fwd(a, b, margin):

@@ -16,15 +16,28 @@ import ctypes as C
 import torch
 
 from . import _lib, ops
-from ._lib import check, lib
+from ._lib import Copy2d, check, lib, raw_stream
 
 
 def _p(t):
-    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+    # a plain int / None converts to the ABI's void* through argtypes; cheaper than building a c_void_p per argument
+    return t.data_ptr() if t is not None else None
 
 
 def _st():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return raw_stream()
+
+
+def _copy_table(items):
+    """ctypes table of DfbCopy2d items (src, dst, rows, cols, src_ld, dst_ld)."""
+    tbl = (Copy2d * len(items))()
+    for k, it in enumerate(items):
+        tbl[k] = Copy2d(*it)
+    return tbl
+
+
+def _copy_batch(tbl):
+    check(lib.dfb_copy2d_batch(tbl, len(tbl), _st()))
 
 
 class _Layer:
@@ -44,14 +57,29 @@ class _Layer:
             check(lib.dfb_conv_create_ex(cin, self.cout_pad, 1, 1, _p(self.w), None, None, None, 1, 1, C.byref(self.dg)))
         self.dg_out = (cin + 63) // 64 * 64                        # channels of the data gradient's output
 
-    def load(self, w, b):
-        """w [cout, cin] (a parameter or a column slice of one), b [cout] or None."""
-        self.w[: self.cout].copy_(w.detach())
+    def stage(self, items, w, b, row0=0):
+        """Queue the copies of w [rows, cols] (a parameter or a column slice of one; cols <= cin, the rest of the staging
+        row stays zero) and b [rows] or None into the padded staging tensors, from row `row0` on."""
+        w = w.detach()
+        assert w.dtype == torch.float32 and w.stride(1) == 1 and row0 + w.shape[0] <= self.cout_pad and w.shape[1] <= self.cin
+        items.append((w.data_ptr(), self.w.data_ptr() + 4 * row0 * self.cin, w.shape[0], w.shape[1], w.stride(0), self.cin))
         if b is not None:
-            self.b[: self.cout].copy_(b.detach())
+            b = b.detach()
+            assert b.dtype == torch.float32 and b.is_contiguous()
+            items.append((b.data_ptr(), self.b.data_ptr() + 4 * row0, 1, b.shape[0], b.shape[0], b.shape[0]))
+
+    def update(self):
+        """Re-pack the weight images from the staging tensors (queued while a dfb_conv_pack_begin batch is open)."""
         check(lib.dfb_conv_update(self.fwd, _p(self.w), _p(self.b), None, None, _st()))
         if self.dg is not None:
             check(lib.dfb_conv_update(self.dg, _p(self.w), None, None, None, _st()))
+
+    def load(self, w, b):
+        """w [cout, cin] (a parameter or a column slice of one), b [cout] or None (one layer, outside a refresh)."""
+        items = []
+        self.stage(items, w, b)
+        _copy_batch(_copy_table(items))
+        self.update()
 
     def __del__(self):
         try:
@@ -99,6 +127,7 @@ class NetTrainer:
                 self.L[f"t{k}"] = _Layer(H2, H2, dev)
             self.L["th"] = _Layer(H2, 5, dev)                        # transient rgb(3), sigma, beta
         self._versions = None
+        self._copy_tbl = None  # (parameter pointers, DfbCopy2d table of the parameter -> staging copies)
         self._bufs = {}
         self._live = False     # a tape of this executor is waiting for its backward
 
@@ -111,38 +140,45 @@ class NetTrainer:
         v = [(p.data_ptr(), p._version) for p in n.parameters()]
         if v == self._versions:
             return
-        # every layer's (re)packing request of this load goes out as ONE launch (the staging tensors stay untouched until
-        # dfb_conv_pack_end); launched one by one they were 116 launches per training step
+        # parameters -> padded staging tensors as ONE batched strided copy (the table is rebuilt only when a parameter has
+        # moved), then every layer's (re)packing request as ONE launch (the staging tensors stay untouched until
+        # dfb_conv_pack_end).  Issued tensor by tensor this was ~70 copies and 116 packing launches per training step.
+        ptrs = tuple(pv[0] for pv in v)
+        if self._copy_tbl is None or self._copy_tbl[0] != ptrs:
+            items = []
+            self._stage_layers(n, items)
+            self._copy_tbl = (ptrs, _copy_table(items))
+        _copy_batch(self._copy_tbl[1])
         check(lib.dfb_conv_pack_begin())
         try:
-            self._load_layers(n)
+            for layer in self.L.values():
+                layer.update()
         finally:
             check(lib.dfb_conv_pack_end(_st()))
         self._versions = v
 
-    def _load_layers(self, n):
+    def _stage_layers(self, n, items):
         W = self.W
         for i in range(8):
             lin = getattr(n, f"xyz_encoding_{i + 1}")[0]
-            if i == 0:
-                w = torch.nn.functional.pad(lin.weight, (0, 1))      # 63 -> 64 input columns
-            elif i == 4:
-                w = lin.weight[:, 63:]
-                self.L["xpe"].load(torch.nn.functional.pad(lin.weight[:, :63], (0, 1)), None)
+            if i == 4:
+                self.L["xpe"].stage(items, lin.weight[:, :63], None)     # 63 of 64 staging columns, the last stays zero
+                self.L["x4"].stage(items, lin.weight[:, 63:], lin.bias)
             else:
-                w = lin.weight
-            self.L[f"x{i}"].load(w, lin.bias)
-        self.L["sigma"].load(n.static_sigma[0].weight, n.static_sigma[0].bias)
-        self.L["final"].load(n.xyz_encoding_final.weight, n.xyz_encoding_final.bias)
-        self.L["dir"].load(n.dir_encoding[0].weight[:, :W], n.dir_encoding[0].bias)
-        self.L["rgb"].load(n.static_rgb[0].weight, n.static_rgb[0].bias)
+                self.L[f"x{i}"].stage(items, lin.weight, lin.bias)       # layer 0: 63 of 64 columns
+        self.L["sigma"].stage(items, n.static_sigma[0].weight, n.static_sigma[0].bias)
+        self.L["final"].stage(items, n.xyz_encoding_final.weight, n.xyz_encoding_final.bias)
+        self.L["dir"].stage(items, n.dir_encoding[0].weight[:, :W], n.dir_encoding[0].bias)
+        self.L["rgb"].stage(items, n.static_rgb[0].weight, n.static_rgb[0].bias)
         if self.fine:
             te = n.transient_encoding
-            self.L["t0"].load(te[0].weight[:, :W], te[0].bias)
+            self.L["t0"].stage(items, te[0].weight[:, :W], te[0].bias)
             for k, idx in ((1, 2), (2, 4), (3, 6)):
-                self.L[f"t{k}"].load(te[idx].weight, te[idx].bias)
-            self.L["th"].load(torch.cat([n.transient_rgb[0].weight, n.transient_sigma[0].weight, n.transient_beta[0].weight], 0),
-                              torch.cat([n.transient_rgb[0].bias, n.transient_sigma[0].bias, n.transient_beta[0].bias], 0))
+                self.L[f"t{k}"].stage(items, te[idx].weight, te[idx].bias)
+            row = 0
+            for head in (n.transient_rgb[0], n.transient_sigma[0], n.transient_beta[0]):   # rows 0..2 | 3 | 4 of one layer
+                self.L["th"].stage(items, head.weight, head.bias, row0=row)
+                row += head.weight.shape[0]
 
     # ---- buffers ----------------------------------------------------------------------------------------------------
     def begin(self):
@@ -396,10 +432,11 @@ class _CompositeFn(torch.autograd.Function):
 
 
 def _embed(x, L):
-    out = [x]
-    for l in range(L):
-        out += [torch.sin(x * 2.0 ** l), torch.cos(x * 2.0 ** l)]
-    return torch.cat(out, -1)
+    """[x, sin(x 2^0), cos(x 2^0), ..., sin(x 2^(L-1)), cos(x 2^(L-1))] along the last axis (models/nerfw.py Embedding with
+    log-spaced bands), all bands in one pass: 5 launches instead of 4 L + 1, same values element for element."""
+    xb = x[..., None, :] * (2.0 ** torch.arange(L, device=x.device, dtype=x.dtype))[:, None]      # [..., L, C]
+    sc = torch.stack([torch.sin(xb), torch.cos(xb)], -2)                                            # [..., L, 2, C]
+    return torch.cat([x, sc.reshape(*x.shape[:-1], -1)], -1)
 
 
 def render_rays_train(ray_batch, network_fn, network_fine, embedding_a, embedding_t, N_samples, N_importance, perturb=0.,

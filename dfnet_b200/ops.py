@@ -5,7 +5,7 @@ import weakref
 import torch
 
 from . import _lib
-from ._lib import lib, check
+from ._lib import lib, check, raw_stream
 
 
 def _require_cuda(t, name):
@@ -22,7 +22,7 @@ def _ptr(t):
 
 
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return raw_stream()
 
 
 def linspace(start, end, steps):

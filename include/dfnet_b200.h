@@ -426,6 +426,15 @@ int dfb_pose_error(const float* pred, const float* gt, int n, int use_svd, float
  * its status on the host), and its adjoint G [n,9] -> dA [n,9].  aux [n,21] doubles = U | V | s, written by the forward. */
 int dfb_polar3x3_fwd(const float* A, int n, float* Q, double* aux, void* stream);
 int dfb_polar3x3_bwd(const double* aux, const float* G, int n, float* dA, void* stream);
+/* n strided fp32 copies dst[r*dst_ld + c] = src[r*src_ld + c] (r < rows, c < cols) in one launch: the parameter ->
+ * padded staging step of the NeRF-W training executor (what `param.data.copy_` does per tensor in the reference's
+ * optimizer loop has no counterpart there; this replaces the host-side python copies of dfnet_b200/nerf_train.py). */
+typedef struct DfbCopy2d {
+  const float* src;
+  float* dst;
+  int rows, cols, src_ld, dst_ld;
+} DfbCopy2d;
+int dfb_copy2d_batch(const DfbCopy2d* items, int n, void* stream);
 
 #ifdef __cplusplus
 }

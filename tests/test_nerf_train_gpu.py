@@ -182,3 +182,50 @@ def test_train_on_batch_nerfw_loop_body():
         losses.append(float(loss))
     assert np.isfinite(losses).all() and losses[-1] < losses[0] and torch.isfinite(psnr)
     assert abs(opt.param_groups[0]["lr"] - args.lrate * 0.1 ** (11 / 5000)) < 1e-12
+
+
+def test_copy2d_batch_vs_torch_copies():
+    """dfb_copy2d_batch (parameters -> padded staging, one launch): column slices, row offsets, 1-row biases, > 96 items
+    (two launches), an empty item; bit-exact against tensor.copy_ and nothing outside the rectangles is touched."""
+    from dfnet_b200._lib import Copy2d, check, lib
+    gen = torch.Generator().manual_seed(3)
+    items, pairs = [], []
+    for k in range(130):
+        R, Cs, Cd = int(torch.randint(1, 70, (1,), generator=gen)), int(torch.randint(8, 300, (1,), generator=gen)), 0
+        cols = int(torch.randint(0 if k == 7 else 1, Cs + 1, (1,), generator=gen))
+        c0 = int(torch.randint(0, Cs - cols + 1, (1,), generator=gen))
+        Cd = cols + int(torch.randint(0, 9, (1,), generator=gen))
+        src = torch.randn(R, Cs, generator=gen).to(dev())
+        dst = torch.full((R + 3, Cd), -7.0, device=dev())
+        want = dst.clone()
+        want[2:2 + R, :cols] = src[:, c0:c0 + cols]
+        view = src[:, c0:c0 + cols]
+        items.append((view.data_ptr() if cols else src.data_ptr(), dst.data_ptr() + 4 * 2 * Cd, R, cols, Cs, Cd))
+        pairs.append((dst, want, src))
+    tbl = (Copy2d * len(items))(*[Copy2d(*it) for it in items])
+    check(lib.dfb_copy2d_batch(tbl, len(items), None))
+    torch.cuda.synchronize()
+    for dst, want, _ in pairs:
+        assert torch.equal(dst, want)
+
+
+def test_trainer_refresh_tracks_parameter_updates():
+    """The executor's staged copy of the parameters follows in-place optimizer updates (version counters) and the cached
+    copy table survives them: forward after `p.add_` equals a fresh executor's forward on the same values."""
+    from dfnet_b200 import nerf_train, nerfw
+    mods = [m.to(dev()) for m in nerfw.make_synthetic_nerf(D=8, W=128, fine=True)]
+    fine = mods[1]
+    tr = nerf_train.NetTrainer(fine)
+    P = 64
+    pe = (torch.randn(P, 64, device=dev()) * 0.5).half()
+    rb_d, rb_t = torch.randn(8, 64, device=dev()) * 0.1, torch.randn(8, 64, device=dev()) * 0.1
+    with torch.no_grad():
+        raw0, _ = tr.forward(pe, P, rb_d, rb_t, 8)
+        raw0 = raw0.clone()
+        tr._live = False
+        for p in fine.parameters():
+            p.add_(0.01 * torch.randn_like(p))
+        raw1, _ = tr.forward(pe, P, rb_d, rb_t, 8)
+        raw2, _ = nerf_train.NetTrainer(fine).forward(pe, P, rb_d, rb_t, 8)
+    assert (raw1 - raw0).abs().max() > 1e-4
+    assert torch.equal(raw1, raw2)
