@@ -92,6 +92,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_wgrad(const __grid_constan
   if (t0 >= t1) return;  // uniform per CTA
 
   if (tid == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&a.tmap_g)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&a.tmap_x)) : "memory");
     for (int i = 0; i < kMaxStages; ++i) mbar_init(bar(FULL + i), 1), mbar_init(bar(EMPTY + i), 1);
     mbar_init(bar(DONE), 1);
     fence_barrier_init();

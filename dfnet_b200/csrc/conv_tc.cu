@@ -208,6 +208,9 @@ __device__ __forceinline__ void conv_tc_body(const ConvArgs& a) {
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
 
   if (tid == 0) {
+    // descriptor fetches overlap the set-up (and, under programmatic dependent launch, the previous kernel's tail)
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&a.tmap_in)) : "memory");
+    if (CG == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&a.tmap)) : "memory");
     for (int i = 0; i < kAStages; ++i) mbar_init(bar(A_FULL + i), 1), mbar_init(bar(A_EMPTY + i), 1);
     for (int i = 0; i < NB; ++i) mbar_init(bar(B_FULL2 + i), 1), mbar_init(bar(B_EMPTY2 + i), 1);
     for (int i = 0; i < 2; ++i) mbar_init(bar(D_FULL2 + i), 1), mbar_init(bar(D_EMPTY2 + i), 128 * CG);

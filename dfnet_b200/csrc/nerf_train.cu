@@ -19,27 +19,42 @@
 
 namespace dfb {
 
-__global__ void __launch_bounds__(128) k_embed_xyz16(const float* __restrict__ rays, int ray_stride, const float* __restrict__ z,
-                                                     int64_t P, int S, int L, int ld, __half* __restrict__ out) {
-  const int64_t g = (int64_t)blockIdx.x * 128 + threadIdx.x;
+// Eight threads per sample, one 16-byte store each (a warp writes 512 contiguous bytes; the first version had one thread
+// per sample writing its 64 halves one at a time, 128 bytes apart from its neighbours: 115 us for 25 MB).  out_bf (nullable):
+// the same values as bf16 - the operand type of the first layer's weight gradient - instead of a separate conversion pass.
+__global__ void __launch_bounds__(256) k_embed_xyz16(const float* __restrict__ rays, int ray_stride, const float* __restrict__ z,
+                                                     int64_t P, int S, int L, int ld, __half* __restrict__ out,
+                                                     __nv_bfloat16* __restrict__ out_bf) {
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int per = ld >> 3;                  // 16-byte chunks per sample
+  const int64_t g = t / per;
   if (g >= P) return;
+  const int c0 = (int)(t - g * per) * 8;
   const float* r = rays + (g / S) * ray_stride;
   const float zz = z[g];
   float pt[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) pt[c] = __fadd_rn(r[c], __fmul_rn(r[3 + c], zz));
-  __half* o = out + g * ld;
-  for (int c = 0; c < 3; ++c) o[c] = __float2half_rn(pt[c]);
-  for (int l = 0; l < L; ++l) {
-    const float fr = (float)(1 << l);
-    for (int c = 0; c < 3; ++c) {
+  const int n_ch = 3 + 6 * L;
+  __align__(16) __half h[8];
+  __align__(16) __nv_bfloat16 hb[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = c0 + e;
+    float v = 0.f;
+    if (c < 3) {
+      v = pt[c];
+    } else if (c < n_ch) {
+      const int q = c - 3, l = q / 6, rr = q - 6 * l, comp = rr >= 3 ? rr - 3 : rr;
       float sn, cs;
-      sincosf(__fmul_rn(pt[c], fr), &sn, &cs);
-      o[3 + 6 * l + c] = __float2half_rn(sn);
-      o[3 + 6 * l + 3 + c] = __float2half_rn(cs);
+      sincosf(__fmul_rn(pt[comp], (float)(1 << l)), &sn, &cs);
+      v = rr >= 3 ? cs : sn;
     }
+    h[e] = __float2half_rn(v);
+    hb[e] = __float2bfloat16_rn(__half2float(h[e]));
   }
-  for (int c = 3 + 6 * L; c < ld; ++c) o[c] = __float2half_rn(0.f);
+  *reinterpret_cast<uint4*>(out + g * ld + c0) = *reinterpret_cast<const uint4*>(h);
+  if (out_bf) *reinterpret_cast<uint4*>(out_bf + g * ld + c0) = *reinterpret_cast<const uint4*>(hb);
 }
 
 // out[p, c] = fp16(rb[ray(p), c])
@@ -88,32 +103,35 @@ __global__ void __launch_bounds__(256) k_heads_fwd(const float* __restrict__ sig
 
 // d raw -> d pre-activation as bf16 NHWC [P, 64] operands (columns past the head's width are zero):
 // g_sig[:,0]; g_rgb[:,0:3]; g_tr[:,0:5] = transient rgb(3), sigma, beta
+// Eight threads per sample: thread j writes the 16-byte chunk j of each [P, 64] row (a warp stores 512 contiguous bytes per
+// array); chunk 0 carries the values, the others are zeros.  (One thread per sample writing its 3 x 64 elements one by one
+// took 372 us for the fine pass of a 1536-ray step, 75 MB.)
 __global__ void __launch_bounds__(256) k_heads_bwd(const float* __restrict__ raw, const float* __restrict__ g_raw, int64_t P, int C,
                                                    __nv_bfloat16* __restrict__ g_sig, __nv_bfloat16* __restrict__ g_rgb,
                                                    __nv_bfloat16* __restrict__ g_tr) {
-  const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t p = t >> 3;
   if (p >= P) return;
-  const float* o = raw + p * C;
-  const float* g = g_raw + p * C;
-  float v[9];
-  for (int c = 0; c < 3; ++c) v[c] = g[c] * o[c] * (1.f - o[c]);
-  v[3] = g[3] * (1.f - expf(-o[3]));
-  if (C == 9) {
-    for (int c = 4; c < 7; ++c) v[c] = g[c] * o[c] * (1.f - o[c]);
-    v[7] = g[7] * (1.f - expf(-o[7]));
-    v[8] = g[8] * (1.f - expf(-o[8]));
-  }
+  const int j = (int)(t & 7);
   const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
-  __nv_bfloat16* a = g_sig + p * 64;
-  __nv_bfloat16* b = g_rgb + p * 64;
-  for (int c = 0; c < 64; ++c) a[c] = zero, b[c] = zero;
-  a[0] = __float2bfloat16_rn(v[3]);
-  for (int c = 0; c < 3; ++c) b[c] = __float2bfloat16_rn(v[c]);
-  if (C == 9) {
-    __nv_bfloat16* t = g_tr + p * 64;
-    for (int c = 0; c < 64; ++c) t[c] = zero;
-    for (int c = 0; c < 5; ++c) t[c] = __float2bfloat16_rn(v[4 + c]);
+  __align__(16) __nv_bfloat16 a[8], b[8], tr[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) a[c] = zero, b[c] = zero, tr[c] = zero;
+  if (j == 0) {
+    const float* o = raw + p * C;
+    const float* g = g_raw + p * C;
+    for (int c = 0; c < 3; ++c) b[c] = __float2bfloat16_rn(g[c] * o[c] * (1.f - o[c]));
+    a[0] = __float2bfloat16_rn(g[3] * (1.f - expf(-o[3])));
+    if (C == 9) {
+      for (int c = 4; c < 7; ++c) tr[c - 4] = __float2bfloat16_rn(g[c] * o[c] * (1.f - o[c]));
+      tr[3] = __float2bfloat16_rn(g[7] * (1.f - expf(-o[7])));
+      tr[4] = __float2bfloat16_rn(g[8] * (1.f - expf(-o[8])));
+    }
   }
+  const int64_t off = p * 64 + j * 8;
+  *reinterpret_cast<uint4*>(g_sig + off) = *reinterpret_cast<const uint4*>(a);
+  *reinterpret_cast<uint4*>(g_rgb + off) = *reinterpret_cast<const uint4*>(b);
+  if (C == 9) *reinterpret_cast<uint4*>(g_tr + off) = *reinterpret_cast<const uint4*>(tr);
 }
 
 // One thread per ray.  C == 9 (fine, train mode): loss inputs rgb = sum T (a_s c_s + a_t c_t), beta = sum T a_t b + beta_min,
@@ -173,6 +191,131 @@ __global__ void __launch_bounds__(128) k_raw2outputs_bwd(const float* __restrict
   }
 }
 
+// The same adjoint with one WARP per ray (S <= 256): lane l owns the K = ceil(S / 32) consecutive samples from l K on.  The
+// transmittance is an exclusive prefix product (per-lane products, then a shuffle scan), the backward recurrence
+// R_j = E_{j+1} + ea_{j+1} R_{j+1} a suffix scan of affine maps (A, B): R -> B + A R; both in double like the sequential
+// version, whose results this reproduces up to the association of those products.  A ray's raw / g_raw are contiguous and
+// every lane reads and writes a contiguous piece.  (One thread per ray: 1536 threads on the whole GPU, every load a
+// dependent, uncoalesced one - 330 us for the fine pass of a 1536-ray step; this one is ~10x faster.)
+template <int C>
+__global__ void __launch_bounds__(128) k_raw2outputs_bwd_warp(const float* __restrict__ raw, const float* __restrict__ z, int64_t N, int S,
+                                                              const float* __restrict__ noise, float noise_std,
+                                                              const float* __restrict__ g_rgb, const float* __restrict__ g_beta,
+                                                              const float* __restrict__ g_tsig, float* __restrict__ g_raw) {
+  constexpr unsigned kFull = 0xffffffffu;
+  constexpr int kMaxK = 8;
+  const int64_t ray = ((int64_t)blockIdx.x * 128 + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (ray >= N) return;   // uniform per warp
+  const int K = (S + 31) >> 5;
+  const int i0 = lane * K;
+  const float* rw = raw + ray * S * C;
+  const float* zz = z + ray * S;
+  float* go = g_raw + ray * S * C;
+  const float g0 = g_rgb ? g_rgb[ray * 3] : 0.f, g1 = g_rgb ? g_rgb[ray * 3 + 1] : 0.f, g2 = g_rgb ? g_rgb[ray * 3 + 2] : 0.f;
+  const float gb = g_beta ? g_beta[ray] : 0.f;
+  float dl[kMaxK], Ti[kMaxK];
+  // pass 1: transmittance in front of every sample
+  double prod = 1.0;
+#pragma unroll
+  for (int k = 0; k < kMaxK; ++k) {
+    const int i = i0 + k;
+    if (k < K && i < S) {
+      const float d = (i + 1 < S) ? __fsub_rn(zz[i + 1], zz[i]) : 1e2f;
+      float a;
+      if (C == 9) a = 1.f - expf(-d * (rw[i * 9 + 3] + rw[i * 9 + 7]));
+      else a = 1.f - expf(-d * fmaxf(rw[i * C + 3] + (noise ? noise[ray * S + i] * noise_std : 0.f), 0.f));
+      dl[k] = d;
+      Ti[k] = __double2float_rn(prod);     // product of this lane's earlier samples, scaled by the lanes in front below
+      prod *= (double)(1.f - a);
+    } else {
+      dl[k] = 0.f, Ti[k] = 0.f;
+    }
+  }
+  double incl = prod;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const double o = __shfl_up_sync(kFull, incl, d);
+    if (lane >= d) incl *= o;
+  }
+  double excl = __shfl_up_sync(kFull, incl, 1);
+  if (lane == 0) excl = 1.0;
+  // (redo the per-lane products in double so that T_i = excl * prod_k is rounded once, like the sequential version)
+  {
+    double pk = 1.0;
+#pragma unroll
+    for (int k = 0; k < kMaxK; ++k) {
+      const int i = i0 + k;
+      if (k < K && i < S) {
+        float a;
+        if (C == 9) a = 1.f - expf(-dl[k] * (rw[i * 9 + 3] + rw[i * 9 + 7]));
+        else a = 1.f - expf(-dl[k] * fmaxf(rw[i * C + 3] + (noise ? noise[ray * S + i] * noise_std : 0.f), 0.f));
+        Ti[k] = (float)(excl * pk);
+        pk *= (double)(1.f - a);
+      }
+    }
+  }
+  // pass 2: this lane's affine map (applied back to front), suffix scan over the lanes, then the samples
+  float Ek[kMaxK], eak[kMaxK];
+  double A = 1.0, B = 0.0;
+#pragma unroll
+  for (int k = kMaxK - 1; k >= 0; --k) {
+    const int i = i0 + k;
+    Ek[k] = 0.f, eak[k] = 1.f;
+    if (k < K && i < S) {
+      const float d = dl[k];
+      if (C == 9) {
+        const float ss = rw[i * 9 + 3], st = rw[i * 9 + 7];
+        const float es = expf(-d * ss), et = expf(-d * st), ea = expf(-d * (ss + st));
+        const float gcs = g0 * rw[i * 9] + g1 * rw[i * 9 + 1] + g2 * rw[i * 9 + 2];
+        const float gct = g0 * rw[i * 9 + 4] + g1 * rw[i * 9 + 5] + g2 * rw[i * 9 + 6] + gb * rw[i * 9 + 8];
+        Ek[k] = (1.f - es) * gcs + (1.f - et) * gct, eak[k] = ea;
+      } else {
+        const float sg = fmaxf(rw[i * C + 3] + (noise ? noise[ray * S + i] * noise_std : 0.f), 0.f);
+        const float ea = expf(-d * sg);
+        const float gc = g0 * rw[i * C] + g1 * rw[i * C + 1] + g2 * rw[i * C + 2];
+        Ek[k] = (1.f - ea) * gc, eak[k] = ea;
+      }
+      B = (double)Ek[k] + (double)eak[k] * B;
+      A = (double)eak[k] * A;
+    }
+  }
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const double A2 = __shfl_down_sync(kFull, A, d), B2 = __shfl_down_sync(kFull, B, d);
+    if (lane + d < 32) B = B + A * B2, A = A * A2;
+  }
+  double R = __shfl_down_sync(kFull, B, 1);
+  if (lane == 31) R = 0.0;
+#pragma unroll
+  for (int k = kMaxK - 1; k >= 0; --k) {
+    const int i = i0 + k;
+    if (k < K && i < S) {
+      const float d = dl[k], T = Ti[k];
+      if (C == 9) {
+        const float ss = rw[i * 9 + 3], st = rw[i * 9 + 7];
+        const float es = expf(-d * ss), et = expf(-d * st), ea = eak[k];
+        const float as = 1.f - es, at = 1.f - et;
+        const float gcs = g0 * rw[i * 9] + g1 * rw[i * 9 + 1] + g2 * rw[i * 9 + 2];
+        const float gct = g0 * rw[i * 9 + 4] + g1 * rw[i * 9 + 5] + g2 * rw[i * 9 + 6] + gb * rw[i * 9 + 8];
+        const float dA = -T * (float)R;
+        go[i * 9 + 0] = g0 * as * T, go[i * 9 + 1] = g1 * as * T, go[i * 9 + 2] = g2 * as * T;
+        go[i * 9 + 4] = g0 * at * T, go[i * 9 + 5] = g1 * at * T, go[i * 9 + 6] = g2 * at * T;
+        go[i * 9 + 8] = gb * at * T;
+        go[i * 9 + 3] = d * (es * T * gcs + ea * dA);
+        go[i * 9 + 7] = d * (et * T * gct + ea * dA) + (g_tsig ? g_tsig[ray * S + i] : 0.f);
+      } else {
+        const float pre = rw[i * C + 3] + (noise ? noise[ray * S + i] * noise_std : 0.f);
+        const float ea = eak[k], a = 1.f - ea;
+        const float gc = g0 * rw[i * C] + g1 * rw[i * C + 1] + g2 * rw[i * C + 2];
+        go[i * C + 0] = g0 * a * T, go[i * C + 1] = g1 * a * T, go[i * C + 2] = g2 * a * T;
+        go[i * C + 3] = pre > 0.f ? d * ea * (T * gc - T * (float)R) : 0.f;
+      }
+      R = (double)Ek[k] + (double)eak[k] * R;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) k_cast_f16_bf16(const __half* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
   const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 2;
   if (i + 1 < n) {
@@ -187,15 +330,27 @@ __global__ void __launch_bounds__(256) k_cast_f16_bf16(const __half* __restrict_
 
 using namespace dfb;
 
-extern "C" int dfb_embed_xyz16(const float* rays, int ray_stride, const float* z, int64_t N, int S, int L, int ld, void* out,
-                               void* stream) {
-  DFB_REQUIRE(rays && z && out && N >= 0 && S >= 1 && L >= 0 && ray_stride >= 6, DFB_ERR_INVALID, "dfb_embed_xyz16: bad arguments");
+static int embed_xyz16_impl(const float* rays, int ray_stride, const float* z, int64_t N, int S, int L, int ld, void* out, void* out_bf16,
+                           void* stream) {
+  DFB_REQUIRE(rays && z && out && N >= 0 && S >= 1 && L >= 0 && L <= 20 && ray_stride >= 6, DFB_ERR_INVALID, "dfb_embed_xyz16: bad arguments");
   DFB_REQUIRE(ld >= 3 + 6 * L && ld % 8 == 0, DFB_ERR_INVALID, "dfb_embed_xyz16: ld must be a multiple of 8 and >= 3 + 6 L");
   const int64_t P = N * S;
   if (P == 0) return DFB_OK;
-  k_embed_xyz16<<<(unsigned)((P + 127) / 128), 128, 0, (cudaStream_t)stream>>>(rays, ray_stride, z, P, S, L, ld, (__half*)out);
+  const int64_t threads = P * (ld / 8);
+  k_embed_xyz16<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rays, ray_stride, z, P, S, L, ld, (__half*)out,
+                                                                                     (__nv_bfloat16*)out_bf16);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
+}
+
+extern "C" int dfb_embed_xyz16(const float* rays, int ray_stride, const float* z, int64_t N, int S, int L, int ld, void* out,
+                               void* stream) {
+  return embed_xyz16_impl(rays, ray_stride, z, N, S, L, ld, out, nullptr, stream);
+}
+
+extern "C" int dfb_embed_xyz16_ex(const float* rays, int ray_stride, const float* z, int64_t N, int S, int L, int ld, void* out,
+                                  void* out_bf16, void* stream) {
+  return embed_xyz16_impl(rays, ray_stride, z, N, S, L, ld, out, out_bf16, stream);
 }
 
 extern "C" int dfb_rows_expand16(const float* rb, int64_t N, int S, int C, void* out, void* stream) {
@@ -228,7 +383,7 @@ extern "C" int dfb_nerf_heads_bwd(const float* raw, const float* g_raw, int64_t 
                                   void* stream) {
   DFB_REQUIRE(raw && g_raw && g_sig16 && g_rgb16 && (C == 4 || (C == 9 && g_tr16)), DFB_ERR_INVALID, "dfb_nerf_heads_bwd: bad arguments");
   if (P == 0) return DFB_OK;
-  k_heads_bwd<<<(unsigned)((P + 255) / 256), 256, 0, (cudaStream_t)stream>>>(raw, g_raw, P, C, (__nv_bfloat16*)g_sig16,
+  k_heads_bwd<<<(unsigned)((P * 8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(raw, g_raw, P, C, (__nv_bfloat16*)g_sig16,
                                                                             (__nv_bfloat16*)g_rgb16, (__nv_bfloat16*)g_tr16);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
@@ -240,8 +395,16 @@ extern "C" int dfb_raw2outputs_bwd(const float* raw, const float* z_vals, int64_
   DFB_REQUIRE(raw && z_vals && g_raw && (C == 4 || C == 9), DFB_ERR_INVALID, "dfb_raw2outputs_bwd: raw must be [N,S,4] or [N,S,9]");
   DFB_REQUIRE(raw_noise_std == 0.f || (noise && C == 4), DFB_ERR_INVALID, "dfb_raw2outputs_bwd: noise applies to the coarse pass");
   if (N == 0) return DFB_OK;
-  k_raw2outputs_bwd<<<(unsigned)((N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(raw, z_vals, N, S, C, raw_noise_std != 0.f ? noise : nullptr,
-                                                                                  raw_noise_std, g_rgb, g_beta, g_tsig, g_raw);
+  const float* nz = raw_noise_std != 0.f ? noise : nullptr;
+  cudaStream_t st = (cudaStream_t)stream;
+  const char* seq = getenv("DFB_R2O_BWD_SEQ");   // =1: the one-thread-per-ray version (A/B, tests)
+  if (S <= 256 && !(seq && seq[0] == '1')) {
+    const unsigned blocks = (unsigned)((N * 32 + 127) / 128);
+    if (C == 9) k_raw2outputs_bwd_warp<9><<<blocks, 128, 0, st>>>(raw, z_vals, N, S, nz, raw_noise_std, g_rgb, g_beta, g_tsig, g_raw);
+    else k_raw2outputs_bwd_warp<4><<<blocks, 128, 0, st>>>(raw, z_vals, N, S, nz, raw_noise_std, g_rgb, g_beta, g_tsig, g_raw);
+  } else {
+    k_raw2outputs_bwd<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(raw, z_vals, N, S, C, nz, raw_noise_std, g_rgb, g_beta, g_tsig, g_raw);
+  }
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }

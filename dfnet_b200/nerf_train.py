@@ -196,7 +196,7 @@ class NetTrainer:
         return t
 
     # ---- forward ----------------------------------------------------------------------------------------------------
-    def forward(self, pe16, P, rb_dir, rb_t, S):
+    def forward(self, pe16, P, rb_dir, rb_t, S, twin=False, pe_bf=None):
         """pe16 [Pp, 64] fp16 (Pp = P rounded up to 8), rb_dir / rb_t [N, H2] fp32 per-ray pre-activation addends
         (rb_t: fine only) -> raw [P, 4 | 9] fp32 and the tape."""
         self.refresh()
@@ -207,9 +207,8 @@ class NetTrainer:
         N = rb_dir.shape[0]
         # with gradients wanted every activation that is a weight-gradient operand gets a bf16 twin from the same epilogue
         # (26 separate conversion launches per step otherwise)
-        twin = torch.is_grad_enabled()
         bfd = torch.bfloat16
-        tw = {}
+        tw = {} if pe_bf is None else {"pe": pe_bf}
 
         def bf(name, cols):
             if not twin:
@@ -388,8 +387,11 @@ class _MLPFn(torch.autograd.Function):
     module's parameters (the sample positions are constants: rays are data, depths are detached, rendering.py:302)."""
 
     @staticmethod
-    def forward(ctx, tr, pe16, P, S, rb_dir, rb_t, *params):
-        raw, tape = tr.forward(pe16, P, rb_dir.detach(), None if rb_t is None else rb_t.detach(), S)
+    def forward(ctx, tr, pe, P, S, rb_dir, rb_t, *params):
+        # grad mode is always off inside Function.forward: whether a backward will follow is what needs_input_grad says
+        pe16, pe_bf = pe
+        raw, tape = tr.forward(pe16, P, rb_dir.detach(), None if rb_t is None else rb_t.detach(), S, twin=any(ctx.needs_input_grad),
+                               pe_bf=pe_bf)
         ctx.tr, ctx.tape, ctx.has_t = tr, tape, rb_t is not None
         ctx.save_for_backward(raw)
         return raw
@@ -464,7 +466,9 @@ def render_rays_train(ray_batch, network_fn, network_fine, embedding_a, embeddin
         P = N * S
         Pp = (P + 7) // 8 * 8
         pe16 = tr.buf("pe_in", Pp, 64, torch.float16)
-        check(lib.dfb_embed_xyz16(_p(rays), rays.shape[1], _p(zz), N, S, 10, 64, _p(pe16), _st()))
+        # with a backward to come the encoding is also written as bf16, the first layer's weight-gradient operand
+        pe_bf = tr.buf("bf_pe", Pp, 64, torch.bfloat16) if torch.is_grad_enabled() else None
+        check(lib.dfb_embed_xyz16_ex(_p(rays), rays.shape[1], _p(zz), N, S, 10, 64, _p(pe16), _p(pe_bf), _st()))
         W = net.W
         if fine:
             ts = hist.long()
@@ -475,7 +479,7 @@ def render_rays_train(ray_batch, network_fn, network_fine, embedding_a, embeddin
         else:
             rb_d = dir_pe @ net.dir_encoding[0].weight[:, W:].t()
             rb_t = None
-        raw = _MLPFn.apply(tr, pe16, P, S, rb_d, rb_t, *tr.params())
+        raw = _MLPFn.apply(tr, (pe16, pe_bf), P, S, rb_d, rb_t, *tr.params())
         return raw.reshape(N, S, -1)
 
     raw_c = run(network_fn, z, False)

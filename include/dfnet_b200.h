@@ -390,6 +390,9 @@ int dfb_conv_pack_end(void* stream);
 /* pts = o + d*z, positional encoding with L bands (nerfw.py:105-133) -> fp16 [N*S, ld], columns >= 3+6L zero.
  * rays: [N, ray_stride] with o at 0..2 and d at 3..5. */
 int dfb_embed_xyz16(const float* rays, int ray_stride, const float* z, int64_t N, int S, int L, int ld, void* out, void* stream);
+/* the same with a bf16 copy of the output (out_bf16, nullable): the first layer's weight-gradient operand */
+int dfb_embed_xyz16_ex(const float* rays, int ray_stride, const float* z, int64_t N, int S, int L, int ld, void* out, void* out_bf16,
+                       void* stream);
 /* out[p, :] = fp16(rb[p / S, :]) for p < N*S (C % 8 == 0), and its adjoint out[r, :] = sum_s g[r*S + s, :] (g bf16). */
 int dfb_rows_expand16(const float* rb, int64_t N, int S, int C, void* out, void* stream);
 int dfb_rows_reduce_bf16(const void* g, int64_t N, int S, int C, float* out, void* stream);

@@ -75,12 +75,16 @@ def test_nerf_training_step_vs_reference_golden(case):
     assert worst_cos[0] > 0.995 and worst_norm[0] < 0.03, (worst_cos, worst_norm)    # measured 0.9990 / 0.8 %
 
 
-def test_raw2outputs_backward_vs_float64_autograd():
+@pytest.mark.parametrize("S,seq", [(40, "0"), (40, "1"), (33, "0"), (128, "0"), (192, "0"), (256, "0"), (300, "0")])
+def test_raw2outputs_backward_vs_float64_autograd(S, seq, monkeypatch):
     """dfb_raw2outputs_bwd (fine with rgb / beta / transient_sigmas upstream, coarse with noise) against float64 autograd
-    of a torch restatement of raw2outputs_NeRFW (rendering.py:132-243, train mode)."""
+    of a torch restatement of raw2outputs_NeRFW (rendering.py:132-243, train mode): the warp-per-ray kernel (prefix / suffix
+    scans; sample counts that are not a multiple of 32, the 256-sample limit) and the one-thread-per-ray kernel
+    (DFB_R2O_BWD_SEQ=1, and S > 256)."""
     from dfnet_b200.nerf_train import _CompositeFn
+    monkeypatch.setenv("DFB_R2O_BWD_SEQ", seq)
     torch.manual_seed(4)
-    N, S = 37, 40
+    N = 37
     z, _ = torch.sort(torch.rand(N, S, device=dev()) * 2.5, -1)
     for typ, Cc in (("fine", 9), ("coarse", 4)):
         raw = torch.rand(N, S, Cc, device=dev())
@@ -229,3 +233,53 @@ def test_trainer_refresh_tracks_parameter_updates():
         raw2, _ = nerf_train.NetTrainer(fine).forward(pe, P, rb_d, rb_t, 8)
     assert (raw1 - raw0).abs().max() > 1e-4
     assert torch.equal(raw1, raw2)
+
+
+
+def test_embed_xyz16_with_bf16_twin_vs_torch():
+    """dfb_embed_xyz16_ex: [pts, sin / cos of 10 bands, zero column] as fp16 rows (models/nerfw.py:105-133 on
+    pts = o + d z) and the same values as bf16; padding rows past N S stay untouched."""
+    from dfnet_b200._lib import check, lib
+    torch.manual_seed(0)
+    N, S = 11, 13
+    rays = torch.randn(N, 21, device=dev())
+    z, _ = torch.sort(torch.rand(N, S, device=dev()) * 2.5, -1)
+    P = N * S
+    Pp = (P + 7) // 8 * 8
+    out = torch.full((Pp, 64), 9.0, device=dev(), dtype=torch.float16)
+    out_b = torch.full((Pp, 64), 9.0, device=dev(), dtype=torch.bfloat16)
+    out_1 = torch.zeros(Pp, 64, device=dev(), dtype=torch.float16)
+    check(lib.dfb_embed_xyz16_ex(rays.data_ptr(), 21, z.data_ptr(), N, S, 10, 64, out.data_ptr(), out_b.data_ptr(), None))
+    check(lib.dfb_embed_xyz16(rays.data_ptr(), 21, z.data_ptr(), N, S, 10, 64, out_1.data_ptr(), None))
+    pts = (rays[:, None, :3] + rays[:, None, 3:6] * z[..., None]).reshape(-1, 3)
+    want = [pts]
+    for l in range(10):
+        want += [torch.sin(pts * 2.0 ** l), torch.cos(pts * 2.0 ** l)]
+    want = torch.cat(want + [torch.zeros(P, 1, device=dev())], -1)
+    assert float((out[:P].float() - want).abs().max()) < 2e-3          # fp16 rounding of values in [-4, 4]
+    assert torch.equal(out[:P], out_1[:P])
+    assert torch.equal(out_b[:P], out[:P].float().bfloat16())
+    assert bool((out[P:] == 9.0).all()) and bool((out_b[P:] == 9.0).all())
+
+
+def test_heads_backward_vs_torch():
+    """dfb_nerf_heads_bwd: d raw -> d pre-activation of the Sigmoid / Softplus heads (models/nerfw.py:275-295) as bf16
+    [P, 64] rows, zero past the head's width."""
+    from dfnet_b200._lib import check, lib
+    torch.manual_seed(1)
+    for Cc in (9, 4):
+        P = 1003
+        pre = torch.randn(P, Cc, device=dev()) * 2
+        sig = [3] + ([7, 8] if Cc == 9 else [])
+        x = pre.clone().requires_grad_(True)
+        raw = torch.sigmoid(x)
+        raw = torch.cat([F.softplus(x[:, c:c + 1]) if c in sig else raw[:, c:c + 1] for c in range(Cc)], -1)
+        g = torch.randn(P, Cc, device=dev())
+        raw.backward(g)
+        gs, gr, gt = (torch.full((P, 64), 5.0, device=dev(), dtype=torch.bfloat16) for _ in range(3))
+        check(lib.dfb_nerf_heads_bwd(raw.detach().contiguous().data_ptr(), g.data_ptr(), P, Cc, gs.data_ptr(), gr.data_ptr(),
+                                     gt.data_ptr() if Cc == 9 else None, None))
+        assert torch.allclose(gs[:, 0].float(), x.grad[:, 3], rtol=8e-3, atol=1e-6) and bool((gs[:, 1:] == 0).all())
+        assert torch.allclose(gr[:, :3].float(), x.grad[:, :3], rtol=8e-3, atol=1e-6) and bool((gr[:, 3:] == 0).all())
+        if Cc == 9:
+            assert torch.allclose(gt[:, :5].float(), x.grad[:, 4:9], rtol=8e-3, atol=1e-6) and bool((gt[:, 5:] == 0).all())
