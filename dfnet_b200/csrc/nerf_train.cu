@@ -15,6 +15,8 @@
 //   k_raw2outputs_bwd      adjoint of raw2outputs_NeRFW (models/rendering.py:132-243) in train mode w.r.t. raw, for the
 //                          outputs the NeRF-W loss reads: rgb (coarse / fine), beta, transient_sigmas
 //   k_cast_f16_bf16        forward activations (fp16) as bf16 operands of the weight-gradient kernel
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace dfb {
@@ -326,9 +328,117 @@ __global__ void __launch_bounds__(256) k_cast_f16_bf16(const __half* __restrict_
   }
 }
 
+// ---- NeRF-W loss (models/losses.py:42-57), all four terms in one pass ---------------------------------------------------
+//   c_l = coef * 0.5 mean((rgb_c - t)^2)      f_l = coef * mean((rgb_f - t)^2 / (2 beta^2))
+//   b_l = coef * (3 + mean(log beta))         s_l = coef * lambda_u * mean(transient_sigmas)
+// As tensor expressions these are ~25 launches forward and ~35 backward on a few thousand values, all host time in a
+// launch-bound training step.  Partial sums in double per block, summed in block order by a second, single-block launch
+// (deterministic).  out[4] = the four terms, out[4] (fifth value) = mean((rgb_f - t)^2) for the PSNR read-out.
+constexpr int kLossBlocks = 64;
+
+__global__ void __launch_bounds__(256) k_nerfw_loss_partial(const float* __restrict__ rc, const float* __restrict__ rf,
+                                                            const float* __restrict__ beta, const float* __restrict__ ts,
+                                                            const float* __restrict__ tg, int64_t N, int S, double* __restrict__ ws) {
+  double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  const int64_t stride = (int64_t)gridDim.x * 256, i0 = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  for (int64_t n = i0; n < N; n += stride) {
+    const float b = beta[n];
+    float sc = 0.f, sf = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float t = tg[n * 3 + c], dc = rc[n * 3 + c] - t, df = rf[n * 3 + c] - t;
+      sc += dc * dc, sf += df * df;
+    }
+    acc[0] += (double)sc, acc[1] += (double)(sf / (2.f * b * b)), acc[2] += (double)logf(b), acc[4] += (double)sf;
+  }
+  for (int64_t i = i0; i < N * S; i += stride) acc[3] += (double)ts[i];
+  __shared__ double sm[5][256];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) sm[k][threadIdx.x] = acc[k];
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) sm[k][threadIdx.x] += sm[k][threadIdx.x + w];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 5) ws[blockIdx.x * 5 + threadIdx.x] = sm[threadIdx.x][0];
+}
+
+__global__ void k_nerfw_loss_final(const double* __restrict__ ws, int blocks, int64_t N, int S, float coef, float lambda_u,
+                                   float* __restrict__ out) {
+  if (threadIdx.x >= 5) return;
+  double s = 0.0;
+  for (int b = 0; b < blocks; ++b) s += ws[b * 5 + threadIdx.x];
+  const double n3 = 3.0 * (double)N, ns = (double)N * (double)S;
+  double v;
+  switch (threadIdx.x) {
+    case 0: v = coef * 0.5 * s / n3; break;
+    case 1: v = coef * s / n3; break;
+    case 2: v = coef * (3.0 + s / (double)N); break;
+    case 3: v = coef * lambda_u * s / ns; break;
+    default: v = s / n3; break;
+  }
+  out[threadIdx.x] = (float)v;
+}
+
+// adjoint: g[4] are the upstream gradients of the four terms (device scalars, nullable = 0)
+__global__ void __launch_bounds__(256) k_nerfw_loss_bwd(const float* __restrict__ rc, const float* __restrict__ rf,
+                                                        const float* __restrict__ beta, const float* __restrict__ tg, int64_t N, int S,
+                                                        float coef, float lambda_u, const float* __restrict__ gc_p,
+                                                        const float* __restrict__ gf_p, const float* __restrict__ gb_p,
+                                                        const float* __restrict__ gs_p, float* __restrict__ g_rc,
+                                                        float* __restrict__ g_rf, float* __restrict__ g_beta, float* __restrict__ g_ts) {
+  const float gc = gc_p ? *gc_p : 0.f, gf = gf_p ? *gf_p : 0.f, gb = gb_p ? *gb_p : 0.f, gs = gs_p ? *gs_p : 0.f;
+  const float inv3n = 1.f / (3.f * (float)N), invn = 1.f / (float)N;
+  const int64_t stride = (int64_t)gridDim.x * 256, i0 = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  for (int64_t n = i0; n < N; n += stride) {
+    const float b = beta[n], ib2 = 1.f / (b * b);
+    float sf = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float t = tg[n * 3 + c], dc = rc[n * 3 + c] - t, df = rf[n * 3 + c] - t;
+      if (g_rc) g_rc[n * 3 + c] = gc * coef * dc * inv3n;
+      if (g_rf) g_rf[n * 3 + c] = gf * coef * df * ib2 * inv3n;
+      sf += df * df;
+    }
+    if (g_beta) g_beta[n] = -gf * coef * sf * ib2 / b * inv3n + gb * coef * invn / b;
+  }
+  if (g_ts) {
+    const float v = gs * coef * lambda_u / ((float)N * (float)S);
+    for (int64_t i = i0; i < N * S; i += stride) g_ts[i] = v;
+  }
+}
+
 }  // namespace dfb
 
 using namespace dfb;
+
+extern "C" size_t dfb_nerfw_loss_workspace_bytes(void) { return (size_t)kLossBlocks * 5 * sizeof(double); }
+
+extern "C" int dfb_nerfw_loss_fwd(const float* rgb_coarse, const float* rgb_fine, const float* beta, const float* transient_sigmas,
+                                  const float* targets, int64_t N, int S, float coef, float lambda_u, void* ws, float* out5, void* stream) {
+  DFB_REQUIRE(rgb_coarse && rgb_fine && beta && transient_sigmas && targets && ws && out5 && N >= 1 && S >= 1, DFB_ERR_INVALID,
+              "dfb_nerfw_loss_fwd: bad arguments");
+  const int blocks = (int)std::min<int64_t>(kLossBlocks, (N * S + 255) / 256);
+  k_nerfw_loss_partial<<<blocks, 256, 0, (cudaStream_t)stream>>>(rgb_coarse, rgb_fine, beta, transient_sigmas, targets, N, S, (double*)ws);
+  DFB_LAUNCH_CHECK();
+  k_nerfw_loss_final<<<1, 32, 0, (cudaStream_t)stream>>>((const double*)ws, blocks, N, S, coef, lambda_u, out5);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+extern "C" int dfb_nerfw_loss_bwd(const float* rgb_coarse, const float* rgb_fine, const float* beta, const float* targets, int64_t N, int S,
+                                  float coef, float lambda_u, const float* g_c, const float* g_f, const float* g_b, const float* g_s,
+                                  float* g_rgb_coarse, float* g_rgb_fine, float* g_beta, float* g_transient_sigmas, void* stream) {
+  DFB_REQUIRE(rgb_coarse && rgb_fine && beta && targets && N >= 1 && S >= 1, DFB_ERR_INVALID, "dfb_nerfw_loss_bwd: bad arguments");
+  const int blocks = (int)std::min<int64_t>(148 * 4, ((g_transient_sigmas ? N * S : N) + 255) / 256);
+  k_nerfw_loss_bwd<<<blocks, 256, 0, (cudaStream_t)stream>>>(rgb_coarse, rgb_fine, beta, targets, N, S, coef, lambda_u, g_c, g_f, g_b, g_s,
+                                                              g_rgb_coarse, g_rgb_fine, g_beta, g_transient_sigmas);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
 
 static int embed_xyz16_impl(const float* rays, int ray_stride, const float* z, int64_t N, int S, int L, int ld, void* out, void* out_bf16,
                            void* stream) {

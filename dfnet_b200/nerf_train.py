@@ -537,7 +537,8 @@ def train_on_batch_nerfw(args, target, pose, img_idx, H, W, focal, N_rand, optim
     loss_d = loss_func(results, target_s)
     loss = sum(l for l in loss_d.values())
     with torch.no_grad():
-        psnr = -10. * torch.log10(torch.mean((rgb - target_s) ** 2))
+        mse_f = getattr(loss_func, "last_mse_fine", None)       # NerfWLoss' fused pass already has it
+        psnr = -10. * torch.log10(mse_f if mse_f is not None else torch.mean((rgb - target_s) ** 2))
     loss.backward()
     optimizer.step()
     decay_rate, decay_steps = 0.1, args.lrate_decay * 1000

@@ -407,6 +407,16 @@ int dfb_nerf_heads_bwd(const float* raw, const float* g_raw, int64_t P, int C, v
  * C = 9: g_rgb [N,3], g_beta [N], g_tsig [N,S] (any may be NULL); C = 4: g_rgb (+ the coarse pass' noise draws). */
 int dfb_raw2outputs_bwd(const float* raw, const float* z_vals, int64_t N, int S, int C, const float* noise, float raw_noise_std,
                         const float* g_rgb, const float* g_beta, const float* g_tsig, float* g_raw, void* stream);
+/* NerfWLoss (models/losses.py:42-57) in one pass: out5 = {c_l, f_l, b_l, s_l, mean((rgb_fine - targets)^2)} with
+ * c_l = coef 0.5 mean((rgb_coarse - t)^2), f_l = coef mean((rgb_fine - t)^2 / (2 beta^2)), b_l = coef (3 + mean(log beta)),
+ * s_l = coef lambda_u mean(transient_sigmas).  rgb [N,3], beta [N], transient_sigmas [N,S], ws: dfb_nerfw_loss_workspace_bytes().
+ * _bwd: g_c..g_s = upstream gradients of the four terms (device scalars, NULL = 0); every output is nullable. */
+size_t dfb_nerfw_loss_workspace_bytes(void);
+int dfb_nerfw_loss_fwd(const float* rgb_coarse, const float* rgb_fine, const float* beta, const float* transient_sigmas,
+                       const float* targets, int64_t N, int S, float coef, float lambda_u, void* ws, float* out5, void* stream);
+int dfb_nerfw_loss_bwd(const float* rgb_coarse, const float* rgb_fine, const float* beta, const float* targets, int64_t N, int S,
+                       float coef, float lambda_u, const float* g_c, const float* g_f, const float* g_b, const float* g_s,
+                       float* g_rgb_coarse, float* g_rgb_fine, float* g_beta, float* g_transient_sigmas, void* stream);
 int dfb_cast_f16_bf16(const void* src, void* dst, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -283,3 +283,35 @@ def test_heads_backward_vs_torch():
         assert torch.allclose(gr[:, :3].float(), x.grad[:, :3], rtol=8e-3, atol=1e-6) and bool((gr[:, 3:] == 0).all())
         if Cc == 9:
             assert torch.allclose(gt[:, :5].float(), x.grad[:, 4:9], rtol=8e-3, atol=1e-6) and bool((gt[:, 5:] == 0).all())
+
+
+@pytest.mark.parametrize("N,S", [(1, 1), (37, 40), (1536, 128), (5000, 192)])
+def test_fused_nerfw_loss_vs_tensor_expressions(N, S):
+    """NerfWLoss on CUDA tensors (dfb_nerfw_loss_fwd / _bwd) against the same module's tensor expressions
+    (models/losses.py:42-57) evaluated in float64 on the host: the four terms, the fine pass' mean squared error and the
+    gradients w.r.t. rgb_coarse, rgb_fine, beta, transient_sigmas under unequal upstream weights."""
+    from dfnet_b200.losses import NerfWLoss
+    torch.manual_seed(N + S)
+    lf = NerfWLoss(coef=0.7, lambda_u=0.02)
+    host = dict(rgb_coarse=torch.rand(N, 3), rgb_fine=torch.rand(N, 3), beta=torch.rand(N) * 0.8 + 0.1, transient_sigmas=torch.rand(N, S) * 3)
+    tg = torch.rand(N, 3)
+    wts = dict(c_l=1.0, f_l=0.5, b_l=2.0, s_l=3.0)
+    a = {k: v.to(dev()).requires_grad_(True) for k, v in host.items()}
+    b = {k: v.double().requires_grad_(True) for k, v in host.items()}
+    la, lb = lf(a, tg.to(dev())), lf(b, tg.double())
+    assert lf.last_mse_fine is None                      # the float64 host call took the tensor-expression path
+    la2 = lf(a, tg.to(dev()))
+    assert lf.last_mse_fine is not None
+    assert abs(float(lf.last_mse_fine) - float(((host["rgb_fine"] - tg) ** 2).mean())) < 1e-6
+    for k in wts:
+        assert abs(float(la[k]) - float(lb[k])) < 2e-6 * max(1.0, abs(float(lb[k]))), k
+        assert float(la2[k]) == float(la[k])             # deterministic
+    sum(wts[k] * la[k] for k in wts).backward()
+    sum(wts[k] * lb[k] for k in wts).backward()
+    for k in host:
+        ga, gb = a[k].grad.cpu().double(), b[k].grad
+        assert float((ga - gb).abs().max()) <= 2e-6 * float(gb.abs().max()) + 1e-12, k
+    # only some inputs require gradient
+    c = {k: v.to(dev()).requires_grad_(k == "beta") for k, v in host.items()}
+    sum(lf(c, tg.to(dev())).values()).backward()
+    assert c["rgb_fine"].grad is None and c["beta"].grad is not None
