@@ -50,6 +50,7 @@ struct WgArgs {
   alignas(64) CUtensorMap tmap_g;
   alignas(64) CUtensorMap tmap_x;
   int n_stages;        // tile ring depth (3 where shared memory allows, else 2)
+  int sw128;           // 1: pixel-major 128-byte-swizzled tiles (1x1 layers with 64-channel multiples), see the producer
   int atomic;          // 1: the epilogue adds to dW (pixel tiles split over CTAs, or the caller accumulates); 0: it stores
   const uint16_t* gO;  // NHWC [B,H,W,Cout]
   const uint16_t* X;   // NHWC [B,H,W,Cin_pad]
@@ -123,8 +124,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_wgrad(const __grid_constan
           const int b = t / tiles_img, ti = t % tiles_img;
           const int y0 = (ti / a.tiles_x) * kTH, x0 = (ti % a.tiles_x) * kTW;
           mbar_expect_tx(bar(FULL + st), kGBytes + a.x_bytes);
-          tma_load_5d<1>(sG + st * kGBytes, &a.tmap_g, 0, x0, y0, cob * 16, b, bar(FULL + st));
-          tma_load_5d<1>(sX + st * a.x_bytes, &a.tmap_x, 0, x0 - a.pad, y0 + ky - a.pad, cib * npan, b, bar(FULL + st));
+          if (a.sw128) {
+            // 1x1 layers: a tile is 128 pixels x 64 channels per box, one 128-byte row per pixel, 128-byte swizzle - the
+            // canonical MN-major SWIZZLE_128B operand (8 pixels x 128 B atoms).  An eighth of the rows the TMA unit has to
+            // move compared with the 16-byte rows of the panel layout, which is what bounded this kernel (~5 000 cycles per
+            // tile against 1 536 for its MMAs).
+            for (int sl = 0; sl < 2; ++sl)
+              tma_load_4d(sG + st * kGBytes + sl * 16384u, &a.tmap_g, cob * 128 + sl * 64, x0, y0, b, bar(FULL + st));
+            for (int sl = 0; sl < a.NB / 64; ++sl)
+              tma_load_4d(sX + st * a.x_bytes + sl * 16384u, &a.tmap_x, cib * a.NB + sl * 64, x0, y0, b, bar(FULL + st));
+          } else {
+            tma_load_5d<1>(sG + st * kGBytes, &a.tmap_g, 0, x0, y0, cob * 16, b, bar(FULL + st));
+            tma_load_5d<1>(sX + st * a.x_bytes, &a.tmap_x, 0, x0 - a.pad, y0 + ky - a.pad, cib * npan, b, bar(FULL + st));
+          }
         }
         __syncwarp();
       }
@@ -140,7 +152,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_wgrad(const __grid_constan
         uint32_t v[32];
         tmem_ld32(t_row + kx * a.NB + c0, v);
         tmem_ld_wait(v);
-        if (co < a.Cout) {
+        if (co < a.Cout && a.atomic && a.KH == 1 && (a.Cin & 3) == 0) {
+          // 1x1 layers: a thread's 32 columns are contiguous in dW -> 16-byte vector atomics (a quarter of the L2 atomic
+          // operations; with the pixel tiles split over every SM each dW element receives ~148 of them)
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int ci = cib * a.NB + c0 + j;
+            if (c0 + j < a.NB && ci < a.Cin)   // NB and Cin are multiples of 4: a group is in range as a whole
+              atomicAdd(reinterpret_cast<float4*>(a.dW + (int64_t)co * a.Cin + ci),
+                        make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+          }
+        } else if (co < a.Cout) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int ci = cib * a.NB + c0 + j;
@@ -157,8 +179,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_wgrad(const __grid_constan
     // ===== MMA issuer ===============================================================================
     const uint32_t idesc = make_idesc_ex(a.fmt, a.fmt, 1, 1, a.NB, 128);
     // MN-major, no swizzle: LBO = distance between 8-pixel K groups (next patch row), SBO = panel stride
-    const uint32_t a_hi = (2048u >> 4) | (1u << 14), a_lbo = (128u >> 4) << 16;
-    const uint32_t b_hi = (xpanel >> 4) | (1u << 14), b_lbo = ((uint32_t)(a.PW * 16) >> 4) << 16;
+    // MN-major, 128-byte swizzle (sw128): SBO = 1024 B between 8-pixel K groups, LBO = 16 KB between 64-channel slabs
+    const uint32_t a_hi = a.sw128 ? ((1024u >> 4) | (1u << 14) | (2u << 29)) : ((2048u >> 4) | (1u << 14));
+    const uint32_t a_lbo = (a.sw128 ? (16384u >> 4) : (128u >> 4)) << 16;
+    const uint32_t b_hi = a.sw128 ? a_hi : ((xpanel >> 4) | (1u << 14));
+    const uint32_t b_lbo = (a.sw128 ? (16384u >> 4) : ((uint32_t)(a.PW * 16) >> 4)) << 16;
+    const uint32_t a_ks = a.sw128 ? (2048u >> 4) : 16u;                       // start-address step per K = 16 pixels
+    const uint32_t b_ks = a.sw128 ? (2048u >> 4) : (uint32_t)(2 * a.PW);
     uint32_t seq = 0;
     for (int t = t0; t < t1; ++t, ++seq) {
       const uint32_t st = seq % kStages, ph = (seq / kStages) & 1;
@@ -170,7 +197,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_wgrad(const __grid_constan
         for (int kx = 0; kx < a.KW; ++kx) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)  // K = 16 pixels = two patch rows
-            umma_f16<1>(tmem_base + kx * a.NB, mk64(g_lo + ks * 16u, a_hi), mk64(x_lo + (uint32_t)(ks * 2 * a.PW + kx), b_hi), idesc,
+            umma_f16<1>(tmem_base + kx * a.NB, mk64(g_lo + ks * a_ks, a_hi), mk64(x_lo + ks * b_ks + (uint32_t)kx, b_hi), idesc,
                         (uint32_t)(seq | ks));
         }
         umma_commit<1>(bar(EMPTY + st));
@@ -213,8 +240,7 @@ __global__ void __launch_bounds__(256) k_bias_grad(const uint16_t* __restrict__ 
   pdl_wait();
   pdl_launch_dependents();
   float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int64_t p = (int64_t)blockIdx.x * nl + lane; p < npix; p += (int64_t)gridDim.x * nl) {
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(gO + p * C) + g);
+  auto add8 = [&](const uint4& v) {
     const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -225,7 +251,19 @@ __global__ void __launch_bounds__(256) k_bias_grad(const uint16_t* __restrict__ 
         s[2 * e] += f.x, s[2 * e + 1] += f.y;
       }
     }
+  };
+  // four independent 16-byte loads in flight per thread (one per trip left every load waiting for the previous add:
+  // 1.4 TB/s on the 50 MB gradients of a NeRF layer)
+  const int64_t step = (int64_t)gridDim.x * nl;
+  int64_t p = (int64_t)blockIdx.x * nl + lane;
+  for (; p + 3 * step < npix; p += 4 * step) {
+    const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(gO + p * C) + g);
+    const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(gO + (p + step) * C) + g);
+    const uint4 v2 = __ldg(reinterpret_cast<const uint4*>(gO + (p + 2 * step) * C) + g);
+    const uint4 v3 = __ldg(reinterpret_cast<const uint4*>(gO + (p + 3 * step) * C) + g);
+    add8(v0), add8(v1), add8(v2), add8(v3);
   }
+  for (; p < npix; p += step) add8(__ldg(reinterpret_cast<const uint4*>(gO + p * C) + g));
   __shared__ float sm[256 * 8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) sm[lane * C + g * 8 + e] = s[e];
@@ -347,9 +385,11 @@ static int conv_wgrad_impl(const void* gO, const void* X, int B, int H, int W, i
   DFB_REQUIRE(smem <= 232448, DFB_ERR_UNSUPPORTED, "shared memory budget exceeded");
   DFB_REQUIRE(Cout % 8 == 0, DFB_ERR_INVALID, "dfb_conv_wgrad: Cout must be a multiple of 8");
   {
-    int rc = make_patch_tmap(gO, B, H, W, Cout, wg::kTH, wg::kTW, &a.tmap_g, 16);
+    const char* e = getenv("DFB_WGRAD_SW128");   // =0: the panel layout for every layer (A/B, tests)
+    a.sw128 = (KH == 1 && a.NB % 64 == 0 && !(e && e[0] == '0')) ? 1 : 0;
+    int rc = make_patch_tmap(gO, B, H, W, Cout, wg::kTH, wg::kTW, &a.tmap_g, a.sw128 ? -64 : 16);
     if (rc) return rc;
-    rc = make_patch_tmap(X, B, H, W, Cin_pad, wg::kTH, a.PW, &a.tmap_x, a.NB / 8);
+    rc = make_patch_tmap(X, B, H, W, Cin_pad, wg::kTH, a.PW, &a.tmap_x, a.sw128 ? -64 : a.NB / 8);
     if (rc) return rc;
   }
   a.atomic = (a.n_split > 1 || accumulate) ? 1 : 0;
@@ -370,7 +410,7 @@ static int conv_wgrad_impl(const void* gO, const void* X, int B, int H, int W, i
     const int64_t npix = (int64_t)B * H * W;
     if (Cout == 64 || Cout == 128 || Cout == 256 || Cout == 512) {
       const int nl = 256 / (Cout / 8);
-      const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((npix + nl - 1) / nl, 148 * 4));
+      const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((npix + 4 * nl - 1) / (4 * nl), 148 * 8));
       auto kern = fmt ? wg::k_bias_grad<__nv_bfloat16> : wg::k_bias_grad<__half>;
       DFB_CHECK_CUDA(dfb_launch_pdl(kern, dim3(blocks), dim3(256), 0, st, true, (const uint16_t*)gO, npix, Cout, dB));
     } else {

@@ -729,6 +729,26 @@ int dfb::make_patch_tmap(const void* in, int B, int H, int W, int Cpad, int PH, 
 
 static int make_patch_tmap_uncached(const void* in, int B, int H, int W, int Cpad, int PH, int PW, CUtensorMap* out, int npanels) {
   static PFN_cuTensorMapEncodeTiled encode = nullptr;
+  if (npanels == -64) {
+    // pixel-major 128-byte-swizzled box: NHWC as [B][H][W][C], box = PH x PW pixels x 64 channels (one 128-byte row per pixel)
+    if (!encode) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      DFB_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+      DFB_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, DFB_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+      encode = (PFN_cuTensorMapEncodeTiled)fn;
+    }
+    DFB_REQUIRE(((uintptr_t)in & 15) == 0 && Cpad % 8 == 0, DFB_ERR_INVALID, "conv input must be 16-byte aligned NHWC with C % 8 == 0");
+    const cuuint64_t dims[4] = {(cuuint64_t)Cpad, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)Cpad * 2, (cuuint64_t)W * Cpad * 2, (cuuint64_t)H * W * Cpad * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)PW, (cuuint32_t)PH, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(in), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DFB_REQUIRE(r == CUDA_SUCCESS, DFB_ERR_CUDA, "cuTensorMapEncodeTiled (pixel-major, %dx%dx%dx%d) failed (%d)", B, H, W, Cpad, (int)r);
+    return DFB_OK;
+  }
   if (!encode) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;

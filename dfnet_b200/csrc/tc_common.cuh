@@ -132,6 +132,12 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tma
   }
 }
 
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tmap, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
 template <int CG = 1>
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
   if (CG == 1) {

@@ -43,7 +43,11 @@ def close_grad(got, want, tol=3e-2, cos_min=0.999):
 
 
 @pytest.mark.parametrize("cin,cout,k,B,H,W", [(64, 128, 3, 2, 37, 45), (3, 64, 3, 1, 40, 56), (256, 512, 3, 1, 20, 24),
-                                               (128, 64, 3, 3, 16, 8), (64, 128, 5, 1, 33, 20), (256, 64, 1, 1, 24, 24)])
+                                               (128, 64, 3, 3, 16, 8), (64, 128, 5, 1, 33, 20), (256, 64, 1, 1, 24, 24),
+                                               # 1x1 layers: the pixel-major 128-byte-swizzled tiles (64-channel multiples), ragged
+                                               # images, a NeRF layer ([P/8, 8] "image"), and a width that stays on the panel layout
+                                               (128, 128, 1, 1, 1000, 8), (64, 128, 1, 2, 19, 13), (128, 64, 1, 1, 5, 3),
+                                               (192, 256, 1, 1, 33, 20), (48, 64, 1, 1, 24, 24)])
 def test_conv_wgrad_vs_torch(cin, cout, k, B, H, W):
     ops = _ops()
     torch.manual_seed(1)
