@@ -51,6 +51,8 @@ struct WgArgs {
   alignas(64) CUtensorMap tmap_x;
   int n_stages;        // tile ring depth (3 where shared memory allows, else 2)
   int sw128;           // 1: pixel-major 128-byte-swizzled tiles (1x1 layers with 64-channel multiples), see the producer
+  int tap_major;       // 1: dW points to a scratch image [KH][KW][Cout][Cin_s] (input channel fastest) that takes 16-byte vector
+  int Cin_s;           //    atomics; k_wgrad_unpack transposes it into [Cout][Cin][KH][KW] afterwards
   int atomic;          // 1: the epilogue adds to dW (pixel tiles split over CTAs, or the caller accumulates); 0: it stores
   const uint16_t* gO;  // NHWC [B,H,W,Cout]
   const uint16_t* X;   // NHWC [B,H,W,Cin_pad]
@@ -152,7 +154,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_wgrad(const __grid_constan
         uint32_t v[32];
         tmem_ld32(t_row + kx * a.NB + c0, v);
         tmem_ld_wait(v);
-        if (co < a.Cout && a.atomic && a.KH == 1 && (a.Cin & 3) == 0) {
+        if (co < a.Cout && a.tap_major) {
+          float* base = a.dW + ((int64_t)(ky * a.KW + kx) * a.Cout + co) * a.Cin_s;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int ci = cib * a.NB + c0 + j;
+            if (c0 + j < a.NB && ci < a.Cin_s)   // columns past Cin hold the zero padding channels of X
+              atomicAdd(reinterpret_cast<float4*>(base + ci),
+                        make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+          }
+        } else if (co < a.Cout && a.atomic && a.KH == 1 && (a.Cin & 3) == 0) {
           // 1x1 layers: a thread's 32 columns are contiguous in dW -> 16-byte vector atomics (a quarter of the L2 atomic
           // operations; with the pixel tiles split over every SM each dW element receives ~148 of them)
 #pragma unroll
@@ -211,6 +222,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_wgrad(const __grid_constan
   if (warp == 4) {
     tc_fence_after();
     tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+// dW[co][ci][ky][kx] (+)= S[ky][kx][co][ci]: the tap-major scratch image of a 3x3 / 5x5 weight gradient into the parameter's
+// layout.  With the pixel tiles split over the SMs every dW element receives n_split atomics; in the parameter's layout a
+// thread's 32 accumulator columns are KH*KW floats apart (scalar atomics, ~75 M of them for the 13 encoder layers of a
+// 480x640 training step), in the tap-major image they are contiguous and go out as 16-byte vector atomics.
+__global__ void __launch_bounds__(256) k_wgrad_unpack(const float* __restrict__ S, float* __restrict__ dW, int Cout, int Cin, int Cin_s,
+                                                      int taps, int accumulate) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= (int64_t)Cout * Cin) return;
+  const int co = (int)(i / Cin), ci = (int)(i - (int64_t)co * Cin);
+  float* o = dW + i * taps;
+  for (int t = 0; t < taps; ++t) {
+    const float v = S[((int64_t)t * Cout + co) * Cin_s + ci];
+    o[t] = accumulate ? o[t] + v : v;
   }
 }
 
@@ -347,6 +374,32 @@ extern "C" int dfb_conv_wgrad_acc(const void* gO, const void* X, int B, int H, i
   return conv_wgrad_impl(gO, X, B, H, W, Cin, Cin_pad, Cout, KH, fmt, dW, dB, stream, 1);
 }
 
+// Scratch image of the tap-major path: one buffer per (host thread, stream), grown on demand and kept for the life of the
+// process (at most 9.4 MB for a 512 x 512 x 3 x 3 layer).  Launches on one stream are ordered, so a buffer is never shared
+// by two gradients in flight; growing it goes through cudaFree, which waits for the device.
+static int wgrad_scratch(cudaStream_t st, size_t bytes, float** out) {
+  struct Entry { cudaStream_t st; int dev; float* p; size_t bytes; };
+  static thread_local std::vector<Entry> cache;
+  int dev = 0;
+  DFB_CHECK_CUDA(cudaGetDevice(&dev));
+  for (Entry& e : cache)
+    if (e.st == st && e.dev == dev) {
+      if (e.bytes < bytes) {
+        DFB_CHECK_CUDA(cudaFree(e.p));
+        e.p = nullptr, e.bytes = 0;
+        DFB_CHECK_CUDA(cudaMalloc(&e.p, bytes));
+        e.bytes = bytes;
+      }
+      *out = e.p;
+      return DFB_OK;
+    }
+  Entry e = {st, dev, nullptr, std::max<size_t>(bytes, (size_t)512 * 512 * 9 * 4)};
+  DFB_CHECK_CUDA(cudaMalloc(&e.p, e.bytes));
+  cache.push_back(e);
+  *out = e.p;
+  return DFB_OK;
+}
+
 static int conv_wgrad_impl(const void* gO, const void* X, int B, int H, int W, int Cin, int Cin_pad, int Cout, int KH, int fmt,
                            float* dW, float* dB, void* stream, int accumulate) {
   DFB_REQUIRE(gO && X && dW, DFB_ERR_INVALID, "dfb_conv_wgrad: null argument");
@@ -393,7 +446,19 @@ static int conv_wgrad_impl(const void* gO, const void* X, int B, int H, int W, i
     if (rc) return rc;
   }
   a.atomic = (a.n_split > 1 || accumulate) ? 1 : 0;
-  if (a.n_split > 1 && !accumulate) DFB_CHECK_CUDA(cudaMemsetAsync(dW, 0, (size_t)Cout * Cin * KH * KH * 4, st));
+  float* scratch = nullptr;
+  {
+    const char* e = getenv("DFB_WGRAD_TAP_MAJOR");   // =0: scalar atomics straight into dW (A/B, tests)
+    if (KH > 1 && a.n_split > 1 && !(e && e[0] == '0')) {
+      a.Cin_s = round_up(Cin, 4);
+      const size_t bytes = (size_t)KH * KH * Cout * a.Cin_s * 4;
+      const int rc = wgrad_scratch(st, bytes, &scratch);
+      if (rc) return rc;
+      DFB_CHECK_CUDA(cudaMemsetAsync(scratch, 0, bytes, st));
+      a.tap_major = 1, a.dW = scratch;
+    }
+  }
+  if (a.n_split > 1 && !accumulate && !a.tap_major) DFB_CHECK_CUDA(cudaMemsetAsync(dW, 0, (size_t)Cout * Cin * KH * KH * 4, st));
   {
     static thread_local uint64_t attr_set = 0;   // bit d: set on device d
     int cur = 0;
@@ -405,6 +470,11 @@ static int conv_wgrad_impl(const void* gO, const void* X, int B, int H, int W, i
   }
   DFB_CHECK_CUDA(dfb_launch_pdl(wg::k_conv_wgrad, dim3(units * a.n_split), dim3(wg::kThreads), smem, st, true, a));
   DFB_LAUNCH_CHECK();
+  if (a.tap_major) {
+    const int64_t n = (int64_t)Cout * Cin;
+    wg::k_wgrad_unpack<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(scratch, dW, Cout, Cin, a.Cin_s, KH * KH, accumulate);
+    DFB_LAUNCH_CHECK();
+  }
   if (dB) {
     if (!accumulate) DFB_CHECK_CUDA(cudaMemsetAsync(dB, 0, (size_t)Cout * 4, st));
     const int64_t npix = (int64_t)B * H * W;
