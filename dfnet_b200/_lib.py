@@ -26,6 +26,7 @@ SYMBOLS = [
     "dfb_resize_bilinear_ac_bwd", "dfb_dfnet_bwd_bucket_event", "dfb_luma_hist", "dfb_resize_area", "dfb_pose_error", "dfb_polar3x3_fwd", "dfb_polar3x3_bwd", "dfb_debug_conv_prof",
     "dfb_conv_update", "dfb_conv_pack_begin", "dfb_conv_pack_end", "dfb_embed_xyz16", "dfb_embed_xyz16_ex", "dfb_rows_expand16", "dfb_rows_reduce_bf16", "dfb_nerf_heads_fwd", "dfb_nerf_heads_bwd",
     "dfb_raw2outputs_bwd", "dfb_cast_f16_bf16", "dfb_render_poses_fwd", "dfb_copy2d_batch", "dfb_nerfw_loss_workspace_bytes", "dfb_nerfw_loss_fwd", "dfb_nerfw_loss_bwd",
+    "dfb_pose_rays_fwd", "dfb_pose_rays_workspace_bytes", "dfb_pose_rays_bwd",
 ]
 
 MMA_FP32_SIMT, MMA_F16, MMA_BF16, MMA_F16_SPLIT_COARSE = 0, 1, 2, 3
@@ -136,6 +137,10 @@ def _load():
     lib.dfb_polar3x3_fwd.argtypes = [vp, i32, vp, vp, vp]
     lib.dfb_polar3x3_bwd.argtypes = [vp, vp, i32, vp, vp]
     lib.dfb_copy2d_batch.argtypes = [vp, i32, vp]
+    lib.dfb_pose_rays_fwd.argtypes = [vp, i32, i32, i32, f32, vp, vp, vp, vp]
+    lib.dfb_pose_rays_workspace_bytes.restype = C.c_size_t
+    lib.dfb_pose_rays_workspace_bytes.argtypes = []
+    lib.dfb_pose_rays_bwd.argtypes = [vp, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp]
     lib.dfb_nerfw_loss_workspace_bytes.restype = C.c_size_t
     lib.dfb_nerfw_loss_workspace_bytes.argtypes = []
     lib.dfb_nerfw_loss_fwd.argtypes = [vp, vp, vp, vp, vp, i64, i32, f32, f32, vp, vp, vp]

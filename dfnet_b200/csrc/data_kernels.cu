@@ -347,3 +347,111 @@ extern "C" int dfb_copy2d_batch(const DfbCopy2d* items, int n, void* stream) {
   return DFB_OK;
 }
 
+// ---- rays of a pose and their adjoint ---------------------------------------------------------------------------------------
+// get_rays (models/ray_utils.py:5-15) + viewdirs = rays_d / |rays_d| (rendering.py:366-370) for the differentiable render of
+// train_on_batch, where the pose carries gradient: as tensor expressions that is ~20 launches forward and ~25 backward in
+// the host-bound first 2 ms of the step.  Same arithmetic as k_prep_rays.  Adjoint: with dir_i = (dx, dy, -1) the pixel
+// direction, g_R[k][b] = sum_i gd_i[k] dir_i[b], g_t[k] = sum_i g_o_i[k], gd = g_d + (g_v - v (v . g_v)) / |d|.
+namespace {
+__device__ __forceinline__ void pixel_dir(int64_t r, int H, int W, float focal, float& dx, float& dy) {
+  const int pj = (int)(r / W), pi = (int)(r % W);
+  dx = __fdiv_rn(__fsub_rn((float)pi, (float)(W * 0.5)), focal);
+  dy = -__fdiv_rn(__fsub_rn((float)pj, (float)(H * 0.5)), focal);
+}
+
+__global__ void __launch_bounds__(256) k_pose_rays_fwd(const float* __restrict__ c2w, int ld, int H, int W, float focal,
+                                                       float* __restrict__ ro, float* __restrict__ rd, float* __restrict__ vd) {
+  const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (r >= (int64_t)H * W) return;
+  float dx, dy, d[3];
+  pixel_dir(r, H, W, focal, dx, dy);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float* R = c2w + k * ld;
+    d[k] = __fadd_rn(__fadd_rn(__fmul_rn(dx, R[0]), __fmul_rn(dy, R[1])), __fmul_rn(-1.0f, R[2]));
+    ro[r * 3 + k] = R[3];
+    rd[r * 3 + k] = d[k];
+  }
+  const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+#pragma unroll
+  for (int k = 0; k < 3; ++k) vd[r * 3 + k] = __fdiv_rn(d[k], nrm);
+}
+
+constexpr int kPoseBlocks = 64;
+
+__global__ void __launch_bounds__(256) k_pose_rays_bwd(const float* __restrict__ c2w, int ld, int H, int W, float focal,
+                                                       const float* __restrict__ g_o, const float* __restrict__ g_d,
+                                                       const float* __restrict__ g_v, double* __restrict__ ws) {
+  double acc[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) acc[k] = 0.0;
+  const int64_t N = (int64_t)H * W;
+  for (int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x; r < N; r += (int64_t)gridDim.x * 256) {
+    float dx, dy, d[3], gd[3];
+    pixel_dir(r, H, W, focal, dx, dy);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float* R = c2w + k * ld;
+      d[k] = dx * R[0] + dy * R[1] - R[2];
+      gd[k] = g_d ? g_d[r * 3 + k] : 0.f;
+    }
+    if (g_v) {
+      const float inv = rsqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+      const float v[3] = {d[0] * inv, d[1] * inv, d[2] * inv};
+      const float gv[3] = {g_v[r * 3], g_v[r * 3 + 1], g_v[r * 3 + 2]};
+      const float dot = v[0] * gv[0] + v[1] * gv[1] + v[2] * gv[2];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) gd[k] += (gv[k] - v[k] * dot) * inv;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      acc[k * 4 + 0] += (double)(gd[k] * dx), acc[k * 4 + 1] += (double)(gd[k] * dy), acc[k * 4 + 2] -= (double)gd[k];
+      if (g_o) acc[k * 4 + 3] += (double)g_o[r * 3 + k];
+    }
+  }
+  __shared__ double sm[8][12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) {
+    double v = acc[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 12) {
+    double v = 0.0;
+    for (int w = 0; w < 8; ++w) v += sm[w][threadIdx.x];
+    ws[blockIdx.x * 12 + threadIdx.x] = v;
+  }
+}
+
+__global__ void k_pose_rays_bwd_final(const double* __restrict__ ws, int blocks, float* __restrict__ out) {
+  if (threadIdx.x >= 12) return;
+  double v = 0.0;
+  for (int b = 0; b < blocks; ++b) v += ws[b * 12 + threadIdx.x];
+  out[threadIdx.x] = (float)v;
+}
+}  // namespace
+
+extern "C" int dfb_pose_rays_fwd(const float* c2w, int row_stride, int H, int W, float focal, float* rays_o, float* rays_d,
+                                 float* viewdirs, void* stream) {
+  DFB_REQUIRE(c2w && rays_o && rays_d && viewdirs && H > 0 && W > 0 && row_stride >= 4, DFB_ERR_INVALID, "dfb_pose_rays_fwd: bad arguments");
+  const int64_t N = (int64_t)H * W;
+  k_pose_rays_fwd<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(c2w, row_stride, H, W, focal, rays_o, rays_d, viewdirs);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+extern "C" size_t dfb_pose_rays_workspace_bytes(void) { return (size_t)kPoseBlocks * 12 * sizeof(double); }
+
+extern "C" int dfb_pose_rays_bwd(const float* c2w, int row_stride, int H, int W, float focal, const float* g_rays_o, const float* g_rays_d,
+                                 const float* g_viewdirs, void* ws, float* g_c2w12, void* stream) {
+  DFB_REQUIRE(c2w && ws && g_c2w12 && H > 0 && W > 0 && row_stride >= 4, DFB_ERR_INVALID, "dfb_pose_rays_bwd: bad arguments");
+  const int64_t N = (int64_t)H * W;
+  const int blocks = (int)std::min<int64_t>(kPoseBlocks, (N + 255) / 256);
+  k_pose_rays_bwd<<<blocks, 256, 0, (cudaStream_t)stream>>>(c2w, row_stride, H, W, focal, g_rays_o, g_rays_d, g_viewdirs, (double*)ws);
+  DFB_LAUNCH_CHECK();
+  k_pose_rays_bwd_final<<<1, 32, 0, (cudaStream_t)stream>>>((const double*)ws, blocks, g_c2w12);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+

@@ -48,10 +48,20 @@ def inference_pose_regression(args, data, device, model, retFeature=False, isSin
     return features, pose
 
 
+_MOVE_VEC_CACHE = {}
+
+
 def fix_coord_supp(args, pose, world_setup_dict, device=None):
     """Reference dm/direct_pose_model.py:147-167: predicted pose -> NeRF world scale (in place, like the reference)."""
     sc = world_setup_dict["pose_scale"]
-    move_all_cam_vec = torch.as_tensor(np.asarray(world_setup_dict["move_all_cam_vec"], np.float32), device=pose.device)
+    # the offset is a constant of the run: one upload per (value, device) instead of a pageable host-to-device copy per step
+    key = (tuple(float(x) for x in world_setup_dict["move_all_cam_vec"]), str(pose.device))
+    move_all_cam_vec = _MOVE_VEC_CACHE.get(key)
+    if move_all_cam_vec is None:
+        if len(_MOVE_VEC_CACHE) > 64:
+            _MOVE_VEC_CACHE.clear()
+        move_all_cam_vec = torch.as_tensor(np.asarray(world_setup_dict["move_all_cam_vec"], np.float32), device=pose.device)
+        _MOVE_VEC_CACHE[key] = move_all_cam_vec
     sc2 = world_setup_dict["pose_scale2"]
     pose[:, :3, 3] *= sc
     pose[:, :3, 3] += move_all_cam_vec

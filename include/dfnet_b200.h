@@ -448,6 +448,14 @@ typedef struct DfbCopy2d {
   int rows, cols, src_ld, dst_ld;
 } DfbCopy2d;
 int dfb_copy2d_batch(const DfbCopy2d* items, int n, void* stream);
+/* get_rays (models/ray_utils.py:5-15) with viewdirs = rays_d / |rays_d| (rendering.py:366-370) for a pose that carries
+ * gradient, and the adjoint: rays_o / rays_d / viewdirs [H*W,3]; g_c2w12 = d loss / d c2w[:3,:4] (row-major) from the
+ * gradients of the three outputs (each nullable).  ws: dfb_pose_rays_workspace_bytes(). */
+int dfb_pose_rays_fwd(const float* c2w, int row_stride, int H, int W, float focal, float* rays_o, float* rays_d, float* viewdirs,
+                      void* stream);
+size_t dfb_pose_rays_workspace_bytes(void);
+int dfb_pose_rays_bwd(const float* c2w, int row_stride, int H, int W, float focal, const float* g_rays_o, const float* g_rays_d,
+                      const float* g_viewdirs, void* ws, float* g_c2w12, void* stream);
 
 #ifdef __cplusplus
 }

@@ -465,3 +465,36 @@ def test_polar_orthogonalize_vs_torch_svd():
     gw = a64.grad
     err = float((a32.grad.cpu().double() - gw).abs().max()) / float(gw.abs().max())
     assert err < 1e-5, err
+
+
+@pytest.mark.parametrize("H,W,shape", [(120, 160, (3, 4)), (37, 53, (4, 4)), (1, 1, (3, 4))])
+def test_pose_rays_and_adjoint_vs_torch(H, W, shape):
+    """dfb_pose_rays_fwd / _bwd (get_rays of a pose that carries gradient + view-direction normalisation, ray_utils.py:5-15,
+    rendering.py:366-370) against the tensor expressions and torch autograd."""
+    from dfnet_b200 import rendering
+    torch.manual_seed(5)
+    focal = 73.5
+    base = torch.eye(4, device=dev())[:shape[0]].clone()
+    base[:3, :3] += 0.1 * torch.randn(3, 3, device=dev())
+    base[:3, 3] = torch.tensor([0.3, -0.2, 1.5], device=dev())
+    a, b = base.clone().requires_grad_(True), base.clone().requires_grad_(True)
+    o1, d1, v1 = rendering._PoseRaysFn.apply(a, H, W, focal)
+    o2, d2 = rendering._get_rays_torch(H, W, focal, b)
+    o2, d2 = o2.reshape(-1, 3), d2.reshape(-1, 3)
+    v2 = d2 / torch.norm(d2, dim=-1, keepdim=True)
+    for x, y in ((o1, o2), (d1, d2), (v1, v2)):
+        assert float((x - y).abs().max()) <= 2e-6 * float(y.abs().max())
+    wo, wd, wv = torch.randn_like(o1), torch.randn_like(d1), torch.randn_like(v1)
+    ((o1 * wo).sum() + (d1 * wd).sum() + (v1 * wv).sum()).backward()
+    ((o2 * wo).sum() + (d2 * wd).sum() + (v2 * wv).sum()).backward()
+    assert a.grad.shape == b.grad.shape
+    assert float((a.grad - b.grad).abs().max()) <= 2e-5 * float(b.grad.abs().max()) + 1e-6
+    # only the view directions carry gradient
+    c = base.clone().requires_grad_(True)
+    _, _, v3 = rendering._PoseRaysFn.apply(c, H, W, focal)
+    e = base.clone().requires_grad_(True)
+    _, d4 = rendering._get_rays_torch(H, W, focal, e)
+    d4 = d4.reshape(-1, 3)
+    (v3 * wv).sum().backward()
+    ((d4 / torch.norm(d4, dim=-1, keepdim=True)) * wv).sum().backward()
+    assert float((c.grad - e.grad).abs().max()) <= 2e-5 * float(e.grad.abs().max()) + 1e-6
