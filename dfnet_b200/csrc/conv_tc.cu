@@ -447,7 +447,7 @@ struct PackArgs {
 };
 
 // weight image: [n tile][channel slice][weight stage][tap in stage][8 panels][nt rows][8 elements]; one thread = the 8
-// elements (input channels) of one row = one 16-byte store.  Batched: a training loop re-packs every convolution of the
+// elements (input channels) of one row for every tap = KH * KW 16-byte stores.  Batched: a training loop re-packs every convolution of the
 // pose regressor after each optimizer step (51 images), which as one launch per image cost ~1 ms of the 20 ms step.
 constexpr int kMaxPack = 64;
 struct PackBatchArgs {
@@ -463,7 +463,11 @@ __global__ void __launch_bounds__(256) k_pack_conv_weights(const __grid_constant
     if ((int)blockIdx.x >= b.blk0[mid]) lo = mid; else hi = mid;
   }
   const PackArgs& a = b.e[lo];
-  const int64_t i = (int64_t)((int)blockIdx.x - b.blk0[lo]) * blockDim.x + threadIdx.x;   // 8-element group
+  // one thread = the 8 input channels of one image row FOR EVERY TAP: its source is one contiguous run of 8 * KH * KW floats
+  // (forward) or eight runs of KH * KW floats next to its neighbours' (data gradient), and neighbouring threads store
+  // neighbouring 16-byte rows.  (With one thread per row and tap every 4-byte read of a warp hit its own 32-byte sector,
+  // 18 KB apart: 0.25 ms for the four images of the 13 encoder layers, L2-bound.)
+  const int64_t i = (int64_t)((int)blockIdx.x - b.blk0[lo]) * blockDim.x + threadIdx.x;
   if (i < a.Cout) {
     float bf = 0.f;
     if (!a.dgrad) {  // y = scale * (conv + bias) + shift
@@ -472,44 +476,55 @@ __global__ void __launch_bounds__(256) k_pack_conv_weights(const __grid_constant
     }
     a.bias[i] = bf;
   }
-  if (i * 8 >= a.total) return;
+  const int per_row = a.n_wst * a.tps;                 // rows of the image this thread writes (taps incl. stage padding)
+  if (i * 8 * per_row >= a.total) return;
   int64_t r = i;
   const int rows = a.nt / a.cg;
-  int rr = (int)(r % rows); r /= rows;
+  const int rr0 = (int)(r % rows); r /= rows;
   const int pp = (int)(r % 8); r /= 8;
-  const int tis = (int)(r % a.tps); r /= a.tps;
-  if (a.cg == 2) { rr += (int)(r % 2) * rows; r /= 2; }
-  const int ws = (int)(r % a.n_wst); r /= a.n_wst;
+  int half = 0;
+  if (a.cg == 2) { half = (int)(r % 2); r /= 2; }
   const int cc = (int)(r % a.n_cc); r /= a.n_cc;
   const int t = (int)r;
-  const int tp = ws * a.tps + tis;
-  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (tp < a.KH * a.KW) {
-    const int ky = tp / a.KW, kx = tp % a.KW;
-    const int ci0 = (cc * 8 + pp) * 8, n = t * a.nt + rr;
-    const int64_t kk = (int64_t)a.KH * a.KW;
-    if (!a.dgrad) {
-      const float scn = a.sc ? a.sc[n] : 1.f;
-      const float* src = a.w + ((int64_t)n * a.Cin0 + ci0) * kk + ky * a.KW + kx;
+  const int rr = rr0 + half * rows;
+  const int ci0 = (cc * 8 + pp) * 8, n = t * a.nt + rr;
+  const int64_t kk = (int64_t)a.KH * a.KW;
+  const float scn = (!a.dgrad && a.sc) ? a.sc[n] : 1.f;
+  float scd[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e)
-        if (ci0 + e < a.Cin0) v[e] = scn * src[e * kk];
-    } else if (n < a.Cin0) {
-      // data gradient: n = input channel of the layer, ci = its output channel, filter flipped
-      const float* src = a.w + ((int64_t)ci0 * a.Cin0 + n) * kk + (a.KH - 1 - ky) * a.KW + (a.KW - 1 - kx);
+  for (int e = 0; e < 8; ++e) scd[e] = (a.dgrad && a.sc && ci0 + e < a.Cout0) ? a.sc[ci0 + e] : 1.f;
+  for (int ws = 0; ws < a.n_wst; ++ws)
+    for (int tis = 0; tis < a.tps; ++tis) {
+      const int tp = ws * a.tps + tis;
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (tp < a.KH * a.KW) {
+        const int ky = tp / a.KW, kx = tp % a.KW;
+        if (!a.dgrad) {
+          const float* src = a.w + ((int64_t)n * a.Cin0 + ci0) * kk + ky * a.KW + kx;
 #pragma unroll
-      for (int e = 0; e < 8; ++e)
-        if (ci0 + e < a.Cout0) v[e] = (a.sc ? a.sc[ci0 + e] : 1.f) * src[(int64_t)e * a.Cin0 * kk];
+          for (int e = 0; e < 8; ++e)
+            if (ci0 + e < a.Cin0) v[e] = scn * src[e * kk];
+        } else if (n < a.Cin0) {
+          // data gradient: n = input channel of the layer, ci = its output channel, filter flipped
+          const float* src = a.w + ((int64_t)ci0 * a.Cin0 + n) * kk + (a.KH - 1 - ky) * a.KW + (a.KW - 1 - kx);
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (ci0 + e < a.Cout0) v[e] = scd[e] * src[(int64_t)e * a.Cin0 * kk];
+        }
+      }
+      uint32_t pk[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t lo16 = a.fmt ? __bfloat16_as_ushort(__float2bfloat16_rn(v[2 * q])) : __half_as_ushort(__float2half_rn(v[2 * q]));
+        const uint32_t hi16 = a.fmt ? __bfloat16_as_ushort(__float2bfloat16_rn(v[2 * q + 1])) : __half_as_ushort(__float2half_rn(v[2 * q + 1]));
+        pk[q] = lo16 | (hi16 << 16);
+      }
+      // image order: [n tile][channel slice][weight stage][row half (cta_group::2)][tap in stage][8 panels][rows][8]
+      int64_t o = ((int64_t)t * a.n_cc + cc) * a.n_wst + ws;
+      if (a.cg == 2) o = o * 2 + half;
+      o = ((o * a.tps + tis) * 8 + pp) * rows + rr0;
+      reinterpret_cast<uint4*>(a.img)[o] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
-  }
-  uint32_t pk[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const uint32_t lo16 = a.fmt ? __bfloat16_as_ushort(__float2bfloat16_rn(v[2 * q])) : __half_as_ushort(__float2half_rn(v[2 * q]));
-    const uint32_t hi16 = a.fmt ? __bfloat16_as_ushort(__float2bfloat16_rn(v[2 * q + 1])) : __half_as_ushort(__float2half_rn(v[2 * q + 1]));
-    pk[q] = lo16 | (hi16 << 16);
-  }
-  reinterpret_cast<uint4*>(a.img)[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
 }
 
 // Packing requests collected between pack_batch_begin() and pack_batch_flush() (dfb_dfnet_load_ex) go out as ONE launch
@@ -532,7 +547,7 @@ static int pack_push(const PackArgs& a, cudaStream_t st) {
     const int rc = pack_launch(st);
     if (rc) return rc;
   }
-  const int64_t groups = std::max<int64_t>(a.total / 8, a.Cout);
+  const int64_t groups = std::max<int64_t>(a.total / 8 / ((int64_t)a.n_wst * a.tps), a.Cout);   // one thread per (row, 8 channels)
   const int k = g_pack.args.n++;
   if (k == 0) g_pack.args.blk0[0] = 0;
   g_pack.args.e[k] = a;
@@ -552,11 +567,19 @@ int dfb_conv_update_impl(DfbConv* c, const float* weight, const float* bias, con
   // Device-resident sources (a training loop re-loads the parameters after every optimizer step) are packed in place;
   // only host tensors are staged.  (Staging everything through cudaMallocAsync cost ~60 pool allocations per step, and
   // the pool hands its memory back to the driver at synchronisation points: sporadic 30-500 ms stalls.)
+  // (the answer is remembered per pointer: a training loop asks about the same ~100 parameter tensors after every optimizer
+  // step, and cudaPointerGetAttributes is 1-2 us a call.  Only "device" answers are kept; CUDA's address range is never
+  // handed to pageable host allocations.)
   auto on_device = [](const void* p) {
     if (!p) return true;
+    static thread_local const void* known[256] = {};
+    const size_t slot = ((uintptr_t)p >> 8) * 0x9E3779B97F4A7C15ull >> 56;
+    if (known[slot] == p) return true;
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+    const bool dev = at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+    if (dev) known[slot] = p;
+    return dev;
   };
   float* stage = nullptr;
   const float *dw = weight, *db = bias, *dsc = bn_scale, *dsh = bn_shift;

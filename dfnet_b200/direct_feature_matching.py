@@ -162,6 +162,8 @@ def apply_gradients(model, optimizer):
             parallel.allreduce_gradients_(model.parameters())
     optimizer.step()
     optimizer.zero_grad()
+    # (measured and dropped: re-packing the updated weights here, behind the optimizer step, instead of in front of the next
+    # forward - the host is not ahead of the GPU at this point, the step got 0.2 ms slower)
 
 
 def train_on_batch(args, data, model, feat_model, pose, img_idx, hwf, optimizer, half_res, device, world_setup_dict,
