@@ -86,6 +86,11 @@ else:
 for i in range(6):
     step(i)
 torch.cuda.synchronize()
+if os.environ.get("NOPROF") == "1":     # plain run of the same steps, e.g. under ncu (which cannot share CUPTI with torch.profiler)
+    for i in range(steps):
+        step(i)
+    torch.cuda.synchronize()
+    raise SystemExit(0)
 marks = []
 with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CPU, torch.profiler.ProfilerActivity.CUDA]) as prof:
     for i in range(steps):
