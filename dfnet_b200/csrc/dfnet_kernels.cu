@@ -225,22 +225,30 @@ __global__ void k_cos_rows_partial(const float* __restrict__ fa, const float* __
 }
 
 // loss = 1 - mean_rows( ab / (max(|a|,eps) * max(|b|,eps)) )   (torch >= 1.12 clamps each norm)
-__global__ void k_cos_rows_final(const float* __restrict__ ws, int rows, int splits, float eps, float* __restrict__ loss) {
+// One warp per row: the lanes share the row's `splits` partial sums (with one thread per row and a serial loop over the
+// splits this single-block launch took 17 us of the 78 us loss).  blockDim = 1024.
+__global__ void __launch_bounds__(1024) k_cos_rows_final(const float* __restrict__ ws, int rows, int splits, float eps,
+                                                         float* __restrict__ loss) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   float acc = 0.f;
-  for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+  for (int r = warp; r < rows; r += nw) {
     float ab = 0.f, aa = 0.f, bb = 0.f;
-    for (int s = 0; s < splits; ++s) {
+    for (int s = lane; s < splits; s += 32) {
       const float* o = ws + ((int64_t)r * splits + s) * 3;
       ab += o[0], aa += o[1], bb += o[2];
     }
-    acc += ab / (fmaxf(sqrtf(aa), eps) * fmaxf(sqrtf(bb), eps));
+    for (int d = 16; d > 0; d >>= 1) {
+      ab += __shfl_xor_sync(0xffffffffu, ab, d);
+      aa += __shfl_xor_sync(0xffffffffu, aa, d);
+      bb += __shfl_xor_sync(0xffffffffu, bb, d);
+    }
+    acc += ab / (fmaxf(sqrtf(aa), eps) * fmaxf(sqrtf(bb), eps));   // identical in every lane
   }
   __shared__ float sm[32];
-  for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  if (lane == 0) sm[warp] = acc;
   __syncthreads();
   if (threadIdx.x < 32) {
-    acc = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.f;
+    acc = threadIdx.x < nw ? sm[threadIdx.x] : 0.f;
     for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
     if (threadIdx.x == 0) *loss = 1.f - acc / (float)rows;
   }
@@ -768,7 +776,7 @@ extern "C" int dfb_cosine_loss(const float* fr, const float* ft, int C, int64_t 
     DFB_REQUIRE(ws_bytes >= (size_t)C * splits * 3 * 4, DFB_ERR_WORKSPACE, "workspace too small");
     k_cos_rows_partial<<<dim3(splits, C), 256, 0, st>>>(fr, ft, HW, splits, (float*)ws);
     DFB_LAUNCH_CHECK();
-    k_cos_rows_final<<<1, 256, 0, st>>>((const float*)ws, C, splits, eps, loss);
+    k_cos_rows_final<<<1, 1024, 0, st>>>((const float*)ws, C, splits, eps, loss);
     DFB_LAUNCH_CHECK();
   } else {
     const int blocks = (int)((HW + 255) / 256);
@@ -1116,12 +1124,18 @@ __global__ void k_resize_bicubic_bwd(const float* __restrict__ gdst, float* __re
 extern "C" int dfb_cosine_loss_bwd(const float* fr, const float* ft, int C, int64_t HW, int per_channel, float eps,
                                    const float* g_loss, float* g_fr, void* ws, size_t ws_bytes, void* stream) {
   DFB_REQUIRE(fr && ft && g_loss && g_fr && ws && C >= 1 && HW >= 1, DFB_ERR_INVALID, "null or empty argument");
+  // per_channel bit 1: ws still holds the row statistics dfb_cosine_loss left there for the same fr / ft - the pass that
+  // recomputes them (a second read of both 157 MB stacks at 480x640) is skipped
+  const bool have_stats = (per_channel & 2) != 0;
+  per_channel &= 1;
   DFB_REQUIRE(!per_channel, DFB_ERR_UNSUPPORTED, "the backward covers the reference default per_channel=False");
   cudaStream_t st = (cudaStream_t)stream;
   const int splits = (int)std::min<int64_t>(64, std::max<int64_t>(1, HW / 4096));
   DFB_REQUIRE(ws_bytes >= (size_t)C * splits * 3 * 4, DFB_ERR_WORKSPACE, "workspace too small");
-  k_cos_rows_partial<<<dim3(splits, C), 256, 0, st>>>(fr, ft, HW, splits, (float*)ws);
-  DFB_LAUNCH_CHECK();
+  if (!have_stats) {
+    k_cos_rows_partial<<<dim3(splits, C), 256, 0, st>>>(fr, ft, HW, splits, (float*)ws);
+    DFB_LAUNCH_CHECK();
+  }
   const int bx = (int)std::min<int64_t>(64, std::max<int64_t>(1, HW / 2048));
   k_cos_rows_bwd<<<dim3(bx, C), 256, 0, st>>>(fr, ft, (const float*)ws, splits, HW, C, eps, g_loss, g_fr);
   DFB_LAUNCH_CHECK();

@@ -396,19 +396,19 @@ class _CosineLossFn(torch.autograd.Function):
         check(lib.dfb_cosine_loss(C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), Cc, HW, int(bool(per_channel)), 1e-6,
                                   C.c_void_p(loss.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel() * 4,
                                   raw_stream()))
-        ctx.save_for_backward(a, b)
+        # the workspace keeps the per-row statistics: the backward reads them instead of recomputing them
+        ctx.save_for_backward(a, b, ws)
         ctx.per_channel = bool(per_channel)
         return loss
 
     @staticmethod
     def backward(ctx, g):
-        a, b = ctx.saved_tensors
+        a, b, ws = ctx.saved_tensors
         Cc = a.shape[0]
         HW = a.numel() // Cc
         g = g.float().contiguous()
         ga = torch.empty_like(a)
-        ws = torch.empty(Cc * 64 * 3, device=a.device)
-        check(lib.dfb_cosine_loss_bwd(C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), Cc, HW, int(ctx.per_channel), 1e-6,
+        check(lib.dfb_cosine_loss_bwd(C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), Cc, HW, int(ctx.per_channel) | 2, 1e-6,
                                       C.c_void_p(g.data_ptr()), C.c_void_p(ga.data_ptr()), C.c_void_p(ws.data_ptr()),
                                       ws.numel() * 4, raw_stream()))
         return ga, None, None  # the target stream is a constant of the step (its inputs carry no gradient)

@@ -360,7 +360,8 @@ int dfb_dfnet_bwd(DfbDfnet* d, int B, int H, int W, uint32_t flags, int upH, int
 int dfb_dfnet_bwd_bucket_event(DfbDfnet* d, int first_layer, void* event);
 
 /* Backward of dfb_cosine_loss w.r.t. fr (g_loss: device scalar), of dfb_mse w.r.t. a, and the adjoints of the two
- * resampling operators (outputs overwritten). */
+ * resampling operators (outputs overwritten).  dfb_cosine_loss_bwd: per_channel bit 1 (value 2) = `ws` is the workspace
+ * dfb_cosine_loss was called with for the same fr / ft and still holds its row statistics (they are not recomputed). */
 int dfb_cosine_loss_bwd(const float* fr, const float* ft, int C, int64_t HW, int per_channel, float eps, const float* g_loss,
                         float* g_fr, void* ws, size_t ws_bytes, void* stream);
 int dfb_mse_bwd(const float* a, const float* b, int64_t n, const float* g_loss, float* g_a, void* stream);

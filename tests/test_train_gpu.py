@@ -110,6 +110,16 @@ def test_loss_and_resample_backward_vs_torch():
     fr2 = fr.detach().clone().requires_grad_(True)
     (1 - torch.nn.CosineSimilarity(dim=1, eps=1e-6)(fr2, ft).mean()).backward()
     assert float((fr.grad - fr2.grad).abs().max()) < 1e-4 * float(fr2.grad.abs().max())
+    # the ABI's two ways of getting the row statistics: recomputed (flag 0) and left in the workspace by the forward (flag 2,
+    # what the autograd function above uses) give the same gradient
+    from dfnet_b200._lib import check, lib
+    a_, b_ = fr.detach().contiguous(), ft.contiguous()
+    g1, g2, one = torch.empty_like(a_), torch.empty_like(a_), torch.ones((), device=dev())
+    ws1, ws2, loss = torch.empty(128 * 64 * 3, device=dev()), torch.empty(128 * 64 * 3, device=dev()), torch.empty((), device=dev())
+    check(lib.dfb_cosine_loss_bwd(a_.data_ptr(), b_.data_ptr(), 128, 4800, 0, 1e-6, one.data_ptr(), g1.data_ptr(), ws1.data_ptr(), ws1.numel() * 4, None))
+    check(lib.dfb_cosine_loss(a_.data_ptr(), b_.data_ptr(), 128, 4800, 0, 1e-6, loss.data_ptr(), ws2.data_ptr(), ws2.numel() * 4, None))
+    check(lib.dfb_cosine_loss_bwd(a_.data_ptr(), b_.data_ptr(), 128, 4800, 2, 1e-6, one.data_ptr(), g2.data_ptr(), ws2.data_ptr(), ws2.numel() * 4, None))
+    assert torch.equal(g1, g2) and torch.equal(g1, fr.grad)
     # MSE
     a = torch.rand(1, 3, 48, 64, device=dev(), requires_grad=True)
     b = torch.rand(1, 3, 48, 64, device=dev())
