@@ -24,7 +24,7 @@ SYMBOLS = [
     "dfb_conv_create_ex", "dfb_conv_fwd_ex", "dfb_conv_fwd_ex2", "dfb_conv_wgrad", "dfb_conv_wgrad_acc", "dfb_dfnet_load_ex", "dfb_dfnet_bn_batch_stats", "dfb_dfnet_tape_bytes", "dfb_debug_dfnet_tape_layout",
     "dfb_dfnet_bwd_workspace_bytes", "dfb_dfnet_bwd", "dfb_cosine_loss_bwd", "dfb_mse_bwd", "dfb_resize_bicubic_bwd",
     "dfb_resize_bilinear_ac_bwd", "dfb_dfnet_bwd_bucket_event", "dfb_luma_hist", "dfb_resize_area", "dfb_pose_error", "dfb_polar3x3_fwd", "dfb_polar3x3_bwd", "dfb_debug_conv_prof",
-    "dfb_conv_update", "dfb_conv_pack_begin", "dfb_conv_pack_end", "dfb_embed_xyz16", "dfb_embed_xyz16_ex", "dfb_rows_expand16", "dfb_rows_reduce_bf16", "dfb_nerf_heads_fwd", "dfb_nerf_heads_bwd",
+    "dfb_conv_update", "dfb_conv_update_many", "dfb_conv_pack_begin", "dfb_conv_pack_end", "dfb_embed_xyz16", "dfb_embed_xyz16_ex", "dfb_rows_expand16", "dfb_rows_reduce_bf16", "dfb_nerf_heads_fwd", "dfb_nerf_heads_bwd",
     "dfb_raw2outputs_bwd", "dfb_cast_f16_bf16", "dfb_render_poses_fwd", "dfb_copy2d_batch", "dfb_nerfw_loss_workspace_bytes", "dfb_nerfw_loss_fwd", "dfb_nerfw_loss_bwd",
     "dfb_pose_rays_fwd", "dfb_pose_rays_workspace_bytes", "dfb_pose_rays_bwd",
 ]
@@ -120,6 +120,7 @@ def _load():
                                   vp, C.c_size_t, vp]
     lib.dfb_dfnet_bwd_bucket_event.argtypes = [vp, i32, vp]
     lib.dfb_conv_update.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.dfb_conv_update_many.argtypes = [vp, vp, vp, i32, vp]
     lib.dfb_embed_xyz16.argtypes = [vp, i32, vp, i64, i32, i32, i32, vp, vp]
     lib.dfb_embed_xyz16_ex.argtypes = [vp, i32, vp, i64, i32, i32, i32, vp, vp, vp]
     lib.dfb_rows_expand16.argtypes = [vp, i64, i32, i32, vp, vp]

@@ -707,6 +707,17 @@ extern "C" int dfb_conv_update(DfbConv* c, const float* weight, const float* bia
   return dfb_conv_update_impl(c, weight, bias, bn_scale, bn_shift, stream);
 }
 
+// n handles in one call, bracketed as one packing launch (bias[i] nullable; no BatchNorm folding): the per-call cost of the
+// foreign-function interface is what a training loop with ~60 small layers pays after every optimizer step.
+extern "C" int dfb_conv_update_many(DfbConv* const* convs, const float* const* weights, const float* const* biases, int n, void* stream) {
+  DFB_REQUIRE(n >= 0 && (n == 0 || (convs && weights && biases)), DFB_ERR_INVALID, "dfb_conv_update_many: bad arguments");
+  int rc = dfb_conv_pack_begin();
+  if (rc) return rc;
+  for (int i = 0; i < n && !rc; ++i) rc = dfb_conv_update_impl(convs[i], weights[i], biases[i], nullptr, nullptr, stream);
+  const int rc2 = dfb_conv_pack_end(stream);
+  return rc ? rc : rc2;
+}
+
 extern "C" void dfb_conv_destroy(DfbConv* c) {
   if (!c) return;
   if (c->wimg) cudaFree(c->wimg);

@@ -128,6 +128,7 @@ class NetTrainer:
             self.L["th"] = _Layer(H2, 5, dev)                        # transient rgb(3), sigma, beta
         self._versions = None
         self._copy_tbl = None  # (parameter pointers, DfbCopy2d table of the parameter -> staging copies)
+        self._update_tbl = None
         self._bufs = {}
         self._live = False     # a tape of this executor is waiting for its backward
 
@@ -149,12 +150,16 @@ class NetTrainer:
             self._stage_layers(n, items)
             self._copy_tbl = (ptrs, _copy_table(items))
         _copy_batch(self._copy_tbl[1])
-        check(lib.dfb_conv_pack_begin())
-        try:
+        if self._update_tbl is None:      # handles and staging tensors never move: (forward, data-gradient) x layers, built once
+            hs, ws, bs = [], [], []
             for layer in self.L.values():
-                layer.update()
-        finally:
-            check(lib.dfb_conv_pack_end(_st()))
+                hs.append(layer.fwd.value), ws.append(layer.w.data_ptr()), bs.append(layer.b.data_ptr())
+                if layer.dg is not None:
+                    hs.append(layer.dg.value), ws.append(layer.w.data_ptr()), bs.append(None)
+            arr = C.c_void_p * len(hs)
+            self._update_tbl = (arr(*hs), arr(*ws), arr(*bs), len(hs))
+        t = self._update_tbl
+        check(lib.dfb_conv_update_many(t[0], t[1], t[2], t[3], _st()))
         self._versions = v
 
     def _stage_layers(self, n, items):

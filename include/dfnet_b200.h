@@ -388,6 +388,8 @@ int dfb_conv_update(DfbConv* conv, const float* weight, const float* bias, const
  * tensors is queued and all of them go out as ONE packing launch on `stream` (the sources must stay unchanged until then). */
 int dfb_conv_pack_begin(void);
 int dfb_conv_pack_end(void* stream);
+/* dfb_conv_pack_begin, dfb_conv_update(convs[i], weights[i], biases[i], NULL, NULL) for i < n, dfb_conv_pack_end in one call. */
+int dfb_conv_update_many(DfbConv* const* convs, const float* const* weights, const float* const* biases, int n, void* stream);
 /* pts = o + d*z, positional encoding with L bands (nerfw.py:105-133) -> fp16 [N*S, ld], columns >= 3+6L zero.
  * rays: [N, ray_stride] with o at 0..2 and d at 3..5. */
 int dfb_embed_xyz16(const float* rays, int ray_stride, const float* z, int64_t N, int S, int L, int ld, void* out, void* stream);
