@@ -114,9 +114,12 @@ __device__ void polar_orthogonal(const double R[9], double Q[9], double* Vout = 
       for (int k = 0; k < 3; ++k) s += R[k * 3 + i] * R[k * 3 + j];
       A[i * 3 + j] = s;
     }
+  // cyclic Jacobi converges quadratically: 5-6 sweeps reach 1e-32 of the trace, far below double precision (running the
+  // full 30 sweeps - dependent double sqrt / div chains on one thread - made this a 40 us kernel on the step's critical path)
+  const double tiny = 1e-32 * (fabs(A[0]) + fabs(A[4]) + fabs(A[8]));
   for (int sweep = 0; sweep < 30; ++sweep) {
     const double off = fabs(A[1]) + fabs(A[2]) + fabs(A[5]);
-    if (off < 1e-300) break;
+    if (off <= tiny) break;
     for (int p = 0; p < 2; ++p)
       for (int q = p + 1; q < 3; ++q) {
         const double apq = A[p * 3 + q];
