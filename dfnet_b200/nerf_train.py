@@ -446,6 +446,9 @@ def _embed(x, L):
     return torch.cat([x, sc.reshape(*x.shape[:-1], -1)], -1)
 
 
+_T_VALS = {}
+
+
 def render_rays_train(ray_batch, network_fn, network_fine, embedding_a, embedding_t, N_samples, N_importance, perturb=0.,
                       raw_noise_std=0., lindisp=False, retraw=False, pytest=False):
     """render_rays (rendering.py:245-337) with test_time=False, differentiable w.r.t. the networks and embeddings."""
@@ -453,7 +456,9 @@ def render_rays_train(ray_batch, network_fn, network_fine, embedding_a, embeddin
     N = ray_batch.shape[0]
     rays = ray_batch.detach().float().contiguous()
     near, far, viewdirs, hist = rays[:, 6:7], rays[:, 7:8], rays[:, 8:11], rays[:, 11:]
-    t_vals = ops.linspace(0., 1., N_samples).to(dev)
+    t_vals = _T_VALS.get((N_samples, dev))           # constant of the run: one upload instead of a pageable copy per step
+    if t_vals is None:
+        t_vals = _T_VALS[(N_samples, dev)] = ops.linspace(0., 1., N_samples).to(dev)
     z = near * (1. - t_vals) + far * t_vals if not lindisp else 1. / (1. / near * (1. - t_vals) + 1. / far * t_vals)
     z = z.expand(N, N_samples)
     if perturb > 0.:
