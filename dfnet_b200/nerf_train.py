@@ -15,7 +15,7 @@ import ctypes as C
 
 import torch
 
-from . import _lib, ops
+from . import ops
 from ._lib import Copy2d, check, lib, raw_stream
 
 
